@@ -1,0 +1,339 @@
+"""TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
+
+ctypes binding of the CPU oracle (oracle/plonky2_oracle.c), a plain-C restatement of the
+reference's commit path.  Imported only by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs -- never by qp-plonky2_b200/.
+
+Parity status: Poseidon permutation pinned by the reference's KATs; layers above it are
+"parity unpinned" by golden data (the reference holds none and cannot be compiled here) and are
+pinned structurally and against oracle/pyref.py.  See plonky2_oracle.h.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libplonky2_oracle.so")
+
+P = 0xFFFFFFFF00000001
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (gcc only)."""
+    src = [os.path.join(_HERE, f) for f in ("plonky2_oracle.c", "plonky2_oracle.h", "poseidon_constants.h")]
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src
+    )
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+_lib = None
+
+u64p = C.POINTER(C.c_uint64)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(u64p)
+
+
+class Challenger(C.Structure):
+    """core/src/challenger.rs state, laid out as orc_challenger."""
+
+    _fields_ = [
+        ("sponge_state", C.c_uint64 * 12),
+        ("input_buffer", C.c_uint64 * 8),
+        ("output_buffer", C.c_uint64 * 8),
+        ("n_in", C.c_uint32),
+        ("n_out", C.c_uint32),
+    ]
+
+    def __init__(self):
+        super().__init__()
+        lib().orc_challenger_init(C.byref(self))
+
+    def observe(self, elems):
+        a = np.ascontiguousarray(np.asarray(elems, dtype=np.uint64).reshape(-1))
+        lib().orc_challenger_observe(C.byref(self), _ptr(a), a.size)
+
+    def get_challenge(self) -> int:
+        return int(lib().orc_challenger_get(C.byref(self)))
+
+    def get_extension_challenge(self):
+        return (self.get_challenge(), self.get_challenge())
+
+    def clone(self):
+        c = Challenger.__new__(Challenger)
+        C.memmove(C.byref(c), C.byref(self), C.sizeof(Challenger))
+        return c
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(_LIB_PATH)
+    u64, u32, sz, dbl = C.c_uint64, C.c_uint, C.c_size_t, C.c_double
+    sig = {
+        "orc_gl_add": (u64, [u64, u64]),
+        "orc_gl_sub": (u64, [u64, u64]),
+        "orc_gl_mul": (u64, [u64, u64]),
+        "orc_gl_canon": (u64, [u64]),
+        "orc_gl_pow": (u64, [u64, u64]),
+        "orc_gl_inv": (u64, [u64]),
+        "orc_gl_inverse_2exp": (u64, [u32]),
+        "orc_gl_primitive_root": (u64, [u32]),
+        "orc_gl_coset_shift": (u64, []),
+        "orc_ext_mul": (None, [u64p, u64p, u64p]),
+        "orc_reverse_index_bits": (None, [u64p, sz, sz]),
+        "orc_fft": (None, [u64p, u32, u32]),
+        "orc_ifft": (None, [u64p, u32]),
+        "orc_coset_fft": (None, [u64p, u32, u64, u32]),
+        "orc_fft_naive": (None, [u64p, u64p, u32, u64]),
+        "orc_poseidon": (None, [u64p]),
+        "orc_poseidon_naive": (None, [u64p]),
+        "orc_hash_no_pad": (None, [u64p, sz, u64p]),
+        "orc_hash_leaf": (None, [u64p, sz, u64p]),
+        "orc_two_to_one": (None, [u64p, u64p, u64p]),
+        "orc_merkle_tree_new": (C.c_int, [u64p, sz, sz, u32, u64p, u64p]),
+        "orc_merkle_prove": (None, [sz, sz, u32, u64p, u64p]),
+        "orc_merkle_verify": (C.c_int, [u64p, sz, sz, u64p, u32, u64p, u32]),
+        "orc_batch_from_values": (C.c_int, [u64p, sz, u32, u32, u32, u64p, u64p, u64p, u64p, u64p, C.POINTER(dbl)]),
+        "orc_batch_from_coeffs": (C.c_int, [u64p, sz, u32, u32, u32, u64p, u64p, u64p, u64p, C.POINTER(dbl)]),
+        "orc_challenger_init": (None, [C.POINTER(Challenger)]),
+        "orc_challenger_observe": (None, [C.POINTER(Challenger), u64p, sz]),
+        "orc_challenger_get": (u64, [C.POINTER(Challenger)]),
+        "orc_fri_reduction_arity_bits": (u32, [u32, u32, u32, u32, u32, C.POINTER(u32)]),
+        "orc_fri_committed_trees": (
+            C.c_int,
+            [u64p, u64p, u32, u32, u32, C.POINTER(u32), u32, C.POINTER(Challenger), u64p,
+             C.POINTER(u64p), C.POINTER(u64p), u64p, u64p],
+        ),
+        "orc_fri_proof_of_work": (u64, [C.POINTER(Challenger), u32]),
+        "orc_num_threads": (C.c_int, []),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+# ---------------------------------------------------------------------------------------------
+# numpy-level helpers
+# ---------------------------------------------------------------------------------------------
+
+def rand_felts(shape, seed):
+    """Uniform canonical Goldilocks elements (rejection of values >= p is a 2^-32 event; we
+    reduce instead, which is equally uniform for test purposes)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = rng.integers(0, 2**64, size=shape, dtype=np.uint64)
+    return np.where(a >= np.uint64(P), a - np.uint64(P), a).astype(np.uint64)
+
+
+def poseidon(state):
+    s = np.array(state, dtype=np.uint64).copy()
+    lib().orc_poseidon(_ptr(s))
+    return canon(s)
+
+
+def poseidon_naive(state):
+    s = np.array(state, dtype=np.uint64).copy()
+    lib().orc_poseidon_naive(_ptr(s))
+    return canon(s)
+
+
+def canon(a):
+    a = np.asarray(a, dtype=np.uint64)
+    return np.where(a >= np.uint64(P), a - np.uint64(P), a).astype(np.uint64)
+
+
+def hash_leaf(x):
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.uint64))
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_hash_leaf(_ptr(a) if a.size else None, a.size, _ptr(out))
+    return canon(out)
+
+
+def hash_no_pad(x):
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.uint64))
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_hash_no_pad(_ptr(a) if a.size else None, a.size, _ptr(out))
+    return canon(out)
+
+
+def two_to_one(l, r):
+    l = np.ascontiguousarray(np.asarray(l, dtype=np.uint64))
+    r = np.ascontiguousarray(np.asarray(r, dtype=np.uint64))
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_two_to_one(_ptr(l), _ptr(r), _ptr(out))
+    return canon(out)
+
+
+def fft(v, zero_factor=0):
+    a = np.array(v, dtype=np.uint64).copy()
+    lib().orc_fft(_ptr(a), int(a.size).bit_length() - 1, zero_factor)
+    return canon(a)
+
+
+def ifft(v):
+    a = np.array(v, dtype=np.uint64).copy()
+    lib().orc_ifft(_ptr(a), int(a.size).bit_length() - 1)
+    return canon(a)
+
+
+def coset_fft(v, shift, zero_factor=0):
+    a = np.array(v, dtype=np.uint64).copy()
+    lib().orc_coset_fft(_ptr(a), int(a.size).bit_length() - 1, shift, zero_factor)
+    return canon(a)
+
+
+def fft_naive(v, shift=1):
+    a = np.ascontiguousarray(np.asarray(v, dtype=np.uint64))
+    out = np.zeros_like(a)
+    lib().orc_fft_naive(_ptr(a), _ptr(out), int(a.size).bit_length() - 1, shift)
+    return canon(out)
+
+
+def reverse_index_bits(v):
+    a = np.array(v, dtype=np.uint64).copy()
+    n = a.shape[0]
+    w = a.size // n
+    lib().orc_reverse_index_bits(_ptr(a), n, w)
+    return a
+
+
+class MerkleTree:
+    """plonky2/src/hash/merkle_tree.rs: leaves [N][L], digests (reference layout), cap."""
+
+    def __init__(self, leaves, cap_height):
+        leaves = np.ascontiguousarray(np.asarray(leaves, dtype=np.uint64))
+        n, L = leaves.shape
+        if n == 0 or n & (n - 1) or cap_height > n.bit_length() - 1:
+            raise ValueError("cap_height should be at most log2(leaves.len())")
+        self.leaves = leaves
+        self.cap_height = cap_height
+        self.digests = np.zeros((2 * (n - (1 << cap_height)), 4), dtype=np.uint64)
+        self.cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
+        rc = lib().orc_merkle_tree_new(_ptr(leaves), n, L, cap_height, _ptr(self.digests), _ptr(self.cap))
+        if rc:
+            raise ValueError("merkle_tree_new failed")
+
+    def prove(self, i):
+        n = self.leaves.shape[0]
+        k = n.bit_length() - 1 - self.cap_height
+        sib = np.zeros((k, 4), dtype=np.uint64)
+        lib().orc_merkle_prove(i, n, self.cap_height, _ptr(self.digests), _ptr(sib))
+        return sib
+
+
+def merkle_verify(leaf, index, cap, siblings):
+    leaf = np.ascontiguousarray(np.asarray(leaf, dtype=np.uint64))
+    cap = np.ascontiguousarray(np.asarray(cap, dtype=np.uint64))
+    sib = np.ascontiguousarray(np.asarray(siblings, dtype=np.uint64)).reshape(-1, 4)
+    ch = int(cap.shape[0]).bit_length() - 1
+    return bool(lib().orc_merkle_verify(_ptr(leaf), leaf.size, index, _ptr(cap), ch,
+                                        _ptr(sib) if sib.size else None, sib.shape[0]))
+
+
+class PolynomialBatch:
+    """plonky2/src/fri/oracle.rs:33-40 -- polynomials (coeffs), merkle tree, scope timings."""
+
+    SCOPES = ("IFFT", "FFT + blinding", "transpose LDEs", "build Merkle tree")
+
+    @classmethod
+    def from_values(cls, values, rate_bits, cap_height, salt=None):
+        return cls._make(values, rate_bits, cap_height, salt, True)
+
+    @classmethod
+    def from_coeffs(cls, coeffs, rate_bits, cap_height, salt=None):
+        return cls._make(coeffs, rate_bits, cap_height, salt, False)
+
+    @classmethod
+    def _make(cls, data, rate_bits, cap_height, salt, is_values):
+        data = np.ascontiguousarray(np.asarray(data, dtype=np.uint64))
+        ncols, n = data.shape
+        lg_n = n.bit_length() - 1
+        assert 1 << lg_n == n
+        N = n << rate_bits
+        L = ncols + (4 if salt is not None else 0)
+        if cap_height > lg_n + rate_bits:
+            raise ValueError("cap_height should be at most log2(leaves.len())")
+        if salt is not None:
+            salt = np.ascontiguousarray(np.asarray(salt, dtype=np.uint64))
+            assert salt.shape == (4, N)
+        self = cls()
+        self.degree_log, self.rate_bits, self.blinding = lg_n, rate_bits, salt is not None
+        self.leaves = np.zeros((N, L), dtype=np.uint64)
+        self.digests = np.zeros((2 * (N - (1 << cap_height)), 4), dtype=np.uint64)
+        self.cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
+        ms = (C.c_double * 4)()
+        if is_values:
+            self.polynomials = np.zeros_like(data)
+            rc = lib().orc_batch_from_values(_ptr(data), ncols, lg_n, rate_bits, cap_height, _ptr(salt),
+                                             _ptr(self.polynomials), _ptr(self.leaves),
+                                             _ptr(self.digests), _ptr(self.cap), ms)
+        else:
+            self.polynomials = canon(data)
+            rc = lib().orc_batch_from_coeffs(_ptr(data), ncols, lg_n, rate_bits, cap_height, _ptr(salt),
+                                             _ptr(self.leaves), _ptr(self.digests), _ptr(self.cap), ms)
+        if rc:
+            raise ValueError("orc_batch failed rc=%d" % rc)
+        self.scope_ms = dict(zip(cls.SCOPES, list(ms)))
+        return self
+
+    def get_lde_values(self, index, step=1):
+        """oracle.rs:286-291"""
+        bits = self.degree_log + self.rate_bits
+        i = int(format(index * step, "0%db" % bits)[::-1], 2)
+        row = self.leaves[i]
+        return row[: len(row) - (4 if self.blinding else 0)]
+
+
+def fri_reduction_arity_bits(degree_bits, rate_bits, cap_height, arity_bits=4, final_poly_bits=5):
+    out = (C.c_uint * 64)()
+    k = lib().orc_fri_reduction_arity_bits(degree_bits, rate_bits, cap_height, arity_bits, final_poly_bits, out)
+    return [int(out[i]) for i in range(k)]
+
+
+def fri_committed_trees(coeffs, values, rate_bits, cap_height, arity_bits, challenger, keep_trees=False):
+    """plonky2/src/fri/prover.rs:85-143.  coeffs/values: [n][2] ext elements.
+    Returns dict(caps, betas, final_poly, leaves?, digests?)."""
+    co = np.array(coeffs, dtype=np.uint64).copy()
+    va = np.array(values, dtype=np.uint64).copy()
+    n = co.shape[0]
+    lg_n = n.bit_length() - 1
+    R = len(arity_bits)
+    ncap = 1 << cap_height
+    caps = np.zeros((R, ncap, 4), dtype=np.uint64)
+    betas = np.zeros((R, 2), dtype=np.uint64)
+    tot = sum(arity_bits)
+    final = np.zeros(((n >> tot) >> rate_bits, 2), dtype=np.uint64)
+    ab = (C.c_uint * max(R, 1))(*arity_bits)
+    leaves, digests = [], []
+    lp = dp = None
+    if keep_trees:
+        m = n
+        for a in arity_bits:
+            leaves.append(np.zeros((m >> a, 2 << a), dtype=np.uint64))
+            digests.append(np.zeros((2 * ((m >> a) - ncap), 4), dtype=np.uint64))
+            m >>= a
+        lp = (u64p * R)(*[_ptr(x) for x in leaves])
+        dp = (u64p * R)(*[_ptr(x) if x.size else None for x in digests])
+    rc = lib().orc_fri_committed_trees(_ptr(co), _ptr(va), lg_n, rate_bits, cap_height, ab, R,
+                                       C.byref(challenger), _ptr(caps), lp, dp, _ptr(betas), _ptr(final))
+    if rc:
+        raise ValueError("fri_committed_trees rc=%d" % rc)
+    return dict(caps=caps, betas=betas, final_poly=final, leaves=leaves, digests=digests)
+
+
+def fri_proof_of_work(challenger, pow_bits):
+    return int(lib().orc_fri_proof_of_work(C.byref(challenger), pow_bits))

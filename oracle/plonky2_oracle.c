@@ -1,0 +1,706 @@
+/* TEST INFRASTRUCTURE -- NOT PRODUCT CODE.  See plonky2_oracle.h for the status header.
+ *
+ * Plain C11 (+ OpenMP where the reference uses rayon) restatement of the reference's CPU
+ * commit path.  Citations are reference-relative file:line.
+ */
+#include "plonky2_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "poseidon_constants.h"
+
+typedef unsigned __int128 u128;
+#define EPS 0xFFFFFFFFULL
+
+static double now_ms(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Goldilocks field, p = 2^64 - 2^32 + 1.  Values are raw u64, possibly >= p; compare canonical.
+ * field/src/goldilocks_field.rs
+ * ---------------------------------------------------------------------------------------- */
+
+/* goldilocks_field.rs:221-228 */
+uint64_t orc_gl_canon(uint64_t a) { return a >= ORC_P ? a - ORC_P : a; }
+
+/* goldilocks_field.rs:249-265 */
+uint64_t orc_gl_add(uint64_t a, uint64_t b) {
+    uint64_t s = a + b;
+    int over = s < a;
+    uint64_t s2 = s + (over ? EPS : 0);
+    if (s2 < s) s2 += EPS; /* double overflow */
+    return s2;
+}
+
+/* goldilocks_field.rs:280-294 */
+uint64_t orc_gl_sub(uint64_t a, uint64_t b) {
+    uint64_t d = a - b;
+    int under = a < b;
+    uint64_t d2 = d - (under ? EPS : 0);
+    if (d2 > d) d2 -= EPS; /* double underflow */
+    return d2;
+}
+
+/* goldilocks_field.rs:390-403 (reduce128) */
+static inline uint64_t reduce128(u128 x) {
+    uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
+    uint64_t hi_hi = hi >> 32, hi_lo = hi & EPS;
+    uint64_t t0 = lo - hi_hi;
+    if (lo < hi_hi) t0 -= EPS;
+    uint64_t t1 = hi_lo * EPS;
+    uint64_t t2 = t0 + t1;
+    if (t2 < t0) t2 += EPS;
+    return t2;
+}
+
+/* goldilocks_field.rs:381-385 (reduce96) */
+static inline uint64_t reduce96(uint64_t lo, uint32_t hi) {
+    uint64_t t1 = (uint64_t)hi * EPS;
+    uint64_t t2 = lo + t1;
+    if (t2 < lo) t2 += EPS;
+    return t2;
+}
+
+/* goldilocks_field.rs:303-310 */
+uint64_t orc_gl_mul(uint64_t a, uint64_t b) { return reduce128((u128)a * b); }
+
+static inline uint64_t gl_mul(uint64_t a, uint64_t b) { return reduce128((u128)a * b); }
+static inline uint64_t gl_add(uint64_t a, uint64_t b) { return orc_gl_add(a, b); }
+static inline uint64_t gl_sub(uint64_t a, uint64_t b) { return orc_gl_sub(a, b); }
+
+uint64_t orc_gl_pow(uint64_t a, uint64_t e) {
+    uint64_t r = 1, b = a;
+    while (e) {
+        if (e & 1) r = gl_mul(r, b);
+        b = gl_mul(b, b);
+        e >>= 1;
+    }
+    return r;
+}
+
+/* Fermat inverse a^(p-2) (goldilocks_field.rs:112-151 computes the same power with an
+ * addition chain). */
+uint64_t orc_gl_inv(uint64_t a) { return orc_gl_pow(a, ORC_P - 2); }
+
+/* field/src/types.rs:239-278; exp <= 32 here */
+uint64_t orc_gl_inverse_2exp(unsigned k) { return ORC_P - ((ORC_P - 1) >> k); }
+
+/* field/src/types.rs:280-284, goldilocks_field.rs:91 */
+uint64_t orc_gl_primitive_root(unsigned k) {
+    uint64_t b = 7277203076849721926ULL;
+    for (unsigned i = k; i < 32; i++) b = gl_mul(b, b);
+    return b;
+}
+
+/* field/src/types.rs:453-455, goldilocks_field.rs:84 */
+uint64_t orc_gl_coset_shift(void) { return 14293326489335486720ULL; }
+
+/* field/src/extension/quadratic.rs:186-199, goldilocks_extensions.rs:13-26 (W = 7) */
+void orc_ext_mul(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]) {
+    uint64_t c0 = gl_add(gl_mul(a[0], b[0]), gl_mul(7, gl_mul(a[1], b[1])));
+    uint64_t c1 = gl_add(gl_mul(a[0], b[1]), gl_mul(a[1], b[0]));
+    out[0] = c0;
+    out[1] = c1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Bit reversal: result[i] = arr[bitrev(i)]   (util/src/lib.rs:49-97, 181-230)
+ * elem_words = u64 words per element (1 for base field, 2 for F_p^2, ...).
+ * ---------------------------------------------------------------------------------------- */
+static inline size_t bitrev(size_t x, unsigned bits) {
+    size_t r = 0;
+    for (unsigned i = 0; i < bits; i++) {
+        r = (r << 1) | (x & 1);
+        x >>= 1;
+    }
+    return r;
+}
+
+static unsigned log2_strict(size_t n) {
+    unsigned k = 0;
+    while (((size_t)1 << k) < n) k++;
+    return k;
+}
+
+void orc_reverse_index_bits(uint64_t *arr, size_t n, size_t w) {
+    unsigned bits = log2_strict(n);
+    uint64_t tmp[16];
+    for (size_t i = 0; i < n; i++) {
+        size_t j = bitrev(i, bits);
+        if (i < j) {
+            memcpy(tmp, arr + i * w, w * 8);
+            memcpy(arr + i * w, arr + j * w, w * 8);
+            memcpy(arr + j * w, tmp, w * 8);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * FFT (field/src/fft.rs)
+ * ---------------------------------------------------------------------------------------- */
+
+/* fft.rs:14-33.  Row j (= lg_half_m) holds omega_{2^(j+1)}^i for i < 2^j; omega_m does not
+ * depend on n, so one table built for the largest size serves all.  Row j lives at
+ * table[2^j .. 2^(j+1)). */
+static uint64_t *g_roots = NULL;
+static unsigned g_roots_lg = 0;
+
+static const uint64_t *root_table(unsigned lg_n) {
+    const uint64_t *ret;
+#pragma omp critical(orc_roots)
+    {
+        if (g_roots_lg < lg_n || !g_roots) {
+            free(g_roots);
+            size_t n = (size_t)1 << lg_n;
+            g_roots = (uint64_t *)malloc((n < 2 ? 2 : n) * 8);
+            g_roots[0] = 1;
+            for (unsigned j = 0; j < lg_n; j++) {
+                uint64_t w = orc_gl_primitive_root(j + 1), cur = 1;
+                size_t half = (size_t)1 << j;
+                for (size_t i = 0; i < half; i++) {
+                    g_roots[half + i] = cur;
+                    cur = gl_mul(cur, w);
+                }
+            }
+            g_roots_lg = lg_n;
+        }
+        ret = g_roots;
+    }
+    return ret;
+}
+
+/* fft.rs:165-202 (fft_classic) with the scalar loop of fft.rs:138-156 */
+static void fft_classic(uint64_t *v, unsigned lg_n, unsigned r, const uint64_t *roots) {
+    size_t n = (size_t)1 << lg_n;
+    orc_reverse_index_bits(v, n, 1);
+    if (r > 0) {
+        size_t mask = ~(((size_t)1 << r) - 1);
+        for (size_t i = 0; i < n; i++) v[i] = v[i & mask];
+    }
+    for (unsigned lg_half_m = r; lg_half_m < lg_n; lg_half_m++) {
+        size_t half_m = (size_t)1 << lg_half_m, m = half_m * 2;
+        const uint64_t *row = roots + half_m;
+        for (size_t k = 0; k < n; k += m) {
+            for (size_t j = 0; j < half_m; j++) {
+                uint64_t t = gl_mul(row[j], v[k + half_m + j]);
+                uint64_t u = v[k + j];
+                v[k + j] = gl_add(u, t);
+                v[k + half_m + j] = gl_sub(u, t);
+            }
+        }
+    }
+}
+
+/* fft.rs:53-61 */
+void orc_fft(uint64_t *v, unsigned lg_n, unsigned zero_factor) {
+    fft_classic(v, lg_n, zero_factor, root_table(lg_n));
+}
+
+/* fft.rs:68-91 */
+void orc_ifft(uint64_t *v, unsigned lg_n) {
+    size_t n = (size_t)1 << lg_n;
+    uint64_t n_inv = orc_gl_inverse_2exp(lg_n);
+    fft_classic(v, lg_n, 0, root_table(lg_n));
+    v[0] = gl_mul(v[0], n_inv);
+    if (n > 1) v[n / 2] = gl_mul(v[n / 2], n_inv);
+    for (size_t i = 1; i < n / 2; i++) {
+        size_t j = n - i;
+        uint64_t ci = gl_mul(v[j], n_inv), cj = gl_mul(v[i], n_inv);
+        v[i] = ci;
+        v[j] = cj;
+    }
+}
+
+/* field/src/polynomial/mod.rs:280-293 */
+void orc_coset_fft(uint64_t *v, unsigned lg_n, uint64_t shift, unsigned zero_factor) {
+    size_t n = (size_t)1 << lg_n;
+    uint64_t pw = 1;
+    for (size_t i = 0; i < n; i++) {
+        v[i] = gl_mul(pw, v[i]);
+        pw = gl_mul(pw, shift);
+    }
+    orc_fft(v, lg_n, zero_factor);
+}
+
+/* Direct O(n^2) evaluation on shift*H, the statement fft.rs:230-249 and
+ * polynomial/mod.rs:477-495 test against: out[k] = sum_i in[i] (shift w^k)^i. */
+void orc_fft_naive(const uint64_t *in, uint64_t *out, unsigned lg_n, uint64_t shift) {
+    size_t n = (size_t)1 << lg_n;
+    uint64_t w = orc_gl_primitive_root(lg_n);
+    for (size_t k = 0; k < n; k++) {
+        uint64_t x = gl_mul(shift, orc_gl_pow(w, k));
+        uint64_t acc = 0;
+        for (size_t i = n; i-- > 0;) acc = gl_add(gl_mul(acc, x), in[i]);
+        out[k] = acc;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Poseidon, width 12 (core/src/poseidon.rs, core/src/poseidon_goldilocks.rs)
+ * ---------------------------------------------------------------------------------------- */
+
+/* poseidon.rs:546-552 */
+static inline uint64_t sbox(uint64_t x) {
+    uint64_t x2 = gl_mul(x, x), x4 = gl_mul(x2, x2), x3 = gl_mul(x, x2);
+    return gl_mul(x3, x4);
+}
+
+/* poseidon.rs:504-513 */
+static inline void constant_layer(uint64_t s[12], unsigned round) {
+    for (int i = 0; i < 12; i++) {
+        /* add_canonical_u64 (goldilocks_field.rs:206-211) */
+        uint64_t c = POSEIDON_ALL_ROUND_CONSTANTS[i + 12 * round];
+        uint64_t t = s[i] + c;
+        s[i] = t + (t < c ? EPS : 0);
+    }
+}
+
+/* poseidon.rs:178-198, 245-264 (mds_row_shf + mds_layer).  The coefficients are < 2^6, so the
+ * 32-bit halves of the state can be accumulated in u64 without overflow and recombined, as
+ * poseidon_goldilocks.rs:217-248 does. */
+static inline void mds_layer(uint64_t s[12]) {
+    uint64_t lo[12], hi[12], out[12];
+    for (int i = 0; i < 12; i++) {
+        lo[i] = s[i] & EPS;
+        hi[i] = s[i] >> 32;
+    }
+    for (int r = 0; r < 12; r++) {
+        uint64_t al = 0, ah = 0;
+        for (int i = 0; i < 12; i++) {
+            int k = i + r >= 12 ? i + r - 12 : i + r;
+            al += lo[k] * POSEIDON_MDS_CIRC[i];
+            ah += hi[k] * POSEIDON_MDS_CIRC[i];
+        }
+        al += lo[r] * POSEIDON_MDS_DIAG[r];
+        ah += hi[r] * POSEIDON_MDS_DIAG[r];
+        u128 sum = (u128)al + ((u128)ah << 32);
+        out[r] = reduce96((uint64_t)sum, (uint32_t)(sum >> 64));
+    }
+    memcpy(s, out, sizeof out);
+}
+
+/* poseidon.rs:574-581 */
+static void full_rounds(uint64_t s[12], unsigned *round) {
+    for (int k = 0; k < 4; k++) {
+        constant_layer(s, *round);
+        for (int i = 0; i < 12; i++) s[i] = sbox(s[i]);
+        mds_layer(s);
+        (*round)++;
+    }
+}
+
+/* poseidon.rs:584-596 with :302-313 (first constant layer), :315-342 (initial matrix),
+ * :378-408 (fast partial MDS) */
+static void partial_rounds_fast(uint64_t s[12], unsigned *round) {
+    for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], POSEIDON_FAST_PARTIAL_FIRST_ROUND_CONSTANT[i]);
+    uint64_t t[12];
+    t[0] = s[0];
+    for (int c = 1; c < 12; c++) t[c] = 0;
+    for (int r = 1; r < 12; r++)
+        for (int c = 1; c < 12; c++)
+            t[c] = gl_add(t[c], gl_mul(s[r], POSEIDON_FAST_PARTIAL_ROUND_INITIAL_MATRIX[(r - 1) * 11 + (c - 1)]));
+    memcpy(s, t, sizeof t);
+
+    for (int i = 0; i < 22; i++) {
+        s[0] = sbox(s[0]);
+        s[0] = gl_add(s[0], POSEIDON_FAST_PARTIAL_ROUND_CONSTANTS[i]);
+        /* d = [M_00 | w_hat] . state, accumulated in 160 bits then reduced (reduce_u160,
+         * poseidon.rs:46-52); any exact mod-p evaluation gives the same canonical value. */
+        u128 acc_lo = 0;
+        uint32_t acc_hi = 0;
+        for (int j = 1; j < 12; j++) {
+            u128 prod = (u128)s[j] * POSEIDON_FAST_PARTIAL_ROUND_W_HATS[i * 11 + j - 1];
+            u128 n = acc_lo + prod;
+            acc_hi += n < prod;
+            acc_lo = n;
+        }
+        {
+            u128 prod = (u128)s[0] * (POSEIDON_MDS_CIRC[0] + POSEIDON_MDS_DIAG[0]);
+            u128 n = acc_lo + prod;
+            acc_hi += n < prod;
+            acc_lo = n;
+        }
+        uint64_t red_hi = reduce96((uint64_t)(acc_lo >> 64), acc_hi);
+        uint64_t d = reduce128(((u128)red_hi << 64) + (uint64_t)acc_lo);
+        for (int j = 1; j < 12; j++)
+            s[j] = gl_add(s[j], gl_mul(s[0], POSEIDON_FAST_PARTIAL_ROUND_VS[i * 11 + j - 1]));
+        s[0] = d;
+    }
+    *round += 22;
+}
+
+/* poseidon.rs:599-609 */
+void orc_poseidon(uint64_t s[12]) {
+    unsigned round = 0;
+    full_rounds(s, &round);
+    partial_rounds_fast(s, &round);
+    full_rounds(s, &round);
+}
+
+/* poseidon.rs:613-633 (poseidon_naive, the KAT-defining form) */
+void orc_poseidon_naive(uint64_t s[12]) {
+    unsigned round = 0;
+    full_rounds(s, &round);
+    for (int k = 0; k < 22; k++) {
+        constant_layer(s, round);
+        s[0] = sbox(s[0]);
+        mds_layer(s);
+        round++;
+    }
+    full_rounds(s, &round);
+}
+
+/* core/src/hashing.rs:68-95 (hash_n_to_m_no_pad, 4 outputs) */
+void orc_hash_no_pad(const uint64_t *in, size_t len, uint64_t out[4]) {
+    uint64_t s[12] = {0};
+    for (size_t off = 0; off < len; off += 8) {
+        size_t c = len - off < 8 ? len - off : 8;
+        memcpy(s, in + off, c * 8);
+        orc_poseidon(s);
+    }
+    memcpy(out, s, 32);
+}
+
+/* core/src/hashing.rs:150-168 (fork-specific domain-separated leaf hash) */
+void orc_hash_leaf(const uint64_t *in, size_t len, uint64_t out[4]) {
+    uint64_t s[12] = {0};
+    s[8] = (uint64_t)len + 1;
+    for (size_t off = 0; off < len; off += 8) {
+        size_t c = len - off < 8 ? len - off : 8;
+        memcpy(s, in + off, c * 8);
+        orc_poseidon(s);
+    }
+    memcpy(out, s, 32);
+}
+
+/* core/src/hashing.rs:47-64 (compress) */
+void orc_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]) {
+    uint64_t s[12] = {0};
+    memcpy(s, l, 32);
+    memcpy(s + 4, r, 32);
+    orc_poseidon(s);
+    memcpy(out, s, 32);
+}
+
+static void canon4(uint64_t d[4]) {
+    for (int i = 0; i < 4; i++) d[i] = orc_gl_canon(d[i]);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Merkle tree (plonky2/src/hash/merkle_tree.rs)
+ * ---------------------------------------------------------------------------------------- */
+
+/* merkle_tree.rs:56-83 (fill_subtree).  digests_buf holds 2*(n_leaves-1) digests. */
+static void fill_subtree(uint64_t *digests_buf, size_t n_digests, const uint64_t *leaves,
+                         size_t n_leaves, size_t leaf_len, uint64_t out[4]) {
+    if (n_digests == 0) {
+        orc_hash_leaf(leaves, leaf_len, out);
+        canon4(out);
+        return;
+    }
+    size_t half = n_digests / 2;
+    uint64_t *left_mem = digests_buf + (half - 1) * 4;
+    uint64_t *right_mem = digests_buf + half * 4;
+    uint64_t l[4], r[4];
+    size_t hl = n_leaves / 2;
+    if (n_leaves >= 2048) {
+#pragma omp task shared(l)
+        fill_subtree(digests_buf, half - 1, leaves, hl, leaf_len, l);
+#pragma omp task shared(r)
+        fill_subtree(right_mem + 4, half - 1, leaves + hl * leaf_len, hl, leaf_len, r);
+#pragma omp taskwait
+    } else {
+        fill_subtree(digests_buf, half - 1, leaves, hl, leaf_len, l);
+        fill_subtree(right_mem + 4, half - 1, leaves + hl * leaf_len, hl, leaf_len, r);
+    }
+    memcpy(left_mem, l, 32);
+    memcpy(right_mem, r, 32);
+    orc_two_to_one(l, r, out);
+    canon4(out);
+}
+
+/* merkle_tree.rs:163-194 (new) + :85-119 (fill_digests_buf) */
+int orc_merkle_tree_new(const uint64_t *leaves, size_t n_leaves, size_t leaf_len,
+                        unsigned cap_height, uint64_t *digests, uint64_t *cap) {
+    if (n_leaves == 0 || (n_leaves & (n_leaves - 1))) return 1;
+    unsigned lg = log2_strict(n_leaves);
+    if (cap_height > lg) return 1;
+    size_t n_cap = (size_t)1 << cap_height;
+    size_t n_digests = 2 * (n_leaves - n_cap);
+    if (n_digests == 0) {
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < n_leaves; i++) {
+            orc_hash_leaf(leaves + i * leaf_len, leaf_len, cap + i * 4);
+            canon4(cap + i * 4);
+        }
+        return 0;
+    }
+    size_t sub_d = n_digests >> cap_height, sub_l = n_leaves >> cap_height;
+#pragma omp parallel
+#pragma omp single
+    for (size_t t = 0; t < n_cap; t++) {
+#pragma omp task firstprivate(t)
+        fill_subtree(digests + t * sub_d * 4, sub_d, leaves + t * sub_l * leaf_len, sub_l, leaf_len,
+                     cap + t * 4);
+    }
+    return 0;
+}
+
+/* merkle_tree.rs:121-160 (merkle_tree_prove) */
+void orc_merkle_prove(size_t leaf_index, size_t n_leaves, unsigned cap_height,
+                      const uint64_t *digests, uint64_t *siblings) {
+    unsigned num_layers = log2_strict(n_leaves) - cap_height;
+    size_t digest_len = 2 * (n_leaves - ((size_t)1 << cap_height));
+    size_t tree_index = leaf_index >> num_layers;
+    size_t tree_len = digest_len >> cap_height;
+    const uint64_t *tree = digests + tree_len * tree_index * 4;
+    size_t pair_index = leaf_index & (((size_t)1 << num_layers) - 1);
+    for (unsigned i = 0; i < num_layers; i++) {
+        size_t parity = pair_index & 1;
+        pair_index >>= 1;
+        size_t siblings_index = (pair_index << (i + 1)) + ((size_t)1 << i) - 1;
+        size_t sibling_index = 2 * siblings_index + (1 - parity);
+        memcpy(siblings + i * 4, tree + sibling_index * 4, 32);
+    }
+}
+
+/* core/src/merkle_proofs.rs:59-97 with a single leaf (verify_merkle_proof_to_cap) */
+int orc_merkle_verify(const uint64_t *leaf, size_t leaf_len, size_t leaf_index,
+                      const uint64_t *cap, unsigned cap_height, const uint64_t *siblings,
+                      unsigned n_siblings) {
+    (void)cap_height;
+    uint64_t cur[4];
+    orc_hash_leaf(leaf, leaf_len, cur);
+    for (unsigned i = 0; i < n_siblings; i++) {
+        uint64_t nxt[4];
+        if (leaf_index & 1)
+            orc_two_to_one(siblings + i * 4, cur, nxt);
+        else
+            orc_two_to_one(cur, siblings + i * 4, nxt);
+        leaf_index >>= 1;
+        memcpy(cur, nxt, 32);
+    }
+    for (int k = 0; k < 4; k++)
+        if (orc_gl_canon(cur[k]) != orc_gl_canon(cap[leaf_index * 4 + k])) return 0;
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * PolynomialBatch (plonky2/src/fri/oracle.rs:168-283)
+ * ---------------------------------------------------------------------------------------- */
+
+int orc_batch_from_coeffs(const uint64_t *coeffs, size_t n_cols, unsigned lg_n, unsigned rate_bits,
+                          unsigned cap_height, const uint64_t *salt, uint64_t *leaves_out,
+                          uint64_t *digests_out, uint64_t *cap_out, double scope_ms[4]) {
+    size_t n = (size_t)1 << lg_n, N = n << rate_bits;
+    unsigned lg_N = lg_n + rate_bits;
+    if (cap_height > lg_N) return 1;
+    size_t leaf_len = n_cols + (salt ? 4 : 0);
+    double t0 = now_ms();
+    /* "FFT + blinding": oracle.rs:202-206, 267-283 -- par over columns */
+    uint64_t *lde = (uint64_t *)malloc(leaf_len * N * 8);
+    if (!lde) return 2;
+    root_table(lg_N);
+    uint64_t g = orc_gl_coset_shift();
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t c = 0; c < n_cols; c++) {
+        uint64_t *col = lde + c * N;
+        memcpy(col, coeffs + c * n, n * 8);          /* lde(): zero-pad, polynomial/mod.rs:199-201 */
+        memset(col + n, 0, (N - n) * 8);
+        orc_coset_fft(col, lg_N, g, rate_bits);      /* coset_fft_with_options(g, Some(r), table) */
+    }
+    if (salt) memcpy(lde + n_cols * N, salt, 4 * N * 8); /* oracle.rs:259-263, salt injected */
+    double t1 = now_ms();
+    /* "transpose LDEs" + reverse_index_bits_in_place(leaves): oracle.rs:208-209 */
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < N; i++) {
+        size_t src = bitrev(i, lg_N);
+        uint64_t *leaf = leaves_out + i * leaf_len;
+        for (size_t c = 0; c < leaf_len; c++) leaf[c] = orc_gl_canon(lde[c * N + src]);
+    }
+    free(lde);
+    double t2 = now_ms();
+    /* "build Merkle tree": oracle.rs:210-214 */
+    int rc = orc_merkle_tree_new(leaves_out, N, leaf_len, cap_height, digests_out, cap_out);
+    double t3 = now_ms();
+    if (scope_ms) {
+        scope_ms[1] = t1 - t0;
+        scope_ms[2] = t2 - t1;
+        scope_ms[3] = t3 - t2;
+    }
+    return rc;
+}
+
+int orc_batch_from_values(const uint64_t *values, size_t n_cols, unsigned lg_n, unsigned rate_bits,
+                          unsigned cap_height, const uint64_t *salt, uint64_t *coeffs_out,
+                          uint64_t *leaves_out, uint64_t *digests_out, uint64_t *cap_out,
+                          double scope_ms[4]) {
+    size_t n = (size_t)1 << lg_n;
+    double t0 = now_ms();
+    root_table(lg_n + rate_bits);
+    /* "IFFT": oracle.rs:176-180 -- par over columns */
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t c = 0; c < n_cols; c++) {
+        uint64_t *col = coeffs_out + c * n;
+        if (col != values + c * n) memcpy(col, values + c * n, n * 8);
+        orc_ifft(col, lg_n);
+        for (size_t i = 0; i < n; i++) col[i] = orc_gl_canon(col[i]);
+    }
+    double t1 = now_ms();
+    if (scope_ms) scope_ms[0] = t1 - t0;
+    return orc_batch_from_coeffs(coeffs_out, n_cols, lg_n, rate_bits, cap_height, salt, leaves_out,
+                                 digests_out, cap_out, scope_ms);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Challenger (core/src/challenger.rs)
+ * ---------------------------------------------------------------------------------------- */
+void orc_challenger_init(orc_challenger *c) { memset(c, 0, sizeof *c); }
+
+/* challenger.rs:125-140 */
+static void duplexing(orc_challenger *c) {
+    for (uint32_t i = 0; i < c->n_in; i++) c->sponge_state[i] = c->input_buffer[i];
+    c->n_in = 0;
+    orc_poseidon(c->sponge_state);
+    for (int i = 0; i < 8; i++) c->output_buffer[i] = c->sponge_state[i];
+    c->n_out = 8;
+}
+
+/* challenger.rs:35-46 */
+void orc_challenger_observe(orc_challenger *c, const uint64_t *elems, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        c->n_out = 0;
+        c->input_buffer[c->n_in++] = elems[i];
+        if (c->n_in == 8) duplexing(c);
+    }
+}
+
+/* challenger.rs:78-89: pop from the END of the output buffer */
+uint64_t orc_challenger_get(orc_challenger *c) {
+    if (c->n_in != 0 || c->n_out == 0) duplexing(c);
+    return orc_gl_canon(c->output_buffer[--c->n_out]);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * FRI commit phase
+ * ---------------------------------------------------------------------------------------- */
+
+/* core/src/fri.rs:50-61 */
+unsigned orc_fri_reduction_arity_bits(unsigned degree_bits, unsigned rate_bits, unsigned cap_height,
+                                      unsigned arity_bits, unsigned final_poly_bits, unsigned *out) {
+    unsigned k = 0;
+    while (degree_bits > final_poly_bits && degree_bits + rate_bits - arity_bits >= cap_height) {
+        out[k++] = arity_bits;
+        degree_bits -= arity_bits;
+    }
+    return k;
+}
+
+/* coset_fft over F_p^2 = two base-field lanes (extension/mod.rs:73-76: the ext 2-adic
+ * generator is the embedded base one, so twiddles are base-field). */
+static void ext_coset_fft(uint64_t *v /* n x 2 */, unsigned lg_n, uint64_t shift) {
+    size_t n = (size_t)1 << lg_n;
+    uint64_t *lane = (uint64_t *)malloc(n * 8);
+    for (int k = 0; k < 2; k++) {
+        for (size_t i = 0; i < n; i++) lane[i] = v[2 * i + k];
+        orc_coset_fft(lane, lg_n, shift, 0);
+        for (size_t i = 0; i < n; i++) v[2 * i + k] = orc_gl_canon(lane[i]);
+    }
+    free(lane);
+}
+
+/* plonky2/src/fri/prover.rs:85-143 */
+int orc_fri_committed_trees(uint64_t *coeffs, uint64_t *values, unsigned lg_n, unsigned rate_bits,
+                            unsigned cap_height, const unsigned *arity_bits, unsigned n_rounds,
+                            orc_challenger *challenger, uint64_t *caps_out, uint64_t **leaves_out,
+                            uint64_t **digests_out, uint64_t *betas_out, uint64_t *final_poly_out) {
+    size_t n = (size_t)1 << lg_n;
+    size_t cap_words = ((size_t)1 << cap_height) * 4;
+    uint64_t shift = orc_gl_coset_shift();
+    for (unsigned step = 0; step < n_rounds; step++) {
+        unsigned ab = arity_bits[step];
+        size_t arity = (size_t)1 << ab;
+        /* reverse_index_bits_in_place(values); leaves = chunks of `arity`, flattened */
+        orc_reverse_index_bits(values, n, 2);
+        for (size_t i = 0; i < 2 * n; i++) values[i] = orc_gl_canon(values[i]);
+        size_t n_leaves = n >> ab, leaf_len = 2 * arity;
+        if (cap_height > log2_strict(n_leaves)) return 1;
+        size_t n_dig = 2 * (n_leaves - ((size_t)1 << cap_height));
+        uint64_t *dig = (uint64_t *)malloc((n_dig ? n_dig : 1) * 32);
+        uint64_t *cap = caps_out + step * cap_words;
+        int rc = orc_merkle_tree_new(values, n_leaves, leaf_len, cap_height, dig, cap);
+        if (rc) {
+            free(dig);
+            return rc;
+        }
+        if (leaves_out && leaves_out[step]) memcpy(leaves_out[step], values, n * 16);
+        if (digests_out && digests_out[step]) memcpy(digests_out[step], dig, n_dig * 32);
+        free(dig);
+        orc_challenger_observe(challenger, cap, cap_words);
+        uint64_t beta[2];
+        beta[0] = orc_challenger_get(challenger);
+        beta[1] = orc_challenger_get(challenger);
+        if (betas_out) {
+            betas_out[2 * step] = beta[0];
+            betas_out[2 * step + 1] = beta[1];
+        }
+        /* reduce_with_powers over chunks (core/src/plonk_common.rs:87-98) */
+        for (size_t i = 0; i < n_leaves; i++) {
+            uint64_t sum[2] = {0, 0};
+            for (size_t j = arity; j-- > 0;) {
+                uint64_t t[2];
+                orc_ext_mul(sum, beta, t);
+                sum[0] = gl_add(t[0], coeffs[2 * (i * arity + j)]);
+                sum[1] = gl_add(t[1], coeffs[2 * (i * arity + j) + 1]);
+            }
+            coeffs[2 * i] = orc_gl_canon(sum[0]);
+            coeffs[2 * i + 1] = orc_gl_canon(sum[1]);
+        }
+        n = n_leaves;
+        lg_n -= ab;
+        if (step + 1 == n_rounds) continue;
+        shift = orc_gl_pow(shift, arity);
+        memcpy(values, coeffs, n * 16);
+        ext_coset_fft(values, lg_n, shift);
+    }
+    size_t fin = n >> rate_bits;
+    memcpy(final_poly_out, coeffs, fin * 16);
+    return 0;
+}
+
+/* plonky2/src/fri/prover.rs:159-208, smallest-witness rule */
+uint64_t orc_fri_proof_of_work(orc_challenger *ch, unsigned pow_bits) {
+    uint64_t base[12];
+    memcpy(base, ch->sponge_state, sizeof base);
+    for (uint32_t i = 0; i < ch->n_in; i++) base[i] = ch->input_buffer[i];
+    uint32_t pos = ch->n_in;
+    uint64_t w;
+    for (w = 0;; w++) {
+        uint64_t s[12];
+        memcpy(s, base, sizeof s);
+        s[pos] = w;
+        orc_poseidon(s);
+        uint64_t resp = orc_gl_canon(s[7]);
+        unsigned lz = resp ? (unsigned)__builtin_clzll(resp) : 64;
+        if (lz >= pow_bits) break;
+    }
+    orc_challenger_observe(ch, &w, 1);
+    (void)orc_challenger_get(ch);
+    return w;
+}

@@ -1,0 +1,121 @@
+/* TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
+ *
+ * CPU oracle: a plain-C restatement of the reference's (Quantus-Network/qp-plonky2)
+ * polynomial-commitment path.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library; the product path
+ * (qp-plonky2_b200/) never links, imports or calls it.
+ *
+ * Parity status: the Poseidon permutation is PINNED by the reference's four known-answer
+ * vectors (core/src/poseidon_goldilocks.rs:455-490) and the bit-reversal by the reference's
+ * table (plonky2/src/util/mod.rs:56-123).  Everything above the permutation (leaf hashes,
+ * digests, caps, LDE values, FRI commitments) is "parity unpinned" by golden data: the
+ * reference holds no vectors for it and no Rust toolchain exists in this image, so those
+ * layers are pinned only structurally (FFT == naive evaluation, every-leaf Merkle round trip,
+ * FRI fold consistency, and agreement with the independent big-integer restatement
+ * oracle/pyref.py).
+ *
+ * Every function cites the reference file:line it follows (paths relative to the reference
+ * root).
+ */
+#ifndef PLONKY2_ORACLE_H
+#define PLONKY2_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_P 0xFFFFFFFF00000001ULL
+#define ORC_SPONGE_WIDTH 12
+#define ORC_SPONGE_RATE 8
+
+/* ---- field (field/src/goldilocks_field.rs) ---- */
+uint64_t orc_gl_add(uint64_t a, uint64_t b);
+uint64_t orc_gl_sub(uint64_t a, uint64_t b);
+uint64_t orc_gl_mul(uint64_t a, uint64_t b);
+uint64_t orc_gl_canon(uint64_t a);
+uint64_t orc_gl_pow(uint64_t a, uint64_t e);
+uint64_t orc_gl_inv(uint64_t a);
+uint64_t orc_gl_inverse_2exp(unsigned k);
+uint64_t orc_gl_primitive_root(unsigned k);
+uint64_t orc_gl_coset_shift(void);
+
+/* ---- quadratic extension F_p[X]/(X^2-7) ---- */
+void orc_ext_mul(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]);
+
+/* ---- bit reversal / FFT ---- */
+void orc_reverse_index_bits(uint64_t *arr, size_t n, size_t elem_words);
+void orc_fft(uint64_t *v, unsigned lg_n, unsigned zero_factor);
+void orc_ifft(uint64_t *v, unsigned lg_n);
+void orc_coset_fft(uint64_t *v, unsigned lg_n, uint64_t shift, unsigned zero_factor);
+void orc_fft_naive(const uint64_t *in, uint64_t *out, unsigned lg_n, uint64_t shift);
+
+/* ---- Poseidon ---- */
+void orc_poseidon(uint64_t state[12]);
+void orc_poseidon_naive(uint64_t state[12]);
+void orc_hash_no_pad(const uint64_t *in, size_t len, uint64_t out[4]);
+void orc_hash_leaf(const uint64_t *in, size_t len, uint64_t out[4]);
+void orc_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]);
+
+/* ---- Merkle tree ---- */
+/* leaves: leaf-major [n_leaves][leaf_len]; digests: 2*(n_leaves - 2^cap_height) x 4;
+ * cap: 2^cap_height x 4.  Returns 0, or 1 if cap_height > log2(n_leaves) or n_leaves is not
+ * a power of two (the reference's panics). */
+int orc_merkle_tree_new(const uint64_t *leaves, size_t n_leaves, size_t leaf_len,
+                        unsigned cap_height, uint64_t *digests, uint64_t *cap);
+void orc_merkle_prove(size_t leaf_index, size_t n_leaves, unsigned cap_height,
+                      const uint64_t *digests, uint64_t *siblings /* (lgN-h) x 4 */);
+int orc_merkle_verify(const uint64_t *leaf, size_t leaf_len, size_t leaf_index,
+                      const uint64_t *cap, unsigned cap_height, const uint64_t *siblings,
+                      unsigned n_siblings);
+
+/* ---- PolynomialBatch ---- */
+/* values/coeffs are column-major [n_cols][n]; leaves_out leaf-major [N][n_cols + (salt?4:0)];
+ * salt (optional, may be NULL) is column-major [4][N] in natural (pre bit-reversal) point order,
+ * standing in for the reference's F::rand_vec salt columns.  scope_ms[4] receives the wall time
+ * of "IFFT", "FFT + blinding", "transpose LDEs", "build Merkle tree". */
+int orc_batch_from_values(const uint64_t *values, size_t n_cols, unsigned lg_n, unsigned rate_bits,
+                          unsigned cap_height, const uint64_t *salt, uint64_t *coeffs_out,
+                          uint64_t *leaves_out, uint64_t *digests_out, uint64_t *cap_out,
+                          double scope_ms[4]);
+int orc_batch_from_coeffs(const uint64_t *coeffs, size_t n_cols, unsigned lg_n, unsigned rate_bits,
+                          unsigned cap_height, const uint64_t *salt, uint64_t *leaves_out,
+                          uint64_t *digests_out, uint64_t *cap_out, double scope_ms[4]);
+
+/* ---- Challenger (core/src/challenger.rs) ---- */
+typedef struct {
+    uint64_t sponge_state[12];
+    uint64_t input_buffer[8];
+    uint64_t output_buffer[8];
+    uint32_t n_in, n_out;
+} orc_challenger;
+void orc_challenger_init(orc_challenger *c);
+void orc_challenger_observe(orc_challenger *c, const uint64_t *elems, size_t n);
+uint64_t orc_challenger_get(orc_challenger *c);
+
+/* ---- FRI commit phase (plonky2/src/fri/prover.rs:85-143) ---- */
+/* Computes reduction_arity_bits for ConstantArityBits(arity_bits, final_poly_bits)
+ * (core/src/fri.rs:50-61).  Returns the count, writes into out[] (capacity 64). */
+unsigned orc_fri_reduction_arity_bits(unsigned degree_bits, unsigned rate_bits, unsigned cap_height,
+                                      unsigned arity_bits, unsigned final_poly_bits, unsigned *out);
+
+/* coeffs/values: n ext elements (2 u64 each, interleaved).  Consumed (overwritten).
+ * For round i: caps_out + i*(2^cap_height*4); if leaves_out[i]/digests_out[i] non-NULL they
+ * receive that round's tree.  final_poly_out gets (n >> total_arity >> rate_bits) ext elems.
+ * betas_out gets one ext element per round. */
+int orc_fri_committed_trees(uint64_t *coeffs, uint64_t *values, unsigned lg_n, unsigned rate_bits,
+                            unsigned cap_height, const unsigned *arity_bits, unsigned n_rounds,
+                            orc_challenger *challenger, uint64_t *caps_out, uint64_t **leaves_out,
+                            uint64_t **digests_out, uint64_t *betas_out, uint64_t *final_poly_out);
+
+/* PoW grinding, deterministic rule = smallest witness (serial `find`,
+ * maybe_rayon/src/lib.rs:254-259; plonky2/src/fri/prover.rs:159-208). */
+uint64_t orc_fri_proof_of_work(orc_challenger *challenger, unsigned pow_bits);
+
+int orc_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
