@@ -1,0 +1,165 @@
+/* qp_plonky2_b200 -- C ABI of the B200-native polynomial-commitment path.
+ *
+ * Drop-in boundary for the hot path of Quantus-Network/qp-plonky2:
+ * the reference has no FFI, so each entry point below replaces one whole Rust function behind a
+ * cargo feature; the Rust shim a maintainer would add is shown in INTEGRATION.md.  Reference
+ * citations are relative to the reference root.
+ *
+ * Conventions
+ *   - every function returns an int: QP_OK, or the code of the reference's panic / error
+ *     condition it mirrors; nothing throws across the boundary.  qp_last_error() gives text.
+ *   - field elements are Goldilocks u64 (p = 2^64 - 2^32 + 1); inputs may be non-canonical,
+ *     every output is canonical (what the reference serialises, core/src/config.rs:104-109).
+ *   - `space` says where a caller buffer lives: QP_HOST (pageable or pinned) or QP_DEVICE.
+ *   - column-major inputs are [n_cols][n] (the reference's Vec<PolynomialValues>), rows/leaves
+ *     are leaf-major [count][leaf_len] (its Vec<Vec<F>>).
+ *   - handles own device memory (LDE values stay on the device, column-major in leaf order);
+ *     they are immutable after creation and may be read from any thread.
+ *   - there is NO CPU fallback: without a CUDA device every call fails with QP_ERR_CUDA.
+ */
+#ifndef QP_PLONKY2_B200_H
+#define QP_PLONKY2_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    QP_OK = 0,
+    QP_ERR_CUDA = 1,           /* CUDA runtime failure (incl. no device) */
+    QP_ERR_CAP_HEIGHT = 2,     /* assert cap_height <= log2(leaves.len()), plonky2/src/hash/merkle_tree.rs:164-170 */
+    QP_ERR_NOT_POW2 = 3,       /* log2_strict panic, util/src/lib.rs:25-29 */
+    QP_ERR_DEGREE_MISMATCH = 4,/* "Polynomial degrees inconsistent", plonky2/src/fri/oracle.rs:277 */
+    QP_ERR_BAD_ARG = 5,        /* null pointer / out-of-range index (slice index panic) */
+    QP_ERR_TOO_LARGE = 6,      /* exceeds the field's two-adicity (types.rs:281 assert) or device memory */
+    QP_ERR_BLINDING_NO_SALT = 7/* blinding requested without injected salt ("Cannot set blinding without rand feature", oracle.rs:238) */
+};
+
+enum { QP_HOST = 0, QP_DEVICE = 1 };
+
+#define QP_SALT_SIZE 4 /* plonky2/src/fri/oracle.rs:29 */
+
+typedef struct qp_ctx qp_ctx;
+typedef struct qp_batch qp_batch;
+typedef struct qp_tree qp_tree;
+typedef struct qp_fri qp_fri;
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* One context per (process, GPU).  `stream` is a cudaStream_t (or NULL for a private stream);
+ * max_lde_log bounds the twiddle table (log2 of the largest transform, <= 32). */
+int qp_ctx_create(int device, void* stream, unsigned max_lde_log, qp_ctx** out);
+void qp_ctx_destroy(qp_ctx* ctx);
+const char* qp_last_error(const qp_ctx* ctx);
+int qp_ctx_synchronize(qp_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t qp_ctx_launch_count(const qp_ctx* ctx);
+
+/* ---- PolynomialBatch (plonky2/src/fri/oracle.rs:33-40) -------------------------------------- */
+/* PolynomialBatch::from_values (oracle.rs:168-190): values[n_cols][2^degree_log] -> iNTT ->
+ * from_coeffs.  `salt` stands in for the reference's F::rand_vec blinding columns
+ * (oracle.rs:259-263): [QP_SALT_SIZE][N] in natural point order, required iff blinding != 0.
+ * Sharding (multi-GPU, one process per GPU): the batch holds LDE blocks
+ * [block_first, block_first + block_count) of the 2^rate_bits coset blocks (= leaves
+ * [block_first * n, ...) ), and the cap entries / digests of exactly those leaves.  Pass
+ * block_first = 0, block_count = 2^rate_bits for the whole batch. */
+int qp_batch_from_values(qp_ctx* ctx, const uint64_t* values, int space, size_t n_cols,
+                         unsigned degree_log, unsigned rate_bits, int blinding, unsigned cap_height,
+                         const uint64_t* salt, unsigned block_first, unsigned block_count,
+                         qp_batch** out);
+/* PolynomialBatch::from_coeffs (oracle.rs:193-223). */
+int qp_batch_from_coeffs(qp_ctx* ctx, const uint64_t* coeffs, int space, size_t n_cols,
+                         unsigned degree_log, unsigned rate_bits, int blinding, unsigned cap_height,
+                         const uint64_t* salt, unsigned block_first, unsigned block_count,
+                         qp_batch** out);
+void qp_batch_free(qp_batch* b);
+
+/* iNTT of columns only (the "IFFT" scope, oracle.rs:176-180): values[n_cols][n] -> coeffs.
+ * Used by the multi-GPU path, which shards columns for the iNTT and cosets for the rest. */
+int qp_ifft_columns(qp_ctx* ctx, const uint64_t* values, int space, size_t n_cols,
+                    unsigned degree_log, uint64_t* coeffs_out, int out_space);
+
+/* merkle_tree.cap: (local) cap entries, [n_local_cap][4]; n_local_cap = 2^cap_height *
+ * block_count / 2^rate_bits (whole batch: 2^cap_height). */
+int qp_batch_cap(const qp_batch* b, uint64_t* out, int space);
+size_t qp_batch_cap_len(const qp_batch* b);
+/* .polynomials: coefficients [n_cols][n], natural order. */
+int qp_batch_coeffs(const qp_batch* b, uint64_t* out, int space);
+/* merkle_tree.digests in the reference layout (local slice), [n_digests][4]. */
+int qp_batch_digests(const qp_batch* b, uint64_t* out, int space);
+size_t qp_batch_digests_len(const qp_batch* b);
+/* merkle_tree.leaves[first .. first+count): leaf-major rows [count][leaf_len], salt included. */
+int qp_batch_leaves(const qp_batch* b, size_t first, size_t count, uint64_t* out, int space);
+size_t qp_batch_leaf_len(const qp_batch* b);
+/* get_lde_values(index, step) (oracle.rs:286-291): row at bit-reversed index*step, salt stripped;
+ * out holds n_cols elements (host). */
+int qp_batch_get_lde_values(const qp_batch* b, size_t index, size_t step, uint64_t* out);
+/* Rows for many leaf indices at once (query openings, fri/prover.rs:246-249). */
+int qp_batch_get_leaves(const qp_batch* b, const uint64_t* leaf_indices, unsigned n, uint64_t* out);
+/* MerkleTree::prove (merkle_tree.rs:201-207): siblings bottom-up, [lg N - cap_height][4]. */
+int qp_batch_prove(const qp_batch* b, size_t leaf_index, uint64_t* siblings_out);
+/* TimingTree scopes (oracle.rs:176-214), milliseconds of device time:
+ * [0] "IFFT", [1] "FFT + blinding", [2] "transpose LDEs" (always 0: fused away), [3] "build Merkle tree". */
+int qp_batch_timing(const qp_batch* b, double ms[4]);
+/* Device time (CUDA events on the launching stream) per kernel group, milliseconds:
+ * [0] iNTT passes, [1] LDE passes, [2] leaf_hash_kernel, [3] tree_level_kernel launches. */
+int qp_batch_kernel_timing(const qp_batch* b, double ms[4]);
+/* Raw device pointers for device-resident consumers (quotient / openings kernels). */
+const uint64_t* qp_batch_device_lde(const qp_batch* b);    /* [leaf_len][N_local], leaf order */
+const uint64_t* qp_batch_device_coeffs(const qp_batch* b); /* [n_cols][n] */
+
+/* ---- MerkleTree (plonky2/src/hash/merkle_tree.rs:163-207) ---------------------------------- */
+/* MerkleTree::new(leaves, cap_height) on caller-provided leaf-major rows. */
+int qp_merkle_tree_new(qp_ctx* ctx, const uint64_t* leaves, int space, size_t n_leaves,
+                       size_t leaf_len, unsigned cap_height, qp_tree** out);
+void qp_tree_free(qp_tree* t);
+int qp_tree_cap(const qp_tree* t, uint64_t* out, int space);
+int qp_tree_digests(const qp_tree* t, uint64_t* out, int space);
+size_t qp_tree_digests_len(const qp_tree* t);
+int qp_tree_prove(const qp_tree* t, size_t leaf_index, uint64_t* siblings_out);
+int qp_tree_get(const qp_tree* t, size_t leaf_index, uint64_t* out); /* MerkleTree::get */
+
+/* ---- Poseidon primitives (core/src/poseidon.rs:599-609, hashing.rs) ------------------------- */
+/* Batch of width-12 permutations, states [count][12] (in place). */
+int qp_poseidon_permute(qp_ctx* ctx, uint64_t* states, int space, size_t count);
+
+/* ---- transforms (field/src/fft.rs, polynomial/mod.rs) ---------------------------------------- */
+/* coset_fft_with_options(shift) of `n_vec` polynomials [n_vec][2^lg_n] -> values in NATURAL
+ * order (bit_reversed = 0) or bit-reversed order (bit_reversed = 1).  shift = 1 gives fft. */
+int qp_coset_fft(qp_ctx* ctx, const uint64_t* coeffs, int space, size_t n_vec, unsigned lg_n,
+                 uint64_t shift, int bit_reversed, uint64_t* out, int out_space);
+
+/* ---- FRI commit phase (plonky2/src/fri/prover.rs:85-143) ------------------------------------ */
+/* The transcript (Challenger, core/src/challenger.rs) stays with the caller: each round is
+ *   qp_fri_commit_round -> cap   (observe_cap, get_extension_challenge on the caller's side)
+ *   qp_fri_fold_round(beta)      (fold by beta; unless last: coset FFT with shift^arity)
+ * Inputs are F_p^2 arrays [n][2] (interleaved c0, c1): the LDE polynomial coefficients and
+ * its values in natural order (fri_proof's two arguments, prover.rs:24-31). */
+int qp_fri_begin(qp_ctx* ctx, const uint64_t* coeffs_ext, const uint64_t* values_ext, int space,
+                 unsigned lg_n, unsigned rate_bits, unsigned cap_height, qp_fri** out);
+int qp_fri_commit_round(qp_fri* f, unsigned arity_bits, uint64_t* cap_out /* [2^cap_height][4] host */);
+int qp_fri_fold_round(qp_fri* f, const uint64_t beta[2], int is_last);
+/* Final polynomial: coeffs truncated to len >> rate_bits (prover.rs:138-141); returns its
+ * length in *len_out (ext elements) and writes [len][2] to out (host). */
+int qp_fri_final_poly(qp_fri* f, uint64_t* out, size_t* len_out);
+/* Tree of commit round r: leaf (x_index >> arity_bits) flattened [2*arity], and its path. */
+int qp_fri_tree_get(const qp_fri* f, unsigned round, size_t leaf_index, uint64_t* out);
+int qp_fri_tree_prove(const qp_fri* f, unsigned round, size_t leaf_index, uint64_t* siblings_out);
+int qp_fri_tree_digests(const qp_fri* f, unsigned round, uint64_t* out, int space);
+size_t qp_fri_tree_digests_len(const qp_fri* f, unsigned round);
+unsigned qp_fri_num_rounds(const qp_fri* f);
+void qp_fri_free(qp_fri* f);
+
+/* Proof-of-work grinding (plonky2/src/fri/prover.rs:159-208).  `state12` is the duplex state
+ * with the pending inputs already written (duplex_intermediate_state), `witness_pos` the lane
+ * the candidate goes to.  Returns the SMALLEST witness whose response (lane 7 after the
+ * permutation) has >= min_leading_zeros leading zero bits -- the deterministic rule of the
+ * serial `find` (maybe_rayon/src/lib.rs:254-259). */
+int qp_fri_proof_of_work(qp_ctx* ctx, const uint64_t state12[12], unsigned witness_pos,
+                         unsigned min_leading_zeros, uint64_t* witness_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,53 @@
+/* qp_plonky2_host -- host-side mirror of the reference's transcript around the commit path.
+ *
+ * NOT part of the drop-in FFI: in a Rust build these roles are played by the reference's own
+ * `Challenger` (core/src/challenger.rs) and `fri_proof` driver (plonky2/src/fri/prover.rs:24-71),
+ * which call the device entry points of qp_plonky2_b200.h.  This header exists because the
+ * image has no Rust toolchain: it gives the C++/Python harnesses the same orchestration, so
+ * the parity tests and bench.py exercise the path exactly the way the shim would.
+ *
+ * The Fiat-Shamir transcript is inherently serial (one permutation per 8 observed elements)
+ * and stays on the host, as SURVEY.md section 8 (a14) specifies; it is never timed as part of
+ * a kernel and never substitutes for a device computation.
+ */
+#ifndef QP_PLONKY2_HOST_H
+#define QP_PLONKY2_HOST_H
+#include "qp_plonky2_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* core/src/challenger.rs:12-18 */
+typedef struct {
+    uint64_t sponge_state[12];
+    uint64_t input_buffer[8];
+    uint64_t output_buffer[8];
+    uint32_t n_in, n_out;
+} qp_challenger;
+
+void qp_challenger_init(qp_challenger* c);                                   /* Challenger::new */
+void qp_challenger_observe(qp_challenger* c, const uint64_t* elems, size_t n);/* observe_elements / observe_cap */
+uint64_t qp_challenger_get(qp_challenger* c);                                /* get_challenge */
+
+/* core/src/fri.rs:50-61 (ConstantArityBits).  Returns the number of reductions. */
+unsigned qp_fri_reduction_arity_bits(unsigned degree_bits, unsigned rate_bits, unsigned cap_height,
+                                     unsigned arity_bits, unsigned final_poly_bits, unsigned out[64]);
+
+/* fri_committed_trees (plonky2/src/fri/prover.rs:85-143) driven over the device step API:
+ * per round commit -> observe_cap -> beta = get_extension_challenge -> fold.
+ * caps_out: [n_rounds][2^cap_height][4]; final_poly_out: [(n >> sum arity) >> rate_bits][2]. */
+int qp_fri_committed_trees(qp_ctx* ctx, const uint64_t* coeffs_ext, const uint64_t* values_ext, int space,
+                           unsigned lg_n, unsigned rate_bits, unsigned cap_height,
+                           const unsigned* arity_bits, unsigned n_rounds, qp_challenger* challenger,
+                           uint64_t* caps_out, uint64_t* final_poly_out, size_t* final_len_out,
+                           qp_fri** fri_out);
+
+/* fri_proof_of_work (prover.rs:159-208): grinds on the device, then observes the witness and
+ * draws the response on the transcript, as the reference does. */
+int qp_fri_grind(qp_ctx* ctx, qp_challenger* challenger, unsigned proof_of_work_bits, uint64_t* witness_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

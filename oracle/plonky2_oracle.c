@@ -40,49 +40,51 @@ int orc_num_threads(void) {
 uint64_t orc_gl_canon(uint64_t a) { return a >= ORC_P ? a - ORC_P : a; }
 
 /* goldilocks_field.rs:249-265 */
-uint64_t orc_gl_add(uint64_t a, uint64_t b) {
-    uint64_t s = a + b;
-    int over = s < a;
-    uint64_t s2 = s + (over ? EPS : 0);
-    if (s2 < s) s2 += EPS; /* double overflow */
+static inline uint64_t gl_add(uint64_t a, uint64_t b) {
+    /* branch-free on the common carry (the reference uses add/sbb inline asm for this,
+     * goldilocks_field.rs:345-368); the double overflow is the rare, hinted branch. */
+    uint64_t s, s2;
+    uint64_t over = __builtin_add_overflow(a, b, &s);
+    uint64_t over2 = __builtin_add_overflow(s, (0 - over) & EPS, &s2);
+    if (__builtin_expect(over2, 0)) s2 += EPS;
     return s2;
 }
 
 /* goldilocks_field.rs:280-294 */
-uint64_t orc_gl_sub(uint64_t a, uint64_t b) {
-    uint64_t d = a - b;
-    int under = a < b;
-    uint64_t d2 = d - (under ? EPS : 0);
-    if (d2 > d) d2 -= EPS; /* double underflow */
+static inline uint64_t gl_sub(uint64_t a, uint64_t b) {
+    uint64_t d, d2;
+    uint64_t under = __builtin_sub_overflow(a, b, &d);
+    uint64_t under2 = __builtin_sub_overflow(d, (0 - under) & EPS, &d2);
+    if (__builtin_expect(under2, 0)) d2 -= EPS;
     return d2;
 }
+uint64_t orc_gl_add(uint64_t a, uint64_t b) { return gl_add(a, b); }
+uint64_t orc_gl_sub(uint64_t a, uint64_t b) { return gl_sub(a, b); }
 
 /* goldilocks_field.rs:390-403 (reduce128) */
 static inline uint64_t reduce128(u128 x) {
     uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
     uint64_t hi_hi = hi >> 32, hi_lo = hi & EPS;
     uint64_t t0 = lo - hi_hi;
-    if (lo < hi_hi) t0 -= EPS;
+    if (__builtin_expect(lo < hi_hi, 0)) t0 -= EPS; /* branch_hint(): a borrow is exceedingly rare */
     uint64_t t1 = hi_lo * EPS;
-    uint64_t t2 = t0 + t1;
-    if (t2 < t0) t2 += EPS;
-    return t2;
+    uint64_t t2;
+    uint64_t c = __builtin_add_overflow(t0, t1, &t2); /* add_no_canonicalize_trashing_input */
+    return t2 + ((0 - c) & EPS);
 }
 
 /* goldilocks_field.rs:381-385 (reduce96) */
 static inline uint64_t reduce96(uint64_t lo, uint32_t hi) {
     uint64_t t1 = (uint64_t)hi * EPS;
-    uint64_t t2 = lo + t1;
-    if (t2 < lo) t2 += EPS;
-    return t2;
+    uint64_t t2;
+    uint64_t c = __builtin_add_overflow(lo, t1, &t2);
+    return t2 + ((0 - c) & EPS);
 }
 
 /* goldilocks_field.rs:303-310 */
 uint64_t orc_gl_mul(uint64_t a, uint64_t b) { return reduce128((u128)a * b); }
 
 static inline uint64_t gl_mul(uint64_t a, uint64_t b) { return reduce128((u128)a * b); }
-static inline uint64_t gl_add(uint64_t a, uint64_t b) { return orc_gl_add(a, b); }
-static inline uint64_t gl_sub(uint64_t a, uint64_t b) { return orc_gl_sub(a, b); }
 
 uint64_t orc_gl_pow(uint64_t a, uint64_t e) {
     uint64_t r = 1, b = a;
@@ -263,27 +265,32 @@ static inline uint64_t sbox(uint64_t x) {
 
 /* poseidon.rs:504-513 */
 static inline void constant_layer(uint64_t s[12], unsigned round) {
+#pragma GCC unroll 12
     for (int i = 0; i < 12; i++) {
         /* add_canonical_u64 (goldilocks_field.rs:206-211) */
         uint64_t c = POSEIDON_ALL_ROUND_CONSTANTS[i + 12 * round];
-        uint64_t t = s[i] + c;
-        s[i] = t + (t < c ? EPS : 0);
+        uint64_t t;
+        uint64_t ov = __builtin_add_overflow(s[i], c, &t);
+        s[i] = t + ((0 - ov) & EPS);
     }
 }
 
 /* poseidon.rs:178-198, 245-264 (mds_row_shf + mds_layer).  The coefficients are < 2^6, so the
  * 32-bit halves of the state can be accumulated in u64 without overflow and recombined, as
  * poseidon_goldilocks.rs:217-248 does. */
-static inline void mds_layer(uint64_t s[12]) {
+static inline __attribute__((always_inline)) void mds_layer(uint64_t s[12]) {
     uint64_t lo[12], hi[12], out[12];
+#pragma GCC unroll 12
     for (int i = 0; i < 12; i++) {
         lo[i] = s[i] & EPS;
         hi[i] = s[i] >> 32;
     }
+#pragma GCC unroll 12
     for (int r = 0; r < 12; r++) {
         uint64_t al = 0, ah = 0;
+#pragma GCC unroll 12
         for (int i = 0; i < 12; i++) {
-            int k = i + r >= 12 ? i + r - 12 : i + r;
+            const int k = (i + r) % 12;
             al += lo[k] * POSEIDON_MDS_CIRC[i];
             ah += hi[k] * POSEIDON_MDS_CIRC[i];
         }
@@ -299,6 +306,7 @@ static inline void mds_layer(uint64_t s[12]) {
 static void full_rounds(uint64_t s[12], unsigned *round) {
     for (int k = 0; k < 4; k++) {
         constant_layer(s, *round);
+#pragma GCC unroll 12
         for (int i = 0; i < 12; i++) s[i] = sbox(s[i]);
         mds_layer(s);
         (*round)++;
@@ -312,7 +320,9 @@ static void partial_rounds_fast(uint64_t s[12], unsigned *round) {
     uint64_t t[12];
     t[0] = s[0];
     for (int c = 1; c < 12; c++) t[c] = 0;
+#pragma GCC unroll 12
     for (int r = 1; r < 12; r++)
+#pragma GCC unroll 12
         for (int c = 1; c < 12; c++)
             t[c] = gl_add(t[c], gl_mul(s[r], POSEIDON_FAST_PARTIAL_ROUND_INITIAL_MATRIX[(r - 1) * 11 + (c - 1)]));
     memcpy(s, t, sizeof t);
@@ -324,6 +334,7 @@ static void partial_rounds_fast(uint64_t s[12], unsigned *round) {
          * poseidon.rs:46-52); any exact mod-p evaluation gives the same canonical value. */
         u128 acc_lo = 0;
         uint32_t acc_hi = 0;
+#pragma GCC unroll 12
         for (int j = 1; j < 12; j++) {
             u128 prod = (u128)s[j] * POSEIDON_FAST_PARTIAL_ROUND_W_HATS[i * 11 + j - 1];
             u128 n = acc_lo + prod;
@@ -338,6 +349,7 @@ static void partial_rounds_fast(uint64_t s[12], unsigned *round) {
         }
         uint64_t red_hi = reduce96((uint64_t)(acc_lo >> 64), acc_hi);
         uint64_t d = reduce128(((u128)red_hi << 64) + (uint64_t)acc_lo);
+#pragma GCC unroll 12
         for (int j = 1; j < 12; j++)
             s[j] = gl_add(s[j], gl_mul(s[0], POSEIDON_FAST_PARTIAL_ROUND_VS[i * 11 + j - 1]));
         s[0] = d;

@@ -1,0 +1,561 @@
+"""qp_plonky2_b200 -- B200-native polynomial-commitment path of Quantus-Network/qp-plonky2.
+
+Python host mirror of the reference interface for the hot path (names, argument meaning and
+error behaviour follow the Rust API; citations are reference-relative file:line):
+
+    PolynomialBatch.from_values / from_coeffs      plonky2/src/fri/oracle.rs:168-223
+    PolynomialBatch.get_lde_values                 plonky2/src/fri/oracle.rs:286-291
+    MerkleTree(leaves, cap_height) / .prove / .get plonky2/src/hash/merkle_tree.rs:163-207
+    Challenger                                     core/src/challenger.rs
+    fri_committed_trees / fri_proof_of_work        plonky2/src/fri/prover.rs:85-208
+
+Everything goes through the C ABI in include/qp_plonky2_b200.h (ctypes, plain pointers): the
+same entry points a Rust shim would bind.  There is no CPU fallback: if the
+CUDA library is not built, or no GPU is present, the calls raise.
+
+Host data are numpy uint64 arrays; device data may be passed as torch CUDA tensors (int64 or
+uint64 storage), in which case no host<->device copy of the input happens.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libqp_plonky2_b200.so")
+_SOURCES = [
+    os.path.join(_HERE, "csrc", f)
+    for f in ("qp_plonky2.cu", "goldilocks.cuh", "poseidon.cuh", "poseidon_constants.h", "ntt.cuh",
+              "merkle.cuh", "fri.cuh")
+] + [
+    os.path.join(_HERE, "host", "transcript.cpp"),
+    os.path.join(_ROOT, "include", "qp_plonky2_b200.h"),
+    os.path.join(_ROOT, "include", "qp_plonky2_host.h"),
+]
+
+P = 0xFFFFFFFF00000001
+SALT_SIZE = 4
+QP_HOST, QP_DEVICE = 0, 1
+
+ERRORS = {
+    1: "CUDA failure",
+    2: "cap_height should be at most log2(leaves.len())",
+    3: "Not a power of two",
+    4: "Polynomial degrees inconsistent",
+    5: "bad argument",
+    6: "too large",
+    7: "Cannot set blinding without salt",
+}
+
+
+class QpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("qp_plonky2_b200 error %d (%s): %s" % (code, ERRORS.get(code, "?"), msg))
+        self.code = code
+
+
+def nvcc_path():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    stale = (not os.path.exists(LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in _SOURCES
+    )
+    if not (force or stale):
+        return LIB_PATH
+    cmd = [
+        nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+        "-Xcompiler", "-fPIC", "-shared", "-o", LIB_PATH,
+        os.path.join(_HERE, "csrc", "qp_plonky2.cu"), os.path.join(_HERE, "host", "transcript.cpp"),
+    ]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+u64p = C.POINTER(C.c_uint64)
+
+
+class _ChallengerState(C.Structure):
+    _fields_ = [
+        ("sponge_state", C.c_uint64 * 12),
+        ("input_buffer", C.c_uint64 * 8),
+        ("output_buffer", C.c_uint64 * 8),
+        ("n_in", C.c_uint32),
+        ("n_out", C.c_uint32),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load the C-ABI library.  Fails loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "qp_plonky2_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'`; "
+            "there is no CPU fallback" % LIB_PATH
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, sz, i32 = C.c_void_p, C.c_uint64, C.c_uint, C.c_size_t, C.c_int
+    pp = C.POINTER(vp)
+    sig = {
+        "qp_ctx_create": (i32, [i32, vp, u32, pp]),
+        "qp_ctx_destroy": (None, [vp]),
+        "qp_last_error": (C.c_char_p, [vp]),
+        "qp_ctx_synchronize": (i32, [vp]),
+        "qp_ctx_launch_count": (u64, [vp]),
+        "qp_batch_from_values": (i32, [vp, vp, i32, sz, u32, u32, i32, u32, vp, u32, u32, pp]),
+        "qp_batch_from_coeffs": (i32, [vp, vp, i32, sz, u32, u32, i32, u32, vp, u32, u32, pp]),
+        "qp_batch_free": (None, [vp]),
+        "qp_ifft_columns": (i32, [vp, vp, i32, sz, u32, vp, i32]),
+        "qp_batch_cap": (i32, [vp, vp, i32]),
+        "qp_batch_cap_len": (sz, [vp]),
+        "qp_batch_coeffs": (i32, [vp, vp, i32]),
+        "qp_batch_digests": (i32, [vp, vp, i32]),
+        "qp_batch_digests_len": (sz, [vp]),
+        "qp_batch_leaves": (i32, [vp, sz, sz, vp, i32]),
+        "qp_batch_leaf_len": (sz, [vp]),
+        "qp_batch_get_lde_values": (i32, [vp, sz, sz, vp]),
+        "qp_batch_get_leaves": (i32, [vp, vp, u32, vp]),
+        "qp_batch_prove": (i32, [vp, sz, vp]),
+        "qp_batch_timing": (i32, [vp, C.POINTER(C.c_double)]),
+        "qp_batch_kernel_timing": (i32, [vp, C.POINTER(C.c_double)]),
+        "qp_batch_device_lde": (vp, [vp]),
+        "qp_batch_device_coeffs": (vp, [vp]),
+        "qp_merkle_tree_new": (i32, [vp, vp, i32, sz, sz, u32, pp]),
+        "qp_tree_free": (None, [vp]),
+        "qp_tree_cap": (i32, [vp, vp, i32]),
+        "qp_tree_digests": (i32, [vp, vp, i32]),
+        "qp_tree_digests_len": (sz, [vp]),
+        "qp_tree_prove": (i32, [vp, sz, vp]),
+        "qp_tree_get": (i32, [vp, sz, vp]),
+        "qp_poseidon_permute": (i32, [vp, vp, i32, sz]),
+        "qp_coset_fft": (i32, [vp, vp, i32, sz, u32, u64, i32, vp, i32]),
+        "qp_fri_begin": (i32, [vp, vp, vp, i32, u32, u32, u32, pp]),
+        "qp_fri_commit_round": (i32, [vp, u32, vp]),
+        "qp_fri_fold_round": (i32, [vp, vp, i32]),
+        "qp_fri_final_poly": (i32, [vp, vp, C.POINTER(sz)]),
+        "qp_fri_tree_get": (i32, [vp, u32, sz, vp]),
+        "qp_fri_tree_prove": (i32, [vp, u32, sz, vp]),
+        "qp_fri_tree_digests": (i32, [vp, u32, vp, i32]),
+        "qp_fri_tree_digests_len": (sz, [vp, u32]),
+        "qp_fri_num_rounds": (u32, [vp]),
+        "qp_fri_free": (None, [vp]),
+        "qp_fri_proof_of_work": (i32, [vp, vp, u32, u32, u64p]),
+        # host transcript mirror (include/qp_plonky2_host.h)
+        "qp_challenger_init": (None, [C.POINTER(_ChallengerState)]),
+        "qp_challenger_observe": (None, [C.POINTER(_ChallengerState), vp, sz]),
+        "qp_challenger_get": (u64, [C.POINTER(_ChallengerState)]),
+        "qp_fri_reduction_arity_bits": (u32, [u32, u32, u32, u32, u32, C.POINTER(u32)]),
+        "qp_fri_committed_trees": (i32, [vp, vp, vp, i32, u32, u32, u32, C.POINTER(u32), u32,
+                                         C.POINTER(_ChallengerState), vp, vp, C.POINTER(sz), pp]),
+        "qp_fri_grind": (i32, [vp, C.POINTER(_ChallengerState), u32, u64p]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    L._exported = sorted(sig)
+    _lib = L
+    return L
+
+
+# ---------------------------------------------------------------------------------------------
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _buf(x):
+    """-> (pointer, space, keepalive, shape) for numpy (host) or torch CUDA (device) arrays."""
+    if _is_torch(x):
+        assert x.is_contiguous() and x.element_size() == 8
+        space = QP_DEVICE if x.is_cuda else QP_HOST
+        return C.c_void_p(x.data_ptr()), space, x, tuple(x.shape)
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.uint64))
+    return C.c_void_p(a.ctypes.data), QP_HOST, a, a.shape
+
+
+def _np_ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One per (process, GPU): stream, twiddle table, scratch pool."""
+
+    def __init__(self, device: int = 0, max_lde_log: int = 24, stream=None):
+        self._h = C.c_void_p()
+        rc = lib().qp_ctx_create(device, C.c_void_p(stream) if stream else None, max_lde_log, C.byref(self._h))
+        if rc:
+            raise QpError(rc, "qp_ctx_create failed (no usable CUDA device? there is no CPU fallback)")
+        self.device = device
+
+    def check(self, rc):
+        if rc:
+            raise QpError(rc, lib().qp_last_error(self._h).decode())
+
+    def synchronize(self):
+        self.check(lib().qp_ctx_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().qp_ctx_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib().qp_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- primitives ----
+    def poseidon(self, states):
+        """Batch of width-12 permutations (core/src/poseidon.rs:599-609)."""
+        a = np.ascontiguousarray(np.asarray(states, dtype=np.uint64)).reshape(-1, 12).copy()
+        self.check(lib().qp_poseidon_permute(self._h, _np_ptr(a), QP_HOST, a.shape[0]))
+        return a
+
+    def coset_fft(self, coeffs, shift=1, bit_reversed=False):
+        """coset_fft_with_options (field/src/polynomial/mod.rs:280-293) of every row."""
+        p, space, keep, shape = _buf(coeffs)
+        n_vec, n = (1, shape[0]) if len(shape) == 1 else shape
+        lg = int(n).bit_length() - 1
+        if (1 << lg) != n:
+            raise QpError(3, "Not a power of two: %d" % n)
+        out = np.zeros((n_vec, n), dtype=np.uint64)
+        self.check(lib().qp_coset_fft(self._h, p, space, n_vec, lg, shift, int(bit_reversed), _np_ptr(out), QP_HOST))
+        return out.reshape(shape)
+
+    def ifft_columns(self, values, out_device=None):
+        """The "IFFT" scope alone (oracle.rs:176-180); out_device: optional torch CUDA tensor."""
+        p, space, keep, shape = _buf(values)
+        n_cols, n = shape
+        lg = int(n).bit_length() - 1
+        if (1 << lg) != n:
+            raise QpError(3, "Not a power of two: %d" % n)
+        if out_device is not None:
+            self.check(lib().qp_ifft_columns(self._h, p, space, n_cols, lg, C.c_void_p(out_device.data_ptr()), QP_DEVICE))
+            self.synchronize()
+            return out_device
+        out = np.zeros((n_cols, n), dtype=np.uint64)
+        self.check(lib().qp_ifft_columns(self._h, p, space, n_cols, lg, _np_ptr(out), QP_HOST))
+        return out
+
+
+class _Cap:
+    pass
+
+
+class BatchMerkleView:
+    """The `merkle_tree` field of a PolynomialBatch: cap / digests / leaves served from the
+    device on demand (materialising 9 GB of leaves per commit on the host would erase the win,
+    SURVEY.md section 7)."""
+
+    def __init__(self, batch):
+        self._b = batch
+
+    @property
+    def cap(self):
+        b = self._b
+        out = np.zeros((lib().qp_batch_cap_len(b._h), 4), dtype=np.uint64)
+        b.ctx.check(lib().qp_batch_cap(b._h, _np_ptr(out), QP_HOST))
+        return out
+
+    @property
+    def digests(self):
+        b = self._b
+        out = np.zeros((lib().qp_batch_digests_len(b._h), 4), dtype=np.uint64)
+        if out.size:
+            b.ctx.check(lib().qp_batch_digests(b._h, _np_ptr(out), QP_HOST))
+        return out
+
+    def leaves(self, first=0, count=None):
+        b = self._b
+        if count is None:
+            count = b.n_local_leaves - first
+        out = np.zeros((count, b.leaf_len), dtype=np.uint64)
+        if out.size:
+            b.ctx.check(lib().qp_batch_leaves(b._h, first, count, _np_ptr(out), QP_HOST))
+        return out
+
+    def get(self, i):
+        return self.leaves(i, 1)[0]
+
+    def get_many(self, indices):
+        b = self._b
+        idx = np.ascontiguousarray(np.asarray(indices, dtype=np.uint64))
+        out = np.zeros((idx.size, b.leaf_len), dtype=np.uint64)
+        b.ctx.check(lib().qp_batch_get_leaves(b._h, _np_ptr(idx), idx.size, _np_ptr(out)))
+        return out
+
+    def prove(self, leaf_index):
+        b = self._b
+        k = b.local_lg_leaves - b.local_cap_height
+        out = np.zeros((k, 4), dtype=np.uint64)
+        b.ctx.check(lib().qp_batch_prove(b._h, leaf_index, _np_ptr(out) if k else None))
+        return out
+
+
+class PolynomialBatch:
+    """plonky2/src/fri/oracle.rs:33-40.  Fields: polynomials (coefficients), merkle_tree,
+    degree_log, rate_bits, blinding.  `timing` holds the reference's four TimingTree scopes."""
+
+    SCOPES = ("IFFT", "FFT + blinding", "transpose LDEs", "build Merkle tree")
+
+    def __init__(self):
+        self._h = C.c_void_p()
+
+    @classmethod
+    def from_values(cls, ctx, values, rate_bits, blinding, cap_height, salt=None, block_first=0,
+                    block_count=None):
+        return cls._make(ctx, values, rate_bits, blinding, cap_height, salt, block_first, block_count, True)
+
+    @classmethod
+    def from_coeffs(cls, ctx, polynomials, rate_bits, blinding, cap_height, salt=None, block_first=0,
+                    block_count=None):
+        return cls._make(ctx, polynomials, rate_bits, blinding, cap_height, salt, block_first, block_count, False)
+
+    @classmethod
+    def _make(cls, ctx, data, rate_bits, blinding, cap_height, salt, block_first, block_count, is_values):
+        if not _is_torch(data):
+            # Vec<PolynomialValues>: every column must have the same length (oracle.rs:277)
+            rows = list(data) if not isinstance(data, np.ndarray) else data
+            if len(rows) == 0:
+                raise QpError(5, "polynomials[0]: index out of bounds (empty batch)")
+            if not isinstance(rows, np.ndarray) and len({len(r) for r in rows}) != 1:
+                raise QpError(4, "Polynomial degrees inconsistent")
+        p, space, keep, shape = _buf(data)
+        if len(shape) != 2:
+            raise QpError(5, "expected [n_cols][n]")
+        n_cols, n = shape
+        lg = int(n).bit_length() - 1
+        if n == 0 or (1 << lg) != n:
+            raise QpError(3, "Not a power of two: %d" % n)
+        if block_count is None:
+            block_count = 1 << rate_bits
+        sp = None
+        skeep = None
+        if blinding:
+            if salt is None:
+                raise QpError(7, "blinding=True needs salt[4][N] (the reference draws it from its RNG)")
+            sp, sspace, skeep, sshape = _buf(salt)
+            if sspace != space or tuple(sshape) != (SALT_SIZE, n << rate_bits):
+                raise QpError(5, "salt must be [4][N] in the same memory space as the data")
+        self = cls()
+        self.ctx = ctx
+        fn = lib().qp_batch_from_values if is_values else lib().qp_batch_from_coeffs
+        rc = fn(ctx._h, p, space, n_cols, lg, rate_bits, int(bool(blinding)), cap_height, sp, block_first,
+                block_count, C.byref(self._h))
+        ctx.check(rc)
+        self.n_cols, self.degree_log, self.rate_bits = n_cols, lg, rate_bits
+        self.blinding, self.cap_height = bool(blinding), cap_height
+        self.block_first, self.block_count = block_first, block_count
+        self.leaf_len = int(lib().qp_batch_leaf_len(self._h))
+        self.n_local_leaves = block_count << lg
+        self.local_lg_leaves = self.n_local_leaves.bit_length() - 1
+        self.local_cap_height = int(lib().qp_batch_cap_len(self._h)).bit_length() - 1
+        self.merkle_tree = BatchMerkleView(self)
+        ms = (C.c_double * 4)()
+        lib().qp_batch_timing(self._h, ms)
+        self.timing = dict(zip(cls.SCOPES, list(ms)))
+        lib().qp_batch_kernel_timing(self._h, ms)
+        self.kernel_ms = dict(zip(("intt", "lde", "leaf_hash", "tree_levels"), list(ms)))
+        return self
+
+    @property
+    def polynomials(self):
+        out = np.zeros((self.n_cols, 1 << self.degree_log), dtype=np.uint64)
+        self.ctx.check(lib().qp_batch_coeffs(self._h, _np_ptr(out), QP_HOST))
+        return out
+
+    def get_lde_values(self, index, step=1):
+        out = np.zeros(self.n_cols, dtype=np.uint64)
+        self.ctx.check(lib().qp_batch_get_lde_values(self._h, index, step, _np_ptr(out)))
+        return out
+
+    @property
+    def device_lde_ptr(self):
+        return lib().qp_batch_device_lde(self._h)
+
+    @property
+    def device_coeffs_ptr(self):
+        return lib().qp_batch_device_coeffs(self._h)
+
+    def free(self):
+        if self._h:
+            lib().qp_batch_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class MerkleTree:
+    """plonky2/src/hash/merkle_tree.rs:163-207 on caller-provided leaf-major rows."""
+
+    def __init__(self, ctx, leaves, cap_height):
+        self._h = C.c_void_p()
+        self.ctx = ctx
+        if not _is_torch(leaves) and not isinstance(leaves, np.ndarray):
+            leaves = list(leaves)
+            if len({len(r) for r in leaves}) > 1:
+                raise QpError(5, "ragged leaves are not supported by the device path")
+            leaves = np.asarray(leaves, dtype=np.uint64).reshape(len(leaves), -1)
+        p, space, keep, shape = _buf(leaves)
+        n, L = shape
+        self.n_leaves, self.leaf_len, self.cap_height = n, L, cap_height
+        ctx.check(lib().qp_merkle_tree_new(ctx._h, p, space, n, L, cap_height, C.byref(self._h)))
+
+    @property
+    def cap(self):
+        out = np.zeros((1 << self.cap_height, 4), dtype=np.uint64)
+        self.ctx.check(lib().qp_tree_cap(self._h, _np_ptr(out), QP_HOST))
+        return out
+
+    @property
+    def digests(self):
+        out = np.zeros((lib().qp_tree_digests_len(self._h), 4), dtype=np.uint64)
+        if out.size:
+            self.ctx.check(lib().qp_tree_digests(self._h, _np_ptr(out), QP_HOST))
+        return out
+
+    def get(self, i):
+        out = np.zeros(self.leaf_len, dtype=np.uint64)
+        self.ctx.check(lib().qp_tree_get(self._h, i, _np_ptr(out) if out.size else None))
+        return out
+
+    def prove(self, i):
+        k = self.n_leaves.bit_length() - 1 - self.cap_height
+        out = np.zeros((k, 4), dtype=np.uint64)
+        self.ctx.check(lib().qp_tree_prove(self._h, i, _np_ptr(out) if k else None))
+        return out
+
+    def free(self):
+        if self._h:
+            lib().qp_tree_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Challenger:
+    """core/src/challenger.rs -- host-side duplex sponge (see include/qp_plonky2_host.h)."""
+
+    def __init__(self):
+        self._s = _ChallengerState()
+        lib().qp_challenger_init(C.byref(self._s))
+
+    def observe_elements(self, elems):
+        a = np.ascontiguousarray(np.asarray(elems, dtype=np.uint64).reshape(-1))
+        if a.size:
+            lib().qp_challenger_observe(C.byref(self._s), _np_ptr(a), a.size)
+
+    observe_cap = observe_elements
+
+    def observe_element(self, e):
+        self.observe_elements([e])
+
+    def get_challenge(self) -> int:
+        return int(lib().qp_challenger_get(C.byref(self._s)))
+
+    def get_n_challenges(self, n):
+        return [self.get_challenge() for _ in range(n)]
+
+    def get_extension_challenge(self):
+        return (self.get_challenge(), self.get_challenge())
+
+
+def fri_reduction_arity_bits(degree_bits, rate_bits, cap_height, arity_bits=4, final_poly_bits=5):
+    """FriReductionStrategy::ConstantArityBits (core/src/fri.rs:50-61)."""
+    out = (C.c_uint * 64)()
+    k = lib().qp_fri_reduction_arity_bits(degree_bits, rate_bits, cap_height, arity_bits, final_poly_bits, out)
+    return [int(out[i]) for i in range(k)]
+
+
+class FriCommitment:
+    """Result of fri_committed_trees: per-round trees (device-resident) + final polynomial."""
+
+    def __init__(self, ctx, handle, caps, final_poly, arity_bits, lg_n, cap_height):
+        self.ctx, self._h = ctx, handle
+        self.caps, self.final_poly = caps, final_poly
+        self.arity_bits, self.lg_n, self.cap_height = list(arity_bits), lg_n, cap_height
+
+    def tree_get(self, rnd, leaf_index):
+        out = np.zeros(2 << self.arity_bits[rnd], dtype=np.uint64)
+        self.ctx.check(lib().qp_fri_tree_get(self._h, rnd, leaf_index, _np_ptr(out)))
+        return out
+
+    def tree_prove(self, rnd, leaf_index):
+        lg = self.lg_n - sum(self.arity_bits[: rnd + 1])
+        k = lg - self.cap_height
+        out = np.zeros((k, 4), dtype=np.uint64)
+        self.ctx.check(lib().qp_fri_tree_prove(self._h, rnd, leaf_index, _np_ptr(out) if k else None))
+        return out
+
+    def tree_digests(self, rnd):
+        out = np.zeros((lib().qp_fri_tree_digests_len(self._h, rnd), 4), dtype=np.uint64)
+        if out.size:
+            self.ctx.check(lib().qp_fri_tree_digests(self._h, rnd, _np_ptr(out), QP_HOST))
+        return out
+
+    def free(self):
+        if self._h:
+            lib().qp_fri_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def fri_committed_trees(ctx, coeffs, values, challenger, rate_bits, cap_height, arity_bits):
+    """plonky2/src/fri/prover.rs:85-143.  coeffs/values: F_p^2 arrays [n][2] (natural order)."""
+    pc, space, k1, shape = _buf(coeffs)
+    pv, space2, k2, shape2 = _buf(values)
+    if space != space2 or tuple(shape) != tuple(shape2) or len(shape) != 2 or shape[1] != 2:
+        raise QpError(5, "coeffs/values must both be [n][2] in the same memory space")
+    n = shape[0]
+    lg = int(n).bit_length() - 1
+    if n == 0 or (1 << lg) != n:
+        raise QpError(3, "Not a power of two: %d" % n)
+    R = len(arity_bits)
+    caps = np.zeros((R, 1 << cap_height, 4), dtype=np.uint64)
+    tot = sum(arity_bits)
+    final = np.zeros(((n >> tot) >> rate_bits, 2), dtype=np.uint64)
+    ab = (C.c_uint * max(R, 1))(*arity_bits)
+    h = C.c_void_p()
+    flen = C.c_size_t()
+    rc = lib().qp_fri_committed_trees(ctx._h, pc, pv, space, lg, rate_bits, cap_height, ab, R,
+                                      C.byref(challenger._s), _np_ptr(caps), _np_ptr(final) if final.size else None,
+                                      C.byref(flen), C.byref(h))
+    ctx.check(rc)
+    return FriCommitment(ctx, h, caps, final, arity_bits, lg, cap_height)
+
+
+def fri_proof_of_work(ctx, challenger, proof_of_work_bits) -> int:
+    """plonky2/src/fri/prover.rs:159-208, smallest-witness rule."""
+    w = C.c_uint64()
+    ctx.check(lib().qp_fri_grind(ctx._h, C.byref(challenger._s), proof_of_work_bits, C.byref(w)))
+    return int(w.value)

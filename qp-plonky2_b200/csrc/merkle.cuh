@@ -1,0 +1,156 @@
+// Poseidon Merkle tree kernels: leaf hashing straight off the (column-major, leaf-ordered) LDE,
+// internal levels, cap -- digests written in the reference's interleaved layout.
+//
+// Reference semantics:
+//   hash_leaf   core/src/hashing.rs:150-168   state[8] = len+1, overwrite-mode absorb of 8-chunks
+//   two_to_one  core/src/hashing.rs:47-64     [l0..l3, r0..r3, 0,0,0,0] -> permute -> [0..4)
+//   layout      plonky2/src/hash/merkle_tree.rs:56-83,121-160: per cap-subtree block, node k of
+//               layer l (0 = leaf digests) lives at 2*((k>>1) << (l+1)) + 2*(2^l - 1) + (k&1);
+//               subtree roots go to `cap`.
+#pragma once
+#include "poseidon.cuh"
+
+namespace merkle {
+
+struct TreeShape {
+    unsigned lg_leaves;   // log2(#leaves)
+    unsigned cap_height;
+    __host__ __device__ unsigned num_layers() const { return lg_leaves - cap_height; }
+    __host__ __device__ size_t sub_digests() const {  // digests per cap subtree
+        return 2 * (((size_t)1 << num_layers()) - 1);
+    }
+};
+
+
+// Slot (in digests, units of 4 u64) of node k of `layer` inside subtree t; layer < num_layers.
+__device__ __forceinline__ size_t digest_slot(const TreeShape& sh, unsigned layer, size_t t, size_t k) {
+    return t * sh.sub_digests() + 2 * ((k >> 1) << (layer + 1)) + 2 * (((size_t)1 << layer) - 1) + (k & 1);
+}
+
+__device__ __forceinline__ void store_digest(uint64_t* dst, const uint64_t (&s)[12]) {
+    ulonglong2 a, b;
+    a.x = gl::canon(s[0]);
+    a.y = gl::canon(s[1]);
+    b.x = gl::canon(s[2]);
+    b.y = gl::canon(s[3]);
+    reinterpret_cast<ulonglong2*>(dst)[0] = a;
+    reinterpret_cast<ulonglong2*>(dst)[1] = b;
+}
+
+// Where leaf i's digest goes: layer 0 of its subtree, or straight into the cap if the tree is
+// all cap (merkle_tree.rs:94-103).
+__device__ __forceinline__ uint64_t* leaf_digest_ptr(const TreeShape& sh, uint64_t* digests,
+                                                     uint64_t* cap, size_t i) {
+    const unsigned nl = sh.num_layers();
+    if (nl == 0) return cap + 4 * i;
+    const size_t t = i >> nl, k = i & (((size_t)1 << nl) - 1);
+    return digests + 4 * digest_slot(sh, 0, t, k);
+}
+
+// Where the elements of a leaf live.
+//   AffineLayout: element c of leaf i = data[c * col_stride + i * row_stride]
+//       column-major LDE (the commit path):    col_stride = N, row_stride = 1  (coalesced across the warp)
+//       leaf-major rows (MerkleTree::new API): col_stride = 1, row_stride = leaf_len
+//   ExtPlanesLayout: FRI commit leaves = 2^arity_bits consecutive F_p^2 values flattened
+//       (flatten, field/src/extension/mod.rs:129-138) out of two coordinate planes.
+struct AffineLayout {
+    const uint64_t* data;
+    size_t col_stride, row_stride;
+    __device__ __forceinline__ uint64_t get(size_t i, unsigned c) const {
+        return data[(size_t)c * col_stride + i * row_stride];
+    }
+};
+struct ExtPlanesLayout {
+    const uint64_t* planes;
+    size_t n;
+    unsigned arity_bits;
+    __device__ __forceinline__ uint64_t get(size_t i, unsigned c) const {
+        return planes[(size_t)(c & 1) * n + (i << arity_bits) + (c >> 1)];
+    }
+};
+
+// One thread per leaf.
+template <class Layout>
+__global__ void __launch_bounds__(128)
+leaf_hash_kernel(Layout lay, unsigned leaf_len, TreeShape sh, uint64_t* __restrict__ digests,
+                 uint64_t* __restrict__ cap) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ((size_t)1 << sh.lg_leaves)) return;
+    uint64_t s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = 0;
+    s[8] = (uint64_t)leaf_len + 1;
+    // hashing.rs:160-163: one permutation per 8-chunk, the last chunk may be short (its missing
+    // lanes keep the previous state).  Software pipeline: fetch chunk ch+1 while permuting ch.
+    const unsigned n_chunks = (leaf_len + 7) / 8;
+    uint64_t nxt[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        if ((unsigned)k < leaf_len) nxt[k] = lay.get(i, k);
+#pragma unroll 1
+    for (unsigned ch = 0; ch < n_chunks; ch++) {
+        const unsigned c = ch * 8;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (c + k < leaf_len) s[k] = nxt[k];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (c + 8 + k < leaf_len) nxt[k] = lay.get(i, c + 8 + k);
+        poseidon::permute(s);
+    }
+    store_digest(leaf_digest_ptr(sh, digests, cap, i), s);
+}
+
+// One thread per node of `layer` (1 <= layer <= num_layers): two_to_one of its children.
+__global__ void __launch_bounds__(128)
+tree_level_kernel(TreeShape sh, unsigned layer, uint64_t* __restrict__ digests,
+                  uint64_t* __restrict__ cap) {
+    const unsigned nl = sh.num_layers();
+    const size_t per_sub = (size_t)1 << (nl - layer);
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (per_sub << sh.cap_height)) return;
+    const size_t t = idx >> (nl - layer), k = idx & (per_sub - 1);
+    // children = the sibling pair k of layer-1: adjacent, left first
+    const uint64_t* ch = digests + 4 * digest_slot(sh, layer - 1, t, 2 * k);
+    uint64_t s[12];
+    const ulonglong2* c2 = reinterpret_cast<const ulonglong2*>(ch);
+    ulonglong2 v0 = c2[0], v1 = c2[1], v2 = c2[2], v3 = c2[3];
+    s[0] = v0.x; s[1] = v0.y; s[2] = v1.x; s[3] = v1.y;
+    s[4] = v2.x; s[5] = v2.y; s[6] = v3.x; s[7] = v3.y;
+    s[8] = s[9] = s[10] = s[11] = 0;
+    poseidon::permute(s);
+    uint64_t* out = (layer == nl) ? cap + 4 * t : digests + 4 * digest_slot(sh, layer, t, k);
+    store_digest(out, s);
+}
+
+// Merkle opening: siblings bottom-up (merkle_tree.rs:121-160).  One thread per (query, layer).
+__global__ void merkle_paths_kernel(TreeShape sh, const uint64_t* __restrict__ digests,
+                                    const uint64_t* __restrict__ leaf_indices, unsigned n_queries,
+                                    uint64_t* __restrict__ out /* [n_queries][num_layers][4] */) {
+    const unsigned nl = sh.num_layers();
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_queries * nl) return;
+    const unsigned qy = id / nl, layer = id % nl;
+    const size_t leaf = leaf_indices[qy];
+    const size_t t = leaf >> nl, k = (leaf & (((size_t)1 << nl) - 1)) >> layer;
+    const uint64_t* srcp = digests + 4 * digest_slot(sh, layer, t, k ^ 1);
+    uint64_t* dst = out + 4 * ((size_t)qy * nl + layer);
+#pragma unroll
+    for (int e = 0; e < 4; e++) dst[e] = srcp[e];
+}
+
+// Gather whole leaves (rows): out[q][c] = element c of leaf idx[q] (canonical).
+template <class Layout>
+__global__ void gather_rows_kernel(Layout lay, unsigned leaf_len,
+                                   const uint64_t* __restrict__ leaf_indices, size_t first,
+                                   size_t n_rows, uint64_t* __restrict__ out) {
+    const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_rows * leaf_len) return;
+    const size_t qy = id / leaf_len;
+    const unsigned c = (unsigned)(id % leaf_len);
+    const size_t leaf = leaf_indices ? (size_t)leaf_indices[qy] : first + qy;
+    out[id] = gl::canon(lay.get(leaf, c));
+}
+
+
+}  // namespace merkle

@@ -1,0 +1,1163 @@
+// qp_plonky2_b200: C-ABI library (include/qp_plonky2_b200.h) over the sm_100a kernels.
+// Single translation unit: the __constant__ round-constant table is shared by every kernel.
+//
+// There is no CPU data path in this file: host code only plans launches, owns handles and
+// moves bytes.  If no CUDA device is usable every entry point returns QP_ERR_CUDA.
+#include "../../include/qp_plonky2_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fri.cuh"
+#include "goldilocks.cuh"
+#include "merkle.cuh"
+#include "ntt.cuh"
+#include "poseidon.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct ScaleTables {
+    uint64_t* lo = nullptr;  // [n_inner][2^split]
+    uint64_t* hi = nullptr;  // [n_inner][2^(L-split)]
+    int split = 0;
+};
+
+struct qp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t* tw = nullptr;  // tw[(1<<lg)+e] = w_{2^lg}^e, e < 2^lg
+    unsigned tw_lg = 0;
+    uint64_t launches = 0;
+    std::string err;
+    std::mutex mu;
+    // coset scale tables keyed by (L, rate_bits, block_first, block_count) for the LDE
+    std::map<std::vector<uint64_t>, ScaleTables> scale_cache;
+    cudaEvent_t ev[8] = {};
+};
+
+#define CUDA_TRY(ctx, expr)                                                                  \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                 \
+            return QP_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                                          \
+    do {                                                                                     \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                     \
+        (ctx)->launches++;                                                                   \
+        cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e != cudaSuccess) {                                                             \
+            (ctx)->err = std::string(#kernel) + ": " + cudaGetErrorString(_e);               \
+            return QP_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+static int fail(qp_ctx* ctx, int code, const char* msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+// stream-ordered allocations from the device's default pool (kept cached between commits)
+static int dev_alloc(qp_ctx* ctx, uint64_t** p, size_t n_words) {
+    *p = nullptr;
+    if (n_words == 0) return QP_OK;
+    cudaError_t e = cudaMallocAsync((void**)p, n_words * 8, ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaMallocAsync: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? QP_ERR_TOO_LARGE : QP_ERR_CUDA;
+    }
+    return QP_OK;
+}
+static void dev_free(qp_ctx* ctx, uint64_t* p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+static int copy_out(qp_ctx* ctx, uint64_t* dst, int space, const uint64_t* src_dev, size_t n_words) {
+    if (!dst) return fail(ctx, QP_ERR_BAD_ARG, "null output buffer");
+    if (n_words == 0) return QP_OK;
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst, src_dev, n_words * 8,
+                                  space == QP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    if (space != QP_DEVICE) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return QP_OK;
+}
+
+// caller buffer -> device pointer (copying if it is host memory); *owned tells who frees
+static int to_device(qp_ctx* ctx, const uint64_t* p, int space, size_t n_words, const uint64_t** dev,
+                     uint64_t** owned) {
+    *owned = nullptr;
+    if (!p && n_words) return fail(ctx, QP_ERR_BAD_ARG, "null input buffer");
+    if (space == QP_DEVICE) {
+        *dev = p;
+        return QP_OK;
+    }
+    int rc = dev_alloc(ctx, owned, n_words);
+    if (rc) return rc;
+    if (n_words)
+        CUDA_TRY(ctx, cudaMemcpyAsync(*owned, p, n_words * 8, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = *owned;
+    return QP_OK;
+}
+
+// ---- table construction kernels -------------------------------------------------------------
+// tw[(1<<lg) + e] = w_{2^lg}^e.  One thread per entry: e-th power by square-and-multiply of the
+// level's generator (host-computed, passed in gens[lg]).
+__global__ void build_twiddles_kernel(uint64_t* tw, unsigned max_lg, const uint64_t* gens) {
+    const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= ((size_t)2 << max_lg)) return;
+    if (id == 0) {
+        tw[0] = 0;
+        return;
+    }
+    const unsigned lg = 63 - __clzll((long long)id);
+    const uint64_t e = id - ((uint64_t)1 << lg);
+    tw[id] = gl::canon(gl::pow(gens[lg], e));
+}
+
+// lo[q][c] = s_q^c, hi[q][t] = s_q^(t << split)
+__global__ void build_scale_kernel(uint64_t* lo, uint64_t* hi, const uint64_t* shifts, unsigned n_inner,
+                                   int L, int split) {
+    const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n_lo = (size_t)1 << split, n_hi = (size_t)1 << (L - split);
+    if (id < n_inner * n_lo) {
+        const unsigned q = id >> split;
+        lo[id] = gl::canon(gl::pow(shifts[q], id & (n_lo - 1)));
+    } else if (id < n_inner * (n_lo + n_hi)) {
+        const size_t k = id - n_inner * n_lo;
+        const unsigned q = k >> (L - split);
+        hi[k] = gl::canon(gl::pow(shifts[q], (k & (n_hi - 1)) << split));
+    }
+}
+
+// out[i] = in[bitrev(i)] for `n_vec` vectors of 2^lg elements (canonicalising)
+__global__ void bitrev_permute_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
+                                      unsigned lg, size_t n_vec) {
+    const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (n_vec << lg)) return;
+    const size_t v = id >> lg, i = id & (((size_t)1 << lg) - 1);
+    const size_t src = lg ? (size_t)(__brevll((unsigned long long)i) >> (64 - lg)) : 0;
+    out[id] = gl::canon(in[(v << lg) + src]);
+}
+
+// salt columns: dst[k][i_loc] = salt[k][bitrev_lgN(first_leaf + i_loc)]
+__global__ void salt_to_leaf_order_kernel(const uint64_t* __restrict__ salt, uint64_t* __restrict__ dst,
+                                          unsigned lg_N, size_t first_leaf, size_t n_loc) {
+    const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= QP_SALT_SIZE * n_loc) return;
+    const size_t k = id / n_loc, i = id % n_loc;
+    const size_t leaf = first_leaf + i;
+    const size_t src = lg_N ? (size_t)(__brevll((unsigned long long)leaf) >> (64 - lg_N)) : 0;
+    dst[id] = gl::canon(salt[(k << lg_N) + src]);
+}
+
+__global__ void __launch_bounds__(128) permute_states_kernel(uint64_t* states, size_t count) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint64_t s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = states[i * 12 + k];
+    poseidon::permute(s);
+#pragma unroll
+    for (int k = 0; k < 12; k++) states[i * 12 + k] = gl::canon(s[k]);
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int qp_ctx_create(int device, void* stream, unsigned max_lde_log, qp_ctx** out) {
+    if (!out) return QP_ERR_BAD_ARG;
+    *out = nullptr;
+    if (max_lde_log > 32) return QP_ERR_TOO_LARGE;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) {
+        cudaGetLastError();
+        return QP_ERR_CUDA;
+    }
+    qp_ctx* ctx = new qp_ctx();
+    ctx->device = device;
+    CUDA_TRY(ctx, cudaSetDevice(device));
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete ctx;
+            return QP_ERR_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    for (auto& e : ctx->ev) cudaEventCreate(&e);
+    // keep freed blocks cached in the pool: commits allocate and free multi-GB buffers
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    // ALL_ROUND_CONSTANTS -> constant memory (core/src/poseidon.rs:57-155)
+    cudaError_t e = cudaMemcpyToSymbolAsync(poseidon::c_round_constants, POSEIDON_ALL_ROUND_CONSTANTS,
+                                            sizeof(POSEIDON_ALL_ROUND_CONSTANTS), 0,
+                                            cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return QP_ERR_CUDA;
+    }
+    // twiddle table of full rows up to max_lde_log (fft_root_table, field/src/fft.rs:14-33)
+    unsigned lg = max_lde_log < 1 ? 1 : max_lde_log;
+    ctx->tw_lg = lg;
+    int rc = dev_alloc(ctx, &ctx->tw, (size_t)2 << lg);
+    if (rc) {
+        delete ctx;
+        return rc;
+    }
+    uint64_t gens[33];
+    for (unsigned k = 0; k <= 32; k++) gens[k] = gl::host_primitive_root(k);
+    uint64_t* d_gens = nullptr;
+    rc = dev_alloc(ctx, &d_gens, 33);
+    if (rc) {
+        delete ctx;
+        return rc;
+    }
+    cudaMemcpyAsync(d_gens, gens, sizeof gens, cudaMemcpyHostToDevice, ctx->stream);
+    build_twiddles_kernel<<<cdiv((size_t)2 << lg, 256), 256, 0, ctx->stream>>>(ctx->tw, lg, d_gens);
+    ctx->launches++;
+    dev_free(ctx, d_gens);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+        delete ctx;
+        return QP_ERR_CUDA;
+    }
+    *out = ctx;
+    return QP_OK;
+}
+
+extern "C" void qp_ctx_destroy(qp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->scale_cache) {
+        cudaFree(kv.second.lo);
+        cudaFree(kv.second.hi);
+    }
+    cudaFreeAsync(ctx->tw, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& e : ctx->ev) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* qp_last_error(const qp_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+extern "C" int qp_ctx_synchronize(qp_ctx* ctx) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return QP_OK;
+}
+extern "C" uint64_t qp_ctx_launch_count(const qp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// NTT driver
+// ---------------------------------------------------------------------------------------------
+struct NttJob {
+    const uint64_t* src = nullptr;
+    uint64_t* dst = nullptr;
+    int L = 0;
+    unsigned n_vec = 1;
+    int inner_bits = 0;
+    size_t src_outer = 0, src_inner = 0, dst_outer = 0, dst_inner = 0;
+    const ScaleTables* scale = nullptr;
+    int out_mode = ntt::OUT_NATURAL;
+};
+
+template <int K>
+static int launch_strided(qp_ctx* ctx, const ntt::PassParams& p) {
+    const unsigned grid = p.n_vec << (p.L - ntt::TILE_LOG);
+    LAUNCH(ctx, ntt::strided_pass_kernel<K>, grid, ntt::THREADS, ntt::SMEM_ELEMS * 8, p);
+    return QP_OK;
+}
+template <int K>
+static int launch_final(qp_ctx* ctx, const ntt::PassParams& p) {
+    const size_t chunks = (size_t)p.n_vec << (p.L - K);
+    const unsigned grid = cdiv(chunks, (size_t)1 << (ntt::TILE_LOG - K));
+    LAUNCH(ctx, ntt::final_pass_kernel<K>, grid, ntt::THREADS, ntt::SMEM_ELEMS * 8, p);
+    return QP_OK;
+}
+
+static int dispatch_strided(qp_ctx* ctx, int K, const ntt::PassParams& p) {
+    switch (K) {
+        case 1: return launch_strided<1>(ctx, p);
+        case 2: return launch_strided<2>(ctx, p);
+        case 3: return launch_strided<3>(ctx, p);
+        case 4: return launch_strided<4>(ctx, p);
+        case 5: return launch_strided<5>(ctx, p);
+        case 6: return launch_strided<6>(ctx, p);
+        case 7: return launch_strided<7>(ctx, p);
+        case 8: return launch_strided<8>(ctx, p);
+        case 9: return launch_strided<9>(ctx, p);
+        case 10: return launch_strided<10>(ctx, p);
+    }
+    return fail(ctx, QP_ERR_BAD_ARG, "bad strided K");
+}
+static int dispatch_final(qp_ctx* ctx, int K, const ntt::PassParams& p) {
+    switch (K) {
+        case 0: return launch_final<0>(ctx, p);
+        case 1: return launch_final<1>(ctx, p);
+        case 2: return launch_final<2>(ctx, p);
+        case 3: return launch_final<3>(ctx, p);
+        case 4: return launch_final<4>(ctx, p);
+        case 5: return launch_final<5>(ctx, p);
+        case 6: return launch_final<6>(ctx, p);
+        case 7: return launch_final<7>(ctx, p);
+        case 8: return launch_final<8>(ctx, p);
+        case 9: return launch_final<9>(ctx, p);
+        case 10: return launch_final<10>(ctx, p);
+        case 11: return launch_final<11>(ctx, p);
+        case 12: return launch_final<12>(ctx, p);
+    }
+    return fail(ctx, QP_ERR_BAD_ARG, "bad final K");
+}
+
+// Forward DIF transform of every vector; result at dst in bit-reversed order (OUT_NATURAL means
+// "leave each element where DIF puts it") or as inverse-transform coefficients (OUT_INVERSE).
+static int run_ntt(qp_ctx* ctx, const NttJob& job) {
+    if ((unsigned)job.L > ctx->tw_lg) return fail(ctx, QP_ERR_TOO_LARGE, "transform larger than the context's twiddle table");
+    if (job.n_vec == 0) return QP_OK;
+    const int L = job.L;
+    // The final pass handles the last Kf stages.  Natural output: Kf = 12 (one contiguous tile
+    // per CTA).  Inverse output: Kf = 10 so that 4 chunks per CTA give 32-byte store runs.
+    int Kf = (job.out_mode == ntt::OUT_INVERSE) ? 10 : 12;
+    if (L <= ntt::TILE_LOG) Kf = L;
+    // strided passes above it: K <= kmax so that the tile keeps >= 2^(12-kmax) contiguous columns
+    const int kmax = (job.out_mode == ntt::OUT_INVERSE) ? 10 : 8;
+    const int rem = L - Kf;
+    const int n_strided = rem > 0 ? (rem + kmax - 1) / kmax : 0;
+    ntt::PassParams p{};
+    p.tw = ctx->tw;
+    p.L = L;
+    p.n_vec = job.n_vec;
+    p.inner_bits = job.inner_bits;
+    p.out_mode = job.out_mode;
+    p.n_inv = gl::P - ((gl::P - 1) >> L);  // inverse_2exp, field/src/types.rs:239-278
+    bool first = true;
+    int s_hi = L;  // stages [s_lo, s_hi) remain above
+    for (int i = 0; i < n_strided; i++) {
+        const int K = rem / n_strided + (i < rem % n_strided ? 1 : 0);
+        const int s_lo = s_hi - K;
+        if (s_lo < ntt::TILE_LOG - K) return fail(ctx, QP_ERR_BAD_ARG, "internal: strided tile wider than block");
+        p.s_lo = s_lo;
+        p.src = first ? job.src : job.dst;
+        p.dst = job.dst;
+        p.src_outer_stride = first ? job.src_outer : job.dst_outer;
+        p.src_inner_stride = first ? job.src_inner : job.dst_inner;
+        p.dst_outer_stride = job.dst_outer;
+        p.dst_inner_stride = job.dst_inner;
+        p.scale_lo = (first && job.scale) ? job.scale->lo : nullptr;
+        p.scale_hi = (first && job.scale) ? job.scale->hi : nullptr;
+        p.scale_split = job.scale ? job.scale->split : 0;
+        int rc = dispatch_strided(ctx, K, p);
+        if (rc) return rc;
+        first = false;
+        s_hi = s_lo;
+    }
+    p.s_lo = 0;
+    p.src = first ? job.src : job.dst;
+    p.dst = job.dst;
+    p.src_outer_stride = first ? job.src_outer : job.dst_outer;
+    p.src_inner_stride = first ? job.src_inner : job.dst_inner;
+    p.dst_outer_stride = job.dst_outer;
+    p.dst_inner_stride = job.dst_inner;
+    p.scale_lo = (first && job.scale) ? job.scale->lo : nullptr;
+    p.scale_hi = (first && job.scale) ? job.scale->hi : nullptr;
+    p.scale_split = job.scale ? job.scale->split : 0;
+    return dispatch_final(ctx, Kf, p);
+}
+
+// Scale tables for x_i *= shift_q^i, q < n_inner (shifts on host).
+static int build_scale(qp_ctx* ctx, int L, const std::vector<uint64_t>& shifts, ScaleTables* out) {
+    const unsigned n_inner = (unsigned)shifts.size();
+    out->split = L / 2;
+    const size_t n_lo = (size_t)1 << out->split, n_hi = (size_t)1 << (L - out->split);
+    CUDA_TRY(ctx, cudaMalloc((void**)&out->lo, n_inner * n_lo * 8));
+    CUDA_TRY(ctx, cudaMalloc((void**)&out->hi, n_inner * n_hi * 8));
+    uint64_t* d_shifts = nullptr;
+    int rc = dev_alloc(ctx, &d_shifts, n_inner);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_shifts, shifts.data(), n_inner * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // `shifts` may die before the copy runs
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    LAUNCH(ctx, build_scale_kernel, cdiv(n_inner * (n_lo + n_hi), 256), 256, 0, out->lo, out->hi, d_shifts,
+           n_inner, L, out->split);
+    dev_free(ctx, d_shifts);
+    return QP_OK;
+}
+
+static void free_scale(ScaleTables* s) {
+    cudaFree(s->lo);
+    cudaFree(s->hi);
+    s->lo = s->hi = nullptr;
+}
+
+static unsigned host_bitrev(unsigned x, unsigned bits) {
+    unsigned r = 0;
+    for (unsigned i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
+
+// Coset tables of the LDE: leaf-order block q is the coset g * w_N^bitrev_r(q) (see ntt.cuh).
+static int lde_scale(qp_ctx* ctx, int L, unsigned rate_bits, unsigned block_first, unsigned block_count,
+                     const ScaleTables** out) {
+    std::vector<uint64_t> key = {(uint64_t)L, rate_bits, block_first, block_count};
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    auto it = ctx->scale_cache.find(key);
+    if (it == ctx->scale_cache.end()) {
+        const uint64_t wN = gl::host_primitive_root(L + rate_bits);
+        std::vector<uint64_t> shifts(block_count);
+        for (unsigned b = 0; b < block_count; b++)
+            shifts[b] = gl::host_mul(gl::GENERATOR, gl::host_pow(wN, host_bitrev(block_first + b, rate_bits)));
+        ScaleTables st;
+        int rc = build_scale(ctx, L, shifts, &st);
+        if (rc) return rc;
+        it = ctx->scale_cache.emplace(key, st).first;
+    }
+    *out = &it->second;
+    return QP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Merkle driver
+// ---------------------------------------------------------------------------------------------
+struct TreeBuf {
+    merkle::TreeShape shape{0, 0};
+    uint64_t* digests = nullptr;  // [n_digests][4]
+    uint64_t* cap = nullptr;      // [2^cap_height][4]
+    size_t n_digests() const { return 2 * (((size_t)1 << shape.lg_leaves) - ((size_t)1 << shape.cap_height)); }
+    size_t n_cap() const { return (size_t)1 << shape.cap_height; }
+};
+
+template <class Layout>
+static int build_tree(qp_ctx* ctx, Layout lay, unsigned leaf_len, TreeBuf* t, cudaEvent_t after_leaves = nullptr) {
+    int rc = dev_alloc(ctx, &t->digests, t->n_digests() * 4);
+    if (rc) return rc;
+    rc = dev_alloc(ctx, &t->cap, t->n_cap() * 4);
+    if (rc) return rc;
+    const size_t n_leaves = (size_t)1 << t->shape.lg_leaves;
+    LAUNCH(ctx, merkle::leaf_hash_kernel<Layout>, cdiv(n_leaves, 128), 128, 0, lay, leaf_len, t->shape,
+           t->digests, t->cap);
+    if (after_leaves) cudaEventRecord(after_leaves, ctx->stream);
+    const unsigned nl = t->shape.num_layers();
+    for (unsigned layer = 1; layer <= nl; layer++) {
+        const size_t nodes = (size_t)1 << (t->shape.lg_leaves - layer);
+        LAUNCH(ctx, merkle::tree_level_kernel, cdiv(nodes, 128), 128, 0, t->shape, layer, t->digests, t->cap);
+    }
+    return QP_OK;
+}
+
+static int tree_prove(qp_ctx* ctx, const TreeBuf& t, size_t leaf_index, uint64_t* siblings_out) {
+    if (!siblings_out && t.shape.num_layers()) return fail(ctx, QP_ERR_BAD_ARG, "null output buffer");
+    if (leaf_index >> t.shape.lg_leaves) return fail(ctx, QP_ERR_BAD_ARG, "leaf index out of range");
+    const unsigned nl = t.shape.num_layers();
+    if (nl == 0) return QP_OK;
+    uint64_t* d_idx = nullptr;
+    uint64_t* d_out = nullptr;
+    int rc = dev_alloc(ctx, &d_idx, 1);
+    if (rc) return rc;
+    rc = dev_alloc(ctx, &d_out, (size_t)nl * 4);
+    if (rc) return rc;
+    uint64_t idx = leaf_index;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_idx, &idx, 8, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, merkle::merkle_paths_kernel, cdiv(nl, 64), 64, 0, t.shape, t.digests, d_idx, 1u, d_out);
+    rc = copy_out(ctx, siblings_out, QP_HOST, d_out, (size_t)nl * 4);
+    dev_free(ctx, d_idx);
+    dev_free(ctx, d_out);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PolynomialBatch
+// ---------------------------------------------------------------------------------------------
+struct qp_batch {
+    qp_ctx* ctx = nullptr;
+    size_t n_cols = 0;
+    unsigned degree_log = 0, rate_bits = 0, cap_height = 0;  // global parameters
+    bool blinding = false;
+    unsigned block_first = 0, block_count = 0;
+    size_t leaf_len = 0;     // n_cols (+4 when blinding)
+    size_t n_local = 0;      // local leaves = block_count << degree_log
+    uint64_t* coeffs = nullptr;  // [n_cols][n]
+    uint64_t* lde = nullptr;     // [leaf_len][n_local], leaf order
+    TreeBuf tree;                // local tree: lg_leaves = log2(n_local), local cap height
+    float ms[4] = {0, 0, 0, 0};
+    float ms_leaf_hash = 0, ms_tree_levels = 0;
+};
+
+static bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
+static unsigned ilog2(size_t x) {
+    unsigned k = 0;
+    while (((size_t)1 << k) < x) k++;
+    return k;
+}
+
+// from_coeffs on device-resident coefficients (takes ownership of d_coeffs)
+static int batch_from_device_coeffs(qp_ctx* ctx, uint64_t* d_coeffs, size_t n_cols, unsigned degree_log,
+                                    unsigned rate_bits, int blinding, unsigned cap_height,
+                                    const uint64_t* salt_dev, unsigned block_first, unsigned block_count,
+                                    float ifft_ms, qp_batch** out) {
+    const size_t n = (size_t)1 << degree_log;
+    qp_batch* b = new qp_batch();
+    b->ctx = ctx;
+    b->n_cols = n_cols;
+    b->degree_log = degree_log;
+    b->rate_bits = rate_bits;
+    b->cap_height = cap_height;
+    b->blinding = blinding != 0;
+    b->block_first = block_first;
+    b->block_count = block_count;
+    b->leaf_len = n_cols + (blinding ? QP_SALT_SIZE : 0);
+    b->n_local = (size_t)block_count << degree_log;
+    b->coeffs = d_coeffs;
+    b->ms[0] = ifft_ms;
+    const unsigned shard_bits = rate_bits - ilog2(block_count);  // log2(#shards)
+    b->tree.shape.lg_leaves = ilog2(b->n_local);
+    b->tree.shape.cap_height = cap_height - shard_bits;
+    *out = b;
+
+    int rc = dev_alloc(ctx, &b->lde, b->leaf_len * b->n_local);
+    if (rc) return rc;
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    // "FFT + blinding" (oracle.rs:202-206, 267-283)
+    const ScaleTables* st = nullptr;
+    rc = lde_scale(ctx, (int)degree_log, rate_bits, block_first, block_count, &st);
+    if (rc) return rc;
+    NttJob job;
+    job.src = d_coeffs;
+    job.dst = b->lde;
+    job.L = (int)degree_log;
+    job.n_vec = (unsigned)(n_cols * block_count);
+    job.inner_bits = (int)ilog2(block_count);
+    job.src_outer = n;
+    job.src_inner = 0;
+    job.dst_outer = b->n_local;
+    job.dst_inner = n;
+    job.scale = st;
+    job.out_mode = ntt::OUT_NATURAL;
+    rc = run_ntt(ctx, job);
+    if (rc) return rc;
+    if (blinding) {
+        LAUNCH(ctx, salt_to_leaf_order_kernel, cdiv(QP_SALT_SIZE * b->n_local, 256), 256, 0, salt_dev,
+               b->lde + n_cols * b->n_local, degree_log + rate_bits, (size_t)block_first << degree_log,
+               b->n_local);
+    }
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    // "transpose LDEs" is fused away: the LDE is already in leaf order, column-major.
+    // "build Merkle tree" (oracle.rs:210-214)
+    merkle::AffineLayout lay{b->lde, b->n_local, 1};
+    rc = build_tree(ctx, lay, (unsigned)b->leaf_len, &b->tree, ctx->ev[5]);
+    if (rc) return rc;
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&b->ms[1], ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&b->ms[3], ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&b->ms_leaf_hash, ctx->ev[2], ctx->ev[5]);
+    cudaEventElapsedTime(&b->ms_tree_levels, ctx->ev[5], ctx->ev[3]);
+    return QP_OK;
+}
+
+static int check_batch_args(qp_ctx* ctx, size_t n_cols, unsigned degree_log, unsigned rate_bits, int blinding,
+                            unsigned cap_height, const uint64_t* salt, unsigned block_first,
+                            unsigned block_count, qp_batch** out) {
+    if (!ctx) return QP_ERR_BAD_ARG;
+    if (!out) return fail(ctx, QP_ERR_BAD_ARG, "null out");
+    *out = nullptr;
+    if (n_cols == 0) return fail(ctx, QP_ERR_BAD_ARG, "polynomials[0]: empty batch (index out of bounds)");
+    if (degree_log + rate_bits > ctx->tw_lg) return fail(ctx, QP_ERR_TOO_LARGE, "LDE larger than the context's max_lde_log");
+    if (cap_height > degree_log + rate_bits)
+        return fail(ctx, QP_ERR_CAP_HEIGHT, "cap_height should be at most log2(leaves.len())");
+    if (blinding && !salt) return fail(ctx, QP_ERR_BLINDING_NO_SALT, "blinding needs injected salt");
+    if (!is_pow2(block_count) || block_count > (1u << rate_bits) || block_first % block_count ||
+        block_first + block_count > (1u << rate_bits))
+        return fail(ctx, QP_ERR_BAD_ARG, "bad coset block range");
+    const unsigned shard_bits = rate_bits - ilog2(block_count);
+    if (cap_height < shard_bits) return fail(ctx, QP_ERR_BAD_ARG, "shard smaller than a cap subtree");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return QP_OK;
+}
+
+extern "C" int qp_batch_from_coeffs(qp_ctx* ctx, const uint64_t* coeffs, int space, size_t n_cols,
+                                    unsigned degree_log, unsigned rate_bits, int blinding,
+                                    unsigned cap_height, const uint64_t* salt, unsigned block_first,
+                                    unsigned block_count, qp_batch** out) {
+    int rc = check_batch_args(ctx, n_cols, degree_log, rate_bits, blinding, cap_height, salt, block_first,
+                              block_count, out);
+    if (rc) return rc;
+    if (!coeffs) return fail(ctx, QP_ERR_BAD_ARG, "null coeffs");
+    const size_t n = (size_t)1 << degree_log;
+    uint64_t* d_coeffs = nullptr;
+    rc = dev_alloc(ctx, &d_coeffs, n_cols * n);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_coeffs, coeffs, n_cols * n * 8,
+                                  space == QP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    const uint64_t* d_salt = nullptr;
+    uint64_t* salt_owned = nullptr;
+    if (blinding) {
+        rc = to_device(ctx, salt, space, (size_t)QP_SALT_SIZE << (degree_log + rate_bits), &d_salt, &salt_owned);
+        if (rc) return rc;
+    }
+    rc = batch_from_device_coeffs(ctx, d_coeffs, n_cols, degree_log, rate_bits, blinding, cap_height, d_salt,
+                                  block_first, block_count, 0.f, out);
+    dev_free(ctx, salt_owned);
+    if (rc) {
+        qp_batch_free(*out);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+static int ifft_device(qp_ctx* ctx, const uint64_t* d_values, size_t n_cols, unsigned degree_log,
+                       uint64_t* d_coeffs) {
+    NttJob job;
+    job.src = d_values;
+    job.dst = d_coeffs;
+    job.L = (int)degree_log;
+    job.n_vec = (unsigned)n_cols;
+    job.inner_bits = 0;
+    job.src_outer = (size_t)1 << degree_log;
+    job.dst_outer = (size_t)1 << degree_log;
+    job.out_mode = ntt::OUT_INVERSE;
+    return run_ntt(ctx, job);
+}
+
+extern "C" int qp_batch_from_values(qp_ctx* ctx, const uint64_t* values, int space, size_t n_cols,
+                                    unsigned degree_log, unsigned rate_bits, int blinding,
+                                    unsigned cap_height, const uint64_t* salt, unsigned block_first,
+                                    unsigned block_count, qp_batch** out) {
+    int rc = check_batch_args(ctx, n_cols, degree_log, rate_bits, blinding, cap_height, salt, block_first,
+                              block_count, out);
+    if (rc) return rc;
+    if (!values) return fail(ctx, QP_ERR_BAD_ARG, "null values");
+    const size_t n = (size_t)1 << degree_log;
+    const uint64_t* d_values = nullptr;
+    uint64_t* values_owned = nullptr;
+    rc = to_device(ctx, values, space, n_cols * n, &d_values, &values_owned);
+    if (rc) return rc;
+    uint64_t* d_coeffs = nullptr;
+    rc = dev_alloc(ctx, &d_coeffs, n_cols * n);
+    if (rc) return rc;
+    // "IFFT" (oracle.rs:176-180)
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    rc = ifft_device(ctx, d_values, n_cols, degree_log, d_coeffs);
+    cudaEventRecord(ctx->ev[4], ctx->stream);
+    dev_free(ctx, values_owned);
+    if (rc) {
+        dev_free(ctx, d_coeffs);
+        return rc;
+    }
+    const uint64_t* d_salt = nullptr;
+    uint64_t* salt_owned = nullptr;
+    if (blinding) {
+        rc = to_device(ctx, salt, space, (size_t)QP_SALT_SIZE << (degree_log + rate_bits), &d_salt, &salt_owned);
+        if (rc) return rc;
+    }
+    rc = batch_from_device_coeffs(ctx, d_coeffs, n_cols, degree_log, rate_bits, blinding, cap_height, d_salt,
+                                  block_first, block_count, 0.f, out);
+    dev_free(ctx, salt_owned);
+    if (rc) {
+        qp_batch_free(*out);
+        *out = nullptr;
+        return rc;
+    }
+    cudaEventElapsedTime(&(*out)->ms[0], ctx->ev[0], ctx->ev[4]);
+    return QP_OK;
+}
+
+extern "C" int qp_ifft_columns(qp_ctx* ctx, const uint64_t* values, int space, size_t n_cols,
+                               unsigned degree_log, uint64_t* coeffs_out, int out_space) {
+    if (!ctx) return QP_ERR_BAD_ARG;
+    if (!values || !coeffs_out) return fail(ctx, QP_ERR_BAD_ARG, "null buffer");
+    if (degree_log > ctx->tw_lg) return fail(ctx, QP_ERR_TOO_LARGE, "transform larger than max_lde_log");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)1 << degree_log;
+    const uint64_t* d_values = nullptr;
+    uint64_t* values_owned = nullptr;
+    int rc = to_device(ctx, values, space, n_cols * n, &d_values, &values_owned);
+    if (rc) return rc;
+    uint64_t* d_coeffs = coeffs_out;
+    uint64_t* coeffs_owned = nullptr;
+    if (out_space != QP_DEVICE) {
+        rc = dev_alloc(ctx, &coeffs_owned, n_cols * n);
+        if (rc) return rc;
+        d_coeffs = coeffs_owned;
+    }
+    rc = ifft_device(ctx, d_values, n_cols, degree_log, d_coeffs);
+    if (!rc && out_space != QP_DEVICE) rc = copy_out(ctx, coeffs_out, QP_HOST, d_coeffs, n_cols * n);
+    dev_free(ctx, values_owned);
+    dev_free(ctx, coeffs_owned);
+    return rc;
+}
+
+extern "C" void qp_batch_free(qp_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    dev_free(b->ctx, b->coeffs);
+    dev_free(b->ctx, b->lde);
+    dev_free(b->ctx, b->tree.digests);
+    dev_free(b->ctx, b->tree.cap);
+    delete b;
+}
+
+extern "C" size_t qp_batch_cap_len(const qp_batch* b) { return b ? b->tree.n_cap() : 0; }
+extern "C" size_t qp_batch_digests_len(const qp_batch* b) { return b ? b->tree.n_digests() : 0; }
+extern "C" size_t qp_batch_leaf_len(const qp_batch* b) { return b ? b->leaf_len : 0; }
+extern "C" const uint64_t* qp_batch_device_lde(const qp_batch* b) { return b ? b->lde : nullptr; }
+extern "C" const uint64_t* qp_batch_device_coeffs(const qp_batch* b) { return b ? b->coeffs : nullptr; }
+
+extern "C" int qp_batch_cap(const qp_batch* b, uint64_t* out, int space) {
+    if (!b) return QP_ERR_BAD_ARG;
+    return copy_out(b->ctx, out, space, b->tree.cap, b->tree.n_cap() * 4);
+}
+extern "C" int qp_batch_coeffs(const qp_batch* b, uint64_t* out, int space) {
+    if (!b) return QP_ERR_BAD_ARG;
+    return copy_out(b->ctx, out, space, b->coeffs, b->n_cols << b->degree_log);
+}
+extern "C" int qp_batch_digests(const qp_batch* b, uint64_t* out, int space) {
+    if (!b) return QP_ERR_BAD_ARG;
+    return copy_out(b->ctx, out, space, b->tree.digests, b->tree.n_digests() * 4);
+}
+
+static int batch_gather(const qp_batch* b, const uint64_t* idx_host, size_t first, size_t count,
+                        unsigned row_len, uint64_t* out, int space) {
+    qp_ctx* ctx = b->ctx;
+    if (!out) return fail(ctx, QP_ERR_BAD_ARG, "null output buffer");
+    if (count == 0) return QP_OK;
+    uint64_t* d_idx = nullptr;
+    int rc;
+    if (idx_host) {
+        for (size_t i = 0; i < count; i++)
+            if (idx_host[i] >= b->n_local) return fail(ctx, QP_ERR_BAD_ARG, "leaf index out of range");
+        rc = dev_alloc(ctx, &d_idx, count);
+        if (rc) return rc;
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_idx, idx_host, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+    } else if (first + count > b->n_local) {
+        return fail(ctx, QP_ERR_BAD_ARG, "leaf range out of bounds");
+    }
+    uint64_t* d_out = out;
+    uint64_t* owned = nullptr;
+    if (space != QP_DEVICE) {
+        rc = dev_alloc(ctx, &owned, count * row_len);
+        if (rc) return rc;
+        d_out = owned;
+    }
+    merkle::AffineLayout lay{b->lde, b->n_local, 1};
+    LAUNCH(ctx, merkle::gather_rows_kernel<merkle::AffineLayout>, cdiv(count * row_len, 256), 256, 0, lay,
+           row_len, d_idx, first, count, d_out);
+    rc = QP_OK;
+    if (space != QP_DEVICE) rc = copy_out(ctx, out, QP_HOST, d_out, count * row_len);
+    dev_free(ctx, d_idx);
+    dev_free(ctx, owned);
+    return rc;
+}
+
+extern "C" int qp_batch_leaves(const qp_batch* b, size_t first, size_t count, uint64_t* out, int space) {
+    if (!b) return QP_ERR_BAD_ARG;
+    return batch_gather(b, nullptr, first, count, (unsigned)b->leaf_len, out, space);
+}
+
+extern "C" int qp_batch_get_lde_values(const qp_batch* b, size_t index, size_t step, uint64_t* out) {
+    if (!b) return QP_ERR_BAD_ARG;
+    const unsigned bits = b->degree_log + b->rate_bits;
+    const size_t nat = index * step;
+    if (nat >> bits) return fail(b->ctx, QP_ERR_BAD_ARG, "LDE index out of range");
+    size_t leaf = 0;
+    for (unsigned i = 0; i < bits; i++) leaf |= ((nat >> i) & 1) << (bits - 1 - i);
+    const size_t first_leaf = (size_t)b->block_first << b->degree_log;
+    if (leaf < first_leaf || leaf >= first_leaf + b->n_local)
+        return fail(b->ctx, QP_ERR_BAD_ARG, "LDE row lives on another shard");
+    // salt stripped (oracle.rs:290)
+    return batch_gather(b, nullptr, leaf - first_leaf, 1, (unsigned)b->n_cols, out, QP_HOST);
+}
+
+extern "C" int qp_batch_get_leaves(const qp_batch* b, const uint64_t* leaf_indices, unsigned n, uint64_t* out) {
+    if (!b) return QP_ERR_BAD_ARG;
+    if (!leaf_indices && n) return fail(b->ctx, QP_ERR_BAD_ARG, "null indices");
+    return batch_gather(b, leaf_indices, 0, n, (unsigned)b->leaf_len, out, QP_HOST);
+}
+
+extern "C" int qp_batch_prove(const qp_batch* b, size_t leaf_index, uint64_t* siblings_out) {
+    if (!b) return QP_ERR_BAD_ARG;
+    return tree_prove(b->ctx, b->tree, leaf_index, siblings_out);
+}
+
+extern "C" int qp_batch_timing(const qp_batch* b, double ms[4]) {
+    if (!b || !ms) return QP_ERR_BAD_ARG;
+    for (int i = 0; i < 4; i++) ms[i] = b->ms[i];
+    return QP_OK;
+}
+extern "C" int qp_batch_kernel_timing(const qp_batch* b, double ms[4]) {
+    if (!b || !ms) return QP_ERR_BAD_ARG;
+    ms[0] = b->ms[0];          // iNTT passes
+    ms[1] = b->ms[1];          // LDE passes (+ salt)
+    ms[2] = b->ms_leaf_hash;   // leaf_hash_kernel alone
+    ms[3] = b->ms_tree_levels; // tree_level_kernel x num_layers
+    return QP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MerkleTree::new on caller rows
+// ---------------------------------------------------------------------------------------------
+struct qp_tree {
+    qp_ctx* ctx = nullptr;
+    uint64_t* leaves = nullptr;  // leaf-major [n][leaf_len] (device copy)
+    size_t n_leaves = 0, leaf_len = 0;
+    TreeBuf tree;
+};
+
+extern "C" int qp_merkle_tree_new(qp_ctx* ctx, const uint64_t* leaves, int space, size_t n_leaves,
+                                  size_t leaf_len, unsigned cap_height, qp_tree** out) {
+    if (!ctx) return QP_ERR_BAD_ARG;
+    if (!out) return fail(ctx, QP_ERR_BAD_ARG, "null out");
+    *out = nullptr;
+    if (!is_pow2(n_leaves)) return fail(ctx, QP_ERR_NOT_POW2, "Not a power of two");
+    if (cap_height > ilog2(n_leaves))
+        return fail(ctx, QP_ERR_CAP_HEIGHT, "cap_height should be at most log2(leaves.len())");
+    if (!leaves && leaf_len) return fail(ctx, QP_ERR_BAD_ARG, "null leaves");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    qp_tree* t = new qp_tree();
+    t->ctx = ctx;
+    t->n_leaves = n_leaves;
+    t->leaf_len = leaf_len;
+    t->tree.shape.lg_leaves = ilog2(n_leaves);
+    t->tree.shape.cap_height = cap_height;
+    *out = t;
+    int rc = dev_alloc(ctx, &t->leaves, n_leaves * leaf_len);
+    if (!rc && leaf_len)
+        CUDA_TRY(ctx, cudaMemcpyAsync(t->leaves, leaves, n_leaves * leaf_len * 8,
+                                      space == QP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                      ctx->stream));
+    if (!rc) {
+        merkle::AffineLayout lay{t->leaves, 1, leaf_len};
+        rc = build_tree(ctx, lay, (unsigned)leaf_len, &t->tree);
+    }
+    if (!rc) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (rc) {
+        qp_tree_free(t);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+extern "C" void qp_tree_free(qp_tree* t) {
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    dev_free(t->ctx, t->leaves);
+    dev_free(t->ctx, t->tree.digests);
+    dev_free(t->ctx, t->tree.cap);
+    delete t;
+}
+extern "C" int qp_tree_cap(const qp_tree* t, uint64_t* out, int space) {
+    if (!t) return QP_ERR_BAD_ARG;
+    return copy_out(t->ctx, out, space, t->tree.cap, t->tree.n_cap() * 4);
+}
+extern "C" int qp_tree_digests(const qp_tree* t, uint64_t* out, int space) {
+    if (!t) return QP_ERR_BAD_ARG;
+    return copy_out(t->ctx, out, space, t->tree.digests, t->tree.n_digests() * 4);
+}
+extern "C" size_t qp_tree_digests_len(const qp_tree* t) { return t ? t->tree.n_digests() : 0; }
+extern "C" int qp_tree_prove(const qp_tree* t, size_t leaf_index, uint64_t* siblings_out) {
+    if (!t) return QP_ERR_BAD_ARG;
+    return tree_prove(t->ctx, t->tree, leaf_index, siblings_out);
+}
+extern "C" int qp_tree_get(const qp_tree* t, size_t leaf_index, uint64_t* out) {
+    if (!t) return QP_ERR_BAD_ARG;
+    if (leaf_index >= t->n_leaves) return fail(t->ctx, QP_ERR_BAD_ARG, "leaf index out of range");
+    if (t->leaf_len == 0) return QP_OK;
+    return copy_out(t->ctx, out, QP_HOST, t->leaves + leaf_index * t->leaf_len, t->leaf_len);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Poseidon / transforms
+// ---------------------------------------------------------------------------------------------
+extern "C" int qp_poseidon_permute(qp_ctx* ctx, uint64_t* states, int space, size_t count) {
+    if (!ctx) return QP_ERR_BAD_ARG;
+    if (!states && count) return fail(ctx, QP_ERR_BAD_ARG, "null states");
+    if (count == 0) return QP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t* d_in = nullptr;
+    uint64_t* owned = nullptr;
+    int rc = to_device(ctx, states, space, count * 12, &d_in, &owned);
+    if (rc) return rc;
+    uint64_t* d = const_cast<uint64_t*>(d_in);
+    LAUNCH(ctx, permute_states_kernel, cdiv(count, 128), 128, 0, d, count);
+    if (space != QP_DEVICE) rc = copy_out(ctx, states, QP_HOST, d, count * 12);
+    dev_free(ctx, owned);
+    return rc;
+}
+
+// coset FFT of device-resident vectors; output bit-reversed in `dst` (device).
+static int coset_fft_device(qp_ctx* ctx, const uint64_t* d_src, uint64_t* d_dst, size_t n_vec, unsigned lg_n,
+                            uint64_t shift) {
+    ScaleTables st;
+    bool scaled = gl::canon(shift) != 1;
+    if (scaled) {
+        int rc = build_scale(ctx, (int)lg_n, std::vector<uint64_t>{shift}, &st);
+        if (rc) return rc;
+    }
+    NttJob job;
+    job.src = d_src;
+    job.dst = d_dst;
+    job.L = (int)lg_n;
+    job.n_vec = (unsigned)n_vec;
+    job.src_outer = job.dst_outer = (size_t)1 << lg_n;
+    job.scale = scaled ? &st : nullptr;
+    int rc = run_ntt(ctx, job);
+    if (scaled) {
+        cudaStreamSynchronize(ctx->stream);
+        free_scale(&st);
+    }
+    return rc;
+}
+
+extern "C" int qp_coset_fft(qp_ctx* ctx, const uint64_t* coeffs, int space, size_t n_vec, unsigned lg_n,
+                            uint64_t shift, int bit_reversed, uint64_t* out, int out_space) {
+    if (!ctx) return QP_ERR_BAD_ARG;
+    if (!coeffs || !out) return fail(ctx, QP_ERR_BAD_ARG, "null buffer");
+    if (lg_n > ctx->tw_lg) return fail(ctx, QP_ERR_TOO_LARGE, "transform larger than max_lde_log");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t words = n_vec << lg_n;
+    const uint64_t* d_in = nullptr;
+    uint64_t* in_owned = nullptr;
+    int rc = to_device(ctx, coeffs, space, words, &d_in, &in_owned);
+    if (rc) return rc;
+    uint64_t* d_tmp = nullptr;
+    rc = dev_alloc(ctx, &d_tmp, words);
+    if (rc) return rc;
+    rc = coset_fft_device(ctx, d_in, d_tmp, n_vec, lg_n, shift);
+    uint64_t* d_res = d_tmp;
+    uint64_t* d_nat = nullptr;
+    if (!rc && !bit_reversed) {
+        rc = dev_alloc(ctx, &d_nat, words);
+        if (!rc) {
+            LAUNCH(ctx, bitrev_permute_kernel, cdiv(words, 256), 256, 0, d_tmp, d_nat, lg_n, n_vec);
+            d_res = d_nat;
+        }
+    }
+    if (!rc) rc = copy_out(ctx, out, out_space, d_res, words);
+    if (!rc && out_space == QP_DEVICE) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, in_owned);
+    dev_free(ctx, d_tmp);
+    dev_free(ctx, d_nat);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FRI commit phase
+// ---------------------------------------------------------------------------------------------
+struct FriRound {
+    unsigned arity_bits = 0;
+    unsigned lg_n = 0;           // values in this round
+    uint64_t* values = nullptr;  // planes [2][n], bit-reversed order (= leaf order)
+    TreeBuf tree;
+};
+
+struct qp_fri {
+    qp_ctx* ctx = nullptr;
+    unsigned lg_n = 0, rate_bits = 0, cap_height = 0;
+    unsigned cur_lg = 0;          // current number of coefficients (log2)
+    uint64_t* coeffs = nullptr;   // planes [2][2^cur_lg], natural order
+    uint64_t* values = nullptr;   // planes of the NEXT round to commit (bit-reversed)
+    uint64_t shift = gl::GENERATOR;
+    std::vector<FriRound> rounds;
+    bool committed = false;       // a commit_round awaits its fold_round
+};
+
+extern "C" int qp_fri_begin(qp_ctx* ctx, const uint64_t* coeffs_ext, const uint64_t* values_ext, int space,
+                            unsigned lg_n, unsigned rate_bits, unsigned cap_height, qp_fri** out) {
+    if (!ctx) return QP_ERR_BAD_ARG;
+    if (!out) return fail(ctx, QP_ERR_BAD_ARG, "null out");
+    *out = nullptr;
+    if (!coeffs_ext || !values_ext) return fail(ctx, QP_ERR_BAD_ARG, "null input");
+    if (lg_n > ctx->tw_lg) return fail(ctx, QP_ERR_TOO_LARGE, "FRI domain larger than max_lde_log");
+    if (rate_bits > lg_n) return fail(ctx, QP_ERR_BAD_ARG, "rate_bits > lde_bits");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)1 << lg_n;
+    qp_fri* f = new qp_fri();
+    f->ctx = ctx;
+    f->lg_n = f->cur_lg = lg_n;
+    f->rate_bits = rate_bits;
+    f->cap_height = cap_height;
+    *out = f;
+    const uint64_t *d_c = nullptr, *d_v = nullptr;
+    uint64_t *c_owned = nullptr, *v_owned = nullptr;
+    int rc = to_device(ctx, coeffs_ext, space, 2 * n, &d_c, &c_owned);
+    if (!rc) rc = to_device(ctx, values_ext, space, 2 * n, &d_v, &v_owned);
+    if (!rc) rc = dev_alloc(ctx, &f->coeffs, 2 * n);
+    if (!rc) rc = dev_alloc(ctx, &f->values, 2 * n);
+    if (!rc) {
+        LAUNCH(ctx, fri::ext_to_planes_kernel, cdiv(n, 256), 256, 0, d_c, f->coeffs, lg_n, 0);
+        // reverse_index_bits_in_place(values) (prover.rs:98)
+        LAUNCH(ctx, fri::ext_to_planes_kernel, cdiv(n, 256), 256, 0, d_v, f->values, lg_n, 1);
+    }
+    dev_free(ctx, c_owned);
+    dev_free(ctx, v_owned);
+    if (rc) {
+        qp_fri_free(f);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+extern "C" int qp_fri_commit_round(qp_fri* f, unsigned arity_bits, uint64_t* cap_out) {
+    if (!f) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = f->ctx;
+    if (f->committed || !f->values) return fail(ctx, QP_ERR_BAD_ARG, "commit_round called out of order");
+    if (arity_bits > f->cur_lg) return fail(ctx, QP_ERR_BAD_ARG, "arity exceeds domain");
+    const unsigned lg_leaves = f->cur_lg - arity_bits;
+    if (f->cap_height > lg_leaves)
+        return fail(ctx, QP_ERR_CAP_HEIGHT, "cap_height should be at most log2(leaves.len())");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    FriRound r;
+    r.arity_bits = arity_bits;
+    r.lg_n = f->cur_lg;
+    r.values = f->values;
+    f->values = nullptr;
+    r.tree.shape.lg_leaves = lg_leaves;
+    r.tree.shape.cap_height = f->cap_height;
+    // leaves = chunks of `arity` consecutive (bit-reversed) values, flattened (prover.rs:99-104)
+    merkle::ExtPlanesLayout lay{r.values, (size_t)1 << r.lg_n, arity_bits};
+    int rc = build_tree(ctx, lay, 2u << arity_bits, &r.tree);
+    f->rounds.push_back(r);
+    if (rc) return rc;
+    f->committed = true;
+    return copy_out(ctx, cap_out, QP_HOST, r.tree.cap, r.tree.n_cap() * 4);
+}
+
+extern "C" int qp_fri_fold_round(qp_fri* f, const uint64_t beta[2], int is_last) {
+    if (!f) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = f->ctx;
+    if (!f->committed || !beta) return fail(ctx, QP_ERR_BAD_ARG, "fold_round called out of order");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const unsigned ab = f->rounds.back().arity_bits;
+    const size_t n_in = (size_t)1 << f->cur_lg, n_out = n_in >> ab;
+    uint64_t* folded = nullptr;
+    int rc = dev_alloc(ctx, &folded, 2 * n_out);
+    if (rc) return rc;
+    LAUNCH(ctx, fri::fold_kernel, cdiv(n_out, 128), 128, 0, f->coeffs, n_in, ab, beta[0], beta[1], folded);
+    dev_free(ctx, f->coeffs);
+    f->coeffs = folded;
+    f->cur_lg -= ab;
+    f->committed = false;
+    if (is_last) return QP_OK;
+    // shift <- shift^arity ; values <- coset_fft(coeffs, shift) (prover.rs:121-122), kept bit-reversed
+    f->shift = gl::host_pow(f->shift, (uint64_t)1 << ab);
+    rc = dev_alloc(ctx, &f->values, 2 * n_out);
+    if (rc) return rc;
+    return coset_fft_device(ctx, f->coeffs, f->values, 2, f->cur_lg, f->shift);
+}
+
+extern "C" int qp_fri_final_poly(qp_fri* f, uint64_t* out, size_t* len_out) {
+    if (!f) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = f->ctx;
+    if (f->cur_lg < f->rate_bits) return fail(ctx, QP_ERR_BAD_ARG, "final polynomial shorter than the rate");
+    const size_t len = ((size_t)1 << f->cur_lg) >> f->rate_bits;
+    if (len_out) *len_out = len;
+    if (!out) return QP_OK;
+    uint64_t* d = nullptr;
+    int rc = dev_alloc(ctx, &d, 2 * len);
+    if (rc) return rc;
+    LAUNCH(ctx, fri::planes_to_ext_kernel, cdiv(len, 256), 256, 0, f->coeffs, (size_t)1 << f->cur_lg, (size_t)0,
+           len, d);
+    rc = copy_out(ctx, out, QP_HOST, d, 2 * len);
+    dev_free(ctx, d);
+    return rc;
+}
+
+extern "C" unsigned qp_fri_num_rounds(const qp_fri* f) { return f ? (unsigned)f->rounds.size() : 0; }
+
+extern "C" int qp_fri_tree_get(const qp_fri* f, unsigned round, size_t leaf_index, uint64_t* out) {
+    if (!f) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = f->ctx;
+    if (round >= f->rounds.size()) return fail(ctx, QP_ERR_BAD_ARG, "round out of range");
+    const FriRound& r = f->rounds[round];
+    if (leaf_index >> r.tree.shape.lg_leaves) return fail(ctx, QP_ERR_BAD_ARG, "leaf index out of range");
+    const unsigned row_len = 2u << r.arity_bits;
+    uint64_t* d = nullptr;
+    int rc = dev_alloc(ctx, &d, row_len);
+    if (rc) return rc;
+    merkle::ExtPlanesLayout lay{r.values, (size_t)1 << r.lg_n, r.arity_bits};
+    LAUNCH(ctx, merkle::gather_rows_kernel<merkle::ExtPlanesLayout>, 1, 64, 0, lay, row_len,
+           (const uint64_t*)nullptr, leaf_index, (size_t)1, d);
+    rc = copy_out(ctx, out, QP_HOST, d, row_len);
+    dev_free(ctx, d);
+    return rc;
+}
+
+extern "C" int qp_fri_tree_prove(const qp_fri* f, unsigned round, size_t leaf_index, uint64_t* siblings_out) {
+    if (!f) return QP_ERR_BAD_ARG;
+    if (round >= f->rounds.size()) return fail(f->ctx, QP_ERR_BAD_ARG, "round out of range");
+    return tree_prove(f->ctx, f->rounds[round].tree, leaf_index, siblings_out);
+}
+extern "C" int qp_fri_tree_digests(const qp_fri* f, unsigned round, uint64_t* out, int space) {
+    if (!f) return QP_ERR_BAD_ARG;
+    if (round >= f->rounds.size()) return fail(f->ctx, QP_ERR_BAD_ARG, "round out of range");
+    const TreeBuf& t = f->rounds[round].tree;
+    return copy_out(f->ctx, out, space, t.digests, t.n_digests() * 4);
+}
+extern "C" size_t qp_fri_tree_digests_len(const qp_fri* f, unsigned round) {
+    return (f && round < f->rounds.size()) ? f->rounds[round].tree.n_digests() : 0;
+}
+
+extern "C" void qp_fri_free(qp_fri* f) {
+    if (!f) return;
+    cudaSetDevice(f->ctx->device);
+    dev_free(f->ctx, f->coeffs);
+    dev_free(f->ctx, f->values);
+    for (auto& r : f->rounds) {
+        dev_free(f->ctx, r.values);
+        dev_free(f->ctx, r.tree.digests);
+        dev_free(f->ctx, r.tree.cap);
+    }
+    delete f;
+}
+
+extern "C" int qp_fri_proof_of_work(qp_ctx* ctx, const uint64_t state12[12], unsigned witness_pos,
+                                    unsigned min_leading_zeros, uint64_t* witness_out) {
+    if (!ctx) return QP_ERR_BAD_ARG;
+    if (!state12 || !witness_out || witness_pos >= 12) return fail(ctx, QP_ERR_BAD_ARG, "bad PoW arguments");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    uint64_t* d_state = nullptr;
+    uint64_t* d_found = nullptr;
+    int rc = dev_alloc(ctx, &d_state, 12);
+    if (!rc) rc = dev_alloc(ctx, &d_found, 1);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_state, state12, 96, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_found, 0xff, 8, ctx->stream));
+    // Batches in increasing candidate order; the first batch with a hit contains the global
+    // minimum.  Batch size grows with the expected work 2^min_leading_zeros.
+    uint64_t batch = (uint64_t)1 << 16;
+    uint64_t base = 0;
+    uint64_t found = UINT64_MAX;
+    while (true) {
+        const uint64_t remaining = gl::P - base;
+        const uint64_t cnt = batch < remaining ? batch : remaining;
+        LAUNCH(ctx, fri::pow_kernel, cdiv(cnt, 128), 128, 0, d_state, witness_pos, min_leading_zeros, base,
+               (unsigned long long*)d_found);
+        CUDA_TRY(ctx, cudaMemcpyAsync(&found, d_found, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (found != UINT64_MAX) break;
+        base += cnt;
+        if (base >= gl::P) break;
+        if (batch < ((uint64_t)1 << 26)) batch <<= 2;
+    }
+    dev_free(ctx, d_state);
+    dev_free(ctx, d_found);
+    if (found == UINT64_MAX) return fail(ctx, QP_ERR_BAD_ARG, "Proof of work failed. This is highly unlikely!");
+    *witness_out = found;
+    return QP_OK;
+}

