@@ -395,9 +395,9 @@ class PolynomialBatch:
         return lib().qp_batch_device_coeffs(self._h)
 
     def free(self):
-        if self._h:
+        if self._h and self.ctx._h:
             lib().qp_batch_free(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -447,9 +447,9 @@ class MerkleTree:
         return out
 
     def free(self):
-        if self._h:
+        if self._h and self.ctx._h:
             lib().qp_tree_free(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -519,9 +519,9 @@ class FriCommitment:
         return out
 
     def free(self):
-        if self._h:
+        if self._h and self.ctx._h:
             lib().qp_fri_free(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:

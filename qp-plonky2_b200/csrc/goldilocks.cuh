@@ -33,46 +33,60 @@ __device__ __forceinline__ void unpack(uint64_t v, uint32_t& lo, uint32_t& hi) {
 
 // ---- add / sub ---------------------------------------------------------------------------
 // 32-bit carry chains: ptxas turns each of these into IADD3/IADD3.X pairs with the carry held
-// in a predicate (5 SASS instructions for the single-correction forms), where the obvious
+// in a predicate (4-5 SASS instructions for the single-correction forms), where the obvious
 // 64-bit C (`s = a + b; if (s < a) s += EPS`) costs 8 (compare + select).
 
-// a + b (mod p) when at most one wrap can occur, i.e. a + b < 2^65 - 2^32: true whenever one
-// operand is canonical (< p) or, more generally, <= 2^64 - 2^32.
+// NOTE on carry flags: ptxas keeps CC.CF in "ARM style" -- after add.cc it is the carry, after
+// sub.cc it is NOT-borrow, and subc computes a + ~b + CF.  So `subc m, 0, 0` yields the borrow
+// mask (0xffffffff on borrow) after a SUBTRACT chain, but the inverse of the carry mask after an
+// ADD chain.  After additions the carry is therefore turned into a predicate (addc / setp) and
+// the mask selected from it; ptxas folds that into one SEL on the carry predicate.
+
+// a + b (mod p) when at most one wrap can occur, i.e. a + b < 2^64 + p: true whenever one
+// operand is <= p.  5 SASS instructions.
 __device__ __forceinline__ uint64_t add1(uint64_t a, uint64_t b) {
     uint32_t a0, a1, b0, b1, s0, s1;
     unpack(a, a0, a1);
     unpack(b, b0, b1);
     asm("{\n\t"
-        ".reg .u32 m;\n\t"
+        ".reg .u32 c, m;\n\t"
+        ".reg .pred p;\n\t"
         "add.cc.u32   %0, %2, %4;\n\t"
         "addc.cc.u32  %1, %3, %5;\n\t"
-        "subc.u32     m, 0, 0;\n\t"   // m = 0 - CF = carry ? 0xffffffff : 0  (= carry * EPS)
+        "addc.u32     c, 0, 0;\n\t"
+        "setp.ne.u32  p, c, 0;\n\t"
+        "selp.u32     m, 0xffffffff, 0, p;\n\t"   // carry * EPS
         "add.cc.u32   %0, %0, m;\n\t"
         "addc.u32     %1, %1, 0;\n\t"
         "}"
-        : "=r"(s0), "=r"(s1)
+        : "=&r"(s0), "=&r"(s1)
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
     return pack(s0, s1);
 }
 
 // a + b (mod p), total over u64 x u64 (goldilocks_field.rs:249-265).  A second wrap needs both
-// operands >= 2^64 - 2^32 + ... (non-canonical); after it s < 2^32 so a third cannot occur.
+// operands non-canonical; after it the sum is < 2^32, so a third cannot occur.
 __device__ __forceinline__ uint64_t add(uint64_t a, uint64_t b) {
     uint32_t a0, a1, b0, b1, s0, s1;
     unpack(a, a0, a1);
     unpack(b, b0, b1);
     asm("{\n\t"
-        ".reg .u32 m;\n\t"
+        ".reg .u32 c, m;\n\t"
+        ".reg .pred p;\n\t"
         "add.cc.u32   %0, %2, %4;\n\t"
         "addc.cc.u32  %1, %3, %5;\n\t"
-        "subc.u32     m, 0, 0;\n\t"
+        "addc.u32     c, 0, 0;\n\t"
+        "setp.ne.u32  p, c, 0;\n\t"
+        "selp.u32     m, 0xffffffff, 0, p;\n\t"
         "add.cc.u32   %0, %0, m;\n\t"
         "addc.cc.u32  %1, %1, 0;\n\t"
-        "subc.u32     m, 0, 0;\n\t"
+        "addc.u32     c, 0, 0;\n\t"
+        "setp.ne.u32  p, c, 0;\n\t"
+        "selp.u32     m, 0xffffffff, 0, p;\n\t"
         "add.cc.u32   %0, %0, m;\n\t"
         "addc.u32     %1, %1, 0;\n\t"
         "}"
-        : "=r"(s0), "=r"(s1)
+        : "=&r"(s0), "=&r"(s1)
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
     return pack(s0, s1);
 }
@@ -90,7 +104,7 @@ __device__ __forceinline__ uint64_t sub1(uint64_t a, uint64_t b) {
         "sub.cc.u32   %0, %0, m;\n\t"
         "subc.u32     %1, %1, 0;\n\t"
         "}"
-        : "=r"(s0), "=r"(s1)
+        : "=&r"(s0), "=&r"(s1)
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
     return pack(s0, s1);
 }
@@ -111,7 +125,7 @@ __device__ __forceinline__ uint64_t sub(uint64_t a, uint64_t b) {
         "sub.cc.u32   %0, %0, m;\n\t"
         "subc.u32     %1, %1, 0;\n\t"
         "}"
-        : "=r"(s0), "=r"(s1)
+        : "=&r"(s0), "=&r"(s1)
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
     return pack(s0, s1);
 }
@@ -145,7 +159,7 @@ __device__ __forceinline__ uint64_t reduce128(uint64_t lo, uint64_t hi) {
         "sub.cc.u32   %0, %0, m;\n\t"   // borrow only if lo < 2^32, so this cannot borrow again
         "subc.u32     %1, %1, 0;\n\t"
         "}"
-        : "=r"(t0), "=r"(t1)
+        : "=&r"(t0), "=&r"(t1)
         : "r"(x0), "r"(x1), "r"(x3));
     return reduce96(pack(t0, t1), x2);
 }

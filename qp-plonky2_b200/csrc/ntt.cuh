@@ -247,6 +247,14 @@ __global__ void __launch_bounds__(THREADS) final_pass_kernel(PassParams p) {
         return load_scaled(p, src_vec, inner, (pc << K) + row);
     };
     auto st = [&](int, int, uint64_t) {};
+    if constexpr (K == 0) {
+        // length-1 vectors: no butterflies, every "chunk" is one element
+#pragma unroll
+        for (int u = 0; u < EPT; u++) {
+            const int e = u * THREADS + threadIdx.x;
+            smem[padi(e)] = ld(0, e);
+        }
+    }
     run_rounds<MODE_FINAL, K, K, true>(smem, p, 0, ld, st);
     __syncthreads();
     // copy-out: smem[(c << K) + row] holds position `row` of chunk c (bit-reversed order)

@@ -51,7 +51,7 @@ __device__ __forceinline__ uint64_t mds_row(const uint32_t (&lo)[12], const uint
         "add.cc.u32  %0, %2, %3;\n\t"
         "addc.u32    %1, %4, 0;\n\t"
         "}"
-        : "=r"(s1), "=r"(s2)
+        : "=&r"(s1), "=&r"(s2)
         : "r"(al1), "r"(ah0), "r"(ah1));
     return gl::reduce96(gl::pack(al0, s1), s2);
 }

@@ -275,6 +275,10 @@ struct NttJob {
     size_t src_outer = 0, src_inner = 0, dst_outer = 0, dst_inner = 0;
     const ScaleTables* scale = nullptr;
     int out_mode = ntt::OUT_NATURAL;
+    // OUT_INVERSE permutes across CTAs in its final pass, so that pass cannot run in place: the
+    // strided passes work in `scratch` ([n_vec][2^L], may alias src if the caller owns src) and
+    // the final pass goes scratch -> dst.  nullptr = allocate a temporary.
+    uint64_t* scratch = nullptr;
 };
 
 template <int K>
@@ -346,6 +350,20 @@ static int run_ntt(qp_ctx* ctx, const NttJob& job) {
     p.inner_bits = job.inner_bits;
     p.out_mode = job.out_mode;
     p.n_inv = gl::P - ((gl::P - 1) >> L);  // inverse_2exp, field/src/types.rs:239-278
+    // where the strided passes live
+    uint64_t* work = job.dst;
+    size_t work_outer = job.dst_outer, work_inner = job.dst_inner;
+    uint64_t* tmp = nullptr;
+    if (job.out_mode == ntt::OUT_INVERSE && n_strided > 0) {
+        work = job.scratch;
+        if (!work) {
+            int rc = dev_alloc(ctx, &tmp, (size_t)job.n_vec << L);
+            if (rc) return rc;
+            work = tmp;
+        }
+        work_outer = (size_t)1 << (L + job.inner_bits);
+        work_inner = (size_t)1 << L;
+    }
     bool first = true;
     int s_hi = L;  // stages [s_lo, s_hi) remain above
     for (int i = 0; i < n_strided; i++) {
@@ -353,31 +371,36 @@ static int run_ntt(qp_ctx* ctx, const NttJob& job) {
         const int s_lo = s_hi - K;
         if (s_lo < ntt::TILE_LOG - K) return fail(ctx, QP_ERR_BAD_ARG, "internal: strided tile wider than block");
         p.s_lo = s_lo;
-        p.src = first ? job.src : job.dst;
-        p.dst = job.dst;
-        p.src_outer_stride = first ? job.src_outer : job.dst_outer;
-        p.src_inner_stride = first ? job.src_inner : job.dst_inner;
-        p.dst_outer_stride = job.dst_outer;
-        p.dst_inner_stride = job.dst_inner;
+        p.src = first ? job.src : work;
+        p.dst = work;
+        p.src_outer_stride = first ? job.src_outer : work_outer;
+        p.src_inner_stride = first ? job.src_inner : work_inner;
+        p.dst_outer_stride = work_outer;
+        p.dst_inner_stride = work_inner;
         p.scale_lo = (first && job.scale) ? job.scale->lo : nullptr;
         p.scale_hi = (first && job.scale) ? job.scale->hi : nullptr;
         p.scale_split = job.scale ? job.scale->split : 0;
         int rc = dispatch_strided(ctx, K, p);
-        if (rc) return rc;
+        if (rc) {
+            dev_free(ctx, tmp);
+            return rc;
+        }
         first = false;
         s_hi = s_lo;
     }
     p.s_lo = 0;
-    p.src = first ? job.src : job.dst;
+    p.src = first ? job.src : work;
     p.dst = job.dst;
-    p.src_outer_stride = first ? job.src_outer : job.dst_outer;
-    p.src_inner_stride = first ? job.src_inner : job.dst_inner;
+    p.src_outer_stride = first ? job.src_outer : work_outer;
+    p.src_inner_stride = first ? job.src_inner : work_inner;
     p.dst_outer_stride = job.dst_outer;
     p.dst_inner_stride = job.dst_inner;
     p.scale_lo = (first && job.scale) ? job.scale->lo : nullptr;
     p.scale_hi = (first && job.scale) ? job.scale->hi : nullptr;
     p.scale_split = job.scale ? job.scale->split : 0;
-    return dispatch_final(ctx, Kf, p);
+    int rc = dispatch_final(ctx, Kf, p);
+    dev_free(ctx, tmp);
+    return rc;
 }
 
 // Scale tables for x_i *= shift_q^i, q < n_inner (shifts on host).
@@ -622,7 +645,7 @@ extern "C" int qp_batch_from_coeffs(qp_ctx* ctx, const uint64_t* coeffs, int spa
 }
 
 static int ifft_device(qp_ctx* ctx, const uint64_t* d_values, size_t n_cols, unsigned degree_log,
-                       uint64_t* d_coeffs) {
+                       uint64_t* d_coeffs, uint64_t* scratch = nullptr) {
     NttJob job;
     job.src = d_values;
     job.dst = d_coeffs;
@@ -632,6 +655,7 @@ static int ifft_device(qp_ctx* ctx, const uint64_t* d_values, size_t n_cols, uns
     job.src_outer = (size_t)1 << degree_log;
     job.dst_outer = (size_t)1 << degree_log;
     job.out_mode = ntt::OUT_INVERSE;
+    job.scratch = scratch;
     return run_ntt(ctx, job);
 }
 
@@ -653,7 +677,7 @@ extern "C" int qp_batch_from_values(qp_ctx* ctx, const uint64_t* values, int spa
     if (rc) return rc;
     // "IFFT" (oracle.rs:176-180)
     cudaEventRecord(ctx->ev[0], ctx->stream);
-    rc = ifft_device(ctx, d_values, n_cols, degree_log, d_coeffs);
+    rc = ifft_device(ctx, d_values, n_cols, degree_log, d_coeffs, values_owned);
     cudaEventRecord(ctx->ev[4], ctx->stream);
     dev_free(ctx, values_owned);
     if (rc) {
@@ -696,7 +720,7 @@ extern "C" int qp_ifft_columns(qp_ctx* ctx, const uint64_t* values, int space, s
         if (rc) return rc;
         d_coeffs = coeffs_owned;
     }
-    rc = ifft_device(ctx, d_values, n_cols, degree_log, d_coeffs);
+    rc = ifft_device(ctx, d_values, n_cols, degree_log, d_coeffs, values_owned);
     if (!rc && out_space != QP_DEVICE) rc = copy_out(ctx, coeffs_out, QP_HOST, d_coeffs, n_cols * n);
     dev_free(ctx, values_owned);
     dev_free(ctx, coeffs_owned);
