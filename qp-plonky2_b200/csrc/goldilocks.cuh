@@ -137,12 +137,19 @@ __device__ __forceinline__ uint64_t neg(uint64_t a) {
 
 // ---- reduction / multiplication ----------------------------------------------------------
 
-// (hi:lo) + 0 -> lo + hi32 * EPS with the single possible wrap folded back
-// (reduce96, goldilocks_field.rs:381-385).  hi32 * EPS < 2^64 - 2^32, so one correction is enough.
+// (hi:lo), hi 32 bits  ->  lo + hi * EPS with the single possible wrap folded back
+// (reduce96, goldilocks_field.rs:381-385).  hi * EPS = (hi << 32) - hi is formed on the ALU pipe
+// (2 instructions) instead of one IMAD.WIDE: on B200 the fma-heavy pipe is the scarce one
+// (IMAD.WIDE = 4 pipe cycles).  hi * EPS <= (2^32-1)^2 < p, so one correction is enough.
 __device__ __forceinline__ uint64_t reduce96(uint64_t lo, uint32_t hi) {
-    uint64_t pr;
-    asm("mul.wide.u32 %0, %1, 0xffffffff;" : "=l"(pr) : "r"(hi));
-    return add1(lo, pr);
+    uint32_t p0, p1;
+    asm("{\n\t"
+        "sub.cc.u32   %0, 0, %2;\n\t"    // low word:  -hi
+        "subc.u32     %1, %2, 0;\n\t"    // high word: hi - (hi != 0)
+        "}"
+        : "=&r"(p0), "=&r"(p1)
+        : "r"(hi));
+    return add1(lo, pack(p0, p1));
 }
 
 // Reduce the 128-bit value (hi:lo) mod p; output is some u64 representative

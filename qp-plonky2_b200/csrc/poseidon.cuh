@@ -4,16 +4,28 @@
 // Reference semantics: core/src/poseidon.rs:599-633 (poseidon / poseidon_naive -- the two are
 // the same function; the KATs at core/src/poseidon_goldilocks.rs:455-490 pin it).
 //
-// B200 formulation (not the reference's): the reference speeds up the 22 partial rounds with
-// the FAST_PARTIAL_* sparse-matrix tables, whose entries are full 64-bit constants (23 full
-// modular multiplies per round).  On the GPU integer pipe a dense multiply by the MDS matrix is
-// CHEAPER than that, because every MDS coefficient is < 2^6: the state is split into 32-bit
-// halves and each row is 2 x 12 IMAD.WIDE.U32 accumulations (no carries: 12 * 41 * 2^32 < 2^42)
-// followed by ONE 96-bit reduction.  So all 30 rounds use the same naive round function
-//      state <- MDS * sbox(state)            (sbox on lane 0 only in partial rounds)
-// and the next round's constants ride in as the initial value of the row accumulators, which
-// makes the constant layer free.  Exact arithmetic => identical outputs to the reference.
+// B200 formulation (not the reference's).  ncu on B200 shows the kernel is bound by the
+// fma-heavy pipe: IMAD.WIDE.U32 issues at 8 lanes/clk/SMSP (4 pipe cycles per warp
+// instruction), so the count of wide multiplies is what matters.
+//   * Linear layers never use full 64x64 products.  Every MDS coefficient is < 2^6, so the
+//     state is split into 32-bit halves and each output row is 2 x 12 IMAD.WIDE accumulations
+//     (no carries: sums stay < 2^43) followed by ONE 96-bit reduction; the next round's
+//     constants ride in as the initial value of the accumulators (constant layer for free).
+//   * The reference replaces the 22 partial rounds' MDS by sparse matrices with full 64-bit
+//     entries (FAST_PARTIAL_*, 23 modular multiplies per round).  Here three partial rounds are
+//     fused instead: with d = x0^7 - x0 the round is x' = M x + d m0 + rc', so after three rounds
+//         x''' = M^3 x + d1 M^3 e0 + d2 M^2 e0 + d3 M e0 + K
+//     and only lane 0 of the intermediate states is needed (one row of M, one of M^2).  The
+//     entries of M^2, M^3 are still < 2^25, so they remain 32-bit immediates of IMAD.WIDE:
+//     414 wide multiplies per three rounds instead of 864 (dense) or ~345 + 69 reductions (sparse).
+//   * 96-bit reductions are ALU-only (no IMAD), 128-bit products use ptxas' fused 7-instruction
+//     sequence (goldilocks.cuh).
+//   * One loop body per round type, shared by both halves of the permutation, keeps the code
+//     (~40 KB) inside the instruction cache; a fully unrolled permutation stalls on fetch.
+// Exact arithmetic => identical outputs to the reference.
 #pragma once
+#include <cuda_runtime.h>
+
 #include "goldilocks.cuh"
 #include "poseidon_constants.h"
 
@@ -22,28 +34,90 @@ namespace poseidon {
 static constexpr int WIDTH = 12;
 static constexpr int RATE = 8;
 static constexpr int N_ROUNDS = 30;
+static constexpr int N_PARTIAL_GROUPS = 7;  // rounds 4..24 in groups of three; round 25 alone
 
-// ALL_ROUND_CONSTANTS (core/src/poseidon.rs:57-155), uploaded once per context.
-__constant__ uint64_t c_round_constants[WIDTH * N_ROUNDS];
+struct Mat {
+    uint32_t a[12][12];
+};
 
-
-// One MDS row (core/src/poseidon.rs:178-198: sum_i s[(i+r)%12]*CIRC[i] + s[r]*DIAG[r]) plus an
-// additive 64-bit constant `rc` (the NEXT round's constant for this lane, canonical).
-template <int R>
-__device__ __forceinline__ uint64_t mds_row(const uint32_t (&lo)[12], const uint32_t (&hi)[12],
-                                            uint64_t rc) {
+// M = circ(17,15,41,16,2,28,13,13,39,18,34,20) + diag(8,0,...)  (poseidon_goldilocks.rs:24-25):
+// M[r][c] = CIRC[(c - r) mod 12] + (r == c ? DIAG[r] : 0), core/src/poseidon.rs:178-198.
+__host__ __device__ constexpr Mat mds_matrix() {
     constexpr uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-    uint32_t rc0, rc1;
-    gl::unpack(rc, rc0, rc1);
-    uint64_t al = rc0, ah = rc1;
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-        const int k = (i + R) % 12;
-        uint32_t c = C[i] + ((R == 0 && i == 0) ? 8u : 0u);  // DIAG = [8, 0, ..., 0]
-        al += (uint64_t)lo[k] * c;
-        ah += (uint64_t)hi[k] * c;
+    Mat m{};
+    for (int r = 0; r < 12; r++)
+        for (int c = 0; c < 12; c++) m.a[r][c] = C[(c - r + 12) % 12] + ((r == 0 && c == 0) ? 8u : 0u);
+    return m;
+}
+__host__ __device__ constexpr Mat mat_mul(const Mat& x, const Mat& y) {
+    Mat z{};
+    for (int r = 0; r < 12; r++)
+        for (int c = 0; c < 12; c++) {
+            uint64_t acc = 0;
+            for (int k = 0; k < 12; k++) acc += (uint64_t)x.a[r][k] * y.a[k][c];
+            z.a[r][c] = (uint32_t)acc;  // < 2^25 for M^2, M^3 (row sums of M are <= 264)
+        }
+    return z;
+}
+static constexpr Mat M1 = mds_matrix();
+static constexpr Mat M2 = mat_mul(M1, M1);
+static constexpr Mat M3 = mat_mul(M2, M1);
+// device code cannot name namespace-scope constexpr objects: each device function re-declares
+// the matrices as local compile-time constants (all entries fold into immediates)
+#define QP_POSEIDON_MATS                                 \
+    constexpr Mat m1 = mds_matrix();                     \
+    constexpr Mat m2 = mat_mul(m1, m1);                  \
+    constexpr Mat m3 = mat_mul(m2, m1);                  \
+    (void)m2;                                            \
+    (void)m3;
+
+// Device constants, uploaded once per context by upload_constants():
+//   c_rc[12 * r + i]      ALL_ROUND_CONSTANTS (core/src/poseidon.rs:57-155), plus a zero row 30
+//   c_grp_k[g][0..1]      scalars of partial group g:  rc'_0  and  (M rc' + rc'')_0
+//   c_grp_K[g][0..11]     vector  M^2 rc' + M rc'' + rc'''          (rc', rc'', rc''' = constants
+//                         of the three rounds FOLLOWING the group's first round)
+__constant__ uint64_t c_rc[WIDTH * (N_ROUNDS + 1)];
+__constant__ uint64_t c_grp_k[N_PARTIAL_GROUPS][2];
+__constant__ uint64_t c_grp_K[N_PARTIAL_GROUPS][WIDTH];
+
+// Host side: derive the group constants (mod p, exact) and upload everything.
+static inline cudaError_t upload_constants(cudaStream_t stream) {
+    typedef unsigned __int128 u128;
+    const uint64_t P = gl::P;
+    static uint64_t rc[WIDTH * (N_ROUNDS + 1)];
+    static uint64_t gk[N_PARTIAL_GROUPS][2];
+    static uint64_t gK[N_PARTIAL_GROUPS][WIDTH];
+    for (int i = 0; i < WIDTH * N_ROUNDS; i++) rc[i] = POSEIDON_ALL_ROUND_CONSTANTS[i];
+    for (int i = 0; i < WIDTH; i++) rc[WIDTH * N_ROUNDS + i] = 0;
+    auto matvec = [&](const Mat& m, const uint64_t* v, uint64_t* out) {
+        for (int r = 0; r < 12; r++) {
+            u128 acc = 0;
+            for (int c = 0; c < 12; c++) acc += (u128)m.a[r][c] * (v[c] % P);
+            out[r] = (uint64_t)(acc % P);
+        }
+    };
+    for (int g = 0; g < N_PARTIAL_GROUPS; g++) {
+        const int r = 4 + 3 * g;  // first round of the group
+        const uint64_t* r1 = rc + 12 * (r + 1);
+        const uint64_t* r2 = rc + 12 * (r + 2);
+        const uint64_t* r3 = rc + 12 * (r + 3);
+        uint64_t m1r1[12], m2r1[12], m1r2[12];
+        matvec(M1, r1, m1r1);
+        matvec(M2, r1, m2r1);
+        matvec(M1, r2, m1r2);
+        gk[g][0] = r1[0];
+        gk[g][1] = (uint64_t)(((u128)m1r1[0] + r2[0]) % P);
+        for (int i = 0; i < 12; i++) gK[g][i] = (uint64_t)(((u128)m2r1[i] + m1r2[i] + r3[i]) % P);
     }
-    // value = al + ah * 2^32, al, ah < 2^43:  (s2 : s1 : s0) then reduce96.
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_rc, rc, sizeof rc, 0, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_grp_k, gk, sizeof gk, 0, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_grp_K, gK, sizeof gK, 0, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // the sources are static host arrays
+    return e;
+}
+
+// 96-bit (s2 : lo64) row value -> field element.  al + ah * 2^32 with al, ah < 2^58.
+__device__ __forceinline__ uint64_t fold_row(uint64_t al, uint64_t ah) {
     uint32_t al0, al1, ah0, ah1, s1, s2;
     gl::unpack(al, al0, al1);
     gl::unpack(ah, ah0, ah1);
@@ -56,43 +130,94 @@ __device__ __forceinline__ uint64_t mds_row(const uint32_t (&lo)[12], const uint
     return gl::reduce96(gl::pack(al0, s1), s2);
 }
 
-// state <- MDS(state) + rc[0..12]   (rc may be nullptr => no constants)
+// acc += row R of matrix MAT times the state halves (2 x 12 IMAD.WIDE with immediate operands)
+#define QP_DOT_ROW(MAT, R, lo, hi, al, ah)                       \
+    _Pragma("unroll") for (int k_ = 0; k_ < 12; k_++) {          \
+        al += (uint64_t)lo[k_] * MAT.a[R][k_];                   \
+        ah += (uint64_t)hi[k_] * MAT.a[R][k_];                   \
+    }
+
+// state <- M * state + rc[0..12]
 __device__ __forceinline__ void mds_layer(uint64_t (&s)[12], const uint64_t* rc) {
+    QP_POSEIDON_MATS
     uint32_t lo[12], hi[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) gl::unpack(s[i], lo[i], hi[i]);
-#define QP_ROW(R) s[R] = mds_row<R>(lo, hi, rc ? rc[R] : 0ULL);
-    QP_ROW(0) QP_ROW(1) QP_ROW(2) QP_ROW(3) QP_ROW(4) QP_ROW(5)
-    QP_ROW(6) QP_ROW(7) QP_ROW(8) QP_ROW(9) QP_ROW(10) QP_ROW(11)
-#undef QP_ROW
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        uint32_t c0, c1;
+        gl::unpack(rc[r], c0, c1);
+        uint64_t al = c0, ah = c1;
+        QP_DOT_ROW(m1, r, lo, hi, al, ah)
+        s[r] = fold_row(al, ah);
+    }
+}
+
+// (x0^7 - x0) split into halves
+__device__ __forceinline__ void sbox_delta(uint64_t x0, uint32_t& dlo, uint32_t& dhi) {
+    gl::unpack(gl::sub(gl::pow7(x0), x0), dlo, dhi);
+}
+
+// Three fused partial rounds (see header).  `s` enters with its round constants already added.
+__device__ __forceinline__ void partial_group(uint64_t (&s)[12], int g) {
+    QP_POSEIDON_MATS
+    uint32_t lo[12], hi[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) gl::unpack(s[i], lo[i], hi[i]);
+    uint32_t d1l, d1h, d2l, d2h, d3l, d3h, c0, c1;
+    sbox_delta(s[0], d1l, d1h);
+    // lane 0 after round 1:  (M x)_0 + d1 M00 + rc'_0
+    gl::unpack(c_grp_k[g][0], c0, c1);
+    uint64_t al = c0, ah = c1;
+    QP_DOT_ROW(m1, 0, lo, hi, al, ah)
+    al += (uint64_t)d1l * m1.a[0][0];
+    ah += (uint64_t)d1h * m1.a[0][0];
+    sbox_delta(fold_row(al, ah), d2l, d2h);
+    // lane 0 after round 2:  (M^2 x)_0 + d1 (M^2)_00 + d2 M00 + (M rc' + rc'')_0
+    gl::unpack(c_grp_k[g][1], c0, c1);
+    al = c0;
+    ah = c1;
+    QP_DOT_ROW(m2, 0, lo, hi, al, ah)
+    al += (uint64_t)d1l * m2.a[0][0] + (uint64_t)d2l * m1.a[0][0];
+    ah += (uint64_t)d1h * m2.a[0][0] + (uint64_t)d2h * m1.a[0][0];
+    sbox_delta(fold_row(al, ah), d3l, d3h);
+    // full state after round 3
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        gl::unpack(c_grp_K[g][r], c0, c1);
+        al = c0;
+        ah = c1;
+        QP_DOT_ROW(m3, r, lo, hi, al, ah)
+        al += (uint64_t)d1l * m3.a[r][0] + (uint64_t)d2l * m2.a[r][0] + (uint64_t)d3l * m1.a[r][0];
+        ah += (uint64_t)d1h * m3.a[r][0] + (uint64_t)d2h * m2.a[r][0] + (uint64_t)d3h * m1.a[r][0];
+        s[r] = fold_row(al, ah);
+    }
 }
 
 // The permutation.  State lanes may be any u64 representatives; outputs likewise.
 __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
-    // round 0 constant layer (poseidon.rs:504-513); later rounds get theirs from mds_layer
+    // round 0 constant layer (poseidon.rs:504-513); every later round gets its constants from
+    // the linear layer that precedes it
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl::add1(s[i], c_round_constants[i]);
+    for (int i = 0; i < 12; i++) s[i] = gl::add1(s[i], c_rc[i]);
 #pragma unroll 1
-    for (int r = 0; r < 4; r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = gl::pow7(s[i]);
-        mds_layer(s, c_round_constants + 12 * (r + 1));
-    }
+    for (int half = 0; half < 2; half++) {
+        // four full rounds (poseidon.rs:574-581)
+        const int base = half * 26;
 #pragma unroll 1
-    for (int r = 4; r < 26; r++) {
-        s[0] = gl::pow7(s[0]);
-        mds_layer(s, c_round_constants + 12 * (r + 1));
-    }
+        for (int r = base; r < base + 4; r++) {
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = gl::pow7(s[i]);
+            mds_layer(s, c_rc + 12 * (r + 1));  // row 30 is zero
+        }
+        if (half == 0) {
+            // 22 partial rounds (poseidon.rs:623-628): 7 fused triples + round 25
 #pragma unroll 1
-    for (int r = 26; r < 29; r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = gl::pow7(s[i]);
-        mds_layer(s, c_round_constants + 12 * (r + 1));
+            for (int g = 0; g < N_PARTIAL_GROUPS; g++) partial_group(s, g);
+            s[0] = gl::pow7(s[0]);
+            mds_layer(s, c_rc + 12 * 26);
+        }
     }
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl::pow7(s[i]);
-    mds_layer(s, nullptr);
 }
-
 
 }  // namespace poseidon

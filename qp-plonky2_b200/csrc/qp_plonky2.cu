@@ -205,11 +205,8 @@ extern "C" int qp_ctx_create(int device, void* stream, unsigned max_lde_log, qp_
         uint64_t thr = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
-    // ALL_ROUND_CONSTANTS -> constant memory (core/src/poseidon.rs:57-155)
-    cudaError_t e = cudaMemcpyToSymbolAsync(poseidon::c_round_constants, POSEIDON_ALL_ROUND_CONSTANTS,
-                                            sizeof(POSEIDON_ALL_ROUND_CONSTANTS), 0,
-                                            cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) {
+    // Poseidon round constants (+ derived constants of the fused partial rounds) -> constant memory
+    if (poseidon::upload_constants(ctx->stream) != cudaSuccess) {
         delete ctx;
         return QP_ERR_CUDA;
     }
