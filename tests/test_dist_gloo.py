@@ -1,0 +1,80 @@
+"""World-size-2 (and 4) `gloo` test of the multi-GPU plumbing (qp-plonky2_b200/dist.py): column
+sharding of the iNTT, the padded all-gather of coefficients, coset-block assignment and the
+all-gather of cap entries.  The oracle stands in for the device compute, so this runs on CPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_cols, lg_n, rate, cap_h, ret):
+    import torch.distributed as dist
+
+    import oracle
+    import qp_plonky2_b200.dist as qd
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        vals = oracle.rand_felts((n_cols, 1 << lg_n), 42)
+        want = oracle.PolynomialBatch.from_values(vals, rate, cap_h)
+        lo, hi = qd.column_shard(n_cols, world, rank)
+
+        def ifft_fn(v, rows):
+            out = np.zeros((rows, 1 << lg_n), dtype=np.uint64)
+            for k in range(v.shape[0]):
+                out[k] = oracle.ifft(v[k])
+            return out
+
+        def commit_fn(coeffs_all, first, count):
+            assert (coeffs_all == want.polynomials).all(), "gathered coefficients differ"
+            b = oracle.PolynomialBatch.from_coeffs(coeffs_all, rate, cap_h)
+            per_block = (1 << cap_h) >> rate
+            return b, b.cap[first * per_block : (first + count) * per_block].copy()
+
+        _, cap = qd.sharded_commit(vals[lo:hi], n_cols, lg_n, rate, cap_h, rank=rank, world=world,
+                                   ifft_fn=ifft_fn, commit_fn=commit_fn, all_gather_fn=qd.torch_all_gather)
+        ret[rank] = bool((cap == want.cap).all())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_cols", [(2, 5), (2, 8), (4, 7)])
+def test_sharded_commit_plumbing(world, n_cols):
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, n_cols, 6, 3, 4, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def test_shard_arithmetic():
+    import qp_plonky2_b200.dist as qd
+
+    for n_cols in (1, 5, 135, 143):
+        for world in (1, 2, 4, 8):
+            spans = [qd.column_shard(n_cols, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n_cols
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+            assert qd.padded_cols(n_cols, world) == max(b - a for a, b in spans)
+    assert [qd.block_shard(3, 4, 8, r) for r in range(8)] == [(r, 1) for r in range(8)]
+    assert [qd.block_shard(3, 4, 2, r) for r in range(2)] == [(0, 4), (4, 4)]
+    with pytest.raises(ValueError):
+        qd.block_shard(3, 4, 16, 0)      # more ranks than cosets
+    with pytest.raises(ValueError):
+        qd.block_shard(3, 1, 4, 0)       # a shard would be smaller than a cap subtree
+    with pytest.raises(ValueError):
+        qd.block_shard(3, 4, 3, 0)       # not a power of two
