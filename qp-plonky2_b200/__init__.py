@@ -25,7 +25,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libqp_plonky2_b200.so")
+# QP_PLONKY2_LIB: load a differently-built library (kernel experiments, tools/exp_variants.py)
+LIB_PATH = os.environ.get("QP_PLONKY2_LIB") or os.path.join(_HERE, "libqp_plonky2_b200.so")
 _SOURCES = [
     os.path.join(_HERE, "csrc", f)
     for f in ("qp_plonky2.cu", "goldilocks.cuh", "poseidon.cuh", "poseidon_constants.h", "ntt.cuh",

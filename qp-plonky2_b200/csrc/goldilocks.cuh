@@ -11,6 +11,12 @@
 #pragma once
 #include <cstdint>
 
+// 1: x^7 uses the explicit 4 x IMAD.WIDE product (mul_hv); measured slower than the compiler's
+// fused sequence on B200 (39.8 vs 38.8 ms), so off by default.
+#ifndef QP_POSEIDON_EXPLICIT_MUL
+#define QP_POSEIDON_EXPLICIT_MUL 0
+#endif
+
 namespace gl {
 
 static constexpr uint64_t P = 0xFFFFFFFF00000001ULL;
@@ -171,21 +177,98 @@ __device__ __forceinline__ uint64_t reduce128(uint64_t lo, uint64_t hi) {
     return reduce96(pack(t0, t1), x2);
 }
 
-// a * b (mod p) (goldilocks_field.rs:303-310).  The 128-bit product is written as a C
-// multiply so ptxas emits its fused 7-instruction IMAD.WIDE.U32 sequence (carry in a predicate).
+// 64 x 64 -> 128 bit product as (lo, hi).  Four IMAD.WIDE.U32 and a 32-bit carry chain that
+// ptxas folds into five IADD3/IADD3.X with dual carry predicates.  (Letting the compiler expand
+// `(unsigned __int128)a * b` gives 4 IMAD.WIDE + IMAD.WIDE.X + IMAD.X + MOV: 28 cycles of the
+// fma-heavy pipe instead of 16 -- that pipe is the bottleneck of the Poseidon kernels.)
+__device__ __forceinline__ void mul_wide(uint64_t a, uint64_t b, uint64_t& lo, uint64_t& hi) {
+    uint32_t a0, a1, b0, b1;
+    unpack(a, a0, a1);
+    unpack(b, b0, b1);
+    uint64_t L, M, N, H;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(L) : "r"(a0), "r"(b0));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(M) : "r"(a0), "r"(b1));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(N) : "r"(a1), "r"(b0));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(H) : "r"(a1), "r"(b1));
+    uint32_t l0, l1, m0, m1, n0, n1, h0, h1, x1, x2, x3;
+    unpack(L, l0, l1);
+    unpack(M, m0, m1);
+    unpack(N, n0, n1);
+    unpack(H, h0, h1);
+    asm("{\n\t"
+        "add.cc.u32  %0, %3, %4;\n\t"
+        "addc.cc.u32 %1, %5, %6;\n\t"
+        "addc.u32    %2, %7, 0;\n\t"
+        "add.cc.u32  %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.u32    %2, %2, 0;\n\t"
+        "}"
+        : "=&r"(x1), "=&r"(x2), "=&r"(x3)
+        : "r"(l1), "r"(m0), "r"(h0), "r"(m1), "r"(h1), "r"(n0), "r"(n1));
+    lo = pack(l0, x1);
+    hi = pack(x2, x3);
+}
+
+// a^2 as (lo, hi): three IMAD.WIDE.U32 (the cross term is added twice).
+__device__ __forceinline__ void sqr_wide(uint64_t a, uint64_t& lo, uint64_t& hi) {
+    uint32_t a0, a1;
+    unpack(a, a0, a1);
+    uint64_t L, M, H;
+    asm("mul.wide.u32 %0, %1, %1;" : "=l"(L) : "r"(a0));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(M) : "r"(a0), "r"(a1));
+    asm("mul.wide.u32 %0, %1, %1;" : "=l"(H) : "r"(a1));
+    uint32_t l0, l1, m0, m1, h0, h1, x1, x2, x3;
+    unpack(L, l0, l1);
+    unpack(M, m0, m1);
+    unpack(H, h0, h1);
+    asm("{\n\t"
+        "add.cc.u32  %0, %3, %4;\n\t"
+        "addc.cc.u32 %1, %5, %6;\n\t"
+        "addc.u32    %2, %7, 0;\n\t"
+        "add.cc.u32  %0, %0, %4;\n\t"
+        "addc.cc.u32 %1, %1, %6;\n\t"
+        "addc.u32    %2, %2, 0;\n\t"
+        "}"
+        : "=&r"(x1), "=&r"(x2), "=&r"(x3)
+        : "r"(l1), "r"(m0), "r"(h0), "r"(m1), "r"(h1));
+    lo = pack(l0, x1);
+    hi = pack(x2, x3);
+}
+
+// a * b (mod p) (goldilocks_field.rs:303-310).  Two forms with the same result:
+//   mul    -- compiler-expanded 128-bit product: fewest ALU instructions (the NTT kernels are
+//             ALU-pipe bound);
+//   mul_hv -- explicit 4 x IMAD.WIDE form: fewest fma-heavy pipe cycles (the Poseidon kernels are
+//             bound by that pipe).
 __device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) {
     unsigned __int128 p = (unsigned __int128)a * b;
     return reduce128((uint64_t)p, (uint64_t)(p >> 64));
 }
-
+__device__ __forceinline__ uint64_t mul_hv(uint64_t a, uint64_t b) {
+    uint64_t lo, hi;
+    mul_wide(a, b, lo, hi);
+    return reduce128(lo, hi);
+}
 __device__ __forceinline__ uint64_t sqr(uint64_t a) { return mul(a, a); }
+__device__ __forceinline__ uint64_t sqr_hv(uint64_t a) {
+    uint64_t lo, hi;
+    sqr_wide(a, lo, hi);
+    return reduce128(lo, hi);
+}
 
 // x^7 (core/src/poseidon.rs:546-552)
 __device__ __forceinline__ uint64_t pow7(uint64_t x) {
+#if QP_POSEIDON_EXPLICIT_MUL
+    uint64_t x2 = sqr_hv(x);
+    uint64_t x4 = sqr_hv(x2);
+    uint64_t x3 = mul_hv(x, x2);
+    return mul_hv(x3, x4);
+#else
     uint64_t x2 = sqr(x);
     uint64_t x4 = sqr(x2);
     uint64_t x3 = mul(x, x2);
     return mul(x3, x4);
+#endif
 }
 
 __device__ __forceinline__ uint64_t pow(uint64_t a, uint64_t e) {

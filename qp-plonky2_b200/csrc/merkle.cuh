@@ -70,12 +70,25 @@ struct ExtPlanesLayout {
 };
 
 // One thread per leaf.
+#ifndef QP_LEAF_MIN_BLOCKS
+#define QP_LEAF_MIN_BLOCKS 1
+#endif
+#ifndef QP_LEAF_BLOCK       // threads per block of the leaf kernel
+#define QP_LEAF_BLOCK 128
+#endif
+#ifndef QP_LEAF_SYNC        // 1: barrier per Poseidon round (all warps of the block in lockstep)
+#define QP_LEAF_SYNC 0
+#endif
 template <class Layout>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(QP_LEAF_BLOCK, QP_LEAF_MIN_BLOCKS)
 leaf_hash_kernel(Layout lay, unsigned leaf_len, TreeShape sh, uint64_t* __restrict__ digests,
                  uint64_t* __restrict__ cap) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ((size_t)1 << sh.lg_leaves)) return;
+    const size_t n_leaves = (size_t)1 << sh.lg_leaves;
+    const size_t i_raw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // threads past the end hash the last leaf again and drop the result, so that every thread
+    // of the block reaches the same barriers
+    const bool live = i_raw < n_leaves;
+    const size_t i = live ? i_raw : n_leaves - 1;
     uint64_t s[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) s[k] = 0;
@@ -96,9 +109,9 @@ leaf_hash_kernel(Layout lay, unsigned leaf_len, TreeShape sh, uint64_t* __restri
 #pragma unroll
         for (int k = 0; k < 8; k++)
             if (c + 8 + k < leaf_len) nxt[k] = lay.get(i, c + 8 + k);
-        poseidon::permute(s);
+        poseidon::permute<QP_LEAF_SYNC != 0>(s);
     }
-    store_digest(leaf_digest_ptr(sh, digests, cap, i), s);
+    if (live) store_digest(leaf_digest_ptr(sh, digests, cap, i), s);
 }
 
 // One thread per node of `layer` (1 <= layer <= num_layers): two_to_one of its children.

@@ -194,7 +194,95 @@ __device__ __forceinline__ void partial_group(uint64_t (&s)[12], int g) {
     }
 }
 
+// Experiment knobs (tools/exp_variants.py); the defaults are the measured best on B200
+// (leaf hash at 2^21 leaves x 135: unrolled 41.8 ms, ODD_IN_FULL 41.5, + SBOX_ROT 2/3/4/6 =
+// 40.1/39.5/38.8/38.3, + MDS_ROT 40.9, barrier-per-round lockstep 42-44, explicit-mul 39.8).
+// Smaller code wins until the rotation moves cost more than the instruction fetches they save.
+#ifndef QP_POSEIDON_SBOX_ROT   // L > 0: S-box layer as 12/L iterations x L lanes with a register rotation
+#define QP_POSEIDON_SBOX_ROT 6
+#endif
+#ifndef QP_POSEIDON_ODD_IN_FULL  // 1: the 22nd partial round reuses the full-round body
+#define QP_POSEIDON_ODD_IN_FULL 1
+#endif
+#ifndef QP_POSEIDON_MDS_ROT    // 1: MDS layer as 3 iterations x 4 rows with a register rotation
+#define QP_POSEIDON_MDS_ROT 0
+#endif
+
+// S-box layer on all 12 lanes (poseidon.rs:554-562)
+__device__ __forceinline__ void sbox_all(uint64_t (&s)[12]) {
+#if QP_POSEIDON_SBOX_ROT
+    constexpr int L = QP_POSEIDON_SBOX_ROT;
+#pragma unroll 1
+    for (int it = 0; it < 12 / L; it++) {
+        uint64_t t[L];
+#pragma unroll
+        for (int i = 0; i < L; i++) t[i] = gl::pow7(s[i]);
+#pragma unroll
+        for (int i = 0; i < 12 - L; i++) s[i] = s[i + L];
+#pragma unroll
+        for (int i = 0; i < L; i++) s[12 - L + i] = t[i];
+    }
+#else
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = gl::pow7(s[i]);
+#endif
+}
+
+#if QP_POSEIDON_MDS_ROT
+// state <- M * state + rc: the circulant part row r is row 0 applied to the state rotated by r,
+// so 4 rows per iteration with a rotation by 4 share one piece of code; the diagonal term
+// 8 * s[0] of row 0 is added in iteration 0 only (uniform predicate).
+__device__ __forceinline__ void mds_layer_rot(uint64_t (&s)[12], const uint64_t* rc) {
+    constexpr uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    uint32_t lo[12], hi[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) gl::unpack(s[i], lo[i], hi[i]);
+    const uint32_t d_lo = lo[0], d_hi = hi[0];
+#pragma unroll 1
+    for (int it = 0; it < 3; it++) {
+        uint64_t out[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t c0, c1;
+            gl::unpack(rc[4 * it + q], c0, c1);
+            uint64_t al = c0, ah = c1;
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+                al += (uint64_t)lo[(k + q) % 12] * C[k];
+                ah += (uint64_t)hi[(k + q) % 12] * C[k];
+            }
+            if (q == 0 && it == 0) {
+                al += (uint64_t)d_lo * 8u;
+                ah += (uint64_t)d_hi * 8u;
+            }
+            out[q] = fold_row(al, ah);
+        }
+        // rotate the halves by 4 and shift the finished rows into the state
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t tl = lo[q], th = hi[q];
+            lo[q] = lo[q + 4];
+            hi[q] = hi[q + 4];
+            lo[q + 4] = lo[q + 8];
+            hi[q + 4] = hi[q + 8];
+            lo[q + 8] = tl;
+            hi[q + 8] = th;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = s[i + 4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) s[8 + q] = out[q];
+    }
+}
+#define QP_MDS_LAYER mds_layer_rot
+#else
+#define QP_MDS_LAYER mds_layer
+#endif
+
 // The permutation.  State lanes may be any u64 representatives; outputs likewise.
+// SYNC: all threads of the block run it together and meet at a barrier per round, which keeps
+// the warps of an SM inside the same window of code (instruction-cache working set).
+template <bool SYNC = false>
 __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
     // round 0 constant layer (poseidon.rs:504-513); every later round gets its constants from
     // the linear layer that precedes it
@@ -202,20 +290,40 @@ __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
     for (int i = 0; i < 12; i++) s[i] = gl::add1(s[i], c_rc[i]);
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
-        // four full rounds (poseidon.rs:574-581)
+        // four full rounds (poseidon.rs:574-581); with ODD_IN_FULL the first half runs a fifth
+        // pass of the same body for partial round 25 (S-box on lane 0 only)
+#if QP_POSEIDON_ODD_IN_FULL
+        const int n_pass = half == 0 ? 4 : 5;
+        const int first = half == 0 ? 0 : 25;
+#pragma unroll 1
+        for (int r = first; r < first + n_pass; r++) {
+            if (SYNC) __syncthreads();
+            if (r == 25)
+                s[0] = gl::pow7(s[0]);
+            else
+                sbox_all(s);
+            QP_MDS_LAYER(s, c_rc + 12 * (r + 1));  // row 30 is zero
+        }
+#else
         const int base = half * 26;
 #pragma unroll 1
         for (int r = base; r < base + 4; r++) {
-#pragma unroll
-            for (int i = 0; i < 12; i++) s[i] = gl::pow7(s[i]);
-            mds_layer(s, c_rc + 12 * (r + 1));  // row 30 is zero
+            if (SYNC) __syncthreads();
+            sbox_all(s);
+            QP_MDS_LAYER(s, c_rc + 12 * (r + 1));  // row 30 is zero
         }
+#endif
         if (half == 0) {
             // 22 partial rounds (poseidon.rs:623-628): 7 fused triples + round 25
 #pragma unroll 1
-            for (int g = 0; g < N_PARTIAL_GROUPS; g++) partial_group(s, g);
+            for (int g = 0; g < N_PARTIAL_GROUPS; g++) {
+                if (SYNC) __syncthreads();
+                partial_group(s, g);
+            }
+#if !QP_POSEIDON_ODD_IN_FULL
             s[0] = gl::pow7(s[0]);
             mds_layer(s, c_rc + 12 * 26);
+#endif
         }
     }
 }

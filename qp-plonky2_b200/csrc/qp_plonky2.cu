@@ -469,8 +469,8 @@ static int build_tree(qp_ctx* ctx, Layout lay, unsigned leaf_len, TreeBuf* t, cu
     rc = dev_alloc(ctx, &t->cap, t->n_cap() * 4);
     if (rc) return rc;
     const size_t n_leaves = (size_t)1 << t->shape.lg_leaves;
-    LAUNCH(ctx, merkle::leaf_hash_kernel<Layout>, cdiv(n_leaves, 128), 128, 0, lay, leaf_len, t->shape,
-           t->digests, t->cap);
+    LAUNCH(ctx, merkle::leaf_hash_kernel<Layout>, cdiv(n_leaves, QP_LEAF_BLOCK), QP_LEAF_BLOCK, 0, lay, leaf_len,
+           t->shape, t->digests, t->cap);
     if (after_leaves) cudaEventRecord(after_leaves, ctx->stream);
     const unsigned nl = t->shape.num_layers();
     for (unsigned layer = 1; layer <= nl; layer++) {
