@@ -146,6 +146,9 @@ def run_ours(args):
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     dist = None
     if world > 1:
+        # keep stdout to the single JSON line: NCCL prints its version banner there
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
 
         torch.cuda.set_device(local)

@@ -41,6 +41,12 @@ struct qp_ctx {
     // coset scale tables keyed by (L, rate_bits, block_first, block_count) for the LDE
     std::map<std::vector<uint64_t>, ScaleTables> scale_cache;
     cudaEvent_t ev[8] = {};
+    // host -> device uploads of large inputs run on their own stream, in column groups, so that
+    // the transfer of group g+1 overlaps the transforms of group g (qp_batch_from_values)
+    cudaStream_t copy_stream = nullptr;
+    static constexpr int MAX_GROUPS = 16;
+    cudaEvent_t copy_ev[MAX_GROUPS] = {};
+    cudaEvent_t ready_ev = nullptr;
 };
 
 #define CUDA_TRY(ctx, expr)                                                                  \
@@ -199,6 +205,9 @@ extern "C" int qp_ctx_create(int device, void* stream, unsigned max_lde_log, qp_
         ctx->own_stream = true;
     }
     for (auto& e : ctx->ev) cudaEventCreate(&e);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (auto& e : ctx->copy_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ready_ev, cudaEventDisableTiming);
     // keep freed blocks cached in the pool: commits allocate and free multi-GB buffers
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -249,6 +258,9 @@ extern "C" void qp_ctx_destroy(qp_ctx* ctx) {
     cudaFreeAsync(ctx->tw, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
+    for (auto& e : ctx->copy_ev) cudaEventDestroy(e);
+    cudaEventDestroy(ctx->ready_ev);
+    cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -525,12 +537,10 @@ static unsigned ilog2(size_t x) {
     return k;
 }
 
-// from_coeffs on device-resident coefficients (takes ownership of d_coeffs)
-static int batch_from_device_coeffs(qp_ctx* ctx, uint64_t* d_coeffs, size_t n_cols, unsigned degree_log,
-                                    unsigned rate_bits, int blinding, unsigned cap_height,
-                                    const uint64_t* salt_dev, unsigned block_first, unsigned block_count,
-                                    float ifft_ms, qp_batch** out) {
-    const size_t n = (size_t)1 << degree_log;
+// Phase 1: the batch object and its LDE buffer (takes ownership of d_coeffs).
+static int batch_create(qp_ctx* ctx, uint64_t* d_coeffs, size_t n_cols, unsigned degree_log, unsigned rate_bits,
+                        int blinding, unsigned cap_height, unsigned block_first, unsigned block_count,
+                        qp_batch** out) {
     qp_batch* b = new qp_batch();
     b->ctx = ctx;
     b->n_cols = n_cols;
@@ -543,43 +553,48 @@ static int batch_from_device_coeffs(qp_ctx* ctx, uint64_t* d_coeffs, size_t n_co
     b->leaf_len = n_cols + (blinding ? QP_SALT_SIZE : 0);
     b->n_local = (size_t)block_count << degree_log;
     b->coeffs = d_coeffs;
-    b->ms[0] = ifft_ms;
     const unsigned shard_bits = rate_bits - ilog2(block_count);  // log2(#shards)
     b->tree.shape.lg_leaves = ilog2(b->n_local);
     b->tree.shape.cap_height = cap_height - shard_bits;
     *out = b;
+    return dev_alloc(ctx, &b->lde, b->leaf_len * b->n_local);
+}
 
-    int rc = dev_alloc(ctx, &b->lde, b->leaf_len * b->n_local);
-    if (rc) return rc;
-    cudaEventRecord(ctx->ev[1], ctx->stream);
-    // "FFT + blinding" (oracle.rs:202-206, 267-283)
+// Phase 2: "FFT + blinding" (oracle.rs:202-206, 267-283) for columns [c0, c1).
+static int batch_lde_columns(qp_batch* b, size_t c0, size_t c1) {
+    qp_ctx* ctx = b->ctx;
+    const size_t n = (size_t)1 << b->degree_log;
     const ScaleTables* st = nullptr;
-    rc = lde_scale(ctx, (int)degree_log, rate_bits, block_first, block_count, &st);
+    int rc = lde_scale(ctx, (int)b->degree_log, b->rate_bits, b->block_first, b->block_count, &st);
     if (rc) return rc;
     NttJob job;
-    job.src = d_coeffs;
-    job.dst = b->lde;
-    job.L = (int)degree_log;
-    job.n_vec = (unsigned)(n_cols * block_count);
-    job.inner_bits = (int)ilog2(block_count);
+    job.src = b->coeffs + c0 * n;
+    job.dst = b->lde + c0 * b->n_local;
+    job.L = (int)b->degree_log;
+    job.n_vec = (unsigned)((c1 - c0) * b->block_count);
+    job.inner_bits = (int)ilog2(b->block_count);
     job.src_outer = n;
     job.src_inner = 0;
     job.dst_outer = b->n_local;
     job.dst_inner = n;
     job.scale = st;
     job.out_mode = ntt::OUT_NATURAL;
-    rc = run_ntt(ctx, job);
-    if (rc) return rc;
-    if (blinding) {
+    return run_ntt(ctx, job);
+}
+
+// Phase 3: salt columns, "build Merkle tree" (oracle.rs:210-214), timings.  ev[1] must have been
+// recorded where the LDE phase started.
+static int batch_finish(qp_batch* b, const uint64_t* salt_dev) {
+    qp_ctx* ctx = b->ctx;
+    if (b->blinding) {
         LAUNCH(ctx, salt_to_leaf_order_kernel, cdiv(QP_SALT_SIZE * b->n_local, 256), 256, 0, salt_dev,
-               b->lde + n_cols * b->n_local, degree_log + rate_bits, (size_t)block_first << degree_log,
-               b->n_local);
+               b->lde + b->n_cols * b->n_local, b->degree_log + b->rate_bits,
+               (size_t)b->block_first << b->degree_log, b->n_local);
     }
     cudaEventRecord(ctx->ev[2], ctx->stream);
     // "transpose LDEs" is fused away: the LDE is already in leaf order, column-major.
-    // "build Merkle tree" (oracle.rs:210-214)
     merkle::AffineLayout lay{b->lde, b->n_local, 1};
-    rc = build_tree(ctx, lay, (unsigned)b->leaf_len, &b->tree, ctx->ev[5]);
+    int rc = build_tree(ctx, lay, (unsigned)b->leaf_len, &b->tree, ctx->ev[5]);
     if (rc) return rc;
     cudaEventRecord(ctx->ev[3], ctx->stream);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -588,6 +603,20 @@ static int batch_from_device_coeffs(qp_ctx* ctx, uint64_t* d_coeffs, size_t n_co
     cudaEventElapsedTime(&b->ms_leaf_hash, ctx->ev[2], ctx->ev[5]);
     cudaEventElapsedTime(&b->ms_tree_levels, ctx->ev[5], ctx->ev[3]);
     return QP_OK;
+}
+
+// from_coeffs on device-resident coefficients (takes ownership of d_coeffs)
+static int batch_from_device_coeffs(qp_ctx* ctx, uint64_t* d_coeffs, size_t n_cols, unsigned degree_log,
+                                    unsigned rate_bits, int blinding, unsigned cap_height,
+                                    const uint64_t* salt_dev, unsigned block_first, unsigned block_count,
+                                    qp_batch** out) {
+    int rc = batch_create(ctx, d_coeffs, n_cols, degree_log, rate_bits, blinding, cap_height, block_first,
+                          block_count, out);
+    if (rc) return rc;
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    rc = batch_lde_columns(*out, 0, n_cols);
+    if (rc) return rc;
+    return batch_finish(*out, salt_dev);
 }
 
 static int check_batch_args(qp_ctx* ctx, size_t n_cols, unsigned degree_log, unsigned rate_bits, int blinding,
@@ -632,7 +661,7 @@ extern "C" int qp_batch_from_coeffs(qp_ctx* ctx, const uint64_t* coeffs, int spa
         if (rc) return rc;
     }
     rc = batch_from_device_coeffs(ctx, d_coeffs, n_cols, degree_log, rate_bits, blinding, cap_height, d_salt,
-                                  block_first, block_count, 0.f, out);
+                                  block_first, block_count, out);
     dev_free(ctx, salt_owned);
     if (rc) {
         qp_batch_free(*out);
@@ -665,38 +694,89 @@ extern "C" int qp_batch_from_values(qp_ctx* ctx, const uint64_t* values, int spa
     if (rc) return rc;
     if (!values) return fail(ctx, QP_ERR_BAD_ARG, "null values");
     const size_t n = (size_t)1 << degree_log;
-    const uint64_t* d_values = nullptr;
-    uint64_t* values_owned = nullptr;
-    rc = to_device(ctx, values, space, n_cols * n, &d_values, &values_owned);
-    if (rc) return rc;
     uint64_t* d_coeffs = nullptr;
     rc = dev_alloc(ctx, &d_coeffs, n_cols * n);
     if (rc) return rc;
-    // "IFFT" (oracle.rs:176-180)
-    cudaEventRecord(ctx->ev[0], ctx->stream);
-    rc = ifft_device(ctx, d_values, n_cols, degree_log, d_coeffs, values_owned);
-    cudaEventRecord(ctx->ev[4], ctx->stream);
-    dev_free(ctx, values_owned);
-    if (rc) {
-        dev_free(ctx, d_coeffs);
-        return rc;
-    }
     const uint64_t* d_salt = nullptr;
     uint64_t* salt_owned = nullptr;
-    if (blinding) {
-        rc = to_device(ctx, salt, space, (size_t)QP_SALT_SIZE << (degree_log + rate_bits), &d_salt, &salt_owned);
+
+    // Host input of at least 64 MiB: upload in column groups on the copy stream and run the
+    // iNTT + LDE of group g while group g+1 is still in flight.
+    const bool pipelined = space != QP_DEVICE && n_cols * n * 8 >= ((size_t)64 << 20) && n_cols >= 2;
+    if (!pipelined) {
+        const uint64_t* d_values = nullptr;
+        uint64_t* values_owned = nullptr;
+        rc = to_device(ctx, values, space, n_cols * n, &d_values, &values_owned);
         if (rc) return rc;
+        // "IFFT" (oracle.rs:176-180)
+        cudaEventRecord(ctx->ev[0], ctx->stream);
+        rc = ifft_device(ctx, d_values, n_cols, degree_log, d_coeffs, values_owned);
+        cudaEventRecord(ctx->ev[4], ctx->stream);
+        dev_free(ctx, values_owned);
+        if (rc) {
+            dev_free(ctx, d_coeffs);
+            return rc;
+        }
+        if (blinding) {
+            rc = to_device(ctx, salt, space, (size_t)QP_SALT_SIZE << (degree_log + rate_bits), &d_salt, &salt_owned);
+            if (rc) return rc;
+        }
+        rc = batch_from_device_coeffs(ctx, d_coeffs, n_cols, degree_log, rate_bits, blinding, cap_height, d_salt,
+                                      block_first, block_count, out);
+        dev_free(ctx, salt_owned);
+        if (rc) {
+            qp_batch_free(*out);
+            *out = nullptr;
+            return rc;
+        }
+        cudaEventElapsedTime(&(*out)->ms[0], ctx->ev[0], ctx->ev[4]);
+        return QP_OK;
     }
-    rc = batch_from_device_coeffs(ctx, d_coeffs, n_cols, degree_log, rate_bits, blinding, cap_height, d_salt,
-                                  block_first, block_count, 0.f, out);
+
+    uint64_t* d_values = nullptr;
+    rc = dev_alloc(ctx, &d_values, n_cols * n);
+    if (!rc) rc = batch_create(ctx, d_coeffs, n_cols, degree_log, rate_bits, blinding, cap_height, block_first,
+                               block_count, out);
+    if (rc) {
+        dev_free(ctx, d_values);
+        if (*out) {
+            qp_batch_free(*out);
+            *out = nullptr;
+        } else {
+            dev_free(ctx, d_coeffs);
+        }
+        return rc;
+    }
+    const int n_groups = (int)(n_cols < 9 ? n_cols : 9);
+    const size_t per = (n_cols + n_groups - 1) / n_groups;
+    // the copy stream may only touch d_values once the (stream-ordered) allocation has happened
+    cudaEventRecord(ctx->ready_ev, ctx->stream);
+    cudaStreamWaitEvent(ctx->copy_stream, ctx->ready_ev, 0);
+    for (int g = 0; g < n_groups; g++) {
+        const size_t c0 = g * per, c1 = (c0 + per < n_cols) ? c0 + per : n_cols;
+        if (c0 >= c1) break;
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_values + c0 * n, values + c0 * n, (c1 - c0) * n * 8, cudaMemcpyHostToDevice,
+                                      ctx->copy_stream));
+        cudaEventRecord(ctx->copy_ev[g], ctx->copy_stream);
+    }
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    for (int g = 0; g < n_groups && !rc; g++) {
+        const size_t c0 = g * per, c1 = (c0 + per < n_cols) ? c0 + per : n_cols;
+        if (c0 >= c1) break;
+        cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[g], 0);
+        rc = ifft_device(ctx, d_values + c0 * n, c1 - c0, degree_log, d_coeffs + c0 * n, d_values + c0 * n);
+        if (!rc) rc = batch_lde_columns(*out, c0, c1);
+    }
+    dev_free(ctx, d_values);
+    if (!rc && blinding)
+        rc = to_device(ctx, salt, space, (size_t)QP_SALT_SIZE << (degree_log + rate_bits), &d_salt, &salt_owned);
+    if (!rc) rc = batch_finish(*out, d_salt);  // ms[1] = iNTT + LDE + upload wait ("IFFT" is folded into it)
     dev_free(ctx, salt_owned);
     if (rc) {
         qp_batch_free(*out);
         *out = nullptr;
-        return rc;
     }
-    cudaEventElapsedTime(&(*out)->ms[0], ctx->ev[0], ctx->ev[4]);
-    return QP_OK;
+    return rc;
 }
 
 extern "C" int qp_ifft_columns(qp_ctx* ctx, const uint64_t* values, int space, size_t n_cols,

@@ -196,6 +196,19 @@ def test_batch_from_values_parity(qp, ctx, lg_n, cols, rate, cap_h, salt):
     assert set(got.timing) == {"IFFT", "FFT + blinding", "transpose LDEs", "build Merkle tree"}
 
 
+def test_batch_pipelined_host_upload(qp, ctx):
+    """host inputs >= 64 MiB take the column-group pipeline (upload overlapped with iNTT + LDE);
+    2^16 x 135 is 70.8 MB.  Same commitment as the oracle, bit for bit."""
+    vals = oracle.rand_felts((135, 1 << 16), 4242)
+    want = oracle.PolynomialBatch.from_values(vals, 3, 4)
+    got = qp.PolynomialBatch.from_values(ctx, vals, 3, False, 4)
+    assert (got.merkle_tree.cap == want.cap).all()
+    assert (got.polynomials == want.polynomials).all()
+    assert (got.merkle_tree.digests == want.digests).all()
+    idx = [0, 1, 77777, (1 << 19) - 1]
+    assert (got.merkle_tree.get_many(idx) == want.leaves[idx]).all()
+
+
 def test_batch_device_input(qp, ctx):
     """inputs already resident in HBM (torch CUDA tensor) give the same commitment"""
     import torch
