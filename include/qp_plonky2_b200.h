@@ -151,6 +151,36 @@ size_t qp_fri_tree_digests_len(const qp_fri* f, unsigned round);
 unsigned qp_fri_num_rounds(const qp_fri* f);
 void qp_fri_free(qp_fri* f);
 
+/* ---- opening side of prove_openings (plonky2/src/fri/oracle.rs:320-358) --------------------- */
+/* PolynomialCoeffs::eval of every polynomial of the batch at an F_p^2 point -- the work of
+ * OpeningSet::new (plonky2/src/plonk/proof.rs:289-327, field/src/polynomial/mod.rs:155-160).
+ * out: [n_cols][2] (host). */
+int qp_batch_eval_polys(const qp_batch* b, const uint64_t point[2], uint64_t* out);
+
+/* reduce_openings_to_unmasked_final_poly (oracle.rs:129-165) followed by the padded coset FFT
+ * (oracle.rs:329-343), entirely on the device; the result is a FRI state ready for
+ * qp_fri_commit_round.  The caller flattens the FriInstanceInfo into, per batch (= per opening
+ * point), a list of (polynomial, F_p^2 weight) terms: an opening expression at position i of the
+ * batch contributes alpha^i * coefficient (One -> 1, PointPower(k) -> point^k, Constant(c) -> c)
+ * for each of its terms (core/src/fri_structure.rs:59-108, core/src/reducing.rs:63-72).  `shift`
+ * is alpha^(number of expressions of this batch), applied to the running sum before this batch's
+ * quotient is added (shift_poly, reducing.rs:94-97).  All batches must have the same degree. */
+typedef struct {
+    const qp_batch* batch;   /* oracle holding the polynomial */
+    size_t poly_index;       /* column inside that oracle */
+    uint64_t weight[2];
+} qp_opening_term;
+typedef struct {
+    uint64_t point[2];
+    const qp_opening_term* terms;
+    size_t n_terms;
+    uint64_t shift[2];
+} qp_opening_batch;
+int qp_fri_begin_from_openings(qp_ctx* ctx, const qp_opening_batch* batches, size_t n_batches,
+                               unsigned degree_log, unsigned rate_bits, unsigned cap_height, qp_fri** out);
+/* The unmasked final polynomial produced by the call above: [2^degree_log][2] (host). */
+int qp_fri_initial_coeffs(const qp_fri* f, uint64_t* out);
+
 /* Proof-of-work grinding (plonky2/src/fri/prover.rs:159-208).  `state12` is the duplex state
  * with the pending inputs already written (duplex_intermediate_state), `witness_pos` the lane
  * the candidate goes to.  Returns the SMALLEST witness whose response (lane 7 after the

@@ -43,6 +43,11 @@ int qp_fri_committed_trees(qp_ctx* ctx, const uint64_t* coeffs_ext, const uint64
                            uint64_t* caps_out, uint64_t* final_poly_out, size_t* final_len_out,
                            qp_fri** fri_out);
 
+/* The same loop on an existing FRI state (e.g. one built by qp_fri_begin_from_openings). */
+int qp_fri_run_commit_phase(qp_fri* f, unsigned cap_height, const unsigned* arity_bits, unsigned n_rounds,
+                            qp_challenger* challenger, uint64_t* caps_out, uint64_t* final_poly_out,
+                            size_t* final_len_out);
+
 /* fri_proof_of_work (prover.rs:159-208): grinds on the device, then observes the witness and
  * draws the response on the transcript, as the reference does. */
 int qp_fri_grind(qp_ctx* ctx, qp_challenger* challenger, unsigned proof_of_work_bits, uint64_t* witness_out);

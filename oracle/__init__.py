@@ -117,6 +117,8 @@ def lib():
              C.POINTER(u64p), C.POINTER(u64p), u64p, u64p],
         ),
         "orc_fri_proof_of_work": (u64, [C.POINTER(Challenger), u32]),
+        "orc_eval_poly_ext": (None, [u64p, sz, u64p, u64p]),
+        "orc_reduce_openings": (None, [sz, C.POINTER(sz), C.POINTER(u64p), u64p, u64p, u64p, u32, u64p]),
         "orc_num_threads": (C.c_int, []),
     }
     for name, (res, args) in sig.items():
@@ -337,3 +339,28 @@ def fri_committed_trees(coeffs, values, rate_bits, cap_height, arity_bits, chall
 
 def fri_proof_of_work(challenger, pow_bits):
     return int(lib().orc_fri_proof_of_work(C.byref(challenger), pow_bits))
+
+
+def eval_poly_ext(coeffs, point):
+    """PolynomialCoeffs::eval at an F_p^2 point -> (c0, c1)"""
+    a = np.ascontiguousarray(np.asarray(coeffs, dtype=np.uint64))
+    pt = np.array(point, dtype=np.uint64)
+    out = np.zeros(2, dtype=np.uint64)
+    lib().orc_eval_poly_ext(_ptr(a), a.size, _ptr(pt), _ptr(out))
+    return out
+
+
+def reduce_openings(batches, degree_log):
+    """reduce_openings_to_unmasked_final_poly.  batches: list of dict(point=(a,b), shift=(a,b),
+    terms=[(poly ndarray[n], (w0, w1)), ...]).  Returns final poly [n][2]."""
+    nb = len(batches)
+    n_terms = (C.c_size_t * nb)(*[len(b["terms"]) for b in batches])
+    polys = [np.ascontiguousarray(np.asarray(p, dtype=np.uint64)) for b in batches for p, _ in b["terms"]]
+    ptrs = (u64p * max(len(polys), 1))(*[_ptr(p) for p in polys])
+    w = np.array([list(wt) for b in batches for _, wt in b["terms"]], dtype=np.uint64).reshape(-1, 2)
+    pts = np.array([list(b["point"]) for b in batches], dtype=np.uint64)
+    sh = np.array([list(b["shift"]) for b in batches], dtype=np.uint64)
+    out = np.zeros((1 << degree_log, 2), dtype=np.uint64)
+    lib().orc_reduce_openings(nb, n_terms, ptrs, _ptr(np.ascontiguousarray(w)) if w.size else None, _ptr(pts), _ptr(sh),
+                              degree_log, _ptr(out))
+    return out

@@ -716,3 +716,72 @@ uint64_t orc_fri_proof_of_work(orc_challenger *ch, unsigned pow_bits) {
     (void)orc_challenger_get(ch);
     return w;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Opening side of prove_openings
+ * ---------------------------------------------------------------------------------------- */
+
+/* field/src/polynomial/mod.rs:155-160 (eval: Horner from the leading coefficient), with the base
+ * coefficients embedded in F_p^2 (to_extension, proof.rs:299-304). */
+void orc_eval_poly_ext(const uint64_t *coeffs, size_t n, const uint64_t point[2], uint64_t out[2]) {
+    uint64_t acc[2] = {0, 0};
+    for (size_t i = n; i-- > 0;) {
+        uint64_t t[2];
+        orc_ext_mul(acc, point, t);
+        acc[0] = gl_add(t[0], coeffs[i]);
+        acc[1] = t[1];
+    }
+    out[0] = orc_gl_canon(acc[0]);
+    out[1] = orc_gl_canon(acc[1]);
+}
+
+/* plonky2/src/fri/oracle.rs:129-165.  composition = sum_t weight_t * poly_t (the alpha-powers and
+ * FriCoefficient values are folded into the weights by the caller, reducing.rs:63-72);
+ * quotient = divide_by_linear(point) (division.rs:77-90) padded with one zero;
+ * final = final * shift + quotient (reducing.rs:94-97). */
+void orc_reduce_openings(size_t n_batches, const size_t *n_terms, const uint64_t *const *term_polys,
+                         const uint64_t *weights, const uint64_t *points, const uint64_t *shifts,
+                         unsigned degree_log, uint64_t *final_out) {
+    size_t n = (size_t)1 << degree_log;
+    uint64_t *comp = (uint64_t *)malloc(n * 16);
+    uint64_t *bs = (uint64_t *)malloc(n * 16);
+    size_t base = 0;
+    for (size_t i = 0; i < 2 * n; i++) final_out[i] = 0;
+    for (size_t b = 0; b < n_batches; b++) {
+        for (size_t j = 0; j < n; j++) {
+            uint64_t a0 = 0, a1 = 0;
+            for (size_t t = 0; t < n_terms[b]; t++) {
+                uint64_t c = term_polys[base + t][j];
+                a0 = gl_add(a0, gl_mul(weights[2 * (base + t)], c));
+                a1 = gl_add(a1, gl_mul(weights[2 * (base + t) + 1], c));
+            }
+            comp[2 * j] = a0;
+            comp[2 * j + 1] = a1;
+        }
+        /* divide_by_linear: bs = scan from the top of acc = acc*z + c; drop the last (= p(z)); reverse */
+        const uint64_t *z = points + 2 * b;
+        uint64_t acc[2] = {0, 0};
+        for (size_t i = n; i-- > 0;) {
+            uint64_t t[2];
+            orc_ext_mul(acc, z, t);
+            acc[0] = gl_add(t[0], comp[2 * i]);
+            acc[1] = gl_add(t[1], comp[2 * i + 1]);
+            bs[2 * i] = acc[0];
+            bs[2 * i + 1] = acc[1];
+        }
+        /* quotient[k] = bs[k+1] for k < n-1, quotient[n-1] = 0 (the pushed zero) */
+        for (size_t k = 0; k < n; k++) {
+            uint64_t q[2] = {0, 0}, f[2];
+            if (k + 1 < n) {
+                q[0] = bs[2 * (k + 1)];
+                q[1] = bs[2 * (k + 1) + 1];
+            }
+            orc_ext_mul(final_out + 2 * k, shifts + 2 * b, f);
+            final_out[2 * k] = orc_gl_canon(gl_add(f[0], q[0]));
+            final_out[2 * k + 1] = orc_gl_canon(gl_add(f[1], q[1]));
+        }
+        base += n_terms[b];
+    }
+    free(comp);
+    free(bs);
+}

@@ -113,6 +113,15 @@ int orc_fri_committed_trees(uint64_t *coeffs, uint64_t *values, unsigned lg_n, u
  * maybe_rayon/src/lib.rs:254-259; plonky2/src/fri/prover.rs:159-208). */
 uint64_t orc_fri_proof_of_work(orc_challenger *challenger, unsigned pow_bits);
 
+/* ---- opening side (plonky2/src/fri/oracle.rs:129-165, plonky2/src/plonk/proof.rs:289-327) ---- */
+/* PolynomialCoeffs::eval of a base-field polynomial at an F_p^2 point (Horner). */
+void orc_eval_poly_ext(const uint64_t *coeffs, size_t n, const uint64_t point[2], uint64_t out[2]);
+/* reduce_openings_to_unmasked_final_poly with the instance flattened the same way as the C ABI:
+ * batch b has n_terms[b] (polynomial pointer, weight) terms, a point and a shift. */
+void orc_reduce_openings(size_t n_batches, const size_t *n_terms, const uint64_t *const *term_polys,
+                         const uint64_t *weights, const uint64_t *points, const uint64_t *shifts,
+                         unsigned degree_log, uint64_t *final_out /* [n][2] */);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

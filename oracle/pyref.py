@@ -279,3 +279,29 @@ def fri_committed_trees(coeffs, values, rate_bits, cap_height, arity_bits, chall
         values = list(zip(lane0, lane1))
     final = coeffs[: len(coeffs) >> rate_bits]
     return caps, betas, final, trees
+
+
+# ----- opening side (plonky2/src/fri/oracle.rs:129-165) --------------------------------------
+def eval_poly_ext(coeffs, point):
+    acc = (0, 0)
+    for c in reversed(coeffs):
+        acc = ext_add(ext_mul(acc, point), (c % P, 0))
+    return acc
+
+
+def reduce_openings(batches, n):
+    """batches: list of dict(point, shift, terms=[(poly list, weight)]) -> final poly list of ext."""
+    final = [(0, 0)] * n
+    for b in batches:
+        comp = [(0, 0)] * n
+        for poly, w in b["terms"]:
+            comp = [ext_add(comp[j], ((w[0] * poly[j]) % P, (w[1] * poly[j]) % P)) for j in range(n)]
+        # (comp(X) - comp(z)) / (X - z) by synthetic division, then one zero pad
+        z = b["point"]
+        q = [(0, 0)] * n
+        acc = (0, 0)
+        for i in range(n - 1, 0, -1):
+            acc = ext_add(ext_mul(acc, z), comp[i])
+            q[i - 1] = acc
+        final = [ext_add(ext_mul(final[k], b["shift"]), q[k]) for k in range(n)]
+    return final

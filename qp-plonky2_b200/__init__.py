@@ -153,6 +153,11 @@ def lib():
         "qp_fri_num_rounds": (u32, [vp]),
         "qp_fri_free": (None, [vp]),
         "qp_fri_proof_of_work": (i32, [vp, vp, u32, u32, u64p]),
+        "qp_batch_eval_polys": (i32, [vp, vp, vp]),
+        "qp_fri_begin_from_openings": (i32, [vp, vp, sz, u32, u32, u32, pp]),
+        "qp_fri_initial_coeffs": (i32, [vp, vp]),
+        "qp_fri_run_commit_phase": (i32, [vp, u32, C.POINTER(u32), u32, C.POINTER(_ChallengerState), vp, vp,
+                                          C.POINTER(sz)]),
         # host transcript mirror (include/qp_plonky2_host.h)
         "qp_challenger_init": (None, [C.POINTER(_ChallengerState)]),
         "qp_challenger_observe": (None, [C.POINTER(_ChallengerState), vp, sz]),
@@ -387,6 +392,14 @@ class PolynomialBatch:
         self.ctx.check(lib().qp_batch_get_lde_values(self._h, index, step, _np_ptr(out)))
         return out
 
+    def eval_polys(self, point):
+        """Every polynomial of the batch evaluated at an F_p^2 point (OpeningSet::new,
+        plonky2/src/plonk/proof.rs:289-327) -> [n_cols][2]."""
+        pt = np.array([int(point[0]), int(point[1])], dtype=np.uint64)
+        out = np.zeros((self.n_cols, 2), dtype=np.uint64)
+        self.ctx.check(lib().qp_batch_eval_polys(self._h, _np_ptr(pt), _np_ptr(out)))
+        return out
+
     @property
     def device_lde_ptr(self):
         return lib().qp_batch_device_lde(self._h)
@@ -553,6 +566,58 @@ def fri_committed_trees(ctx, coeffs, values, challenger, rate_bits, cap_height, 
                                       C.byref(flen), C.byref(h))
     ctx.check(rc)
     return FriCommitment(ctx, h, caps, final, arity_bits, lg, cap_height)
+
+
+class _OpeningTerm(C.Structure):
+    _fields_ = [("batch", C.c_void_p), ("poly_index", C.c_size_t), ("weight", C.c_uint64 * 2)]
+
+
+class _OpeningBatch(C.Structure):
+    _fields_ = [("point", C.c_uint64 * 2), ("terms", C.POINTER(_OpeningTerm)), ("n_terms", C.c_size_t),
+                ("shift", C.c_uint64 * 2)]
+
+
+def fri_from_openings(ctx, batches, degree_log, rate_bits, cap_height):
+    """reduce_openings_to_unmasked_final_poly + padded coset FFT on the device
+    (plonky2/src/fri/oracle.rs:129-165, 329-343).  batches: list of dict(point=(a, b), shift=(a, b),
+    terms=[(PolynomialBatch, poly_index, (w0, w1)), ...]).  Returns a FriCommitment whose commit
+    phase has not run yet (use fri_commit_phase)."""
+    keep = []
+    arr = (_OpeningBatch * len(batches))()
+    for i, b in enumerate(batches):
+        terms = (_OpeningTerm * max(len(b["terms"]), 1))()
+        for k, (pb, idx, w) in enumerate(b["terms"]):
+            terms[k].batch = pb._h
+            terms[k].poly_index = idx
+            terms[k].weight[0], terms[k].weight[1] = int(w[0]), int(w[1])
+        keep.append(terms)
+        arr[i].point[0], arr[i].point[1] = int(b["point"][0]), int(b["point"][1])
+        arr[i].terms = terms
+        arr[i].n_terms = len(b["terms"])
+        arr[i].shift[0], arr[i].shift[1] = int(b["shift"][0]), int(b["shift"][1])
+    h = C.c_void_p()
+    ctx.check(lib().qp_fri_begin_from_openings(ctx._h, arr, len(batches), degree_log, rate_bits, cap_height, C.byref(h)))
+    return FriCommitment(ctx, h, None, None, [], degree_log + rate_bits, cap_height)
+
+
+def fri_commit_phase(fri, challenger, rate_bits, arity_bits):
+    """fri_committed_trees' loop (prover.rs:93-126) on an existing device FRI state."""
+    R = len(arity_bits)
+    n = 1 << fri.lg_n
+    caps = np.zeros((R, 1 << fri.cap_height, 4), dtype=np.uint64)
+    final = np.zeros(((n >> sum(arity_bits)) >> rate_bits, 2), dtype=np.uint64)
+    ab = (C.c_uint * max(R, 1))(*arity_bits)
+    flen = C.c_size_t()
+    fri.ctx.check(lib().qp_fri_run_commit_phase(fri._h, fri.cap_height, ab, R, C.byref(challenger._s), _np_ptr(caps),
+                                                _np_ptr(final) if final.size else None, C.byref(flen)))
+    fri.caps, fri.final_poly, fri.arity_bits = caps, final, list(arity_bits)
+    return fri
+
+
+def fri_initial_coeffs(fri, degree_log):
+    out = np.zeros((1 << degree_log, 2), dtype=np.uint64)
+    fri.ctx.check(lib().qp_fri_initial_coeffs(fri._h, _np_ptr(out)))
+    return out
 
 
 def fri_proof_of_work(ctx, challenger, proof_of_work_bits) -> int:

@@ -18,6 +18,7 @@
 #include "goldilocks.cuh"
 #include "merkle.cuh"
 #include "ntt.cuh"
+#include "openings.cuh"
 #include "poseidon.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -1074,6 +1075,8 @@ struct qp_fri {
     uint64_t* coeffs = nullptr;   // planes [2][2^cur_lg], natural order
     uint64_t* values = nullptr;   // planes of the NEXT round to commit (bit-reversed)
     uint64_t shift = gl::GENERATOR;
+    uint64_t* initial = nullptr;  // planes [2][2^initial_lg]: the unmasked final poly (from openings)
+    unsigned initial_lg = 0;
     std::vector<FriRound> rounds;
     bool committed = false;       // a commit_round awaits its fold_round
 };
@@ -1111,6 +1114,189 @@ extern "C" int qp_fri_begin(qp_ctx* ctx, const uint64_t* coeffs_ext, const uint6
         qp_fri_free(f);
         *out = nullptr;
     }
+    return rc;
+}
+
+// ---- host-side F_p^2 helpers (a handful of scalars per call; table seeds only) ----------------
+namespace hx {
+typedef unsigned __int128 u128;
+struct E {
+    uint64_t a, b;
+};
+static inline uint64_t fmul(uint64_t x, uint64_t y) { return (uint64_t)(((u128)x * y) % gl::P); }
+static inline uint64_t fadd(uint64_t x, uint64_t y) { return (uint64_t)(((u128)x + y) % gl::P); }
+static inline uint64_t fsub(uint64_t x, uint64_t y) { return (uint64_t)(((u128)x + gl::P - y % gl::P) % gl::P); }
+static inline E mul(E x, E y) {  // X^2 = 7
+    return E{fadd(fmul(x.a, y.a), fmul(7, fmul(x.b, y.b))), fadd(fmul(x.a, y.b), fmul(x.b, y.a))};
+}
+static inline E inv(E x) {  // (a - bX) / (a^2 - 7 b^2)
+    uint64_t nrm = fsub(fmul(x.a, x.a), fmul(7, fmul(x.b, x.b)));
+    uint64_t ni = gl::host_pow(nrm, gl::P - 2);
+    return E{fmul(x.a, ni), fmul(fsub(0, x.b), ni)};
+}
+}  // namespace hx
+
+// planes [2][2^lg_n] of z^i on the device
+static int build_power_table(qp_ctx* ctx, hx::E z, unsigned lg_n, uint64_t** out) {
+    uint64_t sq[64];
+    hx::E cur = z;
+    for (int b = 0; b < 32; b++) {
+        sq[2 * b] = cur.a;
+        sq[2 * b + 1] = cur.b;
+        cur = hx::mul(cur, cur);
+    }
+    uint64_t* d_sq = nullptr;
+    int rc = dev_alloc(ctx, &d_sq, 64);
+    if (!rc) rc = dev_alloc(ctx, out, (size_t)2 << lg_n);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_sq, sq, sizeof sq, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // sq is a stack array
+    LAUNCH(ctx, openings::power_table_kernel, cdiv((size_t)1 << lg_n, 256), 256, 0, d_sq, lg_n, *out);
+    dev_free(ctx, d_sq);
+    return QP_OK;
+}
+
+extern "C" int qp_batch_eval_polys(const qp_batch* b, const uint64_t point[2], uint64_t* out) {
+    if (!b) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = b->ctx;
+    if (!point || !out) return fail(ctx, QP_ERR_BAD_ARG, "null argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    uint64_t* pw = nullptr;
+    uint64_t* d_out = nullptr;
+    int rc = build_power_table(ctx, hx::E{point[0] % gl::P, point[1] % gl::P}, b->degree_log, &pw);
+    if (!rc) rc = dev_alloc(ctx, &d_out, 2 * b->n_cols);
+    if (!rc) {
+        LAUNCH(ctx, openings::eval_polys_kernel, (unsigned)b->n_cols, 256, 0, b->coeffs, (size_t)1 << b->degree_log, pw,
+               d_out);
+        rc = copy_out(ctx, out, QP_HOST, d_out, 2 * b->n_cols);
+    }
+    dev_free(ctx, pw);
+    dev_free(ctx, d_out);
+    return rc;
+}
+
+// values <- coset LDE (shift g) of the coefficient planes, in bit-reversed order; also keeps the
+// zero-padded coefficient planes the fold kernel reads.
+static int fri_from_device_planes(qp_ctx* ctx, uint64_t* fin /* [2][n], consumed */, unsigned degree_log,
+                                  unsigned rate_bits, unsigned cap_height, qp_fri** out) {
+    const size_t n = (size_t)1 << degree_log, N = n << rate_bits;
+    qp_fri* f = new qp_fri();
+    f->ctx = ctx;
+    f->lg_n = f->cur_lg = degree_log + rate_bits;
+    f->rate_bits = rate_bits;
+    f->cap_height = cap_height;
+    f->initial = fin;
+    f->initial_lg = degree_log;
+    *out = f;
+    int rc = dev_alloc(ctx, &f->coeffs, 2 * N);
+    if (!rc) rc = dev_alloc(ctx, &f->values, 2 * N);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemsetAsync(f->coeffs, 0, 2 * N * 8, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(f->coeffs, fin, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(f->coeffs + N, fin + n, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    const ScaleTables* st = nullptr;
+    rc = lde_scale(ctx, (int)degree_log, rate_bits, 0, 1u << rate_bits, &st);
+    if (rc) return rc;
+    NttJob job;
+    job.src = fin;
+    job.dst = f->values;
+    job.L = (int)degree_log;
+    job.n_vec = 2u << rate_bits;
+    job.inner_bits = (int)rate_bits;
+    job.src_outer = n;
+    job.src_inner = 0;
+    job.dst_outer = N;
+    job.dst_inner = n;
+    job.scale = st;
+    return run_ntt(ctx, job);
+}
+
+extern "C" int qp_fri_begin_from_openings(qp_ctx* ctx, const qp_opening_batch* batches, size_t n_batches,
+                                          unsigned degree_log, unsigned rate_bits, unsigned cap_height,
+                                          qp_fri** out) {
+    if (!ctx) return QP_ERR_BAD_ARG;
+    if (!out) return fail(ctx, QP_ERR_BAD_ARG, "null out");
+    *out = nullptr;
+    if (!batches || n_batches == 0) return fail(ctx, QP_ERR_BAD_ARG, "no opening batches");
+    if (degree_log + rate_bits > ctx->tw_lg) return fail(ctx, QP_ERR_TOO_LARGE, "FRI domain larger than max_lde_log");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)1 << degree_log;
+    const size_t n_seg = (n + openings::SCAN_SEG - 1) / openings::SCAN_SEG;
+    uint64_t *fin = nullptr, *d = nullptr, *totals = nullptr;
+    int rc = dev_alloc(ctx, &fin, 2 * n);
+    if (!rc) rc = dev_alloc(ctx, &d, 2 * n);
+    if (!rc) rc = dev_alloc(ctx, &totals, 2 * n_seg);
+    for (size_t bi = 0; bi < n_batches && !rc; bi++) {
+        const qp_opening_batch& ob = batches[bi];
+        if (!ob.terms && ob.n_terms) rc = fail(ctx, QP_ERR_BAD_ARG, "null terms");
+        std::vector<const uint64_t*> ptrs(ob.n_terms);
+        std::vector<uint64_t> w(2 * ob.n_terms);
+        for (size_t t = 0; t < ob.n_terms && !rc; t++) {
+            const qp_batch* pb = ob.terms[t].batch;
+            if (!pb || pb->ctx != ctx || pb->degree_log != degree_log || ob.terms[t].poly_index >= pb->n_cols)
+                rc = fail(ctx, QP_ERR_DEGREE_MISMATCH, "opening term: bad oracle / polynomial index / degree");
+            else {
+                ptrs[t] = pb->coeffs + ob.terms[t].poly_index * n;
+                w[2 * t] = ob.terms[t].weight[0] % gl::P;
+                w[2 * t + 1] = ob.terms[t].weight[1] % gl::P;
+            }
+        }
+        if (rc) break;
+        uint64_t *d_ptrs = nullptr, *d_w = nullptr, *pw = nullptr, *ipw = nullptr;
+        rc = dev_alloc(ctx, &d_ptrs, ob.n_terms ? ob.n_terms : 1);
+        if (!rc) rc = dev_alloc(ctx, &d_w, ob.n_terms ? 2 * ob.n_terms : 1);
+        if (!rc && ob.n_terms) {
+            cudaMemcpyAsync(d_ptrs, ptrs.data(), ob.n_terms * 8, cudaMemcpyHostToDevice, ctx->stream);
+            cudaMemcpyAsync(d_w, w.data(), 2 * ob.n_terms * 8, cudaMemcpyHostToDevice, ctx->stream);
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors die at the end of the iteration
+        }
+        const hx::E z{ob.point[0] % gl::P, ob.point[1] % gl::P};
+        const bool z_zero = z.a == 0 && z.b == 0;
+        if (!rc && !z_zero) rc = build_power_table(ctx, z, degree_log, &pw);
+        if (!rc && !z_zero) rc = build_power_table(ctx, hx::inv(z), degree_log, &ipw);
+        if (!rc) {
+            LAUNCH(ctx, openings::weighted_sum_kernel, cdiv(n, 256), 256, 0, (const uint64_t* const*)d_ptrs, d_w,
+                   (unsigned)ob.n_terms, n, pw, d);
+            const uint64_t s0 = ob.shift[0] % gl::P, s1 = ob.shift[1] % gl::P;
+            if (z_zero) {
+                LAUNCH(ctx, openings::shift_accumulate_kernel, cdiv(n, 256), 256, 0, d, n, s0, s1, bi == 0, fin);
+            } else {
+                LAUNCH(ctx, openings::suffix_scan_segments_kernel, (unsigned)n_seg, 256, 0, d, n, totals);
+                LAUNCH(ctx, openings::suffix_scan_totals_kernel, 1, 32, 0, totals, n_seg);
+                LAUNCH(ctx, openings::quotient_accumulate_kernel, cdiv(n, 256), 256, 0, d, totals, n, ipw, s0, s1,
+                       bi == 0, fin);
+            }
+        }
+        dev_free(ctx, d_ptrs);
+        dev_free(ctx, d_w);
+        dev_free(ctx, pw);
+        dev_free(ctx, ipw);
+    }
+    dev_free(ctx, d);
+    dev_free(ctx, totals);
+    if (rc) {
+        dev_free(ctx, fin);
+        return rc;
+    }
+    rc = fri_from_device_planes(ctx, fin, degree_log, rate_bits, cap_height, out);
+    if (rc) {
+        qp_fri_free(*out);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+extern "C" int qp_fri_initial_coeffs(const qp_fri* f, uint64_t* out) {
+    if (!f) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = f->ctx;
+    if (!f->initial) return fail(ctx, QP_ERR_BAD_ARG, "FRI state was not built from openings");
+    const size_t n = (size_t)1 << f->initial_lg;
+    uint64_t* dtmp = nullptr;
+    int rc = dev_alloc(ctx, &dtmp, 2 * n);
+    if (rc) return rc;
+    LAUNCH(ctx, fri::planes_to_ext_kernel, cdiv(n, 256), 256, 0, f->initial, n, (size_t)0, n, dtmp);
+    rc = copy_out(ctx, out, QP_HOST, dtmp, 2 * n);
+    dev_free(ctx, dtmp);
     return rc;
 }
 
@@ -1219,6 +1405,7 @@ extern "C" void qp_fri_free(qp_fri* f) {
     cudaSetDevice(f->ctx->device);
     dev_free(f->ctx, f->coeffs);
     dev_free(f->ctx, f->values);
+    dev_free(f->ctx, f->initial);
     for (auto& r : f->rounds) {
         dev_free(f->ctx, r.values);
         dev_free(f->ctx, r.tree.digests);

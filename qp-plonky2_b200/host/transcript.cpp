@@ -69,16 +69,12 @@ extern "C" unsigned qp_fri_reduction_arity_bits(unsigned degree_bits, unsigned r
     return k;
 }
 
-extern "C" int qp_fri_committed_trees(qp_ctx* ctx, const uint64_t* coeffs_ext, const uint64_t* values_ext,
-                                      int space, unsigned lg_n, unsigned rate_bits, unsigned cap_height,
-                                      const unsigned* arity_bits, unsigned n_rounds, qp_challenger* ch,
-                                      uint64_t* caps_out, uint64_t* final_poly_out, size_t* final_len_out,
-                                      qp_fri** fri_out) {
-    if (!ch || !fri_out || (n_rounds && (!arity_bits || !caps_out))) return QP_ERR_BAD_ARG;
-    qp_fri* f = nullptr;
-    int rc = qp_fri_begin(ctx, coeffs_ext, values_ext, space, lg_n, rate_bits, cap_height, &f);
-    if (rc) return rc;
+extern "C" int qp_fri_run_commit_phase(qp_fri* f, unsigned cap_height, const unsigned* arity_bits,
+                                       unsigned n_rounds, qp_challenger* ch, uint64_t* caps_out,
+                                       uint64_t* final_poly_out, size_t* final_len_out) {
+    if (!f || !ch || (n_rounds && (!arity_bits || !caps_out))) return QP_ERR_BAD_ARG;
     const size_t cap_words = ((size_t)1 << cap_height) * 4;
+    int rc = QP_OK;
     for (unsigned step = 0; step < n_rounds && !rc; step++) {
         uint64_t* cap = caps_out + step * cap_words;
         rc = qp_fri_commit_round(f, arity_bits[step], cap);
@@ -88,6 +84,19 @@ extern "C" int qp_fri_committed_trees(qp_ctx* ctx, const uint64_t* coeffs_ext, c
         rc = qp_fri_fold_round(f, beta, step + 1 == n_rounds);
     }
     if (!rc) rc = qp_fri_final_poly(f, final_poly_out, final_len_out);
+    return rc;
+}
+
+extern "C" int qp_fri_committed_trees(qp_ctx* ctx, const uint64_t* coeffs_ext, const uint64_t* values_ext,
+                                      int space, unsigned lg_n, unsigned rate_bits, unsigned cap_height,
+                                      const unsigned* arity_bits, unsigned n_rounds, qp_challenger* ch,
+                                      uint64_t* caps_out, uint64_t* final_poly_out, size_t* final_len_out,
+                                      qp_fri** fri_out) {
+    if (!ch || !fri_out || (n_rounds && (!arity_bits || !caps_out))) return QP_ERR_BAD_ARG;
+    qp_fri* f = nullptr;
+    int rc = qp_fri_begin(ctx, coeffs_ext, values_ext, space, lg_n, rate_bits, cap_height, &f);
+    if (rc) return rc;
+    rc = qp_fri_run_commit_phase(f, cap_height, arity_bits, n_rounds, ch, caps_out, final_poly_out, final_len_out);
     if (rc) {
         qp_fri_free(f);
         f = nullptr;

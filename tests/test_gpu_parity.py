@@ -382,3 +382,64 @@ def test_full_size_commit_properties(qp, ctx):
     back = ctx.coset_fft(coeffs[:2], shift=1)
     assert (back == d[:2].cpu().numpy().view(np.uint64)).all()
     print("full-size timing (ms):", b.timing)
+
+
+# ---- opening side of prove_openings -----------------------------------------
+
+def test_eval_polys_at_ext_point(qp, ctx):
+    """OpeningSet::new: every committed polynomial evaluated at zeta (plonky2/src/plonk/proof.rs:289-327)"""
+    for lg_n, cols in ((0, 2), (5, 7), (12, 20), (16, 3)):
+        vals = oracle.rand_felts((cols, 1 << lg_n), 700 + lg_n)
+        b = qp.PolynomialBatch.from_values(ctx, vals, 1, False, 0)
+        co = b.polynomials
+        for pt in ((5, 0), (1234567891011, 987654321), (0, 0), (P - 1, P - 2)):
+            got = b.eval_polys(pt)
+            for c in range(cols):
+                assert (got[c] == oracle.eval_poly_ext(co[c], pt)).all()
+
+
+@pytest.mark.parametrize("lg_n,rate,zero_point", [(1, 1, False), (5, 2, False), (6, 3, True), (11, 3, False), (13, 3, False)])
+def test_fri_from_openings_parity(qp, ctx, lg_n, rate, zero_point):
+    """reduce_openings_to_unmasked_final_poly + final coset FFT + commit phase, all on the device,
+    against the oracle's reduce_openings -> coset_fft -> fri_committed_trees."""
+    n = 1 << lg_n
+    cap_h = min(2, lg_n + rate)
+    rng = np.random.default_rng(lg_n)
+    o1 = qp.PolynomialBatch.from_values(ctx, oracle.rand_felts((5, n), 1), rate, False, cap_h)
+    o2 = qp.PolynomialBatch.from_values(ctx, oracle.rand_felts((3, n), 2), rate, False, cap_h)
+    oracles = [o1, o2]
+    coeffs = [o1.polynomials, o2.polynomials]
+    dev_batches, ref_batches = [], []
+    for b in range(3):
+        k = int(rng.integers(1, 9))
+        pt = tuple(int(x) for x in oracle.rand_felts(2, 40 + b))
+        if zero_point and b == 1:
+            pt = (0, 0)
+        sh = tuple(int(x) for x in oracle.rand_felts(2, 50 + b))
+        dt, rt = [], []
+        for _ in range(k):
+            oi = int(rng.integers(0, 2))
+            pi = int(rng.integers(0, coeffs[oi].shape[0]))
+            w = tuple(int(x) for x in oracle.rand_felts(2, int(rng.integers(0, 1 << 30))))
+            dt.append((oracles[oi], pi, w))
+            rt.append((coeffs[oi][pi], w))
+        dev_batches.append(dict(point=pt, shift=sh, terms=dt))
+        ref_batches.append(dict(point=pt, shift=sh, terms=rt))
+    f = qp.fri_from_openings(ctx, dev_batches, lg_n, rate, cap_h)
+    want_final = oracle.reduce_openings(ref_batches, lg_n)
+    assert (qp.fri_initial_coeffs(f, lg_n) == want_final).all()
+    # commit phase on top of it
+    N = n << rate
+    co = np.zeros((N, 2), dtype=np.uint64)
+    co[:n] = want_final
+    g = oracle.lib().orc_gl_coset_shift()
+    va = np.stack([oracle.coset_fft(co[:, 0], g), oracle.coset_fft(co[:, 1], g)], axis=1)
+    arities = [a for a in ([2, 1] if lg_n >= 5 else [1]) if a <= lg_n]
+    while sum(arities) > lg_n or (lg_n + rate - sum(arities[:1])) < cap_h:
+        arities.pop()
+    ca, cb = qp.Challenger(), oracle.Challenger()
+    qp.fri_commit_phase(f, ca, rate, arities)
+    o = oracle.fri_committed_trees(co, va, rate, cap_h, arities, cb)
+    assert (f.caps == o["caps"]).all()
+    assert (f.final_poly == o["final_poly"]).all()
+    assert ca.get_challenge() == cb.get_challenge()

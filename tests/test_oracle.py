@@ -272,3 +272,53 @@ def test_fri_pow_smallest_witness():
         ok = resp < (1 << 56)
         assert ok == (cand == w)
     del ref
+
+
+# ---- opening side ---------------------------------------------------------------------------
+
+def _random_opening_batches(n, n_polys, seed, zero_point=False):
+    rng = np.random.default_rng(seed)
+    polys = oracle.rand_felts((n_polys, n), seed)
+    batches = []
+    for b in range(3):
+        k = int(rng.integers(1, n_polys + 1))
+        idx = rng.integers(0, n_polys, k)        # repeated polynomials are allowed
+        w = oracle.rand_felts((k, 2), seed + 10 + b)
+        pt = oracle.rand_felts(2, seed + 20 + b)
+        if zero_point and b == 1:
+            pt = np.zeros(2, dtype=np.uint64)
+        batches.append(dict(point=tuple(int(x) for x in pt), shift=tuple(int(x) for x in oracle.rand_felts(2, seed + 30 + b)),
+                            terms=[(polys[i], (int(a), int(c))) for i, (a, c) in zip(idx, w)], idx=[int(i) for i in idx]))
+    return polys, batches
+
+
+@pytest.mark.parametrize("lg,zero_point", [(0, False), (1, False), (5, False), (6, True)])
+def test_reduce_openings_vs_pyref(lg, zero_point):
+    n = 1 << lg
+    polys, batches = _random_opening_batches(n, 6, 900 + lg, zero_point)
+    got = oracle.reduce_openings(batches, lg)
+    pb = [dict(point=b["point"], shift=b["shift"], terms=[([int(x) for x in p], w) for p, w in b["terms"]]) for b in batches]
+    want = pyref.reduce_openings(pb, n)
+    assert got.tolist() == [list(x) for x in want]
+    # the quotient identity itself: (X - z) * q(X) + comp(z) == comp(X) for a single batch with shift anything
+    one = [batches[0]]
+    q = oracle.reduce_openings(one, lg)
+    z = batches[0]["point"]
+    comp = [(0, 0)] * n
+    for p, w in pb[0]["terms"]:
+        comp = [pyref.ext_add(comp[j], ((w[0] * p[j]) % P, (w[1] * p[j]) % P)) for j in range(n)]
+    cz = (0, 0)
+    for c in reversed(comp):
+        cz = pyref.ext_add(pyref.ext_mul(cz, z), c)
+    qq = [tuple(int(x) for x in r) for r in q]
+    for j in range(n):
+        lhs = pyref.ext_add(qq[j - 1] if j > 0 else (0, 0), tuple((-x) % P for x in pyref.ext_mul(z, qq[j])))
+        if j == 0:
+            lhs = pyref.ext_add(lhs, cz)
+        assert lhs == comp[j]
+
+
+def test_eval_poly_ext_vs_pyref():
+    c = oracle.rand_felts(37, 5)
+    pt = (123456789, 987654321)
+    assert tuple(int(x) for x in oracle.eval_poly_ext(c, pt)) == pyref.eval_poly_ext([int(x) for x in c], pt)
