@@ -99,6 +99,8 @@ int qp_batch_get_lde_values(const qp_batch* b, size_t index, size_t step, uint64
 int qp_batch_get_leaves(const qp_batch* b, const uint64_t* leaf_indices, unsigned n, uint64_t* out);
 /* MerkleTree::prove (merkle_tree.rs:201-207): siblings bottom-up, [lg N - cap_height][4]. */
 int qp_batch_prove(const qp_batch* b, size_t leaf_index, uint64_t* siblings_out);
+/* The same for n leaves in one call: siblings_out[n][lg N - cap_height][4]. */
+int qp_batch_prove_many(const qp_batch* b, const uint64_t* leaf_indices, unsigned n, uint64_t* siblings_out);
 /* TimingTree scopes (oracle.rs:176-214), milliseconds of device time:
  * [0] "IFFT", [1] "FFT + blinding", [2] "transpose LDEs" (always 0: fused away), [3] "build Merkle tree". */
 int qp_batch_timing(const qp_batch* b, double ms[4]);
@@ -146,6 +148,10 @@ int qp_fri_final_poly(qp_fri* f, uint64_t* out, size_t* len_out);
 /* Tree of commit round r: leaf (x_index >> arity_bits) flattened [2*arity], and its path. */
 int qp_fri_tree_get(const qp_fri* f, unsigned round, size_t leaf_index, uint64_t* out);
 int qp_fri_tree_prove(const qp_fri* f, unsigned round, size_t leaf_index, uint64_t* siblings_out);
+/* n openings of one commit-phase tree in one call (fri_prover_query_round, prover.rs:250-258):
+ * leaves_out[n][2*arity], siblings_out[n][layers][4]. */
+int qp_fri_tree_open_many(const qp_fri* f, unsigned round, const uint64_t* leaf_indices, unsigned n,
+                          uint64_t* leaves_out, uint64_t* siblings_out);
 int qp_fri_tree_digests(const qp_fri* f, unsigned round, uint64_t* out, int space);
 size_t qp_fri_tree_digests_len(const qp_fri* f, unsigned round);
 unsigned qp_fri_num_rounds(const qp_fri* f);

@@ -52,6 +52,22 @@ int qp_fri_run_commit_phase(qp_fri* f, unsigned cap_height, const unsigned* arit
  * draws the response on the transcript, as the reference does. */
 int qp_fri_grind(qp_ctx* ctx, qp_challenger* challenger, unsigned proof_of_work_bits, uint64_t* witness_out);
 
+/* fri_proof (plonky2/src/fri/prover.rs:24-71) on an existing FRI state: commit phase, final
+ * polynomial, proof of work, query rounds -- serialised exactly as Write::write_fri_proof does
+ * (plonky2/src/util/serialization/mod.rs:1654-1667): commit-phase caps || per query [per initial
+ * tree: leaf values, u8 path length, siblings; per commit round: 2^arity F_p^2 evals, path] ||
+ * final polynomial || pow witness, all little-endian canonical u64.
+ * initial_oracles are the whole (unsharded) batches whose trees the queries open, in order.
+ * The call consumes the FRI state and advances the transcript, so it cannot be repeated: give it
+ * a buffer of at least qp_fri_proof_len() bytes.  *len_out receives the bytes written. */
+size_t qp_fri_proof_len(const size_t* oracle_leaf_lens, size_t n_oracles, unsigned lde_bits, unsigned rate_bits,
+                        unsigned cap_height, const unsigned* arity_bits, unsigned n_rounds,
+                        unsigned num_query_rounds);
+int qp_fri_proof(qp_ctx* ctx, const qp_batch* const* initial_oracles, size_t n_oracles, qp_fri* f,
+                 qp_challenger* challenger, unsigned rate_bits, unsigned cap_height, const unsigned* arity_bits,
+                 unsigned n_rounds, unsigned proof_of_work_bits, unsigned num_query_rounds, uint8_t* out,
+                 size_t capacity, size_t* len_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -364,3 +364,38 @@ def reduce_openings(batches, degree_log):
     lib().orc_reduce_openings(nb, n_terms, ptrs, _ptr(np.ascontiguousarray(w)) if w.size else None, _ptr(pts), _ptr(sh),
                               degree_log, _ptr(out))
     return out
+
+
+def fri_proof_bytes(oracle_batches, coeffs, values, challenger, rate_bits, cap_height, arity_bits, pow_bits,
+                    num_query_rounds) -> bytes:
+    """fri_proof (plonky2/src/fri/prover.rs:24-71) + write_fri_proof
+    (plonky2/src/util/serialization/mod.rs:1654-1667) from the oracle's pieces.
+    oracle_batches: oracle.PolynomialBatch objects (initial trees); coeffs/values: [n][2]."""
+    n = coeffs.shape[0]
+    r = fri_committed_trees(coeffs, values, rate_bits, cap_height, arity_bits, challenger, keep_trees=True)
+    final = r["final_poly"]
+    challenger.observe(final.reshape(-1))                      # observe_final_poly
+    w = fri_proof_of_work(challenger, pow_bits)
+    xs = [challenger.get_challenge() % n for _ in range(num_query_rounds)]
+    out = bytearray()
+    out += r["caps"].astype("<u8").tobytes()
+    lg = n.bit_length() - 1
+    for x in xs:
+        for b in oracle_batches:
+            out += b.leaves[x].astype("<u8").tobytes()
+            sib = np.zeros((lg - cap_height, 4), dtype=np.uint64)
+            lib().orc_merkle_prove(x, n, cap_height, _ptr(b.digests), _ptr(sib) if sib.size else None)
+            out += bytes([sib.shape[0]]) + sib.astype("<u8").tobytes()
+        idx, m = x, n
+        for k, a in enumerate(arity_bits):
+            idx >>= a
+            m >>= a
+            out += r["leaves"][k][idx].astype("<u8").tobytes()
+            layers = (m.bit_length() - 1) - cap_height
+            sib = np.zeros((layers, 4), dtype=np.uint64)
+            if layers:
+                lib().orc_merkle_prove(idx, m, cap_height, _ptr(r["digests"][k]), _ptr(sib))
+            out += bytes([layers]) + sib.astype("<u8").tobytes()
+    out += final.astype("<u8").tobytes()
+    out += int(w).to_bytes(8, "little")
+    return bytes(out)

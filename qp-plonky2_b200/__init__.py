@@ -154,6 +154,11 @@ def lib():
         "qp_fri_free": (None, [vp]),
         "qp_fri_proof_of_work": (i32, [vp, vp, u32, u32, u64p]),
         "qp_batch_eval_polys": (i32, [vp, vp, vp]),
+        "qp_batch_prove_many": (i32, [vp, vp, u32, vp]),
+        "qp_fri_tree_open_many": (i32, [vp, u32, vp, u32, vp, vp]),
+        "qp_fri_proof": (i32, [vp, pp, sz, vp, C.POINTER(_ChallengerState), u32, u32, C.POINTER(u32), u32, u32, u32,
+                               vp, sz, C.POINTER(sz)]),
+        "qp_fri_proof_len": (sz, [C.POINTER(sz), sz, u32, u32, u32, C.POINTER(u32), u32, u32]),
         "qp_fri_begin_from_openings": (i32, [vp, vp, sz, u32, u32, u32, pp]),
         "qp_fri_initial_coeffs": (i32, [vp, vp]),
         "qp_fri_run_commit_phase": (i32, [vp, u32, C.POINTER(u32), u32, C.POINTER(_ChallengerState), vp, vp,
@@ -612,6 +617,23 @@ def fri_commit_phase(fri, challenger, rate_bits, arity_bits):
                                                 _np_ptr(final) if final.size else None, C.byref(flen)))
     fri.caps, fri.final_poly, fri.arity_bits = caps, final, list(arity_bits)
     return fri
+
+
+def fri_proof(ctx, oracles, fri, challenger, rate_bits, arity_bits, proof_of_work_bits, num_query_rounds) -> bytes:
+    """fri_proof (plonky2/src/fri/prover.rs:24-71) on a device FRI state, serialised like
+    write_fri_proof (plonky2/src/util/serialization/mod.rs:1654-1667).  `oracles`: the initial
+    PolynomialBatch trees the queries open, in order."""
+    R = len(arity_bits)
+    ab = (C.c_uint * max(R, 1))(*arity_bits)
+    lens = (C.c_size_t * max(len(oracles), 1))(*[o.leaf_len for o in oracles])
+    need = lib().qp_fri_proof_len(lens, len(oracles), fri.lg_n, rate_bits, fri.cap_height, ab, R, num_query_rounds)
+    buf = (C.c_uint8 * need)()
+    hs = (C.c_void_p * max(len(oracles), 1))(*[o._h for o in oracles])
+    got = C.c_size_t()
+    ctx.check(lib().qp_fri_proof(ctx._h, hs, len(oracles), fri._h, C.byref(challenger._s), rate_bits, fri.cap_height,
+                                 ab, R, proof_of_work_bits, num_query_rounds, buf, need, C.byref(got)))
+    assert got.value == need, (got.value, need)
+    return bytes(buf)
 
 
 def fri_initial_coeffs(fri, degree_log):

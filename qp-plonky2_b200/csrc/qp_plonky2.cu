@@ -493,6 +493,27 @@ static int build_tree(qp_ctx* ctx, Layout lay, unsigned leaf_len, TreeBuf* t, cu
     return QP_OK;
 }
 
+// Siblings for many leaves at once: out[q][layer][4]
+static int tree_prove_many(qp_ctx* ctx, const TreeBuf& t, const uint64_t* leaf_indices, unsigned n_q,
+                           uint64_t* siblings_out) {
+    const unsigned nl = t.shape.num_layers();
+    if (n_q == 0 || nl == 0) return QP_OK;
+    if (!leaf_indices || !siblings_out) return fail(ctx, QP_ERR_BAD_ARG, "null buffer");
+    for (unsigned i = 0; i < n_q; i++)
+        if (leaf_indices[i] >> t.shape.lg_leaves) return fail(ctx, QP_ERR_BAD_ARG, "leaf index out of range");
+    uint64_t* d_idx = nullptr;
+    uint64_t* d_out = nullptr;
+    int rc = dev_alloc(ctx, &d_idx, n_q);
+    if (!rc) rc = dev_alloc(ctx, &d_out, (size_t)n_q * nl * 4);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_idx, leaf_indices, (size_t)n_q * 8, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, merkle::merkle_paths_kernel, cdiv((size_t)n_q * nl, 128), 128, 0, t.shape, t.digests, d_idx, n_q, d_out);
+    rc = copy_out(ctx, siblings_out, QP_HOST, d_out, (size_t)n_q * nl * 4);
+    dev_free(ctx, d_idx);
+    dev_free(ctx, d_out);
+    return rc;
+}
+
 static int tree_prove(qp_ctx* ctx, const TreeBuf& t, size_t leaf_index, uint64_t* siblings_out) {
     if (!siblings_out && t.shape.num_layers()) return fail(ctx, QP_ERR_BAD_ARG, "null output buffer");
     if (leaf_index >> t.shape.lg_leaves) return fail(ctx, QP_ERR_BAD_ARG, "leaf index out of range");
@@ -895,6 +916,11 @@ extern "C" int qp_batch_get_leaves(const qp_batch* b, const uint64_t* leaf_indic
 extern "C" int qp_batch_prove(const qp_batch* b, size_t leaf_index, uint64_t* siblings_out) {
     if (!b) return QP_ERR_BAD_ARG;
     return tree_prove(b->ctx, b->tree, leaf_index, siblings_out);
+}
+
+extern "C" int qp_batch_prove_many(const qp_batch* b, const uint64_t* leaf_indices, unsigned n, uint64_t* siblings_out) {
+    if (!b) return QP_ERR_BAD_ARG;
+    return tree_prove_many(b->ctx, b->tree, leaf_indices, n, siblings_out);
 }
 
 extern "C" int qp_batch_timing(const qp_batch* b, double ms[4]) {
@@ -1390,6 +1416,32 @@ extern "C" int qp_fri_tree_prove(const qp_fri* f, unsigned round, size_t leaf_in
     if (round >= f->rounds.size()) return fail(f->ctx, QP_ERR_BAD_ARG, "round out of range");
     return tree_prove(f->ctx, f->rounds[round].tree, leaf_index, siblings_out);
 }
+extern "C" int qp_fri_tree_open_many(const qp_fri* f, unsigned round, const uint64_t* leaf_indices, unsigned n,
+                                     uint64_t* leaves_out, uint64_t* siblings_out) {
+    if (!f) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = f->ctx;
+    if (round >= f->rounds.size()) return fail(ctx, QP_ERR_BAD_ARG, "round out of range");
+    if (n == 0) return QP_OK;
+    if (!leaf_indices || !leaves_out) return fail(ctx, QP_ERR_BAD_ARG, "null buffer");
+    const FriRound& r = f->rounds[round];
+    for (unsigned i = 0; i < n; i++)
+        if (leaf_indices[i] >> r.tree.shape.lg_leaves) return fail(ctx, QP_ERR_BAD_ARG, "leaf index out of range");
+    const unsigned row_len = 2u << r.arity_bits;
+    uint64_t *d_idx = nullptr, *d_rows = nullptr;
+    int rc = dev_alloc(ctx, &d_idx, n);
+    if (!rc) rc = dev_alloc(ctx, &d_rows, (size_t)n * row_len);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_idx, leaf_indices, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    merkle::ExtPlanesLayout lay{r.values, (size_t)1 << r.lg_n, r.arity_bits};
+    LAUNCH(ctx, merkle::gather_rows_kernel<merkle::ExtPlanesLayout>, cdiv((size_t)n * row_len, 128), 128, 0, lay,
+           row_len, (const uint64_t*)d_idx, (size_t)0, (size_t)n, d_rows);
+    rc = copy_out(ctx, leaves_out, QP_HOST, d_rows, (size_t)n * row_len);
+    dev_free(ctx, d_idx);
+    dev_free(ctx, d_rows);
+    if (!rc) rc = tree_prove_many(ctx, r.tree, leaf_indices, n, siblings_out);
+    return rc;
+}
+
 extern "C" int qp_fri_tree_digests(const qp_fri* f, unsigned round, uint64_t* out, int space) {
     if (!f) return QP_ERR_BAD_ARG;
     if (round >= f->rounds.size()) return fail(f->ctx, QP_ERR_BAD_ARG, "round out of range");

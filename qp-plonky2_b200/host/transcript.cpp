@@ -3,6 +3,7 @@
 #include "../../include/qp_plonky2_host.h"
 
 #include <cstring>
+#include <vector>
 
 #include "../csrc/poseidon_constants.h"
 
@@ -117,4 +118,120 @@ extern "C" int qp_fri_grind(qp_ctx* ctx, qp_challenger* ch, unsigned pow_bits, u
     qp_challenger_observe(ch, witness_out, 1);
     (void)qp_challenger_get(ch);
     return QP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fri_proof: commit phase + final poly + PoW + query rounds, serialised like write_fri_proof
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct ByteSink {
+    uint8_t* out;
+    size_t cap, len = 0;
+    void u8(uint8_t x) {
+        if (out && len < cap) out[len] = x;
+        len++;
+    }
+    void u64s(const uint64_t* p, size_t n) {  // write_field_vec: canonical LE u64 (serialization/mod.rs:1313-1330)
+        if (out && len + 8 * n <= cap) std::memcpy(out + len, p, 8 * n);
+        len += 8 * n;
+    }
+    void path(const uint64_t* sib, unsigned layers) {  // write_merkle_proof (mod.rs:1529-1543)
+        u8((uint8_t)layers);
+        u64s(sib, 4 * (size_t)layers);
+    }
+};
+}  // namespace
+
+extern "C" int qp_fri_proof(qp_ctx* ctx, const qp_batch* const* oracles, size_t n_oracles, qp_fri* f,
+                            qp_challenger* ch, unsigned rate_bits, unsigned cap_height, const unsigned* arity_bits,
+                            unsigned n_rounds, unsigned pow_bits, unsigned num_queries, uint8_t* out,
+                            size_t capacity, size_t* len_out) {
+    if (!ctx || !f || !ch || !len_out || (n_oracles && !oracles) || (n_rounds && !arity_bits)) return QP_ERR_BAD_ARG;
+    const size_t cap_words = ((size_t)1 << cap_height) * 4;
+    // commit phase (prover.rs:38-49)
+    std::vector<uint64_t> caps(cap_words * (n_rounds ? n_rounds : 1));
+    size_t final_len = 0;
+    int rc = qp_fri_run_commit_phase(f, cap_height, arity_bits, n_rounds, ch, caps.data(), nullptr, &final_len);
+    if (rc) return rc;
+    std::vector<uint64_t> final_poly(2 * (final_len ? final_len : 1));
+    rc = qp_fri_final_poly(f, final_poly.data(), &final_len);
+    if (rc) return rc;
+    // observe_final_poly (prover.rs:145-157), then grinding (prover.rs:159-208)
+    qp_challenger_observe(ch, final_poly.data(), 2 * final_len);
+    uint64_t pow_witness = 0;
+    rc = qp_fri_grind(ctx, ch, pow_bits, &pow_witness);
+    if (rc) return rc;
+    // query indices (prover.rs:221-226): challenge mod lde size
+    unsigned lde_bits = 0;
+    {
+        // lde size = final_len << rate_bits << sum(arity)
+        size_t n = (final_len << rate_bits);
+        for (unsigned i = 0; i < n_rounds; i++) n <<= arity_bits[i];
+        while (((size_t)1 << lde_bits) < n) lde_bits++;
+    }
+    const size_t lde = (size_t)1 << lde_bits;
+    std::vector<uint64_t> x(num_queries);
+    for (unsigned q = 0; q < num_queries; q++) x[q] = qp_challenger_get(ch) % lde;
+
+    // gather everything per tree with one call each
+    std::vector<std::vector<uint64_t>> o_rows(n_oracles), o_paths(n_oracles);
+    std::vector<size_t> o_len(n_oracles);
+    const unsigned o_layers = lde_bits - cap_height;
+    for (size_t t = 0; t < n_oracles && !rc; t++) {
+        if (qp_batch_cap_len(oracles[t]) != ((size_t)1 << cap_height)) return QP_ERR_BAD_ARG;  // sharded batch
+        o_len[t] = qp_batch_leaf_len(oracles[t]);
+        o_rows[t].resize((size_t)num_queries * o_len[t] + 1);
+        o_paths[t].resize((size_t)num_queries * o_layers * 4 + 1);
+        rc = qp_batch_get_leaves(oracles[t], x.data(), num_queries, o_rows[t].data());
+        if (!rc) rc = qp_batch_prove_many(oracles[t], x.data(), num_queries, o_paths[t].data());
+    }
+    std::vector<std::vector<uint64_t>> r_rows(n_rounds), r_paths(n_rounds);
+    std::vector<unsigned> r_layers(n_rounds);
+    {
+        std::vector<uint64_t> idx(x);
+        unsigned bits = lde_bits;
+        for (unsigned i = 0; i < n_rounds && !rc; i++) {
+            for (auto& v : idx) v >>= arity_bits[i];
+            bits -= arity_bits[i];
+            r_layers[i] = bits - cap_height;
+            r_rows[i].resize((size_t)num_queries * (2u << arity_bits[i]) + 1);
+            r_paths[i].resize((size_t)num_queries * r_layers[i] * 4 + 1);
+            rc = qp_fri_tree_open_many(f, i, idx.data(), num_queries, r_rows[i].data(), r_paths[i].data());
+        }
+    }
+    if (rc) return rc;
+
+    ByteSink w{out, capacity};
+    for (unsigned i = 0; i < n_rounds; i++) w.u64s(caps.data() + i * cap_words, cap_words);  // write_merkle_cap
+    for (unsigned q = 0; q < num_queries; q++) {
+        for (size_t t = 0; t < n_oracles; t++) {  // write_fri_initial_proof
+            w.u64s(o_rows[t].data() + (size_t)q * o_len[t], o_len[t]);
+            w.path(o_paths[t].data() + (size_t)q * o_layers * 4, o_layers);
+        }
+        for (unsigned i = 0; i < n_rounds; i++) {  // write_fri_query_step
+            const size_t row = 2u << arity_bits[i];
+            w.u64s(r_rows[i].data() + (size_t)q * row, row);
+            w.path(r_paths[i].data() + (size_t)q * r_layers[i] * 4, r_layers[i]);
+        }
+    }
+    w.u64s(final_poly.data(), 2 * final_len);
+    w.u64s(&pow_witness, 1);
+    *len_out = w.len;
+    return (out && w.len > capacity) ? QP_ERR_BAD_ARG : QP_OK;
+}
+
+extern "C" size_t qp_fri_proof_len(const size_t* oracle_leaf_lens, size_t n_oracles, unsigned lde_bits,
+                                   unsigned rate_bits, unsigned cap_height, const unsigned* arity_bits,
+                                   unsigned n_rounds, unsigned num_queries) {
+    size_t total = (size_t)n_rounds * ((size_t)1 << cap_height) * 32;
+    size_t per_query = 0;
+    for (size_t t = 0; t < n_oracles; t++) per_query += oracle_leaf_lens[t] * 8 + 1 + (size_t)(lde_bits - cap_height) * 32;
+    unsigned bits = lde_bits;
+    for (unsigned i = 0; i < n_rounds; i++) {
+        bits -= arity_bits[i];
+        per_query += ((size_t)2 << arity_bits[i]) * 8 + 1 + (size_t)(bits - cap_height) * 32;
+    }
+    total += per_query * num_queries;
+    total += (((size_t)1 << bits) >> rate_bits) * 16 + 8;  // final polynomial + pow witness
+    return total;
 }

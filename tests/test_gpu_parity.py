@@ -443,3 +443,46 @@ def test_fri_from_openings_parity(qp, ctx, lg_n, rate, zero_point):
     assert (f.caps == o["caps"]).all()
     assert (f.final_poly == o["final_poly"]).all()
     assert ca.get_challenge() == cb.get_challenge()
+
+
+@pytest.mark.parametrize("lg_n,rate,cap_h,pow_bits,queries", [(5, 2, 1, 4, 3), (9, 3, 4, 8, 5), (12, 3, 4, 16, 28)])
+def test_fri_proof_bytes_parity(qp, ctx, lg_n, rate, cap_h, pow_bits, queries):
+    """Whole FRI proof (commit phase, final poly, PoW, query openings of the initial trees and of
+    every commit-phase tree) serialised like write_fri_proof -- byte for byte against the oracle.
+    This is prove_openings from the alpha-reduction on (plonky2/src/fri/oracle.rs:320-358)."""
+    n = 1 << lg_n
+    v1, v2 = oracle.rand_felts((6, n), 11), oracle.rand_felts((3, n), 12)
+    salt = oracle.rand_felts((4, n << rate), 13)
+    d1 = qp.PolynomialBatch.from_values(ctx, v1, rate, False, cap_h)
+    d2 = qp.PolynomialBatch.from_values(ctx, v2, rate, True, cap_h, salt=salt)
+    o1 = oracle.PolynomialBatch.from_values(v1, rate, cap_h)
+    o2 = oracle.PolynomialBatch.from_values(v2, rate, cap_h, salt=salt)
+    rng = np.random.default_rng(7)
+    dev_b, ref_b = [], []
+    for b in range(2):
+        pt = tuple(int(x) for x in oracle.rand_felts(2, 60 + b))
+        sh = tuple(int(x) for x in oracle.rand_felts(2, 70 + b))
+        dt, rt = [], []
+        for (dd, oo, cols) in ((d1, o1, 6), (d2, o2, 3)):
+            for pi in range(cols):
+                w = tuple(int(x) for x in oracle.rand_felts(2, int(rng.integers(0, 1 << 30))))
+                dt.append((dd, pi, w))
+                rt.append((oo.polynomials[pi], w))
+        dev_b.append(dict(point=pt, shift=sh, terms=dt))
+        ref_b.append(dict(point=pt, shift=sh, terms=rt))
+    arities = oracle.fri_reduction_arity_bits(lg_n, rate, cap_h, arity_bits=min(4, max(1, lg_n // 3)), final_poly_bits=2)
+    ca, cb = qp.Challenger(), oracle.Challenger()
+    ca.observe_elements([9, 8, 7])
+    cb.observe(u64([9, 8, 7]))
+    f = qp.fri_from_openings(ctx, dev_b, lg_n, rate, cap_h)
+    got = qp.fri_proof(ctx, [d1, d2], f, ca, rate, arities, pow_bits, queries)
+    fin = oracle.reduce_openings(ref_b, lg_n)
+    N = n << rate
+    co = np.zeros((N, 2), dtype=np.uint64)
+    co[:n] = fin
+    g = oracle.lib().orc_gl_coset_shift()
+    va = np.stack([oracle.coset_fft(co[:, 0], g), oracle.coset_fft(co[:, 1], g)], axis=1)
+    want = oracle.fri_proof_bytes([o1, o2], co, va, cb, rate, cap_h, arities, pow_bits, queries)
+    assert len(got) == len(want)
+    assert got == want
+    assert ca.get_challenge() == cb.get_challenge()
