@@ -3,11 +3,11 @@
 // Values are raw u64 and may be NON-canonical (any representative in [0, 2^64)), exactly as
 // the reference carries them (field/src/goldilocks_field.rs:33-37); canonicalise only where
 // bytes leave the device path (digests, LDE rows, caps).  All routines are total over u64
-// inputs.  The multiply is 4x IMAD.WIDE.U32 (fma pipe) and the reduction is
+// inputs.  The multiply is 4x IMAD.WIDE.U32 (fma-heavy pipe) and the reduction is
 //      x = x0 + x1 b + x2 b^2 + x3 b^3,  b = 2^32,  b^2 = b - 1,  b^3 = -1  (mod p)
-//        = (x1:x0) - x3 + x2*(2^32-1)
-// (reference reduce128, goldilocks_field.rs:390-403), done with carry-chained 32-bit PTX so
-// no 64-bit compare/select sequences are generated.
+//        = (x0 - x2 - x3) + (x1 + x2) b
+// (reference reduce128, goldilocks_field.rs:390-403), one signed multi-word sum and one
+// fold of its overflow word: 16 SASS instructions per modular multiplication.
 #pragma once
 #include <cstdint>
 
@@ -142,39 +142,50 @@ __device__ __forceinline__ uint64_t neg(uint64_t a) {
 }
 
 // ---- reduction / multiplication ----------------------------------------------------------
+// Reductions.  With B = 2^32:  B^2 = B - 1 and B^3 = -1 (mod p), so a value given by 32-bit words
+//      x0 + x1 B + x2 B^2 + x3 B^3  =  (x0 - x2 - x3) + (x1 + x2) B            (reduce128,
+// goldilocks_field.rs:390-403 computes the same thing as lo - hi_hi + hi_lo * EPS).  The right-hand
+// side is evaluated as ONE signed multi-word sum u + v B whose overflow word w is in {-1, 0, 1};
+// w B^2 = w EPS is folded back once, and the bounds below show that this last addition cannot
+// wrap.  Written with 64-bit C arithmetic on purpose: ptxas turns it into 3-input IADD3 with dual
+// carry predicates (9 SASS instructions for reduce128, against 13 for the borrow/carry-chain form
+// that PTX add.cc/sub.cc can express).
 
-// (hi:lo), hi 32 bits  ->  lo + hi * EPS with the single possible wrap folded back
-// (reduce96, goldilocks_field.rs:381-385).  hi * EPS = (hi << 32) - hi is formed on the ALU pipe
-// (2 instructions) instead of one IMAD.WIDE: on B200 the fma-heavy pipe is the scarce one
-// (IMAD.WIDE = 4 pipe cycles).  hi * EPS <= (2^32-1)^2 < p, so one correction is enough.
-__device__ __forceinline__ uint64_t reduce96(uint64_t lo, uint32_t hi) {
-    uint32_t p0, p1;
-    asm("{\n\t"
-        "sub.cc.u32   %0, 0, %2;\n\t"    // low word:  -hi
-        "subc.u32     %1, %2, 0;\n\t"    // high word: hi - (hi != 0)
-        "}"
-        : "=&r"(p0), "=&r"(p1)
-        : "r"(hi));
-    return add1(lo, pack(p0, p1));
+// r + w * EPS for a small signed w
+__device__ __forceinline__ uint64_t add_w_eps(uint64_t r, int64_t w) {
+    return r + (uint64_t)((w << 32) - w);
 }
 
-// Reduce the 128-bit value (hi:lo) mod p; output is some u64 representative
-// (reduce128, goldilocks_field.rs:390-403):  lo - hi_hi + hi_lo * EPS.
+// (hi:lo), hi 32 bits  ->  lo + hi * EPS  (reduce96, goldilocks_field.rs:381-385).
+// u = x0 - hi, v = x1 + hi + (u >> 32) in [0, 2^33 - 2]; w = 1 implies r <= B^2 - B - 1, so r + EPS < B^2.
+__device__ __forceinline__ uint64_t reduce96(uint64_t lo, uint32_t hi) {
+    uint32_t x0, x1;
+    unpack(lo, x0, x1);
+    const int64_t u = (int64_t)(uint64_t)x0 - (int64_t)(uint64_t)hi;
+    const int64_t v = (int64_t)((uint64_t)x1 + hi) + (u >> 32);
+    return add_w_eps(pack((uint32_t)u, (uint32_t)v), v >> 32);
+}
+
+// Reduce the 128-bit value (hi:lo) mod p; output is some u64 representative.
+// u in [-(2B - 2), B), v = x1 + x2 + (u >> 32) in [-2, 2B - 2].  w = 1: the value is at most
+// 2B^2 - 2B, so r <= B^2 - 2B and r + EPS < B^2.  w = -1: the value is at least -(B - 1), so
+// r >= B^2 - B + 1 > EPS.
 __device__ __forceinline__ uint64_t reduce128(uint64_t lo, uint64_t hi) {
-    uint32_t x0, x1, x2, x3, t0, t1;
+    uint32_t x0, x1, x2, x3;
     unpack(lo, x0, x1);
     unpack(hi, x2, x3);
-    asm("{\n\t"
-        ".reg .u32 m;\n\t"
-        "sub.cc.u32   %0, %2, %4;\n\t"
-        "subc.cc.u32  %1, %3, 0;\n\t"
-        "subc.u32     m, 0, 0;\n\t"
-        "sub.cc.u32   %0, %0, m;\n\t"   // borrow only if lo < 2^32, so this cannot borrow again
-        "subc.u32     %1, %1, 0;\n\t"
-        "}"
-        : "=&r"(t0), "=&r"(t1)
-        : "r"(x0), "r"(x1), "r"(x3));
-    return reduce96(pack(t0, t1), x2);
+    const int64_t u = (int64_t)(uint64_t)x0 - (int64_t)(uint64_t)x2 - (int64_t)(uint64_t)x3;
+    const int64_t v = (int64_t)((uint64_t)x1 + x2) + (u >> 32);
+    return add_w_eps(pack((uint32_t)u, (uint32_t)v), v >> 32);
+}
+
+// w0 + (w1 + v0) B + v1 B^2  ->  field element, for w1 + v1 < 2^32: the sum of two 64-bit
+// accumulators (w1:w0) + (v1:v0) B with small high words, as the Poseidon linear layers produce.
+// = (w0 - v1) + (w1 + v0 + v1) B; v <= 2B - 2, so w <= 1 and r + EPS < B^2 as in reduce96.
+__device__ __forceinline__ uint64_t fold3(uint32_t w0, uint32_t w1, uint32_t v0, uint32_t v1) {
+    const int64_t u = (int64_t)(uint64_t)w0 - (int64_t)(uint64_t)v1;
+    const int64_t v = (int64_t)((uint64_t)w1 + v0 + v1) + (u >> 32);
+    return add_w_eps(pack((uint32_t)u, (uint32_t)v), v >> 32);
 }
 
 // 64 x 64 -> 128 bit product as (lo, hi).  Four IMAD.WIDE.U32 and a 32-bit carry chain that

@@ -35,6 +35,7 @@ static constexpr int WIDTH = 12;
 static constexpr int RATE = 8;
 static constexpr int N_ROUNDS = 30;
 static constexpr int N_PARTIAL_GROUPS = 7;  // rounds 4..24 in groups of three; round 25 alone
+static constexpr int N_PARTIAL_PAIRS = 11;  // FP64 formulation: rounds 4..25 in pairs
 
 struct Mat {
     uint32_t a[12][12];
@@ -79,6 +80,15 @@ static constexpr Mat M3 = mat_mul(M2, M1);
 __constant__ uint64_t c_rc[WIDTH * (N_ROUNDS + 1)];
 __constant__ uint64_t c_grp_k[N_PARTIAL_GROUPS][2];
 __constant__ uint64_t c_grp_K[N_PARTIAL_GROUPS][WIDTH];
+// FP64-pipe formulation (see f64 below): the same constants as (2^52 + low half, 2^52 + high half)
+// doubles, and the constants of the 11 fused PAIRS of partial rounds:
+//   c_pair_k[g]        rc'_0                      (rc', rc'' = constants of the two rounds
+//   c_pair_K[g][0..11] M rc' + rc''                FOLLOWING the pair's first round)
+__constant__ double c_rc_d[WIDTH * (N_ROUNDS + 1)][2];
+__constant__ uint64_t c_pair_k[N_PARTIAL_PAIRS];
+__constant__ uint64_t c_pair_K[N_PARTIAL_PAIRS][WIDTH];
+__constant__ double c_pair_k_d[N_PARTIAL_PAIRS][2];
+__constant__ double c_pair_K_d[N_PARTIAL_PAIRS][WIDTH][2];
 
 // Host side: derive the group constants (mod p, exact) and upload everything.
 static inline cudaError_t upload_constants(cudaStream_t stream) {
@@ -109,25 +119,53 @@ static inline cudaError_t upload_constants(cudaStream_t stream) {
         gk[g][1] = (uint64_t)(((u128)m1r1[0] + r2[0]) % P);
         for (int i = 0; i < 12; i++) gK[g][i] = (uint64_t)(((u128)m2r1[i] + m1r2[i] + r3[i]) % P);
     }
+    // FP64 tables
+    static double rcd[WIDTH * (N_ROUNDS + 1)][2];
+    static uint64_t pk[N_PARTIAL_PAIRS], pK[N_PARTIAL_PAIRS][WIDTH];
+    static double pkd[N_PARTIAL_PAIRS][2], pKd[N_PARTIAL_PAIRS][WIDTH][2];
+    // (2^52 + low half, 2^52 + high half) of c' = c - (1 + K) 2^64 mod p with 2^32 - K added to the
+    // high part, K = 0x43300000: the exponent words of the two finished accumulators then cancel
+    // inside fold_row_f64 (derivation there)
+    auto split = [&](uint64_t v, double* out) {
+        const uint64_t K = 0x43300000ULL;
+        const uint64_t two64 = (uint64_t)((((u128)1) << 64) % P);
+        const uint64_t excess = (uint64_t)((u128)(1 + K) * two64 % P);
+        const uint64_t c = (uint64_t)(((u128)(v % P) + P - excess) % P);
+        out[0] = 4503599627370496.0 + (double)(uint32_t)c;
+        out[1] = 4503599627370496.0 + (double)(uint32_t)(c >> 32) + (double)((1ULL << 32) - K);
+    };
+    for (int i = 0; i < WIDTH * (N_ROUNDS + 1); i++) split(rc[i], rcd[i]);
+    for (int g = 0; g < N_PARTIAL_PAIRS; g++) {
+        const int r = 4 + 2 * g;
+        const uint64_t* r1 = rc + 12 * (r + 1);
+        const uint64_t* r2 = rc + 12 * (r + 2);
+        uint64_t m1r1[12];
+        matvec(M1, r1, m1r1);
+        pk[g] = r1[0];
+        split(pk[g], pkd[g]);
+        for (int i = 0; i < 12; i++) {
+            pK[g][i] = (uint64_t)(((u128)m1r1[i] + r2[i]) % P);
+            split(pK[g][i], pKd[g][i]);
+        }
+    }
     cudaError_t e = cudaMemcpyToSymbolAsync(c_rc, rc, sizeof rc, 0, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_rc_d, rcd, sizeof rcd, 0, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_pair_k, pk, sizeof pk, 0, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_pair_K, pK, sizeof pK, 0, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_pair_k_d, pkd, sizeof pkd, 0, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_pair_K_d, pKd, sizeof pKd, 0, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_grp_k, gk, sizeof gk, 0, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_grp_K, gK, sizeof gK, 0, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // the sources are static host arrays
     return e;
 }
 
-// 96-bit (s2 : lo64) row value -> field element.  al + ah * 2^32 with al, ah < 2^58.
+// al + ah * 2^32 -> field element, for al, ah < 2^62 (gl::fold3)
 __device__ __forceinline__ uint64_t fold_row(uint64_t al, uint64_t ah) {
-    uint32_t al0, al1, ah0, ah1, s1, s2;
+    uint32_t al0, al1, ah0, ah1;
     gl::unpack(al, al0, al1);
     gl::unpack(ah, ah0, ah1);
-    asm("{\n\t"
-        "add.cc.u32  %0, %2, %3;\n\t"
-        "addc.u32    %1, %4, 0;\n\t"
-        "}"
-        : "=&r"(s1), "=&r"(s2)
-        : "r"(al1), "r"(ah0), "r"(ah1));
-    return gl::reduce96(gl::pack(al0, s1), s2);
+    return gl::fold3(al0, al1, ah0, ah1);
 }
 
 // acc += row R of matrix MAT times the state halves (2 x 12 IMAD.WIDE with immediate operands)
@@ -191,6 +229,144 @@ __device__ __forceinline__ void partial_group(uint64_t (&s)[12], int g) {
         al += (uint64_t)d1l * m3.a[r][0] + (uint64_t)d2l * m2.a[r][0] + (uint64_t)d3l * m1.a[r][0];
         ah += (uint64_t)d1h * m3.a[r][0] + (uint64_t)d2h * m2.a[r][0] + (uint64_t)d3h * m1.a[r][0];
         s[r] = fold_row(al, ah);
+    }
+}
+
+// ---- FP64-pipe formulation of the linear layers ---------------------------------------------
+// Measured on B200 (tools/microbench/int_pipes.cu, profiles/r01_int_pipe_microbench.txt):
+// IMAD.WIDE.U32 costs 4.3 issue cycles per warp instruction and overlaps with almost nothing,
+// while DFMA costs 2.3 on its own pipe and overlaps with the integer pipes.  A product
+// (32-bit half) x (matrix entry < 2^17) summed over a row stays below 2^50, so it is EXACT in a
+// double: the linear layers run on the FP64 pipe, bit-exactly, at half the cost.
+//   in : u32 half h -> double: bits (0x43300000 : h) are 2^52 + h; one DADD removes the 2^52.
+//   out: accumulators start at 2^52 + (constant half), so the finished sum is 2^52 + v with
+//        v < 2^52 sitting in the mantissa: no conversion instruction, just the two words.
+//        (fold_row_f64 also cancels the exponent words, so the read-back is free.)
+// The 22 partial rounds are fused in PAIRS (entries of M^2 < 2^17 keep two 32-bit limbs exact):
+//     x'' = M^2 x + d1 M^2 e0 + d2 M e0 + K,   d = x0^7 - x0,
+// 362 DFMA per two rounds.  QP_POSEIDON_F64_FULL / _PART = how many of the 12 output rows of a
+// full-round / pair layer go to the FP64 pipe; the remaining rows use IMAD.WIDE (pipe balance).
+#ifndef QP_POSEIDON_F64
+#define QP_POSEIDON_F64 1
+#endif
+#ifndef QP_POSEIDON_F64_FULL
+#define QP_POSEIDON_F64_FULL 12
+#endif
+#ifndef QP_POSEIDON_F64_PART
+#define QP_POSEIDON_F64_PART 12
+#endif
+#ifndef QP_POSEIDON_I2F   // 1: cvt.rn.f64.u32 (I2F, XU pipe, otherwise idle) instead of the 2^52 trick for the inputs
+#define QP_POSEIDON_I2F 1
+#endif
+
+namespace f64 {
+__device__ __forceinline__ double from_u32(uint32_t h) {
+#if QP_POSEIDON_I2F
+    return (double)h;
+#else
+    return __hiloint2double(0x43300000, (int)h) - 4503599627370496.0;
+#endif
+}
+}  // namespace f64
+
+// Finished FP64 accumulators -> field element.  al = 2^52 + a, ah = 2^52 + h + 2^32 - K with
+// K = 0x43300000 (the exponent word of 2^52) and a, h < 2^51.  Read as raw words, al is the
+// integer a + K 2^32 and ah is h + 2^32 - K + K 2^32, so
+//     raw(al) + raw(ah) 2^32 = a + h 2^32 + (1 + K) 2^64 :
+// the exponent words cancel except for a constant multiple of 2^64, which the host subtracted
+// from the round constant (upload_constants).  No masking, no conversion instruction.
+__device__ __forceinline__ uint64_t fold_row_f64(double al, double ah) {
+    // high words are K + small: their sum stays below 2^32 as gl::fold3 requires
+    return gl::fold3((uint32_t)__double2loint(al), (uint32_t)__double2hiint(al),
+                     (uint32_t)__double2loint(ah), (uint32_t)__double2hiint(ah));
+}
+
+#define QP_DOT_ROW_F64(MAT, R, dl, dh, al, ah)                   \
+    _Pragma("unroll") for (int k_ = 0; k_ < 12; k_++) {          \
+        al = fma(dl[k_], (double)MAT.a[R][k_], al);              \
+        ah = fma(dh[k_], (double)MAT.a[R][k_], ah);              \
+    }
+
+// state <- M * state + rc[ri .. ri+12)   (ri = 12 * round)
+__device__ __forceinline__ void mds_layer_f64(uint64_t (&s)[12], int ri) {
+    QP_POSEIDON_MATS
+    uint32_t lo[12], hi[12];
+    double dl[12], dh[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        gl::unpack(s[i], lo[i], hi[i]);
+        dl[i] = f64::from_u32(lo[i]);
+        dh[i] = f64::from_u32(hi[i]);
+    }
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        if (r < QP_POSEIDON_F64_FULL) {
+            double al = c_rc_d[ri + r][0], ah = c_rc_d[ri + r][1];
+            QP_DOT_ROW_F64(m1, r, dl, dh, al, ah)
+            s[r] = fold_row_f64(al, ah);
+        } else {
+            uint32_t c0, c1;
+            gl::unpack(c_rc[ri + r], c0, c1);
+            uint64_t al = c0, ah = c1;
+            QP_DOT_ROW(m1, r, lo, hi, al, ah)
+            s[r] = fold_row(al, ah);
+        }
+    }
+}
+
+// Two fused partial rounds.  `s` enters with its round constants already added.
+__device__ __forceinline__ void partial_pair_f64(uint64_t (&s)[12], int g) {
+    QP_POSEIDON_MATS
+    uint32_t lo[12], hi[12];
+    double dl[12], dh[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        gl::unpack(s[i], lo[i], hi[i]);
+        dl[i] = f64::from_u32(lo[i]);
+        dh[i] = f64::from_u32(hi[i]);
+    }
+    uint32_t d1l, d1h, d2l, d2h;
+    sbox_delta(s[0], d1l, d1h);
+    const double e1l = f64::from_u32(d1l), e1h = f64::from_u32(d1h);
+    // lane 0 after the first round:  (M x)_0 + d1 M00 + rc'_0
+    uint64_t y0;
+    if (QP_POSEIDON_F64_PART > 0) {
+        double al = c_pair_k_d[g][0], ah = c_pair_k_d[g][1];
+        QP_DOT_ROW_F64(m1, 0, dl, dh, al, ah)
+        al = fma(e1l, (double)m1.a[0][0], al);
+        ah = fma(e1h, (double)m1.a[0][0], ah);
+        y0 = fold_row_f64(al, ah);
+    } else {
+        uint32_t c0, c1;
+        gl::unpack(c_pair_k[g], c0, c1);
+        uint64_t al = c0, ah = c1;
+        QP_DOT_ROW(m1, 0, lo, hi, al, ah)
+        al += (uint64_t)d1l * m1.a[0][0];
+        ah += (uint64_t)d1h * m1.a[0][0];
+        y0 = fold_row(al, ah);
+    }
+    sbox_delta(y0, d2l, d2h);
+    const double e2l = f64::from_u32(d2l), e2h = f64::from_u32(d2h);
+    // full state after the second round
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        if (r < QP_POSEIDON_F64_PART) {
+            double al = c_pair_K_d[g][r][0], ah = c_pair_K_d[g][r][1];
+            QP_DOT_ROW_F64(m2, r, dl, dh, al, ah)
+            al = fma(e1l, (double)m2.a[r][0], al);
+            ah = fma(e1h, (double)m2.a[r][0], ah);
+            al = fma(e2l, (double)m1.a[r][0], al);
+            ah = fma(e2h, (double)m1.a[r][0], ah);
+            s[r] = fold_row_f64(al, ah);
+        } else {
+            uint32_t c0, c1;
+            gl::unpack(c_pair_K[g][r], c0, c1);
+            uint64_t al = c0, ah = c1;
+            QP_DOT_ROW(m2, r, lo, hi, al, ah)
+            al += (uint64_t)d1l * m2.a[r][0] + (uint64_t)d2l * m1.a[r][0];
+            ah += (uint64_t)d1h * m2.a[r][0] + (uint64_t)d2h * m1.a[r][0];
+            s[r] = fold_row(al, ah);
+        }
     }
 }
 
@@ -282,6 +458,34 @@ __device__ __forceinline__ void mds_layer_rot(uint64_t (&s)[12], const uint64_t*
 // The permutation.  State lanes may be any u64 representatives; outputs likewise.
 // SYNC: all threads of the block run it together and meet at a barrier per round, which keeps
 // the warps of an SM inside the same window of code (instruction-cache working set).
+#if QP_POSEIDON_F64
+template <bool SYNC = false>
+__device__ __forceinline__ void permute(uint64_t (&s)[12]) {
+    // round 0 constant layer (poseidon.rs:504-513); every later round gets its constants from
+    // the linear layer that precedes it
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = gl::add1(s[i], c_rc[i]);
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        // four full rounds (poseidon.rs:574-581)
+        const int base = half * 26;
+#pragma unroll 1
+        for (int r = base; r < base + 4; r++) {
+            if (SYNC) __syncthreads();
+            sbox_all(s);
+            mds_layer_f64(s, 12 * (r + 1));  // row 30 is zero
+        }
+        if (half == 0) {
+            // 22 partial rounds (poseidon.rs:623-628) as 11 fused pairs
+#pragma unroll 1
+            for (int g = 0; g < N_PARTIAL_PAIRS; g++) {
+                if (SYNC) __syncthreads();
+                partial_pair_f64(s, g);
+            }
+        }
+    }
+}
+#else
 template <bool SYNC = false>
 __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
     // round 0 constant layer (poseidon.rs:504-513); every later round gets its constants from
@@ -327,5 +531,6 @@ __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
         }
     }
 }
+#endif  // QP_POSEIDON_F64
 
 }  // namespace poseidon

@@ -23,6 +23,9 @@ KEYS = [
     ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe cycles %"),
     ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "FMA-heavy pipe cycles % (IMAD)"),
     ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe cycles %"),
+    ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "FP64 pipe inst % (DFMA)"),
+    ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "FP64 pipe cycles %"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU pipe inst % (I2F)"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput % (max unit)"),
     ("smsp__inst_executed.sum", "warp instructions"),
     ("dram__bytes_read.sum", "DRAM read"),
