@@ -195,6 +195,56 @@ int qp_fri_initial_coeffs(const qp_fri* f, uint64_t* out);
 int qp_fri_proof_of_work(qp_ctx* ctx, const uint64_t state12[12], unsigned witness_pos,
                          unsigned min_leading_zeros, uint64_t* witness_out);
 
+/* ---- Plonk permutation argument and quotient polynomials ------------------------------------ */
+/* What CommonCircuitData / ProverOnlyCircuitData contribute to these two steps
+ * (plonky2/src/plonk/circuit_data.rs:412-470), created once per circuit and kept on the device.
+ * The gate set (common_data.gates + selectors_info) arrives as a straight-line constraint program
+ * over F_p: 64-bit words  op | dst << 8 | a << 24 | b << 40  with
+ *   1 LDW dst = wire a            2 LDK dst = constants_sigmas polynomial a
+ *   3 LDP dst = public_inputs_hash[a]   4 LDI dst = pool[a]
+ *   5 ADD  6 SUB  7 MUL   (dst = r[a] op r[b])
+ *   8 EMIT a   the next constraint of the current gate, LAST constraint first
+ *   9 GATE a   end of a gate; r[a] holds its filter (compute_filter, gates/gate.rs:326-333)
+ * The program evaluates evaluate_gate_constraints_base_batch (vanishing_poly.rs:700-726); a Rust
+ * shim produces it by running Gate::eval_unfiltered_base_one over a recording field type, the
+ * Python mirror (qp-plonky2_b200/plonk.py) from its own gate classes. */
+typedef struct {
+    uint32_t degree_bits;            /* common_data.degree_bits() */
+    uint32_t quotient_degree_bits;   /* log2_ceil(quotient_degree_factor) */
+    uint32_t num_challenges;         /* config.num_challenges (<= 4) */
+    uint32_t num_routed_wires, num_wires;
+    uint32_t num_constants;          /* common_data.num_constants: sigmas start at this polynomial */
+    uint32_t num_partial_products;   /* per challenge */
+    uint32_t max_degree;             /* permutation_partial_product_degree() = quotient_degree_factor */
+    const uint64_t* k_is;            /* [num_routed_wires] (host) */
+    const uint64_t* sigmas;          /* prover_data.sigmas as columns [num_routed_wires][n]; may be NULL */
+    int sigmas_space;
+    const uint64_t* program;         /* (host) */
+    size_t program_len;
+    const uint64_t* pool;            /* field constants of the program (host) */
+    size_t pool_len;
+    uint32_t program_regs;           /* registers the program uses */
+} qp_circuit_desc;
+typedef struct qp_circuit qp_circuit;
+int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* desc, qp_circuit** out);
+void qp_circuit_free(qp_circuit* c);
+/* all_wires_permutation_partial_products (plonky2/src/plonk/prover.rs:402-480) followed by the
+ * Z-first ordering of prover.rs:255-261.  wires: witness columns [>= num_routed_wires][n] (values on
+ * H); betas, gammas: [num_challenges] (host).  out: [(nc + nc * num_partial_products)][n] value
+ * columns = Z_0 .. Z_{nc-1}, then the partial products of challenge 0, 1, ... -- the input of the
+ * second PolynomialBatch::from_values of prove(). */
+int qp_circuit_partial_products_and_zs(qp_circuit* c, const uint64_t* wires, int space, const uint64_t* betas,
+                                       const uint64_t* gammas, uint64_t* out, int out_space);
+/* compute_quotient_polys (plonky2/src/plonk/prover.rs:640-866, without lookups): evaluates the
+ * vanishing polynomial on the coset of size n << quotient_degree_bits from the three oracles' LDEs
+ * (which stay on the device), divides by Z_H and interpolates (coset_ifft).  out:
+ * [num_challenges][n << quotient_degree_bits] coefficients; read as [num_challenges *
+ * 2^quotient_degree_bits][n] they are the chunks prove() commits with from_coeffs (prover.rs:309-333). */
+int qp_circuit_compute_quotient_polys(qp_circuit* c, const qp_batch* constants_sigmas, const qp_batch* wires,
+                                      const qp_batch* zs_partial_products, const uint64_t* betas,
+                                      const uint64_t* gammas, const uint64_t* alphas,
+                                      const uint64_t public_inputs_hash[4], uint64_t* out, int out_space);
+
 #ifdef __cplusplus
 }
 #endif

@@ -120,6 +120,11 @@ def lib():
         "orc_eval_poly_ext": (None, [u64p, sz, u64p, u64p]),
         "orc_reduce_openings": (None, [sz, C.POINTER(sz), C.POINTER(u64p), u64p, u64p, u64p, u32, u64p]),
         "orc_num_threads": (C.c_int, []),
+        "orc_eval_vanishing_poly_base": (None, [C.c_void_p, u64, u64, u64p, u64p, u64p, u64p, u64p, u64p, u64p, u64p,
+                                                u64p, u64p, u64p]),
+        "orc_compute_quotient_polys": (C.c_int, [C.c_void_p, u32, u64p, sz, u64p, sz, u64p, sz, u64p, u64p, u64p,
+                                                 u64p, u64p]),
+        "orc_partial_products_and_zs": (None, [C.c_void_p, u64p, u64p, u64p, u64p, u64p]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -399,3 +404,72 @@ def fri_proof_bytes(oracle_batches, coeffs, values, challenger, rate_bits, cap_h
     out += final.astype("<u8").tobytes()
     out += int(w).to_bytes(8, "little")
     return bytes(out)
+
+
+# ---------------------------------------------------------------------------------------------
+# plonk permutation argument and quotient (plonky2/src/plonk/prover.rs:402-480,640-866)
+# ---------------------------------------------------------------------------------------------
+GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC = 0, 1, 2, 3
+
+
+class _OrcGate(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("param", C.c_uint32), ("index", C.c_uint32),
+                ("selector_index", C.c_uint32), ("group_start", C.c_uint32), ("group_end", C.c_uint32)]
+
+
+class _OrcCircuit(C.Structure):
+    _fields_ = [("degree_bits", C.c_uint32), ("quotient_degree_bits", C.c_uint32),
+                ("num_challenges", C.c_uint32), ("num_routed_wires", C.c_uint32), ("num_wires", C.c_uint32),
+                ("num_constants", C.c_uint32), ("num_partial_products", C.c_uint32), ("max_degree", C.c_uint32),
+                ("num_selectors", C.c_uint32), ("num_lookup_selectors", C.c_uint32), ("num_gates", C.c_uint32),
+                ("gates", C.POINTER(_OrcGate)), ("k_is", u64p)]
+
+
+class Circuit:
+    """The circuit description the oracle's plonk functions take.  `gates`: list of
+    (kind, param, selector_index, (group_start, group_end)) in SORTED gate order."""
+
+    def __init__(self, degree_bits, quotient_degree_bits, num_challenges, num_routed_wires, num_wires,
+                 num_constants, num_partial_products, max_degree, num_selectors, gates, k_is):
+        self._gates = (_OrcGate * len(gates))()
+        for i, (kind, param, sel, (gs, ge)) in enumerate(gates):
+            self._gates[i] = _OrcGate(kind, param, i, sel, gs, ge)
+        self._k_is = np.ascontiguousarray(k_is, dtype=np.uint64)
+        self.c = _OrcCircuit(degree_bits, quotient_degree_bits, num_challenges, num_routed_wires, num_wires,
+                             num_constants, num_partial_products, max_degree, num_selectors, 0, len(gates),
+                             self._gates, _ptr(self._k_is))
+        self.num_challenges = num_challenges
+        self.degree_bits, self.quotient_degree_bits = degree_bits, quotient_degree_bits
+        self.num_partial_products = num_partial_products
+
+    def eval_vanishing_poly_base(self, x, constants, wires, local_zs, next_zs, partial_products, s_sigmas,
+                                 betas, gammas, alphas, pih):
+        """eval_vanishing_poly_base_batch for one point x (vanishing_poly.rs:166-330)."""
+        arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in
+                (constants, wires, local_zs, next_zs, partial_products, s_sigmas, betas, gammas, alphas, pih)]
+        res = np.zeros(self.num_challenges, dtype=np.uint64)
+        z_h = (pow(int(x), 1 << self.degree_bits, P) - 1) % P
+        lib().orc_eval_vanishing_poly_base(C.byref(self.c), int(x), z_h, *[_ptr(a) for a in arrs], _ptr(res))
+        return res
+
+    def compute_quotient_polys(self, rate_bits, cs_leaves, wires_leaves, zs_leaves, betas, gammas, alphas, pih):
+        """compute_quotient_polys (prover.rs:640-866) from the three oracles' leaf-major LDE rows."""
+        arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in (betas, gammas, alphas, pih)]
+        L = [np.ascontiguousarray(a, dtype=np.uint64) for a in (cs_leaves, wires_leaves, zs_leaves)]
+        out = np.zeros((self.num_challenges, 1 << (self.degree_bits + self.quotient_degree_bits)), dtype=np.uint64)
+        rc = lib().orc_compute_quotient_polys(C.byref(self.c), rate_bits, _ptr(L[0]), L[0].shape[1], _ptr(L[1]),
+                                              L[1].shape[1], _ptr(L[2]), L[2].shape[1],
+                                              *[_ptr(a) for a in arrs], _ptr(out))
+        assert rc == 0, "Having constraints of degree higher than the rate is not supported yet."
+        return out
+
+    def partial_products_and_zs(self, wires, sigmas, betas, gammas):
+        """all_wires_permutation_partial_products, Z columns first (prover.rs:255-261,402-480)."""
+        w = np.ascontiguousarray(wires, dtype=np.uint64)
+        s = np.ascontiguousarray(sigmas, dtype=np.uint64)
+        b = np.ascontiguousarray(betas, dtype=np.uint64)
+        g = np.ascontiguousarray(gammas, dtype=np.uint64)
+        nc = self.num_challenges
+        out = np.zeros((nc * (1 + self.num_partial_products), 1 << self.degree_bits), dtype=np.uint64)
+        lib().orc_partial_products_and_zs(C.byref(self.c), _ptr(w), _ptr(s), _ptr(b), _ptr(g), _ptr(out))
+        return out

@@ -785,3 +785,212 @@ void orc_reduce_openings(size_t n_batches, const size_t *n_terms, const uint64_t
     free(comp);
     free(bs);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Plonk permutation argument and quotient polynomials
+ * plonky2/src/plonk/prover.rs:402-480,640-866, plonky2/src/plonk/vanishing_poly.rs:166-330,
+ * plonky2/src/util/partial_products.rs, field/src/zero_poly_coset.rs
+ * ---------------------------------------------------------------------------------------- */
+
+/* compute_filter, plonky2/src/gates/gate.rs:326-333 */
+static uint64_t gate_filter(const orc_gate *g, uint64_t s, int many_selectors) {
+    uint64_t f = 1;
+    for (unsigned i = g->group_start; i < g->group_end; i++)
+        if (i != g->index) f = gl_mul(f, gl_sub(i, s));
+    if (many_selectors) f = gl_mul(f, gl_sub(0xFFFFFFFFULL /* UNUSED_SELECTOR */, s));
+    return f;
+}
+
+/* eval_unfiltered of the supported gates; `consts` already has the selector prefix removed
+ * (gate.rs:179).  Adds filter * constraint_k into acc[k] (vanishing_poly.rs:700-726). */
+static void gate_eval_add(const orc_gate *g, const uint64_t *consts, const uint64_t *wires,
+                          const uint64_t pih[4], uint64_t filter, uint64_t *acc) {
+    switch (g->kind) {
+    case ORC_GATE_NOOP: /* gates/noop.rs: no constraints */
+        break;
+    case ORC_GATE_CONSTANT: /* gates/constant.rs:121-129 */
+        for (unsigned i = 0; i < g->param; i++)
+            acc[i] = gl_add(acc[i], gl_mul(filter, gl_sub(consts[i], wires[i])));
+        break;
+    case ORC_GATE_PUBLIC_INPUT: /* gates/public_input.rs:103-113 */
+        for (unsigned i = 0; i < 4; i++)
+            acc[i] = gl_add(acc[i], gl_mul(filter, gl_sub(wires[i], pih[i])));
+        break;
+    case ORC_GATE_ARITHMETIC: /* gates/arithmetic_base.rs:168-185 */
+        for (unsigned i = 0; i < g->param; i++) {
+            uint64_t m0 = wires[4 * i], m1 = wires[4 * i + 1], ad = wires[4 * i + 2], out = wires[4 * i + 3];
+            uint64_t computed = gl_add(gl_mul(gl_mul(m0, m1), consts[0]), gl_mul(ad, consts[1]));
+            acc[i] = gl_add(acc[i], gl_mul(filter, gl_sub(out, computed)));
+        }
+        break;
+    }
+}
+
+unsigned orc_gate_num_constraints(const orc_gate *g) {
+    switch (g->kind) {
+    case ORC_GATE_CONSTANT: return g->param;
+    case ORC_GATE_PUBLIC_INPUT: return 4;
+    case ORC_GATE_ARITHMETIC: return g->param;
+    default: return 0;
+    }
+}
+
+static unsigned circuit_num_gate_constraints(const orc_circuit *c) {
+    unsigned m = 0;
+    for (unsigned i = 0; i < c->num_gates; i++) {
+        unsigned k = orc_gate_num_constraints(&c->gates[i]);
+        if (k > m) m = k;
+    }
+    return m;
+}
+
+/* eval_vanishing_poly_base_batch for one point (vanishing_poly.rs:166-330, without lookups).
+ * x is the evaluation point itself (the reference passes the coset-shifted x), z_h_x = Z_H(x)
+ * = x^n - 1.  res[num_challenges]. */
+void orc_eval_vanishing_poly_base(const orc_circuit *c, uint64_t x, uint64_t z_h_x, const uint64_t *constants,
+                                  const uint64_t *wires, const uint64_t *local_zs, const uint64_t *next_zs,
+                                  const uint64_t *partial_products, const uint64_t *s_sigmas,
+                                  const uint64_t *betas, const uint64_t *gammas, const uint64_t *alphas,
+                                  const uint64_t pih[4], uint64_t *res) {
+    const unsigned nc = c->num_challenges, nr = c->num_routed_wires, np = c->num_partial_products;
+    const unsigned ngc = circuit_num_gate_constraints(c);
+    const unsigned n_terms = nc + nc * (np + 1) + ngc;
+    uint64_t *terms = calloc(n_terms, 8);
+    uint64_t *num = malloc(nr * 8), *den = malloc(nr * 8);
+    /* L_0(x) = Z_H(x) / (n (x - 1)), zero_poly_coset.rs:93-96 */
+    const uint64_t n_f = (uint64_t)1 << c->degree_bits;
+    const uint64_t l_0_x = gl_mul(z_h_x, orc_gl_inv(gl_mul(n_f, gl_sub(x, 1))));
+    uint64_t *pp_terms = terms + nc;
+    for (unsigned i = 0; i < nc; i++) {
+        const uint64_t z_x = local_zs[i], z_gx = next_zs[i];
+        terms[i] = gl_mul(l_0_x, gl_sub(z_x, 1));
+        for (unsigned j = 0; j < nr; j++) {
+            const uint64_t s_id = gl_mul(c->k_is[j], x);
+            num[j] = gl_add(gl_add(wires[j], gl_mul(betas[i], s_id)), gammas[i]);
+            den[j] = gl_add(gl_add(wires[j], gl_mul(betas[i], s_sigmas[j])), gammas[i]);
+        }
+        /* check_partial_products, util/partial_products.rs:52-95 */
+        const uint64_t *pp = partial_products + (size_t)i * np;
+        for (unsigned w = 0; w <= np; w++) {
+            const uint64_t prev = w == 0 ? z_x : pp[w - 1];
+            const uint64_t next = w == np ? z_gx : pp[w];
+            uint64_t pn = 1, pd = 1;
+            for (unsigned j = w * c->max_degree; j < (w + 1) * c->max_degree && j < nr; j++) {
+                pn = gl_mul(pn, num[j]);
+                pd = gl_mul(pd, den[j]);
+            }
+            pp_terms[(size_t)i * (np + 1) + w] = gl_sub(gl_mul(prev, pn), gl_mul(next, pd));
+        }
+    }
+    /* gate constraints, vanishing_poly.rs:700-726 */
+    uint64_t *gate_terms = terms + nc + nc * (np + 1);
+    const unsigned prefix = c->num_selectors + c->num_lookup_selectors;
+    for (unsigned g = 0; g < c->num_gates; g++) {
+        const orc_gate *gt = &c->gates[g];
+        const uint64_t f = gate_filter(gt, constants[gt->selector_index], c->num_selectors > 1);
+        gate_eval_add(gt, constants + prefix, wires, pih, f, gate_terms);
+    }
+    /* reduce_with_powers_multi, core/src/plonk_common.rs:68-85 */
+    for (unsigned a = 0; a < nc; a++) {
+        uint64_t cum = 0;
+        for (unsigned t = n_terms; t-- > 0;) cum = gl_add(gl_mul(cum, alphas[a]), terms[t]);
+        res[a] = orc_gl_canon(cum);
+    }
+    free(terms);
+    free(num);
+    free(den);
+}
+
+/* compute_quotient_polys (prover.rs:640-866).  The three oracles are given as their leaf-major
+ * LDE rows (merkle_tree.leaves, [N][leaf_len], N = n << rate_bits; leaf i = point
+ * g w_N^bitrev(i)); out = num_challenges coefficient vectors of length n << quotient_degree_bits. */
+int orc_compute_quotient_polys(const orc_circuit *c, unsigned rate_bits, const uint64_t *cs_leaves,
+                               size_t cs_len, const uint64_t *wires_leaves, size_t wires_len,
+                               const uint64_t *zs_leaves, size_t zs_len, const uint64_t *betas,
+                               const uint64_t *gammas, const uint64_t *alphas, const uint64_t pih[4],
+                               uint64_t *out) {
+    const unsigned qdb = c->quotient_degree_bits, nc = c->num_challenges;
+    if (qdb > rate_bits) return 1; /* prover.rs:662-666 */
+    const unsigned lg_lde = c->degree_bits + qdb, lg_N = c->degree_bits + rate_bits;
+    const size_t lde_size = (size_t)1 << lg_lde;
+    const size_t step = (size_t)1 << (rate_bits - qdb), next_step = (size_t)1 << qdb;
+    /* ZeroPolyOnCoset, zero_poly_coset.rs:24-66 */
+    const size_t rate = (size_t)1 << qdb;
+    uint64_t zh_eval[rate], zh_inv[rate];
+    const uint64_t g_pow_n = orc_gl_pow(orc_gl_coset_shift(), (uint64_t)1 << c->degree_bits);
+    const uint64_t v = orc_gl_primitive_root(qdb);
+    for (size_t k = 0; k < rate; k++) {
+        zh_eval[k] = gl_sub(gl_mul(g_pow_n, orc_gl_pow(v, k)), 1);
+        zh_inv[k] = orc_gl_inv(zh_eval[k]);
+    }
+    const uint64_t w = orc_gl_primitive_root(lg_lde);
+    const unsigned np = c->num_partial_products;
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < lde_size; i++) {
+        const uint64_t x = gl_mul(orc_gl_coset_shift(), orc_gl_pow(w, i));
+        const size_t i_next = (i + next_step) % lde_size;
+        /* get_lde_values(i, step), oracle.rs:286-291 */
+        const size_t row = bitrev(i * step, lg_N), row_next = bitrev(i_next * step, lg_N);
+        const uint64_t *cs = cs_leaves + row * cs_len;
+        const uint64_t *zl = zs_leaves + row * zs_len, *zn = zs_leaves + row_next * zs_len;
+        uint64_t res[16];
+        orc_eval_vanishing_poly_base(c, x, zh_eval[i % rate], cs, wires_leaves + row * wires_len, zl, zn,
+                                     zl + nc, cs + c->num_constants, betas, gammas, alphas, pih, res);
+        for (unsigned a = 0; a < nc; a++) out[(size_t)a * lde_size + i] = gl_mul(res[a], zh_inv[i % rate]);
+    }
+    (void)np;
+    /* values.coset_ifft(F::coset_shift()), field/src/polynomial/mod.rs:58-88 */
+    const uint64_t g_inv = orc_gl_inv(orc_gl_coset_shift());
+    for (unsigned a = 0; a < nc; a++) {
+        uint64_t *p = out + (size_t)a * lde_size;
+        orc_ifft(p, lg_lde);
+        uint64_t s = 1;
+        for (size_t i = 0; i < lde_size; i++) {
+            p[i] = orc_gl_canon(gl_mul(p[i], s));
+            s = gl_mul(s, g_inv);
+        }
+    }
+    return 0;
+}
+
+/* wires_permutation_partial_products_and_zs for every challenge (prover.rs:402-480), laid out as
+ * the prover commits them (prover.rs:255-261): out[(nc + nc*np)][n] = Z_0..Z_{nc-1}, then the
+ * partial products of challenge 0, of challenge 1, ...  wires[num_wires][n], sigmas[nr][n]. */
+void orc_partial_products_and_zs(const orc_circuit *c, const uint64_t *wires, const uint64_t *sigmas,
+                                 const uint64_t *betas, const uint64_t *gammas, uint64_t *out) {
+    const unsigned nc = c->num_challenges, nr = c->num_routed_wires, np = c->num_partial_products;
+    const size_t n = (size_t)1 << c->degree_bits;
+    const uint64_t w = orc_gl_primitive_root(c->degree_bits);
+    uint64_t *chunk = malloc(n * (np + 1) * 8);
+    for (unsigned ch = 0; ch < nc; ch++) {
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < n; i++) {
+            const uint64_t x = orc_gl_pow(w, i);
+            uint64_t q[nr];
+            for (unsigned j = 0; j < nr; j++) {
+                const uint64_t wv = wires[(size_t)j * n + i];
+                const uint64_t num = gl_add(gl_add(wv, gl_mul(betas[ch], gl_mul(c->k_is[j], x))), gammas[ch]);
+                const uint64_t den = gl_add(gl_add(wv, gl_mul(betas[ch], sigmas[(size_t)j * n + i])), gammas[ch]);
+                q[j] = gl_mul(num, orc_gl_inv(den));
+            }
+            /* quotient_chunk_products, util/partial_products.rs:13-24 */
+            for (unsigned k = 0; k <= np; k++) {
+                uint64_t p = 1;
+                for (unsigned j = k * c->max_degree; j < (k + 1) * c->max_degree && j < nr; j++) p = gl_mul(p, q[j]);
+                chunk[i * (np + 1) + k] = p;
+            }
+        }
+        /* partial_products_and_z_gx + the swap (prover.rs:466-473) */
+        uint64_t z_x = 1;
+        for (size_t i = 0; i < n; i++) {
+            uint64_t acc = z_x;
+            out[(size_t)ch * n + i] = orc_gl_canon(z_x);
+            for (unsigned k = 0; k <= np; k++) {
+                acc = gl_mul(acc, chunk[i * (np + 1) + k]);
+                if (k < np) out[((size_t)nc + (size_t)ch * np + k) * n + i] = orc_gl_canon(acc);
+            }
+            z_x = acc;
+        }
+    }
+    free(chunk);
+}

@@ -122,6 +122,40 @@ void orc_reduce_openings(size_t n_batches, const size_t *n_terms, const uint64_t
                          const uint64_t *weights, const uint64_t *points, const uint64_t *shifts,
                          unsigned degree_log, uint64_t *final_out /* [n][2] */);
 
+/* ---- plonk permutation argument and quotient (plonky2/src/plonk/prover.rs:402-480,640-866,
+ *      plonky2/src/plonk/vanishing_poly.rs:166-330) -------------------------------------------- */
+enum { ORC_GATE_NOOP = 0, ORC_GATE_CONSTANT = 1, ORC_GATE_PUBLIC_INPUT = 2, ORC_GATE_ARITHMETIC = 3 };
+typedef struct {
+    uint32_t kind;           /* ORC_GATE_* */
+    uint32_t param;          /* num_consts (ConstantGate) / num_ops (ArithmeticGate) */
+    uint32_t index;          /* position in the sorted gate list = selector value */
+    uint32_t selector_index; /* SelectorsInfo.selector_indices[index] */
+    uint32_t group_start, group_end; /* SelectorsInfo.groups[selector_index] */
+} orc_gate;
+typedef struct {
+    uint32_t degree_bits, quotient_degree_bits;
+    uint32_t num_challenges, num_routed_wires, num_wires;
+    uint32_t num_constants;  /* constant columns (selectors included) of the constants_sigmas oracle */
+    uint32_t num_partial_products, max_degree; /* per challenge; chunk size = quotient_degree_factor */
+    uint32_t num_selectors, num_lookup_selectors;
+    uint32_t num_gates;
+    const orc_gate *gates;
+    const uint64_t *k_is;    /* [num_routed_wires] */
+} orc_circuit;
+unsigned orc_gate_num_constraints(const orc_gate *g);
+void orc_eval_vanishing_poly_base(const orc_circuit *c, uint64_t x, uint64_t z_h_x, const uint64_t *constants,
+                                  const uint64_t *wires, const uint64_t *local_zs, const uint64_t *next_zs,
+                                  const uint64_t *partial_products, const uint64_t *s_sigmas,
+                                  const uint64_t *betas, const uint64_t *gammas, const uint64_t *alphas,
+                                  const uint64_t pih[4], uint64_t *res);
+int orc_compute_quotient_polys(const orc_circuit *c, unsigned rate_bits, const uint64_t *cs_leaves,
+                               size_t cs_len, const uint64_t *wires_leaves, size_t wires_len,
+                               const uint64_t *zs_leaves, size_t zs_len, const uint64_t *betas,
+                               const uint64_t *gammas, const uint64_t *alphas, const uint64_t pih[4],
+                               uint64_t *out);
+void orc_partial_products_and_zs(const orc_circuit *c, const uint64_t *wires, const uint64_t *sigmas,
+                                 const uint64_t *betas, const uint64_t *gammas, uint64_t *out);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

@@ -30,7 +30,7 @@ LIB_PATH = os.environ.get("QP_PLONKY2_LIB") or os.path.join(_HERE, "libqp_plonky
 _SOURCES = [
     os.path.join(_HERE, "csrc", f)
     for f in ("qp_plonky2.cu", "goldilocks.cuh", "poseidon.cuh", "poseidon_constants.h", "ntt.cuh",
-              "merkle.cuh", "fri.cuh")
+              "merkle.cuh", "fri.cuh", "openings.cuh", "quotient.cuh")
 ] + [
     os.path.join(_HERE, "host", "transcript.cpp"),
     os.path.join(_ROOT, "include", "qp_plonky2_b200.h"),
@@ -171,6 +171,11 @@ def lib():
         "qp_fri_committed_trees": (i32, [vp, vp, vp, i32, u32, u32, u32, C.POINTER(u32), u32,
                                          C.POINTER(_ChallengerState), vp, vp, C.POINTER(sz), pp]),
         "qp_fri_grind": (i32, [vp, C.POINTER(_ChallengerState), u32, u64p]),
+        # plonk permutation argument and quotient (plonk.py)
+        "qp_circuit_create": (i32, [vp, vp, pp]),
+        "qp_circuit_free": (None, [vp]),
+        "qp_circuit_partial_products_and_zs": (i32, [vp, vp, i32, vp, vp, vp, i32]),
+        "qp_circuit_compute_quotient_polys": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

@@ -151,9 +151,20 @@ __device__ __forceinline__ uint64_t neg(uint64_t a) {
 // carry predicates (9 SASS instructions for reduce128, against 13 for the borrow/carry-chain form
 // that PTX add.cc/sub.cc can express).
 
-// r + w * EPS for a small signed w
-__device__ __forceinline__ uint64_t add_w_eps(uint64_t r, int64_t w) {
-    return r + (uint64_t)((w << 32) - w);
+// r + w * EPS for a small signed w:  (r1 + w : r0) - sign_extend(w), as a two-word subtraction
+__device__ __forceinline__ uint64_t add_w_eps(uint64_t r, int32_t w) {
+    uint32_t r0, r1, lo, hi;
+    unpack(r, r0, r1);
+    asm("{\n\t"
+        ".reg .u32 t, sgn;\n\t"
+        "add.u32      t, %3, %4;\n\t"
+        "shr.s32      sgn, %4, 31;\n\t"
+        "sub.cc.u32   %0, %2, %4;\n\t"
+        "subc.u32     %1, t, sgn;\n\t"
+        "}"
+        : "=&r"(lo), "=&r"(hi)
+        : "r"(r0), "r"(r1), "r"(w));
+    return pack(lo, hi);
 }
 
 // (hi:lo), hi 32 bits  ->  lo + hi * EPS  (reduce96, goldilocks_field.rs:381-385).
@@ -163,7 +174,7 @@ __device__ __forceinline__ uint64_t reduce96(uint64_t lo, uint32_t hi) {
     unpack(lo, x0, x1);
     const int64_t u = (int64_t)(uint64_t)x0 - (int64_t)(uint64_t)hi;
     const int64_t v = (int64_t)((uint64_t)x1 + hi) + (u >> 32);
-    return add_w_eps(pack((uint32_t)u, (uint32_t)v), v >> 32);
+    return add_w_eps(pack((uint32_t)u, (uint32_t)v), (int32_t)(v >> 32));
 }
 
 // Reduce the 128-bit value (hi:lo) mod p; output is some u64 representative.
@@ -176,7 +187,7 @@ __device__ __forceinline__ uint64_t reduce128(uint64_t lo, uint64_t hi) {
     unpack(hi, x2, x3);
     const int64_t u = (int64_t)(uint64_t)x0 - (int64_t)(uint64_t)x2 - (int64_t)(uint64_t)x3;
     const int64_t v = (int64_t)((uint64_t)x1 + x2) + (u >> 32);
-    return add_w_eps(pack((uint32_t)u, (uint32_t)v), v >> 32);
+    return add_w_eps(pack((uint32_t)u, (uint32_t)v), (int32_t)(v >> 32));
 }
 
 // w0 + (w1 + v0) B + v1 B^2  ->  field element, for w1 + v1 < 2^32: the sum of two 64-bit
@@ -185,7 +196,7 @@ __device__ __forceinline__ uint64_t reduce128(uint64_t lo, uint64_t hi) {
 __device__ __forceinline__ uint64_t fold3(uint32_t w0, uint32_t w1, uint32_t v0, uint32_t v1) {
     const int64_t u = (int64_t)(uint64_t)w0 - (int64_t)(uint64_t)v1;
     const int64_t v = (int64_t)((uint64_t)w1 + v0 + v1) + (u >> 32);
-    return add_w_eps(pack((uint32_t)u, (uint32_t)v), v >> 32);
+    return add_w_eps(pack((uint32_t)u, (uint32_t)v), (int32_t)(v >> 32));
 }
 
 // 64 x 64 -> 128 bit product as (lo, hi).  Four IMAD.WIDE.U32 and a 32-bit carry chain that

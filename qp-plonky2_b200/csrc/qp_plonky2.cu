@@ -20,6 +20,7 @@
 #include "ntt.cuh"
 #include "openings.cuh"
 #include "poseidon.cuh"
+#include "quotient.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // context
@@ -1500,4 +1501,262 @@ extern "C" int qp_fri_proof_of_work(qp_ctx* ctx, const uint64_t state12[12], uns
     if (found == UINT64_MAX) return fail(ctx, QP_ERR_BAD_ARG, "Proof of work failed. This is highly unlikely!");
     *witness_out = found;
     return QP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Plonk permutation argument and quotient polynomials (quotient.cuh)
+// ---------------------------------------------------------------------------------------------
+struct qp_circuit {
+    qp_ctx* ctx = nullptr;
+    qp_circuit_desc d{};          // scalar fields only; the pointers below are the device copies
+    uint64_t* k_is = nullptr;     // [num_routed_wires]
+    uint64_t* sigmas = nullptr;   // [num_routed_wires][n], may be null (quotient-only circuits)
+    uint64_t* program = nullptr;  // program_len + 1 words (OP_END appended)
+    uint64_t* pool = nullptr;
+    uint64_t* zh = nullptr;       // [2][2^qdb]: Z_H on the coset, and its inverses
+    ScaleTables g_inv;            // powers of 1/g up to 2^(degree_bits + qdb)
+};
+
+extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circuit** out) {
+    if (!ctx || !d || !out) return QP_ERR_BAD_ARG;
+    *out = nullptr;
+    if (d->num_challenges == 0 || d->num_challenges > (unsigned)quotient::MAX_CHALLENGES)
+        return fail(ctx, QP_ERR_BAD_ARG, "num_challenges must be 1..4");
+    if (d->max_degree < 2) return fail(ctx, QP_ERR_BAD_ARG, "max_degree > 1 (util/partial_products.rs:17)");
+    if (d->num_routed_wires == 0 || d->num_routed_wires > d->num_wires || !d->k_is)
+        return fail(ctx, QP_ERR_BAD_ARG, "bad wire counts");
+    // num_partial_products(n, max_degree) = ceil(n / max_degree) - 1, util/partial_products.rs:41-48
+    if (d->num_partial_products + 1 != (d->num_routed_wires + d->max_degree - 1) / d->max_degree ||
+        d->num_partial_products + 1 > (unsigned)quotient::MAX_CHUNKS)
+        return fail(ctx, QP_ERR_BAD_ARG, "num_partial_products inconsistent with num_routed_wires / max_degree");
+    if (d->degree_bits + d->quotient_degree_bits > ctx->tw_lg)
+        return fail(ctx, QP_ERR_TOO_LARGE, "quotient domain larger than the context's twiddle table");
+    if (d->program_len && !d->program) return fail(ctx, QP_ERR_BAD_ARG, "null program");
+    if ((size_t)d->program_regs * quotient::BLOCK * 8 > 200 * 1024)
+        return fail(ctx, QP_ERR_TOO_LARGE, "constraint program needs too many registers");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    qp_circuit* c = new qp_circuit();
+    c->ctx = ctx;
+    c->d = *d;
+    const size_t n = (size_t)1 << d->degree_bits;
+    int rc = dev_alloc(ctx, &c->k_is, d->num_routed_wires);
+    if (!rc) rc = dev_alloc(ctx, &c->program, d->program_len + 1);
+    if (!rc) rc = dev_alloc(ctx, &c->pool, d->pool_len ? d->pool_len : 1);
+    if (!rc) rc = dev_alloc(ctx, &c->zh, (size_t)2 << d->quotient_degree_bits);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(c->k_is, d->k_is, d->num_routed_wires * 8, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<uint64_t> prog(d->program, d->program + d->program_len);
+    prog.push_back(quotient::OP_END);
+    CUDA_TRY(ctx, cudaMemcpyAsync(c->program, prog.data(), prog.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (d->pool_len)
+        CUDA_TRY(ctx, cudaMemcpyAsync(c->pool, d->pool, d->pool_len * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // ZeroPolyOnCoset (field/src/zero_poly_coset.rs:24-66): g^n v^k - 1 and inverses, k < 2^qdb
+    const size_t rate = (size_t)1 << d->quotient_degree_bits;
+    std::vector<uint64_t> zh(2 * rate);
+    const uint64_t g_pow_n = gl::host_pow(gl::GENERATOR, (uint64_t)1 << d->degree_bits);
+    const uint64_t v = gl::host_primitive_root(d->quotient_degree_bits);
+    for (size_t k = 0; k < rate; k++) {
+        const uint64_t t = gl::host_mul(g_pow_n, gl::host_pow(v, k));
+        zh[k] = t ? t - 1 : gl::P - 1;
+        zh[rate + k] = gl::host_pow(zh[k], gl::P - 2);
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(c->zh, zh.data(), zh.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors die here
+    if (d->sigmas) {
+        const uint64_t* dev = nullptr;
+        uint64_t* owned = nullptr;
+        rc = to_device(ctx, d->sigmas, d->sigmas_space, (size_t)d->num_routed_wires * n, &dev, &owned);
+        if (rc) return rc;
+        if (!owned) {
+            rc = dev_alloc(ctx, &owned, (size_t)d->num_routed_wires * n);
+            if (rc) return rc;
+            CUDA_TRY(ctx, cudaMemcpyAsync(owned, dev, (size_t)d->num_routed_wires * n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        c->sigmas = owned;
+    }
+    rc = build_scale(ctx, (int)(d->degree_bits + d->quotient_degree_bits), {gl::host_pow(gl::GENERATOR, gl::P - 2)}, &c->g_inv);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    c->d.k_is = c->d.sigmas = c->d.program = c->d.pool = nullptr;
+    *out = c;
+    return QP_OK;
+}
+
+extern "C" void qp_circuit_free(qp_circuit* c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    dev_free(c->ctx, c->k_is);
+    dev_free(c->ctx, c->sigmas);
+    dev_free(c->ctx, c->program);
+    dev_free(c->ctx, c->pool);
+    dev_free(c->ctx, c->zh);
+    cudaStreamSynchronize(c->ctx->stream);
+    free_scale(&c->g_inv);
+    delete c;
+}
+
+// all_wires_permutation_partial_products (prover.rs:402-480) + the Z-first reordering of
+// prover.rs:255-261: out[(nc + nc * np)][n].
+extern "C" int qp_circuit_partial_products_and_zs(qp_circuit* c, const uint64_t* wires, int space,
+                                                  const uint64_t* betas, const uint64_t* gammas, uint64_t* out,
+                                                  int out_space) {
+    if (!c) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = c->ctx;
+    if (!wires || !betas || !gammas || !out) return fail(ctx, QP_ERR_BAD_ARG, "null argument");
+    if (!c->sigmas) return fail(ctx, QP_ERR_BAD_ARG, "circuit was created without sigmas");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const qp_circuit_desc& d = c->d;
+    const size_t n = (size_t)1 << d.degree_bits;
+    const unsigned nc = d.num_challenges, np = d.num_partial_products;
+    const uint64_t* d_wires = nullptr;
+    uint64_t* owned = nullptr;
+    // only the routed wires are read
+    int rc = to_device(ctx, wires, space, (size_t)d.num_routed_wires * n, &d_wires, &owned);
+    if (rc) return rc;
+    quotient::PermParams p{};
+    p.degree_bits = d.degree_bits;
+    p.nc = nc;
+    p.nr = d.num_routed_wires;
+    p.np = np;
+    p.max_degree = d.max_degree;
+    p.wires = d_wires;
+    p.sigmas = c->sigmas;
+    p.k_is = c->k_is;
+    p.tw_row = ctx->tw + ((size_t)1 << d.degree_bits);
+    for (unsigned i = 0; i < nc; i++) {
+        p.betas[i] = betas[i];
+        p.gammas[i] = gammas[i];
+    }
+    const size_t tiles_per_vec = n / quotient::SCAN_TILE ? n / quotient::SCAN_TILE : 1;
+    const size_t n_tiles = tiles_per_vec * nc;
+    uint64_t *tile = nullptr, *d_out = nullptr;
+    rc = dev_alloc(ctx, &p.chunk, (size_t)nc * (np + 1) * n);
+    if (!rc) rc = dev_alloc(ctx, &p.rowprod, (size_t)nc * n);
+    if (!rc) rc = dev_alloc(ctx, &tile, n_tiles);
+    const size_t out_words = (size_t)(nc + nc * np) * n;
+    if (!rc) {
+        if (out_space == QP_DEVICE) d_out = out;
+        else rc = dev_alloc(ctx, &d_out, out_words);
+    }
+    if (rc) return rc;
+    LAUNCH(ctx, quotient::perm_chunks_kernel, cdiv(n * nc, 128), 128, 0, p);
+    LAUNCH(ctx, quotient::scan_tile_products_kernel, (unsigned)n_tiles, quotient::SCAN_BLOCK, 0, p.rowprod, n,
+           tiles_per_vec, tile);
+    LAUNCH(ctx, quotient::scan_tiles_kernel, nc, quotient::SCAN_BLOCK, 0, tile, tiles_per_vec);
+    LAUNCH(ctx, quotient::perm_finish_kernel, (unsigned)n_tiles, quotient::SCAN_BLOCK, 0, p, tiles_per_vec, tile, d_out);
+    if (out_space != QP_DEVICE) {
+        rc = copy_out(ctx, out, QP_HOST, d_out, out_words);
+        dev_free(ctx, d_out);
+    }
+    dev_free(ctx, p.chunk);
+    dev_free(ctx, p.rowprod);
+    dev_free(ctx, tile);
+    dev_free(ctx, owned);
+    if (!rc) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+// compute_quotient_polys (prover.rs:640-866): out[num_challenges][n << qdb] coefficients.
+extern "C" int qp_circuit_compute_quotient_polys(qp_circuit* c, const qp_batch* constants_sigmas,
+                                                 const qp_batch* wires, const qp_batch* zs_partial_products,
+                                                 const uint64_t* betas, const uint64_t* gammas,
+                                                 const uint64_t* alphas, const uint64_t public_inputs_hash[4],
+                                                 uint64_t* out, int out_space) {
+    if (!c) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = c->ctx;
+    if (!constants_sigmas || !wires || !zs_partial_products || !betas || !gammas || !alphas ||
+        !public_inputs_hash || !out)
+        return fail(ctx, QP_ERR_BAD_ARG, "null argument");
+    const qp_circuit_desc& d = c->d;
+    const unsigned nc = d.num_challenges, np = d.num_partial_products;
+    const qp_batch* bs[3] = {constants_sigmas, wires, zs_partial_products};
+    for (const qp_batch* b : bs) {
+        if (b->ctx != ctx) return fail(ctx, QP_ERR_BAD_ARG, "batch belongs to another context");
+        if (b->degree_log != d.degree_bits) return fail(ctx, QP_ERR_DEGREE_MISMATCH, "Polynomial degrees inconsistent");
+        // "Having constraints of degree higher than the rate is not supported yet", prover.rs:662-666
+        if (d.quotient_degree_bits > b->rate_bits) return fail(ctx, QP_ERR_BAD_ARG, "quotient degree exceeds the rate");
+        if (b->block_first != 0 || b->block_count != (1u << b->rate_bits))
+            return fail(ctx, QP_ERR_BAD_ARG, "quotient evaluation needs unsharded batches");
+    }
+    if (constants_sigmas->n_cols < (size_t)d.num_constants + d.num_routed_wires || wires->n_cols < d.num_wires ||
+        zs_partial_products->n_cols < (size_t)nc + (size_t)nc * np)
+        return fail(ctx, QP_ERR_BAD_ARG, "batch has too few polynomials for this circuit");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const unsigned lg_lde = d.degree_bits + d.quotient_degree_bits;
+    const size_t n_lde = (size_t)1 << lg_lde;
+    quotient::Params p{};
+    p.degree_bits = d.degree_bits;
+    p.qdb = d.quotient_degree_bits;
+    p.lg_lde = lg_lde;
+    p.nc = nc;
+    p.nr = d.num_routed_wires;
+    p.np = np;
+    p.max_degree = d.max_degree;
+    p.num_constants = d.num_constants;
+    p.cs = constants_sigmas->lde;
+    p.cs_stride = constants_sigmas->n_local;
+    p.wires = wires->lde;
+    p.wires_stride = wires->n_local;
+    p.zs = zs_partial_products->lde;
+    p.zs_stride = zs_partial_products->n_local;
+    p.tw_row = ctx->tw + ((size_t)1 << lg_lde);
+    p.k_is = c->k_is;
+    p.zh_eval = c->zh;
+    p.zh_inv = c->zh + ((size_t)1 << d.quotient_degree_bits);
+    p.program = c->program;
+    p.pool = c->pool;
+    p.n_regs = d.program_regs;
+    const unsigned base = nc + nc * (np + 1);
+    std::vector<uint64_t> apow((size_t)nc * (base + 1));
+    for (unsigned a = 0; a < nc; a++) {
+        p.betas[a] = betas[a];
+        p.gammas[a] = gammas[a];
+        p.alphas[a] = alphas[a];
+        uint64_t pw = 1;
+        for (unsigned t = 0; t <= base; t++) {
+            apow[(size_t)a * (base + 1) + t] = pw;
+            pw = gl::host_mul(pw, alphas[a] % gl::P);
+        }
+    }
+    for (int i = 0; i < 4; i++) p.pih[i] = public_inputs_hash[i];
+    uint64_t *d_apow = nullptr, *d_out = nullptr;
+    int rc = dev_alloc(ctx, &d_apow, apow.size());
+    const size_t out_words = (size_t)nc * n_lde;
+    if (!rc) {
+        if (out_space == QP_DEVICE) d_out = out;
+        else rc = dev_alloc(ctx, &d_out, out_words);
+    }
+    uint64_t* d_vals = nullptr;
+    if (!rc) rc = dev_alloc(ctx, &d_vals, out_words);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_apow, apow.data(), apow.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    p.alpha_pows = d_apow;
+    p.out = d_vals;
+    const size_t smem = (size_t)(d.program_regs ? d.program_regs : 1) * quotient::BLOCK * 8;
+    if (smem > 48 * 1024)
+        CUDA_TRY(ctx, cudaFuncSetAttribute(quotient::quotient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(ctx, quotient::quotient_kernel, cdiv(n_lde, quotient::BLOCK), quotient::BLOCK, smem, p);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // apow dies at return
+    // values.coset_ifft(F::coset_shift()), polynomial/mod.rs:58-88
+    NttJob job;
+    job.src = d_vals;
+    job.dst = d_out;
+    job.L = (int)lg_lde;
+    job.n_vec = nc;
+    job.inner_bits = 0;
+    job.src_outer = n_lde;
+    job.dst_outer = n_lde;
+    job.out_mode = ntt::OUT_INVERSE;
+    job.scratch = d_vals;
+    rc = run_ntt(ctx, job);
+    if (!rc) {
+        LAUNCH(ctx, quotient::scale_powers_kernel, cdiv(out_words, 256), 256, 0, d_out, (size_t)nc, lg_lde,
+               c->g_inv.lo, c->g_inv.hi, c->g_inv.split);
+        if (out_space != QP_DEVICE) rc = copy_out(ctx, out, QP_HOST, d_out, out_words);
+    }
+    if (out_space != QP_DEVICE) dev_free(ctx, d_out);
+    dev_free(ctx, d_vals);
+    dev_free(ctx, d_apow);
+    if (!rc) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
 }

@@ -1,0 +1,354 @@
+// Plonk permutation argument and quotient evaluation on the device.
+//
+// Reference semantics:
+//   wires_permutation_partial_products_and_zs   plonky2/src/plonk/prover.rs:402-480
+//   compute_quotient_polys                      plonky2/src/plonk/prover.rs:640-866
+//   eval_vanishing_poly_base_batch              plonky2/src/plonk/vanishing_poly.rs:166-330
+//   check_partial_products                      plonky2/src/util/partial_products.rs:52-95
+//   ZeroPolyOnCoset                             field/src/zero_poly_coset.rs
+//   reduce_with_powers_multi                    core/src/plonk_common.rs:68-85
+//
+// B200 formulation.  The three oracles keep their LDE column-major in leaf order (ntt.cuh), so
+// the points of the quotient domain (every `step`-th point of the LDE) are the FIRST n << qdb
+// positions of every column: one thread per position reads all columns coalesced, and the
+// reference's per-batch gather/transposes (prover.rs:745-800) do not exist.  The gate set is
+// data (common_data.gates): the host compiles every gate's filtered constraints into one
+// straight-line program over F_p (plonk.py / the Rust shim's recording field type) and the
+// kernel interprets it with its register file in shared memory -- exact arithmetic, so any
+// evaluation order gives the reference's values.
+#pragma once
+#include "goldilocks.cuh"
+
+namespace quotient {
+
+// Constraint program: 64-bit words  op | dst << 8 | a << 24 | b << 40.
+enum : unsigned {
+    OP_END = 0,
+    OP_LDW = 1,   // dst = wire column a
+    OP_LDK = 2,   // dst = constants_sigmas column a
+    OP_LDP = 3,   // dst = public_inputs_hash[a]
+    OP_LDI = 4,   // dst = pool[a]
+    OP_ADD = 5,
+    OP_SUB = 6,
+    OP_MUL = 7,
+    OP_EMIT = 8,  // next constraint of the current gate (emitted LAST to FIRST): h = h alpha + r[a]
+    OP_GATE = 9,  // end of a gate: G += r[a] (filter) * h, h = 0
+};
+
+constexpr int MAX_CHALLENGES = 4;
+constexpr int BLOCK = 128;
+
+__device__ __forceinline__ uint64_t inverse(uint64_t a) { return gl::pow(a, gl::P - 2); }
+
+__device__ __forceinline__ size_t brev(size_t x, unsigned bits) {
+    return bits ? (size_t)(__brevll((unsigned long long)x) >> (64 - bits)) : 0;
+}
+
+struct Params {
+    // domains
+    unsigned degree_bits, qdb, lg_lde;     // lg_lde = degree_bits + qdb
+    unsigned nc, nr, np, max_degree, num_constants;
+    // oracles: column-major LDE in leaf order, column stride = their local LDE length
+    const uint64_t* cs;
+    size_t cs_stride;
+    const uint64_t* wires;
+    size_t wires_stride;
+    const uint64_t* zs;
+    size_t zs_stride;
+    // tables
+    const uint64_t* tw_row;      // tw_row[i] = w_{2^lg_lde}^i
+    const uint64_t* k_is;        // [nr]
+    const uint64_t* zh_eval;     // [2^qdb]  g^n v^k - 1
+    const uint64_t* zh_inv;      // [2^qdb]
+    const uint64_t* alpha_pows;  // [nc][base + 1], base = nc + nc (np + 1)
+    uint64_t betas[MAX_CHALLENGES], gammas[MAX_CHALLENGES], alphas[MAX_CHALLENGES];
+    uint64_t pih[4];
+    // gate program
+    const uint64_t* program;
+    const uint64_t* pool;
+    unsigned n_regs;
+    uint64_t* out;  // [nc][2^lg_lde], natural order
+};
+
+// One thread per point of the quotient domain, enumerated in leaf order.
+__global__ void __launch_bounds__(BLOCK) quotient_kernel(Params p) {
+    extern __shared__ uint64_t regs[];  // [n_regs][BLOCK]
+    const size_t n_lde = (size_t)1 << p.lg_lde;
+    const size_t pos_raw = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    const bool live = pos_raw < n_lde;
+    const size_t pos = live ? pos_raw : n_lde - 1;
+    const size_t i = brev(pos, p.lg_lde);  // natural index: the point is g w^i
+    const size_t pos_next = brev((i + ((size_t)1 << p.qdb)) & (n_lde - 1), p.lg_lde);
+    const uint64_t x = gl::mul(gl::GENERATOR, p.tw_row[i]);
+    const unsigned zi = (unsigned)(i & (((size_t)1 << p.qdb) - 1));
+    // L_0(x) = Z_H(x) / (n (x - 1)), zero_poly_coset.rs:93-96
+    const uint64_t l_0 = gl::mul(p.zh_eval[zi], inverse(gl::mul((uint64_t)1 << p.degree_bits, gl::sub(x, 1))));
+    const unsigned base = p.nc + p.nc * (p.np + 1);
+    uint64_t res[MAX_CHALLENGES];
+#pragma unroll
+    for (int a = 0; a < MAX_CHALLENGES; a++) res[a] = 0;
+    auto add_term = [&](unsigned t, uint64_t term) {
+#pragma unroll
+        for (int a = 0; a < MAX_CHALLENGES; a++)
+            if (a < (int)p.nc) res[a] = gl::add(res[a], gl::mul(term, p.alpha_pows[a * (base + 1) + t]));
+    };
+    // the L_0(x) (Z(x) - 1) terms, vanishing_poly.rs:268-272
+    for (unsigned ch = 0; ch < p.nc; ch++) add_term(ch, gl::mul(l_0, gl::sub(p.zs[ch * p.zs_stride + pos], 1)));
+    // partial product checks, vanishing_poly.rs:297-320
+    {
+        uint64_t pn[MAX_CHALLENGES], pd[MAX_CHALLENGES], bx[MAX_CHALLENGES];
+#pragma unroll
+        for (int c = 0; c < MAX_CHALLENGES; c++) {
+            pn[c] = pd[c] = 1;
+            bx[c] = c < (int)p.nc ? gl::mul(p.betas[c], x) : 0;
+        }
+        unsigned w = 0, in_chunk = 0;
+        for (unsigned j = 0; j < p.nr; j++) {
+            const uint64_t wire = p.wires[j * p.wires_stride + pos];
+            const uint64_t sigma = p.cs[(p.num_constants + j) * p.cs_stride + pos];
+            const uint64_t k = p.k_is[j];
+#pragma unroll
+            for (int c = 0; c < MAX_CHALLENGES; c++) {
+                if (c < (int)p.nc) {
+                    const uint64_t wg = gl::add(wire, p.gammas[c]);
+                    pn[c] = gl::mul(pn[c], gl::add(wg, gl::mul(bx[c], k)));
+                    pd[c] = gl::mul(pd[c], gl::add(wg, gl::mul(p.betas[c], sigma)));
+                }
+            }
+            if (++in_chunk == p.max_degree || j + 1 == p.nr) {
+#pragma unroll
+                for (int c = 0; c < MAX_CHALLENGES; c++) {
+                    if (c < (int)p.nc) {
+                        // accumulators Z(x), p_0 .. p_{np-1}, Z(g x): util/partial_products.rs:60-63
+                        const uint64_t prev = w == 0 ? p.zs[c * p.zs_stride + pos]
+                                                     : p.zs[(p.nc + c * p.np + w - 1) * p.zs_stride + pos];
+                        const uint64_t next = w == p.np ? p.zs[c * p.zs_stride + pos_next]
+                                                        : p.zs[(p.nc + c * p.np + w) * p.zs_stride + pos];
+                        add_term(p.nc + c * (p.np + 1) + w, gl::sub(gl::mul(prev, pn[c]), gl::mul(next, pd[c])));
+                        pn[c] = pd[c] = 1;
+                    }
+                }
+                w++;
+                in_chunk = 0;
+            }
+        }
+    }
+    // gate constraints (vanishing_poly.rs:700-726): G = sum over gates of filter * Horner(constraints)
+    uint64_t G[MAX_CHALLENGES], h[MAX_CHALLENGES];
+#pragma unroll
+    for (int a = 0; a < MAX_CHALLENGES; a++) G[a] = h[a] = 0;
+    uint64_t* r = regs + threadIdx.x;
+    for (const uint64_t* pc = p.program;; pc++) {
+        const uint64_t ins = *pc;
+        const unsigned op = ins & 0xff, dst = (ins >> 8) & 0xffff, a = (ins >> 24) & 0xffff, b = (ins >> 40) & 0xffff;
+        if (op == OP_END) break;
+        switch (op) {
+            case OP_LDW: r[dst * BLOCK] = p.wires[a * p.wires_stride + pos]; break;
+            case OP_LDK: r[dst * BLOCK] = p.cs[a * p.cs_stride + pos]; break;
+            case OP_LDP: r[dst * BLOCK] = p.pih[a & 3]; break;
+            case OP_LDI: r[dst * BLOCK] = p.pool[a]; break;
+            case OP_ADD: r[dst * BLOCK] = gl::add(r[a * BLOCK], r[b * BLOCK]); break;
+            case OP_SUB: r[dst * BLOCK] = gl::sub(r[a * BLOCK], r[b * BLOCK]); break;
+            case OP_MUL: r[dst * BLOCK] = gl::mul(r[a * BLOCK], r[b * BLOCK]); break;
+            case OP_EMIT: {
+                const uint64_t v = r[a * BLOCK];
+#pragma unroll
+                for (int c = 0; c < MAX_CHALLENGES; c++)
+                    if (c < (int)p.nc) h[c] = gl::add(gl::mul(h[c], p.alphas[c]), v);
+                break;
+            }
+            case OP_GATE: {
+                const uint64_t f = r[a * BLOCK];
+#pragma unroll
+                for (int c = 0; c < MAX_CHALLENGES; c++)
+                    if (c < (int)p.nc) {
+                        G[c] = gl::add(G[c], gl::mul(f, h[c]));
+                        h[c] = 0;
+                    }
+                break;
+            }
+        }
+    }
+    if (!live) return;
+    const uint64_t zinv = p.zh_inv[zi];
+#pragma unroll
+    for (int a = 0; a < MAX_CHALLENGES; a++)
+        if (a < (int)p.nc) {
+            const uint64_t total = gl::add(res[a], gl::mul(G[a], p.alpha_pows[a * (base + 1) + base]));
+            p.out[((size_t)a << p.lg_lde) + i] = gl::canon(gl::mul(total, zinv));  // prover.rs:848-853
+        }
+}
+
+// coeffs[v][i] *= s^i with s^i = lo[i & mask] * hi[i >> split]   (coset_ifft's g^-i, polynomial/mod.rs:82-87)
+__global__ void scale_powers_kernel(uint64_t* __restrict__ data, size_t n_vec, unsigned lg, const uint64_t* lo,
+                                    const uint64_t* hi, int split) {
+    const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (n_vec << lg)) return;
+    const size_t i = id & (((size_t)1 << lg) - 1);
+    const uint64_t f = gl::mul(lo[i & (((size_t)1 << split) - 1)], hi[i >> split]);
+    data[id] = gl::canon(gl::mul(data[id], f));
+}
+
+// ---- Z and partial products ------------------------------------------------------------------
+struct PermParams {
+    unsigned degree_bits, nc, nr, np, max_degree;
+    const uint64_t* wires;   // [num_wires][n] witness columns (values on H, natural order)
+    const uint64_t* sigmas;  // [nr][n]
+    const uint64_t* k_is;
+    const uint64_t* tw_row;  // w_n^i
+    uint64_t betas[MAX_CHALLENGES], gammas[MAX_CHALLENGES];
+    uint64_t* chunk;         // [nc][np + 1][n]  quotient chunk products
+    uint64_t* rowprod;       // [nc][n]          product of a row's chunks
+};
+
+constexpr int MAX_CHUNKS = 32;
+
+// Thread per (row, challenge): chunk products of numerators / denominators, one batch inversion
+// per row (Montgomery's trick; the reference inverts every denominator, prover.rs:449-455 -- the
+// quotient of the products is the same field element).
+__global__ void __launch_bounds__(128) perm_chunks_kernel(PermParams p) {
+    const size_t n = (size_t)1 << p.degree_bits;
+    const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n * p.nc) return;
+    const unsigned ch = (unsigned)(id >> p.degree_bits);
+    const size_t i = id & (n - 1);
+    const uint64_t beta = p.betas[ch], gamma = p.gammas[ch];
+    const uint64_t bx = gl::mul(beta, p.tw_row[i]);
+    uint64_t nprod[MAX_CHUNKS], dprod[MAX_CHUNKS];
+    const unsigned n_chunks = p.np + 1;
+    unsigned j = 0;
+    for (unsigned k = 0; k < n_chunks; k++) {
+        uint64_t pn = 1, pd = 1;
+        for (unsigned e = 0; e < p.max_degree && j < p.nr; e++, j++) {
+            const uint64_t wg = gl::add(p.wires[j * n + i], gamma);
+            pn = gl::mul(pn, gl::add(wg, gl::mul(bx, p.k_is[j])));
+            pd = gl::mul(pd, gl::add(wg, gl::mul(beta, p.sigmas[j * n + i])));
+        }
+        nprod[k] = pn;
+        dprod[k] = pd;
+    }
+    // batch inversion of dprod[0..n_chunks)
+    uint64_t pref[MAX_CHUNKS];
+    uint64_t acc = 1;
+    for (unsigned k = 0; k < n_chunks; k++) {
+        pref[k] = acc;
+        acc = gl::mul(acc, dprod[k]);
+    }
+    uint64_t inv = inverse(acc);
+    uint64_t row = 1;
+    for (unsigned k = n_chunks; k-- > 0;) {
+        const uint64_t dinv = gl::mul(inv, pref[k]);
+        inv = gl::mul(inv, dprod[k]);
+        nprod[k] = gl::mul(nprod[k], dinv);  // quotient chunk product
+    }
+    for (unsigned k = 0; k < n_chunks; k++) {
+        p.chunk[((size_t)ch * n_chunks + k) * n + i] = nprod[k];
+        row = gl::mul(row, nprod[k]);
+    }
+    p.rowprod[(size_t)ch * n + i] = row;
+}
+
+// Exclusive prefix PRODUCT over each of `n_vec` vectors of 2^lg elements, three phases.
+constexpr int SCAN_BLOCK = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+// Tiles never straddle vectors: block b works on tile (b % tiles_per_vec) of vector (b / tiles_per_vec),
+// tiles_per_vec = max(1, n / SCAN_TILE); elements past the vector's end count as 1.
+// phase 1: per-tile products
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_tile_products_kernel(const uint64_t* __restrict__ in, size_t n,
+                                                                        size_t tiles_per_vec,
+                                                                        uint64_t* __restrict__ tile_prod) {
+    __shared__ uint64_t sh[SCAN_BLOCK];
+    const size_t vec = blockIdx.x / tiles_per_vec, tile = blockIdx.x % tiles_per_vec;
+    const size_t off = tile * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    const size_t base = vec * n + off;
+    uint64_t acc = 1;
+#pragma unroll
+    for (int e = 0; e < SCAN_ITEMS; e++)
+        if (off + e < n) acc = gl::mul(acc, in[base + e]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = SCAN_BLOCK / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] = gl::mul(sh[threadIdx.x], sh[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_prod[blockIdx.x] = sh[0];
+}
+
+// phase 2: exclusive scan of the tile products of every vector (one block per vector, serial over
+// tiles in chunks of SCAN_BLOCK)
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_tiles_kernel(uint64_t* tile_prod, size_t tiles_per_vec) {
+    __shared__ uint64_t sh[SCAN_BLOCK];
+    __shared__ uint64_t carry;
+    uint64_t* v = tile_prod + (size_t)blockIdx.x * tiles_per_vec;
+    if (threadIdx.x == 0) carry = 1;
+    __syncthreads();
+    for (size_t t0 = 0; t0 < tiles_per_vec; t0 += SCAN_BLOCK) {
+        const size_t t = t0 + threadIdx.x;
+        const uint64_t mine = t < tiles_per_vec ? v[t] : 1;
+        sh[threadIdx.x] = mine;
+        __syncthreads();
+        // Hillis-Steele inclusive scan
+        for (int s = 1; s < SCAN_BLOCK; s <<= 1) {
+            uint64_t o = 1;
+            if ((int)threadIdx.x >= s) o = sh[threadIdx.x - s];
+            __syncthreads();
+            if ((int)threadIdx.x >= s) sh[threadIdx.x] = gl::mul(sh[threadIdx.x], o);
+            __syncthreads();
+        }
+        const uint64_t incl = sh[threadIdx.x];
+        const uint64_t c = carry;
+        const uint64_t excl = threadIdx.x == 0 ? c : gl::mul(c, sh[threadIdx.x - 1]);
+        __syncthreads();
+        if (t < tiles_per_vec) v[t] = excl;
+        if (threadIdx.x == SCAN_BLOCK - 1) carry = gl::mul(c, incl);
+        __syncthreads();
+    }
+}
+
+// phase 3: Z(w^i) = exclusive prefix product; partial products p_k(w^i) = Z * chunk_0 ... chunk_k.
+// out[(nc + nc np)][n]: Z_0 .. Z_{nc-1}, then the np partial products of challenge 0, 1, ...
+// (the order they are committed in, prover.rs:255-261).
+__global__ void __launch_bounds__(SCAN_BLOCK) perm_finish_kernel(PermParams p, size_t tiles_per_vec,
+                                                                 const uint64_t* __restrict__ tile_excl,
+                                                                 uint64_t* __restrict__ out) {
+    __shared__ uint64_t sh[SCAN_BLOCK];
+    const size_t n = (size_t)1 << p.degree_bits;
+    const size_t vec = blockIdx.x / tiles_per_vec, tile = blockIdx.x % tiles_per_vec;
+    const size_t off = tile * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    const size_t base = vec * n + off;
+    uint64_t v[SCAN_ITEMS];
+    uint64_t acc = 1;
+#pragma unroll
+    for (int e = 0; e < SCAN_ITEMS; e++) {
+        v[e] = off + e < n ? p.rowprod[base + e] : 1;
+        acc = gl::mul(acc, v[e]);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 1; s < SCAN_BLOCK; s <<= 1) {
+        uint64_t o = 1;
+        if ((int)threadIdx.x >= s) o = sh[threadIdx.x - s];
+        __syncthreads();
+        if ((int)threadIdx.x >= s) sh[threadIdx.x] = gl::mul(sh[threadIdx.x], o);
+        __syncthreads();
+    }
+    uint64_t z = tile_excl[blockIdx.x];
+    if (threadIdx.x > 0) z = gl::mul(z, sh[threadIdx.x - 1]);
+    const unsigned n_chunks = p.np + 1;
+#pragma unroll
+    for (int e = 0; e < SCAN_ITEMS; e++) {
+        if (off + e < n) {
+            const unsigned ch = (unsigned)vec;
+            const size_t i = off + e;
+            out[(size_t)ch * n + i] = gl::canon(z);
+            uint64_t a = z;
+            for (unsigned k = 0; k < p.np; k++) {
+                a = gl::mul(a, p.chunk[((size_t)ch * n_chunks + k) * n + i]);
+                out[((size_t)p.nc + (size_t)ch * p.np + k) * n + i] = gl::canon(a);
+            }
+            z = gl::mul(z, v[e]);
+        }
+    }
+}
+
+}  // namespace quotient

@@ -1,0 +1,409 @@
+"""Host mirror of the circuit data that the permutation argument and the quotient evaluation need.
+
+Reference interface (citations reference-relative):
+    Gate trait (id / degree / num_constants / num_constraints / eval_unfiltered)  plonky2/src/gates/gate.rs
+    NoopGate, ConstantGate, PublicInputGate, ArithmeticGate                       plonky2/src/gates/{noop,constant,public_input,arithmetic_base}.rs
+    selector_polynomials -> SelectorsInfo                                         plonky2/src/gates/selectors.rs:99-166
+    get_unique_coset_shifts (k_is)                                                field/src/cosets.rs:9-24
+    CommonCircuitData fields                                                      plonky2/src/plonk/circuit_data.rs:412-470
+    wires_permutation_partial_products_and_zs / compute_quotient_polys            plonky2/src/plonk/prover.rs:402-480,640-866
+
+The device never sees gate objects: `CommonCircuitData.constraint_program()` runs every gate's
+`eval_unfiltered` over a recording value type and compiles the result, with the gate filters
+(gate.rs:326-333), into the straight-line program of include/qp_plonky2_b200.h.  A Rust shim does
+the same with a recording `Field` type over `Gate::eval_unfiltered_base_one`.
+"""
+import ctypes as C
+
+import numpy as np
+
+P = 0xFFFFFFFF00000001
+MULTIPLICATIVE_GROUP_GENERATOR = 14293326489335486720  # field/src/goldilocks_field.rs:84
+UNUSED_SELECTOR = 0xFFFFFFFF  # core/src/selectors.rs
+
+OP_END, OP_LDW, OP_LDK, OP_LDP, OP_LDI, OP_ADD, OP_SUB, OP_MUL, OP_EMIT, OP_GATE = range(10)
+
+
+# ---- recording value type ------------------------------------------------------------------------
+class Val:
+    """A node of the constraint expression DAG."""
+
+    __slots__ = ("prog", "idx")
+
+    def __init__(self, prog, idx):
+        self.prog, self.idx = prog, idx
+
+    def _bin(self, op, other):
+        if not isinstance(other, Val):
+            other = self.prog.imm(other)
+        return self.prog._node(op, self.idx, other.idx)
+
+    def __add__(self, o):
+        return self._bin(OP_ADD, o)
+
+    def __sub__(self, o):
+        return self._bin(OP_SUB, o)
+
+    def __mul__(self, o):
+        return self._bin(OP_MUL, o)
+
+    def __rsub__(self, o):
+        return self.prog.imm(o) - self
+
+    __radd__ = __add__
+    __rmul__ = __mul__
+
+
+class ConstraintProgram:
+    """Builds the program: leaves are loads, inner nodes field operations; `emit_gate` appends a
+    gate's constraints (in REVERSE order, as the kernel's Horner step wants) and its filter."""
+
+    def __init__(self):
+        self.nodes = []    # (op, a, b)
+        self.memo = {}
+        self.pool = []
+        self.pool_index = {}
+        self.actions = []  # (OP_EMIT | OP_GATE, node)
+
+    def _node(self, op, a=0, b=0):
+        key = (op, a, b)
+        if op in (OP_ADD, OP_MUL) and a > b:
+            key = (op, b, a)
+        i = self.memo.get(key)
+        if i is None:
+            i = len(self.nodes)
+            self.nodes.append(key)
+            self.memo[key] = i
+        return Val(self, i)
+
+    def wire(self, i):
+        return self._node(OP_LDW, i)
+
+    def constant(self, i):
+        """Polynomial i of the constants_sigmas oracle."""
+        return self._node(OP_LDK, i)
+
+    def public_input_hash(self, i):
+        return self._node(OP_LDP, i)
+
+    def imm(self, v):
+        v = int(v) % P
+        k = self.pool_index.get(v)
+        if k is None:
+            k = len(self.pool)
+            self.pool.append(v)
+            self.pool_index[v] = k
+        return self._node(OP_LDI, k)
+
+    def emit_gate(self, constraints, filt):
+        for c in reversed(constraints):
+            self.actions.append((OP_EMIT, c.idx))
+        self.actions.append((OP_GATE, filt.idx))
+
+    def compile(self):
+        """-> (code uint64[], pool uint64[], n_regs).  Nodes are scheduled lazily in action order
+        and registers are reused after a node's last use."""
+        nodes = self.nodes
+        # schedule: post-order from each action's root
+        order, seen = [], set()
+        sched = []  # ("node", i) | ("act", op, i)
+        for op, root in self.actions:
+            stack = [(root, False)]
+            while stack:
+                i, done = stack.pop()
+                if i in seen:
+                    continue
+                nop, a, b = nodes[i]
+                if done or nop in (OP_LDW, OP_LDK, OP_LDP, OP_LDI):
+                    seen.add(i)
+                    order.append(i)
+                    sched.append(("node", i))
+                    continue
+                stack.append((i, True))
+                for ch in (b, a):
+                    if ch not in seen:
+                        stack.append((ch, False))
+            sched.append(("act", op, root))
+        last_use = {}
+        for t, s in enumerate(sched):
+            if s[0] == "node":
+                nop, a, b = nodes[s[1]]
+                if nop in (OP_ADD, OP_SUB, OP_MUL):
+                    last_use[a] = t
+                    last_use[b] = t
+            else:
+                last_use[s[2]] = t
+        reg_of, free, n_regs, code = {}, [], 0, []
+        for t, s in enumerate(sched):
+            if s[0] == "node":
+                i = s[1]
+                nop, a, b = nodes[i]
+                ra = rb = 0
+                if nop in (OP_ADD, OP_SUB, OP_MUL):
+                    ra, rb = reg_of[a], reg_of[b]
+                    for ch in {a, b}:
+                        if last_use.get(ch) == t:
+                            free.append(reg_of[ch])
+                else:
+                    ra = a
+                if free:
+                    r = free.pop()
+                else:
+                    r = n_regs
+                    n_regs += 1
+                reg_of[i] = r
+                code.append(nop | (r << 8) | (ra << 24) | (rb << 40))
+                if i not in last_use:  # dead value
+                    free.append(r)
+            else:
+                _, op, root = s
+                code.append(op | (reg_of[root] << 24))
+                if last_use.get(root) == t:
+                    free.append(reg_of[root])
+        assert n_regs < (1 << 16) and len(self.pool) < (1 << 16)
+        return (np.array(code, dtype=np.uint64), np.array(self.pool or [0], dtype=np.uint64), max(n_regs, 1))
+
+
+# ---- gates ------------------------------------------------------------------------------------------
+class Gate:
+    def id(self):
+        raise NotImplementedError
+
+    degree = 0
+    num_constants = 0
+    num_constraints = 0
+
+    def eval_unfiltered(self, consts, wires, pih):
+        """consts(i) / wires(i) / pih(i) -> values; returns the list of constraints."""
+        return []
+
+
+class NoopGate(Gate):  # plonky2/src/gates/noop.rs
+    def id(self):
+        return "NoopGate"
+
+
+class ConstantGate(Gate):  # plonky2/src/gates/constant.rs
+    degree = 1
+
+    def __init__(self, num_consts):
+        self.num_consts = self.num_constants = self.num_constraints = num_consts
+
+    def id(self):
+        return "ConstantGate { num_consts: %d }" % self.num_consts
+
+    def eval_unfiltered(self, consts, wires, pih):
+        return [consts(i) - wires(i) for i in range(self.num_consts)]  # constant.rs:121-129
+
+
+class PublicInputGate(Gate):  # plonky2/src/gates/public_input.rs
+    degree = 1
+    num_constraints = 4
+
+    def id(self):
+        return "PublicInputGate"
+
+    def eval_unfiltered(self, consts, wires, pih):
+        return [wires(i) - pih(i) for i in range(4)]  # public_input.rs:103-113
+
+
+class ArithmeticGate(Gate):  # plonky2/src/gates/arithmetic_base.rs
+    degree = 3
+    num_constants = 2
+
+    def __init__(self, num_ops):
+        self.num_ops = self.num_constraints = num_ops
+
+    @staticmethod
+    def new_from_config(num_routed_wires):
+        return ArithmeticGate(num_routed_wires // 4)  # arithmetic_base.rs:44-47
+
+    def id(self):
+        return "ArithmeticGate { num_ops: %d }" % self.num_ops
+
+    def eval_unfiltered(self, consts, wires, pih):
+        c0, c1 = consts(0), consts(1)
+        out = []
+        for i in range(self.num_ops):  # arithmetic_base.rs:168-185
+            m0, m1, addend, output = wires(4 * i), wires(4 * i + 1), wires(4 * i + 2), wires(4 * i + 3)
+            out.append(output - (m0 * m1 * c0 + addend * c1))
+        return out
+
+
+def sort_gates(gates):
+    """circuit_builder.rs:1177-1179: by (degree, id)."""
+    return sorted(gates, key=lambda g: (g.degree, g.id()))
+
+
+def selectors_info(gates, max_degree):
+    """selector_polynomials' grouping (selectors.rs:99-166) for SORTED gates:
+    -> (selector_indices[gate], groups[(start, end)])."""
+    num_gates = len(gates)
+    max_gate_degree = gates[-1].degree
+    if max_gate_degree + num_gates - 1 <= max_degree:
+        return [0] * num_gates, [(0, num_gates)]
+    if max_gate_degree >= max_degree:
+        raise ValueError("%s has too high degree. Consider increasing `quotient_degree_factor`." % gates[-1].id())
+    groups, start = [], 0
+    while start < num_gates:
+        size = 0
+        while start + size < num_gates and size + gates[start + size].degree < max_degree:
+            size += 1
+        groups.append((start, start + size))
+        start += size
+    idx = []
+    for i in range(num_gates):
+        idx.append(next(k for k, (a, b) in enumerate(groups) if a <= i < b))
+    return idx, groups
+
+
+def get_unique_coset_shifts(num_shifts):
+    """field/src/cosets.rs:9-24: g^0 .. g^(num_shifts-1)."""
+    out, v = [], 1
+    for _ in range(num_shifts):
+        out.append(v)
+        v = v * MULTIPLICATIVE_GROUP_GENERATOR % P
+    return np.array(out, dtype=np.uint64)
+
+
+def log2_ceil(x):
+    return max(0, (int(x) - 1).bit_length())
+
+
+class CommonCircuitData:
+    """The fields of CommonCircuitData (circuit_data.rs:412-470) that the permutation argument and
+    the quotient use; no lookups.  `gates` in any order (sorted here like the builder does)."""
+
+    def __init__(self, degree_bits, gates, num_wires=143, num_routed_wires=80, num_challenges=2,
+                 quotient_degree_factor=8, rate_bits=3, cap_height=4):
+        self.degree_bits = degree_bits
+        self.num_wires, self.num_routed_wires = num_wires, num_routed_wires
+        self.num_challenges = num_challenges
+        self.quotient_degree_factor = quotient_degree_factor
+        self.rate_bits, self.cap_height = rate_bits, cap_height
+        self.gates = sort_gates(gates)
+        # circuit_builder.rs:1180-1181: selector_polynomials(gates, instances, quotient_degree_factor + 1)
+        self.selector_indices, self.groups = selectors_info(self.gates, quotient_degree_factor + 1)
+        self.num_selectors = len(self.groups)
+        self.num_lookup_selectors = 0
+        self.num_gate_constants = max(g.num_constants for g in self.gates)
+        self.num_constants = self.num_selectors + self.num_gate_constants  # circuit_builder.rs:1196-1197
+        self.num_gate_constraints = max(g.num_constraints for g in self.gates)
+        self.k_is = get_unique_coset_shifts(num_routed_wires)
+        # util/partial_products.rs:41-48
+        self.num_partial_products = -(-num_routed_wires // quotient_degree_factor) - 1
+        self.quotient_degree_bits = log2_ceil(quotient_degree_factor)
+
+    def gate_index(self, gate_id):
+        return next(i for i, g in enumerate(self.gates) if g.id() == gate_id)
+
+    def constraint_program(self):
+        """evaluate_gate_constraints_base_batch (vanishing_poly.rs:700-726) as a program."""
+        prog = ConstraintProgram()
+        prefix = self.num_selectors + self.num_lookup_selectors  # gate.rs:179 remove_prefix
+        for i, g in enumerate(self.gates):
+            sel = self.selector_indices[i]
+            start, end = self.groups[sel]
+            s = prog.constant(sel)
+            # compute_filter, gate.rs:326-333
+            factors = [j - s for j in range(start, end) if j != i]
+            if self.num_selectors > 1:
+                factors.append(UNUSED_SELECTOR - s)
+            filt = prog.imm(1)
+            for f in factors:
+                filt = filt * f
+            cons = g.eval_unfiltered(lambda k: prog.constant(prefix + k), prog.wire, prog.public_input_hash)
+            assert len(cons) == g.num_constraints
+            if cons:
+                prog.emit_gate(cons, filt)
+        return prog.compile()
+
+
+class _Desc(C.Structure):
+    _fields_ = [
+        ("degree_bits", C.c_uint32), ("quotient_degree_bits", C.c_uint32), ("num_challenges", C.c_uint32),
+        ("num_routed_wires", C.c_uint32), ("num_wires", C.c_uint32), ("num_constants", C.c_uint32),
+        ("num_partial_products", C.c_uint32), ("max_degree", C.c_uint32),
+        ("k_is", C.c_void_p), ("sigmas", C.c_void_p), ("sigmas_space", C.c_int),
+        ("program", C.c_void_p), ("program_len", C.c_size_t), ("pool", C.c_void_p), ("pool_len", C.c_size_t),
+        ("program_regs", C.c_uint32),
+    ]
+
+
+class Circuit:
+    """Device-resident circuit data: k_is, sigmas (prover_data.sigmas as columns), the compiled
+    gate program.  One per circuit, like ProverOnlyCircuitData."""
+
+    def __init__(self, ctx, common, sigmas=None):
+        from . import _buf, lib  # late: this module is imported by the package
+        self.ctx, self.common = ctx, common
+        code, pool, n_regs = common.constraint_program()
+        self.program = (code, pool, n_regs)
+        k_is = np.ascontiguousarray(common.k_is, dtype=np.uint64)
+        d = _Desc()
+        d.degree_bits, d.quotient_degree_bits = common.degree_bits, common.quotient_degree_bits
+        d.num_challenges = common.num_challenges
+        d.num_routed_wires, d.num_wires = common.num_routed_wires, common.num_wires
+        d.num_constants = common.num_constants
+        d.num_partial_products, d.max_degree = common.num_partial_products, common.quotient_degree_factor
+        d.k_is = k_is.ctypes.data
+        keep = None
+        if sigmas is not None:
+            ptr, space, keep, shape = _buf(sigmas)
+            assert tuple(shape) == (common.num_routed_wires, 1 << common.degree_bits)
+            d.sigmas, d.sigmas_space = ptr.value, space
+        d.program, d.program_len = code.ctypes.data, code.size
+        d.pool, d.pool_len = pool.ctypes.data, pool.size
+        d.program_regs = n_regs
+        self._h = C.c_void_p()
+        ctx.check(lib().qp_circuit_create(ctx._h, C.byref(d), C.byref(self._h)))
+        del keep
+
+    def partial_products_and_zs(self, wires, betas, gammas, out_device=None):
+        """all_wires_permutation_partial_products + Z-first ordering (prover.rs:255-261,402-480):
+        -> value columns [(nc + nc*np)][n] for the second from_values of prove()."""
+        from . import QP_DEVICE, QP_HOST, _buf, _np_ptr, lib
+        c = self.common
+        ptr, space, keep, shape = _buf(wires)
+        assert shape[0] >= c.num_routed_wires and shape[1] == 1 << c.degree_bits
+        b = np.ascontiguousarray(betas, dtype=np.uint64)
+        g = np.ascontiguousarray(gammas, dtype=np.uint64)
+        rows = c.num_challenges * (1 + c.num_partial_products)
+        if out_device is not None:
+            self.ctx.check(lib().qp_circuit_partial_products_and_zs(
+                self._h, ptr, space, _np_ptr(b), _np_ptr(g), C.c_void_p(out_device.data_ptr()), QP_DEVICE))
+            return out_device
+        out = np.zeros((rows, 1 << c.degree_bits), dtype=np.uint64)
+        self.ctx.check(lib().qp_circuit_partial_products_and_zs(
+            self._h, ptr, space, _np_ptr(b), _np_ptr(g), _np_ptr(out), QP_HOST))
+        return out
+
+    def compute_quotient_polys(self, constants_sigmas, wires, zs_partial_products, betas, gammas, alphas,
+                               public_inputs_hash, out_device=None):
+        """compute_quotient_polys (prover.rs:640-866) -> coefficients [nc][n << quotient_degree_bits]."""
+        from . import QP_DEVICE, QP_HOST, _np_ptr, lib
+        c = self.common
+        arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in (betas, gammas, alphas, public_inputs_hash)]
+        n_lde = 1 << (c.degree_bits + c.quotient_degree_bits)
+        if out_device is not None:
+            self.ctx.check(lib().qp_circuit_compute_quotient_polys(
+                self._h, constants_sigmas._h, wires._h, zs_partial_products._h, *[_np_ptr(a) for a in arrs],
+                C.c_void_p(out_device.data_ptr()), QP_DEVICE))
+            return out_device
+        out = np.zeros((c.num_challenges, n_lde), dtype=np.uint64)
+        self.ctx.check(lib().qp_circuit_compute_quotient_polys(
+            self._h, constants_sigmas._h, wires._h, zs_partial_products._h, *[_np_ptr(a) for a in arrs],
+            _np_ptr(out), QP_HOST))
+        return out
+
+    def free(self):
+        from . import lib
+        if self._h:
+            lib().qp_circuit_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

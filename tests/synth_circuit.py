@@ -1,0 +1,156 @@
+"""Test infrastructure: a synthetic Plonk circuit with a satisfying witness.
+
+The reference builds circuits with CircuitBuilder (out of scope); the
+permutation argument and the quotient only consume its OUTPUT -- gate list, selector and constant
+polynomials, sigma polynomials, and a witness.  This module fabricates those directly:
+
+  * rows are assigned one of {NoopGate, ConstantGate(2), PublicInputGate, ArithmeticGate(routed/4)}
+    (gate semantics: plonky2/src/gates/*.rs) with random gate constants;
+  * the witness satisfies every gate; inputs of arithmetic operations are, with probability 1/2,
+    COPIES of unconstrained cells elsewhere in the trace, and every copy class is wired as one cycle
+    of the permutation sigma (what CircuitBuilder::sigma_vecs derives from `connect` calls,
+    circuit_builder.rs:1199-1205), so Z and the partial products are non-trivial.
+"""
+import numpy as np
+
+import oracle
+from qp_plonky2_b200 import plonk
+
+P = oracle.P
+
+
+def _mulmod(a, b):
+    return ((a.astype(object) * b.astype(object)) % P).astype(np.uint64)
+
+
+def _addmod(a, b):
+    return ((a.astype(object) + b.astype(object)) % P).astype(np.uint64)
+
+
+class SynthCircuit:
+    def __init__(self, degree_bits, seed=1, num_wires=143, num_routed_wires=80, num_challenges=2,
+                 quotient_degree_factor=8, rate_bits=3, cap_height=4):
+        rng = np.random.Generator(np.random.PCG64(seed))
+        n = 1 << degree_bits
+        nr = num_routed_wires
+        self.n = n
+        gates = [plonk.NoopGate(), plonk.ConstantGate(2), plonk.PublicInputGate(),
+                 plonk.ArithmeticGate.new_from_config(nr)]
+        self.common = c = plonk.CommonCircuitData(degree_bits, gates, num_wires, nr, num_challenges,
+                                                  quotient_degree_factor, rate_bits, cap_height)
+        kinds = {"NoopGate": oracle.GATE_NOOP, "ConstantGate": oracle.GATE_CONSTANT,
+                 "PublicInputGate": oracle.GATE_PUBLIC_INPUT, "ArithmeticGate": oracle.GATE_ARITHMETIC}
+        og = []
+        for i, g in enumerate(c.gates):
+            name = g.id().split(" ")[0]
+            param = getattr(g, "num_consts", getattr(g, "num_ops", 0))
+            og.append((kinds[name], param, c.selector_indices[i], c.groups[c.selector_indices[i]]))
+        self.oracle_circuit = oracle.Circuit(degree_bits, c.quotient_degree_bits, num_challenges, nr, num_wires,
+                                             c.num_constants, c.num_partial_products, quotient_degree_factor,
+                                             c.num_selectors, og, c.k_is)
+        idx = {g.id().split(" ")[0]: i for i, g in enumerate(c.gates)}
+        # gate per row: mostly arithmetic, a few of the others; row 0 is the public-input gate
+        row_gate = rng.choice([idx["NoopGate"], idx["ConstantGate"], idx["ArithmeticGate"]], size=n, p=[0.2, 0.1, 0.7])
+        row_gate[0] = idx["PublicInputGate"]
+        self.row_gate = row_gate
+        # constants: selector polynomials (selectors.rs:141-159), then the gate constants
+        consts = np.zeros((c.num_constants, n), dtype=np.uint64)
+        for s, (a, b) in enumerate(c.groups):
+            in_group = (row_gate >= a) & (row_gate < b)
+            consts[s] = np.where(in_group, row_gate, plonk.UNUSED_SELECTOR if c.num_selectors > 1 else row_gate)
+        gate_consts = oracle.rand_felts((c.num_gate_constants, n), seed + 1)
+        uses = (row_gate == idx["ConstantGate"]) | (row_gate == idx["ArithmeticGate"])
+        consts[c.num_selectors:] = np.where(uses[None, :], gate_consts, 0)
+        self.constants = consts
+        # witness
+        wires = oracle.rand_felts((num_wires, n), seed + 2)
+        self.public_inputs_hash = oracle.rand_felts((4,), seed + 3)
+        pi_rows = row_gate == idx["PublicInputGate"]
+        for k in range(4):
+            wires[k, pi_rows] = self.public_inputs_hash[k]
+        const_rows = row_gate == idx["ConstantGate"]
+        for k in range(2):
+            wires[k, const_rows] = consts[c.num_selectors + k, const_rows]
+        # copy constraints: free cells = routed wires of Noop rows (unconstrained)
+        noop_rows = np.nonzero(row_gate == idx["NoopGate"])[0]
+        arith_rows = np.nonzero(row_gate == idx["ArithmeticGate"])[0]
+        sigma_row = np.tile(np.arange(n, dtype=np.int64), (nr, 1))
+        sigma_col = np.tile(np.arange(nr, dtype=np.int64)[:, None], (1, n))
+        num_ops = nr // 4
+        if len(noop_rows) and len(arith_rows):
+            in_cols = np.array([4 * o + k for o in range(num_ops) for k in range(3)])
+            tc, tr = np.meshgrid(in_cols, arith_rows, indexing="ij")
+            tc, tr = tc.ravel(), tr.ravel()
+            pick = rng.random(tc.size) < 0.5
+            tc, tr = tc[pick], tr[pick]
+            sr = rng.choice(noop_rows, size=tc.size)
+            sc = rng.integers(0, nr, size=tc.size)
+            wires[tc, tr] = wires[sc, sr]
+            # classes keyed by source cell; one cycle per class: source -> t1 -> t2 -> ... -> source
+            key = sc.astype(np.int64) * n + sr
+            order = np.argsort(key, kind="stable")
+            key, tc, tr, sc, sr = key[order], tc[order], tr[order], sc[order], sr[order]
+            first = np.r_[True, key[1:] != key[:-1]]
+            last = np.r_[key[1:] != key[:-1], True]
+            # source -> first target of its class
+            sigma_col[sc[first], sr[first]] = tc[first]
+            sigma_row[sc[first], sr[first]] = tr[first]
+            # target -> next target, last target -> source
+            nxt_c = np.r_[tc[1:], 0]
+            nxt_r = np.r_[tr[1:], 0]
+            nxt_c[last], nxt_r[last] = sc[last], sr[last]
+            sigma_col[tc, tr] = nxt_c
+            sigma_row[tc, tr] = nxt_r
+        # arithmetic outputs (arithmetic_base.rs:181)
+        if len(arith_rows):
+            c0 = consts[c.num_selectors][arith_rows]
+            c1 = consts[c.num_selectors + 1][arith_rows]
+            for o in range(num_ops):
+                m0, m1, ad = wires[4 * o][arith_rows], wires[4 * o + 1][arith_rows], wires[4 * o + 2][arith_rows]
+                wires[4 * o + 3][arith_rows] = _addmod(_mulmod(_mulmod(m0, m1), c0), _mulmod(ad, c1))
+        self.wires = wires
+        # sigma polynomials' values: k_is[col] * w^row  (circuit_builder.rs sigma_vecs)
+        w = oracle.lib().orc_gl_primitive_root(degree_bits)
+        sub = np.ones(n, dtype=object)
+        for i in range(1, n):
+            sub[i] = sub[i - 1] * w % P
+        k_obj = np.array([int(k) for k in c.k_is], dtype=object)
+        self.sigmas = ((k_obj[sigma_col] * sub[sigma_row]) % P).astype(np.uint64)
+        self.subgroup = sub.astype(np.uint64)
+
+    def constants_sigmas(self):
+        return np.ascontiguousarray(np.concatenate([self.constants, self.sigmas], axis=0))
+
+
+def eval_poly(coeffs, x):
+    """Horner over F_p (PolynomialCoeffs::eval)."""
+    out = oracle.lib().orc_eval_poly_ext  # F_p^2 evaluator with point (x, 0)
+    res = np.zeros(2, dtype=np.uint64)
+    pt = np.array([x, 0], dtype=np.uint64)
+    c = np.ascontiguousarray(coeffs, dtype=np.uint64)
+    out(oracle._ptr(c), c.size, oracle._ptr(pt), oracle._ptr(res))
+    return int(res[0])
+
+
+def verifier_identity_holds(sc, cs_polys, wires_polys, zs_polys, quotient_coeffs, betas, gammas, alphas, x0):
+    """The verifier's check (verifier/src/plonk/verifier.rs:86-100) at a base-field point x0:
+    vanishing(x0) == Z_H(x0) * quotient(x0), with every opening computed from the coefficient
+    vectors.  Size-independent property: it holds iff the committed quotient is the right one."""
+    c = sc.common
+    n = 1 << c.degree_bits
+    g = oracle.lib().orc_gl_primitive_root(c.degree_bits)
+    x0 = int(x0)
+    cs = [eval_poly(p, x0) for p in cs_polys]
+    wv = [eval_poly(p, x0) for p in wires_polys]
+    zv = [eval_poly(p, x0) for p in zs_polys]
+    zn = [eval_poly(p, x0 * g % P) for p in zs_polys[: c.num_challenges]]
+    nc = c.num_challenges
+    van = sc.oracle_circuit.eval_vanishing_poly_base(
+        x0, cs[: c.num_constants], wv, zv[:nc], zn, zv[nc:], cs[c.num_constants:], betas, gammas, alphas,
+        sc.public_inputs_hash)
+    z_h = (pow(x0, n, P) - 1) % P
+    ok = True
+    for a in range(nc):
+        q = eval_poly(quotient_coeffs[a], x0)
+        ok &= int(van[a]) == z_h * q % P
+    return ok
