@@ -1,0 +1,97 @@
+"""TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
+
+CPU restatement of prove_with_partition_witness from the full witness on
+(plonky2/src/plonk/prover.rs:176-398) out of the oracle's pieces, and of
+write_proof_with_public_inputs (plonky2/src/util/serialization/mod.rs:2040-2079).  Same scope as
+the device prover: no lookups, no blinding, smallest PoW witness.  Parity status: "unpinned" by
+golden data (the reference cannot be built here); pinned structurally by the verifier identity
+(tests/test_plonk_oracle.py) and, for the FRI part, by tests/test_oracle.py.
+"""
+import numpy as np
+
+import oracle
+from oracle import P
+
+W = 7
+
+
+def ext_mul(a, b):
+    return ((a[0] * b[0] + W * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+
+
+def circuit_digest(cap, degree_bits):
+    ds = oracle.hash_no_pad(np.array([1, 0, 0, 0, 0, 0, 0, 1], dtype=np.uint64))
+    return oracle.hash_no_pad(np.concatenate([np.asarray(cap, dtype=np.uint64).reshape(-1), ds,
+                                              np.array([degree_bits], dtype=np.uint64)]))
+
+
+def prove(oc, cs_batch, num_constants, wires, sigmas, public_inputs, pih_wires_check=None, *, degree_bits,
+          num_wires, num_routed_wires, num_challenges, quotient_degree_factor, num_partial_products,
+          rate_bits=3, cap_height=4, proof_of_work_bits=16, arity_bits=4, final_poly_bits=5, num_query_rounds=28):
+    """oc: oracle.Circuit; cs_batch: oracle.PolynomialBatch of constants + sigmas."""
+    n = 1 << degree_bits
+    nc = num_challenges
+    public_inputs = [int(x) % P for x in public_inputs]
+    pih = oracle.hash_no_pad(np.array(public_inputs, dtype=np.uint64))
+    wb = oracle.PolynomialBatch.from_values(wires, rate_bits, cap_height)
+    ch = oracle.Challenger()
+    arities = oracle.fri_reduction_arity_bits(degree_bits, rate_bits, cap_height, arity_bits, final_poly_bits)
+    # FriParams::observe, core/src/fri.rs:289-321
+    ch.observe([rate_bits, cap_height, proof_of_work_bits, 1, arity_bits, final_poly_bits, num_query_rounds, 0,
+                degree_bits] + list(arities))
+    ch.observe(circuit_digest(cs_batch.cap, degree_bits))
+    ch.observe(pih)
+    ch.observe(wb.cap.reshape(-1))
+    betas = [ch.get_challenge() for _ in range(nc)]
+    gammas = [ch.get_challenge() for _ in range(nc)]
+    zs = oc.partial_products_and_zs(wires, sigmas, betas, gammas)
+    zb = oracle.PolynomialBatch.from_values(zs, rate_bits, cap_height)
+    ch.observe(zb.cap.reshape(-1))
+    alphas = [ch.get_challenge() for _ in range(nc)]
+    q = oc.compute_quotient_polys(rate_bits, cs_batch.leaves, wb.leaves, zb.leaves, betas, gammas, alphas, pih)
+    qd = quotient_degree_factor * n
+    assert not q[:, qd:].any(), "Quotient has failed, the vanishing polynomial is not divisible by Z_H"
+    chunks = np.ascontiguousarray(q[:, :qd]).reshape(nc * quotient_degree_factor, n)
+    qb = oracle.PolynomialBatch.from_coeffs(chunks, rate_bits, cap_height)
+    ch.observe(qb.cap.reshape(-1))
+    zeta = ch.get_extension_challenge()
+    g = oracle.lib().orc_gl_primitive_root(degree_bits)
+    zeta_next = (g * zeta[0] % P, g * zeta[1] % P)
+
+    def ev(batch, point):
+        return np.stack([oracle.eval_poly_ext(p, point) for p in batch.polynomials])
+
+    cs_eval, wires_eval, zs_eval = ev(cs_batch, zeta), ev(wb, zeta), ev(zb, zeta)
+    zs_next_eval, quotient_eval = ev(zb, zeta_next), ev(qb, zeta)
+    n_pre = num_constants + num_routed_wires
+    constants, sig = cs_eval[:num_constants], cs_eval[num_constants:n_pre]
+    plonk_zs, plonk_zs_next, pps = zs_eval[:nc], zs_next_eval[:nc], zs_eval[nc:]
+    for v in (constants, sig, wires_eval, plonk_zs, pps, quotient_eval, plonk_zs_next):
+        ch.observe(np.asarray(v).reshape(-1))
+    alpha = ch.get_extension_challenge()
+    batches = []
+    zeta_polys = list(cs_batch.polynomials[:n_pre]) + list(wb.polynomials) + list(zb.polynomials) + list(qb.polynomials)
+    for point, polys in ((zeta, zeta_polys), (zeta_next, list(zb.polynomials[:nc]))):
+        terms, w = [], (1, 0)
+        for p in polys:
+            terms.append((p, w))
+            w = ext_mul(w, alpha)
+        batches.append(dict(point=point, shift=w, terms=terms))
+    final = oracle.reduce_openings(batches, degree_bits)
+    N = n << rate_bits
+    co = np.zeros((N, 2), dtype=np.uint64)
+    co[:n] = final
+    gs = oracle.lib().orc_gl_coset_shift()
+    va = np.stack([oracle.coset_fft(co[:, 0], gs), oracle.coset_fft(co[:, 1], gs)], axis=1)
+    fri_bytes = oracle.fri_proof_bytes([cs_batch, wb, zb, qb], co, va, ch, rate_bits, cap_height, arities,
+                                       proof_of_work_bits, num_query_rounds)
+    out = bytearray()
+    for cap in (wb.cap, zb.cap, qb.cap):
+        out += np.ascontiguousarray(cap).astype("<u8").tobytes()
+    for v in (constants, sig, wires_eval, plonk_zs, plonk_zs_next, pps, quotient_eval):
+        out += np.ascontiguousarray(v).astype("<u8").tobytes()
+    out += fri_bytes
+    out += np.array([len(public_inputs)] + public_inputs, dtype="<u8").tobytes()
+    return bytes(out), dict(zeta=zeta, alphas=alphas, betas=betas, gammas=gammas, pih=pih, openings=dict(
+        constants=constants, plonk_sigmas=sig, wires=wires_eval, plonk_zs=plonk_zs, plonk_zs_next=plonk_zs_next,
+        partial_products=pps, quotient_polys=quotient_eval))

@@ -64,7 +64,9 @@ class SynthCircuit:
         self.constants = consts
         # witness
         wires = oracle.rand_felts((num_wires, n), seed + 2)
-        self.public_inputs_hash = oracle.rand_felts((4,), seed + 3)
+        # public inputs and their hash (prover.rs:185-186); the PublicInputGate row carries the hash
+        self.public_inputs = [int(x) for x in oracle.rand_felts((3,), seed + 3)]
+        self.public_inputs_hash = oracle.hash_no_pad(np.array(self.public_inputs, dtype=np.uint64))
         pi_rows = row_gate == idx["PublicInputGate"]
         for k in range(4):
             wires[k, pi_rows] = self.public_inputs_hash[k]
@@ -154,3 +156,108 @@ def verifier_identity_holds(sc, cs_polys, wires_polys, zs_polys, quotient_coeffs
         q = eval_poly(quotient_coeffs[a], x0)
         ok &= int(van[a]) == z_h * q % P
     return ok
+
+
+class Ext:
+    """F_p^2 = F_p[X]/(X^2 - 7) element for the restated verifier."""
+
+    __slots__ = ("a", "b")
+
+    def __init__(self, a, b=0):
+        self.a, self.b = int(a) % P, int(b) % P
+
+    @staticmethod
+    def of(x):
+        return x if isinstance(x, Ext) else Ext(x)
+
+    def __add__(self, o):
+        o = Ext.of(o)
+        return Ext(self.a + o.a, self.b + o.b)
+
+    def __sub__(self, o):
+        o = Ext.of(o)
+        return Ext(self.a - o.a, self.b - o.b)
+
+    def __rsub__(self, o):
+        return Ext.of(o) - self
+
+    def __mul__(self, o):
+        o = Ext.of(o)
+        return Ext(self.a * o.a + 7 * self.b * o.b, self.a * o.b + self.b * o.a)
+
+    __radd__ = __add__
+    __rmul__ = __mul__
+
+    def __eq__(self, o):
+        o = Ext.of(o)
+        return self.a == o.a and self.b == o.b
+
+    def pow(self, e):
+        r, x = Ext(1), self
+        while e:
+            if e & 1:
+                r = r * x
+            x = x * x
+            e >>= 1
+        return r
+
+    def inv(self):
+        # (a + bX)^-1 = (a - bX) / (a^2 - 7 b^2)
+        d = pow((self.a * self.a - 7 * self.b * self.b) % P, P - 2, P)
+        return Ext(self.a * d, -self.b * d)
+
+
+def verifier_plonk_identity(common, openings, zeta, betas, gammas, alphas, pih):
+    """verify_with_challenges' algebraic check (verifier/src/plonk/verifier.rs:60-100): evaluate the
+    vanishing polynomial at zeta from the OPENINGS (eval_vanishing_poly, vanishing_poly.rs:38-150)
+    and compare with Z_H(zeta) * sum_i zeta^(n i) quotient_chunk_i(zeta), per challenge."""
+    c = common
+    n = 1 << c.degree_bits
+    z = Ext(*zeta)
+    E = lambda arr: [Ext(int(v[0]), int(v[1])) for v in arr]
+    consts, sig, wires = E(openings["constants"]), E(openings["plonk_sigmas"]), E(openings["wires"])
+    zs, zs_next, pps = E(openings["plonk_zs"]), E(openings["plonk_zs_next"]), E(openings["partial_products"])
+    qs = E(openings["quotient_polys"])
+    nc, nr, npp, md = c.num_challenges, c.num_routed_wires, c.num_partial_products, c.quotient_degree_factor
+    z_h = z.pow(n) - 1
+    l_0 = z_h * ((z - 1) * n).inv()   # eval_l_0, plonk_common.rs
+    terms = []
+    for i in range(nc):
+        terms.append(l_0 * (zs[i] - 1))
+    for i in range(nc):
+        num = [wires[j] + z * (int(c.k_is[j]) * int(betas[i]) % P) + int(gammas[i]) for j in range(nr)]
+        den = [wires[j] + sig[j] * int(betas[i]) + int(gammas[i]) for j in range(nr)]
+        accs = [zs[i]] + pps[i * npp:(i + 1) * npp] + [zs_next[i]]
+        for w in range(npp + 1):
+            pn = pd = Ext(1)
+            for j in range(w * md, min((w + 1) * md, nr)):
+                pn, pd = pn * num[j], pd * den[j]
+            terms.append(accs[w] * pn - accs[w + 1] * pd)
+    gate_terms = [Ext(0)] * c.num_gate_constraints
+    prefix = c.num_selectors
+    for gi, g in enumerate(c.gates):
+        sel = c.selector_indices[gi]
+        a, b = c.groups[sel]
+        s = consts[sel]
+        f = Ext(1)
+        for j in range(a, b):
+            if j != gi:
+                f = f * (Ext(j) - s)
+        if c.num_selectors > 1:
+            f = f * (Ext(plonk.UNUSED_SELECTOR) - s)
+        cons = g.eval_unfiltered(lambda k: consts[prefix + k], lambda k: wires[k], lambda k: Ext(int(pih[k])))
+        for k, cv in enumerate(cons):
+            gate_terms[k] = gate_terms[k] + f * cv
+    terms += gate_terms
+    zeta_pow_deg = z.pow(n)
+    for a in range(nc):
+        acc = Ext(0)
+        for t in reversed(terms):
+            acc = acc * int(alphas[a]) + t
+        chunk = qs[a * c.quotient_degree_factor:(a + 1) * c.quotient_degree_factor]
+        q = Ext(0)
+        for v in reversed(chunk):   # reduce_with_powers(chunk, zeta^n)
+            q = q * zeta_pow_deg + v
+        if not (acc == z_h * q):
+            return False
+    return True

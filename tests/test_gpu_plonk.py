@@ -106,3 +106,70 @@ def test_large_circuit_verifier_identity(qp, ctx):
     for x0 in (5, 0xDEADBEEFCAFEF00D % P):
         assert verifier_identity_holds(sc, g_cs.polynomials, g_w.polynomials, g_z.polynomials, q, betas, gammas,
                                        alphas, x0)
+
+
+@pytest.mark.parametrize("degree_bits,qdf,pow_bits,queries", [(6, 8, 6, 4), (9, 8, 16, 28), (8, 4, 10, 7), (11, 8, 16, 28)])
+def test_full_proof_bytes_match_oracle(qp, ctx, degree_bits, qdf, pow_bits, queries):
+    """prove_with_partition_witness (plonky2/src/plonk/prover.rs:176-398) end to end on the device,
+    serialised like write_proof_with_public_inputs -- byte for byte against the oracle's prove()."""
+    from oracle import prover as oprover
+    from qp_plonky2_b200 import prover
+
+    sc = SynthCircuit(degree_bits, seed=60 + degree_bits, quotient_degree_factor=qdf)
+    c = sc.common
+    circ = plonk.Circuit(ctx, c, sc.sigmas)
+    cfg = prover.FriConfig(c.rate_bits, c.cap_height, pow_bits, 4, 5, queries)
+    pd = prover.ProverData(ctx, circ, sc.constants_sigmas(), cfg)
+    timing = {}
+    got = prover.prove(pd, sc.wires, sc.public_inputs, timing)
+    o_cs = oracle.PolynomialBatch.from_values(sc.constants_sigmas(), c.rate_bits, c.cap_height)
+    assert (pd.circuit_digest == oprover.circuit_digest(o_cs.cap, degree_bits)).all()
+    want, info = oprover.prove(sc.oracle_circuit, o_cs, c.num_constants, sc.wires, sc.sigmas, sc.public_inputs,
+                               degree_bits=degree_bits, num_wires=c.num_wires, num_routed_wires=c.num_routed_wires,
+                               num_challenges=c.num_challenges, quotient_degree_factor=qdf,
+                               num_partial_products=c.num_partial_products, rate_bits=c.rate_bits,
+                               cap_height=c.cap_height, proof_of_work_bits=pow_bits, num_query_rounds=queries)
+    assert len(got) == len(want)
+    assert got == want
+    assert set(timing) >= {"compute wires commitment", "compute quotient polys", "compute opening proofs"}
+
+
+def test_large_proof_openings_pass_the_verifier(qp, ctx):
+    """2^15-row proof on the device (the oracle's quotient would take a minute): parse the opening
+    set back out of the proof bytes, re-derive the challenges with the host transcript and run the
+    restated verifier's algebraic check at zeta."""
+    from qp_plonky2_b200 import prover
+    from synth_circuit import verifier_plonk_identity
+
+    sc = SynthCircuit(15, seed=77)
+    c = sc.common
+    circ = plonk.Circuit(ctx, c, sc.sigmas)
+    pd = prover.ProverData(ctx, circ, sc.constants_sigmas())
+    proof = prover.prove(pd, sc.wires, sc.public_inputs)
+    cap_words = (1 << c.cap_height) * 4
+    n_open = (c.num_constants + c.num_routed_wires + c.num_wires + c.num_challenges * (2 + c.num_partial_products) +
+              c.num_challenges * c.quotient_degree_factor)
+    words = np.frombuffer(proof[: 8 * (3 * cap_words + 2 * n_open)], dtype="<u8")
+    caps = [words[i * cap_words:(i + 1) * cap_words] for i in range(3)]
+    pos = 3 * cap_words
+    nc = c.num_challenges
+    sizes = [("constants", c.num_constants), ("plonk_sigmas", c.num_routed_wires), ("wires", c.num_wires),
+             ("plonk_zs", nc), ("plonk_zs_next", nc), ("partial_products", nc * c.num_partial_products),
+             ("quotient_polys", nc * c.quotient_degree_factor)]
+    openings = {}
+    for name, k in sizes:
+        openings[name] = words[pos:pos + 2 * k].reshape(k, 2)
+        pos += 2 * k
+    # replay the transcript (prover.rs:216-345 / verifier get_challenges.rs:39-96)
+    ch = qp.Challenger()
+    pd.fri.observe(ch, c.degree_bits, pd.reduction_arity_bits)
+    ch.observe_elements(pd.circuit_digest)
+    pih = prover.hash_no_pad(ctx, sc.public_inputs)
+    ch.observe_elements(pih)
+    ch.observe_cap(caps[0])
+    betas, gammas = ch.get_n_challenges(nc), ch.get_n_challenges(nc)
+    ch.observe_cap(caps[1])
+    alphas = ch.get_n_challenges(nc)
+    ch.observe_cap(caps[2])
+    zeta = ch.get_extension_challenge()
+    assert verifier_plonk_identity(c, openings, zeta, betas, gammas, alphas, pih)

@@ -129,3 +129,42 @@ def test_oracle_detects_unsatisfied_witness():
     q = sc.oracle_circuit.compute_quotient_polys(c.rate_bits, cs.leaves, wb.leaves, zb.leaves, betas, gammas,
                                                  alphas, sc.public_inputs_hash)
     assert not verifier_identity_holds(sc, cs.polynomials, wb.polynomials, zb.polynomials, q, betas, gammas, alphas, 77)
+
+
+def _oracle_prove(sc, **kw):
+    from oracle import prover as oprover
+
+    c = sc.common
+    cs = oracle.PolynomialBatch.from_values(sc.constants_sigmas(), c.rate_bits, c.cap_height)
+    return oprover.prove(sc.oracle_circuit, cs, c.num_constants, sc.wires, sc.sigmas, sc.public_inputs,
+                         degree_bits=c.degree_bits, num_wires=c.num_wires, num_routed_wires=c.num_routed_wires,
+                         num_challenges=c.num_challenges, quotient_degree_factor=c.quotient_degree_factor,
+                         num_partial_products=c.num_partial_products, rate_bits=c.rate_bits,
+                         cap_height=c.cap_height, **kw)
+
+
+@pytest.mark.parametrize("degree_bits,qdf", [(6, 8), (7, 4)])
+def test_oracle_proof_openings_satisfy_the_verifier(degree_bits, qdf):
+    """Full oracle prove(): the opening set inside the proof passes the verifier's algebraic check
+    at the Fiat-Shamir point zeta in F_p^2 (verifier/src/plonk/verifier.rs:60-100)."""
+    from synth_circuit import verifier_plonk_identity
+
+    sc = SynthCircuit(degree_bits, seed=41, quotient_degree_factor=qdf)
+    proof, info = _oracle_prove(sc, proof_of_work_bits=6, num_query_rounds=4)
+    assert verifier_plonk_identity(sc.common, info["openings"], info["zeta"], info["betas"], info["gammas"],
+                                   info["alphas"], info["pih"])
+    # tampering with one opening breaks it
+    bad = dict(info["openings"])
+    bad["wires"] = info["openings"]["wires"].copy()
+    bad["wires"][3, 0] ^= 1
+    assert not verifier_plonk_identity(sc.common, bad, info["zeta"], info["betas"], info["gammas"], info["alphas"],
+                                       info["pih"])
+    # layout: 3 caps, opening set, FRI proof, public inputs (serialization/mod.rs:2040-2079)
+    c = sc.common
+    n_open = (c.num_constants + c.num_routed_wires + c.num_wires + 2 * c.num_challenges +
+              c.num_challenges * c.num_partial_products + c.num_challenges * c.quotient_degree_factor)
+    assert proof[: 3 * 16 * 32] != b"" and len(proof) > 3 * 16 * 32 + n_open * 16
+    tail = np.frombuffer(proof[-8 * (1 + len(sc.public_inputs)):], dtype="<u8")
+    assert int(tail[0]) == len(sc.public_inputs) and [int(x) for x in tail[1:]] == sc.public_inputs
+    # deterministic
+    assert _oracle_prove(sc, proof_of_work_bits=6, num_query_rounds=4)[0] == proof
