@@ -263,8 +263,15 @@ def run_ours(args):
     n_loc = N // world
     leaf_bytes = n_loc * (COLS * 8 + 32)                 # 8 B per element read + 32 B digest per leaf
     perms = n_loc * ((COLS + 7) // 8)
+    # DRAM bytes of one launch from the committed ncu --set full capture of this kernel at this size
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp) and world == 1:
+        rec = json.load(open(tp)).get("leaf_hash_kernel", {})
+        if rec.get("rows_log") == args.rows_log:
+            traffic = rec.get("dram_bytes")
     roof = {"kernel": "merkle::leaf_hash_kernel", "bound": "hbm", "achieved": leaf_bytes / (k_leaf * 1e-3) / 1e9,
-            "peak": peak, "unit": "GB/s", "frac": leaf_bytes / (k_leaf * 1e-3) / 1e9 / peak, "traffic": None,
+            "peak": peak, "unit": "GB/s", "frac": leaf_bytes / (k_leaf * 1e-3) / 1e9 / peak, "traffic": traffic,
             "peak_source": peak_src, "ms": k_leaf,
             "note": "integer-issue bound, not HBM bound: %.3g Poseidon permutations/s per GPU" % (perms / (k_leaf * 1e-3)),
             "permutations_per_s": perms / (k_leaf * 1e-3)}
@@ -289,6 +296,30 @@ def run_ours(args):
                                                                                      1 << (args.rows_log - sample)),
                "scopes_ms_sample": scopes}
 
+    # issue-slot roofline of the same kernel: ncu (profiles/r01f_ncu_leaf_hash_full_size.md) counts 17.65k warp
+    # instructions per warp-permutation; one warp instruction per cycle per SM sub-partition is the ceiling
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    instr_per_warp_perm = 17650.0
+    issue_peak = 148 * 4 * sm_mhz * 1e6 * 32 / instr_per_warp_perm
+    roof_issue = {"kernel": "merkle::leaf_hash_kernel", "bound": "issue slots (fma-heavy + ALU + FP64 pipes share one "
+                  "issue port per SM sub-partition)", "achieved": perms / (k_leaf * 1e-3), "peak": issue_peak,
+                  "unit": "Poseidon permutations/s", "frac": perms / (k_leaf * 1e-3) / issue_peak,
+                  "instr_per_warp_permutation": instr_per_warp_perm}
+
+    # ---- secondary metric of BASELINE.json: proof latency at bench_recursion's degrees (N=1 only) ----
+    prove = None
+    if world == 1 and not args.no_prove:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_prove
+            prove = {"what": "prove() from the witness on (wires/Z/quotient commitments, openings, FRI proof, "
+                             "serialisation) for a synthetic 143-wire circuit, standard_recursion_config; "
+                             "witness device-resident; best of 4",
+                     "runs": bench_prove.measure([12, 13, 14], [] if args.no_cpu else [12], reps=5, device=local,
+                                                 verbose=False)}
+        except Exception as e:  # the headline metric does not depend on it
+            prove = {"error": repr(e)}
+
     line = {
         "metric": METRIC, "value": dev_ms, "unit": "ms", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": False, "scaling": "strong",
@@ -297,7 +328,8 @@ def run_ours(args):
         "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(h_vals.numel() * 8),
                 "d2h_bytes_per_step": int((1 << CAP_HEIGHT) * 32 // world)},
         "gpu_launches": int(launches),
-        "roofline": roof, "roofline_lde": roof_lde, "roofline_intt": roof_intt,
+        "roofline": roof, "roofline_issue": roof_issue, "roofline_lde": roof_lde, "roofline_intt": roof_intt,
+        "prove": prove,
         "kernel_ms": {"intt": k_intt, "lde": k_lde, "leaf_hash": k_leaf, "tree_levels": k_tree},
         "cpu_baseline": cpu, "clocks": clocks,
         "cap0": [int(x) for x in caps[0][0]],
@@ -315,6 +347,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--rows-log", type=int, default=ROWS_LOG)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-prove", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

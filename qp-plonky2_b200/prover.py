@@ -102,7 +102,7 @@ def prove(prover_data, wires, public_inputs, timing=None):
     CUDA); public_inputs: list of field elements (already part of the witness)."""
     import time
 
-    from . import Challenger, PolynomialBatch, fri_from_openings, fri_proof
+    from . import Challenger, PolynomialBatch, _is_torch, fri_from_openings, fri_proof
     pd = prover_data
     ctx, circuit = pd.ctx, pd.circuit
     c = circuit.common
@@ -130,22 +130,34 @@ def prove(prover_data, wires, public_inputs, timing=None):
     challenger.observe_cap(wires_cap)
     betas = challenger.get_n_challenges(nc)
     gammas = challenger.get_n_challenges(nc)
-    zs_pp = circuit.partial_products_and_zs(wires, betas, gammas)
+    # a device-resident witness keeps every intermediate polynomial on the device
+    on_device = _is_torch(wires) and wires.is_cuda
+    n = 1 << c.degree_bits
+    zs_pp = None
+    if on_device:
+        import torch
+        zs_pp = torch.empty((nc * (1 + c.num_partial_products), n), dtype=torch.int64, device=wires.device)
+    zs_pp = circuit.partial_products_and_zs(wires, betas, gammas, out_device=zs_pp)
     lap("compute partial products")
     zs_commitment = PolynomialBatch.from_values(ctx, zs_pp, fri.rate_bits, False, fri.cap_height)
     lap("commit to partial products, Z's")
     zs_cap = zs_commitment.merkle_tree.cap
     challenger.observe_cap(zs_cap)
     alphas = challenger.get_n_challenges(nc)
+    quotient = None
+    if on_device:
+        quotient = torch.empty((nc, n << c.quotient_degree_bits), dtype=torch.int64, device=wires.device)
     quotient = circuit.compute_quotient_polys(pd.constants_sigmas_commitment, wires_commitment, zs_commitment,
-                                              betas, gammas, alphas, public_inputs_hash)
+                                              betas, gammas, alphas, public_inputs_hash, out_device=quotient)
     lap("compute quotient polys")
     # prover.rs:309-320: trim to quotient_degree = factor * n and split into degree-n chunks
-    n = 1 << c.degree_bits
     qd = c.quotient_degree_factor * n
-    if quotient.shape[1] > qd and quotient[:, qd:].any():
+    if quotient.shape[1] > qd and bool(quotient[:, qd:].any()):
         raise ValueError("Quotient has failed, the vanishing polynomial is not divisible by Z_H")
-    chunks = np.ascontiguousarray(quotient[:, :qd]).reshape(nc * c.quotient_degree_factor, n)
+    chunks = quotient[:, :qd].contiguous() if on_device else np.ascontiguousarray(quotient[:, :qd])
+    chunks = chunks.reshape(nc * c.quotient_degree_factor, n)
+    if on_device:
+        torch.cuda.current_stream().synchronize()  # a trimming copy runs on torch's stream, the library on its own
     quotient_commitment = PolynomialBatch.from_coeffs(ctx, chunks, fri.rate_bits, False, fri.cap_height)
     lap("commit to quotient polys")
     quotient_cap = quotient_commitment.merkle_tree.cap
