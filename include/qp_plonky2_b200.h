@@ -203,8 +203,9 @@ int qp_fri_proof_of_work(qp_ctx* ctx, const uint64_t state12[12], unsigned witne
  *   1 LDW dst = wire a            2 LDK dst = constants_sigmas polynomial a
  *   3 LDP dst = public_inputs_hash[a]   4 LDI dst = pool[a]
  *   5 ADD  6 SUB  7 MUL   (dst = r[a] op r[b])
- *   8 EMIT a   the next constraint of the current gate, LAST constraint first
- *   9 GATE a   end of a gate; r[a] holds its filter (compute_filter, gates/gate.rs:326-333)
+ *   10 MULI dst = r[a] * pool[b]     11 ADDI dst = r[a] + pool[b]
+ *   8 EMIT a, b  constraint number b of the current gate has the value r[a]
+ *   9 GATE a     end of a gate; r[a] holds its filter (compute_filter, gates/gate.rs:326-333)
  * The program evaluates evaluate_gate_constraints_base_batch (vanishing_poly.rs:700-726); a Rust
  * shim produces it by running Gate::eval_unfiltered_base_one over a recording field type, the
  * Python mirror (qp-plonky2_b200/plonk.py) from its own gate classes. */

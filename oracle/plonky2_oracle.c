@@ -801,6 +801,8 @@ static uint64_t gate_filter(const orc_gate *g, uint64_t s, int many_selectors) {
     return f;
 }
 
+static void poseidon_gate_eval(const uint64_t *wires, uint64_t *c);
+
 /* eval_unfiltered of the supported gates; `consts` already has the selector prefix removed
  * (gate.rs:179).  Adds filter * constraint_k into acc[k] (vanishing_poly.rs:700-726). */
 static void gate_eval_add(const orc_gate *g, const uint64_t *consts, const uint64_t *wires,
@@ -823,11 +825,81 @@ static void gate_eval_add(const orc_gate *g, const uint64_t *consts, const uint6
             acc[i] = gl_add(acc[i], gl_mul(filter, gl_sub(out, computed)));
         }
         break;
+    case ORC_GATE_POSEIDON: {
+        uint64_t c[123];
+        poseidon_gate_eval(wires, c);
+        for (unsigned i = 0; i < 123; i++) acc[i] = gl_add(acc[i], gl_mul(filter, c[i]));
+        break;
     }
+    }
+}
+
+/* PoseidonGate::eval_unfiltered_base_one, plonky2/src/gates/poseidon.rs:204-283.  Wire layout
+ * poseidon.rs:43-100: inputs 0..11, outputs 12..23, swap 24, deltas 25..28, first-half S-box
+ * inputs 29.., partial 65.., second-half 87... */
+static void poseidon_gate_eval(const uint64_t *wires, uint64_t *c /* 123 constraints */) {
+    unsigned k = 0;
+    const uint64_t swap = wires[24];
+    c[k++] = gl_mul(swap, gl_sub(swap, 1));
+    for (int i = 0; i < 4; i++)
+        c[k++] = gl_sub(gl_mul(swap, gl_sub(wires[i + 4], wires[i])), wires[25 + i]);
+    uint64_t st[12];
+    for (int i = 0; i < 4; i++) {
+        st[i] = gl_add(wires[i], wires[25 + i]);
+        st[i + 4] = gl_sub(wires[i + 4], wires[25 + i]);
+    }
+    for (int i = 8; i < 12; i++) st[i] = wires[i];
+    unsigned round = 0;
+    for (int r = 0; r < 4; r++) {
+        constant_layer(st, round);
+        if (r != 0)
+            for (int i = 0; i < 12; i++) {
+                const uint64_t in = wires[29 + 12 * (r - 1) + i];
+                c[k++] = gl_sub(st[i], in);
+                st[i] = in;
+            }
+        for (int i = 0; i < 12; i++) st[i] = sbox(st[i]);
+        mds_layer(st);
+        round++;
+    }
+    /* partial_first_constant_layer + mds_partial_layer_init, core/src/poseidon.rs:302-342 */
+    for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], POSEIDON_FAST_PARTIAL_FIRST_ROUND_CONSTANT[i]);
+    uint64_t t[12];
+    t[0] = st[0];
+    for (int cc = 1; cc < 12; cc++) t[cc] = 0;
+    for (int r = 1; r < 12; r++)
+        for (int cc = 1; cc < 12; cc++)
+            t[cc] = gl_add(t[cc], gl_mul(st[r], POSEIDON_FAST_PARTIAL_ROUND_INITIAL_MATRIX[(r - 1) * 11 + (cc - 1)]));
+    memcpy(st, t, sizeof t);
+    for (int r = 0; r < 22; r++) {
+        const uint64_t in = wires[65 + r];
+        c[k++] = gl_sub(st[0], in);
+        st[0] = sbox(in);
+        if (r != 21) st[0] = gl_add(st[0], POSEIDON_FAST_PARTIAL_ROUND_CONSTANTS[r]);
+        /* mds_partial_layer_fast, core/src/poseidon.rs:378-408 */
+        uint64_t d = gl_mul(st[0], POSEIDON_MDS_CIRC[0] + POSEIDON_MDS_DIAG[0]);
+        for (int j = 1; j < 12; j++) d = gl_add(d, gl_mul(st[j], POSEIDON_FAST_PARTIAL_ROUND_W_HATS[r * 11 + j - 1]));
+        for (int j = 1; j < 12; j++) st[j] = gl_add(st[j], gl_mul(st[0], POSEIDON_FAST_PARTIAL_ROUND_VS[r * 11 + j - 1]));
+        st[0] = d;
+    }
+    round += 22;
+    for (int r = 0; r < 4; r++) {
+        constant_layer(st, round);
+        for (int i = 0; i < 12; i++) {
+            const uint64_t in = wires[87 + 12 * r + i];
+            c[k++] = gl_sub(st[i], in);
+            st[i] = in;
+        }
+        for (int i = 0; i < 12; i++) st[i] = sbox(st[i]);
+        mds_layer(st);
+        round++;
+    }
+    for (int i = 0; i < 12; i++) c[k++] = gl_sub(st[i], wires[12 + i]);
 }
 
 unsigned orc_gate_num_constraints(const orc_gate *g) {
     switch (g->kind) {
+    case ORC_GATE_POSEIDON: return 123; /* poseidon.rs:416-422 */
     case ORC_GATE_CONSTANT: return g->param;
     case ORC_GATE_PUBLIC_INPUT: return 4;
     case ORC_GATE_ARITHMETIC: return g->param;

@@ -4,24 +4,14 @@
 // Reference semantics: core/src/poseidon.rs:599-633 (poseidon / poseidon_naive -- the two are
 // the same function; the KATs at core/src/poseidon_goldilocks.rs:455-490 pin it).
 //
-// B200 formulation (not the reference's).  ncu on B200 shows the kernel is bound by the
-// fma-heavy pipe: IMAD.WIDE.U32 issues at 8 lanes/clk/SMSP (4 pipe cycles per warp
-// instruction), so the count of wide multiplies is what matters.
-//   * Linear layers never use full 64x64 products.  Every MDS coefficient is < 2^6, so the
-//     state is split into 32-bit halves and each output row is 2 x 12 IMAD.WIDE accumulations
-//     (no carries: sums stay < 2^43) followed by ONE 96-bit reduction; the next round's
-//     constants ride in as the initial value of the accumulators (constant layer for free).
-//   * The reference replaces the 22 partial rounds' MDS by sparse matrices with full 64-bit
-//     entries (FAST_PARTIAL_*, 23 modular multiplies per round).  Here three partial rounds are
-//     fused instead: with d = x0^7 - x0 the round is x' = M x + d m0 + rc', so after three rounds
-//         x''' = M^3 x + d1 M^3 e0 + d2 M^2 e0 + d3 M e0 + K
-//     and only lane 0 of the intermediate states is needed (one row of M, one of M^2).  The
-//     entries of M^2, M^3 are still < 2^25, so they remain 32-bit immediates of IMAD.WIDE:
-//     414 wide multiplies per three rounds instead of 864 (dense) or ~345 + 69 reductions (sparse).
-//   * 96-bit reductions are ALU-only (no IMAD), 128-bit products use ptxas' fused 7-instruction
-//     sequence (goldilocks.cuh).
-//   * One loop body per round type, shared by both halves of the permutation, keeps the code
-//     (~40 KB) inside the instruction cache; a fully unrolled permutation stalls on fetch.
+// B200 formulation (not the reference's), details further down and in DESIGN.md section 4.3:
+//   * the linear layers run on the FP64 pipe as EXACT integer arithmetic (DFMA on 32-bit halves,
+//     every row sum < 2^50), the S-box on the integer pipes: the work is spread over four issue
+//     pipes instead of saturating the fma-heavy one with IMAD.WIDE;
+//   * the reference replaces the 22 partial rounds' MDS by sparse matrices with full 64-bit
+//     entries (FAST_PARTIAL_*, 23 modular multiplies per round); here partial rounds are fused in
+//     PAIRS with the small-entry matrix M^2 instead;
+//   * one loop body per round type keeps the code inside the instruction cache.
 // Exact arithmetic => identical outputs to the reference.
 #pragma once
 #include <cuda_runtime.h>
@@ -34,8 +24,7 @@ namespace poseidon {
 static constexpr int WIDTH = 12;
 static constexpr int RATE = 8;
 static constexpr int N_ROUNDS = 30;
-static constexpr int N_PARTIAL_GROUPS = 7;  // rounds 4..24 in groups of three; round 25 alone
-static constexpr int N_PARTIAL_PAIRS = 11;  // FP64 formulation: rounds 4..25 in pairs
+static constexpr int N_PARTIAL_PAIRS = 11;  // rounds 4..25 in fused pairs
 
 struct Mat {
     uint32_t a[12][12];
@@ -56,30 +45,21 @@ __host__ __device__ constexpr Mat mat_mul(const Mat& x, const Mat& y) {
         for (int c = 0; c < 12; c++) {
             uint64_t acc = 0;
             for (int k = 0; k < 12; k++) acc += (uint64_t)x.a[r][k] * y.a[k][c];
-            z.a[r][c] = (uint32_t)acc;  // < 2^25 for M^2, M^3 (row sums of M are <= 264)
+            z.a[r][c] = (uint32_t)acc;  // < 2^17 for M^2 (row sums of M are <= 264)
         }
     return z;
 }
 static constexpr Mat M1 = mds_matrix();
-static constexpr Mat M2 = mat_mul(M1, M1);
-static constexpr Mat M3 = mat_mul(M2, M1);
 // device code cannot name namespace-scope constexpr objects: each device function re-declares
 // the matrices as local compile-time constants (all entries fold into immediates)
 #define QP_POSEIDON_MATS                                 \
     constexpr Mat m1 = mds_matrix();                     \
     constexpr Mat m2 = mat_mul(m1, m1);                  \
-    constexpr Mat m3 = mat_mul(m2, m1);                  \
-    (void)m2;                                            \
-    (void)m3;
+    (void)m2;
 
 // Device constants, uploaded once per context by upload_constants():
 //   c_rc[12 * r + i]      ALL_ROUND_CONSTANTS (core/src/poseidon.rs:57-155), plus a zero row 30
-//   c_grp_k[g][0..1]      scalars of partial group g:  rc'_0  and  (M rc' + rc'')_0
-//   c_grp_K[g][0..11]     vector  M^2 rc' + M rc'' + rc'''          (rc', rc'', rc''' = constants
-//                         of the three rounds FOLLOWING the group's first round)
 __constant__ uint64_t c_rc[WIDTH * (N_ROUNDS + 1)];
-__constant__ uint64_t c_grp_k[N_PARTIAL_GROUPS][2];
-__constant__ uint64_t c_grp_K[N_PARTIAL_GROUPS][WIDTH];
 // FP64-pipe formulation (see f64 below): the same constants as (2^52 + low half, 2^52 + high half)
 // doubles, and the constants of the 11 fused PAIRS of partial rounds:
 //   c_pair_k[g]        rc'_0                      (rc', rc'' = constants of the two rounds
@@ -95,8 +75,6 @@ static inline cudaError_t upload_constants(cudaStream_t stream) {
     typedef unsigned __int128 u128;
     const uint64_t P = gl::P;
     static uint64_t rc[WIDTH * (N_ROUNDS + 1)];
-    static uint64_t gk[N_PARTIAL_GROUPS][2];
-    static uint64_t gK[N_PARTIAL_GROUPS][WIDTH];
     for (int i = 0; i < WIDTH * N_ROUNDS; i++) rc[i] = POSEIDON_ALL_ROUND_CONSTANTS[i];
     for (int i = 0; i < WIDTH; i++) rc[WIDTH * N_ROUNDS + i] = 0;
     auto matvec = [&](const Mat& m, const uint64_t* v, uint64_t* out) {
@@ -106,19 +84,6 @@ static inline cudaError_t upload_constants(cudaStream_t stream) {
             out[r] = (uint64_t)(acc % P);
         }
     };
-    for (int g = 0; g < N_PARTIAL_GROUPS; g++) {
-        const int r = 4 + 3 * g;  // first round of the group
-        const uint64_t* r1 = rc + 12 * (r + 1);
-        const uint64_t* r2 = rc + 12 * (r + 2);
-        const uint64_t* r3 = rc + 12 * (r + 3);
-        uint64_t m1r1[12], m2r1[12], m1r2[12];
-        matvec(M1, r1, m1r1);
-        matvec(M2, r1, m2r1);
-        matvec(M1, r2, m1r2);
-        gk[g][0] = r1[0];
-        gk[g][1] = (uint64_t)(((u128)m1r1[0] + r2[0]) % P);
-        for (int i = 0; i < 12; i++) gK[g][i] = (uint64_t)(((u128)m2r1[i] + m1r2[i] + r3[i]) % P);
-    }
     // FP64 tables
     static double rcd[WIDTH * (N_ROUNDS + 1)][2];
     static uint64_t pk[N_PARTIAL_PAIRS], pK[N_PARTIAL_PAIRS][WIDTH];
@@ -154,8 +119,6 @@ static inline cudaError_t upload_constants(cudaStream_t stream) {
     if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_pair_K, pK, sizeof pK, 0, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_pair_k_d, pkd, sizeof pkd, 0, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_pair_K_d, pKd, sizeof pKd, 0, cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_grp_k, gk, sizeof gk, 0, cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_grp_K, gK, sizeof gK, 0, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // the sources are static host arrays
     return e;
 }
@@ -175,61 +138,9 @@ __device__ __forceinline__ uint64_t fold_row(uint64_t al, uint64_t ah) {
         ah += (uint64_t)hi[k_] * MAT.a[R][k_];                   \
     }
 
-// state <- M * state + rc[0..12]
-__device__ __forceinline__ void mds_layer(uint64_t (&s)[12], const uint64_t* rc) {
-    QP_POSEIDON_MATS
-    uint32_t lo[12], hi[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) gl::unpack(s[i], lo[i], hi[i]);
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        uint32_t c0, c1;
-        gl::unpack(rc[r], c0, c1);
-        uint64_t al = c0, ah = c1;
-        QP_DOT_ROW(m1, r, lo, hi, al, ah)
-        s[r] = fold_row(al, ah);
-    }
-}
-
 // (x0^7 - x0) split into halves
 __device__ __forceinline__ void sbox_delta(uint64_t x0, uint32_t& dlo, uint32_t& dhi) {
     gl::unpack(gl::sub(gl::pow7(x0), x0), dlo, dhi);
-}
-
-// Three fused partial rounds (see header).  `s` enters with its round constants already added.
-__device__ __forceinline__ void partial_group(uint64_t (&s)[12], int g) {
-    QP_POSEIDON_MATS
-    uint32_t lo[12], hi[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) gl::unpack(s[i], lo[i], hi[i]);
-    uint32_t d1l, d1h, d2l, d2h, d3l, d3h, c0, c1;
-    sbox_delta(s[0], d1l, d1h);
-    // lane 0 after round 1:  (M x)_0 + d1 M00 + rc'_0
-    gl::unpack(c_grp_k[g][0], c0, c1);
-    uint64_t al = c0, ah = c1;
-    QP_DOT_ROW(m1, 0, lo, hi, al, ah)
-    al += (uint64_t)d1l * m1.a[0][0];
-    ah += (uint64_t)d1h * m1.a[0][0];
-    sbox_delta(fold_row(al, ah), d2l, d2h);
-    // lane 0 after round 2:  (M^2 x)_0 + d1 (M^2)_00 + d2 M00 + (M rc' + rc'')_0
-    gl::unpack(c_grp_k[g][1], c0, c1);
-    al = c0;
-    ah = c1;
-    QP_DOT_ROW(m2, 0, lo, hi, al, ah)
-    al += (uint64_t)d1l * m2.a[0][0] + (uint64_t)d2l * m1.a[0][0];
-    ah += (uint64_t)d1h * m2.a[0][0] + (uint64_t)d2h * m1.a[0][0];
-    sbox_delta(fold_row(al, ah), d3l, d3h);
-    // full state after round 3
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        gl::unpack(c_grp_K[g][r], c0, c1);
-        al = c0;
-        ah = c1;
-        QP_DOT_ROW(m3, r, lo, hi, al, ah)
-        al += (uint64_t)d1l * m3.a[r][0] + (uint64_t)d2l * m2.a[r][0] + (uint64_t)d3l * m1.a[r][0];
-        ah += (uint64_t)d1h * m3.a[r][0] + (uint64_t)d2h * m2.a[r][0] + (uint64_t)d3h * m1.a[r][0];
-        s[r] = fold_row(al, ah);
-    }
 }
 
 // ---- FP64-pipe formulation of the linear layers ---------------------------------------------
@@ -246,9 +157,6 @@ __device__ __forceinline__ void partial_group(uint64_t (&s)[12], int g) {
 //     x'' = M^2 x + d1 M^2 e0 + d2 M e0 + K,   d = x0^7 - x0,
 // 362 DFMA per two rounds.  QP_POSEIDON_F64_FULL / _PART = how many of the 12 output rows of a
 // full-round / pair layer go to the FP64 pipe; the remaining rows use IMAD.WIDE (pipe balance).
-#ifndef QP_POSEIDON_F64
-#define QP_POSEIDON_F64 1
-#endif
 #ifndef QP_POSEIDON_F64_FULL
 #define QP_POSEIDON_F64_FULL 12
 #endif
@@ -370,18 +278,10 @@ __device__ __forceinline__ void partial_pair_f64(uint64_t (&s)[12], int g) {
     }
 }
 
-// Experiment knobs (tools/exp_variants.py); the defaults are the measured best on B200
-// (leaf hash at 2^21 leaves x 135: unrolled 41.8 ms, ODD_IN_FULL 41.5, + SBOX_ROT 2/3/4/6 =
-// 40.1/39.5/38.8/38.3, + MDS_ROT 40.9, barrier-per-round lockstep 42-44, explicit-mul 39.8).
-// Smaller code wins until the rotation moves cost more than the instruction fetches they save.
-#ifndef QP_POSEIDON_SBOX_ROT   // L > 0: S-box layer as 12/L iterations x L lanes with a register rotation
+// S-box layer as 12/L iterations x L lanes with a register rotation: smaller code wins until the
+// rotation moves cost more than the instruction fetches they save (measured best on B200: L = 6).
+#ifndef QP_POSEIDON_SBOX_ROT
 #define QP_POSEIDON_SBOX_ROT 6
-#endif
-#ifndef QP_POSEIDON_ODD_IN_FULL  // 1: the 22nd partial round reuses the full-round body
-#define QP_POSEIDON_ODD_IN_FULL 1
-#endif
-#ifndef QP_POSEIDON_MDS_ROT    // 1: MDS layer as 3 iterations x 4 rows with a register rotation
-#define QP_POSEIDON_MDS_ROT 0
 #endif
 
 // S-box layer on all 12 lanes (poseidon.rs:554-562)
@@ -404,61 +304,9 @@ __device__ __forceinline__ void sbox_all(uint64_t (&s)[12]) {
 #endif
 }
 
-#if QP_POSEIDON_MDS_ROT
-// state <- M * state + rc: the circulant part row r is row 0 applied to the state rotated by r,
-// so 4 rows per iteration with a rotation by 4 share one piece of code; the diagonal term
-// 8 * s[0] of row 0 is added in iteration 0 only (uniform predicate).
-__device__ __forceinline__ void mds_layer_rot(uint64_t (&s)[12], const uint64_t* rc) {
-    constexpr uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-    uint32_t lo[12], hi[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) gl::unpack(s[i], lo[i], hi[i]);
-    const uint32_t d_lo = lo[0], d_hi = hi[0];
-#pragma unroll 1
-    for (int it = 0; it < 3; it++) {
-        uint64_t out[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            uint32_t c0, c1;
-            gl::unpack(rc[4 * it + q], c0, c1);
-            uint64_t al = c0, ah = c1;
-#pragma unroll
-            for (int k = 0; k < 12; k++) {
-                al += (uint64_t)lo[(k + q) % 12] * C[k];
-                ah += (uint64_t)hi[(k + q) % 12] * C[k];
-            }
-            if (q == 0 && it == 0) {
-                al += (uint64_t)d_lo * 8u;
-                ah += (uint64_t)d_hi * 8u;
-            }
-            out[q] = fold_row(al, ah);
-        }
-        // rotate the halves by 4 and shift the finished rows into the state
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            uint32_t tl = lo[q], th = hi[q];
-            lo[q] = lo[q + 4];
-            hi[q] = hi[q + 4];
-            lo[q + 4] = lo[q + 8];
-            hi[q + 4] = hi[q + 8];
-            lo[q + 8] = tl;
-            hi[q + 8] = th;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = s[i + 4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) s[8 + q] = out[q];
-    }
-}
-#define QP_MDS_LAYER mds_layer_rot
-#else
-#define QP_MDS_LAYER mds_layer
-#endif
-
 // The permutation.  State lanes may be any u64 representatives; outputs likewise.
 // SYNC: all threads of the block run it together and meet at a barrier per round, which keeps
 // the warps of an SM inside the same window of code (instruction-cache working set).
-#if QP_POSEIDON_F64
 template <bool SYNC = false>
 __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
     // round 0 constant layer (poseidon.rs:504-513); every later round gets its constants from
@@ -485,52 +333,5 @@ __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
         }
     }
 }
-#else
-template <bool SYNC = false>
-__device__ __forceinline__ void permute(uint64_t (&s)[12]) {
-    // round 0 constant layer (poseidon.rs:504-513); every later round gets its constants from
-    // the linear layer that precedes it
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl::add1(s[i], c_rc[i]);
-#pragma unroll 1
-    for (int half = 0; half < 2; half++) {
-        // four full rounds (poseidon.rs:574-581); with ODD_IN_FULL the first half runs a fifth
-        // pass of the same body for partial round 25 (S-box on lane 0 only)
-#if QP_POSEIDON_ODD_IN_FULL
-        const int n_pass = half == 0 ? 4 : 5;
-        const int first = half == 0 ? 0 : 25;
-#pragma unroll 1
-        for (int r = first; r < first + n_pass; r++) {
-            if (SYNC) __syncthreads();
-            if (r == 25)
-                s[0] = gl::pow7(s[0]);
-            else
-                sbox_all(s);
-            QP_MDS_LAYER(s, c_rc + 12 * (r + 1));  // row 30 is zero
-        }
-#else
-        const int base = half * 26;
-#pragma unroll 1
-        for (int r = base; r < base + 4; r++) {
-            if (SYNC) __syncthreads();
-            sbox_all(s);
-            QP_MDS_LAYER(s, c_rc + 12 * (r + 1));  // row 30 is zero
-        }
-#endif
-        if (half == 0) {
-            // 22 partial rounds (poseidon.rs:623-628): 7 fused triples + round 25
-#pragma unroll 1
-            for (int g = 0; g < N_PARTIAL_GROUPS; g++) {
-                if (SYNC) __syncthreads();
-                partial_group(s, g);
-            }
-#if !QP_POSEIDON_ODD_IN_FULL
-            s[0] = gl::pow7(s[0]);
-            mds_layer(s, c_rc + 12 * 26);
-#endif
-        }
-    }
-}
-#endif  // QP_POSEIDON_F64
 
 }  // namespace poseidon

@@ -1514,6 +1514,7 @@ struct qp_circuit {
     uint64_t* program = nullptr;  // program_len + 1 words (OP_END appended)
     uint64_t* pool = nullptr;
     uint64_t* zh = nullptr;       // [2][2^qdb]: Z_H on the coset, and its inverses
+    unsigned max_emit = 0;        // largest constraint index in the program
     ScaleTables g_inv;            // powers of 1/g up to 2^(degree_bits + qdb)
 };
 
@@ -1547,6 +1548,25 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
     CUDA_TRY(ctx, cudaMemcpyAsync(c->k_is, d->k_is, d->num_routed_wires * 8, cudaMemcpyHostToDevice, ctx->stream));
     std::vector<uint64_t> prog(d->program, d->program + d->program_len);
     prog.push_back(quotient::OP_END);
+    for (uint64_t ins : prog) {
+        const unsigned op = ins & 0xff, dst = (ins >> 8) & 0xffff, a = (ins >> 24) & 0xffff, b = (ins >> 40) & 0xffff;
+        const bool arith = op == quotient::OP_ADD || op == quotient::OP_SUB || op == quotient::OP_MUL;
+        const bool load = op >= quotient::OP_LDW && op <= quotient::OP_LDI;
+        bool ok = op <= quotient::OP_ADDI;
+        if (arith) ok = dst < d->program_regs && a < d->program_regs && b < d->program_regs;
+        if (op == quotient::OP_MULI || op == quotient::OP_ADDI)
+            ok = dst < d->program_regs && a < d->program_regs && b < d->pool_len;
+        if (load) ok = dst < d->program_regs;
+        if (op == quotient::OP_EMIT || op == quotient::OP_GATE) ok = a < d->program_regs;
+        if (op == quotient::OP_LDW) ok = ok && a < d->num_wires;
+        if (op == quotient::OP_LDK) ok = ok && a < d->num_constants + d->num_routed_wires;
+        if (op == quotient::OP_LDI) ok = ok && a < d->pool_len;
+        if (!ok) {
+            delete c;
+            return fail(ctx, QP_ERR_BAD_ARG, "malformed constraint program");
+        }
+        if (op == quotient::OP_EMIT && b > c->max_emit) c->max_emit = b;
+    }
     CUDA_TRY(ctx, cudaMemcpyAsync(c->program, prog.data(), prog.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (d->pool_len)
         CUDA_TRY(ctx, cudaMemcpyAsync(c->pool, d->pool, d->pool_len * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -1707,14 +1727,16 @@ extern "C" int qp_circuit_compute_quotient_polys(qp_circuit* c, const qp_batch* 
     p.pool = c->pool;
     p.n_regs = d.program_regs;
     const unsigned base = nc + nc * (np + 1);
-    std::vector<uint64_t> apow((size_t)nc * (base + 1));
+    const unsigned stride = (base > c->max_emit ? base : c->max_emit) + 1;
+    p.apow_stride = stride;
+    std::vector<uint64_t> apow((size_t)nc * stride);
     for (unsigned a = 0; a < nc; a++) {
         p.betas[a] = betas[a];
         p.gammas[a] = gammas[a];
         p.alphas[a] = alphas[a];
         uint64_t pw = 1;
-        for (unsigned t = 0; t <= base; t++) {
-            apow[(size_t)a * (base + 1) + t] = pw;
+        for (unsigned t = 0; t < stride; t++) {
+            apow[(size_t)a * stride + t] = pw;
             pw = gl::host_mul(pw, alphas[a] % gl::P);
         }
     }

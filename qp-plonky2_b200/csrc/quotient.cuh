@@ -15,7 +15,9 @@
 // data (common_data.gates): the host compiles every gate's filtered constraints into one
 // straight-line program over F_p (plonk.py / the Rust shim's recording field type) and the
 // kernel interprets it with its register file in shared memory -- exact arithmetic, so any
-// evaluation order gives the reference's values.
+// evaluation order gives the reference's values.  Constraints carry their index (the power of
+// alpha they get), so the program evaluates them in the gate's natural order and registers die
+// young (a Poseidon gate needs ~40 live values, not the ~330 a last-to-first Horner order forces).
 #pragma once
 #include "goldilocks.cuh"
 
@@ -31,8 +33,10 @@ enum : unsigned {
     OP_ADD = 5,
     OP_SUB = 6,
     OP_MUL = 7,
-    OP_EMIT = 8,  // next constraint of the current gate (emitted LAST to FIRST): h = h alpha + r[a]
+    OP_EMIT = 8,  // constraint b of the current gate: h += alpha^b r[a]
     OP_GATE = 9,  // end of a gate: G += r[a] (filter) * h, h = 0
+    OP_MULI = 10, // dst = r[a] * pool[b]
+    OP_ADDI = 11, // dst = r[a] + pool[b]
 };
 
 constexpr int MAX_CHALLENGES = 4;
@@ -60,7 +64,8 @@ struct Params {
     const uint64_t* k_is;        // [nr]
     const uint64_t* zh_eval;     // [2^qdb]  g^n v^k - 1
     const uint64_t* zh_inv;      // [2^qdb]
-    const uint64_t* alpha_pows;  // [nc][base + 1], base = nc + nc (np + 1)
+    const uint64_t* alpha_pows;  // [nc][apow_stride]: alpha^t, t <= max(base, constraints per gate); base = nc + nc (np + 1)
+    unsigned apow_stride;
     uint64_t betas[MAX_CHALLENGES], gammas[MAX_CHALLENGES], alphas[MAX_CHALLENGES];
     uint64_t pih[4];
     // gate program
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(BLOCK) quotient_kernel(Params p) {
     auto add_term = [&](unsigned t, uint64_t term) {
 #pragma unroll
         for (int a = 0; a < MAX_CHALLENGES; a++)
-            if (a < (int)p.nc) res[a] = gl::add(res[a], gl::mul(term, p.alpha_pows[a * (base + 1) + t]));
+            if (a < (int)p.nc) res[a] = gl::add(res[a], gl::mul(term, p.alpha_pows[a * p.apow_stride + t]));
     };
     // the L_0(x) (Z(x) - 1) terms, vanishing_poly.rs:268-272
     for (unsigned ch = 0; ch < p.nc; ch++) add_term(ch, gl::mul(l_0, gl::sub(p.zs[ch * p.zs_stride + pos], 1)));
@@ -150,11 +155,13 @@ __global__ void __launch_bounds__(BLOCK) quotient_kernel(Params p) {
             case OP_ADD: r[dst * BLOCK] = gl::add(r[a * BLOCK], r[b * BLOCK]); break;
             case OP_SUB: r[dst * BLOCK] = gl::sub(r[a * BLOCK], r[b * BLOCK]); break;
             case OP_MUL: r[dst * BLOCK] = gl::mul(r[a * BLOCK], r[b * BLOCK]); break;
+            case OP_MULI: r[dst * BLOCK] = gl::mul(r[a * BLOCK], p.pool[b]); break;
+            case OP_ADDI: r[dst * BLOCK] = gl::add(r[a * BLOCK], p.pool[b]); break;
             case OP_EMIT: {
                 const uint64_t v = r[a * BLOCK];
 #pragma unroll
                 for (int c = 0; c < MAX_CHALLENGES; c++)
-                    if (c < (int)p.nc) h[c] = gl::add(gl::mul(h[c], p.alphas[c]), v);
+                    if (c < (int)p.nc) h[c] = gl::add(h[c], gl::mul(v, p.alpha_pows[c * p.apow_stride + b]));
                 break;
             }
             case OP_GATE: {
@@ -174,7 +181,7 @@ __global__ void __launch_bounds__(BLOCK) quotient_kernel(Params p) {
 #pragma unroll
     for (int a = 0; a < MAX_CHALLENGES; a++)
         if (a < (int)p.nc) {
-            const uint64_t total = gl::add(res[a], gl::mul(G[a], p.alpha_pows[a * (base + 1) + base]));
+            const uint64_t total = gl::add(res[a], gl::mul(G[a], p.alpha_pows[a * p.apow_stride + base]));
             p.out[((size_t)a << p.lg_lde) + i] = gl::canon(gl::mul(total, zinv));  // prover.rs:848-853
         }
 }

@@ -21,7 +21,7 @@ P = 0xFFFFFFFF00000001
 MULTIPLICATIVE_GROUP_GENERATOR = 14293326489335486720  # field/src/goldilocks_field.rs:84
 UNUSED_SELECTOR = 0xFFFFFFFF  # core/src/selectors.rs
 
-OP_END, OP_LDW, OP_LDK, OP_LDP, OP_LDI, OP_ADD, OP_SUB, OP_MUL, OP_EMIT, OP_GATE = range(10)
+OP_END, OP_LDW, OP_LDK, OP_LDP, OP_LDI, OP_ADD, OP_SUB, OP_MUL, OP_EMIT, OP_GATE, OP_MULI, OP_ADDI = range(12)
 
 
 # ---- recording value type ------------------------------------------------------------------------
@@ -35,7 +35,12 @@ class Val:
 
     def _bin(self, op, other):
         if not isinstance(other, Val):
-            other = self.prog.imm(other)
+            # constants go into the instruction (pool index), not into a register
+            if op == OP_MUL:
+                return self.prog._node(OP_MULI, self.idx, self.prog.pool_slot(other))
+            if op == OP_ADD:
+                return self.prog._node(OP_ADDI, self.idx, self.prog.pool_slot(other))
+            return self.prog._node(OP_ADDI, self.idx, self.prog.pool_slot(-int(other)))
         return self.prog._node(op, self.idx, other.idx)
 
     def __add__(self, o):
@@ -56,7 +61,7 @@ class Val:
 
 class ConstraintProgram:
     """Builds the program: leaves are loads, inner nodes field operations; `emit_gate` appends a
-    gate's constraints (in REVERSE order, as the kernel's Horner step wants) and its filter."""
+    gate's constraints (each with its index k: the kernel adds alpha^k * value) and its filter."""
 
     def __init__(self):
         self.nodes = []    # (op, a, b)
@@ -86,19 +91,25 @@ class ConstraintProgram:
     def public_input_hash(self, i):
         return self._node(OP_LDP, i)
 
-    def imm(self, v):
+    def pool_slot(self, v):
         v = int(v) % P
         k = self.pool_index.get(v)
         if k is None:
             k = len(self.pool)
             self.pool.append(v)
             self.pool_index[v] = k
-        return self._node(OP_LDI, k)
+        return k
+
+    def imm(self, v):
+        return self._node(OP_LDI, self.pool_slot(v))
 
     def emit_gate(self, constraints, filt):
-        for c in reversed(constraints):
-            self.actions.append((OP_EMIT, c.idx))
-        self.actions.append((OP_GATE, filt.idx))
+        for k, c in enumerate(constraints):
+            self.actions.append((OP_EMIT, c.idx, k))
+        self.actions.append((OP_GATE, filt.idx, 0))
+        # values are not shared across gates: a wire loaded for one gate would otherwise stay in a
+        # register until the last gate that reads it
+        self.memo = {}
 
     def compile(self):
         """-> (code uint64[], pool uint64[], n_regs).  Nodes are scheduled lazily in action order
@@ -107,7 +118,7 @@ class ConstraintProgram:
         # schedule: post-order from each action's root
         order, seen = [], set()
         sched = []  # ("node", i) | ("act", op, i)
-        for op, root in self.actions:
+        for op, root, k in self.actions:
             stack = [(root, False)]
             while stack:
                 i, done = stack.pop()
@@ -120,10 +131,10 @@ class ConstraintProgram:
                     sched.append(("node", i))
                     continue
                 stack.append((i, True))
-                for ch in (b, a):
+                for ch in ((a,) if nop in (OP_MULI, OP_ADDI) else (b, a)):
                     if ch not in seen:
                         stack.append((ch, False))
-            sched.append(("act", op, root))
+            sched.append(("act", op, root, k))
         last_use = {}
         for t, s in enumerate(sched):
             if s[0] == "node":
@@ -131,6 +142,8 @@ class ConstraintProgram:
                 if nop in (OP_ADD, OP_SUB, OP_MUL):
                     last_use[a] = t
                     last_use[b] = t
+                elif nop in (OP_MULI, OP_ADDI):
+                    last_use[a] = t
             else:
                 last_use[s[2]] = t
         reg_of, free, n_regs, code = {}, [], 0, []
@@ -144,6 +157,10 @@ class ConstraintProgram:
                     for ch in {a, b}:
                         if last_use.get(ch) == t:
                             free.append(reg_of[ch])
+                elif nop in (OP_MULI, OP_ADDI):
+                    ra, rb = reg_of[a], b
+                    if last_use.get(a) == t:
+                        free.append(reg_of[a])
                 else:
                     ra = a
                 if free:
@@ -156,8 +173,8 @@ class ConstraintProgram:
                 if i not in last_use:  # dead value
                     free.append(r)
             else:
-                _, op, root = s
-                code.append(op | (reg_of[root] << 24))
+                _, op, root, k = s
+                code.append(op | (reg_of[root] << 24) | (k << 40))
                 if last_use.get(root) == t:
                     free.append(reg_of[root])
         assert n_regs < (1 << 16) and len(self.pool) < (1 << 16)
@@ -228,6 +245,153 @@ class ArithmeticGate(Gate):  # plonky2/src/gates/arithmetic_base.rs
             m0, m1, addend, output = wires(4 * i), wires(4 * i + 1), wires(4 * i + 2), wires(4 * i + 3)
             out.append(output - (m0 * m1 * c0 + addend * c1))
         return out
+
+
+def _poseidon_constants():
+    """The tables of core/src/poseidon_goldilocks.rs as generated into csrc/poseidon_constants.h
+    (tools/gen_poseidon_constants.py)."""
+    import os
+    import re
+    global _PC
+    if _PC is None:
+        text = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "poseidon_constants.h")).read()
+        _PC = {}
+        for m in re.finditer(r"static const uint64_t (\w+)\[(\d+)\] = \{(.*?)\};", text, re.S):
+            _PC[m.group(1)] = [int(t, 16) for t in re.findall(r"0x([0-9a-fA-F]+)ULL", m.group(3))]
+    return _PC
+
+
+_PC = None
+
+
+class PoseidonGate(Gate):
+    """plonky2/src/gates/poseidon.rs: one width-12 permutation per row, S-box inputs as wires.
+    `arith` supplies the value type: the recording `Val`s for the constraint program, plain
+    integers mod p for witness generation (the gate's generator, poseidon.rs:424-520)."""
+    degree = 7
+    num_constraints = 12 * 7 + 22 + 12 + 1 + 4   # poseidon.rs:416-422
+    WIRE_SWAP = 24
+    START_DELTA = 25
+    START_FULL_0 = 29
+    START_PARTIAL = 29 + 12 * 3
+    START_FULL_1 = 29 + 12 * 3 + 22
+    END = 29 + 12 * 3 + 22 + 12 * 4            # 135 wires
+
+    def id(self):
+        return "PoseidonGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>"
+
+    @staticmethod
+    def _mds(state):
+        k = _poseidon_constants()
+        circ, diag = k["POSEIDON_MDS_CIRC"], k["POSEIDON_MDS_DIAG"]
+        out = []
+        for r in range(12):   # core/src/poseidon.rs:178-198
+            acc = state[r] * (circ[0] + diag[r])
+            for i in range(1, 12):
+                acc = acc + state[(i + r) % 12] * circ[i]
+            out.append(acc)
+        return out
+
+    @staticmethod
+    def _sbox(x):
+        x2 = x * x
+        x4 = x2 * x2
+        return x * x2 * x4
+
+    def _run(self, wires, on_sbox_in, on_constraint):
+        """The body shared by eval_unfiltered and the witness generator (poseidon.rs:204-283).
+        on_sbox_in(wire_index, computed_state) -> value to continue with."""
+        k = _poseidon_constants()
+        rc = k["POSEIDON_ALL_ROUND_CONSTANTS"]
+        swap = wires(self.WIRE_SWAP)
+        on_constraint(swap * (swap - 1))
+        state = [None] * 12
+        for i in range(4):
+            lhs, rhs = wires(i), wires(i + 4)
+            delta = on_sbox_in(self.START_DELTA + i, swap * (rhs - lhs), negate=True)
+            state[i], state[i + 4] = lhs + delta, rhs - delta
+        for i in range(8, 12):
+            state[i] = wires(i)
+        rnd = 0
+        for r in range(4):
+            state = [state[i] + rc[12 * rnd + i] for i in range(12)]
+            if r != 0:
+                state = [on_sbox_in(self.START_FULL_0 + 12 * (r - 1) + i, state[i]) for i in range(12)]
+            state = self._mds([self._sbox(x) for x in state])
+            rnd += 1
+        # partial rounds, fast form (core/src/poseidon.rs:302-342,378-408,584-596)
+        state = [state[i] + k["POSEIDON_FAST_PARTIAL_FIRST_ROUND_CONSTANT"][i] for i in range(12)]
+        init = k["POSEIDON_FAST_PARTIAL_ROUND_INITIAL_MATRIX"]
+        t = [state[0]] + [None] * 11
+        for c in range(1, 12):
+            acc = state[1] * init[c - 1]
+            for r in range(2, 12):
+                acc = acc + state[r] * init[(r - 1) * 11 + (c - 1)]
+            t[c] = acc
+        state = t
+        m00 = k["POSEIDON_MDS_CIRC"][0] + k["POSEIDON_MDS_DIAG"][0]
+        for r in range(22):
+            s0 = self._sbox(on_sbox_in(self.START_PARTIAL + r, state[0]))
+            if r != 21:
+                s0 = s0 + k["POSEIDON_FAST_PARTIAL_ROUND_CONSTANTS"][r]
+            w_hat = k["POSEIDON_FAST_PARTIAL_ROUND_W_HATS"][11 * r: 11 * r + 11]
+            vs = k["POSEIDON_FAST_PARTIAL_ROUND_VS"][11 * r: 11 * r + 11]
+            d = s0 * m00
+            for j in range(1, 12):
+                d = d + state[j] * w_hat[j - 1]
+            state = [d] + [state[j] + s0 * vs[j - 1] for j in range(1, 12)]
+        rnd += 22
+        for r in range(4):
+            state = [state[i] + rc[12 * rnd + i] for i in range(12)]
+            state = [on_sbox_in(self.START_FULL_1 + 12 * r + i, state[i]) for i in range(12)]
+            state = self._mds([self._sbox(x) for x in state])
+            rnd += 1
+        return state
+
+    def eval_unfiltered(self, consts, wires, pih):
+        cons = []
+
+        def on_sbox_in(w, computed, negate=False):
+            cons.append(computed - wires(w))   # delta: swap*(rhs-lhs) - delta_i; S-box: state - sbox_in
+            return wires(w)
+
+        out = self._run(wires, on_sbox_in, cons.append)
+        for i in range(12):
+            cons.append(out[i] - wires(12 + i))
+        return cons
+
+    def generate(self, inputs, swap):
+        """PoseidonGenerator (poseidon.rs:424-520): -> {wire index: value} for one row."""
+
+        class M:  # integer mod p with the operators the body uses
+            __slots__ = ("v",)
+
+            def __init__(self, v):
+                self.v = int(v) % P
+
+            def _o(self, o):
+                return o.v if isinstance(o, M) else int(o)
+
+            def __add__(self, o):
+                return M(self.v + self._o(o))
+
+            def __sub__(self, o):
+                return M(self.v - self._o(o))
+
+            def __mul__(self, o):
+                return M(self.v * self._o(o))
+
+        row = {i: M(inputs[i]) for i in range(12)}
+        row[self.WIRE_SWAP] = M(swap)
+
+        def on_sbox_in(w, computed, negate=False):
+            row[w] = computed
+            return computed
+
+        out = self._run(lambda i: row[i], on_sbox_in, lambda c: None)
+        for i in range(12):
+            row[12 + i] = out[i]
+        return {w: v.v for w, v in row.items()}
 
 
 def sort_gates(gates):

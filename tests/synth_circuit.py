@@ -5,7 +5,9 @@ permutation argument and the quotient only consume its OUTPUT -- gate list, sele
 polynomials, sigma polynomials, and a witness.  This module fabricates those directly:
 
   * rows are assigned one of {NoopGate, ConstantGate(2), PublicInputGate, ArithmeticGate(routed/4)}
-    (gate semantics: plonky2/src/gates/*.rs) with random gate constants;
+    and, with `poseidon=True`, PoseidonGate (the gate recursion circuits spend their rows on;
+    degree 7, 123 constraints, its own selector group) -- gate semantics: plonky2/src/gates/*.rs --
+    with random gate constants;
   * the witness satisfies every gate; inputs of arithmetic operations are, with probability 1/2,
     COPIES of unconstrained cells elsewhere in the trace, and every copy class is wired as one cycle
     of the permutation sigma (what CircuitBuilder::sigma_vecs derives from `connect` calls,
@@ -29,28 +31,35 @@ def _addmod(a, b):
 
 class SynthCircuit:
     def __init__(self, degree_bits, seed=1, num_wires=143, num_routed_wires=80, num_challenges=2,
-                 quotient_degree_factor=8, rate_bits=3, cap_height=4):
+                 quotient_degree_factor=8, rate_bits=3, cap_height=4, poseidon=False):
         rng = np.random.Generator(np.random.PCG64(seed))
         n = 1 << degree_bits
         nr = num_routed_wires
         self.n = n
         gates = [plonk.NoopGate(), plonk.ConstantGate(2), plonk.PublicInputGate(),
                  plonk.ArithmeticGate.new_from_config(nr)]
+        if poseidon:
+            gates.append(plonk.PoseidonGate())
         self.common = c = plonk.CommonCircuitData(degree_bits, gates, num_wires, nr, num_challenges,
                                                   quotient_degree_factor, rate_bits, cap_height)
         kinds = {"NoopGate": oracle.GATE_NOOP, "ConstantGate": oracle.GATE_CONSTANT,
-                 "PublicInputGate": oracle.GATE_PUBLIC_INPUT, "ArithmeticGate": oracle.GATE_ARITHMETIC}
+                 "PublicInputGate": oracle.GATE_PUBLIC_INPUT, "ArithmeticGate": oracle.GATE_ARITHMETIC,
+                 "PoseidonGate": oracle.GATE_POSEIDON}
         og = []
         for i, g in enumerate(c.gates):
-            name = g.id().split(" ")[0]
+            name = g.id().split(" ")[0].split("(")[0]
             param = getattr(g, "num_consts", getattr(g, "num_ops", 0))
             og.append((kinds[name], param, c.selector_indices[i], c.groups[c.selector_indices[i]]))
         self.oracle_circuit = oracle.Circuit(degree_bits, c.quotient_degree_bits, num_challenges, nr, num_wires,
                                              c.num_constants, c.num_partial_products, quotient_degree_factor,
                                              c.num_selectors, og, c.k_is)
-        idx = {g.id().split(" ")[0]: i for i, g in enumerate(c.gates)}
-        # gate per row: mostly arithmetic, a few of the others; row 0 is the public-input gate
-        row_gate = rng.choice([idx["NoopGate"], idx["ConstantGate"], idx["ArithmeticGate"]], size=n, p=[0.2, 0.1, 0.7])
+        idx = {g.id().split(" ")[0].split("(")[0]: i for i, g in enumerate(c.gates)}
+        # gate per row: mostly arithmetic (and Poseidon), a few of the others; row 0 is the public-input gate
+        if poseidon:
+            row_gate = rng.choice([idx["NoopGate"], idx["ConstantGate"], idx["ArithmeticGate"], idx["PoseidonGate"]],
+                                  size=n, p=[0.2, 0.1, 0.3, 0.4])
+        else:
+            row_gate = rng.choice([idx["NoopGate"], idx["ConstantGate"], idx["ArithmeticGate"]], size=n, p=[0.2, 0.1, 0.7])
         row_gate[0] = idx["PublicInputGate"]
         self.row_gate = row_gate
         # constants: selector polynomials (selectors.rs:141-159), then the gate constants
@@ -110,6 +119,13 @@ class SynthCircuit:
             for o in range(num_ops):
                 m0, m1, ad = wires[4 * o][arith_rows], wires[4 * o + 1][arith_rows], wires[4 * o + 2][arith_rows]
                 wires[4 * o + 3][arith_rows] = _addmod(_mulmod(_mulmod(m0, m1), c0), _mulmod(ad, c1))
+        # Poseidon rows: inputs and swap are free, everything else follows (PoseidonGenerator)
+        if poseidon:
+            pg = plonk.PoseidonGate()
+            for r in np.nonzero(row_gate == idx["PoseidonGate"])[0]:
+                row = pg.generate([int(wires[i, r]) for i in range(12)], int(rng.integers(0, 2)))
+                for w, v in row.items():
+                    wires[w, r] = v
         self.wires = wires
         # sigma polynomials' values: k_is[col] * w^row  (circuit_builder.rs sigma_vecs)
         w = oracle.lib().orc_gl_primitive_root(degree_bits)

@@ -46,9 +46,12 @@ def test_partial_products_and_zs_match_oracle(qp, ctx, degree_bits, qdf, nc):
     circ.free()
 
 
-@pytest.mark.parametrize("degree_bits,qdf,nc", [(5, 8, 2), (9, 8, 2), (10, 4, 2), (11, 8, 1), (12, 8, 2)])
-def test_quotient_polys_match_oracle(qp, ctx, degree_bits, qdf, nc):
-    sc = SynthCircuit(degree_bits, seed=20 + degree_bits, quotient_degree_factor=qdf, num_challenges=nc)
+@pytest.mark.parametrize("degree_bits,qdf,nc,poseidon", [(5, 8, 2, False), (9, 8, 2, False), (10, 4, 2, False),
+                                                          (11, 8, 1, False), (12, 8, 2, False), (6, 8, 2, True),
+                                                          (10, 8, 2, True)])
+def test_quotient_polys_match_oracle(qp, ctx, degree_bits, qdf, nc, poseidon):
+    sc = SynthCircuit(degree_bits, seed=20 + degree_bits, quotient_degree_factor=qdf, num_challenges=nc,
+                      poseidon=poseidon)
     c = sc.common
     betas, gammas, alphas = (a[:nc] for a in challenges(70 + degree_bits))
     zs = sc.oracle_circuit.partial_products_and_zs(sc.wires, sc.sigmas, betas, gammas)
@@ -108,14 +111,15 @@ def test_large_circuit_verifier_identity(qp, ctx):
                                        alphas, x0)
 
 
-@pytest.mark.parametrize("degree_bits,qdf,pow_bits,queries", [(6, 8, 6, 4), (9, 8, 16, 28), (8, 4, 10, 7), (11, 8, 16, 28)])
-def test_full_proof_bytes_match_oracle(qp, ctx, degree_bits, qdf, pow_bits, queries):
+@pytest.mark.parametrize("degree_bits,qdf,pow_bits,queries,poseidon", [
+    (6, 8, 6, 4, False), (9, 8, 16, 28, False), (8, 4, 10, 7, False), (11, 8, 16, 28, False), (10, 8, 16, 28, True)])
+def test_full_proof_bytes_match_oracle(qp, ctx, degree_bits, qdf, pow_bits, queries, poseidon):
     """prove_with_partition_witness (plonky2/src/plonk/prover.rs:176-398) end to end on the device,
     serialised like write_proof_with_public_inputs -- byte for byte against the oracle's prove()."""
     from oracle import prover as oprover
     from qp_plonky2_b200 import prover
 
-    sc = SynthCircuit(degree_bits, seed=60 + degree_bits, quotient_degree_factor=qdf)
+    sc = SynthCircuit(degree_bits, seed=60 + degree_bits, quotient_degree_factor=qdf, poseidon=poseidon)
     c = sc.common
     circ = plonk.Circuit(ctx, c, sc.sigmas)
     cfg = prover.FriConfig(c.rate_bits, c.cap_height, pow_bits, 4, 5, queries)
@@ -141,7 +145,7 @@ def test_large_proof_openings_pass_the_verifier(qp, ctx):
     from qp_plonky2_b200 import prover
     from synth_circuit import verifier_plonk_identity
 
-    sc = SynthCircuit(15, seed=77)
+    sc = SynthCircuit(15, seed=77, poseidon=True)
     c = sc.common
     circ = plonk.Circuit(ctx, c, sc.sigmas)
     pd = prover.ProverData(ctx, circ, sc.constants_sigmas())

@@ -37,8 +37,12 @@ def run_program(code, pool, n_regs, wires, consts, pih, alphas):
             r[dst] = (r[a] - r[b]) % P
         elif op == plonk.OP_MUL:
             r[dst] = r[a] * r[b] % P
-        elif op == plonk.OP_EMIT:
-            h = [(h[c] * int(alphas[c]) + r[a]) % P for c in range(nc)]
+        elif op == plonk.OP_MULI:
+            r[dst] = r[a] * int(pool[b]) % P
+        elif op == plonk.OP_ADDI:
+            r[dst] = (r[a] + int(pool[b])) % P
+        elif op == plonk.OP_EMIT:   # constraint index in b
+            h = [(h[c] + r[a] * pow(int(alphas[c]), b, P)) % P for c in range(nc)]
         elif op == plonk.OP_GATE:
             G = [(G[c] + r[a] * h[c]) % P for c in range(nc)]
             h = [0] * nc
@@ -58,20 +62,24 @@ def test_selectors_info_matches_reference_rule(qdf):
     assert c.num_partial_products == -(-80 // qdf) - 1
 
 
-@pytest.mark.parametrize("qdf", [8, 4])
-def test_constraint_program_matches_oracle_gate_evaluation(qdf):
+@pytest.mark.parametrize("qdf,poseidon", [(8, False), (4, False), (8, True)])
+def test_constraint_program_matches_oracle_gate_evaluation(qdf, poseidon):
     """The compiled program and the oracle's hand-written gate evaluators agree on random
     (non-satisfying) inputs: compare the full vanishing value with the permutation terms zeroed
     out by Z = partial products = 0... simpler: both sides computed in full."""
-    sc = SynthCircuit(5, seed=5, quotient_degree_factor=qdf)
+    sc = SynthCircuit(5, seed=5, quotient_degree_factor=qdf, poseidon=poseidon)
     c = sc.common
     code, pool, n_regs = c.constraint_program()
+    if poseidon:   # degree 7 forces a second selector group (selectors.rs:140-150)
+        assert c.groups == [(0, 4), (4, 5)] and c.num_gate_constraints == 123
     rng = np.random.default_rng(7)
     for trial in range(8):
         wires = oracle.rand_felts((c.num_wires,), 100 + trial)
         consts = oracle.rand_felts((c.num_constants,), 200 + trial)
         # a selector value that is a real gate index some of the time
         consts[0] = rng.integers(0, 4)
+        if poseidon and trial % 2:
+            consts[0], consts[1] = plonk.UNUSED_SELECTOR, 4
         pih = oracle.rand_felts((4,), 300 + trial)
         alphas = oracle.rand_felts((2,), 400 + trial)
         nc, np_ = c.num_challenges, c.num_partial_products
@@ -92,9 +100,9 @@ def test_constraint_program_matches_oracle_gate_evaluation(qdf):
             assert G[a] * pow(int(alphas[a]), base, P) % P == want
 
 
-@pytest.mark.parametrize("degree_bits,qdf", [(7, 8), (6, 4)])
-def test_oracle_quotient_satisfies_verifier_identity(degree_bits, qdf):
-    sc = SynthCircuit(degree_bits, seed=11, quotient_degree_factor=qdf)
+@pytest.mark.parametrize("degree_bits,qdf,poseidon", [(7, 8, False), (6, 4, False), (6, 8, True)])
+def test_oracle_quotient_satisfies_verifier_identity(degree_bits, qdf, poseidon):
+    sc = SynthCircuit(degree_bits, seed=11, quotient_degree_factor=qdf, poseidon=poseidon)
     c = sc.common
     cs = oracle.PolynomialBatch.from_values(sc.constants_sigmas(), c.rate_bits, c.cap_height)
     wb = oracle.PolynomialBatch.from_values(sc.wires, c.rate_bits, c.cap_height)
@@ -143,13 +151,13 @@ def _oracle_prove(sc, **kw):
                          cap_height=c.cap_height, **kw)
 
 
-@pytest.mark.parametrize("degree_bits,qdf", [(6, 8), (7, 4)])
-def test_oracle_proof_openings_satisfy_the_verifier(degree_bits, qdf):
+@pytest.mark.parametrize("degree_bits,qdf,poseidon", [(6, 8, False), (7, 4, False), (6, 8, True)])
+def test_oracle_proof_openings_satisfy_the_verifier(degree_bits, qdf, poseidon):
     """Full oracle prove(): the opening set inside the proof passes the verifier's algebraic check
     at the Fiat-Shamir point zeta in F_p^2 (verifier/src/plonk/verifier.rs:60-100)."""
     from synth_circuit import verifier_plonk_identity
 
-    sc = SynthCircuit(degree_bits, seed=41, quotient_degree_factor=qdf)
+    sc = SynthCircuit(degree_bits, seed=41, quotient_degree_factor=qdf, poseidon=poseidon)
     proof, info = _oracle_prove(sc, proof_of_work_bits=6, num_query_rounds=4)
     assert verifier_plonk_identity(sc.common, info["openings"], info["zeta"], info["betas"], info["gammas"],
                                    info["alphas"], info["pih"])

@@ -19,7 +19,7 @@ import qp_plonky2_b200 as qp  # noqa: E402
 from qp_plonky2_b200 import plonk, prover  # noqa: E402
 
 
-def measure(degrees, cpu_degrees=(), reps=5, device=0, verbose=True):
+def measure(degrees, cpu_degrees=(), reps=5, device=0, verbose=True, poseidon=True):
     """-> list of per-degree records (ms = best of reps - 1 timed runs after one warm-up)."""
     import torch
     from synth_circuit import SynthCircuit
@@ -31,7 +31,7 @@ def measure(degrees, cpu_degrees=(), reps=5, device=0, verbose=True):
     ctx = qp.Context(device, max_lde_log=max(a.degrees) + 3)
     out = {"prove": []}
     for lg in a.degrees:
-        sc = SynthCircuit(lg, seed=lg)
+        sc = SynthCircuit(lg, seed=lg, poseidon=poseidon)
         c = sc.common
         circ = plonk.Circuit(ctx, c, sc.sigmas)
         pd = prover.ProverData(ctx, circ, sc.constants_sigmas())
@@ -46,7 +46,8 @@ def measure(degrees, cpu_degrees=(), reps=5, device=0, verbose=True):
             nbytes = len(proof)
             if rep and (best is None or ms < best):
                 best, best_t = ms, t
-        rec = {"degree_bits": lg, "num_wires": c.num_wires, "ms": best, "proof_bytes": nbytes, "scopes_ms": best_t,
+        rec = {"degree_bits": lg, "num_wires": c.num_wires, "gates": [g.id().split(" ")[0].split("(")[0] for g in c.gates],
+               "ms": best, "proof_bytes": nbytes, "scopes_ms": best_t,
                "witness": "device-resident"}
         if lg in a.cpu:
             import oracle
@@ -70,11 +71,12 @@ def measure(degrees, cpu_degrees=(), reps=5, device=0, verbose=True):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--degrees", type=int, nargs="*", default=[12, 13, 14, 16, 18])
+    ap.add_argument("--degrees", type=int, nargs="*", default=[12, 13, 14, 16])
     ap.add_argument("--cpu", type=int, nargs="*", default=[12])
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--no-poseidon", action="store_true")
     a = ap.parse_args()
-    print(json.dumps({"prove": measure(a.degrees, a.cpu, a.reps)}))
+    print(json.dumps({"prove": measure(a.degrees, a.cpu, a.reps, poseidon=not a.no_poseidon)}))
 
 
 if __name__ == "__main__":
