@@ -16,6 +16,10 @@
 #ifndef QP_POSEIDON_EXPLICIT_MUL
 #define QP_POSEIDON_EXPLICIT_MUL 0
 #endif
+// 1: the two squarings of x^7 use three IMAD.WIDE (cross term doubled) instead of the compiler's four
+#ifndef QP_POSEIDON_SQR_HV   // measured on B200: leaf hash 25.69 -> 25.44 ms at 2^21 leaves x 135
+#define QP_POSEIDON_SQR_HV 1
+#endif
 
 namespace gl {
 
@@ -280,7 +284,12 @@ __device__ __forceinline__ uint64_t sqr_hv(uint64_t a) {
 
 // x^7 (core/src/poseidon.rs:546-552)
 __device__ __forceinline__ uint64_t pow7(uint64_t x) {
-#if QP_POSEIDON_EXPLICIT_MUL
+#if QP_POSEIDON_SQR_HV
+    uint64_t x2 = sqr_hv(x);
+    uint64_t x4 = sqr_hv(x2);
+    uint64_t x3 = mul(x, x2);
+    return mul(x3, x4);
+#elif QP_POSEIDON_EXPLICIT_MUL
     uint64_t x2 = sqr_hv(x);
     uint64_t x4 = sqr_hv(x2);
     uint64_t x3 = mul_hv(x, x2);

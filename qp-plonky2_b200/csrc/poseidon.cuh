@@ -65,6 +65,8 @@ __constant__ uint64_t c_rc[WIDTH * (N_ROUNDS + 1)];
 //   c_pair_k[g]        rc'_0                      (rc', rc'' = constants of the two rounds
 //   c_pair_K[g][0..11] M rc' + rc''                FOLLOWING the pair's first round)
 __constant__ double c_rc_d[WIDTH * (N_ROUNDS + 1)][2];
+// c_rc_dd[6 * round + r] = c_rc_d[12 * round + r + 6] - c_rc_d[12 * round + r]   (split layer, below)
+__constant__ double c_rc_dd[6 * (N_ROUNDS + 1)][2];
 __constant__ uint64_t c_pair_k[N_PARTIAL_PAIRS];
 __constant__ uint64_t c_pair_K[N_PARTIAL_PAIRS][WIDTH];
 __constant__ double c_pair_k_d[N_PARTIAL_PAIRS][2];
@@ -100,6 +102,10 @@ static inline cudaError_t upload_constants(cudaStream_t stream) {
         out[1] = 4503599627370496.0 + (double)(uint32_t)(c >> 32) + (double)((1ULL << 32) - K);
     };
     for (int i = 0; i < WIDTH * (N_ROUNDS + 1); i++) split(rc[i], rcd[i]);
+    static double rcdd[6 * (N_ROUNDS + 1)][2];
+    for (int r = 0; r <= N_ROUNDS; r++)
+        for (int i = 0; i < 6; i++)
+            for (int k = 0; k < 2; k++) rcdd[6 * r + i][k] = rcd[12 * r + i + 6][k] - rcd[12 * r + i][k];  // exact
     for (int g = 0; g < N_PARTIAL_PAIRS; g++) {
         const int r = 4 + 2 * g;
         const uint64_t* r1 = rc + 12 * (r + 1);
@@ -115,6 +121,7 @@ static inline cudaError_t upload_constants(cudaStream_t stream) {
     }
     cudaError_t e = cudaMemcpyToSymbolAsync(c_rc, rc, sizeof rc, 0, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_rc_d, rcd, sizeof rcd, 0, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_rc_dd, rcdd, sizeof rcdd, 0, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_pair_k, pk, sizeof pk, 0, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_pair_K, pK, sizeof pK, 0, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_pair_k_d, pkd, sizeof pkd, 0, cudaMemcpyHostToDevice, stream);
@@ -194,6 +201,54 @@ __device__ __forceinline__ uint64_t fold_row_f64(double al, double ah) {
         al = fma(dl[k_], (double)MAT.a[R][k_], al);              \
         ah = fma(dh[k_], (double)MAT.a[R][k_], ah);              \
     }
+
+// Full-round linear layer with the circulant split by the CRT  z^12 - 1 = (z^6 - 1)(z^6 + 1):
+// with u = x[0..6) + x[6..12), v = x[0..6) - x[6..12),
+//     P_r = sum_j c+_j u[(j + r) mod 6]              (cyclic,     c+_j = (c_j + c_{j+6}) / 2)
+//     Q_r = sum_j c-_j s(j + r) v[(j + r) mod 6]     (negacyclic, c-_j = (c_j - c_{j+6}) / 2, s = -1 on wrap)
+//     y_r = P_r + Q_r,   y_{r+6} = P_r - Q_r          (r < 6)
+// Every c_j + c_{j+6} and c_j - c_{j+6} of this MDS matrix is even, so the halved coefficients
+// (15,14,40,17,18,24) and (2,1,1,-1,-16,4) are integers and everything stays exact: 103 FP64
+// operations per plane instead of 144.  P_r starts at the constant of row r; row r + 6 adds the
+// difference of the two constants (exact: both are 2^52 + a 33-bit integer).
+#ifndef QP_POSEIDON_MDS_SPLIT
+#define QP_POSEIDON_MDS_SPLIT 1
+#endif
+__device__ __forceinline__ void mds_layer_split(uint64_t (&s)[12], int round) {
+    constexpr double CP[6] = {15, 14, 40, 17, 18, 24};
+    constexpr double CM[6] = {2, 1, 1, -1, -16, 4};
+    uint32_t w[2][12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) gl::unpack(s[i], w[0][i], w[1][i]);
+    double y[2][12];
+#pragma unroll
+    for (int pl = 0; pl < 2; pl++) {
+        double d[12], u[6], v[6];
+#pragma unroll
+        for (int i = 0; i < 12; i++) d[i] = f64::from_u32(w[pl][i]);
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            u[j] = d[j] + d[j + 6];
+            v[j] = d[j] - d[j + 6];
+        }
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            double P = c_rc_d[12 * round + r][pl];
+            double Q = v[r] * CM[0];
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                const int idx = (j + r) % 6;
+                P = fma(u[idx], CP[j], P);
+                if (j > 0) Q = fma(v[idx], (j + r < 6) ? CM[j] : -CM[j], Q);
+            }
+            y[pl][r] = P + Q;
+            y[pl][r + 6] = (P - Q) + c_rc_dd[6 * round + r][pl];
+        }
+        y[pl][0] = fma(d[0], 8.0, y[pl][0]);  // the diagonal entry of row 0
+    }
+#pragma unroll
+    for (int r = 0; r < 12; r++) s[r] = fold_row_f64(y[0][r], y[1][r]);
+}
 
 // state <- M * state + rc[ri .. ri+12)   (ri = 12 * round)
 __device__ __forceinline__ void mds_layer_f64(uint64_t (&s)[12], int ri) {
@@ -278,10 +333,11 @@ __device__ __forceinline__ void partial_pair_f64(uint64_t (&s)[12], int g) {
     }
 }
 
-// S-box layer as 12/L iterations x L lanes with a register rotation: smaller code wins until the
-// rotation moves cost more than the instruction fetches they save (measured best on B200: L = 6).
+// S-box layer as 12/L iterations x L lanes with a register rotation (smaller code) -- with the
+// linear layers on the FP64 pipe the code fits the instruction cache fully unrolled, and L = 12 (no
+// rotation moves) is the measured best on B200 (leaf hash at 2^21 x 135: L = 6 25.46 ms, L = 12 25.06 ms).
 #ifndef QP_POSEIDON_SBOX_ROT
-#define QP_POSEIDON_SBOX_ROT 6
+#define QP_POSEIDON_SBOX_ROT 12
 #endif
 
 // S-box layer on all 12 lanes (poseidon.rs:554-562)
@@ -321,7 +377,11 @@ __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
         for (int r = base; r < base + 4; r++) {
             if (SYNC) __syncthreads();
             sbox_all(s);
-            mds_layer_f64(s, 12 * (r + 1));  // row 30 is zero
+#if QP_POSEIDON_MDS_SPLIT
+            mds_layer_split(s, r + 1);       // row 30 is zero
+#else
+            mds_layer_f64(s, 12 * (r + 1));
+#endif
         }
         if (half == 0) {
             // 22 partial rounds (poseidon.rs:623-628) as 11 fused pairs
