@@ -229,6 +229,15 @@ typedef struct {
 typedef struct qp_circuit qp_circuit;
 int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* desc, qp_circuit** out);
 void qp_circuit_free(qp_circuit* c);
+/* The scalar fields the circuit was created with (pointers are NULL). */
+int qp_circuit_describe(const qp_circuit* c, qp_circuit_desc* out);
+int qp_circuit_has_sigmas(const qp_circuit* c);
+/* Stream-ordered device scratch ([n_words] u64) for host-side drivers that keep intermediate
+ * polynomials on the device between calls (qp_prove). */
+int qp_dev_alloc(qp_ctx* ctx, size_t n_words, uint64_t** out);
+void qp_dev_free(qp_ctx* ctx, uint64_t* p);
+/* Copy n_words u64 between host and device buffers on the context's stream (synchronous). */
+int qp_memcpy(qp_ctx* ctx, uint64_t* dst, int dst_space, const uint64_t* src, int src_space, size_t n_words);
 /* all_wires_permutation_partial_products (plonky2/src/plonk/prover.rs:402-480) followed by the
  * Z-first ordering of prover.rs:255-261.  wires: witness columns [>= num_routed_wires][n] (values on
  * H); betas, gammas: [num_challenges] (host).  out: [(nc + nc * num_partial_products)][n] value

@@ -68,6 +68,54 @@ int qp_fri_proof(qp_ctx* ctx, const qp_batch* const* initial_oracles, size_t n_o
                  unsigned n_rounds, unsigned proof_of_work_bits, unsigned num_query_rounds, uint8_t* out,
                  size_t capacity, size_t* len_out);
 
+/* ---- circuit data for the quotient (plonky2/src/plonk/circuit_data.rs:412-470) ---------------- */
+/* The gates of a circuit, compiled on the host into the constraint program of qp_circuit_desc
+ * (qp_plonky2_b200.h): gates are sorted by (degree, id) like CircuitBuilder::build does
+ * (circuit_builder.rs:1177-1179), grouped into selector polynomials (gates/selectors.rs:99-166,
+ * max_degree = quotient_degree_factor + 1), filtered (gates/gate.rs:326-333) and evaluated
+ * symbolically (Gate::eval_unfiltered of gates/{noop,constant,public_input,arithmetic_base,poseidon}.rs). */
+enum { QP_GATE_NOOP = 0, QP_GATE_CONSTANT = 1, QP_GATE_PUBLIC_INPUT = 2, QP_GATE_ARITHMETIC = 3, QP_GATE_POSEIDON = 4 };
+typedef struct {
+    uint32_t kind;   /* QP_GATE_* */
+    uint32_t param;  /* ConstantGate: num_consts; ArithmeticGate: num_ops; otherwise 0 */
+} qp_gate_desc;
+typedef struct qp_program qp_program;
+int qp_program_create(const qp_gate_desc* gates, size_t n_gates, unsigned max_degree, qp_program** out);
+void qp_program_free(qp_program* p);
+size_t qp_program_code(const qp_program* p, const uint64_t** code);
+size_t qp_program_pool(const qp_program* p, const uint64_t** pool);
+unsigned qp_program_regs(const qp_program* p);
+unsigned qp_program_num_selectors(const qp_program* p);        /* SelectorsInfo::num_selectors */
+unsigned qp_program_num_gate_constants(const qp_program* p);   /* max over gates of num_constants */
+unsigned qp_program_num_gate_constraints(const qp_program* p); /* common_data.num_gate_constraints */
+/* Gate at position `sorted_index` of common_data.gates: its index in the caller's list, its
+ * selector polynomial and that selector's group range (SelectorsInfo). */
+int qp_program_gate(const qp_program* p, unsigned sorted_index, unsigned* original_index,
+                    unsigned* selector_index, unsigned* group_start, unsigned* group_end);
+
+/* ---- prove (plonky2/src/plonk/prover.rs:176-398) ------------------------------------------------ */
+/* hash_no_pad (core/src/hashing.rs:68-95) on the host: public-input hash, circuit digest. */
+void qp_hash_no_pad(const uint64_t* elems, size_t n, uint64_t out[4]);
+/* circuit_digest (circuit_builder.rs:1289-1303) for an empty domain separator. */
+void qp_circuit_digest(const uint64_t* constants_sigmas_cap, size_t cap_len, unsigned degree_bits, uint64_t out[4]);
+
+typedef struct {
+    uint32_t rate_bits, cap_height, proof_of_work_bits, num_query_rounds; /* FriConfig, core/src/fri.rs */
+    uint32_t arity_bits, final_poly_bits;                                  /* ConstantArityBits(arity_bits, final_poly_bits) */
+    uint32_t quotient_degree_factor;
+} qp_prover_config;
+
+/* prove_with_partition_witness from the full witness on, serialised like
+ * write_proof_with_public_inputs (plonky2/src/util/serialization/mod.rs:2040-2079).  `wires`:
+ * witness matrix [num_wires][n] (host or device); the circuit must have been created with sigmas.
+ * No lookups, no blinding; PoW witness = smallest valid one.  Two-call protocol: with out == NULL only
+ * *len_out (an upper bound of the proof size) is written.  timing_ms (optional, 7 entries) receives the
+ * reference's TimingTree scopes: wires commitment, partial products, their commitment, quotient polys,
+ * quotient commitment, opening set, opening proofs. */
+int qp_prove(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* constants_sigmas, const uint64_t circuit_digest[4],
+             const qp_prover_config* cfg, const uint64_t* wires, int space, const uint64_t* public_inputs,
+             size_t n_public_inputs, uint8_t* out, size_t capacity, size_t* len_out, double* timing_ms);
+
 #ifdef __cplusplus
 }
 #endif

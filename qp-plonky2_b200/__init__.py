@@ -33,6 +33,8 @@ _SOURCES = [
               "merkle.cuh", "fri.cuh", "openings.cuh", "quotient.cuh")
 ] + [
     os.path.join(_HERE, "host", "transcript.cpp"),
+    os.path.join(_HERE, "host", "plonk_host.cpp"),
+    os.path.join(_HERE, "host", "prover.cpp"),
     os.path.join(_ROOT, "include", "qp_plonky2_b200.h"),
     os.path.join(_ROOT, "include", "qp_plonky2_host.h"),
 ]
@@ -73,6 +75,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
         "-Xcompiler", "-fPIC", "-shared", "-o", LIB_PATH,
         os.path.join(_HERE, "csrc", "qp_plonky2.cu"), os.path.join(_HERE, "host", "transcript.cpp"),
+        os.path.join(_HERE, "host", "plonk_host.cpp"), os.path.join(_HERE, "host", "prover.cpp"),
     ]
     if verbose:
         print(" ".join(cmd))
@@ -176,6 +179,24 @@ def lib():
         "qp_circuit_free": (None, [vp]),
         "qp_circuit_partial_products_and_zs": (i32, [vp, vp, i32, vp, vp, vp, i32]),
         "qp_circuit_compute_quotient_polys": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]),
+        "qp_circuit_describe": (i32, [vp, vp]),
+        "qp_circuit_has_sigmas": (i32, [vp]),
+        "qp_dev_alloc": (i32, [vp, sz, pp]),
+        "qp_dev_free": (None, [vp, vp]),
+        "qp_memcpy": (i32, [vp, vp, i32, vp, i32, sz]),
+        # host side of the quotient / prove (include/qp_plonky2_host.h)
+        "qp_program_create": (i32, [vp, sz, u32, pp]),
+        "qp_program_free": (None, [vp]),
+        "qp_program_code": (sz, [vp, pp]),
+        "qp_program_pool": (sz, [vp, pp]),
+        "qp_program_regs": (u32, [vp]),
+        "qp_program_num_selectors": (u32, [vp]),
+        "qp_program_num_gate_constants": (u32, [vp]),
+        "qp_program_num_gate_constraints": (u32, [vp]),
+        "qp_program_gate": (i32, [vp, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
+        "qp_hash_no_pad": (None, [vp, sz, vp]),
+        "qp_circuit_digest": (None, [vp, sz, u32, vp]),
+        "qp_prove": (i32, [vp, vp, vp, vp, vp, vp, i32, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

@@ -1602,6 +1602,32 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
     return QP_OK;
 }
 
+extern "C" int qp_circuit_describe(const qp_circuit* c, qp_circuit_desc* out) {
+    if (!c || !out) return QP_ERR_BAD_ARG;
+    *out = c->d;  // scalar fields; the pointers were cleared at creation
+    return QP_OK;
+}
+extern "C" int qp_circuit_has_sigmas(const qp_circuit* c) { return c && c->sigmas ? 1 : 0; }
+
+// Stream-ordered device scratch for host-side drivers that keep intermediates on the device.
+extern "C" int qp_dev_alloc(qp_ctx* ctx, size_t n_words, uint64_t** out) {
+    if (!ctx || !out) return QP_ERR_BAD_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return dev_alloc(ctx, out, n_words);
+}
+extern "C" void qp_dev_free(qp_ctx* ctx, uint64_t* p) {
+    if (ctx && p) dev_free(ctx, p);
+}
+extern "C" int qp_memcpy(qp_ctx* ctx, uint64_t* dst, int dst_space, const uint64_t* src, int src_space, size_t n_words) {
+    if (!ctx || (n_words && (!dst || !src))) return QP_ERR_BAD_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, n_words * 8, cudaMemcpyDefault, ctx->stream));
+    (void)dst_space;
+    (void)src_space;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return QP_OK;
+}
+
 extern "C" void qp_circuit_free(qp_circuit* c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);

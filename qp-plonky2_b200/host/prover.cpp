@@ -1,0 +1,288 @@
+// prove_with_partition_witness from the full witness on (plonky2/src/plonk/prover.rs:176-398), as a
+// host driver over the device entry points of qp_plonky2_b200.h and the host transcript.  Every
+// polynomial-sized step runs on the device; this file only sequences them, feeds the Fiat-Shamir
+// transcript (serial, host: core/src/challenger.rs) and lays out the proof bytes
+// (write_proof_with_public_inputs, plonky2/src/util/serialization/mod.rs:2040-2079).
+#include <chrono>
+#include <cstring>
+#include <vector>
+
+#include "../../include/qp_plonky2_host.h"
+
+namespace {
+
+typedef unsigned __int128 u128;
+constexpr uint64_t P = 0xFFFFFFFF00000001ULL;
+constexpr uint64_t W = 7;  // F_p^2 = F_p[X]/(X^2 - 7), field/src/goldilocks_extensions.rs:13-26
+
+struct Ext {
+    uint64_t a, b;
+};
+inline uint64_t fmul(uint64_t x, uint64_t y) { return (uint64_t)(((u128)x * y) % P); }
+inline uint64_t fadd(uint64_t x, uint64_t y) { return (uint64_t)(((u128)x + y) % P); }
+inline Ext emul(Ext x, Ext y) {  // field/src/extension/quadratic.rs:186-199
+    return Ext{fadd(fmul(x.a, y.a), fmul(W, fmul(x.b, y.b))), fadd(fmul(x.a, y.b), fmul(x.b, y.a))};
+}
+inline uint64_t fpow(uint64_t x, uint64_t e) {
+    uint64_t r = 1;
+    for (; e; e >>= 1, x = fmul(x, x))
+        if (e & 1) r = fmul(r, x);
+    return r;
+}
+
+void put_u64s(std::vector<uint8_t>& out, const uint64_t* v, size_t n) {  // little-endian canonical u64
+    const size_t at = out.size();
+    out.resize(at + 8 * n);
+    for (size_t i = 0; i < n; i++) {
+        uint64_t x = v[i] % P;
+        for (int k = 0; k < 8; k++) out[at + 8 * i + k] = (uint8_t)(x >> (8 * k));
+    }
+}
+
+struct Timer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double lap(qp_ctx* ctx) {
+        qp_ctx_synchronize(ctx);
+        auto t1 = std::chrono::steady_clock::now();
+        double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        t0 = t1;
+        return ms;
+    }
+};
+
+}  // namespace
+
+extern "C" void qp_hash_no_pad(const uint64_t* elems, size_t n, uint64_t out[4]) {
+    // hash_no_pad = overwrite-mode sponge, rate 8 (core/src/hashing.rs:68-95): exactly what the
+    // challenger's duplex does with its input buffer, so reuse it.
+    qp_challenger c;
+    qp_challenger_init(&c);
+    uint64_t state[12] = {0};
+    for (size_t i = 0; i < n; i += 8) {
+        const size_t k = n - i < 8 ? n - i : 8;
+        std::memcpy(c.sponge_state, state, sizeof state);
+        c.n_in = 0;
+        qp_challenger_observe(&c, elems + i, k);  // a full chunk permutes here ...
+        if (k < 8) (void)qp_challenger_get(&c);    // ... a short one when a challenge is drawn
+        std::memcpy(state, c.sponge_state, sizeof state);
+        c.n_out = 0;
+    }
+    for (int i = 0; i < 4; i++) out[i] = state[i] % P;
+}
+
+extern "C" void qp_circuit_digest(const uint64_t* cap, size_t cap_len, unsigned degree_bits, uint64_t out[4]) {
+    // circuit_builder.rs:1289-1303 with domain_separator = [] ; hash_pad([]) pads to [1,0,0,0,0,0,0,1]
+    const uint64_t pad[8] = {1, 0, 0, 0, 0, 0, 0, 1};
+    uint64_t ds[4];
+    qp_hash_no_pad(pad, 8, ds);
+    std::vector<uint64_t> v(cap, cap + 4 * cap_len);
+    v.insert(v.end(), ds, ds + 4);
+    v.push_back(degree_bits);
+    qp_hash_no_pad(v.data(), v.size(), out);
+}
+
+extern "C" int qp_prove(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* constants_sigmas,
+                        const uint64_t circuit_digest[4], const qp_prover_config* cfg, const uint64_t* wires,
+                        int space, const uint64_t* public_inputs, size_t n_public_inputs, uint8_t* out,
+                        size_t capacity, size_t* len_out, double* timing_ms) {
+    if (!ctx || !circuit || !constants_sigmas || !circuit_digest || !cfg || !len_out) return QP_ERR_BAD_ARG;
+    qp_circuit_desc d;
+    int rc = qp_circuit_describe(circuit, &d);
+    if (rc) return rc;
+    const unsigned nc = d.num_challenges, np = d.num_partial_products, qdf = cfg->quotient_degree_factor;
+    const size_t n = (size_t)1 << d.degree_bits;
+    const size_t n_pre = (size_t)d.num_constants + d.num_routed_wires;
+    const size_t n_zs = (size_t)nc * (1 + np), n_q = (size_t)nc * qdf;
+    const size_t cap_words = ((size_t)4) << cfg->cap_height;
+    unsigned arities[64];
+    const unsigned n_rounds = qp_fri_reduction_arity_bits(d.degree_bits, cfg->rate_bits, cfg->cap_height,
+                                                          cfg->arity_bits, cfg->final_poly_bits, arities);
+    const size_t leaf_lens[4] = {n_pre, d.num_wires, n_zs, n_q};
+    const size_t fri_len = qp_fri_proof_len(leaf_lens, 4, d.degree_bits + cfg->rate_bits, cfg->rate_bits,
+                                            cfg->cap_height, arities, n_rounds, cfg->num_query_rounds);
+    const size_t n_open = n_pre + d.num_wires + n_zs + nc + n_q;
+    const size_t total = 8 * (3 * cap_words + 2 * n_open) + fri_len + 8 * (1 + n_public_inputs);
+    *len_out = total;
+    if (!out) return QP_OK;
+    if (capacity < total || !wires || (n_public_inputs && !public_inputs)) return QP_ERR_BAD_ARG;
+    if (!qp_circuit_has_sigmas(circuit)) return QP_ERR_BAD_ARG;
+    if (qdf == 0 || qdf > (1u << d.quotient_degree_bits)) return QP_ERR_BAD_ARG;
+    if (qp_batch_leaf_len(constants_sigmas) < n_pre) return QP_ERR_BAD_ARG;
+
+    Timer tm;
+    double scopes[7] = {0};
+    uint64_t pih[4];
+    qp_hash_no_pad(public_inputs, n_public_inputs, pih);  // prover.rs:185-186
+    qp_batch *wb = nullptr, *zb = nullptr, *qb = nullptr;
+    qp_fri* fri = nullptr;
+    uint64_t *d_zs = nullptr, *d_q = nullptr;
+    std::vector<uint8_t> bytes;
+    bytes.reserve(total);
+    auto cleanup = [&]() {
+        if (fri) qp_fri_free(fri);
+        qp_batch_free(wb);
+        qp_batch_free(zb);
+        qp_batch_free(qb);
+        qp_dev_free(ctx, d_zs);
+        qp_dev_free(ctx, d_q);
+    };
+#define QP_STEP(expr)            \
+    do {                         \
+        rc = (expr);             \
+        if (rc) {                \
+            cleanup();           \
+            return rc;           \
+        }                        \
+    } while (0)
+
+    // wires commitment, prover.rs:201-214
+    QP_STEP(qp_batch_from_values(ctx, wires, space, d.num_wires, d.degree_bits, cfg->rate_bits, 0, cfg->cap_height,
+                                 nullptr, 0, 1u << cfg->rate_bits, &wb));
+    scopes[0] = tm.lap(ctx);
+    // transcript, prover.rs:216-234; FriParams::observe core/src/fri.rs:289-321
+    qp_challenger ch;
+    qp_challenger_init(&ch);
+    {
+        std::vector<uint64_t> v = {cfg->rate_bits, cfg->cap_height, cfg->proof_of_work_bits,
+                                   1, cfg->arity_bits, cfg->final_poly_bits,  // ConstantArityBits::serialize
+                                   cfg->num_query_rounds, 0 /* leaf_hiding */, d.degree_bits};
+        for (unsigned i = 0; i < n_rounds; i++) v.push_back(arities[i]);
+        qp_challenger_observe(&ch, v.data(), v.size());
+    }
+    qp_challenger_observe(&ch, circuit_digest, 4);
+    qp_challenger_observe(&ch, pih, 4);
+    std::vector<uint64_t> cap(cap_words);
+    QP_STEP(qp_batch_cap(wb, cap.data(), QP_HOST));
+    qp_challenger_observe(&ch, cap.data(), cap_words);
+    put_u64s(bytes, cap.data(), cap_words);
+    std::vector<uint64_t> betas(nc), gammas(nc), alphas(nc);
+    for (auto& b : betas) b = qp_challenger_get(&ch);
+    for (auto& g : gammas) g = qp_challenger_get(&ch);
+    // Z and partial products (prover.rs:250-261), kept on the device
+    QP_STEP(qp_dev_alloc(ctx, n_zs * n, &d_zs));
+    QP_STEP(qp_circuit_partial_products_and_zs(circuit, wires, space, betas.data(), gammas.data(), d_zs, QP_DEVICE));
+    scopes[1] = tm.lap(ctx);
+    QP_STEP(qp_batch_from_values(ctx, d_zs, QP_DEVICE, n_zs, d.degree_bits, cfg->rate_bits, 0, cfg->cap_height, nullptr,
+                                 0, 1u << cfg->rate_bits, &zb));
+    scopes[2] = tm.lap(ctx);
+    QP_STEP(qp_batch_cap(zb, cap.data(), QP_HOST));
+    qp_challenger_observe(&ch, cap.data(), cap_words);
+    put_u64s(bytes, cap.data(), cap_words);
+    for (auto& a : alphas) a = qp_challenger_get(&ch);
+    // quotient polynomials (prover.rs:293-320): coefficients [nc][n << qdb] on the device
+    const size_t n_lde = n << d.quotient_degree_bits;
+    QP_STEP(qp_dev_alloc(ctx, (size_t)nc * n_lde, &d_q));
+    QP_STEP(qp_circuit_compute_quotient_polys(circuit, constants_sigmas, wb, zb, betas.data(), gammas.data(),
+                                              alphas.data(), pih, d_q, QP_DEVICE));
+    scopes[3] = tm.lap(ctx);
+    const uint64_t* d_chunks = d_q;
+    uint64_t* d_trim = nullptr;
+    if (qdf != (1u << d.quotient_degree_bits)) {
+        // trim_to_len(quotient_degree): the tail must be zero ("Quotient has failed, ...")
+        std::vector<uint64_t> host((size_t)nc * n_lde);
+        QP_STEP(qp_memcpy(ctx, host.data(), QP_HOST, d_q, QP_DEVICE, host.size()));
+        std::vector<uint64_t> trimmed((size_t)nc * qdf * n);
+        for (unsigned a = 0; a < nc; a++) {
+            for (size_t i = (size_t)qdf * n; i < n_lde; i++)
+                if (host[a * n_lde + i] % P) {
+                    cleanup();
+                    return QP_ERR_BAD_ARG;
+                }
+            std::memcpy(&trimmed[(size_t)a * qdf * n], &host[a * n_lde], (size_t)qdf * n * 8);
+        }
+        QP_STEP(qp_dev_alloc(ctx, trimmed.size(), &d_trim));
+        rc = qp_memcpy(ctx, d_trim, QP_DEVICE, trimmed.data(), QP_HOST, trimmed.size());
+        if (rc) {
+            qp_dev_free(ctx, d_trim);
+            cleanup();
+            return rc;
+        }
+        d_chunks = d_trim;
+    }
+    rc = qp_batch_from_coeffs(ctx, d_chunks, QP_DEVICE, n_q, d.degree_bits, cfg->rate_bits, 0, cfg->cap_height, nullptr,
+                              0, 1u << cfg->rate_bits, &qb);
+    qp_dev_free(ctx, d_trim);
+    QP_STEP(rc);
+    scopes[4] = tm.lap(ctx);
+    QP_STEP(qp_batch_cap(qb, cap.data(), QP_HOST));
+    qp_challenger_observe(&ch, cap.data(), cap_words);
+    put_u64s(bytes, cap.data(), cap_words);
+    // zeta, prover.rs:338-347
+    const Ext zeta{qp_challenger_get(&ch), qp_challenger_get(&ch)};
+    {
+        Ext z = zeta;
+        for (unsigned i = 0; i < d.degree_bits; i++) z = emul(z, z);
+        if (z.a == 1 && z.b == 0) {  // "Opening point is in the subgroup."
+            cleanup();
+            return QP_ERR_BAD_ARG;
+        }
+    }
+    const uint64_t g = fpow(7277203076849721926ULL, (uint64_t)1 << (32 - d.degree_bits));  // primitive_root_of_unity
+    const Ext zeta_next{fmul(g, zeta.a), fmul(g, zeta.b)};
+    // OpeningSet::new, proof.rs:289-327
+    std::vector<uint64_t> cs_eval(2 * qp_batch_leaf_len(constants_sigmas)), w_eval(2 * (size_t)d.num_wires),
+        z_eval(2 * n_zs), zn_eval(2 * n_zs), q_eval(2 * n_q);
+    const uint64_t pz[2] = {zeta.a, zeta.b}, pzn[2] = {zeta_next.a, zeta_next.b};
+    QP_STEP(qp_batch_eval_polys(constants_sigmas, pz, cs_eval.data()));
+    QP_STEP(qp_batch_eval_polys(wb, pz, w_eval.data()));
+    QP_STEP(qp_batch_eval_polys(zb, pz, z_eval.data()));
+    QP_STEP(qp_batch_eval_polys(zb, pzn, zn_eval.data()));
+    QP_STEP(qp_batch_eval_polys(qb, pz, q_eval.data()));
+    scopes[5] = tm.lap(ctx);
+    // observe_openings(to_fri_openings()), proof.rs:328-368: zeta batch = constants, sigmas, wires,
+    // zs, partial products, quotient polys; zeta_next batch = zs
+    qp_challenger_observe(&ch, cs_eval.data(), 2 * n_pre);
+    qp_challenger_observe(&ch, w_eval.data(), 2 * (size_t)d.num_wires);
+    qp_challenger_observe(&ch, z_eval.data(), 2 * (size_t)nc);
+    qp_challenger_observe(&ch, z_eval.data() + 2 * nc, 2 * (size_t)nc * np);
+    qp_challenger_observe(&ch, q_eval.data(), 2 * n_q);
+    qp_challenger_observe(&ch, zn_eval.data(), 2 * (size_t)nc);
+    // write_opening_set, serialization/mod.rs:1495-1508: constants, sigmas, wires, zs, zs_next,
+    // (lookups: none), partial products, quotient polys
+    put_u64s(bytes, cs_eval.data(), 2 * n_pre);
+    put_u64s(bytes, w_eval.data(), 2 * (size_t)d.num_wires);
+    put_u64s(bytes, z_eval.data(), 2 * (size_t)nc);
+    put_u64s(bytes, zn_eval.data(), 2 * (size_t)nc);
+    put_u64s(bytes, z_eval.data() + 2 * nc, 2 * (size_t)nc * np);
+    put_u64s(bytes, q_eval.data(), 2 * n_q);
+    // prove_openings (fri/oracle.rs:320-358) on get_fri_instance(zeta) (circuit_data.rs:592-612)
+    const Ext alpha{qp_challenger_get(&ch), qp_challenger_get(&ch)};
+    const qp_batch* oracles[4] = {constants_sigmas, wb, zb, qb};
+    std::vector<qp_opening_term> t0, t1;
+    Ext w{1, 0};
+    auto add_terms = [&](std::vector<qp_opening_term>& t, const qp_batch* b, size_t count) {
+        for (size_t i = 0; i < count; i++) {  // reduce_polys: sum_i alpha^i p_i, core/src/reducing.rs:63-72
+            t.push_back(qp_opening_term{b, i, {w.a, w.b}});
+            w = emul(w, alpha);
+        }
+    };
+    add_terms(t0, oracles[0], n_pre);
+    add_terms(t0, oracles[1], d.num_wires);
+    add_terms(t0, oracles[2], n_zs);
+    add_terms(t0, oracles[3], n_q);
+    const Ext shift0 = w;  // shift_poly: alpha^count, reducing.rs:94-97
+    w = Ext{1, 0};
+    add_terms(t1, oracles[2], nc);
+    const Ext shift1 = w;
+    qp_opening_batch ob[2] = {{{zeta.a, zeta.b}, t0.data(), t0.size(), {shift0.a, shift0.b}},
+                              {{zeta_next.a, zeta_next.b}, t1.data(), t1.size(), {shift1.a, shift1.b}}};
+    QP_STEP(qp_fri_begin_from_openings(ctx, ob, 2, d.degree_bits, cfg->rate_bits, cfg->cap_height, &fri));
+    const size_t at = bytes.size();
+    bytes.resize(at + fri_len);
+    size_t got = 0;
+    rc = qp_fri_proof(ctx, oracles, 4, fri, &ch, cfg->rate_bits, cfg->cap_height, arities, n_rounds,
+                      cfg->proof_of_work_bits, cfg->num_query_rounds, bytes.data() + at, fri_len, &got);
+    if (!rc && got != fri_len) rc = QP_ERR_BAD_ARG;
+    QP_STEP(rc);
+    scopes[6] = tm.lap(ctx);
+    // public inputs: u64 length, then the elements (serialization/mod.rs:2077-2078)
+    const uint64_t npi = n_public_inputs;
+    for (int k = 0; k < 8; k++) bytes.push_back((uint8_t)(npi >> (8 * k)));
+    put_u64s(bytes, public_inputs, n_public_inputs);
+    cleanup();
+    if (bytes.size() != total) return QP_ERR_BAD_ARG;
+    std::memcpy(out, bytes.data(), total);
+    if (timing_ms) std::memcpy(timing_ms, scopes, sizeof scopes);
+    return QP_OK;
+#undef QP_STEP
+}

@@ -182,7 +182,13 @@ class ConstraintProgram:
 
 
 # ---- gates ------------------------------------------------------------------------------------------
+GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON = range(5)  # qp_plonky2_host.h
+
+
 class Gate:
+    kind = None   # QP_GATE_* of the native host library
+    param = 0
+
     def id(self):
         raise NotImplementedError
 
@@ -196,6 +202,8 @@ class Gate:
 
 
 class NoopGate(Gate):  # plonky2/src/gates/noop.rs
+    kind = GATE_NOOP
+
     def id(self):
         return "NoopGate"
 
@@ -203,8 +211,10 @@ class NoopGate(Gate):  # plonky2/src/gates/noop.rs
 class ConstantGate(Gate):  # plonky2/src/gates/constant.rs
     degree = 1
 
+    kind = GATE_CONSTANT
+
     def __init__(self, num_consts):
-        self.num_consts = self.num_constants = self.num_constraints = num_consts
+        self.num_consts = self.num_constants = self.num_constraints = self.param = num_consts
 
     def id(self):
         return "ConstantGate { num_consts: %d }" % self.num_consts
@@ -216,6 +226,7 @@ class ConstantGate(Gate):  # plonky2/src/gates/constant.rs
 class PublicInputGate(Gate):  # plonky2/src/gates/public_input.rs
     degree = 1
     num_constraints = 4
+    kind = GATE_PUBLIC_INPUT
 
     def id(self):
         return "PublicInputGate"
@@ -228,8 +239,10 @@ class ArithmeticGate(Gate):  # plonky2/src/gates/arithmetic_base.rs
     degree = 3
     num_constants = 2
 
+    kind = GATE_ARITHMETIC
+
     def __init__(self, num_ops):
-        self.num_ops = self.num_constraints = num_ops
+        self.num_ops = self.num_constraints = self.param = num_ops
 
     @staticmethod
     def new_from_config(num_routed_wires):
@@ -269,6 +282,7 @@ class PoseidonGate(Gate):
     `arith` supplies the value type: the recording `Val`s for the constraint program, plain
     integers mod p for witness generation (the gate's generator, poseidon.rs:424-520)."""
     degree = 7
+    kind = GATE_POSEIDON
     num_constraints = 12 * 7 + 22 + 12 + 1 + 4   # poseidon.rs:416-422
     WIRE_SWAP = 24
     START_DELTA = 25
@@ -483,6 +497,42 @@ class CommonCircuitData:
         return prog.compile()
 
 
+class _GateDesc(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("param", C.c_uint32)]
+
+
+def native_constraint_program(gates, max_degree):
+    """The host library's compiler (qp-plonky2_b200/host/plonk_host.cpp, qp_program_create): the
+    program the device runs.  -> dict(code, pool, n_regs, num_selectors, selector_indices, groups,
+    order) with gates in the reference's sorted order; `order[i]` = index in `gates` of sorted gate i."""
+    from . import lib
+    arr = (_GateDesc * len(gates))(*[_GateDesc(g.kind, g.param) for g in gates])
+    h = C.c_void_p()
+    rc = lib().qp_program_create(arr, len(gates), max_degree, C.byref(h))
+    if rc:
+        raise ValueError("qp_program_create failed (%d): unsupported gate, or a gate of too high degree" % rc)
+    try:
+        ptr = C.c_void_p()
+        n = lib().qp_program_code(h, C.byref(ptr))
+        code = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+        n = lib().qp_program_pool(h, C.byref(ptr))
+        pool = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), shape=(n,)).copy()
+        sel, groups, order = [], {}, []
+        for i in range(len(gates)):
+            o, s_, a, b = C.c_uint(), C.c_uint(), C.c_uint(), C.c_uint()
+            lib().qp_program_gate(h, i, C.byref(o), C.byref(s_), C.byref(a), C.byref(b))
+            order.append(o.value)
+            sel.append(s_.value)
+            groups[s_.value] = (a.value, b.value)
+        return dict(code=code, pool=pool, n_regs=int(lib().qp_program_regs(h)),
+                    num_selectors=int(lib().qp_program_num_selectors(h)), selector_indices=sel,
+                    groups=[groups[k] for k in sorted(groups)], order=order,
+                    num_gate_constants=int(lib().qp_program_num_gate_constants(h)),
+                    num_gate_constraints=int(lib().qp_program_num_gate_constraints(h)))
+    finally:
+        lib().qp_program_free(h)
+
+
 class _Desc(C.Structure):
     _fields_ = [
         ("degree_bits", C.c_uint32), ("quotient_degree_bits", C.c_uint32), ("num_challenges", C.c_uint32),
@@ -501,7 +551,11 @@ class Circuit:
     def __init__(self, ctx, common, sigmas=None):
         from . import _buf, lib  # late: this module is imported by the package
         self.ctx, self.common = ctx, common
-        code, pool, n_regs = common.constraint_program()
+        # the native host compiler produces the program the device runs; the Python
+        # `constraint_program` is the readable mirror the CPU tests compare it with
+        native = native_constraint_program(common.gates, common.quotient_degree_factor + 1)
+        assert native["selector_indices"] == common.selector_indices and native["groups"] == common.groups
+        code, pool, n_regs = native["code"], native["pool"], native["n_regs"]
         self.program = (code, pool, n_regs)
         k_is = np.ascontiguousarray(common.k_is, dtype=np.uint64)
         d = _Desc()

@@ -168,7 +168,7 @@ def test_large_proof_openings_pass_the_verifier(qp, ctx):
     ch = qp.Challenger()
     pd.fri.observe(ch, c.degree_bits, pd.reduction_arity_bits)
     ch.observe_elements(pd.circuit_digest)
-    pih = prover.hash_no_pad(ctx, sc.public_inputs)
+    pih = prover.hash_no_pad(sc.public_inputs)
     ch.observe_elements(pih)
     ch.observe_cap(caps[0])
     betas, gammas = ch.get_n_challenges(nc), ch.get_n_challenges(nc)

@@ -62,14 +62,22 @@ def test_selectors_info_matches_reference_rule(qdf):
     assert c.num_partial_products == -(-80 // qdf) - 1
 
 
+@pytest.mark.parametrize("native", [False, True])
 @pytest.mark.parametrize("qdf,poseidon", [(8, False), (4, False), (8, True)])
-def test_constraint_program_matches_oracle_gate_evaluation(qdf, poseidon):
+def test_constraint_program_matches_oracle_gate_evaluation(qdf, poseidon, native):
     """The compiled program and the oracle's hand-written gate evaluators agree on random
     (non-satisfying) inputs: compare the full vanishing value with the permutation terms zeroed
     out by Z = partial products = 0... simpler: both sides computed in full."""
     sc = SynthCircuit(5, seed=5, quotient_degree_factor=qdf, poseidon=poseidon)
     c = sc.common
-    code, pool, n_regs = c.constraint_program()
+    if native:   # qp-plonky2_b200/host/plonk_host.cpp, the compiler whose output the device runs
+        prog = plonk.native_constraint_program(c.gates, qdf + 1)
+        code, pool, n_regs = prog["code"], prog["pool"], prog["n_regs"]
+        assert prog["selector_indices"] == c.selector_indices and prog["groups"] == c.groups
+        assert prog["order"] == list(range(len(c.gates)))   # already sorted
+        assert prog["num_gate_constraints"] == c.num_gate_constraints
+    else:
+        code, pool, n_regs = c.constraint_program()
     if poseidon:   # degree 7 forces a second selector group (selectors.rs:140-150)
         assert c.groups == [(0, 4), (4, 5)] and c.num_gate_constraints == 123
     rng = np.random.default_rng(7)
@@ -176,3 +184,31 @@ def test_oracle_proof_openings_satisfy_the_verifier(degree_bits, qdf, poseidon):
     assert int(tail[0]) == len(sc.public_inputs) and [int(x) for x in tail[1:]] == sc.public_inputs
     # deterministic
     assert _oracle_prove(sc, proof_of_work_bits=6, num_query_rounds=4)[0] == proof
+
+
+def test_native_program_sorts_gates_like_the_builder():
+    """circuit_builder.rs:1177-1179: by (degree, id) whatever order the caller lists them in."""
+    gates = [plonk.PoseidonGate(), plonk.ArithmeticGate(20), plonk.PublicInputGate(), plonk.NoopGate(), plonk.ConstantGate(2)]
+    prog = plonk.native_constraint_program(gates, 9)
+    assert [gates[i].id().split(" ")[0].split("(")[0] for i in prog["order"]] == [
+        "NoopGate", "ConstantGate", "PublicInputGate", "ArithmeticGate", "PoseidonGate"]
+    assert prog["groups"] == [(0, 4), (4, 5)] and prog["selector_indices"] == [0, 0, 0, 0, 1]
+    with pytest.raises(ValueError):   # "... has too high degree. Consider increasing `quotient_degree_factor`."
+        plonk.native_constraint_program(gates, 7)
+
+
+def test_host_hash_no_pad_and_circuit_digest_match_oracle():
+    import ctypes as C
+    import qp_plonky2_b200 as qp
+    from oracle import prover as oprover
+
+    L = qp.lib()
+    for n in (0, 1, 7, 8, 9, 16, 71):
+        x = oracle.rand_felts((n,), 900 + n)
+        out = np.zeros(4, dtype=np.uint64)
+        L.qp_hash_no_pad(x.ctypes.data if n else None, n, out.ctypes.data)
+        assert (out == oracle.hash_no_pad(x)).all(), n
+    cap = oracle.rand_felts((16, 4), 3)
+    out = np.zeros(4, dtype=np.uint64)
+    L.qp_circuit_digest(cap.ctypes.data, 16, 13, out.ctypes.data)
+    assert (out == oprover.circuit_digest(cap, 13)).all()

@@ -18,7 +18,8 @@ def build(name, flags):
     out = os.path.join(VDIR, name + ".so")
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler",
            "-fPIC", "-shared", "-o", out] + flags.split() + [
-        os.path.join(ROOT, "qp-plonky2_b200/csrc/qp_plonky2.cu"), os.path.join(ROOT, "qp-plonky2_b200/host/transcript.cpp")]
+        os.path.join(ROOT, "qp-plonky2_b200/csrc/qp_plonky2.cu"), os.path.join(ROOT, "qp-plonky2_b200/host/transcript.cpp"),
+        os.path.join(ROOT, "qp-plonky2_b200/host/plonk_host.cpp"), os.path.join(ROOT, "qp-plonky2_b200/host/prover.cpp")]
     subprocess.check_call(cmd)
     print("built", out)
 
