@@ -79,39 +79,60 @@ struct ExtPlanesLayout {
 #ifndef QP_LEAF_SYNC        // 1: barrier per Poseidon round (all warps of the block in lockstep)
 #define QP_LEAF_SYNC 0
 #endif
+// A leaf's sponge can be advanced in pieces: chunks [chunk_first, chunk_first + chunk_count) of
+// 8 elements are absorbed in this launch; the 12-word sponge state of every leaf travels between
+// launches in `state` ([12][n_leaves], column-major so that loads coalesce).  The commit from host
+// memory uses this to hash the columns that have already arrived while later ones are still
+// crossing PCIe.  chunk_first = 0 starts from the initial state (hashing.rs:156-158); the launch
+// that absorbs the last chunk writes the digest.  (0, all, nullptr) is the whole hash in one go.
 template <class Layout>
 __global__ void __launch_bounds__(QP_LEAF_BLOCK, QP_LEAF_MIN_BLOCKS)
 leaf_hash_kernel(Layout lay, unsigned leaf_len, TreeShape sh, uint64_t* __restrict__ digests,
-                 uint64_t* __restrict__ cap) {
+                 uint64_t* __restrict__ cap, unsigned chunk_first, unsigned chunk_count,
+                 uint64_t* __restrict__ state) {
     const size_t n_leaves = (size_t)1 << sh.lg_leaves;
     const size_t i_raw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     // threads past the end hash the last leaf again and drop the result, so that every thread
     // of the block reaches the same barriers
     const bool live = i_raw < n_leaves;
     const size_t i = live ? i_raw : n_leaves - 1;
-    uint64_t s[12];
-#pragma unroll
-    for (int k = 0; k < 12; k++) s[k] = 0;
-    s[8] = (uint64_t)leaf_len + 1;
     // hashing.rs:160-163: one permutation per 8-chunk, the last chunk may be short (its missing
     // lanes keep the previous state).  Software pipeline: fetch chunk ch+1 while permuting ch.
     const unsigned n_chunks = (leaf_len + 7) / 8;
+    const unsigned ch_end = (chunk_count > n_chunks - chunk_first) ? n_chunks : chunk_first + chunk_count;
+    uint64_t s[12];
+    if (chunk_first == 0) {
+#pragma unroll
+        for (int k = 0; k < 12; k++) s[k] = 0;
+        s[8] = (uint64_t)leaf_len + 1;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; k++) s[k] = state[(size_t)k * n_leaves + i];
+    }
     uint64_t nxt[8];
 #pragma unroll
     for (int k = 0; k < 8; k++)
-        if ((unsigned)k < leaf_len) nxt[k] = lay.get(i, k);
+        if (chunk_first * 8 + k < leaf_len) nxt[k] = lay.get(i, chunk_first * 8 + k);
 #pragma unroll 1
-    for (unsigned ch = 0; ch < n_chunks; ch++) {
+    for (unsigned ch = chunk_first; ch < ch_end; ch++) {
         const unsigned c = ch * 8;
 #pragma unroll
         for (int k = 0; k < 8; k++)
             if (c + k < leaf_len) s[k] = nxt[k];
+        if (ch + 1 < ch_end) {
 #pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (c + 8 + k < leaf_len) nxt[k] = lay.get(i, c + 8 + k);
+            for (int k = 0; k < 8; k++)
+                if (c + 8 + k < leaf_len) nxt[k] = lay.get(i, c + 8 + k);
+        }
         poseidon::permute<QP_LEAF_SYNC != 0>(s);
     }
-    if (live) store_digest(leaf_digest_ptr(sh, digests, cap, i), s);
+    if (!live) return;
+    if (ch_end == n_chunks) {
+        store_digest(leaf_digest_ptr(sh, digests, cap, i), s);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; k++) state[(size_t)k * n_leaves + i] = s[k];
+    }
 }
 
 // One thread per node of `layer` (1 <= layer <= num_layers): two_to_one of its children.

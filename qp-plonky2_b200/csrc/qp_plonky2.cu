@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -49,6 +50,7 @@ struct qp_ctx {
     static constexpr int MAX_GROUPS = 16;
     cudaEvent_t copy_ev[MAX_GROUPS] = {};
     cudaEvent_t ready_ev = nullptr;
+    cudaEvent_t grp_ev[3 * MAX_GROUPS] = {};  // per column group: start, after LDE, after partial leaf hash
 };
 
 #define CUDA_TRY(ctx, expr)                                                                  \
@@ -210,6 +212,7 @@ extern "C" int qp_ctx_create(int device, void* stream, unsigned max_lde_log, qp_
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (auto& e : ctx->copy_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ready_ev, cudaEventDisableTiming);
+    for (auto& e : ctx->grp_ev) cudaEventCreate(&e);
     // keep freed blocks cached in the pool: commits allocate and free multi-GB buffers
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -262,6 +265,7 @@ extern "C" void qp_ctx_destroy(qp_ctx* ctx) {
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     for (auto& e : ctx->copy_ev) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ready_ev);
+    for (auto& e : ctx->grp_ev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -476,22 +480,37 @@ struct TreeBuf {
     size_t n_cap() const { return (size_t)1 << shape.cap_height; }
 };
 
+// Leaf hashing, possibly in pieces (merkle::leaf_hash_kernel), and the levels above it.
 template <class Layout>
-static int build_tree(qp_ctx* ctx, Layout lay, unsigned leaf_len, TreeBuf* t, cudaEvent_t after_leaves = nullptr) {
-    int rc = dev_alloc(ctx, &t->digests, t->n_digests() * 4);
-    if (rc) return rc;
-    rc = dev_alloc(ctx, &t->cap, t->n_cap() * 4);
-    if (rc) return rc;
+static int hash_leaves(qp_ctx* ctx, Layout lay, unsigned leaf_len, TreeBuf* t, unsigned chunk_first = 0,
+                       unsigned chunk_count = ~0u, uint64_t* state = nullptr) {
+    if (!t->digests) {
+        int rc = dev_alloc(ctx, &t->digests, t->n_digests() * 4);
+        if (rc) return rc;
+        rc = dev_alloc(ctx, &t->cap, t->n_cap() * 4);
+        if (rc) return rc;
+    }
     const size_t n_leaves = (size_t)1 << t->shape.lg_leaves;
     LAUNCH(ctx, merkle::leaf_hash_kernel<Layout>, cdiv(n_leaves, QP_LEAF_BLOCK), QP_LEAF_BLOCK, 0, lay, leaf_len,
-           t->shape, t->digests, t->cap);
-    if (after_leaves) cudaEventRecord(after_leaves, ctx->stream);
+           t->shape, t->digests, t->cap, chunk_first, chunk_count, state);
+    return QP_OK;
+}
+
+static int build_tree_levels(qp_ctx* ctx, TreeBuf* t) {
     const unsigned nl = t->shape.num_layers();
     for (unsigned layer = 1; layer <= nl; layer++) {
         const size_t nodes = (size_t)1 << (t->shape.lg_leaves - layer);
         LAUNCH(ctx, merkle::tree_level_kernel, cdiv(nodes, 128), 128, 0, t->shape, layer, t->digests, t->cap);
     }
     return QP_OK;
+}
+
+template <class Layout>
+static int build_tree(qp_ctx* ctx, Layout lay, unsigned leaf_len, TreeBuf* t, cudaEvent_t after_leaves = nullptr) {
+    int rc = hash_leaves(ctx, lay, leaf_len, t);
+    if (rc) return rc;
+    if (after_leaves) cudaEventRecord(after_leaves, ctx->stream);
+    return build_tree_levels(ctx, t);
 }
 
 // Siblings for many leaves at once: out[q][layer][4]
@@ -607,7 +626,7 @@ static int batch_lde_columns(qp_batch* b, size_t c0, size_t c1) {
 
 // Phase 3: salt columns, "build Merkle tree" (oracle.rs:210-214), timings.  ev[1] must have been
 // recorded where the LDE phase started.
-static int batch_finish(qp_batch* b, const uint64_t* salt_dev) {
+static int batch_finish(qp_batch* b, const uint64_t* salt_dev, unsigned chunks_done = 0, uint64_t* state = nullptr) {
     qp_ctx* ctx = b->ctx;
     if (b->blinding) {
         LAUNCH(ctx, salt_to_leaf_order_kernel, cdiv(QP_SALT_SIZE * b->n_local, 256), 256, 0, salt_dev,
@@ -617,7 +636,11 @@ static int batch_finish(qp_batch* b, const uint64_t* salt_dev) {
     cudaEventRecord(ctx->ev[2], ctx->stream);
     // "transpose LDEs" is fused away: the LDE is already in leaf order, column-major.
     merkle::AffineLayout lay{b->lde, b->n_local, 1};
-    int rc = build_tree(ctx, lay, (unsigned)b->leaf_len, &b->tree, ctx->ev[5]);
+    // chunks [0, chunks_done) of every leaf were absorbed while the input was still arriving
+    int rc = hash_leaves(ctx, lay, (unsigned)b->leaf_len, &b->tree, chunks_done, ~0u, state);
+    if (rc) return rc;
+    cudaEventRecord(ctx->ev[5], ctx->stream);
+    rc = build_tree_levels(ctx, &b->tree);
     if (rc) return rc;
     cudaEventRecord(ctx->ev[3], ctx->stream);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -725,7 +748,10 @@ extern "C" int qp_batch_from_values(qp_ctx* ctx, const uint64_t* values, int spa
 
     // Host input of at least 64 MiB: upload in column groups on the copy stream and run the
     // iNTT + LDE of group g while group g+1 is still in flight.
-    const bool pipelined = space != QP_DEVICE && n_cols * n * 8 >= ((size_t)64 << 20) && n_cols >= 2;
+    // (QP_PIPELINE_MIN_BYTES lowers the threshold so that the tests can drive this path with small inputs)
+    const char* thr_env = getenv("QP_PIPELINE_MIN_BYTES");
+    const size_t thr = thr_env ? (size_t)strtoull(thr_env, nullptr, 10) : ((size_t)64 << 20);
+    const bool pipelined = space != QP_DEVICE && n_cols * n * 8 >= thr && n_cols >= 2;
     if (!pipelined) {
         const uint64_t* d_values = nullptr;
         uint64_t* values_owned = nullptr;
@@ -770,36 +796,77 @@ extern "C" int qp_batch_from_values(qp_ctx* ctx, const uint64_t* values, int spa
         }
         return rc;
     }
-    const int n_groups = (int)(n_cols < 9 ? n_cols : 9);
-    const size_t per = (n_cols + n_groups - 1) / n_groups;
+    // groups of 16 columns = two 8-element sponge chunks, so that the leaf hash of a group can
+    // run as soon as its LDE is done (merkle::leaf_hash_kernel in pieces): the upload of the
+    // later groups hides behind the hashing of the earlier ones, not only behind the transforms
+    size_t per = 16;
+    while ((n_cols + per - 1) / per > (size_t)qp_ctx::MAX_GROUPS) per += 16;
+    const int n_groups = (int)((n_cols + per - 1) / per);
+    uint64_t* d_state = nullptr;
+    rc = dev_alloc(ctx, &d_state, 12 * (*out)->n_local);
+    if (rc) {
+        dev_free(ctx, d_values);
+        qp_batch_free(*out);
+        *out = nullptr;
+        return rc;
+    }
     // the copy stream may only touch d_values once the (stream-ordered) allocation has happened
     cudaEventRecord(ctx->ready_ev, ctx->stream);
     cudaStreamWaitEvent(ctx->copy_stream, ctx->ready_ev, 0);
     for (int g = 0; g < n_groups; g++) {
         const size_t c0 = g * per, c1 = (c0 + per < n_cols) ? c0 + per : n_cols;
-        if (c0 >= c1) break;
         CUDA_TRY(ctx, cudaMemcpyAsync(d_values + c0 * n, values + c0 * n, (c1 - c0) * n * 8, cudaMemcpyHostToDevice,
                                       ctx->copy_stream));
         cudaEventRecord(ctx->copy_ev[g], ctx->copy_stream);
     }
     cudaEventRecord(ctx->ev[1], ctx->stream);
+    merkle::AffineLayout lay{(*out)->lde, (*out)->n_local, 1};
+    unsigned chunks_done = 0;
+    int hashed_groups = 0;
     for (int g = 0; g < n_groups && !rc; g++) {
         const size_t c0 = g * per, c1 = (c0 + per < n_cols) ? c0 + per : n_cols;
-        if (c0 >= c1) break;
         cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[g], 0);
+        cudaEventRecord(ctx->grp_ev[3 * g], ctx->stream);
         rc = ifft_device(ctx, d_values + c0 * n, c1 - c0, degree_log, d_coeffs + c0 * n, d_values + c0 * n);
         if (!rc) rc = batch_lde_columns(*out, c0, c1);
+        cudaEventRecord(ctx->grp_ev[3 * g + 1], ctx->stream);
+        // absorb the complete chunks of this group, leaving at least the last chunk of the leaf
+        // (and the salt, if any) to batch_finish
+        const unsigned chunk_end = (unsigned)(c1 / 8);
+        const unsigned n_chunks = (unsigned)(((*out)->leaf_len + 7) / 8);
+        if (!rc && chunk_end > chunks_done && chunk_end < n_chunks) {
+            rc = hash_leaves(ctx, lay, (unsigned)(*out)->leaf_len, &(*out)->tree, chunks_done, chunk_end - chunks_done,
+                             d_state);
+            chunks_done = chunk_end;
+            hashed_groups = g + 1;
+        }
+        cudaEventRecord(ctx->grp_ev[3 * g + 2], ctx->stream);
     }
     dev_free(ctx, d_values);
     if (!rc && blinding)
         rc = to_device(ctx, salt, space, (size_t)QP_SALT_SIZE << (degree_log + rate_bits), &d_salt, &salt_owned);
-    if (!rc) rc = batch_finish(*out, d_salt);  // ms[1] = iNTT + LDE + upload wait ("IFFT" is folded into it)
+    if (!rc) rc = batch_finish(*out, d_salt, chunks_done, d_state);  // synchronises the stream
     dev_free(ctx, salt_owned);
+    dev_free(ctx, d_state);
     if (rc) {
         qp_batch_free(*out);
         *out = nullptr;
+        return rc;
     }
-    return rc;
+    // scopes: the transforms and the partial leaf hashes interleave, so sum them per group
+    float t_ntt = 0, t_hash = 0, ms = 0;
+    for (int g = 0; g < n_groups; g++) {
+        cudaEventElapsedTime(&ms, ctx->grp_ev[3 * g], ctx->grp_ev[3 * g + 1]);
+        t_ntt += ms;
+        if (g < hashed_groups) {
+            cudaEventElapsedTime(&ms, ctx->grp_ev[3 * g + 1], ctx->grp_ev[3 * g + 2]);
+            t_hash += ms;
+        }
+    }
+    (*out)->ms[1] = t_ntt;             // "IFFT" + "FFT + blinding" (the upload wait is not in it)
+    (*out)->ms[3] += t_hash;           // "build Merkle tree"
+    (*out)->ms_leaf_hash += t_hash;
+    return QP_OK;
 }
 
 extern "C" int qp_ifft_columns(qp_ctx* ctx, const uint64_t* values, int space, size_t n_cols,

@@ -486,3 +486,22 @@ def test_fri_proof_bytes_parity(qp, ctx, lg_n, rate, cap_h, pow_bits, queries):
     assert len(got) == len(want)
     assert got == want
     assert ca.get_challenge() == cb.get_challenge()
+
+
+@pytest.mark.parametrize("cols,lg_n,blinding", [(5, 8, False), (16, 9, False), (17, 9, True), (40, 10, False),
+                                                (135, 10, False), (143, 11, True), (8, 7, True)])
+def test_from_values_pipelined_upload_with_partial_leaf_hashing(qp, ctx, cols, lg_n, blinding, monkeypatch):
+    """Host input: the upload runs in 16-column groups and the leaf sponge absorbs each group as soon
+    as its LDE exists (merkle::leaf_hash_kernel in pieces).  Same commitment as the oracle's, for
+    leaf lengths on and off the 8-element chunk boundary, with and without salt."""
+    monkeypatch.setenv("QP_PIPELINE_MIN_BYTES", "1")
+    n = 1 << lg_n
+    vals = oracle.rand_felts((cols, n), 900 + cols)
+    salt = oracle.rand_felts((4, n << 3), 901 + cols) if blinding else None
+    got = qp.PolynomialBatch.from_values(ctx, vals, 3, blinding, 4, salt=salt)
+    want = oracle.PolynomialBatch.from_values(vals, 3, 4, salt=salt)
+    assert (got.merkle_tree.cap == want.cap).all()
+    assert (got.merkle_tree.digests == want.digests).all()
+    assert (got.polynomials == want.polynomials).all()
+    assert (got.merkle_tree.leaves() == want.leaves).all()
+    assert got.kernel_ms["leaf_hash"] > 0
