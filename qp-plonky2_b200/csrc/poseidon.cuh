@@ -62,13 +62,11 @@ static constexpr Mat M1 = mds_matrix();
 __constant__ uint64_t c_rc[WIDTH * (N_ROUNDS + 1)];
 // FP64-pipe formulation (see f64 below): the same constants as (2^52 + low half, 2^52 + high half)
 // doubles, and the constants of the 11 fused PAIRS of partial rounds:
-//   c_pair_k[g]        rc'_0                      (rc', rc'' = constants of the two rounds
-//   c_pair_K[g][0..11] M rc' + rc''                FOLLOWING the pair's first round)
+//   c_pair_k_d[g]        rc'_0                      (rc', rc'' = constants of the two rounds
+//   c_pair_K_d[g][0..11] M rc' + rc''                FOLLOWING the pair's first round)
 __constant__ double c_rc_d[WIDTH * (N_ROUNDS + 1)][2];
 // c_rc_dd[6 * round + r] = c_rc_d[12 * round + r + 6] - c_rc_d[12 * round + r]   (split layer, below)
 __constant__ double c_rc_dd[6 * (N_ROUNDS + 1)][2];
-__constant__ uint64_t c_pair_k[N_PARTIAL_PAIRS];
-__constant__ uint64_t c_pair_K[N_PARTIAL_PAIRS][WIDTH];
 __constant__ double c_pair_k_d[N_PARTIAL_PAIRS][2];
 __constant__ double c_pair_K_d[N_PARTIAL_PAIRS][WIDTH][2];
 __constant__ double c_pair_K_dd[N_PARTIAL_PAIRS][6][2];   // c_pair_K_d[g][r + 6] - c_pair_K_d[g][r]
@@ -128,28 +126,11 @@ static inline cudaError_t upload_constants(cudaStream_t stream) {
     if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_pair_K_dd, pKdd, sizeof pKdd, 0, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_rc_d, rcd, sizeof rcd, 0, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_rc_dd, rcdd, sizeof rcdd, 0, cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_pair_k, pk, sizeof pk, 0, cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_pair_K, pK, sizeof pK, 0, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_pair_k_d, pkd, sizeof pkd, 0, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_pair_K_d, pKd, sizeof pKd, 0, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // the sources are static host arrays
     return e;
 }
-
-// al + ah * 2^32 -> field element, for al, ah < 2^62 (gl::fold3)
-__device__ __forceinline__ uint64_t fold_row(uint64_t al, uint64_t ah) {
-    uint32_t al0, al1, ah0, ah1;
-    gl::unpack(al, al0, al1);
-    gl::unpack(ah, ah0, ah1);
-    return gl::fold3(al0, al1, ah0, ah1);
-}
-
-// acc += row R of matrix MAT times the state halves (2 x 12 IMAD.WIDE with immediate operands)
-#define QP_DOT_ROW(MAT, R, lo, hi, al, ah)                       \
-    _Pragma("unroll") for (int k_ = 0; k_ < 12; k_++) {          \
-        al += (uint64_t)lo[k_] * MAT.a[R][k_];                   \
-        ah += (uint64_t)hi[k_] * MAT.a[R][k_];                   \
-    }
 
 // (x0^7 - x0) split into halves
 __device__ __forceinline__ void sbox_delta(uint64_t x0, uint32_t& dlo, uint32_t& dhi) {
@@ -168,14 +149,8 @@ __device__ __forceinline__ void sbox_delta(uint64_t x0, uint32_t& dlo, uint32_t&
 //        (fold_row_f64 also cancels the exponent words, so the read-back is free.)
 // The 22 partial rounds are fused in PAIRS (entries of M^2 < 2^17 keep two 32-bit limbs exact):
 //     x'' = M^2 x + d1 M^2 e0 + d2 M e0 + K,   d = x0^7 - x0,
-// 362 DFMA per two rounds.  QP_POSEIDON_F64_FULL / _PART = how many of the 12 output rows of a
-// full-round / pair layer go to the FP64 pipe; the remaining rows use IMAD.WIDE (pipe balance).
-#ifndef QP_POSEIDON_F64_FULL
-#define QP_POSEIDON_F64_FULL 12
-#endif
-#ifndef QP_POSEIDON_F64_PART
-#define QP_POSEIDON_F64_PART 12
-#endif
+// 362 DFMA per two rounds before the split below.  (Moving rows back to IMAD.WIDE was measured:
+// every row on the FP64 pipe is best, profiles/r01d_variants_fp64_rows.txt.)
 #ifndef QP_POSEIDON_I2F   // 1: cvt.rn.f64.u32 (I2F, XU pipe, otherwise idle) instead of the 2^52 trick for the inputs
 #define QP_POSEIDON_I2F 1
 #endif
@@ -202,12 +177,6 @@ __device__ __forceinline__ uint64_t fold_row_f64(double al, double ah) {
                      (uint32_t)__double2loint(ah), (uint32_t)__double2hiint(ah));
 }
 
-#define QP_DOT_ROW_F64(MAT, R, dl, dh, al, ah)                   \
-    _Pragma("unroll") for (int k_ = 0; k_ < 12; k_++) {          \
-        al = fma(dl[k_], (double)MAT.a[R][k_], al);              \
-        ah = fma(dh[k_], (double)MAT.a[R][k_], ah);              \
-    }
-
 // Full-round linear layer with the circulant split by the CRT  z^12 - 1 = (z^6 - 1)(z^6 + 1):
 // with u = x[0..6) + x[6..12), v = x[0..6) - x[6..12),
 //     P_r = sum_j c+_j u[(j + r) mod 6]              (cyclic,     c+_j = (c_j + c_{j+6}) / 2)
@@ -217,9 +186,6 @@ __device__ __forceinline__ uint64_t fold_row_f64(double al, double ah) {
 // (15,14,40,17,18,24) and (2,1,1,-1,-16,4) are integers and everything stays exact: 103 FP64
 // operations per plane instead of 144.  P_r starts at the constant of row r; row r + 6 adds the
 // difference of the two constants (exact: both are 2^52 + a 33-bit integer).
-#ifndef QP_POSEIDON_MDS_SPLIT
-#define QP_POSEIDON_MDS_SPLIT 1
-#endif
 __device__ __forceinline__ void mds_layer_split(uint64_t (&s)[12], int round) {
     constexpr double CP[6] = {15, 14, 40, 17, 18, 24};
     constexpr double CM[6] = {2, 1, 1, -1, -16, 4};
@@ -254,33 +220,6 @@ __device__ __forceinline__ void mds_layer_split(uint64_t (&s)[12], int round) {
     }
 #pragma unroll
     for (int r = 0; r < 12; r++) s[r] = fold_row_f64(y[0][r], y[1][r]);
-}
-
-// state <- M * state + rc[ri .. ri+12)   (ri = 12 * round)
-__device__ __forceinline__ void mds_layer_f64(uint64_t (&s)[12], int ri) {
-    QP_POSEIDON_MATS
-    uint32_t lo[12], hi[12];
-    double dl[12], dh[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-        gl::unpack(s[i], lo[i], hi[i]);
-        dl[i] = f64::from_u32(lo[i]);
-        dh[i] = f64::from_u32(hi[i]);
-    }
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        if (r < QP_POSEIDON_F64_FULL) {
-            double al = c_rc_d[ri + r][0], ah = c_rc_d[ri + r][1];
-            QP_DOT_ROW_F64(m1, r, dl, dh, al, ah)
-            s[r] = fold_row_f64(al, ah);
-        } else {
-            uint32_t c0, c1;
-            gl::unpack(c_rc[ri + r], c0, c1);
-            uint64_t al = c0, ah = c1;
-            QP_DOT_ROW(m1, r, lo, hi, al, ah)
-            s[r] = fold_row(al, ah);
-        }
-    }
 }
 
 // The same CRT split for the pair layer.  M = C + 8 e0 e0^T (C circulant), so
@@ -374,62 +313,6 @@ __device__ __forceinline__ void partial_pair_split(uint64_t (&s)[12], int g) {
     for (int r = 0; r < 12; r++) s[r] = fold_row_f64(y[0][r], y[1][r]);
 }
 
-// Two fused partial rounds.  `s` enters with its round constants already added.
-__device__ __forceinline__ void partial_pair_f64(uint64_t (&s)[12], int g) {
-    QP_POSEIDON_MATS
-    uint32_t lo[12], hi[12];
-    double dl[12], dh[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-        gl::unpack(s[i], lo[i], hi[i]);
-        dl[i] = f64::from_u32(lo[i]);
-        dh[i] = f64::from_u32(hi[i]);
-    }
-    uint32_t d1l, d1h, d2l, d2h;
-    sbox_delta(s[0], d1l, d1h);
-    const double e1l = f64::from_u32(d1l), e1h = f64::from_u32(d1h);
-    // lane 0 after the first round:  (M x)_0 + d1 M00 + rc'_0
-    uint64_t y0;
-    if (QP_POSEIDON_F64_PART > 0) {
-        double al = c_pair_k_d[g][0], ah = c_pair_k_d[g][1];
-        QP_DOT_ROW_F64(m1, 0, dl, dh, al, ah)
-        al = fma(e1l, (double)m1.a[0][0], al);
-        ah = fma(e1h, (double)m1.a[0][0], ah);
-        y0 = fold_row_f64(al, ah);
-    } else {
-        uint32_t c0, c1;
-        gl::unpack(c_pair_k[g], c0, c1);
-        uint64_t al = c0, ah = c1;
-        QP_DOT_ROW(m1, 0, lo, hi, al, ah)
-        al += (uint64_t)d1l * m1.a[0][0];
-        ah += (uint64_t)d1h * m1.a[0][0];
-        y0 = fold_row(al, ah);
-    }
-    sbox_delta(y0, d2l, d2h);
-    const double e2l = f64::from_u32(d2l), e2h = f64::from_u32(d2h);
-    // full state after the second round
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        if (r < QP_POSEIDON_F64_PART) {
-            double al = c_pair_K_d[g][r][0], ah = c_pair_K_d[g][r][1];
-            QP_DOT_ROW_F64(m2, r, dl, dh, al, ah)
-            al = fma(e1l, (double)m2.a[r][0], al);
-            ah = fma(e1h, (double)m2.a[r][0], ah);
-            al = fma(e2l, (double)m1.a[r][0], al);
-            ah = fma(e2h, (double)m1.a[r][0], ah);
-            s[r] = fold_row_f64(al, ah);
-        } else {
-            uint32_t c0, c1;
-            gl::unpack(c_pair_K[g][r], c0, c1);
-            uint64_t al = c0, ah = c1;
-            QP_DOT_ROW(m2, r, lo, hi, al, ah)
-            al += (uint64_t)d1l * m2.a[r][0] + (uint64_t)d2l * m1.a[r][0];
-            ah += (uint64_t)d1h * m2.a[r][0] + (uint64_t)d2h * m1.a[r][0];
-            s[r] = fold_row(al, ah);
-        }
-    }
-}
-
 // S-box layer as 12/L iterations x L lanes with a register rotation (smaller code) -- with the
 // linear layers on the FP64 pipe the code fits the instruction cache fully unrolled, and L = 12 (no
 // rotation moves) is the measured best on B200 (leaf hash at 2^21 x 135: L = 6 25.46 ms, L = 12 25.06 ms).
@@ -474,22 +357,14 @@ __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
         for (int r = base; r < base + 4; r++) {
             if (SYNC) __syncthreads();
             sbox_all(s);
-#if QP_POSEIDON_MDS_SPLIT
-            mds_layer_split(s, r + 1);       // row 30 is zero
-#else
-            mds_layer_f64(s, 12 * (r + 1));
-#endif
+            mds_layer_split(s, r + 1);  // row 30 is zero
         }
         if (half == 0) {
             // 22 partial rounds (poseidon.rs:623-628) as 11 fused pairs
 #pragma unroll 1
             for (int g = 0; g < N_PARTIAL_PAIRS; g++) {
                 if (SYNC) __syncthreads();
-#if QP_POSEIDON_MDS_SPLIT
                 partial_pair_split(s, g);
-#else
-                partial_pair_f64(s, g);
-#endif
             }
         }
     }
