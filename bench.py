@@ -301,10 +301,10 @@ def run_ours(args):
                                                                                      1 << (args.rows_log - sample)),
                "scopes_ms_sample": scopes}
 
-    # issue-slot roofline of the same kernel: ncu (profiles/r01f_ncu_leaf_hash_full_size.md) counts 17.65k warp
+    # issue-slot roofline of the same kernel: ncu (profiles/r01h_ncu_full.md) counts 16.08k warp
     # instructions per warp-permutation; one warp instruction per cycle per SM sub-partition is the ceiling
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    instr_per_warp_perm = 17650.0
+    instr_per_warp_perm = 16080.0
     issue_peak = 148 * 4 * sm_mhz * 1e6 * 32 / instr_per_warp_perm
     roof_issue = {"kernel": "merkle::leaf_hash_kernel", "bound": "issue slots (fma-heavy + ALU + FP64 pipes share one "
                   "issue port per SM sub-partition)", "achieved": perms / (k_leaf * 1e-3), "peak": issue_peak,
