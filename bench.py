@@ -195,14 +195,22 @@ def run_ours(args):
             ctx.ifft_columns(v, out_device=out[: v.shape[0]])
             return out
 
-        def commit_fn(coeffs_all, first, count):
-            b = qp.PolynomialBatch.from_coeffs(ctx, coeffs_all.contiguous(), RATE_BITS, False, CAP_HEIGHT,
-                                               block_first=first, block_count=count)
-            return b, torch.from_numpy(b.merkle_tree.cap.view(np.int64)).to(dev)
+        def begin_fn(first, count):
+            return qp.PolynomialBatch.begin(ctx, COLS, args.rows_log, RATE_BITS, False, CAP_HEIGHT,
+                                            block_first=first, block_count=count)
+
+        def put_fn(batch, rows, c0):
+            batch.put_coeffs(rows, c0)
+
+        def end_fn(batch):
+            batch.end()
+            return batch, torch.from_numpy(batch.merkle_tree.cap.view(np.int64)).to(dev)
 
         def step(src):
             b, cap = qd.sharded_commit(src, COLS, args.rows_log, RATE_BITS, CAP_HEIGHT, rank=rank, world=world,
-                                       ifft_fn=ifft_fn, commit_fn=commit_fn, all_gather_fn=qd.torch_all_gather)
+                                       ifft_fn=ifft_fn, begin_fn=begin_fn, put_fn=put_fn, end_fn=end_fn,
+                                       all_gather_fn=qd.torch_all_gather,
+                                       all_gather_async_fn=qd.torch_all_gather_async)
             return b, cap.cpu().numpy().view(np.uint64)
 
     # ---- device-resident arm ----

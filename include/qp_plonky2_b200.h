@@ -74,6 +74,15 @@ int qp_batch_from_coeffs(qp_ctx* ctx, const uint64_t* coeffs, int space, size_t 
                          const uint64_t* salt, unsigned block_first, unsigned block_count,
                          qp_batch** out);
 void qp_batch_free(qp_batch* b);
+/* from_coeffs in pieces, for callers whose coefficient columns arrive over time (the multi-GPU
+ * path: the LDE of the columns already gathered overlaps the all-gather of the rest):
+ *   qp_batch_begin -> qp_batch_put_coeffs(columns [c0, c0 + count)) ... -> qp_batch_end (salt iff
+ *   blinding; builds the tree).  Every column must be put exactly once before qp_batch_end; the
+ *   result is the batch qp_batch_from_coeffs would have produced.  Getters are valid after end. */
+int qp_batch_begin(qp_ctx* ctx, size_t n_cols, unsigned degree_log, unsigned rate_bits, int blinding,
+                   unsigned cap_height, unsigned block_first, unsigned block_count, qp_batch** out);
+int qp_batch_put_coeffs(qp_batch* b, const uint64_t* coeffs, int space, size_t c0, size_t count);
+int qp_batch_end(qp_batch* b, const uint64_t* salt, int space);
 
 /* iNTT of columns only (the "IFFT" scope, oracle.rs:176-180): values[n_cols][n] -> coeffs.
  * Used by the multi-GPU path, which shards columns for the iNTT and cosets for the rest. */

@@ -121,6 +121,9 @@ def lib():
         "qp_batch_from_values": (i32, [vp, vp, i32, sz, u32, u32, i32, u32, vp, u32, u32, pp]),
         "qp_batch_from_coeffs": (i32, [vp, vp, i32, sz, u32, u32, i32, u32, vp, u32, u32, pp]),
         "qp_batch_free": (None, [vp]),
+        "qp_batch_begin": (i32, [vp, sz, u32, u32, i32, u32, u32, u32, pp]),
+        "qp_batch_put_coeffs": (i32, [vp, vp, i32, sz, sz]),
+        "qp_batch_end": (i32, [vp, vp, i32]),
         "qp_ifft_columns": (i32, [vp, vp, i32, sz, u32, vp, i32]),
         "qp_batch_cap": (i32, [vp, vp, i32]),
         "qp_batch_cap_len": (sz, [vp]),
@@ -408,6 +411,44 @@ class PolynomialBatch:
         ms = (C.c_double * 4)()
         lib().qp_batch_timing(self._h, ms)
         self.timing = dict(zip(cls.SCOPES, list(ms)))
+        lib().qp_batch_kernel_timing(self._h, ms)
+        self.kernel_ms = dict(zip(("intt", "lde", "leaf_hash", "tree_levels"), list(ms)))
+        return self
+
+    # ---- from_coeffs in pieces (columns arriving over time, e.g. from an all-gather) ----
+    @classmethod
+    def begin(cls, ctx, n_cols, degree_log, rate_bits, blinding, cap_height, block_first=0, block_count=None):
+        if block_count is None:
+            block_count = 1 << rate_bits
+        self = cls()
+        self.ctx = ctx
+        ctx.check(lib().qp_batch_begin(ctx._h, n_cols, degree_log, rate_bits, int(bool(blinding)), cap_height,
+                                       block_first, block_count, C.byref(self._h)))
+        self.n_cols, self.degree_log, self.rate_bits = n_cols, degree_log, rate_bits
+        self.blinding, self.cap_height = bool(blinding), cap_height
+        self.block_first, self.block_count = block_first, block_count
+        return self
+
+    def put_coeffs(self, coeffs, c0):
+        """Coefficient columns [c0, c0 + len(coeffs)): copied in and extended (LDE) right away."""
+        p, space, keep, shape = _buf(coeffs)
+        if len(shape) != 2 or shape[1] != 1 << self.degree_log:
+            raise QpError(4, "Polynomial degrees inconsistent")
+        self.ctx.check(lib().qp_batch_put_coeffs(self._h, p, space, c0, shape[0]))
+
+    def end(self, salt=None):
+        sp, sspace, skeep = None, QP_HOST, None
+        if salt is not None:
+            sp, sspace, skeep, _ = _buf(salt)
+        self.ctx.check(lib().qp_batch_end(self._h, sp, sspace))
+        self.leaf_len = int(lib().qp_batch_leaf_len(self._h))
+        self.n_local_leaves = self.block_count << self.degree_log
+        self.local_lg_leaves = self.n_local_leaves.bit_length() - 1
+        self.local_cap_height = int(lib().qp_batch_cap_len(self._h)).bit_length() - 1
+        self.merkle_tree = BatchMerkleView(self)
+        ms = (C.c_double * 4)()
+        lib().qp_batch_timing(self._h, ms)
+        self.timing = dict(zip(self.SCOPES, list(ms)))
         lib().qp_batch_kernel_timing(self._h, ms)
         self.kernel_ms = dict(zip(("intt", "lde", "leaf_hash", "tree_levels"), list(ms)))
         return self

@@ -869,6 +869,60 @@ extern "C" int qp_batch_from_values(qp_ctx* ctx, const uint64_t* values, int spa
     return QP_OK;
 }
 
+// from_coeffs in pieces (multi-GPU: the LDE of the columns that have arrived overlaps the
+// all-gather of the rest): begin allocates, put copies coefficient columns [c0, c0 + count) in and
+// extends them, end hashes.  Same kernels and the same result as qp_batch_from_coeffs.
+extern "C" int qp_batch_begin(qp_ctx* ctx, size_t n_cols, unsigned degree_log, unsigned rate_bits, int blinding,
+                              unsigned cap_height, unsigned block_first, unsigned block_count, qp_batch** out) {
+    static const uint64_t dummy_salt = 0;  // presence is checked at qp_batch_end
+    int rc = check_batch_args(ctx, n_cols, degree_log, rate_bits, blinding, cap_height,
+                              blinding ? &dummy_salt : nullptr, block_first, block_count, out);
+    if (rc) return rc;
+    uint64_t* d_coeffs = nullptr;
+    rc = dev_alloc(ctx, &d_coeffs, n_cols << degree_log);
+    if (rc) return rc;
+    rc = batch_create(ctx, d_coeffs, n_cols, degree_log, rate_bits, blinding, cap_height, block_first, block_count, out);
+    if (rc) {
+        if (*out) {
+            qp_batch_free(*out);
+            *out = nullptr;
+        } else {
+            dev_free(ctx, d_coeffs);
+        }
+        return rc;
+    }
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    return QP_OK;
+}
+
+extern "C" int qp_batch_put_coeffs(qp_batch* b, const uint64_t* coeffs, int space, size_t c0, size_t count) {
+    if (!b) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = b->ctx;
+    if (!coeffs || c0 + count > b->n_cols) return fail(ctx, QP_ERR_BAD_ARG, "column range out of bounds");
+    if (count == 0) return QP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)1 << b->degree_log;
+    CUDA_TRY(ctx, cudaMemcpyAsync(b->coeffs + c0 * n, coeffs, count * n * 8,
+                                  space == QP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    if (space != QP_DEVICE) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the host buffer may go away
+    return batch_lde_columns(b, c0, c0 + count);
+}
+
+extern "C" int qp_batch_end(qp_batch* b, const uint64_t* salt, int space) {
+    if (!b) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = b->ctx;
+    if (b->blinding && !salt) return fail(ctx, QP_ERR_BLINDING_NO_SALT, "Cannot set blinding without salt");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t* d_salt = nullptr;
+    uint64_t* salt_owned = nullptr;
+    int rc = QP_OK;
+    if (b->blinding)
+        rc = to_device(ctx, salt, space, (size_t)QP_SALT_SIZE << (b->degree_log + b->rate_bits), &d_salt, &salt_owned);
+    if (!rc) rc = batch_finish(b, d_salt);
+    dev_free(ctx, salt_owned);
+    return rc;
+}
+
 extern "C" int qp_ifft_columns(qp_ctx* ctx, const uint64_t* values, int space, size_t n_cols,
                                unsigned degree_log, uint64_t* coeffs_out, int out_space) {
     if (!ctx) return QP_ERR_BAD_ARG;

@@ -4,9 +4,11 @@ Decomposition: leaf i of the commitment is the point g*w_
 top rate_bits bits of the leaf index select one of the 2^rate_bits cosets of the size-n
 subgroup -- which is simultaneously a contiguous range of leaves, i.e. whole cap subtrees.
   1. "IFFT": columns are sharded across ranks (each rank uploads and inverts only its columns);
-  2. all-gather of the coefficients (the ONE data-path collective: n_cols * n * 8 bytes total);
-  3. "FFT + blinding" and "build Merkle tree": rank q computes, for ALL columns, the coset
-     blocks [q * 2^r / W, (q+1) * 2^r / W) and hashes exactly those leaves -- complete rows, local;
+  2. all-gather of the coefficients (the ONE data-path collective: n_cols * n * 8 bytes total),
+     issued in a few pieces so that
+  3. "FFT + blinding" of the columns that have arrived overlaps the rest of the transfer; then
+     "build Merkle tree": rank q computes, for ALL columns, the coset blocks
+     [q * 2^r / W, (q+1) * 2^r / W) and hashes exactly those leaves -- complete rows, local;
   4. all-gather of the cap entries (2^cap_height * 32 bytes) for the host transcript.
 The reference has no counterpart (it is single-process rayon); the result is bit-identical to
 the single-GPU commitment because each leaf and each subtree is computed by the same kernels.
@@ -41,24 +43,41 @@ def padded_cols(n_cols: int, world: int) -> int:
     return -(-n_cols // world)
 
 
+GATHER_CHUNKS = 4  # the coefficient all-gather is issued in this many pieces
+
+
 def sharded_commit(values_local, n_cols, degree_log, rate_bits, cap_height, *, rank, world, ifft_fn,
-                   commit_fn, all_gather_fn):
-    """Run steps 1-4.  values_local: this rank's columns [c_local][n].
+                   begin_fn, put_fn, end_fn, all_gather_fn, all_gather_async_fn=None):
+    """Run steps 1-4.  values_local: this rank's columns [c_local][n] (column_shard).
     ifft_fn(values_local, out_rows) -> coefficients [out_rows][n] (first c_local rows meaningful)
     all_gather_fn(x) -> concatenation over ranks along axis 0
-    commit_fn(coeffs_all [n_cols][n], block_first, block_count) -> (batch, cap_local [k][4])
-    Returns (batch_local, cap_full [2^cap_height][4])."""
+    all_gather_async_fn(x) -> (result, wait): the same, started now and complete after wait()
+    begin_fn(block_first, block_count) -> batch under construction (PolynomialBatch.begin)
+    put_fn(batch, coeff_rows, c0)      -> columns [c0, c0 + len) are in; their LDE may start
+    end_fn(batch) -> (batch, cap_local [k][4])
+    The all-gather of the coefficients runs in GATHER_CHUNKS pieces, all started up front: the LDE
+    of piece k overlaps the transfer of the later pieces.  Returns (batch_local, cap_full)."""
+    if all_gather_async_fn is None:
+        def all_gather_async_fn(x):
+            return all_gather_fn(x), (lambda: None)
     pc = padded_cols(n_cols, world)
     coeffs_local = ifft_fn(values_local, pc)                      # [pc][n], zero rows as padding
-    gathered = all_gather_fn(coeffs_local)                        # [world * pc][n]
-    # drop the padding rows: rank r contributed columns column_shard(r)
-    keep = []
-    for r in range(world):
-        lo, hi = column_shard(n_cols, world, r)
-        keep.extend(range(r * pc, r * pc + (hi - lo)))
-    coeffs_all = gathered if len(keep) == gathered.shape[0] else gathered[keep]
+    step = -(-pc // GATHER_CHUNKS)
+    pieces = []
+    for r0 in range(0, pc, step):
+        r1 = min(r0 + step, pc)
+        pieces.append((r0, r1) + tuple(all_gather_async_fn(coeffs_local[r0:r1])))   # [world * (r1 - r0)][n]
     first, count = block_shard(rate_bits, cap_height, world, rank)
-    batch, cap_local = commit_fn(coeffs_all, first, count)
+    batch = begin_fn(first, count)
+    for r0, r1, gathered, wait in pieces:
+        wait()
+        for r in range(world):
+            lo, hi = column_shard(n_cols, world, r)
+            v1 = min(r1, hi - lo)                                 # rank r's rows past hi - lo are padding
+            if v1 > r0:
+                base = r * (r1 - r0)
+                put_fn(batch, gathered[base: base + (v1 - r0)], lo + r0)
+    batch, cap_local = end_fn(batch)
     cap_full = all_gather_fn(cap_local)
     return batch, cap_full
 
@@ -76,3 +95,18 @@ def torch_all_gather(x, group=None):
     out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     dist.all_gather_into_tensor(out, t, group=group)
     return out.numpy().view(np.uint64) if is_np else out
+
+
+def torch_all_gather_async(x, group=None):
+    """all_gather along axis 0 started asynchronously: -> (result, wait).  wait() makes the current
+    stream (NCCL) or the host (gloo) wait for the collective."""
+    import torch
+    import torch.distributed as dist
+
+    is_np = isinstance(x, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(x).view(np.int64)) if is_np else x.contiguous()
+    world = dist.get_world_size(group)
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    work = dist.all_gather_into_tensor(out, t, group=group, async_op=True)
+    res = out.numpy().view(np.uint64) if is_np else out
+    return res, work.wait

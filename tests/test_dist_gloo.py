@@ -36,20 +36,35 @@ def _worker(rank, world, port, n_cols, lg_n, rate, cap_h, ret):
                 out[k] = oracle.ifft(v[k])
             return out
 
-        def commit_fn(coeffs_all, first, count):
+        state = {}
+
+        def begin_fn(first, count):
+            state["first"], state["count"] = first, count
+            state["seen"] = np.zeros(n_cols, dtype=int)
+            return np.zeros((n_cols, 1 << lg_n), dtype=np.uint64)
+
+        def put_fn(batch, rows, c0):
+            batch[c0:c0 + rows.shape[0]] = rows
+            state["seen"][c0:c0 + rows.shape[0]] += 1
+
+        def end_fn(coeffs_all):
+            assert (state["seen"] == 1).all(), "every column must be put exactly once"
             assert (coeffs_all == want.polynomials).all(), "gathered coefficients differ"
             b = oracle.PolynomialBatch.from_coeffs(coeffs_all, rate, cap_h)
             per_block = (1 << cap_h) >> rate
+            first, count = state["first"], state["count"]
             return b, b.cap[first * per_block : (first + count) * per_block].copy()
 
         _, cap = qd.sharded_commit(vals[lo:hi], n_cols, lg_n, rate, cap_h, rank=rank, world=world,
-                                   ifft_fn=ifft_fn, commit_fn=commit_fn, all_gather_fn=qd.torch_all_gather)
+                                   ifft_fn=ifft_fn, begin_fn=begin_fn, put_fn=put_fn, end_fn=end_fn,
+                                   all_gather_fn=qd.torch_all_gather,
+                                   all_gather_async_fn=qd.torch_all_gather_async)
         ret[rank] = bool((cap == want.cap).all())
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n_cols", [(2, 5), (2, 8), (4, 7)])
+@pytest.mark.parametrize("world,n_cols", [(2, 5), (2, 8), (4, 7), (2, 19), (4, 35)])
 def test_sharded_commit_plumbing(world, n_cols):
     import torch.multiprocessing as mp
 

@@ -505,3 +505,25 @@ def test_from_values_pipelined_upload_with_partial_leaf_hashing(qp, ctx, cols, l
     assert (got.polynomials == want.polynomials).all()
     assert (got.merkle_tree.leaves() == want.leaves).all()
     assert got.kernel_ms["leaf_hash"] > 0
+
+
+@pytest.mark.parametrize("cols,lg_n,blinding,first,count", [(7, 8, False, 0, 8), (19, 10, True, 0, 8), (35, 9, False, 4, 4),
+                                                            (5, 6, False, 6, 2)])
+def test_batch_in_pieces_equals_from_coeffs(qp, ctx, cols, lg_n, blinding, first, count):
+    """qp_batch_begin / put_coeffs / end (columns arriving in arbitrary pieces, as from the chunked
+    all-gather of the multi-GPU path) gives the batch from_coeffs gives."""
+    n = 1 << lg_n
+    co = oracle.rand_felts((cols, n), 800 + cols)
+    salt = oracle.rand_felts((4, n << 3), 801 + cols) if blinding else None
+    want = qp.PolynomialBatch.from_coeffs(ctx, co, 3, blinding, 4, salt=salt, block_first=first, block_count=count)
+    b = qp.PolynomialBatch.begin(ctx, cols, lg_n, 3, blinding, 4, block_first=first, block_count=count)
+    order = list(range(0, cols, 3))
+    for c0 in order[1::2] + order[0::2]:          # out of order, ragged last piece
+        b.put_coeffs(co[c0:c0 + 3], c0)
+    b.end(salt)
+    assert (b.merkle_tree.cap == want.merkle_tree.cap).all()
+    assert (b.merkle_tree.digests == want.merkle_tree.digests).all()
+    assert (b.polynomials == want.polynomials).all()
+    assert (b.merkle_tree.leaves() == want.merkle_tree.leaves()).all()
+    with pytest.raises(qp.QpError):
+        b.put_coeffs(co[:2], cols - 1)            # past the last column
