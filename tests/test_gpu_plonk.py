@@ -177,3 +177,24 @@ def test_large_proof_openings_pass_the_verifier(qp, ctx):
     ch.observe_cap(caps[2])
     zeta = ch.get_extension_challenge()
     assert verifier_plonk_identity(c, openings, zeta, betas, gammas, alphas, pih)
+
+
+@pytest.mark.parametrize("degree_bits,poseidon", [(10, False), (14, True)])
+def test_device_proof_is_accepted_by_the_restated_verifier(qp, ctx, degree_bits, poseidon):
+    """The reference's own acceptance criterion: the full verifier (tests/verifier.py: transcript,
+    plonk identity at zeta, PoW, 28 FRI query rounds with every Merkle path, folding consistency,
+    final polynomial) accepts the device's proof under standard_recursion_config -- at a size where
+    the oracle prover is no longer run -- and rejects it after a bit flip."""
+    import verifier
+    from qp_plonky2_b200 import prover
+
+    sc = SynthCircuit(degree_bits, seed=300 + degree_bits, poseidon=poseidon)
+    c = sc.common
+    circ = plonk.Circuit(ctx, c, sc.sigmas)
+    pd = prover.ProverData(ctx, circ, sc.constants_sigmas())
+    proof = prover.prove(pd, sc.wires, sc.public_inputs)
+    cap = pd.constants_sigmas_commitment.merkle_tree.cap
+    assert verifier.verify(proof, c, pd.fri, cap, pd.circuit_digest) is None
+    bad = bytearray(proof)
+    bad[len(bad) // 2] ^= 4
+    assert verifier.verify(bytes(bad), c, pd.fri, cap, pd.circuit_digest) is not None

@@ -212,3 +212,41 @@ def test_host_hash_no_pad_and_circuit_digest_match_oracle():
     out = np.zeros(4, dtype=np.uint64)
     L.qp_circuit_digest(cap.ctypes.data, 16, 13, out.ctypes.data)
     assert (out == oprover.circuit_digest(cap, 13)).all()
+
+
+class _Fri:
+    def __init__(self, rate_bits=3, cap_height=4, proof_of_work_bits=16, arity_bits=4, final_poly_bits=5,
+                 num_query_rounds=28):
+        self.rate_bits, self.cap_height, self.proof_of_work_bits = rate_bits, cap_height, proof_of_work_bits
+        self.arity_bits, self.final_poly_bits, self.num_query_rounds = arity_bits, final_poly_bits, num_query_rounds
+
+
+@pytest.mark.parametrize("degree_bits,qdf,poseidon,pow_bits,queries", [(6, 8, False, 6, 5), (8, 8, True, 10, 9), (7, 4, False, 5, 4)])
+def test_restated_verifier_accepts_oracle_proofs_and_rejects_tampering(degree_bits, qdf, poseidon, pow_bits, queries):
+    """The reference's acceptance criterion for everything above the permutation:
+    the full verifier -- transcript, plonk identity, PoW, FRI query rounds with every Merkle path,
+    folding consistency, final polynomial -- accepts the oracle's proof and rejects a flipped bit in
+    any part of it."""
+    from oracle import prover as oprover
+    import verifier
+
+    sc = SynthCircuit(degree_bits, seed=91, quotient_degree_factor=qdf, poseidon=poseidon)
+    c = sc.common
+    cs = oracle.PolynomialBatch.from_values(sc.constants_sigmas(), c.rate_bits, c.cap_height)
+    proof, info = _oracle_prove(sc, proof_of_work_bits=pow_bits, num_query_rounds=queries)
+    fri = _Fri(c.rate_bits, c.cap_height, pow_bits, 4, 5, queries)
+    digest = oprover.circuit_digest(cs.cap, degree_bits)
+    assert verifier.verify(proof, c, fri, cs.cap, digest) is None
+    # tampering: one bit in each region of the proof
+    cap_bytes = 3 * (4 << c.cap_height) * 8
+    n_open = (c.num_constants + c.num_routed_wires + c.num_wires + c.num_challenges * (2 + c.num_partial_products) +
+              c.num_challenges * c.quotient_degree_factor)
+    spots = {"wires cap": 5, "quotient cap": cap_bytes - 9, "an opening": cap_bytes + 16 * 7,
+             "commit-phase cap": cap_bytes + 16 * n_open + 3, "a query leaf": cap_bytes + 16 * n_open + 4000,
+             "final poly / pow": len(proof) - 8 * (1 + len(sc.public_inputs)) - 5, "a public input": len(proof) - 3}
+    for what, at in spots.items():
+        bad = bytearray(proof)
+        bad[at] ^= 1
+        assert verifier.verify(bytes(bad), c, fri, cs.cap, digest) is not None, what
+    # and a wrong circuit digest changes every challenge
+    assert verifier.verify(proof, c, fri, cs.cap, digest ^ np.uint64(1)) is not None
