@@ -73,11 +73,14 @@ int qp_fri_proof(qp_ctx* ctx, const qp_batch* const* initial_oracles, size_t n_o
  * (qp_plonky2_b200.h): gates are sorted by (degree, id) like CircuitBuilder::build does
  * (circuit_builder.rs:1177-1179), grouped into selector polynomials (gates/selectors.rs:99-166,
  * max_degree = quotient_degree_factor + 1), filtered (gates/gate.rs:326-333) and evaluated
- * symbolically (Gate::eval_unfiltered of gates/{noop,constant,public_input,arithmetic_base,poseidon}.rs). */
-enum { QP_GATE_NOOP = 0, QP_GATE_CONSTANT = 1, QP_GATE_PUBLIC_INPUT = 2, QP_GATE_ARITHMETIC = 3, QP_GATE_POSEIDON = 4 };
+ * symbolically (Gate::eval_unfiltered of gates/{noop,constant,public_input,arithmetic_base,poseidon,
+ * arithmetic_extension,multiplication_extension,base_sum}.rs). */
+enum { QP_GATE_NOOP = 0, QP_GATE_CONSTANT = 1, QP_GATE_PUBLIC_INPUT = 2, QP_GATE_ARITHMETIC = 3, QP_GATE_POSEIDON = 4,
+       QP_GATE_ARITHMETIC_EXT = 5, QP_GATE_MUL_EXT = 6, QP_GATE_BASE_SUM_2 = 7 };
 typedef struct {
     uint32_t kind;   /* QP_GATE_* */
-    uint32_t param;  /* ConstantGate: num_consts; ArithmeticGate: num_ops; otherwise 0 */
+    uint32_t param;  /* ConstantGate: num_consts; Arithmetic / ArithmeticExtension / MulExtension: num_ops;
+                        BaseSumGate<2>: num_limbs; otherwise 0 */
 } qp_gate_desc;
 typedef struct qp_program qp_program;
 int qp_program_create(const qp_gate_desc* gates, size_t n_gates, unsigned max_degree, qp_program** out);

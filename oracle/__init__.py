@@ -410,6 +410,7 @@ def fri_proof_bytes(oracle_batches, coeffs, values, challenger, rate_bits, cap_h
 # plonk permutation argument and quotient (plonky2/src/plonk/prover.rs:402-480,640-866)
 # ---------------------------------------------------------------------------------------------
 GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON = 0, 1, 2, 3, 4
+GATE_ARITHMETIC_EXT, GATE_MUL_EXT, GATE_BASE_SUM_2 = 5, 6, 7
 
 
 class _OrcGate(C.Structure):

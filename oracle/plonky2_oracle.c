@@ -825,6 +825,34 @@ static void gate_eval_add(const orc_gate *g, const uint64_t *consts, const uint6
             acc[i] = gl_add(acc[i], gl_mul(filter, gl_sub(out, computed)));
         }
         break;
+    case ORC_GATE_ARITHMETIC_EXT: /* gates/arithmetic_extension.rs:92-110 */
+        for (unsigned i = 0; i < g->param; i++) {
+            const uint64_t *w = wires + 8 * i;
+            uint64_t pr[2];
+            orc_ext_mul(w, w + 2, pr);
+            for (int k = 0; k < 2; k++) {
+                uint64_t computed = gl_add(gl_mul(pr[k], consts[0]), gl_mul(w[4 + k], consts[1]));
+                acc[2 * i + k] = gl_add(acc[2 * i + k], gl_mul(filter, gl_sub(w[6 + k], computed)));
+            }
+        }
+        break;
+    case ORC_GATE_MUL_EXT: /* gates/multiplication_extension.rs:86-101 */
+        for (unsigned i = 0; i < g->param; i++) {
+            const uint64_t *w = wires + 6 * i;
+            uint64_t pr[2];
+            orc_ext_mul(w, w + 2, pr);
+            for (int k = 0; k < 2; k++)
+                acc[2 * i + k] = gl_add(acc[2 * i + k], gl_mul(filter, gl_sub(w[4 + k], gl_mul(pr[k], consts[0]))));
+        }
+        break;
+    case ORC_GATE_BASE_SUM_2: { /* gates/base_sum.rs:153-170, B = 2 */
+        uint64_t sum = 0;
+        for (unsigned i = g->param; i >= 1; i--) sum = gl_add(gl_mul(sum, 2), wires[i]); /* reduce_with_powers */
+        acc[0] = gl_add(acc[0], gl_mul(filter, gl_sub(sum, wires[0])));
+        for (unsigned i = 1; i <= g->param; i++)
+            acc[i] = gl_add(acc[i], gl_mul(filter, gl_mul(wires[i], gl_sub(wires[i], 1))));
+        break;
+    }
     case ORC_GATE_POSEIDON: {
         uint64_t c[123];
         poseidon_gate_eval(wires, c);
@@ -900,6 +928,9 @@ static void poseidon_gate_eval(const uint64_t *wires, uint64_t *c /* 123 constra
 unsigned orc_gate_num_constraints(const orc_gate *g) {
     switch (g->kind) {
     case ORC_GATE_POSEIDON: return 123; /* poseidon.rs:416-422 */
+    case ORC_GATE_ARITHMETIC_EXT: return 2 * g->param;
+    case ORC_GATE_MUL_EXT: return 2 * g->param;
+    case ORC_GATE_BASE_SUM_2: return 1 + g->param;
     case ORC_GATE_CONSTANT: return g->param;
     case ORC_GATE_PUBLIC_INPUT: return 4;
     case ORC_GATE_ARITHMETIC: return g->param;

@@ -125,7 +125,7 @@ void orc_reduce_openings(size_t n_batches, const size_t *n_terms, const uint64_t
 /* ---- plonk permutation argument and quotient (plonky2/src/plonk/prover.rs:402-480,640-866,
  *      plonky2/src/plonk/vanishing_poly.rs:166-330) -------------------------------------------- */
 enum { ORC_GATE_NOOP = 0, ORC_GATE_CONSTANT = 1, ORC_GATE_PUBLIC_INPUT = 2, ORC_GATE_ARITHMETIC = 3,
-       ORC_GATE_POSEIDON = 4 };
+       ORC_GATE_POSEIDON = 4, ORC_GATE_ARITHMETIC_EXT = 5, ORC_GATE_MUL_EXT = 6, ORC_GATE_BASE_SUM_2 = 7 };
 typedef struct {
     uint32_t kind;           /* ORC_GATE_* */
     uint32_t param;          /* num_consts (ConstantGate) / num_ops (ArithmeticGate) */

@@ -6,8 +6,10 @@
 //   selector groups                 plonky2/src/gates/selectors.rs:99-166
 //   compute_filter                  plonky2/src/gates/gate.rs:326-333
 //   evaluate_gate_constraints       plonky2/src/plonk/vanishing_poly.rs:700-726
-//   NoopGate / ConstantGate / PublicInputGate / ArithmeticGate / PoseidonGate
-//                                   plonky2/src/gates/{noop,constant,public_input,arithmetic_base,poseidon}.rs
+//   NoopGate / ConstantGate / PublicInputGate / ArithmeticGate / PoseidonGate / ArithmeticExtensionGate /
+//   MulExtensionGate / BaseSumGate<2>
+//                                   plonky2/src/gates/{noop,constant,public_input,arithmetic_base,poseidon,
+//                                   arithmetic_extension,multiplication_extension,base_sum}.rs
 // In a Rust build this role is played by the shim's recording field type run over
 // Gate::eval_unfiltered_base_one; here the same recording evaluation is written in
 // C++ for the gates above.  Pure host logic: no field arithmetic on data happens here.
@@ -107,9 +109,21 @@ GateInfo gate_info(uint32_t kind, uint32_t param) {
         case QP_GATE_POSEIDON:
             return {kind, param, 7, 0, 123,
                     "PoseidonGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>"};
+        case QP_GATE_ARITHMETIC_EXT:
+            return {kind, param, 3, 2, 2 * param, "ArithmeticExtensionGate { num_ops: " + std::to_string(param) + " }"};
+        case QP_GATE_MUL_EXT:
+            return {kind, param, 3, 1, 2 * param, "MulExtensionGate { num_ops: " + std::to_string(param) + " }"};
+        case QP_GATE_BASE_SUM_2:
+            return {kind, param, 2, 0, 1 + param, "BaseSumGate { num_limbs: " + std::to_string(param) + " } + Base: 2"};
     }
     return {kind, param, 0, 0, 0, ""};
 }
+
+// F_p^2 = F_p[X]/(X^2 - 7) over recording values (field/src/extension/quadratic.rs:186-199)
+struct ExtVal {
+    Val a, b;
+};
+ExtVal ext_mul(ExtVal x, ExtVal y) { return ExtVal{x.a * y.a + (x.b * y.b) * 7, x.a * y.b + x.b * y.a}; }
 
 Val sbox(Val x) {  // core/src/poseidon.rs:546-552
     Val x2 = x * x, x4 = x2 * x2;
@@ -208,6 +222,39 @@ void eval_gate(Recorder& R, const GateInfo& g, unsigned prefix, std::vector<Val>
             break;
         }
         case QP_GATE_POSEIDON: eval_poseidon(R, c); break;
+        case QP_GATE_ARITHMETIC_EXT: {  // arithmetic_extension.rs:92-110, D = 2
+            Val c0 = R.constant(prefix), c1 = R.constant(prefix + 1);
+            for (unsigned i = 0; i < g.param; i++) {
+                ExtVal m0{R.wire(8 * i), R.wire(8 * i + 1)}, m1{R.wire(8 * i + 2), R.wire(8 * i + 3)};
+                ExtVal ad{R.wire(8 * i + 4), R.wire(8 * i + 5)}, out{R.wire(8 * i + 6), R.wire(8 * i + 7)};
+                ExtVal pr = ext_mul(m0, m1);
+                c.push_back(out.a - (pr.a * c0 + ad.a * c1));
+                c.push_back(out.b - (pr.b * c0 + ad.b * c1));
+            }
+            break;
+        }
+        case QP_GATE_MUL_EXT: {  // multiplication_extension.rs:86-101
+            Val c0 = R.constant(prefix);
+            for (unsigned i = 0; i < g.param; i++) {
+                ExtVal m0{R.wire(6 * i), R.wire(6 * i + 1)}, m1{R.wire(6 * i + 2), R.wire(6 * i + 3)};
+                ExtVal out{R.wire(6 * i + 4), R.wire(6 * i + 5)};
+                ExtVal pr = ext_mul(m0, m1);
+                c.push_back(out.a - pr.a * c0);
+                c.push_back(out.b - pr.b * c0);
+            }
+            break;
+        }
+        case QP_GATE_BASE_SUM_2: {  // base_sum.rs:153-170 with B = 2
+            // reduce_with_powers(limbs, 2): Horner from the last limb
+            Val acc = R.wire((int)g.param);
+            for (int i = (int)g.param - 1; i >= 1; i--) acc = acc * 2 + R.wire(i);
+            c.push_back(acc - R.wire(0));
+            for (unsigned i = 1; i <= g.param; i++) {
+                Val limb = R.wire((int)i);
+                c.push_back(limb * (limb - 1));  // (limb - 0)(limb - 1)
+            }
+            break;
+        }
         default: break;
     }
 }

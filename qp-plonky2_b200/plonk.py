@@ -182,7 +182,8 @@ class ConstraintProgram:
 
 
 # ---- gates ------------------------------------------------------------------------------------------
-GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON = range(5)  # qp_plonky2_host.h
+(GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON, GATE_ARITHMETIC_EXT, GATE_MUL_EXT,
+ GATE_BASE_SUM_2) = range(8)  # qp_plonky2_host.h
 
 
 class Gate:
@@ -257,6 +258,86 @@ class ArithmeticGate(Gate):  # plonky2/src/gates/arithmetic_base.rs
         for i in range(self.num_ops):  # arithmetic_base.rs:168-185
             m0, m1, addend, output = wires(4 * i), wires(4 * i + 1), wires(4 * i + 2), wires(4 * i + 3)
             out.append(output - (m0 * m1 * c0 + addend * c1))
+        return out
+
+
+def _ext_mul(x, y):
+    """(a0 + a1 X)(b0 + b1 X) mod X^2 - 7, field/src/extension/quadratic.rs:186-199."""
+    return (x[0] * y[0] + (x[1] * y[1]) * 7, x[0] * y[1] + x[1] * y[0])
+
+
+class ArithmeticExtensionGate(Gate):  # plonky2/src/gates/arithmetic_extension.rs (D = 2)
+    degree = 3
+    num_constants = 2
+    kind = GATE_ARITHMETIC_EXT
+
+    def __init__(self, num_ops):
+        self.num_ops = self.param = num_ops
+        self.num_constraints = 2 * num_ops
+
+    @staticmethod
+    def new_from_config(num_routed_wires):
+        return ArithmeticExtensionGate(num_routed_wires // 8)
+
+    def id(self):
+        return "ArithmeticExtensionGate { num_ops: %d }" % self.num_ops
+
+    def eval_unfiltered(self, consts, wires, pih):
+        c0, c1 = consts(0), consts(1)
+        out = []
+        for i in range(self.num_ops):  # arithmetic_extension.rs:92-110
+            w = [wires(8 * i + k) for k in range(8)]
+            pr = _ext_mul((w[0], w[1]), (w[2], w[3]))
+            out.append(w[6] - (pr[0] * c0 + w[4] * c1))
+            out.append(w[7] - (pr[1] * c0 + w[5] * c1))
+        return out
+
+
+class MulExtensionGate(Gate):  # plonky2/src/gates/multiplication_extension.rs (D = 2)
+    degree = 3
+    num_constants = 1
+    kind = GATE_MUL_EXT
+
+    def __init__(self, num_ops):
+        self.num_ops = self.param = num_ops
+        self.num_constraints = 2 * num_ops
+
+    @staticmethod
+    def new_from_config(num_routed_wires):
+        return MulExtensionGate(num_routed_wires // 6)
+
+    def id(self):
+        return "MulExtensionGate { num_ops: %d }" % self.num_ops
+
+    def eval_unfiltered(self, consts, wires, pih):
+        c0 = consts(0)
+        out = []
+        for i in range(self.num_ops):  # multiplication_extension.rs:86-101
+            w = [wires(6 * i + k) for k in range(6)]
+            pr = _ext_mul((w[0], w[1]), (w[2], w[3]))
+            out.append(w[4] - pr[0] * c0)
+            out.append(w[5] - pr[1] * c0)
+        return out
+
+
+class BaseSumGate2(Gate):  # plonky2/src/gates/base_sum.rs with B = 2
+    degree = 2
+    kind = GATE_BASE_SUM_2
+
+    def __init__(self, num_limbs):
+        self.num_limbs = self.param = num_limbs
+        self.num_constraints = 1 + num_limbs
+
+    def id(self):
+        return "BaseSumGate { num_limbs: %d } + Base: 2" % self.num_limbs
+
+    def eval_unfiltered(self, consts, wires, pih):
+        acc = wires(self.num_limbs)           # reduce_with_powers(limbs, 2), base_sum.rs:153-170
+        for i in range(self.num_limbs - 1, 0, -1):
+            acc = acc * 2 + wires(i)
+        out = [acc - wires(0)]
+        for i in range(1, self.num_limbs + 1):
+            out.append(wires(i) * (wires(i) - 1))
         return out
 
 

@@ -31,7 +31,7 @@ def _addmod(a, b):
 
 class SynthCircuit:
     def __init__(self, degree_bits, seed=1, num_wires=143, num_routed_wires=80, num_challenges=2,
-                 quotient_degree_factor=8, rate_bits=3, cap_height=4, poseidon=False):
+                 quotient_degree_factor=8, rate_bits=3, cap_height=4, poseidon=False, extra_gates=False):
         rng = np.random.Generator(np.random.PCG64(seed))
         n = 1 << degree_bits
         nr = num_routed_wires
@@ -40,26 +40,32 @@ class SynthCircuit:
                  plonk.ArithmeticGate.new_from_config(nr)]
         if poseidon:
             gates.append(plonk.PoseidonGate())
+        if extra_gates:   # the extension-field arithmetic and bit-decomposition gates of recursion circuits
+            gates += [plonk.ArithmeticExtensionGate.new_from_config(nr), plonk.MulExtensionGate.new_from_config(nr),
+                      plonk.BaseSumGate2(63)]
         self.common = c = plonk.CommonCircuitData(degree_bits, gates, num_wires, nr, num_challenges,
                                                   quotient_degree_factor, rate_bits, cap_height)
         kinds = {"NoopGate": oracle.GATE_NOOP, "ConstantGate": oracle.GATE_CONSTANT,
                  "PublicInputGate": oracle.GATE_PUBLIC_INPUT, "ArithmeticGate": oracle.GATE_ARITHMETIC,
-                 "PoseidonGate": oracle.GATE_POSEIDON}
+                 "PoseidonGate": oracle.GATE_POSEIDON, "ArithmeticExtensionGate": oracle.GATE_ARITHMETIC_EXT,
+                 "MulExtensionGate": oracle.GATE_MUL_EXT, "BaseSumGate": oracle.GATE_BASE_SUM_2}
         og = []
         for i, g in enumerate(c.gates):
             name = g.id().split(" ")[0].split("(")[0]
-            param = getattr(g, "num_consts", getattr(g, "num_ops", 0))
+            param = g.param
             og.append((kinds[name], param, c.selector_indices[i], c.groups[c.selector_indices[i]]))
         self.oracle_circuit = oracle.Circuit(degree_bits, c.quotient_degree_bits, num_challenges, nr, num_wires,
                                              c.num_constants, c.num_partial_products, quotient_degree_factor,
                                              c.num_selectors, og, c.k_is)
         idx = {g.id().split(" ")[0].split("(")[0]: i for i, g in enumerate(c.gates)}
         # gate per row: mostly arithmetic (and Poseidon), a few of the others; row 0 is the public-input gate
+        kinds_p = {"NoopGate": 0.2, "ConstantGate": 0.1, "ArithmeticGate": 0.7}
         if poseidon:
-            row_gate = rng.choice([idx["NoopGate"], idx["ConstantGate"], idx["ArithmeticGate"], idx["PoseidonGate"]],
-                                  size=n, p=[0.2, 0.1, 0.3, 0.4])
-        else:
-            row_gate = rng.choice([idx["NoopGate"], idx["ConstantGate"], idx["ArithmeticGate"]], size=n, p=[0.2, 0.1, 0.7])
+            kinds_p.update({"ArithmeticGate": 0.3, "PoseidonGate": 0.4})
+        if extra_gates:
+            kinds_p["ArithmeticGate"] -= 0.2
+            kinds_p.update({"ArithmeticExtensionGate": 0.08, "MulExtensionGate": 0.06, "BaseSumGate": 0.06})
+        row_gate = rng.choice([idx[k] for k in kinds_p], size=n, p=list(kinds_p.values()))
         row_gate[0] = idx["PublicInputGate"]
         self.row_gate = row_gate
         # constants: selector polynomials (selectors.rs:141-159), then the gate constants
@@ -69,6 +75,8 @@ class SynthCircuit:
             consts[s] = np.where(in_group, row_gate, plonk.UNUSED_SELECTOR if c.num_selectors > 1 else row_gate)
         gate_consts = oracle.rand_felts((c.num_gate_constants, n), seed + 1)
         uses = (row_gate == idx["ConstantGate"]) | (row_gate == idx["ArithmeticGate"])
+        if extra_gates:
+            uses |= (row_gate == idx["ArithmeticExtensionGate"]) | (row_gate == idx["MulExtensionGate"])
         consts[c.num_selectors:] = np.where(uses[None, :], gate_consts, 0)
         self.constants = consts
         # witness
@@ -119,6 +127,31 @@ class SynthCircuit:
             for o in range(num_ops):
                 m0, m1, ad = wires[4 * o][arith_rows], wires[4 * o + 1][arith_rows], wires[4 * o + 2][arith_rows]
                 wires[4 * o + 3][arith_rows] = _addmod(_mulmod(_mulmod(m0, m1), c0), _mulmod(ad, c1))
+        if extra_gates:
+            c0 = consts[c.num_selectors].astype(object)
+            c1 = consts[c.num_selectors + 1].astype(object)
+            W = wires.astype(object)
+            rows = np.nonzero(row_gate == idx["ArithmeticExtensionGate"])[0]
+            for o in range(nr // 8):   # arithmetic_extension.rs:92-110
+                b = 8 * o
+                p0 = (W[b, rows] * W[b + 2, rows] + 7 * W[b + 1, rows] * W[b + 3, rows]) % P
+                p1 = (W[b, rows] * W[b + 3, rows] + W[b + 1, rows] * W[b + 2, rows]) % P
+                wires[b + 6, rows] = ((p0 * c0[rows] + W[b + 4, rows] * c1[rows]) % P).astype(np.uint64)
+                wires[b + 7, rows] = ((p1 * c0[rows] + W[b + 5, rows] * c1[rows]) % P).astype(np.uint64)
+            rows = np.nonzero(row_gate == idx["MulExtensionGate"])[0]
+            for o in range(nr // 6):   # multiplication_extension.rs:86-101
+                b = 6 * o
+                p0 = (W[b, rows] * W[b + 2, rows] + 7 * W[b + 1, rows] * W[b + 3, rows]) % P
+                p1 = (W[b, rows] * W[b + 3, rows] + W[b + 1, rows] * W[b + 2, rows]) % P
+                wires[b + 4, rows] = ((p0 * c0[rows]) % P).astype(np.uint64)
+                wires[b + 5, rows] = ((p1 * c0[rows]) % P).astype(np.uint64)
+            rows = np.nonzero(row_gate == idx["BaseSumGate"])[0]
+            bits = rng.integers(0, 2, size=(63, len(rows)), dtype=np.uint64)   # base_sum.rs: limbs in {0, 1}
+            wires[1:64, rows] = bits
+            total = np.zeros(len(rows), dtype=object)
+            for i in range(62, -1, -1):
+                total = (total * 2 + bits[i].astype(object)) % P
+            wires[0, rows] = total.astype(np.uint64)
         # Poseidon rows: inputs and swap are free, everything else follows (PoseidonGenerator)
         if poseidon:
             pg = plonk.PoseidonGate()

@@ -63,12 +63,13 @@ def test_selectors_info_matches_reference_rule(qdf):
 
 
 @pytest.mark.parametrize("native", [False, True])
-@pytest.mark.parametrize("qdf,poseidon", [(8, False), (4, False), (8, True)])
-def test_constraint_program_matches_oracle_gate_evaluation(qdf, poseidon, native):
+@pytest.mark.parametrize("qdf,poseidon,extra", [(8, False, False), (4, False, False), (8, True, False), (8, True, True),
+                                                (4, False, True)])
+def test_constraint_program_matches_oracle_gate_evaluation(qdf, poseidon, native, extra):
     """The compiled program and the oracle's hand-written gate evaluators agree on random
     (non-satisfying) inputs: compare the full vanishing value with the permutation terms zeroed
     out by Z = partial products = 0... simpler: both sides computed in full."""
-    sc = SynthCircuit(5, seed=5, quotient_degree_factor=qdf, poseidon=poseidon)
+    sc = SynthCircuit(5, seed=5, quotient_degree_factor=qdf, poseidon=poseidon, extra_gates=extra)
     c = sc.common
     if native:   # qp-plonky2_b200/host/plonk_host.cpp, the compiler whose output the device runs
         prog = plonk.native_constraint_program(c.gates, qdf + 1)
@@ -78,16 +79,18 @@ def test_constraint_program_matches_oracle_gate_evaluation(qdf, poseidon, native
         assert prog["num_gate_constraints"] == c.num_gate_constraints
     else:
         code, pool, n_regs = c.constraint_program()
-    if poseidon:   # degree 7 forces a second selector group (selectors.rs:140-150)
+    if poseidon and not extra:   # degree 7 forces a second selector group (selectors.rs:140-150)
         assert c.groups == [(0, 4), (4, 5)] and c.num_gate_constraints == 123
+    if poseidon and extra:       # Noop, Constant, PublicInput, BaseSum, ArithmeticExtension, Arithmetic | MulExtension, Poseidon
+        assert c.groups == [(0, 6), (6, 8)]
     rng = np.random.default_rng(7)
     for trial in range(8):
         wires = oracle.rand_felts((c.num_wires,), 100 + trial)
         consts = oracle.rand_felts((c.num_constants,), 200 + trial)
         # a selector value that is a real gate index some of the time
-        consts[0] = rng.integers(0, 4)
-        if poseidon and trial % 2:
-            consts[0], consts[1] = plonk.UNUSED_SELECTOR, 4
+        consts[0] = rng.integers(0, c.groups[0][1])
+        if len(c.groups) > 1 and trial % 2:
+            consts[0], consts[1] = plonk.UNUSED_SELECTOR, rng.integers(c.groups[1][0], c.groups[1][1])
         pih = oracle.rand_felts((4,), 300 + trial)
         alphas = oracle.rand_felts((2,), 400 + trial)
         nc, np_ = c.num_challenges, c.num_partial_products
@@ -221,8 +224,10 @@ class _Fri:
         self.arity_bits, self.final_poly_bits, self.num_query_rounds = arity_bits, final_poly_bits, num_query_rounds
 
 
-@pytest.mark.parametrize("degree_bits,qdf,poseidon,pow_bits,queries", [(6, 8, False, 6, 5), (8, 8, True, 10, 9), (7, 4, False, 5, 4)])
-def test_restated_verifier_accepts_oracle_proofs_and_rejects_tampering(degree_bits, qdf, poseidon, pow_bits, queries):
+@pytest.mark.parametrize("degree_bits,qdf,poseidon,pow_bits,queries,extra", [
+    (6, 8, False, 6, 5, False), (8, 8, True, 10, 9, False), (7, 4, False, 5, 4, False), (7, 8, True, 6, 5, True)])
+def test_restated_verifier_accepts_oracle_proofs_and_rejects_tampering(degree_bits, qdf, poseidon, pow_bits, queries,
+                                                                      extra):
     """The reference's acceptance criterion for everything above the permutation:
     the full verifier -- transcript, plonk identity, PoW, FRI query rounds with every Merkle path,
     folding consistency, final polynomial -- accepts the oracle's proof and rejects a flipped bit in
@@ -230,7 +235,7 @@ def test_restated_verifier_accepts_oracle_proofs_and_rejects_tampering(degree_bi
     from oracle import prover as oprover
     import verifier
 
-    sc = SynthCircuit(degree_bits, seed=91, quotient_degree_factor=qdf, poseidon=poseidon)
+    sc = SynthCircuit(degree_bits, seed=91, quotient_degree_factor=qdf, poseidon=poseidon, extra_gates=extra)
     c = sc.common
     cs = oracle.PolynomialBatch.from_values(sc.constants_sigmas(), c.rate_bits, c.cap_height)
     proof, info = _oracle_prove(sc, proof_of_work_bits=pow_bits, num_query_rounds=queries)
