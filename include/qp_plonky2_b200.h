@@ -16,6 +16,11 @@
  *   - handles own device memory (LDE values stay on the device, column-major in leaf order);
  *     they are immutable after creation and may be read from any thread.
  *   - there is NO CPU fallback: without a CUDA device every call fails with QP_ERR_CUDA.
+ *   - threading: a context serialises its work on one stream and keeps per-call scratch (events,
+ *     error text), so calls that CREATE handles on the same context must not overlap; use one
+ *     context per calling thread (contexts are cheap: a stream and a twiddle table).  Finished
+ *     handles are immutable and may be read from any thread (the reference shares the
+ *     constants/sigmas batch across concurrent prove() calls, circuit_data.rs:337-349).
  */
 #ifndef QP_PLONKY2_B200_H
 #define QP_PLONKY2_B200_H
