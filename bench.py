@@ -326,11 +326,11 @@ def run_ours(args):
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_prove
             prove = {"what": "prove() from the witness on (wires/Z/quotient commitments, openings, FRI proof, "
-                             "serialisation) for a synthetic 143-wire circuit (40% PoseidonGate rows, 30% "
-                             "ArithmeticGate, copy constraints), standard_recursion_config; witness "
-                             "device-resident; best of 4",
+                             "serialisation) for a synthetic 143-wire circuit with all 14 gate types of a "
+                             "recursive verifier (22% PoseidonGate rows, four selector groups, copy constraints), "
+                             "standard_recursion_config; witness device-resident; best of 4",
                      "runs": bench_prove.measure([12, 13, 14], [] if args.no_cpu else [12], reps=5, device=local,
-                                                 verbose=False)}
+                                                 verbose=False, recursion=True)}
         except Exception as e:  # the headline metric does not depend on it
             prove = {"error": repr(e)}
 

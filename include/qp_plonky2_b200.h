@@ -220,6 +220,9 @@ int qp_fri_proof_of_work(qp_ctx* ctx, const uint64_t state12[12], unsigned witne
  *   10 MULI dst = r[a] * pool[b]     11 ADDI dst = r[a] + pool[b]
  *   8 EMIT a, b  constraint number b of the current gate has the value r[a]
  *   9 GATE a     end of a gate; r[a] holds its filter (compute_filter, gates/gate.rs:326-333)
+ *   0 END        end of a segment.  A program may consist of several self-contained segments
+ *                (no register is live across an END); their contributions add up, and for small
+ *                circuits different thread blocks evaluate different segments.
  * The program evaluates evaluate_gate_constraints_base_batch (vanishing_poly.rs:700-726); a Rust
  * shim produces it by running Gate::eval_unfiltered_base_one over a recording field type, the
  * Python mirror (qp-plonky2_b200/plonk.py) from its own gate classes. */

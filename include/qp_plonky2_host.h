@@ -74,13 +74,20 @@ int qp_fri_proof(qp_ctx* ctx, const qp_batch* const* initial_oracles, size_t n_o
  * (circuit_builder.rs:1177-1179), grouped into selector polynomials (gates/selectors.rs:99-166,
  * max_degree = quotient_degree_factor + 1), filtered (gates/gate.rs:326-333) and evaluated
  * symbolically (Gate::eval_unfiltered of gates/{noop,constant,public_input,arithmetic_base,poseidon,
- * arithmetic_extension,multiplication_extension,base_sum}.rs). */
+ * arithmetic_extension,multiplication_extension,base_sum,random_access,reducing,reducing_extension,
+ * poseidon_mds,exponentiation,coset_interpolation}.rs) -- the gate set of a recursive verifier circuit
+ * under standard_recursion_config. */
 enum { QP_GATE_NOOP = 0, QP_GATE_CONSTANT = 1, QP_GATE_PUBLIC_INPUT = 2, QP_GATE_ARITHMETIC = 3, QP_GATE_POSEIDON = 4,
-       QP_GATE_ARITHMETIC_EXT = 5, QP_GATE_MUL_EXT = 6, QP_GATE_BASE_SUM_2 = 7 };
+       QP_GATE_ARITHMETIC_EXT = 5, QP_GATE_MUL_EXT = 6, QP_GATE_BASE_SUM_2 = 7, QP_GATE_RANDOM_ACCESS = 8,
+       QP_GATE_REDUCING = 9, QP_GATE_REDUCING_EXT = 10, QP_GATE_POSEIDON_MDS = 11, QP_GATE_EXPONENTIATION = 12,
+       QP_GATE_COSET_INTERPOLATION = 13 };
 typedef struct {
     uint32_t kind;   /* QP_GATE_* */
     uint32_t param;  /* ConstantGate: num_consts; Arithmetic / ArithmeticExtension / MulExtension: num_ops;
-                        BaseSumGate<2>: num_limbs; otherwise 0 */
+                        BaseSumGate<2>: num_limbs; Reducing / ReducingExtension: num_coeffs;
+                        Exponentiation: num_power_bits;
+                        RandomAccess: bits | num_copies << 8 | num_extra_constants << 16;
+                        CosetInterpolation: subgroup_bits | degree << 8; otherwise 0 */
 } qp_gate_desc;
 typedef struct qp_program qp_program;
 int qp_program_create(const qp_gate_desc* gates, size_t n_gates, unsigned max_degree, qp_program** out);
@@ -88,6 +95,10 @@ void qp_program_free(qp_program* p);
 size_t qp_program_code(const qp_program* p, const uint64_t** code);
 size_t qp_program_pool(const qp_program* p, const uint64_t** pool);
 unsigned qp_program_regs(const qp_program* p);
+/* The code is a sequence of self-contained segments separated by OP_END words (a large gate set is
+ * cut into pieces of similar cost that different thread blocks evaluate; the quotient is their
+ * sum).  -> number of segments; offsets[i] = first word of segment i. */
+size_t qp_program_segments(const qp_program* p, const uint32_t** offsets);
 unsigned qp_program_num_selectors(const qp_program* p);        /* SelectorsInfo::num_selectors */
 unsigned qp_program_num_gate_constants(const qp_program* p);   /* max over gates of num_constants */
 unsigned qp_program_num_gate_constraints(const qp_program* p); /* common_data.num_gate_constraints */

@@ -411,6 +411,8 @@ def fri_proof_bytes(oracle_batches, coeffs, values, challenger, rate_bits, cap_h
 # ---------------------------------------------------------------------------------------------
 GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON = 0, 1, 2, 3, 4
 GATE_ARITHMETIC_EXT, GATE_MUL_EXT, GATE_BASE_SUM_2 = 5, 6, 7
+(GATE_RANDOM_ACCESS, GATE_REDUCING, GATE_REDUCING_EXT, GATE_POSEIDON_MDS, GATE_EXPONENTIATION,
+ GATE_COSET_INTERPOLATION) = range(8, 14)
 
 
 class _OrcGate(C.Structure):

@@ -803,6 +803,47 @@ static uint64_t gate_filter(const orc_gate *g, uint64_t s, int many_selectors) {
 
 static void poseidon_gate_eval(const uint64_t *wires, uint64_t *c);
 
+/* F_p^2 helpers on pairs for the extension-field gates */
+static inline void ext_sub2(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]) {
+    out[0] = gl_sub(a[0], b[0]);
+    out[1] = gl_sub(a[1], b[1]);
+}
+static inline void ext_add2(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]) {
+    out[0] = gl_add(a[0], b[0]);
+    out[1] = gl_add(a[1], b[1]);
+}
+
+/* two_adic_subgroup (field/src/types.rs:292-295) and barycentric_weights (field/src/interpolation.rs:53-65)
+ * of CosetInterpolationGate, per subgroup_bits */
+static void coset_interpolation_tables(unsigned bits, uint64_t *domain, uint64_t *weights) {
+    const unsigned n = 1u << bits;
+    const uint64_t g = orc_gl_primitive_root(bits);
+    uint64_t v = 1;
+    for (unsigned i = 0; i < n; i++, v = gl_mul(v, g)) domain[i] = orc_gl_canon(v);
+    for (unsigned i = 0; i < n; i++) {
+        uint64_t d = 1;
+        for (unsigned j = 0; j < n; j++)
+            if (j != i) d = gl_mul(d, gl_sub(domain[i], domain[j]));
+        weights[i] = orc_gl_inv(d);
+    }
+}
+
+/* partial_interpolate, plonky2/src/gates/coset_interpolation.rs:572-599 */
+static void partial_interpolate(const uint64_t *domain, const uint64_t *weights, const uint64_t *values /* [..][2] */,
+                                unsigned lo, unsigned hi, const uint64_t x[2], uint64_t ev[2], uint64_t prod[2]) {
+    for (unsigned j = lo; j < hi; j++) {
+        uint64_t val[2] = {gl_mul(values[2 * j], weights[j]), gl_mul(values[2 * j + 1], weights[j])};
+        uint64_t term[2] = {gl_sub(x[0], domain[j]), x[1]};
+        uint64_t a[2], b[2];
+        orc_ext_mul(ev, term, a);
+        orc_ext_mul(val, prod, b);
+        ext_add2(a, b, ev);
+        orc_ext_mul(prod, term, a);
+        prod[0] = a[0];
+        prod[1] = a[1];
+    }
+}
+
 /* eval_unfiltered of the supported gates; `consts` already has the selector prefix removed
  * (gate.rs:179).  Adds filter * constraint_k into acc[k] (vanishing_poly.rs:700-726). */
 static void gate_eval_add(const orc_gate *g, const uint64_t *consts, const uint64_t *wires,
@@ -857,6 +898,101 @@ static void gate_eval_add(const orc_gate *g, const uint64_t *consts, const uint6
         uint64_t c[123];
         poseidon_gate_eval(wires, c);
         for (unsigned i = 0; i < 123; i++) acc[i] = gl_add(acc[i], gl_mul(filter, c[i]));
+        break;
+    }
+    case ORC_GATE_RANDOM_ACCESS: { /* gates/random_access.rs:144-189; wire layout :78-127 */
+        const unsigned bits = g->param & 0xFF, copies = (g->param >> 8) & 0xFF, extra = g->param >> 16;
+        const unsigned vec = 1u << bits, routed = (2 + vec) * copies + extra;
+        unsigned k = 0;
+        for (unsigned copy = 0; copy < copies; copy++) {
+            const uint64_t *w = wires + (2 + vec) * copy; /* [index, claimed, items...] */
+            const uint64_t *b = wires + routed + copy * bits;
+            uint64_t items[64];
+            for (unsigned i = 0; i < vec; i++) items[i] = w[2 + i];
+            for (unsigned i = 0; i < bits; i++, k++)
+                acc[k] = gl_add(acc[k], gl_mul(filter, gl_mul(b[i], gl_sub(b[i], 1))));
+            uint64_t rec = 0;
+            for (unsigned i = bits; i-- > 0;) rec = gl_add(gl_add(rec, rec), b[i]);
+            acc[k] = gl_add(acc[k], gl_mul(filter, gl_sub(rec, w[0])));
+            k++;
+            for (unsigned i = 0, len = vec; i < bits; i++, len >>= 1)
+                for (unsigned j = 0; j < len / 2; j++)
+                    items[j] = gl_add(items[2 * j], gl_mul(b[i], gl_sub(items[2 * j + 1], items[2 * j])));
+            acc[k] = gl_add(acc[k], gl_mul(filter, gl_sub(items[0], w[1])));
+            k++;
+        }
+        for (unsigned i = 0; i < extra; i++, k++)
+            acc[k] = gl_add(acc[k], gl_mul(filter, gl_sub(consts[i], wires[(2 + vec) * copies + i])));
+        break;
+    }
+    case ORC_GATE_REDUCING:       /* gates/reducing.rs:109-133: output 0..2, alpha 2..4, old_acc 4..6, coeffs 6.. */
+    case ORC_GATE_REDUCING_EXT: { /* gates/reducing_extension.rs:113-132: coefficients are F_p^2 pairs */
+        const int ext = g->kind == ORC_GATE_REDUCING_EXT;
+        const unsigned n = g->param, start_accs = 6 + (ext ? 2 * n : n);
+        const uint64_t *alpha = wires + 2, *cur = wires + 4;
+        for (unsigned i = 0; i < n; i++) {
+            const uint64_t *nxt = (i == n - 1) ? wires : wires + start_accs + 2 * i;
+            uint64_t t[2];
+            orc_ext_mul(cur, alpha, t);
+            if (ext) {
+                t[0] = gl_add(t[0], wires[6 + 2 * i]);
+                t[1] = gl_add(t[1], wires[7 + 2 * i]);
+            } else {
+                t[0] = gl_add(t[0], wires[6 + i]);
+            }
+            acc[2 * i] = gl_add(acc[2 * i], gl_mul(filter, gl_sub(t[0], nxt[0])));
+            acc[2 * i + 1] = gl_add(acc[2 * i + 1], gl_mul(filter, gl_sub(t[1], nxt[1])));
+            cur = nxt;
+        }
+        break;
+    }
+    case ORC_GATE_POSEIDON_MDS: { /* gates/poseidon_mds.rs:150-169: the MDS layer on 12 F_p^2 lanes */
+        for (unsigned r = 0; r < 12; r++)
+            for (unsigned k = 0; k < 2; k++) {
+                uint64_t sum = gl_mul(wires[2 * r + k], POSEIDON_MDS_DIAG[r]);
+                for (unsigned i = 0; i < 12; i++)
+                    sum = gl_add(sum, gl_mul(wires[2 * ((i + r) % 12) + k], POSEIDON_MDS_CIRC[i]));
+                acc[2 * r + k] = gl_add(acc[2 * r + k], gl_mul(filter, gl_sub(wires[24 + 2 * r + k], sum)));
+            }
+        break;
+    }
+    case ORC_GATE_EXPONENTIATION: { /* gates/exponentiation.rs:210-245: base 0, bits 1..1+n (LE), output 1+n */
+        const unsigned n = g->param;
+        const uint64_t base = wires[0], *bit = wires + 1, *inter = wires + 2 + n;
+        for (unsigned i = 0; i < n; i++) {
+            const uint64_t prev = i == 0 ? 1 : gl_mul(inter[i - 1], inter[i - 1]);
+            const uint64_t cur_bit = bit[n - i - 1];
+            const uint64_t computed = gl_mul(prev, gl_add(gl_mul(cur_bit, base), gl_sub(1, cur_bit)));
+            acc[i] = gl_add(acc[i], gl_mul(filter, gl_sub(computed, inter[i])));
+        }
+        acc[n] = gl_add(acc[n], gl_mul(filter, gl_sub(wires[1 + n], inter[n - 1])));
+        break;
+    }
+    case ORC_GATE_COSET_INTERPOLATION: { /* gates/coset_interpolation.rs:260-307; wires :77-155 */
+        const unsigned bits = g->param & 0xFF, degree = g->param >> 8, points = 1u << bits;
+        const unsigned inter = (points - 2) / (degree - 1), start = 1 + 2 * points + 4;
+        uint64_t domain[64], weights[64];
+        coset_interpolation_tables(bits, domain, weights);
+        const uint64_t shift = wires[0], shift_inv = wires[start + 2 * (2 * inter + 1)];
+        const uint64_t *point = wires + 1 + 2 * points, *x = wires + start + 4 * inter, *values = wires + 1;
+        unsigned k = 0;
+        acc[k] = gl_add(acc[k], gl_mul(filter, gl_sub(gl_mul(shift, shift_inv), 1)));
+        k++;
+        for (unsigned j = 0; j < 2; j++, k++)
+            acc[k] = gl_add(acc[k], gl_mul(filter, gl_sub(point[j], gl_mul(x[j], shift))));
+        uint64_t ev[2] = {0, 0}, prod[2] = {1, 0};
+        partial_interpolate(domain, weights, values, 0, degree, x, ev, prod);
+        for (unsigned i = 0; i < inter; i++) {
+            const uint64_t *iev = wires + start + 2 * i, *iprod = wires + start + 2 * (inter + i);
+            for (unsigned j = 0; j < 2; j++, k++) acc[k] = gl_add(acc[k], gl_mul(filter, gl_sub(iev[j], ev[j])));
+            for (unsigned j = 0; j < 2; j++, k++) acc[k] = gl_add(acc[k], gl_mul(filter, gl_sub(iprod[j], prod[j])));
+            const unsigned lo = 1 + (degree - 1) * (i + 1);
+            const unsigned hi = lo + degree - 1 < points ? lo + degree - 1 : points;
+            ev[0] = iev[0], ev[1] = iev[1], prod[0] = iprod[0], prod[1] = iprod[1];
+            partial_interpolate(domain, weights, values, lo, hi, x, ev, prod);
+        }
+        const uint64_t *out = wires + 3 + 2 * points;
+        for (unsigned j = 0; j < 2; j++, k++) acc[k] = gl_add(acc[k], gl_mul(filter, gl_sub(out[j], ev[j])));
         break;
     }
     }
@@ -934,6 +1070,16 @@ unsigned orc_gate_num_constraints(const orc_gate *g) {
     case ORC_GATE_CONSTANT: return g->param;
     case ORC_GATE_PUBLIC_INPUT: return 4;
     case ORC_GATE_ARITHMETIC: return g->param;
+    case ORC_GATE_RANDOM_ACCESS: /* random_access.rs:279-282 */
+        return ((g->param >> 8) & 0xFF) * ((g->param & 0xFF) + 2) + (g->param >> 16);
+    case ORC_GATE_REDUCING:
+    case ORC_GATE_REDUCING_EXT: return 2 * g->param;
+    case ORC_GATE_POSEIDON_MDS: return 24;
+    case ORC_GATE_EXPONENTIATION: return g->param + 1;
+    case ORC_GATE_COSET_INTERPOLATION: { /* coset_interpolation.rs:406-410 */
+        const unsigned points = 1u << (g->param & 0xFF), degree = g->param >> 8;
+        return 5 + 4 * ((points - 2) / (degree - 1));
+    }
     default: return 0;
     }
 }

@@ -125,10 +125,14 @@ void orc_reduce_openings(size_t n_batches, const size_t *n_terms, const uint64_t
 /* ---- plonk permutation argument and quotient (plonky2/src/plonk/prover.rs:402-480,640-866,
  *      plonky2/src/plonk/vanishing_poly.rs:166-330) -------------------------------------------- */
 enum { ORC_GATE_NOOP = 0, ORC_GATE_CONSTANT = 1, ORC_GATE_PUBLIC_INPUT = 2, ORC_GATE_ARITHMETIC = 3,
-       ORC_GATE_POSEIDON = 4, ORC_GATE_ARITHMETIC_EXT = 5, ORC_GATE_MUL_EXT = 6, ORC_GATE_BASE_SUM_2 = 7 };
+       ORC_GATE_POSEIDON = 4, ORC_GATE_ARITHMETIC_EXT = 5, ORC_GATE_MUL_EXT = 6, ORC_GATE_BASE_SUM_2 = 7,
+       ORC_GATE_RANDOM_ACCESS = 8, ORC_GATE_REDUCING = 9, ORC_GATE_REDUCING_EXT = 10, ORC_GATE_POSEIDON_MDS = 11,
+       ORC_GATE_EXPONENTIATION = 12, ORC_GATE_COSET_INTERPOLATION = 13 };
 typedef struct {
     uint32_t kind;           /* ORC_GATE_* */
-    uint32_t param;          /* num_consts (ConstantGate) / num_ops (ArithmeticGate) */
+    uint32_t param;          /* num_consts (ConstantGate) / num_ops (Arithmetic*) / num_limbs / num_coeffs /
+                              * num_power_bits; RandomAccess: bits | copies << 8 | extra constants << 16;
+                              * CosetInterpolation: subgroup_bits | degree << 8 */
     uint32_t index;          /* position in the sorted gate list = selector value */
     uint32_t selector_index; /* SelectorsInfo.selector_indices[index] */
     uint32_t group_start, group_end; /* SelectorsInfo.groups[selector_index] */

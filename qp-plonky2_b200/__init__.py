@@ -193,6 +193,7 @@ def lib():
         "qp_program_code": (sz, [vp, pp]),
         "qp_program_pool": (sz, [vp, pp]),
         "qp_program_regs": (u32, [vp]),
+        "qp_program_segments": (sz, [vp, pp]),
         "qp_program_num_selectors": (u32, [vp]),
         "qp_program_num_gate_constants": (u32, [vp]),
         "qp_program_num_gate_constraints": (u32, [vp]),

@@ -38,6 +38,7 @@ struct qp_ctx {
     bool own_stream = false;
     uint64_t* tw = nullptr;  // tw[(1<<lg)+e] = w_{2^lg}^e, e < 2^lg
     unsigned tw_lg = 0;
+    int sm_count = 148;
     uint64_t launches = 0;
     std::string err;
     std::mutex mu;
@@ -208,6 +209,8 @@ extern "C" int qp_ctx_create(int device, void* stream, unsigned max_lde_log, qp_
         }
         ctx->own_stream = true;
     }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (ctx->sm_count < 1) ctx->sm_count = 148;
     for (auto& e : ctx->ev) cudaEventCreate(&e);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (auto& e : ctx->copy_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -1633,6 +1636,8 @@ struct qp_circuit {
     uint64_t* k_is = nullptr;     // [num_routed_wires]
     uint64_t* sigmas = nullptr;   // [num_routed_wires][n], may be null (quotient-only circuits)
     uint64_t* program = nullptr;  // program_len + 1 words (OP_END appended)
+    uint32_t* seg_off = nullptr;  // first word of every OP_END-terminated segment of the program
+    unsigned n_seg = 0;
     uint64_t* pool = nullptr;
     uint64_t* zh = nullptr;       // [2][2^qdb]: Z_H on the coset, and its inverses
     unsigned max_emit = 0;        // largest constraint index in the program
@@ -1654,7 +1659,7 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
     if (d->degree_bits + d->quotient_degree_bits > ctx->tw_lg)
         return fail(ctx, QP_ERR_TOO_LARGE, "quotient domain larger than the context's twiddle table");
     if (d->program_len && !d->program) return fail(ctx, QP_ERR_BAD_ARG, "null program");
-    if ((size_t)d->program_regs * quotient::BLOCK * 8 > 200 * 1024)
+    if ((size_t)d->program_regs * quotient::BLOCK * 8 + d->pool_len * 8 > 190 * 1024)
         return fail(ctx, QP_ERR_TOO_LARGE, "constraint program needs too many registers");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     qp_circuit* c = new qp_circuit();
@@ -1669,6 +1674,18 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
     CUDA_TRY(ctx, cudaMemcpyAsync(c->k_is, d->k_is, d->num_routed_wires * 8, cudaMemcpyHostToDevice, ctx->stream));
     std::vector<uint64_t> prog(d->program, d->program + d->program_len);
     prog.push_back(quotient::OP_END);
+    std::vector<uint32_t> seg_off;
+    for (size_t k = 0, start = 0; k < prog.size(); k++)
+        if ((prog[k] & 0xff) == quotient::OP_END) {
+            if (k > start) seg_off.push_back((uint32_t)start);
+            start = k + 1;
+        }
+    c->n_seg = (unsigned)seg_off.size();
+    if (!seg_off.empty()) {
+        rc = dev_alloc(ctx, (uint64_t**)&c->seg_off, (seg_off.size() + 1) / 2);
+        if (rc) return rc;
+        CUDA_TRY(ctx, cudaMemcpyAsync(c->seg_off, seg_off.data(), seg_off.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
     for (uint64_t ins : prog) {
         const unsigned op = ins & 0xff, dst = (ins >> 8) & 0xffff, a = (ins >> 24) & 0xffff, b = (ins >> 40) & 0xffff;
         const bool arith = op == quotient::OP_ADD || op == quotient::OP_SUB || op == quotient::OP_MUL;
@@ -1755,6 +1772,7 @@ extern "C" void qp_circuit_free(qp_circuit* c) {
     dev_free(c->ctx, c->k_is);
     dev_free(c->ctx, c->sigmas);
     dev_free(c->ctx, c->program);
+    dev_free(c->ctx, (uint64_t*)c->seg_off);
     dev_free(c->ctx, c->pool);
     dev_free(c->ctx, c->zh);
     cudaStreamSynchronize(c->ctx->stream);
@@ -1871,8 +1889,11 @@ extern "C" int qp_circuit_compute_quotient_polys(qp_circuit* c, const qp_batch* 
     p.zh_eval = c->zh;
     p.zh_inv = c->zh + ((size_t)1 << d.quotient_degree_bits);
     p.program = c->program;
+    p.seg_off = c->seg_off;
+    p.n_seg = c->n_seg;
     p.pool = c->pool;
-    p.n_regs = d.program_regs;
+    p.pool_len = (unsigned)d.pool_len;
+    p.n_regs = d.program_regs ? d.program_regs : 1;
     const unsigned base = nc + nc * (np + 1);
     const unsigned stride = (base > c->max_emit ? base : c->max_emit) + 1;
     p.apow_stride = stride;
@@ -1900,11 +1921,27 @@ extern "C" int qp_circuit_compute_quotient_polys(qp_circuit* c, const qp_batch* 
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(d_apow, apow.data(), apow.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     p.alpha_pows = d_apow;
-    p.out = d_vals;
-    const size_t smem = (size_t)(d.program_regs ? d.program_regs : 1) * quotient::BLOCK * 8;
+    const size_t smem = quotient::smem_words(p.pool_len, nc, stride, p.n_regs) * 8;
+    if (smem > 200 * 1024) return fail(ctx, QP_ERR_TOO_LARGE, "constraint program needs too much shared memory");
     if (smem > 48 * 1024)
         CUDA_TRY(ctx, cudaFuncSetAttribute(quotient::quotient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LAUNCH(ctx, quotient::quotient_kernel, cdiv(n_lde, quotient::BLOCK), quotient::BLOCK, smem, p);
+    // The units of a point (permutation terms + program segments) are spread over blockIdx.y while
+    // the tiles alone leave SMs idle: aim at ~8 resident blocks per SM.
+    const unsigned tiles = (unsigned)cdiv(n_lde, quotient::BLOCK), units = 1 + c->n_seg;
+    unsigned ny = (unsigned)cdiv((size_t)ctx->sm_count * 8, (size_t)tiles);
+    if (ny > units) ny = units;
+    if (ny < 1) ny = 1;
+    uint64_t* d_partial = nullptr;
+    if (ny > 1) {
+        rc = dev_alloc(ctx, &d_partial, (size_t)ny * out_words);
+        if (rc) return rc;
+    }
+    p.out = ny > 1 ? d_partial : d_vals;
+    LAUNCH(ctx, quotient::quotient_kernel, dim3(tiles, ny), quotient::BLOCK, smem, p);
+    if (ny > 1)
+        LAUNCH(ctx, quotient::combine_kernel, cdiv(out_words, 256), 256, 0, d_partial, ny, nc, lg_lde,
+               d.quotient_degree_bits, p.zh_inv, d_vals);
+    dev_free(ctx, d_partial);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // apow dies at return
     // values.coset_ifft(F::coset_shift()), polynomial/mod.rs:58-88
     NttJob job;

@@ -68,111 +68,133 @@ struct Params {
     unsigned apow_stride;
     uint64_t betas[MAX_CHALLENGES], gammas[MAX_CHALLENGES], alphas[MAX_CHALLENGES];
     uint64_t pih[4];
-    // gate program
+    // gate program: n_seg self-contained segments (each ends with OP_END) at seg_off[k]
     const uint64_t* program;
+    const uint32_t* seg_off;
+    unsigned n_seg;
     const uint64_t* pool;
+    unsigned pool_len;
     unsigned n_regs;
-    uint64_t* out;  // [nc][2^lg_lde], natural order
+    // gridDim.y == 1: out = the quotient values [nc][2^lg_lde], natural order.
+    // gridDim.y  > 1: out = partial sums [gridDim.y][nc][2^lg_lde] for combine_kernel.
+    uint64_t* out;
 };
 
-// One thread per point of the quotient domain, enumerated in leaf order.
+// shared memory: pool | alpha powers | register file [n_regs][BLOCK]
+__host__ __device__ inline size_t smem_words(unsigned pool_len, unsigned nc, unsigned apow_stride, unsigned n_regs) {
+    return (size_t)pool_len + (size_t)nc * apow_stride + (size_t)n_regs * BLOCK;
+}
+
+// One thread per point of the quotient domain, enumerated in leaf order.  The work of a point is
+// 1 + n_seg independent units -- the permutation terms and the segments of the gate program --
+// dealt round-robin over blockIdx.y, so that a 2^12-row circuit (256 tiles) still fills 148 SMs.
 __global__ void __launch_bounds__(BLOCK) quotient_kernel(Params p) {
-    extern __shared__ uint64_t regs[];  // [n_regs][BLOCK]
+    extern __shared__ uint64_t smem[];
+    uint64_t* const sh_pool = smem;
+    uint64_t* const sh_apow = sh_pool + p.pool_len;
+    uint64_t* const regs = sh_apow + (size_t)p.nc * p.apow_stride;  // [n_regs][BLOCK]
+    for (unsigned k = threadIdx.x; k < p.pool_len; k += BLOCK) sh_pool[k] = p.pool[k];
+    for (unsigned k = threadIdx.x; k < p.nc * p.apow_stride; k += BLOCK) sh_apow[k] = p.alpha_pows[k];
+    __syncthreads();
     const size_t n_lde = (size_t)1 << p.lg_lde;
     const size_t pos_raw = (size_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool live = pos_raw < n_lde;
     const size_t pos = live ? pos_raw : n_lde - 1;
     const size_t i = brev(pos, p.lg_lde);  // natural index: the point is g w^i
-    const size_t pos_next = brev((i + ((size_t)1 << p.qdb)) & (n_lde - 1), p.lg_lde);
-    const uint64_t x = gl::mul(gl::GENERATOR, p.tw_row[i]);
     const unsigned zi = (unsigned)(i & (((size_t)1 << p.qdb) - 1));
-    // L_0(x) = Z_H(x) / (n (x - 1)), zero_poly_coset.rs:93-96
-    const uint64_t l_0 = gl::mul(p.zh_eval[zi], inverse(gl::mul((uint64_t)1 << p.degree_bits, gl::sub(x, 1))));
     const unsigned base = p.nc + p.nc * (p.np + 1);
-    uint64_t res[MAX_CHALLENGES];
+    uint64_t res[MAX_CHALLENGES], G[MAX_CHALLENGES], h[MAX_CHALLENGES];
 #pragma unroll
-    for (int a = 0; a < MAX_CHALLENGES; a++) res[a] = 0;
+    for (int a = 0; a < MAX_CHALLENGES; a++) res[a] = G[a] = h[a] = 0;
     auto add_term = [&](unsigned t, uint64_t term) {
 #pragma unroll
         for (int a = 0; a < MAX_CHALLENGES; a++)
-            if (a < (int)p.nc) res[a] = gl::add(res[a], gl::mul(term, p.alpha_pows[a * p.apow_stride + t]));
+            if (a < (int)p.nc) res[a] = gl::add(res[a], gl::mul(term, sh_apow[a * p.apow_stride + t]));
     };
-    // the L_0(x) (Z(x) - 1) terms, vanishing_poly.rs:268-272
-    for (unsigned ch = 0; ch < p.nc; ch++) add_term(ch, gl::mul(l_0, gl::sub(p.zs[ch * p.zs_stride + pos], 1)));
-    // partial product checks, vanishing_poly.rs:297-320
-    {
-        uint64_t pn[MAX_CHALLENGES], pd[MAX_CHALLENGES], bx[MAX_CHALLENGES];
-#pragma unroll
-        for (int c = 0; c < MAX_CHALLENGES; c++) {
-            pn[c] = pd[c] = 1;
-            bx[c] = c < (int)p.nc ? gl::mul(p.betas[c], x) : 0;
-        }
-        unsigned w = 0, in_chunk = 0;
-        for (unsigned j = 0; j < p.nr; j++) {
-            const uint64_t wire = p.wires[j * p.wires_stride + pos];
-            const uint64_t sigma = p.cs[(p.num_constants + j) * p.cs_stride + pos];
-            const uint64_t k = p.k_is[j];
+    for (unsigned unit = blockIdx.y; unit < 1 + p.n_seg; unit += gridDim.y) {
+        if (unit == 0) {
+            const size_t pos_next = brev((i + ((size_t)1 << p.qdb)) & (n_lde - 1), p.lg_lde);
+            const uint64_t x = gl::mul(gl::GENERATOR, p.tw_row[i]);
+            // L_0(x) = Z_H(x) / (n (x - 1)), zero_poly_coset.rs:93-96
+            const uint64_t l_0 = gl::mul(p.zh_eval[zi], inverse(gl::mul((uint64_t)1 << p.degree_bits, gl::sub(x, 1))));
+            // the L_0(x) (Z(x) - 1) terms, vanishing_poly.rs:268-272
+            for (unsigned ch = 0; ch < p.nc; ch++) add_term(ch, gl::mul(l_0, gl::sub(p.zs[ch * p.zs_stride + pos], 1)));
+            // partial product checks, vanishing_poly.rs:297-320
+            uint64_t pn[MAX_CHALLENGES], pd[MAX_CHALLENGES], bx[MAX_CHALLENGES];
 #pragma unroll
             for (int c = 0; c < MAX_CHALLENGES; c++) {
-                if (c < (int)p.nc) {
-                    const uint64_t wg = gl::add(wire, p.gammas[c]);
-                    pn[c] = gl::mul(pn[c], gl::add(wg, gl::mul(bx[c], k)));
-                    pd[c] = gl::mul(pd[c], gl::add(wg, gl::mul(p.betas[c], sigma)));
-                }
+                pn[c] = pd[c] = 1;
+                bx[c] = c < (int)p.nc ? gl::mul(p.betas[c], x) : 0;
             }
-            if (++in_chunk == p.max_degree || j + 1 == p.nr) {
+            unsigned w = 0, in_chunk = 0;
+            for (unsigned j = 0; j < p.nr; j++) {
+                const uint64_t wire = p.wires[j * p.wires_stride + pos];
+                const uint64_t sigma = p.cs[(p.num_constants + j) * p.cs_stride + pos];
+                const uint64_t k = p.k_is[j];
 #pragma unroll
                 for (int c = 0; c < MAX_CHALLENGES; c++) {
                     if (c < (int)p.nc) {
-                        // accumulators Z(x), p_0 .. p_{np-1}, Z(g x): util/partial_products.rs:60-63
-                        const uint64_t prev = w == 0 ? p.zs[c * p.zs_stride + pos]
-                                                     : p.zs[(p.nc + c * p.np + w - 1) * p.zs_stride + pos];
-                        const uint64_t next = w == p.np ? p.zs[c * p.zs_stride + pos_next]
-                                                        : p.zs[(p.nc + c * p.np + w) * p.zs_stride + pos];
-                        add_term(p.nc + c * (p.np + 1) + w, gl::sub(gl::mul(prev, pn[c]), gl::mul(next, pd[c])));
-                        pn[c] = pd[c] = 1;
+                        const uint64_t wg = gl::add(wire, p.gammas[c]);
+                        pn[c] = gl::mul(pn[c], gl::add(wg, gl::mul(bx[c], k)));
+                        pd[c] = gl::mul(pd[c], gl::add(wg, gl::mul(p.betas[c], sigma)));
                     }
                 }
-                w++;
-                in_chunk = 0;
-            }
-        }
-    }
-    // gate constraints (vanishing_poly.rs:700-726): G = sum over gates of filter * Horner(constraints)
-    uint64_t G[MAX_CHALLENGES], h[MAX_CHALLENGES];
+                if (++in_chunk == p.max_degree || j + 1 == p.nr) {
 #pragma unroll
-    for (int a = 0; a < MAX_CHALLENGES; a++) G[a] = h[a] = 0;
-    uint64_t* r = regs + threadIdx.x;
-    for (const uint64_t* pc = p.program;; pc++) {
-        const uint64_t ins = *pc;
-        const unsigned op = ins & 0xff, dst = (ins >> 8) & 0xffff, a = (ins >> 24) & 0xffff, b = (ins >> 40) & 0xffff;
-        if (op == OP_END) break;
-        switch (op) {
-            case OP_LDW: r[dst * BLOCK] = p.wires[a * p.wires_stride + pos]; break;
-            case OP_LDK: r[dst * BLOCK] = p.cs[a * p.cs_stride + pos]; break;
-            case OP_LDP: r[dst * BLOCK] = p.pih[a & 3]; break;
-            case OP_LDI: r[dst * BLOCK] = p.pool[a]; break;
-            case OP_ADD: r[dst * BLOCK] = gl::add(r[a * BLOCK], r[b * BLOCK]); break;
-            case OP_SUB: r[dst * BLOCK] = gl::sub(r[a * BLOCK], r[b * BLOCK]); break;
-            case OP_MUL: r[dst * BLOCK] = gl::mul(r[a * BLOCK], r[b * BLOCK]); break;
-            case OP_MULI: r[dst * BLOCK] = gl::mul(r[a * BLOCK], p.pool[b]); break;
-            case OP_ADDI: r[dst * BLOCK] = gl::add(r[a * BLOCK], p.pool[b]); break;
-            case OP_EMIT: {
-                const uint64_t v = r[a * BLOCK];
-#pragma unroll
-                for (int c = 0; c < MAX_CHALLENGES; c++)
-                    if (c < (int)p.nc) h[c] = gl::add(h[c], gl::mul(v, p.alpha_pows[c * p.apow_stride + b]));
-                break;
-            }
-            case OP_GATE: {
-                const uint64_t f = r[a * BLOCK];
-#pragma unroll
-                for (int c = 0; c < MAX_CHALLENGES; c++)
-                    if (c < (int)p.nc) {
-                        G[c] = gl::add(G[c], gl::mul(f, h[c]));
-                        h[c] = 0;
+                    for (int c = 0; c < MAX_CHALLENGES; c++) {
+                        if (c < (int)p.nc) {
+                            // accumulators Z(x), p_0 .. p_{np-1}, Z(g x): util/partial_products.rs:60-63
+                            const uint64_t prev = w == 0 ? p.zs[c * p.zs_stride + pos]
+                                                         : p.zs[(p.nc + c * p.np + w - 1) * p.zs_stride + pos];
+                            const uint64_t next = w == p.np ? p.zs[c * p.zs_stride + pos_next]
+                                                            : p.zs[(p.nc + c * p.np + w) * p.zs_stride + pos];
+                            add_term(p.nc + c * (p.np + 1) + w, gl::sub(gl::mul(prev, pn[c]), gl::mul(next, pd[c])));
+                            pn[c] = pd[c] = 1;
+                        }
                     }
-                break;
+                    w++;
+                    in_chunk = 0;
+                }
+            }
+            continue;
+        }
+        // gate constraints (vanishing_poly.rs:700-726): G = sum over gates of filter * sum_k alpha^k c_k
+        uint64_t* r = regs + threadIdx.x;
+        const uint64_t* pc = p.program + p.seg_off[unit - 1];
+        uint64_t next = __ldg(pc);  // the instruction stream is fetched one word ahead of its use
+        for (;;) {
+            const uint64_t ins = next;
+            const unsigned op = ins & 0xff;
+            if (op == OP_END) break;
+            next = __ldg(++pc);
+            const unsigned dst = (ins >> 8) & 0xffff, a = (ins >> 24) & 0xffff, b = (ins >> 40) & 0xffff;
+            switch (op) {
+                case OP_LDW: r[dst * BLOCK] = p.wires[a * p.wires_stride + pos]; break;
+                case OP_LDK: r[dst * BLOCK] = p.cs[a * p.cs_stride + pos]; break;
+                case OP_LDP: r[dst * BLOCK] = p.pih[a & 3]; break;
+                case OP_LDI: r[dst * BLOCK] = sh_pool[a]; break;
+                case OP_ADD: r[dst * BLOCK] = gl::add(r[a * BLOCK], r[b * BLOCK]); break;
+                case OP_SUB: r[dst * BLOCK] = gl::sub(r[a * BLOCK], r[b * BLOCK]); break;
+                case OP_MUL: r[dst * BLOCK] = gl::mul(r[a * BLOCK], r[b * BLOCK]); break;
+                case OP_MULI: r[dst * BLOCK] = gl::mul(r[a * BLOCK], sh_pool[b]); break;
+                case OP_ADDI: r[dst * BLOCK] = gl::add(r[a * BLOCK], sh_pool[b]); break;
+                case OP_EMIT: {
+                    const uint64_t v = r[a * BLOCK];
+#pragma unroll
+                    for (int c = 0; c < MAX_CHALLENGES; c++)
+                        if (c < (int)p.nc) h[c] = gl::add(h[c], gl::mul(v, sh_apow[c * p.apow_stride + b]));
+                    break;
+                }
+                case OP_GATE: {
+                    const uint64_t f = r[a * BLOCK];
+#pragma unroll
+                    for (int c = 0; c < MAX_CHALLENGES; c++)
+                        if (c < (int)p.nc) {
+                            G[c] = gl::add(G[c], gl::mul(f, h[c]));
+                            h[c] = 0;
+                        }
+                    break;
+                }
             }
         }
     }
@@ -181,9 +203,24 @@ __global__ void __launch_bounds__(BLOCK) quotient_kernel(Params p) {
 #pragma unroll
     for (int a = 0; a < MAX_CHALLENGES; a++)
         if (a < (int)p.nc) {
-            const uint64_t total = gl::add(res[a], gl::mul(G[a], p.alpha_pows[a * p.apow_stride + base]));
-            p.out[((size_t)a << p.lg_lde) + i] = gl::canon(gl::mul(total, zinv));  // prover.rs:848-853
+            const uint64_t total = gl::add(res[a], gl::mul(G[a], sh_apow[a * p.apow_stride + base]));
+            if (gridDim.y == 1)
+                p.out[((size_t)a << p.lg_lde) + i] = gl::canon(gl::mul(total, zinv));  // prover.rs:848-853
+            else
+                p.out[(((size_t)blockIdx.y * p.nc + a) << p.lg_lde) + i] = total;
         }
+}
+
+// out[a][i] = Z_H(x_i)^-1 * sum_y partial[y][a][i]   (the units of quotient_kernel, summed)
+__global__ void combine_kernel(const uint64_t* __restrict__ partial, unsigned n_parts, unsigned nc, unsigned lg_lde,
+                               unsigned qdb, const uint64_t* __restrict__ zh_inv, uint64_t* __restrict__ out) {
+    const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t words = (size_t)nc << lg_lde;
+    if (id >= words) return;
+    uint64_t acc = partial[id];
+    for (unsigned y = 1; y < n_parts; y++) acc = gl::add(acc, partial[(size_t)y * words + id]);
+    const size_t i = id & (((size_t)1 << lg_lde) - 1);
+    out[id] = gl::canon(gl::mul(acc, zh_inv[i & (((size_t)1 << qdb) - 1)]));
 }
 
 // coeffs[v][i] *= s^i with s^i = lo[i & mask] * hi[i >> split]   (coset_ifft's g^-i, polynomial/mod.rs:82-87)

@@ -7,9 +7,12 @@
 //   compute_filter                  plonky2/src/gates/gate.rs:326-333
 //   evaluate_gate_constraints       plonky2/src/plonk/vanishing_poly.rs:700-726
 //   NoopGate / ConstantGate / PublicInputGate / ArithmeticGate / PoseidonGate / ArithmeticExtensionGate /
-//   MulExtensionGate / BaseSumGate<2>
+//   MulExtensionGate / BaseSumGate<2> / RandomAccessGate / ReducingGate / ReducingExtensionGate /
+//   PoseidonMdsGate / ExponentiationGate / CosetInterpolationGate
 //                                   plonky2/src/gates/{noop,constant,public_input,arithmetic_base,poseidon,
-//                                   arithmetic_extension,multiplication_extension,base_sum}.rs
+//                                   arithmetic_extension,multiplication_extension,base_sum,random_access,
+//                                   reducing,reducing_extension,poseidon_mds,exponentiation,
+//                                   coset_interpolation}.rs
 // In a Rust build this role is played by the shim's recording field type run over
 // Gate::eval_unfiltered_base_one; here the same recording evaluation is written in
 // C++ for the gates above.  Pure host logic: no field arithmetic on data happens here.
@@ -98,8 +101,97 @@ struct GateInfo {
     std::string id;
 };
 
+// Debug rendering of PhantomData<F>: core::any::type_name of the field type; the field crate is the
+// package `qp-plonky2-field` with no [lib] rename (field/Cargo.toml:2).
+const char* const PHANTOM = "PhantomData<qp_plonky2_field::goldilocks_field::GoldilocksField>";
+
+// host-side constants of the gates (domain, barycentric weights): plain modular arithmetic
+uint64_t mulmod(uint64_t a, uint64_t b) { return (uint64_t)((unsigned __int128)a * b % P); }
+uint64_t powmod(uint64_t a, uint64_t e) {
+    uint64_t r = 1;
+    for (; e; e >>= 1, a = mulmod(a, a))
+        if (e & 1) r = mulmod(r, a);
+    return r;
+}
+std::vector<uint64_t> two_adic_subgroup(unsigned n_log) {  // field/src/types.rs:280-295
+    uint64_t g = 7277203076849721926ULL;                   // POWER_OF_TWO_GENERATOR, goldilocks_field.rs:91
+    for (unsigned i = n_log; i < 32; i++) g = mulmod(g, g);
+    std::vector<uint64_t> out(1u << n_log);
+    uint64_t v = 1;
+    for (auto& o : out) {
+        o = v;
+        v = mulmod(v, g);
+    }
+    return out;
+}
+std::vector<uint64_t> barycentric_weights(const std::vector<uint64_t>& xs) {  // field/src/interpolation.rs:53-65
+    std::vector<uint64_t> out;
+    for (size_t i = 0; i < xs.size(); i++) {
+        uint64_t d = 1;
+        for (size_t j = 0; j < xs.size(); j++)
+            if (j != i) d = mulmod(d, xs[i] >= xs[j] ? xs[i] - xs[j] : xs[i] + (P - xs[j]));
+        out.push_back(powmod(d, P - 2));
+    }
+    return out;
+}
+
+struct RandomAccessShape {  // random_access.rs:78-127
+    unsigned bits, copies, extra, vec;
+    explicit RandomAccessShape(uint32_t param)
+        : bits(param & 0xFF), copies((param >> 8) & 0xFF), extra(param >> 16), vec(1u << (param & 0xFF)) {}
+    int access_index(unsigned c) const { return (int)((2 + vec) * c); }
+    int claimed(unsigned c) const { return (int)((2 + vec) * c + 1); }
+    int item(unsigned i, unsigned c) const { return (int)((2 + vec) * c + 2 + i); }
+    int extra_constant(unsigned i) const { return (int)((2 + vec) * copies + i); }
+    int bit(unsigned i, unsigned c) const { return (int)((2 + vec) * copies + extra + c * bits + i); }
+};
+
+struct CosetInterpolationShape {  // coset_interpolation.rs:77-155
+    unsigned bits, degree, points, inter, start_inter;
+    explicit CosetInterpolationShape(uint32_t param)
+        : bits(param & 0xFF), degree(param >> 8), points(1u << (param & 0xFF)) {
+        inter = degree > 1 ? (points - 2) / (degree - 1) : 0;
+        start_inter = 1 + 2 * points + 4;
+    }
+    int value(unsigned i) const { return (int)(1 + 2 * i); }
+    int point() const { return (int)(1 + 2 * points); }
+    int eval_value() const { return (int)(3 + 2 * points); }
+    int inter_eval(unsigned i) const { return (int)(start_inter + 2 * i); }
+    int inter_prod(unsigned i) const { return (int)(start_inter + 2 * (inter + i)); }
+    int shifted_point() const { return (int)(start_inter + 4 * inter); }
+    int shift_inverse() const { return (int)(start_inter + 2 * (2 * inter + 1)); }
+};
+
 GateInfo gate_info(uint32_t kind, uint32_t param) {
     switch (kind) {
+        case QP_GATE_RANDOM_ACCESS: {
+            RandomAccessShape g(param);
+            if (!g.bits || g.bits > 6 || !g.copies) break;
+            return {kind, param, g.bits + 1, g.extra, g.copies * (g.bits + 2) + g.extra,
+                    "RandomAccessGate { bits: " + std::to_string(g.bits) + ", num_copies: " + std::to_string(g.copies) +
+                        ", num_extra_constants: " + std::to_string(g.extra) + ", _phantom: " + PHANTOM + " }<D=2>"};
+        }
+        case QP_GATE_REDUCING:
+            if (!param) break;
+            return {kind, param, 2, 0, 2 * param, "ReducingGate { num_coeffs: " + std::to_string(param) + " }"};
+        case QP_GATE_REDUCING_EXT:
+            if (!param) break;
+            return {kind, param, 2, 0, 2 * param, "ReducingExtensionGate { num_coeffs: " + std::to_string(param) + " }"};
+        case QP_GATE_POSEIDON_MDS:
+            return {kind, param, 1, 0, 24, std::string("PoseidonMdsGate(") + PHANTOM + ")<WIDTH=12>"};
+        case QP_GATE_EXPONENTIATION:
+            if (!param) break;
+            return {kind, param, 4, 0, param + 1,
+                    "ExponentiationGate { num_power_bits: " + std::to_string(param) + ", _phantom: " + PHANTOM + " }<D=2>"};
+        case QP_GATE_COSET_INTERPOLATION: {
+            CosetInterpolationShape g(param);
+            if (!g.bits || g.bits > 6 || g.degree < 2) break;
+            std::string w;
+            for (uint64_t x : barycentric_weights(two_adic_subgroup(g.bits))) w += (w.empty() ? "" : ", ") + std::to_string(x);
+            return {kind, param, g.degree, 0, 5 + 4 * g.inter,
+                    "CosetInterpolationGate { subgroup_bits: " + std::to_string(g.bits) + ", degree: " +
+                        std::to_string(g.degree) + ", barycentric_weights: [" + w + "], _phantom: " + PHANTOM + " }<D=2>"};
+        }
         case QP_GATE_NOOP: return {kind, param, 0, 0, 0, "NoopGate"};
         case QP_GATE_CONSTANT:
             return {kind, param, 1, param, param, "ConstantGate { num_consts: " + std::to_string(param) + " }"};
@@ -108,7 +200,7 @@ GateInfo gate_info(uint32_t kind, uint32_t param) {
             return {kind, param, 3, 2, param, "ArithmeticGate { num_ops: " + std::to_string(param) + " }"};
         case QP_GATE_POSEIDON:
             return {kind, param, 7, 0, 123,
-                    "PoseidonGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>"};
+                    std::string("PoseidonGate(") + PHANTOM + ")<WIDTH=12>"};
         case QP_GATE_ARITHMETIC_EXT:
             return {kind, param, 3, 2, 2 * param, "ArithmeticExtensionGate { num_ops: " + std::to_string(param) + " }"};
         case QP_GATE_MUL_EXT:
@@ -124,6 +216,10 @@ struct ExtVal {
     Val a, b;
 };
 ExtVal ext_mul(ExtVal x, ExtVal y) { return ExtVal{x.a * y.a + (x.b * y.b) * 7, x.a * y.b + x.b * y.a}; }
+ExtVal ext_add(ExtVal x, ExtVal y) { return ExtVal{x.a + y.a, x.b + y.b}; }
+ExtVal ext_sub(ExtVal x, ExtVal y) { return ExtVal{x.a - y.a, x.b - y.b}; }
+ExtVal ext_scalar(ExtVal x, uint64_t k) { return ExtVal{x.a * k, x.b * k}; }
+ExtVal ext_wires(Recorder& R, int w) { return ExtVal{R.wire(w), R.wire(w + 1)}; }
 
 Val sbox(Val x) {  // core/src/poseidon.rs:546-552
     Val x2 = x * x, x4 = x2 * x2;
@@ -205,7 +301,8 @@ void eval_poseidon(Recorder& R, std::vector<Val>& c) {
 }
 
 // Gate::eval_unfiltered for the supported gates; `prefix` = selector columns removed (gate.rs:179)
-void eval_gate(Recorder& R, const GateInfo& g, unsigned prefix, std::vector<Val>& c) {
+void eval_gate(Recorder& R, const GateInfo& gi, unsigned prefix, std::vector<Val>& c) {
+    const GateInfo& g = gi;
     switch (g.kind) {
         case QP_GATE_CONSTANT:  // constant.rs:121-129
             for (unsigned i = 0; i < g.param; i++) c.push_back(R.constant(prefix + i) - R.wire(i));
@@ -255,6 +352,112 @@ void eval_gate(Recorder& R, const GateInfo& g, unsigned prefix, std::vector<Val>
             }
             break;
         }
+        case QP_GATE_RANDOM_ACCESS: {  // random_access.rs:144-189 (packed form :307-352)
+            RandomAccessShape g(gi.param);
+            for (unsigned copy = 0; copy < g.copies; copy++) {
+                Val access_index = R.wire(g.access_index(copy));
+                std::vector<Val> items, bits;
+                for (unsigned i = 0; i < g.vec; i++) items.push_back(R.wire(g.item(i, copy)));
+                Val claimed = R.wire(g.claimed(copy));
+                for (unsigned i = 0; i < g.bits; i++) bits.push_back(R.wire(g.bit(i, copy)));
+                for (Val b : bits) c.push_back(b * (b - 1));
+                Val acc = bits.back();  // fold from ZERO: 0.double() + b = b
+                for (int i = (int)g.bits - 2; i >= 0; i--) acc = acc * 2 + bits[i];
+                c.push_back(acc - access_index);
+                for (Val b : bits) {
+                    std::vector<Val> next;
+                    for (size_t k = 0; k + 1 < items.size(); k += 2) next.push_back(items[k] + b * (items[k + 1] - items[k]));
+                    items = next;
+                }
+                c.push_back(items[0] - claimed);
+            }
+            for (unsigned i = 0; i < g.extra; i++) c.push_back(R.constant(prefix + i) - R.wire(g.extra_constant(i)));
+            break;
+        }
+        case QP_GATE_REDUCING:        // reducing.rs:109-133
+        case QP_GATE_REDUCING_EXT: {  // reducing_extension.rs:113-132
+            const bool ext = gi.kind == QP_GATE_REDUCING_EXT;
+            const unsigned n = gi.param, start_accs = 6 + (ext ? 2 * n : n);
+            ExtVal alpha = ext_wires(R, 2), acc = ext_wires(R, 4);
+            for (unsigned i = 0; i < n; i++) {
+                ExtVal nxt = ext_wires(R, i == n - 1 ? 0 : (int)(start_accs + 2 * i));
+                ExtVal t = ext_mul(acc, alpha);
+                if (ext) {
+                    ExtVal co = ext_wires(R, (int)(6 + 2 * i));
+                    c.push_back(t.a + co.a - nxt.a);
+                    c.push_back(t.b + co.b - nxt.b);
+                } else {
+                    c.push_back(t.a + R.wire((int)(6 + i)) - nxt.a);
+                    c.push_back(t.b - nxt.b);
+                }
+                acc = nxt;
+            }
+            break;
+        }
+        case QP_GATE_POSEIDON_MDS: {  // poseidon_mds.rs:150-169, mds_row_shf_field core/src/poseidon.rs:200-215
+            ExtVal in[12];
+            for (int i = 0; i < 12; i++) in[i] = ext_wires(R, 2 * i);
+            for (int r = 0; r < 12; r++) {
+                ExtVal acc = ext_scalar(in[r], POSEIDON_MDS_CIRC[0] + POSEIDON_MDS_DIAG[r]);
+                for (int i = 1; i < 12; i++) acc = ext_add(acc, ext_scalar(in[(i + r) % 12], POSEIDON_MDS_CIRC[i]));
+                c.push_back(R.wire(24 + 2 * r) - acc.a);
+                c.push_back(R.wire(25 + 2 * r) - acc.b);
+            }
+            break;
+        }
+        case QP_GATE_EXPONENTIATION: {  // exponentiation.rs:210-245
+            const int n = (int)gi.param;
+            Val base = R.wire(0), output = R.wire(1 + n);
+            for (int i = 0; i < n; i++) {
+                Val cur_bit = R.wire(1 + (n - i - 1));
+                Val mul_by = cur_bit * base + (R.imm(1) - cur_bit);
+                Val computed = mul_by;
+                if (i != 0) {
+                    Val prev = R.wire(2 + n + i - 1);
+                    computed = prev * prev * mul_by;
+                }
+                c.push_back(computed - R.wire(2 + n + i));
+            }
+            c.push_back(output - R.wire(2 + n + n - 1));
+            break;
+        }
+        case QP_GATE_COSET_INTERPOLATION: {  // coset_interpolation.rs:260-307, partial_interpolate :572-599
+            CosetInterpolationShape g(gi.param);
+            const std::vector<uint64_t> domain = two_adic_subgroup(g.bits), weights = barycentric_weights(domain);
+            Val shift = R.wire(0), shift_inv = R.wire(g.shift_inverse());
+            ExtVal point = ext_wires(R, g.point()), x = ext_wires(R, g.shifted_point());
+            c.push_back(shift * shift_inv - 1);
+            c.push_back(point.a - x.a * shift);
+            c.push_back(point.b - x.b * shift);
+            std::vector<ExtVal> values;
+            for (unsigned i = 0; i < g.points; i++) values.push_back(ext_wires(R, g.value(i)));
+            auto partial = [&](unsigned lo, unsigned hi, ExtVal& ev, ExtVal& prod) {
+                for (unsigned j = lo; j < hi; j++) {
+                    ExtVal val = ext_scalar(values[j], weights[j]);
+                    ExtVal term{x.a - domain[j], x.b};
+                    ev = ext_add(ext_mul(ev, term), ext_mul(val, prod));
+                    prod = ext_mul(prod, term);
+                }
+            };
+            // initial_eval = 0, initial_partial_prod = 1: the first step is (w_0 v_0, x - x_0)
+            ExtVal ev = ext_scalar(values[0], weights[0]), prod{x.a - domain[0], x.b};
+            partial(1, g.degree, ev, prod);
+            for (unsigned i = 0; i < g.inter; i++) {
+                ExtVal iev = ext_wires(R, g.inter_eval(i)), iprod = ext_wires(R, g.inter_prod(i));
+                c.push_back(iev.a - ev.a);
+                c.push_back(iev.b - ev.b);
+                c.push_back(iprod.a - prod.a);
+                c.push_back(iprod.b - prod.b);
+                const unsigned start = 1 + (g.degree - 1) * (i + 1), end = std::min(start + g.degree - 1, g.points);
+                ev = iev;
+                prod = iprod;
+                partial(start, end, ev, prod);
+            }
+            ExtVal out = ext_wires(R, g.eval_value());
+            c.push_back(out.a - ev.a);
+            c.push_back(out.b - ev.b);
+            break;
+        }
         default: break;
     }
 }
@@ -267,84 +470,194 @@ struct qp_program {
     std::vector<uint32_t> selector_indices;
     std::vector<uint32_t> groups;  // [start0, end0, start1, end1, ...]
     std::vector<uint64_t> code, pool;
+    std::vector<uint32_t> segments;  // word offset of every self-contained segment of `code`
     uint32_t n_regs = 1;
     uint32_t num_gate_constants = 0, num_gate_constraints = 0;
 };
 
-static void compile(Recorder& R, qp_program* out) {
-    // lazy post-order schedule from each action's root, registers reused after the last use
-    struct Step {
-        bool is_node;
-        int i;
-        unsigned op, k;
-    };
-    std::vector<Step> sched;
-    std::vector<char> seen(R.nodes.size(), 0);
-    auto is_leaf = [](unsigned op) { return op >= LDW && op <= LDI; };
-    auto is_unary = [](unsigned op) { return op == MULI || op == ADDI; };
-    for (const auto& act : R.actions) {
-        std::vector<std::pair<int, bool>> stack{{act.node, false}};
+// ---- scheduling, segmentation and register allocation -----------------------------------------
+// The device evaluates the program once per point of the quotient domain with its registers in
+// shared memory, so what matters is (1) few registers -- they bound the points resident per SM --
+// and (2) independent pieces that different thread blocks can take for small circuits.
+//   * values are scheduled lazily in post-order from each constraint (they die young);
+//   * a loaded column whose next use is far away is dropped and loaded again (`REMAT_GAP`): a
+//     BaseSumGate reads its 63 limbs twice, 250 steps apart, and would otherwise pin 65 registers;
+//   * the action list is cut at gate boundaries -- and inside a gate that is much larger than the
+//     rest (PoseidonGate) between constraints -- into segments of similar cost.  Every segment is
+//     self-contained (it recomputes what it shares with another), ends with OP_END, and the
+//     result is the sum over segments because sum_gates filter * sum_k alpha^k c_k is additive.
+namespace {
+
+constexpr int REMAT_GAP = 64;          // steps between two uses of a load beyond which it is reloaded
+constexpr unsigned TARGET_SEGMENTS = 6;
+constexpr size_t MIN_SEGMENT_STEPS = 384;
+
+struct Step {
+    unsigned op;   // node op, or EMIT / GATE
+    int dst;       // value id defined (node steps), -1 for actions
+    int a, b;      // value ids (arith), pool slot / column (immediates, loads), constraint index (EMIT: b)
+};
+
+bool is_leaf(unsigned op) { return op >= LDW && op <= LDI; }
+bool is_unary(unsigned op) { return op == MULI || op == ADDI; }
+
+// Schedules `acts` as one self-contained piece; appends the steps; returns how many were added
+// after each action (cumulative), for the cost model.
+struct Scheduler {
+    const Recorder& R;
+    std::vector<Step> steps;
+    std::vector<int> val_of;      // node -> current value id (-1: not computed in this piece)
+    std::vector<int> touched_at;  // node -> step index of its last use (leaves)
+    int n_vals = 0;
+    explicit Scheduler(const Recorder& r) : R(r), val_of(r.nodes.size(), -1), touched_at(r.nodes.size(), -1) {}
+
+    int use_leaf(int i) {  // value id of a loaded column / constant, (re)loading it if it went stale
+        const auto& nd = R.nodes[i];
+        if (val_of[i] < 0 || (int)steps.size() - touched_at[i] > REMAT_GAP) {
+            val_of[i] = n_vals++;
+            steps.push_back({nd.op, val_of[i], nd.a, 0});
+        }
+        touched_at[i] = (int)steps.size();
+        return val_of[i];
+    }
+    int operand(int i) { return is_leaf(R.nodes[i].op) ? use_leaf(i) : val_of[i]; }
+    void compute(int root) {
+        if (is_leaf(R.nodes[root].op) || val_of[root] >= 0) return;
+        std::vector<std::pair<int, bool>> stack{{root, false}};
         while (!stack.empty()) {
             auto [i, done] = stack.back();
             stack.pop_back();
-            if (seen[i]) continue;
             const auto& nd = R.nodes[i];
-            if (done || is_leaf(nd.op)) {
-                seen[i] = 1;
-                sched.push_back({true, i, 0, 0});
+            if (val_of[i] >= 0) continue;
+            if (!done) {
+                stack.push_back({i, true});
+                if (!is_unary(nd.op) && !is_leaf(R.nodes[nd.b].op) && val_of[nd.b] < 0) stack.push_back({nd.b, false});
+                if (!is_leaf(R.nodes[nd.a].op) && val_of[nd.a] < 0) stack.push_back({nd.a, false});
                 continue;
             }
-            stack.push_back({i, true});
-            if (!is_unary(nd.op) && !seen[nd.b]) stack.push_back({nd.b, false});
-            if (!seen[nd.a]) stack.push_back({nd.a, false});
+            const int va = operand(nd.a);
+            const int vb = is_unary(nd.op) ? nd.b : operand(nd.b);
+            val_of[i] = n_vals++;
+            steps.push_back({nd.op, val_of[i], va, vb});
         }
-        sched.push_back({false, act.node, act.op, act.k});
     }
-    std::vector<int> last_use(R.nodes.size(), -1);
-    for (size_t t = 0; t < sched.size(); t++) {
-        const Step& s = sched[t];
-        if (s.is_node) {
-            const auto& nd = R.nodes[s.i];
-            if (nd.op == ADD || nd.op == SUB || nd.op == MUL) last_use[nd.a] = last_use[nd.b] = (int)t;
-            else if (is_unary(nd.op)) last_use[nd.a] = (int)t;
+    void action(const Recorder::Action& act) {
+        compute(act.node);
+        steps.push_back({act.op, -1, operand(act.node), (int)act.k});
+    }
+};
+
+// registers by linear scan over one piece; appends the encoded words (+ OP_END)
+void encode(const Scheduler& S, std::vector<uint64_t>& code, uint32_t& n_regs) {
+    std::vector<int> last_use(S.n_vals, -1);
+    for (size_t t = 0; t < S.steps.size(); t++) {
+        const Step& s = S.steps[t];
+        if (s.dst < 0) last_use[s.a] = (int)t;
+        else if (s.op == ADD || s.op == SUB || s.op == MUL) last_use[s.a] = last_use[s.b] = (int)t;
+        else if (is_unary(s.op)) last_use[s.a] = (int)t;
+    }
+    std::vector<int> reg_of(S.n_vals, -1), free_regs;
+    uint32_t regs = 0;
+    auto release = [&](int v, size_t t) {
+        if (last_use[v] == (int)t) free_regs.push_back(reg_of[v]);
+    };
+    for (size_t t = 0; t < S.steps.size(); t++) {
+        const Step& s = S.steps[t];
+        if (s.dst < 0) {
+            code.push_back(s.op | ((uint64_t)reg_of[s.a] << 24) | ((uint64_t)(unsigned)s.b << 40));
+            release(s.a, t);
+            continue;
+        }
+        uint64_t ra = (uint64_t)(unsigned)s.a, rb = (uint64_t)(unsigned)s.b;
+        if (s.op == ADD || s.op == SUB || s.op == MUL) {
+            ra = reg_of[s.a];
+            rb = reg_of[s.b];
+            release(s.a, t);
+            if (s.b != s.a) release(s.b, t);
+        } else if (is_unary(s.op)) {
+            ra = reg_of[s.a];
+            release(s.a, t);
+        }
+        int r;
+        if (!free_regs.empty()) {
+            r = free_regs.back();
+            free_regs.pop_back();
         } else {
-            last_use[s.i] = (int)t;
+            r = (int)regs++;
         }
+        reg_of[s.dst] = r;
+        code.push_back(s.op | ((uint64_t)r << 8) | (ra << 24) | (rb << 40));
+        if (last_use[s.dst] < 0) free_regs.push_back(r);  // dead value
     }
-    std::vector<int> reg_of(R.nodes.size(), -1), free_regs;
+    code.push_back(END);
+    if (regs > n_regs) n_regs = regs;
+}
+
+}  // namespace
+
+static void compile(Recorder& R, qp_program* out) {
+    // the gates: runs of EMITs closed by a GATE
+    struct GateActs {
+        size_t first, last;  // [first, last] in R.actions, last = the GATE action
+        std::vector<size_t> cum;  // steps after each action when the gate is scheduled alone
+    };
+    std::vector<GateActs> gates;
+    for (size_t i = 0, start = 0; i < R.actions.size(); i++)
+        if (R.actions[i].op == GATE) {
+            gates.push_back({start, i, {}});
+            start = i + 1;
+        }
+    size_t total = 0;
+    for (auto& g : gates) {
+        Scheduler S(R);
+        for (size_t i = g.first; i <= g.last; i++) {
+            S.action(R.actions[i]);
+            g.cum.push_back(S.steps.size());
+        }
+        total += g.cum.back();
+    }
+    const size_t target = std::max(MIN_SEGMENT_STEPS, total / TARGET_SEGMENTS);
+    // pieces = lists of actions; a gate much larger than the target is cut between constraints
+    std::vector<std::vector<Recorder::Action>> pieces;
+    std::vector<Recorder::Action> cur;
+    size_t cur_cost = 0;
+    auto flush = [&]() {
+        if (!cur.empty()) pieces.push_back(cur);
+        cur.clear();
+        cur_cost = 0;
+    };
+    for (const auto& g : gates) {
+        const size_t cost = g.cum.back(), n_emit = g.last - g.first;
+        const size_t parts = std::min<size_t>(std::max<size_t>(1, (cost + target / 2) / target), std::max<size_t>(1, n_emit));
+        if (parts > 1) {
+            flush();
+            size_t i = g.first;
+            for (size_t part = 0; part < parts; part++) {
+                const size_t until = part + 1 == parts ? cost : cost * (part + 1) / parts;
+                std::vector<Recorder::Action> acts;
+                while (i < g.last && (g.cum[i - g.first] <= until || acts.empty())) acts.push_back(R.actions[i++]);
+                if (part + 1 == parts)
+                    while (i < g.last) acts.push_back(R.actions[i++]);
+                if (acts.empty()) continue;
+                acts.push_back(R.actions[g.last]);  // every part closes with the gate's filter
+                pieces.push_back(acts);
+            }
+            continue;
+        }
+        if (cur_cost && cur_cost + cost > target + target / 2) flush();
+        for (size_t i = g.first; i <= g.last; i++) cur.push_back(R.actions[i]);
+        cur_cost += cost;
+        if (cur_cost >= target) flush();
+    }
+    flush();
     uint32_t n_regs = 0;
-    for (size_t t = 0; t < sched.size(); t++) {
-        const Step& s = sched[t];
-        if (s.is_node) {
-            const auto& nd = R.nodes[s.i];
-            uint64_t ra = 0, rb = 0;
-            if (nd.op == ADD || nd.op == SUB || nd.op == MUL) {
-                ra = reg_of[nd.a];
-                rb = reg_of[nd.b];
-                if (last_use[nd.a] == (int)t) free_regs.push_back(reg_of[nd.a]);
-                if (nd.b != nd.a && last_use[nd.b] == (int)t) free_regs.push_back(reg_of[nd.b]);
-            } else if (is_unary(nd.op)) {
-                ra = reg_of[nd.a];
-                rb = nd.b;
-                if (last_use[nd.a] == (int)t) free_regs.push_back(reg_of[nd.a]);
-            } else {
-                ra = nd.a;
-            }
-            int r;
-            if (!free_regs.empty()) {
-                r = free_regs.back();
-                free_regs.pop_back();
-            } else {
-                r = (int)n_regs++;
-            }
-            reg_of[s.i] = r;
-            out->code.push_back(nd.op | ((uint64_t)r << 8) | (ra << 24) | (rb << 40));
-            if (last_use[s.i] < 0) free_regs.push_back(r);
-        } else {
-            out->code.push_back(s.op | ((uint64_t)reg_of[s.i] << 24) | ((uint64_t)s.k << 40));
-            if (last_use[s.i] == (int)t) free_regs.push_back(reg_of[s.i]);
-        }
+    for (const auto& acts : pieces) {
+        Scheduler S(R);
+        for (const auto& a : acts) S.action(a);
+        out->segments.push_back((uint32_t)out->code.size());
+        encode(S, out->code, n_regs);
     }
+    if (!out->code.empty()) out->code.pop_back();  // the library appends the final OP_END itself
     out->pool = R.pool;
     if (out->pool.empty()) out->pool.push_back(0);
     out->n_regs = n_regs ? n_regs : 1;
@@ -423,6 +736,10 @@ extern "C" size_t qp_program_pool(const qp_program* p, const uint64_t** pool) {
     return p->pool.size();
 }
 extern "C" unsigned qp_program_regs(const qp_program* p) { return p->n_regs; }
+extern "C" size_t qp_program_segments(const qp_program* p, const uint32_t** offsets) {
+    if (offsets) *offsets = p->segments.data();
+    return p->segments.size();
+}
 extern "C" unsigned qp_program_num_selectors(const qp_program* p) { return (unsigned)p->groups.size() / 2; }
 extern "C" unsigned qp_program_num_gate_constants(const qp_program* p) { return p->num_gate_constants; }
 extern "C" unsigned qp_program_num_gate_constraints(const qp_program* p) { return p->num_gate_constraints; }

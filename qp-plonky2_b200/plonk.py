@@ -183,7 +183,44 @@ class ConstraintProgram:
 
 # ---- gates ------------------------------------------------------------------------------------------
 (GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON, GATE_ARITHMETIC_EXT, GATE_MUL_EXT,
- GATE_BASE_SUM_2) = range(8)  # qp_plonky2_host.h
+ GATE_BASE_SUM_2, GATE_RANDOM_ACCESS, GATE_REDUCING, GATE_REDUCING_EXT, GATE_POSEIDON_MDS, GATE_EXPONENTIATION,
+ GATE_COSET_INTERPOLATION) = range(14)  # qp_plonky2_host.h
+
+# Debug rendering of PhantomData<F> inside gate ids: core::any::type_name of the field type.  The
+# field crate's package is `qp-plonky2-field` with no [lib] rename (field/Cargo.toml:2), so the path
+# starts with `qp_plonky2_field`.
+_PHANTOM = "PhantomData<qp_plonky2_field::goldilocks_field::GoldilocksField>"
+
+
+class ModP:
+    """Integer mod p with the operators the gate bodies use (witness generation, self-checks)."""
+
+    __slots__ = ("v",)
+
+    def __init__(self, v):
+        self.v = int(v) % P
+
+    @staticmethod
+    def _o(o):
+        return o.v if isinstance(o, ModP) else int(o)
+
+    def __add__(self, o):
+        return ModP(self.v + self._o(o))
+
+    def __sub__(self, o):
+        return ModP(self.v - self._o(o))
+
+    def __rsub__(self, o):
+        return ModP(self._o(o) - self.v)
+
+    def __mul__(self, o):
+        return ModP(self.v * self._o(o))
+
+    __radd__ = __add__
+    __rmul__ = __mul__
+
+    def __int__(self):
+        return self.v
 
 
 class Gate:
@@ -341,6 +378,391 @@ class BaseSumGate2(Gate):  # plonky2/src/gates/base_sum.rs with B = 2
         return out
 
 
+def _ext_add(x, y):
+    return (x[0] + y[0], x[1] + y[1])
+
+
+def _ext_sub(x, y):
+    return (x[0] - y[0], x[1] - y[1])
+
+
+def _ext_scalar(x, k):
+    return (x[0] * k, x[1] * k)
+
+
+def primitive_root_of_unity(n_log):
+    """field/src/types.rs:280-284 with POWER_OF_TWO_GENERATOR of goldilocks_field.rs:91."""
+    g = 7277203076849721926
+    for _ in range(32 - n_log):
+        g = g * g % P
+    return g
+
+
+def two_adic_subgroup(n_log):
+    """field/src/types.rs:292-295."""
+    g, out, v = primitive_root_of_unity(n_log), [], 1
+    for _ in range(1 << n_log):
+        out.append(v)
+        v = v * g % P
+    return out
+
+
+def barycentric_weights(xs):
+    """field/src/interpolation.rs:53-65."""
+    out = []
+    for i, xi in enumerate(xs):
+        d = 1
+        for j, xj in enumerate(xs):
+            if j != i:
+                d = d * (xi - xj) % P
+        out.append(pow(d, P - 2, P))
+    return out
+
+
+class RandomAccessGate(Gate):  # plonky2/src/gates/random_access.rs
+    kind = GATE_RANDOM_ACCESS
+
+    def __init__(self, num_copies, bits, num_extra_constants):
+        self.num_copies, self.bits, self.num_extra_constants = num_copies, bits, num_extra_constants
+        assert bits < 256 and num_copies < 256 and num_extra_constants < 65536
+        self.param = bits | (num_copies << 8) | (num_extra_constants << 16)
+        self.degree = bits + 1                                                # random_access.rs:275-277
+        self.num_constants = num_extra_constants
+        self.num_constraints = num_copies * (bits + 2) + num_extra_constants  # :279-282
+
+    @staticmethod
+    def new_from_config(num_wires, num_routed_wires, bits, config_num_constants=2):
+        vec_size = 1 << bits                                                  # random_access.rs:58-76
+        max_copies = min(num_routed_wires // (2 + vec_size), num_wires // (2 + vec_size + bits))
+        max_extra = num_routed_wires - (2 + vec_size) * max_copies
+        return RandomAccessGate(max_copies, bits, min(max_extra, config_num_constants))
+
+    def id(self):
+        return "RandomAccessGate { bits: %d, num_copies: %d, num_extra_constants: %d, _phantom: %s }<D=2>" % (
+            self.bits, self.num_copies, self.num_extra_constants, _PHANTOM)
+
+    vec_size = property(lambda self: 1 << self.bits)
+
+    def wire_access_index(self, copy):
+        return (2 + self.vec_size) * copy
+
+    def wire_claimed_element(self, copy):
+        return (2 + self.vec_size) * copy + 1
+
+    def wire_list_item(self, i, copy):
+        return (2 + self.vec_size) * copy + 2 + i
+
+    def wire_extra_constant(self, i):
+        return (2 + self.vec_size) * self.num_copies + i
+
+    def num_routed_wires(self):
+        return (2 + self.vec_size) * self.num_copies + self.num_extra_constants
+
+    def wire_bit(self, i, copy):
+        return self.num_routed_wires() + copy * self.bits + i
+
+    def eval_unfiltered(self, consts, wires, pih):
+        out = []
+        for copy in range(self.num_copies):  # random_access.rs:144-189 (packed form :307-352)
+            access_index = wires(self.wire_access_index(copy))
+            items = [wires(self.wire_list_item(i, copy)) for i in range(self.vec_size)]
+            claimed = wires(self.wire_claimed_element(copy))
+            bits = [wires(self.wire_bit(i, copy)) for i in range(self.bits)]
+            for b in bits:
+                out.append(b * (b - 1))
+            acc = None
+            for b in reversed(bits):
+                acc = b if acc is None else acc * 2 + b   # fold from ZERO: 0.double() + b = b
+            out.append(acc - access_index)
+            for b in bits:
+                items = [x + b * (y - x) for x, y in zip(items[0::2], items[1::2])]
+            out.append(items[0] - claimed)
+        for i in range(self.num_extra_constants):
+            out.append(consts(i) - wires(self.wire_extra_constant(i)))
+        return out
+
+    def generate(self, copy_inputs, extra_constants):
+        """RandomAccessGenerator (random_access.rs:370-406): copy_inputs[copy] = (index, [items])."""
+        row = {}
+        for copy, (index, items) in enumerate(copy_inputs):
+            row[self.wire_access_index(copy)] = index
+            for i, v in enumerate(items):
+                row[self.wire_list_item(i, copy)] = v
+            row[self.wire_claimed_element(copy)] = items[index]
+            for i in range(self.bits):
+                row[self.wire_bit(i, copy)] = (index >> i) & 1
+        for i, v in enumerate(extra_constants):
+            row[self.wire_extra_constant(i)] = v
+        return row
+
+
+class ReducingGate(Gate):  # plonky2/src/gates/reducing.rs (D = 2)
+    degree = 2
+    kind = GATE_REDUCING
+    EXT_COEFFS = False
+
+    def __init__(self, num_coeffs):
+        assert num_coeffs > 0
+        self.num_coeffs = self.param = num_coeffs
+        self.num_constraints = 2 * num_coeffs
+
+    @staticmethod
+    def max_coeffs_len(num_wires, num_routed_wires):
+        return min(num_routed_wires - 6, (num_wires - 4) // 3)  # reducing.rs:36-38
+
+    def id(self):
+        return "ReducingGate { num_coeffs: %d }" % self.num_coeffs
+
+    def coeff(self, wires, i):
+        return (wires(6 + i), 0)
+
+    def start_accs(self):
+        return 6 + self.num_coeffs
+
+    def wires_accs(self, i):
+        return 0 if i == self.num_coeffs - 1 else self.start_accs() + 2 * i
+
+    def eval_unfiltered(self, consts, wires, pih):
+        ext = lambda w: (wires(w), wires(w + 1))
+        alpha, acc = ext(2), ext(4)
+        out = []
+        for i in range(self.num_coeffs):  # reducing.rs:109-133
+            nxt = ext(self.wires_accs(i))
+            c = self.coeff(wires, i)
+            t = _ext_mul(acc, alpha)
+            out.append(t[0] + c[0] - nxt[0])
+            out.append((t[1] + c[1] - nxt[1]) if self.EXT_COEFFS else (t[1] - nxt[1]))
+            acc = nxt
+        return out
+
+    def generate(self, alpha, old_acc, coeffs):
+        """ReducingGenerator (reducing.rs:210-242); coeffs: base elements (or pairs for the extension gate)."""
+        row = {2: alpha[0], 3: alpha[1], 4: old_acc[0], 5: old_acc[1]}
+        acc = (ModP(old_acc[0]), ModP(old_acc[1]))
+        al = (ModP(alpha[0]), ModP(alpha[1]))
+        for i, c in enumerate(coeffs):
+            c = c if self.EXT_COEFFS else (c, 0)
+            w = 6 + (2 * i if self.EXT_COEFFS else i)
+            row[w] = c[0]
+            if self.EXT_COEFFS:
+                row[w + 1] = c[1]
+            t = _ext_mul(acc, al)
+            acc = (t[0] + c[0], t[1] + c[1])
+            a = self.wires_accs(i)
+            row[a], row[a + 1] = acc[0].v, acc[1].v
+        return row
+
+
+class ReducingExtensionGate(ReducingGate):  # plonky2/src/gates/reducing_extension.rs (D = 2)
+    kind = GATE_REDUCING_EXT
+    EXT_COEFFS = True
+
+    @staticmethod
+    def max_coeffs_len(num_wires, num_routed_wires):
+        return min((num_routed_wires - 6) // 2, (num_wires - 4) // 4)  # reducing_extension.rs:37-41
+
+    def id(self):
+        return "ReducingExtensionGate { num_coeffs: %d }" % self.num_coeffs
+
+    def coeff(self, wires, i):
+        return (wires(6 + 2 * i), wires(7 + 2 * i))
+
+    def start_accs(self):
+        return 6 + 2 * self.num_coeffs
+
+
+class PoseidonMdsGate(Gate):  # plonky2/src/gates/poseidon_mds.rs (D = 2)
+    degree = 1
+    kind = GATE_POSEIDON_MDS
+    num_constraints = 24
+
+    def id(self):
+        return "PoseidonMdsGate(%s)<WIDTH=12>" % _PHANTOM
+
+    @staticmethod
+    def _mds_ext(inp):
+        k = _poseidon_constants()
+        circ, diag = k["POSEIDON_MDS_CIRC"], k["POSEIDON_MDS_DIAG"]
+        out = []
+        for r in range(12):  # mds_row_shf_field, core/src/poseidon.rs:200-215
+            acc = _ext_scalar(inp[r], circ[0] + diag[r])
+            for i in range(1, 12):
+                acc = _ext_add(acc, _ext_scalar(inp[(i + r) % 12], circ[i]))
+            out.append(acc)
+        return out
+
+    def eval_unfiltered(self, consts, wires, pih):
+        inp = [(wires(2 * i), wires(2 * i + 1)) for i in range(12)]
+        comp = self._mds_ext(inp)
+        out = []
+        for i in range(12):  # poseidon_mds.rs:150-169
+            out.append(wires(24 + 2 * i) - comp[i][0])
+            out.append(wires(25 + 2 * i) - comp[i][1])
+        return out
+
+    def generate(self, inputs):
+        """PoseidonMdsGenerator: inputs = 12 pairs."""
+        row = {}
+        for i, (a, b) in enumerate(inputs):
+            row[2 * i], row[2 * i + 1] = a, b
+        comp = self._mds_ext([(ModP(a), ModP(b)) for a, b in inputs])
+        for i in range(12):
+            row[24 + 2 * i], row[25 + 2 * i] = comp[i][0].v, comp[i][1].v
+        return row
+
+
+class ExponentiationGate(Gate):  # plonky2/src/gates/exponentiation.rs
+    degree = 4
+    kind = GATE_EXPONENTIATION
+
+    def __init__(self, num_power_bits):
+        self.num_power_bits = self.param = num_power_bits
+        self.num_constraints = num_power_bits + 1
+
+    @staticmethod
+    def new_from_config(num_wires, num_routed_wires):
+        return ExponentiationGate(min(num_routed_wires - 2, (num_wires - 2) // 2))  # exponentiation.rs:51-60
+
+    def id(self):
+        return "ExponentiationGate { num_power_bits: %d, _phantom: %s }<D=2>" % (self.num_power_bits, _PHANTOM)
+
+    def eval_unfiltered(self, consts, wires, pih):
+        n = self.num_power_bits
+        base, output = wires(0), wires(1 + n)
+        out = []
+        for i in range(n):  # exponentiation.rs:210-245
+            cur_bit = wires(1 + (n - i - 1))
+            mul_by = cur_bit * base + (1 - cur_bit)
+            if i == 0:
+                computed = mul_by
+            else:
+                prev = wires(2 + n + i - 1)
+                computed = prev * prev * mul_by
+            out.append(computed - wires(2 + n + i))
+        out.append(output - wires(2 + n + n - 1))
+        return out
+
+    def generate(self, base, power_bits):
+        """ExponentiationGenerator (exponentiation.rs:270-306); power_bits little-endian."""
+        n = self.num_power_bits
+        row = {0: base}
+        cur = 1
+        for i in range(n):
+            row[1 + i] = power_bits[i]
+        for i in range(n):
+            if power_bits[n - i - 1] == 1:
+                cur = cur * base % P
+            row[2 + n + i] = cur
+            last = cur
+            cur = cur * cur % P
+        row[1 + n] = last
+        return row
+
+
+class CosetInterpolationGate(Gate):  # plonky2/src/gates/coset_interpolation.rs (D = 2)
+    kind = GATE_COSET_INTERPOLATION
+
+    def __init__(self, subgroup_bits, degree):
+        self.subgroup_bits, self.degree = subgroup_bits, degree
+        self.param = subgroup_bits | (degree << 8)
+        self.num_points = 1 << subgroup_bits
+        self.num_intermediates = (self.num_points - 2) // (degree - 1)
+        self.num_constraints = 1 + 2 + 2 + 4 * self.num_intermediates   # coset_interpolation.rs:406-410
+        self.domain = two_adic_subgroup(subgroup_bits)
+        self.weights = barycentric_weights(self.domain)
+        self.start_intermediates = 1 + 2 * self.num_points + 4
+
+    @staticmethod
+    def with_max_degree(subgroup_bits, max_degree):
+        n_points = 1 << subgroup_bits        # coset_interpolation.rs:49-75
+        n_intermediates = (n_points - 2) // (max_degree - 1)
+        return CosetInterpolationGate(subgroup_bits, (n_points - 2) // (n_intermediates + 1) + 2)
+
+    def id(self):
+        return "CosetInterpolationGate { subgroup_bits: %d, degree: %d, barycentric_weights: [%s], _phantom: %s }<D=2>" % (
+            self.subgroup_bits, self.degree, ", ".join(str(w) for w in self.weights), _PHANTOM)
+
+    def wires_value(self, i):
+        return 1 + 2 * i
+
+    def wires_evaluation_point(self):
+        return 1 + 2 * self.num_points
+
+    def wires_evaluation_value(self):
+        return 3 + 2 * self.num_points
+
+    def wires_intermediate_eval(self, i):
+        return self.start_intermediates + 2 * i
+
+    def wires_intermediate_prod(self, i):
+        return self.start_intermediates + 2 * (self.num_intermediates + i)
+
+    def wires_shifted_evaluation_point(self):
+        return self.start_intermediates + 4 * self.num_intermediates
+
+    def wire_shift_inverse(self):
+        return self.start_intermediates + 2 * (2 * self.num_intermediates + 1)
+
+    def num_wires(self):
+        return self.wire_shift_inverse() + 1
+
+    def _partial(self, lo, hi, values, x, ev, prod):
+        """partial_interpolate, coset_interpolation.rs:572-599."""
+        for j in range(lo, hi):
+            val = _ext_scalar(values[j], self.weights[j])
+            term = (x[0] - self.domain[j], x[1])
+            ev = _ext_add(_ext_mul(ev, term), _ext_mul(val, prod))
+            prod = _ext_mul(prod, term)
+        return ev, prod
+
+    def _first(self, values, x):
+        # initial_eval = 0, initial_partial_prod = 1: the first step is (w_0 v_0, x - x_0)
+        ev = _ext_scalar(values[0], self.weights[0])
+        prod = (x[0] - self.domain[0], x[1])
+        return self._partial(1, self.degree, values, x, ev, prod)
+
+    def eval_unfiltered(self, consts, wires, pih):
+        ext = lambda w: (wires(w), wires(w + 1))
+        shift, shift_inv = wires(0), wires(self.wire_shift_inverse())
+        point, shifted = ext(self.wires_evaluation_point()), ext(self.wires_shifted_evaluation_point())
+        out = [shift * shift_inv - 1]          # coset_interpolation.rs:260-307
+        out += list(_ext_sub(point, _ext_scalar(shifted, shift)))
+        values = [ext(self.wires_value(i)) for i in range(self.num_points)]
+        ev, prod = self._first(values, shifted)
+        for i in range(self.num_intermediates):
+            iev, iprod = ext(self.wires_intermediate_eval(i)), ext(self.wires_intermediate_prod(i))
+            out += list(_ext_sub(iev, ev)) + list(_ext_sub(iprod, prod))
+            start = 1 + (self.degree - 1) * (i + 1)
+            end = min(start + self.degree - 1, self.num_points)
+            ev, prod = self._partial(start, end, values, shifted, iev, iprod)
+        out += list(_ext_sub(ext(self.wires_evaluation_value()), ev))
+        return out
+
+    def generate(self, shift, values, point):
+        """InterpolationGenerator (coset_interpolation.rs:461-530)."""
+        row = {0: shift}
+        for i, (a, b) in enumerate(values):
+            row[self.wires_value(i)], row[self.wires_value(i) + 1] = a, b
+        w = self.wires_evaluation_point()
+        row[w], row[w + 1] = point
+        sinv = pow(shift, P - 2, P)
+        row[self.wire_shift_inverse()] = sinv
+        shifted = (ModP(point[0] * sinv), ModP(point[1] * sinv))
+        w = self.wires_shifted_evaluation_point()
+        row[w], row[w + 1] = shifted[0].v, shifted[1].v
+        vals = [(ModP(a), ModP(b)) for a, b in values]
+        ev, prod = self._first(vals, shifted)
+        for i in range(self.num_intermediates):
+            for w, v in ((self.wires_intermediate_eval(i), ev), (self.wires_intermediate_prod(i), prod)):
+                row[w], row[w + 1] = v[0].v, v[1].v
+            start = 1 + (self.degree - 1) * (i + 1)
+            end = min(start + self.degree - 1, self.num_points)
+            ev, prod = self._partial(start, end, vals, shifted, ev, prod)
+        w = self.wires_evaluation_value()
+        row[w], row[w + 1] = ev[0].v, ev[1].v
+        return row
+
+
 def _poseidon_constants():
     """The tables of core/src/poseidon_goldilocks.rs as generated into csrc/poseidon_constants.h
     (tools/gen_poseidon_constants.py)."""
@@ -373,7 +795,7 @@ class PoseidonGate(Gate):
     END = 29 + 12 * 3 + 22 + 12 * 4            # 135 wires
 
     def id(self):
-        return "PoseidonGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>"
+        return "PoseidonGate(%s)<WIDTH=12>" % _PHANTOM
 
     @staticmethod
     def _mds(state):
@@ -605,7 +1027,9 @@ def native_constraint_program(gates, max_degree):
             order.append(o.value)
             sel.append(s_.value)
             groups[s_.value] = (a.value, b.value)
-        return dict(code=code, pool=pool, n_regs=int(lib().qp_program_regs(h)),
+        n = lib().qp_program_segments(h, C.byref(ptr))
+        segments = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+        return dict(code=code, pool=pool, n_regs=int(lib().qp_program_regs(h)), segments=segments,
                     num_selectors=int(lib().qp_program_num_selectors(h)), selector_indices=sel,
                     groups=[groups[k] for k in sorted(groups)], order=order,
                     num_gate_constants=int(lib().qp_program_num_gate_constants(h)),

@@ -31,7 +31,8 @@ def _addmod(a, b):
 
 class SynthCircuit:
     def __init__(self, degree_bits, seed=1, num_wires=143, num_routed_wires=80, num_challenges=2,
-                 quotient_degree_factor=8, rate_bits=3, cap_height=4, poseidon=False, extra_gates=False):
+                 quotient_degree_factor=8, rate_bits=3, cap_height=4, poseidon=False, extra_gates=False,
+                 recursion_gates=False):
         rng = np.random.Generator(np.random.PCG64(seed))
         n = 1 << degree_bits
         nr = num_routed_wires
@@ -43,12 +44,22 @@ class SynthCircuit:
         if extra_gates:   # the extension-field arithmetic and bit-decomposition gates of recursion circuits
             gates += [plonk.ArithmeticExtensionGate.new_from_config(nr), plonk.MulExtensionGate.new_from_config(nr),
                       plonk.BaseSumGate2(63)]
+        if recursion_gates:   # the rest of a recursive verifier's gate set (standard_recursion_config shapes)
+            gates += [plonk.RandomAccessGate.new_from_config(num_wires, nr, 4),
+                      plonk.ReducingGate(plonk.ReducingGate.max_coeffs_len(num_wires, nr)),
+                      plonk.ReducingExtensionGate(plonk.ReducingExtensionGate.max_coeffs_len(num_wires, nr)),
+                      plonk.PoseidonMdsGate(), plonk.ExponentiationGate.new_from_config(num_wires, nr),
+                      plonk.CosetInterpolationGate.with_max_degree(4, quotient_degree_factor)]
         self.common = c = plonk.CommonCircuitData(degree_bits, gates, num_wires, nr, num_challenges,
                                                   quotient_degree_factor, rate_bits, cap_height)
         kinds = {"NoopGate": oracle.GATE_NOOP, "ConstantGate": oracle.GATE_CONSTANT,
                  "PublicInputGate": oracle.GATE_PUBLIC_INPUT, "ArithmeticGate": oracle.GATE_ARITHMETIC,
                  "PoseidonGate": oracle.GATE_POSEIDON, "ArithmeticExtensionGate": oracle.GATE_ARITHMETIC_EXT,
-                 "MulExtensionGate": oracle.GATE_MUL_EXT, "BaseSumGate": oracle.GATE_BASE_SUM_2}
+                 "MulExtensionGate": oracle.GATE_MUL_EXT, "BaseSumGate": oracle.GATE_BASE_SUM_2,
+                 "RandomAccessGate": oracle.GATE_RANDOM_ACCESS, "ReducingGate": oracle.GATE_REDUCING,
+                 "ReducingExtensionGate": oracle.GATE_REDUCING_EXT, "PoseidonMdsGate": oracle.GATE_POSEIDON_MDS,
+                 "ExponentiationGate": oracle.GATE_EXPONENTIATION,
+                 "CosetInterpolationGate": oracle.GATE_COSET_INTERPOLATION}
         og = []
         for i, g in enumerate(c.gates):
             name = g.id().split(" ")[0].split("(")[0]
@@ -65,6 +76,11 @@ class SynthCircuit:
         if extra_gates:
             kinds_p["ArithmeticGate"] -= 0.2
             kinds_p.update({"ArithmeticExtensionGate": 0.08, "MulExtensionGate": 0.06, "BaseSumGate": 0.06})
+        rec_names = ["RandomAccessGate", "ReducingGate", "ReducingExtensionGate", "PoseidonMdsGate",
+                     "ExponentiationGate", "CosetInterpolationGate"]
+        if recursion_gates:
+            kinds_p[max(kinds_p, key=kinds_p.get)] -= 0.18   # from the most frequent gate (Poseidon / Arithmetic)
+            kinds_p.update({k: 0.03 for k in rec_names})
         row_gate = rng.choice([idx[k] for k in kinds_p], size=n, p=list(kinds_p.values()))
         row_gate[0] = idx["PublicInputGate"]
         self.row_gate = row_gate
@@ -77,6 +93,8 @@ class SynthCircuit:
         uses = (row_gate == idx["ConstantGate"]) | (row_gate == idx["ArithmeticGate"])
         if extra_gates:
             uses |= (row_gate == idx["ArithmeticExtensionGate"]) | (row_gate == idx["MulExtensionGate"])
+        if recursion_gates:
+            uses |= row_gate == idx["RandomAccessGate"]
         consts[c.num_selectors:] = np.where(uses[None, :], gate_consts, 0)
         self.constants = consts
         # witness
@@ -152,6 +170,31 @@ class SynthCircuit:
             for i in range(62, -1, -1):
                 total = (total * 2 + bits[i].astype(object)) % P
             wires[0, rows] = total.astype(np.uint64)
+        if recursion_gates:   # one generator call per row, like the reference's SimpleGenerators
+            G = {g.id().split(" ")[0].split("(")[0]: g for g in c.gates}
+            felt = lambda: int(rng.integers(0, P, dtype=np.uint64))
+            ext = lambda: (felt(), felt())
+            for r in range(n):
+                name = next((k for k in rec_names if row_gate[r] == idx[k]), None)
+                if name is None:
+                    continue
+                g = G[name]
+                if name == "RandomAccessGate":
+                    row = g.generate([(int(rng.integers(0, g.vec_size)), [felt() for _ in range(g.vec_size)])
+                                      for _ in range(g.num_copies)],
+                                     [int(consts[c.num_selectors + i, r]) for i in range(g.num_extra_constants)])
+                elif name == "ReducingGate":
+                    row = g.generate(ext(), ext(), [felt() for _ in range(g.num_coeffs)])
+                elif name == "ReducingExtensionGate":
+                    row = g.generate(ext(), ext(), [ext() for _ in range(g.num_coeffs)])
+                elif name == "PoseidonMdsGate":
+                    row = g.generate([ext() for _ in range(12)])
+                elif name == "ExponentiationGate":
+                    row = g.generate(felt(), [int(b) for b in rng.integers(0, 2, size=g.num_power_bits)])
+                else:
+                    row = g.generate(felt() or 1, [ext() for _ in range(g.num_points)], ext())
+                for w, v in row.items():
+                    wires[w, r] = v
         # Poseidon rows: inputs and swap are free, everything else follows (PoseidonGenerator)
         if poseidon:
             pg = plonk.PoseidonGate()

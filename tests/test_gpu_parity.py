@@ -384,6 +384,45 @@ def test_full_size_commit_properties(qp, ctx):
     print("full-size timing (ms):", b.timing)
 
 
+def test_config_c_row_count_commit_properties(qp):
+    """2^23 rows (BASELINE.json configs[4]'s row count; three-pass transforms of size 2^23, LDE of
+    2^26 points) x 3 columns: size-independent properties, as above -- leaves verify against the cap
+    with the oracle's verifier, a row is the Horner evaluation of the returned coefficients, the
+    forward transform of the coefficients returns the input, and a coset shard of the same
+    commitment (what one of 8 GPUs computes) reproduces its two cap entries."""
+    import torch
+
+    lg_n, cols, rate, cap_h = 23, 3, 3, 4
+    ctx = qp.Context(0, max_lde_log=lg_n + rate)
+    try:
+        gen = torch.Generator(device="cuda").manual_seed(23)
+        d = torch.randint(0, 2**62, (cols, 1 << lg_n), dtype=torch.int64, device="cuda", generator=gen)
+        b = qp.PolynomialBatch.from_values(ctx, d, rate, False, cap_h)
+        cap = b.merkle_tree.cap
+        N = 1 << (lg_n + rate)
+        idxs = [0, N - 1, 123456789 % N, (N // 2) + 77]
+        rows = b.merkle_tree.get_many(idxs)
+        for i, row in zip(idxs, rows):
+            assert oracle.merkle_verify(row, i, cap, b.merkle_tree.prove(i))
+        coeffs = b.polynomials
+        g, w = pyref.GENERATOR, pyref.primitive_root_of_unity(lg_n + rate)
+        i, row = idxs[2], rows[2]
+        nat = int(format(i, "0%db" % (lg_n + rate))[::-1], 2)
+        x = g * pow(w, nat, P) % P
+        acc = 0
+        for ci in coeffs[1][::-1].tolist():
+            acc = (acc * x + ci) % P
+        assert int(row[1]) == acc
+        back = ctx.coset_fft(coeffs[:1], shift=1)
+        assert (back == d[:1].cpu().numpy().view(np.uint64)).all()
+        shard = qp.PolynomialBatch.from_coeffs(ctx, coeffs, rate, False, cap_h, block_first=5, block_count=1)
+        assert (shard.merkle_tree.cap == cap[10:12]).all()
+        shard.free()
+        b.free()
+    finally:
+        ctx.close()
+
+
 # ---- opening side of prove_openings (SURVEY 8f rank 1) -----------------------------------------
 
 def test_eval_polys_at_ext_point(qp, ctx):

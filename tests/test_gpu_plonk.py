@@ -111,17 +111,18 @@ def test_large_circuit_verifier_identity(qp, ctx):
                                        alphas, x0)
 
 
-@pytest.mark.parametrize("degree_bits,qdf,pow_bits,queries,poseidon,extra", [
-    (6, 8, 6, 4, False, False), (9, 8, 16, 28, False, False), (8, 4, 10, 7, False, False), (11, 8, 16, 28, False, False),
-    (10, 8, 16, 28, True, False), (9, 8, 12, 10, True, True)])
-def test_full_proof_bytes_match_oracle(qp, ctx, degree_bits, qdf, pow_bits, queries, poseidon, extra):
+@pytest.mark.parametrize("degree_bits,qdf,pow_bits,queries,poseidon,extra,rec", [
+    (6, 8, 6, 4, False, False, False), (9, 8, 16, 28, False, False, False), (8, 4, 10, 7, False, False, False),
+    (11, 8, 16, 28, False, False, False), (10, 8, 16, 28, True, False, False), (9, 8, 12, 10, True, True, False),
+    (9, 8, 12, 10, True, True, True), (7, 8, 8, 6, False, False, True)])
+def test_full_proof_bytes_match_oracle(qp, ctx, degree_bits, qdf, pow_bits, queries, poseidon, extra, rec):
     """prove_with_partition_witness (plonky2/src/plonk/prover.rs:176-398) end to end on the device,
     serialised like write_proof_with_public_inputs -- byte for byte against the oracle's prove()."""
     from oracle import prover as oprover
     from qp_plonky2_b200 import prover
 
     sc = SynthCircuit(degree_bits, seed=60 + degree_bits, quotient_degree_factor=qdf, poseidon=poseidon,
-                      extra_gates=extra)
+                      extra_gates=extra, recursion_gates=rec)
     c = sc.common
     circ = plonk.Circuit(ctx, c, sc.sigmas)
     cfg = prover.FriConfig(c.rate_bits, c.cap_height, pow_bits, 4, 5, queries)
@@ -181,8 +182,9 @@ def test_large_proof_openings_pass_the_verifier(qp, ctx):
     assert verifier_plonk_identity(c, openings, zeta, betas, gammas, alphas, pih)
 
 
-@pytest.mark.parametrize("degree_bits,poseidon,extra", [(10, False, False), (14, True, False), (12, True, True)])
-def test_device_proof_is_accepted_by_the_restated_verifier(qp, ctx, degree_bits, poseidon, extra):
+@pytest.mark.parametrize("degree_bits,poseidon,extra,rec", [(10, False, False, False), (14, True, False, False),
+                                                            (12, True, True, False), (12, True, True, True)])
+def test_device_proof_is_accepted_by_the_restated_verifier(qp, ctx, degree_bits, poseidon, extra, rec):
     """The reference's own acceptance criterion: the full verifier (tests/verifier.py: transcript,
     plonk identity at zeta, PoW, 28 FRI query rounds with every Merkle path, folding consistency,
     final polynomial) accepts the device's proof under standard_recursion_config -- at a size where
@@ -190,7 +192,7 @@ def test_device_proof_is_accepted_by_the_restated_verifier(qp, ctx, degree_bits,
     import verifier
     from qp_plonky2_b200 import prover
 
-    sc = SynthCircuit(degree_bits, seed=300 + degree_bits, poseidon=poseidon, extra_gates=extra)
+    sc = SynthCircuit(degree_bits, seed=300 + degree_bits, poseidon=poseidon, extra_gates=extra, recursion_gates=rec)
     c = sc.common
     circ = plonk.Circuit(ctx, c, sc.sigmas)
     pd = prover.ProverData(ctx, circ, sc.constants_sigmas())

@@ -23,7 +23,10 @@ def run_program(code, pool, n_regs, wires, consts, pih, alphas):
     for ins in code:
         ins = int(ins)
         op, dst, a, b = ins & 0xFF, (ins >> 8) & 0xFFFF, (ins >> 24) & 0xFFFF, (ins >> 40) & 0xFFFF
-        if op == plonk.OP_LDW:
+        if op == plonk.OP_END:     # segments are self-contained: no register survives an END
+            r = [None] * n_regs
+            assert h == [0] * nc
+        elif op == plonk.OP_LDW:
             r[dst] = int(wires[a])
         elif op == plonk.OP_LDK:
             r[dst] = int(consts[a])
@@ -63,13 +66,16 @@ def test_selectors_info_matches_reference_rule(qdf):
 
 
 @pytest.mark.parametrize("native", [False, True])
-@pytest.mark.parametrize("qdf,poseidon,extra", [(8, False, False), (4, False, False), (8, True, False), (8, True, True),
-                                                (4, False, True)])
-def test_constraint_program_matches_oracle_gate_evaluation(qdf, poseidon, native, extra):
+@pytest.mark.parametrize("qdf,poseidon,extra,rec", [(8, False, False, False), (4, False, False, False),
+                                                    (8, True, False, False), (8, True, True, False),
+                                                    (4, False, True, False), (8, True, True, True),
+                                                    (8, False, False, True)])
+def test_constraint_program_matches_oracle_gate_evaluation(qdf, poseidon, native, extra, rec):
     """The compiled program and the oracle's hand-written gate evaluators agree on random
     (non-satisfying) inputs: compare the full vanishing value with the permutation terms zeroed
     out by Z = partial products = 0... simpler: both sides computed in full."""
-    sc = SynthCircuit(5, seed=5, quotient_degree_factor=qdf, poseidon=poseidon, extra_gates=extra)
+    sc = SynthCircuit(5, seed=5, quotient_degree_factor=qdf, poseidon=poseidon, extra_gates=extra,
+                      recursion_gates=rec)
     c = sc.common
     if native:   # qp-plonky2_b200/host/plonk_host.cpp, the compiler whose output the device runs
         prog = plonk.native_constraint_program(c.gates, qdf + 1)
@@ -79,18 +85,28 @@ def test_constraint_program_matches_oracle_gate_evaluation(qdf, poseidon, native
         assert prog["num_gate_constraints"] == c.num_gate_constraints
     else:
         code, pool, n_regs = c.constraint_program()
+    if poseidon and extra and rec:   # the 14 gates of a recursive verifier circuit: four selector groups
+        assert c.groups == [(0, 7), (7, 11), (11, 13), (13, 14)] and c.num_constants == 4 + 2
+        assert [g.id().split(" ")[0].split("(")[0] for g in c.gates] == [
+            "NoopGate", "ConstantGate", "PoseidonMdsGate", "PublicInputGate", "BaseSumGate", "ReducingExtensionGate",
+            "ReducingGate", "ArithmeticExtensionGate", "ArithmeticGate", "MulExtensionGate", "ExponentiationGate",
+            "RandomAccessGate", "CosetInterpolationGate", "PoseidonGate"]
     if poseidon and not extra:   # degree 7 forces a second selector group (selectors.rs:140-150)
         assert c.groups == [(0, 4), (4, 5)] and c.num_gate_constraints == 123
-    if poseidon and extra:       # Noop, Constant, PublicInput, BaseSum, ArithmeticExtension, Arithmetic | MulExtension, Poseidon
+    if poseidon and extra and not rec:       # Noop, Constant, PublicInput, BaseSum, ArithmeticExtension, Arithmetic | MulExtension, Poseidon
         assert c.groups == [(0, 6), (6, 8)]
     rng = np.random.default_rng(7)
-    for trial in range(8):
+    for trial in range(4 * len(c.gates) if rec else 8):
         wires = oracle.rand_felts((c.num_wires,), 100 + trial)
         consts = oracle.rand_felts((c.num_constants,), 200 + trial)
         # a selector value that is a real gate index some of the time
         consts[0] = rng.integers(0, c.groups[0][1])
         if len(c.groups) > 1 and trial % 2:
             consts[0], consts[1] = plonk.UNUSED_SELECTOR, rng.integers(c.groups[1][0], c.groups[1][1])
+        if rec:   # every gate in turn is the selected one (its group's selector = its index, the others unused)
+            gi = trial % len(c.gates)
+            consts[:c.num_selectors] = plonk.UNUSED_SELECTOR
+            consts[c.selector_indices[gi]] = gi
         pih = oracle.rand_felts((4,), 300 + trial)
         alphas = oracle.rand_felts((2,), 400 + trial)
         nc, np_ = c.num_challenges, c.num_partial_products
@@ -198,6 +214,29 @@ def test_native_program_sorts_gates_like_the_builder():
     assert prog["groups"] == [(0, 4), (4, 5)] and prog["selector_indices"] == [0, 0, 0, 0, 1]
     with pytest.raises(ValueError):   # "... has too high degree. Consider increasing `quotient_degree_factor`."
         plonk.native_constraint_program(gates, 7)
+    # the whole gate set of a recursive verifier circuit, listed in a scrambled order
+    gates = [plonk.CosetInterpolationGate.with_max_degree(4, 8), plonk.PoseidonGate(), plonk.ReducingGate(46),
+             plonk.ExponentiationGate(70), plonk.ArithmeticGate(20), plonk.PublicInputGate(), plonk.PoseidonMdsGate(),
+             plonk.RandomAccessGate.new_from_config(143, 80, 4), plonk.NoopGate(), plonk.MulExtensionGate(13),
+             plonk.ReducingExtensionGate(34), plonk.ConstantGate(2), plonk.BaseSumGate2(63),
+             plonk.ArithmeticExtensionGate(10)]
+    prog = plonk.native_constraint_program(gates, 9)
+    want = plonk.sort_gates(gates)
+    assert [gates[i].id() for i in prog["order"]] == [g.id() for g in want]
+    assert prog["groups"] == [(0, 7), (7, 11), (11, 13), (13, 14)]
+    assert prog["num_gate_constants"] == 2 and prog["num_gate_constraints"] == 123
+    # the program is cut into self-contained segments of similar cost (PoseidonGate, half of the work,
+    # between constraints) and loads with distant uses are repeated instead of pinning registers:
+    # BaseSumGate alone would need 65
+    ends = [i for i, w in enumerate(prog["code"]) if int(w) & 0xFF == plonk.OP_END]
+    assert list(prog["segments"]) == [0] + [e + 1 for e in ends] and len(ends) >= 4
+    sizes = np.diff([0] + ends + [len(prog["code"])])
+    assert sizes.max() < 3 * sizes.min() and prog["n_regs"] <= 40
+    g = plonk.RandomAccessGate.new_from_config(143, 80, 4)      # random_access.rs:58-76 under the standard config
+    assert (g.num_copies, g.num_extra_constants, g.degree, g.num_constraints) == (4, 2, 5, 26)
+    g = plonk.CosetInterpolationGate.with_max_degree(4, 8)      # coset_interpolation.rs:49-75
+    assert (g.degree, g.num_intermediates, g.num_wires(), g.num_constraints) == (6, 2, 48, 13)
+    assert plonk.ExponentiationGate.new_from_config(143, 80).num_power_bits == 70
 
 
 def test_host_hash_no_pad_and_circuit_digest_match_oracle():
@@ -224,10 +263,11 @@ class _Fri:
         self.arity_bits, self.final_poly_bits, self.num_query_rounds = arity_bits, final_poly_bits, num_query_rounds
 
 
-@pytest.mark.parametrize("degree_bits,qdf,poseidon,pow_bits,queries,extra", [
-    (6, 8, False, 6, 5, False), (8, 8, True, 10, 9, False), (7, 4, False, 5, 4, False), (7, 8, True, 6, 5, True)])
+@pytest.mark.parametrize("degree_bits,qdf,poseidon,pow_bits,queries,extra,rec", [
+    (6, 8, False, 6, 5, False, False), (8, 8, True, 10, 9, False, False), (7, 4, False, 5, 4, False, False),
+    (7, 8, True, 6, 5, True, False), (7, 8, True, 6, 5, True, True)])
 def test_restated_verifier_accepts_oracle_proofs_and_rejects_tampering(degree_bits, qdf, poseidon, pow_bits, queries,
-                                                                      extra):
+                                                                      extra, rec):
     """The reference's acceptance criterion for everything above the permutation:
     the full verifier -- transcript, plonk identity, PoW, FRI query rounds with every Merkle path,
     folding consistency, final polynomial -- accepts the oracle's proof and rejects a flipped bit in
@@ -235,7 +275,8 @@ def test_restated_verifier_accepts_oracle_proofs_and_rejects_tampering(degree_bi
     from oracle import prover as oprover
     import verifier
 
-    sc = SynthCircuit(degree_bits, seed=91, quotient_degree_factor=qdf, poseidon=poseidon, extra_gates=extra)
+    sc = SynthCircuit(degree_bits, seed=91, quotient_degree_factor=qdf, poseidon=poseidon, extra_gates=extra,
+                      recursion_gates=rec)
     c = sc.common
     cs = oracle.PolynomialBatch.from_values(sc.constants_sigmas(), c.rate_bits, c.cap_height)
     proof, info = _oracle_prove(sc, proof_of_work_bits=pow_bits, num_query_rounds=queries)

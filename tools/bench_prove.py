@@ -19,7 +19,7 @@ import qp_plonky2_b200 as qp  # noqa: E402
 from qp_plonky2_b200 import plonk, prover  # noqa: E402
 
 
-def measure(degrees, cpu_degrees=(), reps=5, device=0, verbose=True, poseidon=True):
+def measure(degrees, cpu_degrees=(), reps=5, device=0, verbose=True, poseidon=True, recursion=False):
     """-> list of per-degree records (ms = best of reps - 1 timed runs after one warm-up)."""
     import torch
     from synth_circuit import SynthCircuit
@@ -31,7 +31,7 @@ def measure(degrees, cpu_degrees=(), reps=5, device=0, verbose=True, poseidon=Tr
     ctx = qp.Context(device, max_lde_log=max(a.degrees) + 3)
     out = {"prove": []}
     for lg in a.degrees:
-        sc = SynthCircuit(lg, seed=lg, poseidon=poseidon)
+        sc = SynthCircuit(lg, seed=lg, poseidon=poseidon, extra_gates=recursion, recursion_gates=recursion)
         c = sc.common
         circ = plonk.Circuit(ctx, c, sc.sigmas)
         pd = prover.ProverData(ctx, circ, sc.constants_sigmas())
@@ -75,8 +75,10 @@ def main():
     ap.add_argument("--cpu", type=int, nargs="*", default=[12])
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--no-poseidon", action="store_true")
+    ap.add_argument("--recursion", action="store_true",
+                    help="all 14 gate types of a recursive verifier circuit (four selector groups)")
     a = ap.parse_args()
-    print(json.dumps({"prove": measure(a.degrees, a.cpu, a.reps, poseidon=not a.no_poseidon)}))
+    print(json.dumps({"prove": measure(a.degrees, a.cpu, a.reps, poseidon=not a.no_poseidon, recursion=a.recursion)}))
 
 
 if __name__ == "__main__":
