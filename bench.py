@@ -168,11 +168,14 @@ def run_ours(args):
     c_lo, c_hi = (0, COLS) if world == 1 else qd.column_shard(COLS, world, rank)
 
     # synthetic witness: uniform canonical Goldilocks elements, seed 42 (same on every run)
-    gen = torch.Generator(device=dev).manual_seed(42)
-    full = torch.randint(0, 2**63 - 1, (COLS, n), dtype=torch.int64, device=dev, generator=gen)
-    full = full * 2 + torch.randint(0, 2, (COLS, n), dtype=torch.int64, device=dev, generator=gen)  # 64 random bits
-    d_vals = full[c_lo:c_hi].contiguous()
-    del full
+    # (per column, so that a rank generates only its own column shard and every N sees the same matrix)
+    gen = torch.Generator(device=dev)
+    d_vals = torch.empty((c_hi - c_lo, n), dtype=torch.int64, device=dev)
+    for c in range(c_lo, c_hi):
+        gen.manual_seed(42 + c)
+        col = torch.randint(0, 2**63 - 1, (n,), dtype=torch.int64, device=dev, generator=gen)
+        d_vals[c - c_lo] = col * 2 + torch.randint(0, 2, (n,), dtype=torch.int64, device=dev, generator=gen)  # 64 random bits
+    del col
     h_vals = torch.empty(d_vals.shape, dtype=torch.int64).pin_memory()
     h_vals.copy_(d_vals)
     torch.cuda.synchronize()
@@ -281,7 +284,7 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp) and world == 1:
         rec = json.load(open(tp)).get("leaf_hash_kernel", {})
-        if rec.get("rows_log") == args.rows_log:
+        if rec.get("rows_log") == args.rows_log and rec.get("cols", 135) == COLS:
             traffic = rec.get("dram_bytes")
     roof = {"kernel": "merkle::leaf_hash_kernel", "bound": "hbm", "achieved": leaf_bytes / (k_leaf * 1e-3) / 1e9,
             "peak": peak, "unit": "GB/s", "frac": leaf_bytes / (k_leaf * 1e-3) / 1e9 / peak, "traffic": traffic,
@@ -361,9 +364,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--rows-log", type=int, default=ROWS_LOG)
+    ap.add_argument("--cols", type=int, default=COLS,
+                    help="columns of the witness matrix (BASELINE.json configs[4]: --rows-log 23 --cols 400 --gpus 8)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-prove", action="store_true")
     args = ap.parse_args()
+    global COLS, METRIC
+    COLS = args.cols
+    METRIC = "commit_ms_2^%dx%d_rate%d" % (args.rows_log, COLS, RATE_BITS)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -213,13 +213,18 @@ int qp_fri_proof_of_work(qp_ctx* ctx, const uint64_t state12[12], unsigned witne
 /* What CommonCircuitData / ProverOnlyCircuitData contribute to these two steps
  * (plonky2/src/plonk/circuit_data.rs:412-470), created once per circuit and kept on the device.
  * The gate set (common_data.gates + selectors_info) arrives as a straight-line constraint program
- * over F_p: 64-bit words  op | dst << 8 | a << 24 | b << 40  with
- *   1 LDW dst = wire a            2 LDK dst = constants_sigmas polynomial a
- *   3 LDP dst = public_inputs_hash[a]   4 LDI dst = pool[a]
+ * over F_p: 64-bit words  op | dst << 8 | a << 16 | b << 24 | c << 32  (dst, a, b: registers < 256;
+ * c: a column, a pool slot or a constraint index) with
+ *   1 LDW dst = wire c            2 LDK dst = constants_sigmas polynomial c
+ *   3 LDP dst = public_inputs_hash[c]   4 LDI dst = pool[c]
  *   5 ADD  6 SUB  7 MUL   (dst = r[a] op r[b])
- *   10 MULI dst = r[a] * pool[b]     11 ADDI dst = r[a] + pool[b]
- *   8 EMIT a, b  constraint number b of the current gate has the value r[a]
+ *   10 MULI dst = r[a] * pool[c]     11 ADDI dst = r[a] + pool[c]     13 FMAI dst = r[a] * pool[c] + r[b]
+ *   8 EMIT a, c  constraint number c of the current gate has the value r[a]
  *   9 GATE a     end of a gate; r[a] holds its filter (compute_filter, gates/gate.rs:326-333)
+ *   12 WAIT      all column loads issued so far have arrived.  LDW / LDK are asynchronous: after
+ *                issuing one, the device waits until at most 3 loads are in flight, so a program
+ *                must not read a loaded register before 3 further loads or a WAIT have been issued
+ *                (a program that puts a WAIT after every load is always valid).
  *   0 END        end of a segment.  A program may consist of several self-contained segments
  *                (no register is live across an END); their contributions add up, and for small
  *                circuits different thread blocks evaluate different segments.

@@ -89,6 +89,9 @@ typedef struct {
                         RandomAccess: bits | num_copies << 8 | num_extra_constants << 16;
                         CosetInterpolation: subgroup_bits | degree << 8; otherwise 0 */
 } qp_gate_desc;
+/* Column loads of a compiled program are issued this many loads ahead of their first use (the
+ * device keeps that many asynchronous loads in flight; include/qp_plonky2_b200.h, op 12 WAIT). */
+#define QP_PROGRAM_LOAD_LEAD 3
 typedef struct qp_program qp_program;
 int qp_program_create(const qp_gate_desc* gates, size_t n_gates, unsigned max_degree, qp_program** out);
 void qp_program_free(qp_program* p);

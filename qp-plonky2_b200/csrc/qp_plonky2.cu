@@ -1659,7 +1659,7 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
     if (d->degree_bits + d->quotient_degree_bits > ctx->tw_lg)
         return fail(ctx, QP_ERR_TOO_LARGE, "quotient domain larger than the context's twiddle table");
     if (d->program_len && !d->program) return fail(ctx, QP_ERR_BAD_ARG, "null program");
-    if ((size_t)d->program_regs * quotient::BLOCK * 8 + d->pool_len * 8 > 190 * 1024)
+    if (d->program_regs > 256 || (size_t)d->program_regs * quotient::BLOCK * 8 + d->pool_len * 8 > 190 * 1024)
         return fail(ctx, QP_ERR_TOO_LARGE, "constraint program needs too many registers");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     qp_circuit* c = new qp_circuit();
@@ -1687,23 +1687,27 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
         CUDA_TRY(ctx, cudaMemcpyAsync(c->seg_off, seg_off.data(), seg_off.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
     for (uint64_t ins : prog) {
-        const unsigned op = ins & 0xff, dst = (ins >> 8) & 0xffff, a = (ins >> 24) & 0xffff, b = (ins >> 40) & 0xffff;
-        const bool arith = op == quotient::OP_ADD || op == quotient::OP_SUB || op == quotient::OP_MUL;
-        const bool load = op >= quotient::OP_LDW && op <= quotient::OP_LDI;
-        bool ok = op <= quotient::OP_ADDI;
-        if (arith) ok = dst < d->program_regs && a < d->program_regs && b < d->program_regs;
-        if (op == quotient::OP_MULI || op == quotient::OP_ADDI)
-            ok = dst < d->program_regs && a < d->program_regs && b < d->pool_len;
-        if (load) ok = dst < d->program_regs;
-        if (op == quotient::OP_EMIT || op == quotient::OP_GATE) ok = a < d->program_regs;
-        if (op == quotient::OP_LDW) ok = ok && a < d->num_wires;
-        if (op == quotient::OP_LDK) ok = ok && a < d->num_constants + d->num_routed_wires;
-        if (op == quotient::OP_LDI) ok = ok && a < d->pool_len;
+        const unsigned op = ins & 0xff, dst = (ins >> 8) & 0xff, a = (ins >> 16) & 0xff, b = (ins >> 24) & 0xff;
+        const uint64_t cc = ins >> 32;
+        const unsigned nr = d->program_regs;
+        bool ok = op <= quotient::OP_FMAI;
+        switch (op) {
+            case quotient::OP_ADD: case quotient::OP_SUB: case quotient::OP_MUL: ok = dst < nr && a < nr && b < nr; break;
+            case quotient::OP_FMAI: ok = dst < nr && a < nr && b < nr && cc < d->pool_len; break;
+            case quotient::OP_MULI: case quotient::OP_ADDI: ok = dst < nr && a < nr && cc < d->pool_len; break;
+            case quotient::OP_LDW: ok = dst < nr && cc < d->num_wires; break;
+            case quotient::OP_LDK: ok = dst < nr && cc < (uint64_t)d->num_constants + d->num_routed_wires; break;
+            case quotient::OP_LDP: ok = dst < nr && cc < 4; break;
+            case quotient::OP_LDI: ok = dst < nr && cc < d->pool_len; break;
+            case quotient::OP_EMIT: ok = a < nr && cc < 65536; break;
+            case quotient::OP_GATE: ok = a < nr; break;
+            default: break;
+        }
         if (!ok) {
             delete c;
             return fail(ctx, QP_ERR_BAD_ARG, "malformed constraint program");
         }
-        if (op == quotient::OP_EMIT && b > c->max_emit) c->max_emit = b;
+        if (op == quotient::OP_EMIT && cc > c->max_emit) c->max_emit = (unsigned)cc;
     }
     CUDA_TRY(ctx, cudaMemcpyAsync(c->program, prog.data(), prog.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (d->pool_len)

@@ -23,21 +23,47 @@
 
 namespace quotient {
 
-// Constraint program: 64-bit words  op | dst << 8 | a << 24 | b << 40.
+// Constraint program: 64-bit words  op | dst << 8 | a << 16 | b << 24 | c << 32  (dst, a, b:
+// registers; c: a column, a pool slot or a constraint index).
 enum : unsigned {
-    OP_END = 0,
-    OP_LDW = 1,   // dst = wire column a
-    OP_LDK = 2,   // dst = constants_sigmas column a
-    OP_LDP = 3,   // dst = public_inputs_hash[a]
-    OP_LDI = 4,   // dst = pool[a]
+    OP_END = 0,   // end of a segment
+    OP_LDW = 1,   // dst = wire column c              (asynchronous, see LOAD_LEAD)
+    OP_LDK = 2,   // dst = constants_sigmas column c  (asynchronous)
+    OP_LDP = 3,   // dst = public_inputs_hash[c]
+    OP_LDI = 4,   // dst = pool[c]
     OP_ADD = 5,
     OP_SUB = 6,
     OP_MUL = 7,
-    OP_EMIT = 8,  // constraint b of the current gate: h += alpha^b r[a]
+    OP_EMIT = 8,  // constraint c of the current gate: h += alpha^c r[a]
     OP_GATE = 9,  // end of a gate: G += r[a] (filter) * h, h = 0
-    OP_MULI = 10, // dst = r[a] * pool[b]
-    OP_ADDI = 11, // dst = r[a] + pool[b]
+    OP_MULI = 10, // dst = r[a] * pool[c]
+    OP_ADDI = 11, // dst = r[a] + pool[c]
+    OP_WAIT = 12, // every column load issued so far has arrived
+    OP_FMAI = 13, // dst = r[a] * pool[c] + r[b]
 };
+
+// LDW / LDK are asynchronous copies global -> register file (cp.async, 8 bytes per thread): issuing
+// one leaves at most LOAD_LEAD loads in flight, so the compiler (plonk_host.cpp, hoist_loads) issues
+// each load LOAD_LEAD loads ahead of its first use and HBM latency overlaps the arithmetic between.
+constexpr int LOAD_LEAD = 3;
+
+// the register file and the tables live in shared memory and are addressed with 32-bit shared
+// addresses computed once per thread (one LEA per operand in the interpreter loop)
+__device__ __forceinline__ uint64_t lds64(unsigned addr) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(unsigned addr, uint64_t v) {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void load_async(unsigned dst_shared, const uint64_t* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n"
+                 "cp.async.commit_group;\n"
+                 "cp.async.wait_group %2;\n" ::"r"(dst_shared), "l"(src), "n"(LOAD_LEAD)
+                 : "memory");
+}
+__device__ __forceinline__ void load_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 constexpr int MAX_CHALLENGES = 4;
 constexpr int BLOCK = 128;
@@ -111,6 +137,10 @@ __global__ void __launch_bounds__(BLOCK) quotient_kernel(Params p) {
         for (int a = 0; a < MAX_CHALLENGES; a++)
             if (a < (int)p.nc) res[a] = gl::add(res[a], gl::mul(term, sh_apow[a * p.apow_stride + t]));
     };
+    constexpr unsigned REG_SHIFT = 10;  // one register = BLOCK * 8 bytes
+    static_assert(BLOCK * 8 == 1 << REG_SHIFT, "register stride");
+    const unsigned r_base = (unsigned)__cvta_generic_to_shared(regs + threadIdx.x);
+    const unsigned pool_base = (unsigned)__cvta_generic_to_shared(sh_pool);
     for (unsigned unit = blockIdx.y; unit < 1 + p.n_seg; unit += gridDim.y) {
         if (unit == 0) {
             const size_t pos_next = brev((i + ((size_t)1 << p.qdb)) & (n_lde - 1), p.lg_lde);
@@ -159,42 +189,52 @@ __global__ void __launch_bounds__(BLOCK) quotient_kernel(Params p) {
             continue;
         }
         // gate constraints (vanishing_poly.rs:700-726): G = sum over gates of filter * sum_k alpha^k c_k
-        uint64_t* r = regs + threadIdx.x;
         const uint64_t* pc = p.program + p.seg_off[unit - 1];
         uint64_t next = __ldg(pc);  // the instruction stream is fetched one word ahead of its use
         for (;;) {
-            const uint64_t ins = next;
-            const unsigned op = ins & 0xff;
-            if (op == OP_END) break;
+            const unsigned lo = (unsigned)next, c = (unsigned)(next >> 32);
+            const unsigned op = lo & 0xff;
+            if (op == OP_END) break;  // (every segment ends with its loads consumed: nothing is in flight)
             next = __ldg(++pc);
-            const unsigned dst = (ins >> 8) & 0xffff, a = (ins >> 24) & 0xffff, b = (ins >> 40) & 0xffff;
-            switch (op) {
-                case OP_LDW: r[dst * BLOCK] = p.wires[a * p.wires_stride + pos]; break;
-                case OP_LDK: r[dst * BLOCK] = p.cs[a * p.cs_stride + pos]; break;
-                case OP_LDP: r[dst * BLOCK] = p.pih[a & 3]; break;
-                case OP_LDI: r[dst * BLOCK] = sh_pool[a]; break;
-                case OP_ADD: r[dst * BLOCK] = gl::add(r[a * BLOCK], r[b * BLOCK]); break;
-                case OP_SUB: r[dst * BLOCK] = gl::sub(r[a * BLOCK], r[b * BLOCK]); break;
-                case OP_MUL: r[dst * BLOCK] = gl::mul(r[a * BLOCK], r[b * BLOCK]); break;
-                case OP_MULI: r[dst * BLOCK] = gl::mul(r[a * BLOCK], sh_pool[b]); break;
-                case OP_ADDI: r[dst * BLOCK] = gl::add(r[a * BLOCK], sh_pool[b]); break;
-                case OP_EMIT: {
-                    const uint64_t v = r[a * BLOCK];
+            const unsigned rd = r_base + (((lo >> 8) & 0xff) << REG_SHIFT);
+            const unsigned ra = r_base + (((lo >> 16) & 0xff) << REG_SHIFT);
+            const unsigned rb = r_base + ((lo >> 24) << REG_SHIFT);
+            // most frequent first (MDS layers and reducing gates are chains of FMAI)
+            if (op == OP_FMAI) {
+                sts64(rd, gl::add(gl::mul(lds64(ra), lds64(pool_base + c * 8)), lds64(rb)));
+            } else if (op == OP_ADD) {
+                sts64(rd, gl::add(lds64(ra), lds64(rb)));
+            } else if (op == OP_MUL) {
+                sts64(rd, gl::mul(lds64(ra), lds64(rb)));
+            } else if (op == OP_LDW) {
+                load_async(rd, &p.wires[c * p.wires_stride + pos]);
+            } else if (op == OP_SUB) {
+                sts64(rd, gl::sub(lds64(ra), lds64(rb)));
+            } else if (op == OP_MULI) {
+                sts64(rd, gl::mul(lds64(ra), lds64(pool_base + c * 8)));
+            } else if (op == OP_EMIT) {
+                const uint64_t v = lds64(ra);
 #pragma unroll
-                    for (int c = 0; c < MAX_CHALLENGES; c++)
-                        if (c < (int)p.nc) h[c] = gl::add(h[c], gl::mul(v, sh_apow[c * p.apow_stride + b]));
-                    break;
-                }
-                case OP_GATE: {
-                    const uint64_t f = r[a * BLOCK];
+                for (int k = 0; k < MAX_CHALLENGES; k++)
+                    if (k < (int)p.nc) h[k] = gl::add(h[k], gl::mul(v, sh_apow[k * p.apow_stride + c]));
+            } else if (op == OP_ADDI) {
+                sts64(rd, gl::add(lds64(ra), lds64(pool_base + c * 8)));
+            } else if (op == OP_LDI) {
+                sts64(rd, lds64(pool_base + c * 8));
+            } else if (op == OP_LDK) {
+                load_async(rd, &p.cs[c * p.cs_stride + pos]);
+            } else if (op == OP_WAIT) {
+                load_wait_all();
+            } else if (op == OP_GATE) {
+                const uint64_t f = lds64(ra);
 #pragma unroll
-                    for (int c = 0; c < MAX_CHALLENGES; c++)
-                        if (c < (int)p.nc) {
-                            G[c] = gl::add(G[c], gl::mul(f, h[c]));
-                            h[c] = 0;
-                        }
-                    break;
-                }
+                for (int k = 0; k < MAX_CHALLENGES; k++)
+                    if (k < (int)p.nc) {
+                        G[k] = gl::add(G[k], gl::mul(f, h[k]));
+                        h[k] = 0;
+                    }
+            } else if (op == OP_LDP) {
+                sts64(rd, p.pih[c & 3]);
             }
         }
     }

@@ -31,7 +31,7 @@ namespace {
 constexpr uint64_t P = 0xFFFFFFFF00000001ULL;
 constexpr uint64_t UNUSED_SELECTOR = 0xFFFFFFFFULL;  // core/src/selectors.rs
 
-enum Op : unsigned { END = 0, LDW, LDK, LDP, LDI, ADD, SUB, MUL, EMIT, GATE, MULI, ADDI };
+enum Op : unsigned { END = 0, LDW, LDK, LDP, LDI, ADD, SUB, MUL, EMIT, GATE, MULI, ADDI, WAIT, FMAI };
 
 struct Recorder;
 
@@ -493,10 +493,16 @@ constexpr unsigned TARGET_SEGMENTS = 6;
 constexpr size_t MIN_SEGMENT_STEPS = 384;
 
 struct Step {
-    unsigned op;   // node op, or EMIT / GATE
+    unsigned op;   // node op, FMAI, or EMIT / GATE / WAIT
     int dst;       // value id defined (node steps), -1 for actions
-    int a, b;      // value ids (arith), pool slot / column (immediates, loads), constraint index (EMIT: b)
+    int a, b;      // value ids of the register operands (-1: none)
+    int c;         // column (LDW / LDK), pih index (LDP), pool slot (LDI / MULI / ADDI / FMAI), constraint (EMIT)
 };
+
+// instruction word: op | dst << 8 | a << 16 | b << 24 | c << 32   (include/qp_plonky2_b200.h)
+uint64_t word(unsigned op, unsigned dst, unsigned a, unsigned b, unsigned c) {
+    return op | ((uint64_t)dst << 8) | ((uint64_t)a << 16) | ((uint64_t)b << 24) | ((uint64_t)c << 32);
+}
 
 bool is_leaf(unsigned op) { return op >= LDW && op <= LDI; }
 bool is_unary(unsigned op) { return op == MULI || op == ADDI; }
@@ -508,14 +514,45 @@ struct Scheduler {
     std::vector<Step> steps;
     std::vector<int> val_of;      // node -> current value id (-1: not computed in this piece)
     std::vector<int> touched_at;  // node -> step index of its last use (leaves)
+    std::vector<int> uses;        // node -> number of consumers inside this piece
     int n_vals = 0;
-    explicit Scheduler(const Recorder& r) : R(r), val_of(r.nodes.size(), -1), touched_at(r.nodes.size(), -1) {}
+    Scheduler(const Recorder& r, const std::vector<Recorder::Action>& acts)
+        : R(r), val_of(r.nodes.size(), -1), touched_at(r.nodes.size(), -1), uses(r.nodes.size(), 0) {
+        std::vector<char> seen(r.nodes.size(), 0);
+        std::vector<int> stack;
+        for (const auto& a : acts) {
+            uses[a.node]++;
+            stack.push_back(a.node);
+        }
+        while (!stack.empty()) {
+            const int i = stack.back();
+            stack.pop_back();
+            if (seen[i]) continue;
+            seen[i] = 1;
+            const auto& nd = R.nodes[i];
+            if (is_leaf(nd.op)) continue;
+            uses[nd.a]++;
+            stack.push_back(nd.a);
+            if (!is_unary(nd.op)) {
+                uses[nd.b]++;
+                stack.push_back(nd.b);
+            }
+        }
+    }
+    // x * constant + y as ONE instruction when the product has no other consumer (the MDS layers
+    // and the reducing gates are chains of these): which operand of ADD node nd is that product
+    int fusable(const Recorder::Node& nd) const {
+        if (nd.op != ADD) return -1;
+        for (int m : {nd.a, nd.b})
+            if (R.nodes[m].op == MULI && uses[m] == 1 && val_of[m] < 0 && nd.a != nd.b) return m;
+        return -1;
+    }
 
     int use_leaf(int i) {  // value id of a loaded column / constant, (re)loading it if it went stale
         const auto& nd = R.nodes[i];
         if (val_of[i] < 0 || (int)steps.size() - touched_at[i] > REMAT_GAP) {
             val_of[i] = n_vals++;
-            steps.push_back({nd.op, val_of[i], nd.a, 0});
+            steps.push_back({nd.op, val_of[i], -1, -1, is_leaf(nd.op) ? nd.a : 0});
         }
         touched_at[i] = (int)steps.size();
         return val_of[i];
@@ -529,65 +566,99 @@ struct Scheduler {
             stack.pop_back();
             const auto& nd = R.nodes[i];
             if (val_of[i] >= 0) continue;
+            const int prod = fusable(nd);
+            auto want = [&](int k) {
+                if (!is_leaf(R.nodes[k].op) && val_of[k] < 0) stack.push_back({k, false});
+            };
             if (!done) {
                 stack.push_back({i, true});
-                if (!is_unary(nd.op) && !is_leaf(R.nodes[nd.b].op) && val_of[nd.b] < 0) stack.push_back({nd.b, false});
-                if (!is_leaf(R.nodes[nd.a].op) && val_of[nd.a] < 0) stack.push_back({nd.a, false});
+                if (prod >= 0) {
+                    want(prod == nd.a ? nd.b : nd.a);
+                    want(R.nodes[prod].a);
+                } else {
+                    if (!is_unary(nd.op)) want(nd.b);
+                    want(nd.a);
+                }
+                continue;
+            }
+            if (prod >= 0) {
+                const int x = operand(R.nodes[prod].a), y = operand(prod == nd.a ? nd.b : nd.a);
+                val_of[i] = n_vals++;
+                steps.push_back({FMAI, val_of[i], x, y, R.nodes[prod].b});
                 continue;
             }
             const int va = operand(nd.a);
-            const int vb = is_unary(nd.op) ? nd.b : operand(nd.b);
+            if (is_unary(nd.op)) {
+                val_of[i] = n_vals++;
+                steps.push_back({nd.op, val_of[i], va, -1, nd.b});
+                continue;
+            }
+            const int vb = operand(nd.b);
             val_of[i] = n_vals++;
-            steps.push_back({nd.op, val_of[i], va, vb});
+            steps.push_back({nd.op, val_of[i], va, vb, 0});
         }
     }
     void action(const Recorder::Action& act) {
         compute(act.node);
-        steps.push_back({act.op, -1, operand(act.node), (int)act.k});
+        steps.push_back({act.op, -1, operand(act.node), -1, (int)act.k});
     }
 };
+
+// Column loads (LDW / LDK) are asynchronous on the device (cp.async into the register file): the
+// load that sat at the position of its first use is issued QP_PROGRAM_LOAD_LEAD loads earlier, and
+// the device lets at most that many loads stay in flight after issuing one -- so a value has
+// arrived when its consumer runs, and HBM latency overlaps the arithmetic in between.  The last
+// loads of a piece have no successor to wait for them: an explicit WAIT does.
+void hoist_loads(std::vector<Step>& steps) {
+    constexpr size_t D = QP_PROGRAM_LOAD_LEAD;
+    std::vector<size_t> pos;
+    for (size_t t = 0; t < steps.size(); t++)
+        if (steps[t].op == LDW || steps[t].op == LDK) pos.push_back(t);
+    const size_t m = pos.size();
+    if (!m) return;
+    std::vector<Step> out;
+    out.reserve(steps.size() + 1);
+    for (size_t j = 0; j < std::min(D, m); j++) out.push_back(steps[pos[j]]);
+    size_t j = 0;  // next original load position
+    for (size_t t = 0; t < steps.size(); t++) {
+        if (j < m && t == pos[j]) {
+            if (j + D < m) out.push_back(steps[pos[j + D]]);
+            else if (j + D == m || (m < D && j == 0)) out.push_back({WAIT, -1, -1, -1, 0});
+            j++;
+            continue;
+        }
+        out.push_back(steps[t]);
+    }
+    steps.swap(out);
+}
 
 // registers by linear scan over one piece; appends the encoded words (+ OP_END)
 void encode(const Scheduler& S, std::vector<uint64_t>& code, uint32_t& n_regs) {
     std::vector<int> last_use(S.n_vals, -1);
     for (size_t t = 0; t < S.steps.size(); t++) {
         const Step& s = S.steps[t];
-        if (s.dst < 0) last_use[s.a] = (int)t;
-        else if (s.op == ADD || s.op == SUB || s.op == MUL) last_use[s.a] = last_use[s.b] = (int)t;
-        else if (is_unary(s.op)) last_use[s.a] = (int)t;
+        if (s.a >= 0) last_use[s.a] = (int)t;
+        if (s.b >= 0) last_use[s.b] = (int)t;
     }
     std::vector<int> reg_of(S.n_vals, -1), free_regs;
     uint32_t regs = 0;
-    auto release = [&](int v, size_t t) {
-        if (last_use[v] == (int)t) free_regs.push_back(reg_of[v]);
-    };
     for (size_t t = 0; t < S.steps.size(); t++) {
         const Step& s = S.steps[t];
-        if (s.dst < 0) {
-            code.push_back(s.op | ((uint64_t)reg_of[s.a] << 24) | ((uint64_t)(unsigned)s.b << 40));
-            release(s.a, t);
-            continue;
+        const unsigned ra = s.a >= 0 ? (unsigned)reg_of[s.a] : 0, rb = s.b >= 0 ? (unsigned)reg_of[s.b] : 0;
+        if (s.a >= 0 && last_use[s.a] == (int)t) free_regs.push_back(reg_of[s.a]);
+        if (s.b >= 0 && s.b != s.a && last_use[s.b] == (int)t) free_regs.push_back(reg_of[s.b]);
+        unsigned rd = 0;
+        if (s.dst >= 0) {
+            if (!free_regs.empty()) {
+                rd = (unsigned)free_regs.back();
+                free_regs.pop_back();
+            } else {
+                rd = regs++;
+            }
+            reg_of[s.dst] = (int)rd;
+            if (last_use[s.dst] < 0) free_regs.push_back((int)rd);  // dead value
         }
-        uint64_t ra = (uint64_t)(unsigned)s.a, rb = (uint64_t)(unsigned)s.b;
-        if (s.op == ADD || s.op == SUB || s.op == MUL) {
-            ra = reg_of[s.a];
-            rb = reg_of[s.b];
-            release(s.a, t);
-            if (s.b != s.a) release(s.b, t);
-        } else if (is_unary(s.op)) {
-            ra = reg_of[s.a];
-            release(s.a, t);
-        }
-        int r;
-        if (!free_regs.empty()) {
-            r = free_regs.back();
-            free_regs.pop_back();
-        } else {
-            r = (int)regs++;
-        }
-        reg_of[s.dst] = r;
-        code.push_back(s.op | ((uint64_t)r << 8) | (ra << 24) | (rb << 40));
-        if (last_use[s.dst] < 0) free_regs.push_back(r);  // dead value
+        code.push_back(word(s.op, rd, ra, rb, (unsigned)s.c));
     }
     code.push_back(END);
     if (regs > n_regs) n_regs = regs;
@@ -609,7 +680,7 @@ static void compile(Recorder& R, qp_program* out) {
         }
     size_t total = 0;
     for (auto& g : gates) {
-        Scheduler S(R);
+        Scheduler S(R, std::vector<Recorder::Action>(R.actions.begin() + g.first, R.actions.begin() + g.last + 1));
         for (size_t i = g.first; i <= g.last; i++) {
             S.action(R.actions[i]);
             g.cum.push_back(S.steps.size());
@@ -652,8 +723,9 @@ static void compile(Recorder& R, qp_program* out) {
     flush();
     uint32_t n_regs = 0;
     for (const auto& acts : pieces) {
-        Scheduler S(R);
+        Scheduler S(R, acts);
         for (const auto& a : acts) S.action(a);
+        hoist_loads(S.steps);
         out->segments.push_back((uint32_t)out->code.size());
         encode(S, out->code, n_regs);
     }

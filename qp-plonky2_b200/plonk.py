@@ -21,7 +21,18 @@ P = 0xFFFFFFFF00000001
 MULTIPLICATIVE_GROUP_GENERATOR = 14293326489335486720  # field/src/goldilocks_field.rs:84
 UNUSED_SELECTOR = 0xFFFFFFFF  # core/src/selectors.rs
 
-OP_END, OP_LDW, OP_LDK, OP_LDP, OP_LDI, OP_ADD, OP_SUB, OP_MUL, OP_EMIT, OP_GATE, OP_MULI, OP_ADDI = range(12)
+OP_END, OP_LDW, OP_LDK, OP_LDP, OP_LDI, OP_ADD, OP_SUB, OP_MUL, OP_EMIT, OP_GATE, OP_MULI, OP_ADDI, OP_WAIT, OP_FMAI = range(14)
+
+
+def encode_word(op, dst=0, a=0, b=0, c=0):
+    """op | dst << 8 | a << 16 | b << 24 | c << 32 (include/qp_plonky2_b200.h)."""
+    assert dst < 256 and a < 256 and b < 256
+    return op | (dst << 8) | (a << 16) | (b << 24) | (c << 32)
+
+
+def decode_word(ins):
+    ins = int(ins)
+    return ins & 0xFF, (ins >> 8) & 0xFF, (ins >> 16) & 0xFF, (ins >> 24) & 0xFF, ins >> 32
 
 
 # ---- recording value type ------------------------------------------------------------------------
@@ -151,33 +162,37 @@ class ConstraintProgram:
             if s[0] == "node":
                 i = s[1]
                 nop, a, b = nodes[i]
-                ra = rb = 0
+                ra = rb = rc = 0
                 if nop in (OP_ADD, OP_SUB, OP_MUL):
                     ra, rb = reg_of[a], reg_of[b]
                     for ch in {a, b}:
                         if last_use.get(ch) == t:
                             free.append(reg_of[ch])
                 elif nop in (OP_MULI, OP_ADDI):
-                    ra, rb = reg_of[a], b
+                    ra, rc = reg_of[a], b
                     if last_use.get(a) == t:
                         free.append(reg_of[a])
                 else:
-                    ra = a
+                    rc = a
                 if free:
                     r = free.pop()
                 else:
                     r = n_regs
                     n_regs += 1
                 reg_of[i] = r
-                code.append(nop | (r << 8) | (ra << 24) | (rb << 40))
+                code.append(encode_word(nop, r, ra, rb, rc))
+                if nop in (OP_LDW, OP_LDK):
+                    # column loads are asynchronous on the device; this mirror does not overlap
+                    # them (the native compiler hoists them three loads ahead): wait at once
+                    code.append(OP_WAIT)
                 if i not in last_use:  # dead value
                     free.append(r)
             else:
                 _, op, root, k = s
-                code.append(op | (reg_of[root] << 24) | (k << 40))
+                code.append(encode_word(op, 0, reg_of[root], 0, k))
                 if last_use.get(root) == t:
                     free.append(reg_of[root])
-        assert n_regs < (1 << 16) and len(self.pool) < (1 << 16)
+        assert n_regs <= 256
         return (np.array(code, dtype=np.uint64), np.array(self.pool or [0], dtype=np.uint64), max(n_regs, 1))
 
 

@@ -20,20 +20,34 @@ def run_program(code, pool, n_regs, wires, consts, pih, alphas):
     r = [0] * n_regs
     nc = len(alphas)
     G, h = [0] * nc, [0] * nc
+    in_flight = []   # asynchronous column loads: (register, value); at most 3 stay in flight after an issue
+
+    def load(dst, v):
+        r[dst] = None              # unreadable until it lands
+        in_flight.append((dst, v))
+        while len(in_flight) > 3:
+            d, x = in_flight.pop(0)
+            assert r[d] is None, "register overwritten while its load was in flight"
+            r[d] = x
+
     for ins in code:
-        ins = int(ins)
-        op, dst, a, b = ins & 0xFF, (ins >> 8) & 0xFFFF, (ins >> 24) & 0xFFFF, (ins >> 40) & 0xFFFF
+        op, dst, a, b, c = plonk.decode_word(ins)
         if op == plonk.OP_END:     # segments are self-contained: no register survives an END
+            assert not in_flight and h == [0] * nc
             r = [None] * n_regs
-            assert h == [0] * nc
+        elif op == plonk.OP_WAIT:
+            for d, x in in_flight:
+                assert r[d] is None
+                r[d] = x
+            in_flight.clear()
         elif op == plonk.OP_LDW:
-            r[dst] = int(wires[a])
+            load(dst, int(wires[c]))
         elif op == plonk.OP_LDK:
-            r[dst] = int(consts[a])
+            load(dst, int(consts[c]))
         elif op == plonk.OP_LDP:
-            r[dst] = int(pih[a])
+            r[dst] = int(pih[c])
         elif op == plonk.OP_LDI:
-            r[dst] = int(pool[a])
+            r[dst] = int(pool[c])
         elif op == plonk.OP_ADD:
             r[dst] = (r[a] + r[b]) % P
         elif op == plonk.OP_SUB:
@@ -41,13 +55,15 @@ def run_program(code, pool, n_regs, wires, consts, pih, alphas):
         elif op == plonk.OP_MUL:
             r[dst] = r[a] * r[b] % P
         elif op == plonk.OP_MULI:
-            r[dst] = r[a] * int(pool[b]) % P
+            r[dst] = r[a] * int(pool[c]) % P
         elif op == plonk.OP_ADDI:
-            r[dst] = (r[a] + int(pool[b])) % P
-        elif op == plonk.OP_EMIT:   # constraint index in b
-            h = [(h[c] + r[a] * pow(int(alphas[c]), b, P)) % P for c in range(nc)]
+            r[dst] = (r[a] + int(pool[c])) % P
+        elif op == plonk.OP_FMAI:
+            r[dst] = (r[a] * int(pool[c]) + r[b]) % P
+        elif op == plonk.OP_EMIT:   # constraint index in c
+            h = [(h[k] + r[a] * pow(int(alphas[k]), c, P)) % P for k in range(nc)]
         elif op == plonk.OP_GATE:
-            G = [(G[c] + r[a] * h[c]) % P for c in range(nc)]
+            G = [(G[k] + r[a] * h[k]) % P for k in range(nc)]
             h = [0] * nc
     return G
 
