@@ -358,6 +358,7 @@ def run_ours(args):
 
 
 def main():
+    global COLS, METRIC
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -369,7 +370,6 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-prove", action="store_true")
     args = ap.parse_args()
-    global COLS, METRIC
     COLS = args.cols
     METRIC = "commit_ms_2^%dx%d_rate%d" % (args.rows_log, COLS, RATE_BITS)
     if args.impl == "reference":
