@@ -157,6 +157,83 @@ tree_level_kernel(TreeShape sh, unsigned layer, uint64_t* __restrict__ digests,
     store_digest(out, s);
 }
 
+// ---- the upper levels: one permutation per 16 lanes ----------------------------------------------
+// A level with fewer nodes than the GPU has threads costs the LATENCY of one per-thread permutation
+// (16 k dependent-ish instructions, ~28 us on B200) whatever its size, and a 2^15-leaf tree -- the
+// size recursion proofs commit to -- has eleven such levels.  Here lane l of a 16-lane group holds
+// state element l (lanes 12..15 idle): the S-box is one x^7 per lane, the MDS layer eleven shuffles
+// and 24 small multiply-adds per lane (the matrix is circulant: out_l = sum_i C_i s_{(l+i) mod 12},
+// + 8 s_0 in lane 0; core/src/poseidon.rs:178-198), about 3.8 k instructions per permutation on the
+// critical path instead of 16 k -- the reference's poseidon_naive round structure
+// (core/src/poseidon.rs:613-633), which the KATs pin to the same function.  It does several times the
+// total work of the per-thread kernel, so it is used only where that one is latency-bound: measured
+// on B200 (tools/bench_tree_top.py, profiles/r01r_tree_top_threshold.txt) the crossover is at about
+// 2^11 nodes per level (MerkleTree::new on 2^15 short leaves: 333 -> 224 us; 2^11 leaves: 223 -> 133 us).
+// One block = 16 groups = 16 adjacent nodes of `layer`; it then walks up to `up` further levels
+// (8, 4, 2, 1 nodes) inside the block, a barrier between levels.
+constexpr int TOP_BLOCK = 256, TOP_GROUPS = TOP_BLOCK / 16, TOP_MAX_UP = 4;
+
+__device__ __forceinline__ uint64_t shfl16(uint64_t v, int src) {
+    uint32_t lo, hi;
+    gl::unpack(v, lo, hi);
+    lo = __shfl_sync(0xffffffffu, lo, src, 16);
+    hi = __shfl_sync(0xffffffffu, hi, src, 16);
+    return gl::pack(lo, hi);
+}
+
+// lane l's element of the permuted state; `rc` = ALL_ROUND_CONSTANTS in shared memory
+__device__ __forceinline__ uint64_t permute_lanes(uint64_t s, int l, const uint64_t* __restrict__ rc) {
+    constexpr uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};  // poseidon_goldilocks.rs:24
+    const int lm = l < 12 ? l : 0;
+#pragma unroll 1
+    for (int r = 0; r < poseidon::N_ROUNDS; r++) {
+        const uint64_t t = gl::add(s, rc[12 * r + lm]);              // constant_layer
+        const bool full = r < 4 || r >= 26;
+        s = (full || l == 0) ? gl::pow7(t) : t;                      // sbox_layer / sbox on lane 0
+        uint32_t x0, x1;
+        gl::unpack(s, x0, x1);
+        uint64_t lo = l == 0 ? (uint64_t)x0 * 8 : 0, hi = l == 0 ? (uint64_t)x1 * 8 : 0;  // MDS_MATRIX_DIAG
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            const int src = lm + i < 12 ? lm + i : lm + i - 12;
+            const uint32_t y0 = __shfl_sync(0xffffffffu, x0, src, 16), y1 = __shfl_sync(0xffffffffu, x1, src, 16);
+            lo += (uint64_t)y0 * C[i];
+            hi += (uint64_t)y1 * C[i];
+        }
+        uint32_t w0, w1, v0, v1;
+        gl::unpack(lo, w0, w1);
+        gl::unpack(hi, v0, v1);
+        s = gl::fold3(w0, w1, v0, v1);                               // lo + hi 2^32 mod p
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(TOP_BLOCK)
+tree_top_kernel(TreeShape sh, unsigned layer, unsigned up, uint64_t* __restrict__ digests,
+                uint64_t* __restrict__ cap) {
+    __shared__ uint64_t rc[12 * poseidon::N_ROUNDS];
+    for (int i = threadIdx.x; i < 12 * poseidon::N_ROUNDS; i += TOP_BLOCK) rc[i] = poseidon::c_rc[i];
+    __syncthreads();
+    const unsigned nl = sh.num_layers();
+    const int l = threadIdx.x & 15, g = threadIdx.x >> 4;
+    for (unsigned j = 0; j <= up; j++) {
+        const unsigned ly = layer + j;
+        const size_t per_sub = (size_t)1 << (nl - ly);
+        const size_t idx = (((size_t)blockIdx.x * TOP_GROUPS) >> j) + g;
+        const bool active = g < (TOP_GROUPS >> j) && idx < (per_sub << sh.cap_height);
+        const size_t t = idx >> (nl - ly), k = idx & (per_sub - 1);
+        // children = the sibling pair k of ly-1: eight adjacent words, left digest first
+        uint64_t s = 0;
+        if (active && l < 8) s = digests[4 * digest_slot(sh, ly - 1, t, 2 * k) + l];
+        s = permute_lanes(s, l, rc);
+        if (active && l < 4) {
+            uint64_t* out = (ly == nl) ? cap + 4 * t : digests + 4 * digest_slot(sh, ly, t, k);
+            out[l] = gl::canon(s);
+        }
+        __syncthreads();  // the next level of this block reads what this one wrote
+    }
+}
+
 // Merkle opening: siblings bottom-up (merkle_tree.rs:121-160).  One thread per (query, layer).
 __global__ void merkle_paths_kernel(TreeShape sh, const uint64_t* __restrict__ digests,
                                     const uint64_t* __restrict__ leaf_indices, unsigned n_queries,

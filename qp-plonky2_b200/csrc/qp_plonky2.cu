@@ -499,10 +499,30 @@ static int hash_leaves(qp_ctx* ctx, Layout lay, unsigned leaf_len, TreeBuf* t, u
     return QP_OK;
 }
 
+// levels with at most this many nodes go to the 16-lanes-per-permutation kernel (merkle.cuh);
+// the environment variable is for measurements (tools/bench_tree_top.py)
+#ifndef QP_TREE_TOP_NODES
+#define QP_TREE_TOP_NODES 2048
+#endif
+static size_t tree_top_nodes() {
+    static const size_t v = [] {
+        const char* e = getenv("QP_TREE_TOP_NODES");
+        return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)QP_TREE_TOP_NODES;
+    }();
+    return v;
+}
 static int build_tree_levels(qp_ctx* ctx, TreeBuf* t) {
     const unsigned nl = t->shape.num_layers();
     for (unsigned layer = 1; layer <= nl; layer++) {
         const size_t nodes = (size_t)1 << (t->shape.lg_leaves - layer);
+        if (nodes <= tree_top_nodes()) {
+            // latency-bound levels: 16 lanes per permutation, up to five levels per launch
+            const unsigned up = std::min<unsigned>(merkle::TOP_MAX_UP, nl - layer);
+            LAUNCH(ctx, merkle::tree_top_kernel, cdiv(nodes, (size_t)merkle::TOP_GROUPS), merkle::TOP_BLOCK, 0, t->shape,
+                   layer, up, t->digests, t->cap);
+            layer += up;
+            continue;
+        }
         LAUNCH(ctx, merkle::tree_level_kernel, cdiv(nodes, 128), 128, 0, t->shape, layer, t->digests, t->cap);
     }
     return QP_OK;
