@@ -74,11 +74,17 @@ __global__ void fold_kernel(const uint64_t* __restrict__ in, size_t n_in, unsign
 }
 
 // Proof-of-work search (plonky2/src/fri/prover.rs:185-200).  Candidate w = base + global thread
-// id; `found` holds the smallest successful candidate of this launch (init UINT64_MAX).
+// id; `found` holds the smallest successful candidate so far (init UINT64_MAX).  A launch covers
+// far more candidates than the expected 2^min_lz, and a block whose candidates are all larger than
+// a witness already found returns at once: the search costs the waves it needs, not a host round
+// trip per batch.  (A block is only skipped when a SMALLER candidate succeeded, so the minimum --
+// the serial `find` rule -- is kept whatever order the blocks run in.)
 __global__ void __launch_bounds__(128)
 pow_kernel(const uint64_t* __restrict__ state12, unsigned witness_pos, unsigned min_lz,
            uint64_t base, unsigned long long* found) {
-    const uint64_t w = base + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t block_base = base + (uint64_t)blockIdx.x * blockDim.x;
+    if (*(volatile unsigned long long*)found < block_base) return;
+    const uint64_t w = block_base + threadIdx.x;
     if (w >= gl::P) return;
     uint64_t s[12];
 #pragma unroll

@@ -1624,8 +1624,9 @@ extern "C" int qp_fri_proof_of_work(qp_ctx* ctx, const uint64_t state12[12], uns
     CUDA_TRY(ctx, cudaMemcpyAsync(d_state, state12, 96, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(d_found, 0xff, 8, ctx->stream));
     // Batches in increasing candidate order; the first batch with a hit contains the global
-    // minimum.  Batch size grows with the expected work 2^min_leading_zeros.
-    uint64_t batch = (uint64_t)1 << 16;
+    // minimum.  A batch is 64 times the expected work 2^min_leading_zeros (at least 2^20): the
+    // kernel's blocks stop once a smaller witness exists, so a large batch costs nothing extra.
+    uint64_t batch = (uint64_t)1 << (min_leading_zeros + 6 < 20 ? 20 : (min_leading_zeros + 6 > 26 ? 26 : min_leading_zeros + 6));
     uint64_t base = 0;
     uint64_t found = UINT64_MAX;
     while (true) {

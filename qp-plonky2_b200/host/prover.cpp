@@ -4,6 +4,8 @@
 // transcript (serial, host: core/src/challenger.rs) and lays out the proof bytes
 // (write_proof_with_public_inputs, plonky2/src/util/serialization/mod.rs:2040-2079).
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -266,7 +268,11 @@ extern "C" int qp_prove(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* consta
     const Ext shift1 = w;
     qp_opening_batch ob[2] = {{{zeta.a, zeta.b}, t0.data(), t0.size(), {shift0.a, shift0.b}},
                               {{zeta_next.a, zeta_next.b}, t1.data(), t1.size(), {shift1.a, shift1.b}}};
+    const auto t_open = std::chrono::steady_clock::now();
     QP_STEP(qp_fri_begin_from_openings(ctx, ob, 2, d.degree_bits, cfg->rate_bits, cfg->cap_height, &fri));
+    if (getenv("QP_TRACE"))
+        fprintf(stderr, "[qp_prove] %-30s %8.1f us\n", "fri_begin_from_openings",
+                std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_open).count());
     const size_t at = bytes.size();
     bytes.resize(at + fri_len);
     size_t got = 0;

@@ -2,6 +2,9 @@
 // polynomial / hashing work of the commit path is done by the device entry points it calls.
 #include "../../include/qp_plonky2_host.h"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -148,19 +151,31 @@ extern "C" int qp_fri_proof(qp_ctx* ctx, const qp_batch* const* oracles, size_t 
                             size_t capacity, size_t* len_out) {
     if (!ctx || !f || !ch || !len_out || (n_oracles && !oracles) || (n_rounds && !arity_bits)) return QP_ERR_BAD_ARG;
     const size_t cap_words = ((size_t)1 << cap_height) * 4;
+    // QP_TRACE=1: wall-clock of the stages on stderr (every stage ends synchronised)
+    static const bool trace = getenv("QP_TRACE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[qp_fri_proof] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(now - t_prev).count());
+        t_prev = now;
+    };
     // commit phase (prover.rs:38-49)
     std::vector<uint64_t> caps(cap_words * (n_rounds ? n_rounds : 1));
     size_t final_len = 0;
     int rc = qp_fri_run_commit_phase(f, cap_height, arity_bits, n_rounds, ch, caps.data(), nullptr, &final_len);
     if (rc) return rc;
     std::vector<uint64_t> final_poly(2 * (final_len ? final_len : 1));
+    lap("commit phase");
     rc = qp_fri_final_poly(f, final_poly.data(), &final_len);
     if (rc) return rc;
+    lap("final poly");
     // observe_final_poly (prover.rs:145-157), then grinding (prover.rs:159-208)
     qp_challenger_observe(ch, final_poly.data(), 2 * final_len);
     uint64_t pow_witness = 0;
     rc = qp_fri_grind(ctx, ch, pow_bits, &pow_witness);
     if (rc) return rc;
+    lap("proof of work");
     // query indices (prover.rs:221-226): challenge mod lde size
     unsigned lde_bits = 0;
     {
@@ -185,6 +200,7 @@ extern "C" int qp_fri_proof(qp_ctx* ctx, const qp_batch* const* oracles, size_t 
         rc = qp_batch_get_leaves(oracles[t], x.data(), num_queries, o_rows[t].data());
         if (!rc) rc = qp_batch_prove_many(oracles[t], x.data(), num_queries, o_paths[t].data());
     }
+    lap("oracle openings");
     std::vector<std::vector<uint64_t>> r_rows(n_rounds), r_paths(n_rounds);
     std::vector<unsigned> r_layers(n_rounds);
     {
@@ -200,6 +216,7 @@ extern "C" int qp_fri_proof(qp_ctx* ctx, const qp_batch* const* oracles, size_t 
         }
     }
     if (rc) return rc;
+    lap("commit-phase tree openings");
 
     ByteSink w{out, capacity};
     for (unsigned i = 0; i < n_rounds; i++) w.u64s(caps.data() + i * cap_words, cap_words);  // write_merkle_cap
