@@ -1686,6 +1686,13 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
     qp_circuit* c = new qp_circuit();
     c->ctx = ctx;
     c->d = *d;
+    c->d.k_is = c->d.sigmas = c->d.program = c->d.pool = nullptr;  // the caller's host pointers die with the call
+    struct Guard {  // every early return below releases what has been allocated so far
+        qp_circuit* c;
+        ~Guard() {
+            if (c) qp_circuit_free(c);
+        }
+    } guard{c};
     const size_t n = (size_t)1 << d->degree_bits;
     int rc = dev_alloc(ctx, &c->k_is, d->num_routed_wires);
     if (!rc) rc = dev_alloc(ctx, &c->program, d->program_len + 1);
@@ -1724,10 +1731,7 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
             case quotient::OP_GATE: ok = a < nr; break;
             default: break;
         }
-        if (!ok) {
-            delete c;
-            return fail(ctx, QP_ERR_BAD_ARG, "malformed constraint program");
-        }
+        if (!ok) return fail(ctx, QP_ERR_BAD_ARG, "malformed constraint program");
         if (op == quotient::OP_EMIT && cc > c->max_emit) c->max_emit = (unsigned)cc;
     }
     CUDA_TRY(ctx, cudaMemcpyAsync(c->program, prog.data(), prog.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -1761,6 +1765,7 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
     if (rc) return rc;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     c->d.k_is = c->d.sigmas = c->d.program = c->d.pool = nullptr;
+    guard.c = nullptr;
     *out = c;
     return QP_OK;
 }
