@@ -136,6 +136,26 @@ size_t qp_tree_digests_len(const qp_tree* t);
 int qp_tree_prove(const qp_tree* t, size_t leaf_index, uint64_t* siblings_out);
 int qp_tree_get(const qp_tree* t, size_t leaf_index, uint64_t* out); /* MerkleTree::get */
 
+/* ---- BatchMerkleTree::new (plonky2/src/hash/batch_merkle_tree.rs:40-130) ---------------------
+ * One tree over several matrices of strictly decreasing power-of-two heights (the oracle of
+ * batch FRI): the tree over the tallest matrix is capped at the height of the next one, whose rows
+ * are hashed together with those cap entries (hash_leaf(digest || row)), and so on down to
+ * `cap_height`.  matrices[i]: row-major [heights[i]][widths[i]].  Errors are the reference's
+ * asserts: QP_ERR_BAD_ARG (empty / heights not strictly decreasing), QP_ERR_NOT_POW2,
+ * QP_ERR_CAP_HEIGHT (cap_height > log2 of the last height). */
+typedef struct qp_batch_tree qp_batch_tree;
+int qp_batch_merkle_tree_new(qp_ctx* ctx, const uint64_t* const* matrices, int space, const size_t* heights,
+                             const size_t* widths, size_t n_matrices, unsigned cap_height, qp_batch_tree** out);
+void qp_batch_tree_free(qp_batch_tree* t);
+int qp_batch_tree_cap(const qp_batch_tree* t, uint64_t* out, int space);        /* [2^cap_height][4] */
+size_t qp_batch_tree_digests_len(const qp_batch_tree* t);                       /* 2 (heights[0] - 2^cap_height) */
+int qp_batch_tree_digests(const qp_batch_tree* t, uint64_t* out, int space);    /* the stages' digests, concatenated */
+/* open_batch (batch_merkle_tree.rs:133-153): log2(heights[0]) - cap_height siblings, 4 words each */
+int qp_batch_tree_open(const qp_batch_tree* t, size_t leaf_index, uint64_t* siblings_out);
+/* values (batch_merkle_tree.rs:155-164): row leaf_index >> (log2 heights[0] - log2 heights[i]) of every
+ * matrix, concatenated (sum of widths words) */
+int qp_batch_tree_values(const qp_batch_tree* t, size_t leaf_index, uint64_t* out);
+
 /* ---- Poseidon primitives (core/src/poseidon.rs:599-609, hashing.rs) ------------------------- */
 /* Batch of width-12 permutations, states [count][12] (in place). */
 int qp_poseidon_permute(qp_ctx* ctx, uint64_t* states, int space, size_t count);

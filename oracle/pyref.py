@@ -192,6 +192,51 @@ def merkle_verify(leaf, i, cap, siblings):
     return cur == list(cap[i])
 
 
+# ----- BatchMerkleTree (plonky2/src/hash/batch_merkle_tree.rs) -----------------------------
+def batch_merkle_tree(matrices, cap_height):
+    """BatchMerkleTree::new (batch_merkle_tree.rs:40-130): matrices of strictly decreasing power-of-two
+    heights; the tree over the tallest one is capped at the height of the next, whose rows are then
+    hashed together with those cap entries (hash_leaf of digest || row), and so on down to the cap.
+    -> (digests, cap, leaf_heights)"""
+    assert matrices and all(len(m) & (len(m) - 1) == 0 for m in matrices)
+    assert all(len(a) > len(b) for a, b in zip(matrices, matrices[1:]))
+    assert cap_height <= len(matrices[-1]).bit_length() - 1
+    heights = [len(m) for m in matrices] + [1 << cap_height]
+    digests, cap = [], None
+    for j, m in enumerate(matrices):
+        rows = [list(r) for r in m] if j == 0 else [list(cap[i]) + list(m[i]) for i in range(len(m))]
+        d, cap = merkle_tree(rows, heights[j + 1].bit_length() - 1)
+        digests += d
+    return digests, cap, [h.bit_length() - 1 for h in heights[:-1]]
+
+
+def batch_merkle_open(i, matrices, cap_height, digests):
+    """open_batch (batch_merkle_tree.rs:133-153)"""
+    heights = [len(m) for m in matrices] + [1 << cap_height]
+    lg0 = heights[0].bit_length() - 1
+    out, pos = [], 0
+    for j in range(len(matrices)):
+        cur, nxt = heights[j], heights[j + 1]
+        nd = 2 * (cur - nxt)
+        out += merkle_prove(i >> (lg0 - (cur.bit_length() - 1)), cur, nxt.bit_length() - 1, digests[pos:pos + nd])
+        pos += nd
+    return out
+
+
+def batch_merkle_verify(leaf_data, leaf_heights, i, cap, siblings):
+    """verify_batch_merkle_proof_to_cap (core/src/merkle_proofs.rs:59-97)"""
+    cur = hash_leaf(leaf_data[0])
+    height, nxt = leaf_heights[0], 1
+    for s in siblings:
+        cur = two_to_one(s, cur) if i & 1 else two_to_one(cur, s)
+        i >>= 1
+        height -= 1
+        if nxt < len(leaf_heights) and height == leaf_heights[nxt]:
+            cur = hash_leaf(list(cur) + list(leaf_data[nxt]))
+            nxt += 1
+    return nxt == len(leaf_data) and cur == list(cap[i])
+
+
 # ----- PolynomialBatch (plonky2/src/fri/oracle.rs:168-223) ---------------------------------
 def batch_from_values(cols, rate_bits, cap_height, salt=None):
     coeffs = [ifft(c) for c in cols]

@@ -185,6 +185,13 @@ def lib():
         "qp_circuit_describe": (i32, [vp, vp]),
         "qp_circuit_has_sigmas": (i32, [vp]),
         "qp_dev_alloc": (i32, [vp, sz, pp]),
+        "qp_batch_merkle_tree_new": (i32, [vp, vp, i32, vp, vp, sz, u32, pp]),
+        "qp_batch_tree_free": (None, [vp]),
+        "qp_batch_tree_cap": (i32, [vp, vp, i32]),
+        "qp_batch_tree_digests_len": (sz, [vp]),
+        "qp_batch_tree_digests": (i32, [vp, vp, i32]),
+        "qp_batch_tree_open": (i32, [vp, sz, vp]),
+        "qp_batch_tree_values": (i32, [vp, sz, vp]),
         "qp_dev_free": (None, [vp, vp]),
         "qp_memcpy": (i32, [vp, vp, i32, vp, i32, sz]),
         # host side of the quotient / prove (include/qp_plonky2_host.h)
@@ -536,6 +543,62 @@ class MerkleTree:
     def free(self):
         if self._h and self.ctx._h:
             lib().qp_tree_free(self._h)
+        self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class BatchMerkleTree:
+    """plonky2/src/hash/batch_merkle_tree.rs: `leaves` = matrices (2-D arrays, row-major) of strictly
+    decreasing power-of-two heights; same fields and methods as the reference (`cap`, `digests`,
+    `leaf_heights`, `open_batch`, `values`)."""
+
+    def __init__(self, ctx, leaves, cap_height):
+        self._h = C.c_void_p()
+        self.ctx, self.cap_height = ctx, cap_height
+        mats = [np.ascontiguousarray(np.asarray(m, dtype=np.uint64).reshape(len(m), -1)) for m in leaves]
+        if not mats:
+            raise QpError(1, "no leaves")
+        self.heights = [m.shape[0] for m in mats]
+        self.widths = [m.shape[1] for m in mats]
+        self.leaf_heights = [h.bit_length() - 1 for h in self.heights]
+        n = len(mats)
+        ptrs = (C.c_void_p * n)(*[m.ctypes.data for m in mats])
+        hs = (C.c_size_t * n)(*self.heights)
+        ws = (C.c_size_t * n)(*self.widths)
+        ctx.check(lib().qp_batch_merkle_tree_new(ctx._h, ptrs, QP_HOST, hs, ws, n, cap_height, C.byref(self._h)))
+
+    @property
+    def cap(self):
+        out = np.zeros((1 << self.cap_height, 4), dtype=np.uint64)
+        self.ctx.check(lib().qp_batch_tree_cap(self._h, _np_ptr(out), QP_HOST))
+        return out
+
+    @property
+    def digests(self):
+        out = np.zeros((lib().qp_batch_tree_digests_len(self._h), 4), dtype=np.uint64)
+        if out.size:
+            self.ctx.check(lib().qp_batch_tree_digests(self._h, _np_ptr(out), QP_HOST))
+        return out
+
+    def open_batch(self, leaf_index):
+        k = self.leaf_heights[0] - self.cap_height
+        out = np.zeros((k, 4), dtype=np.uint64)
+        self.ctx.check(lib().qp_batch_tree_open(self._h, leaf_index, _np_ptr(out) if k else None))
+        return out
+
+    def values(self, leaf_index):
+        out = np.zeros(sum(self.widths), dtype=np.uint64)
+        self.ctx.check(lib().qp_batch_tree_values(self._h, leaf_index, _np_ptr(out) if out.size else None))
+        return np.split(out, np.cumsum(self.widths)[:-1])
+
+    def free(self):
+        if self._h and self.ctx._h:
+            lib().qp_batch_tree_free(self._h)
         self._h = C.c_void_p()
 
     def __del__(self):

@@ -250,6 +250,17 @@ __global__ void merkle_paths_kernel(TreeShape sh, const uint64_t* __restrict__ d
     for (int e = 0; e < 4; e++) dst[e] = srcp[e];
 }
 
+// BatchMerkleTree stage leaves: out[i] = cap[i] (4 words) || rows[i] (width words)
+// (batch_merkle_tree.rs:91-100).
+__global__ void concat_cap_rows_kernel(const uint64_t* __restrict__ cap, const uint64_t* __restrict__ rows,
+                                       size_t n_rows, size_t width, uint64_t* __restrict__ out) {
+    const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t w4 = width + 4;
+    if (id >= n_rows * w4) return;
+    const size_t i = id / w4, c = id % w4;
+    out[id] = c < 4 ? cap[4 * i + c] : rows[i * width + (c - 4)];
+}
+
 // Gather whole leaves (rows): out[q][c] = element c of leaf idx[q] (canonical).
 template <class Layout>
 __global__ void gather_rows_kernel(Layout lay, unsigned leaf_len,

@@ -1649,6 +1649,145 @@ extern "C" int qp_fri_proof_of_work(qp_ctx* ctx, const uint64_t state12[12], uns
 }
 
 // ---------------------------------------------------------------------------------------------
+// BatchMerkleTree::new (plonky2/src/hash/batch_merkle_tree.rs): a chain of trees, each capped at
+// the height of the next matrix
+// ---------------------------------------------------------------------------------------------
+struct qp_batch_tree {
+    qp_ctx* ctx = nullptr;
+    std::vector<uint64_t*> rows;     // the caller's matrices on the device, row-major
+    std::vector<size_t> heights, widths;
+    std::vector<TreeBuf> stages;     // stage j: leaves = matrix j (|| cap of stage j-1), cap at height j+1
+    uint64_t* scratch = nullptr;     // a stage's concatenated leaves while it is being built
+    unsigned cap_height = 0;
+};
+
+extern "C" void qp_batch_tree_free(qp_batch_tree* t) {
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    for (uint64_t* p : t->rows) dev_free(t->ctx, p);
+    dev_free(t->ctx, t->scratch);
+    for (TreeBuf& s : t->stages) {
+        dev_free(t->ctx, s.digests);
+        dev_free(t->ctx, s.cap);
+    }
+    delete t;
+}
+
+static int batch_tree_build(qp_ctx* ctx, qp_batch_tree* t, const uint64_t* const* matrices, int space) {
+    const size_t n_matrices = t->heights.size();
+    for (size_t j = 0; j < n_matrices; j++) {
+        const size_t h = t->heights[j], w = t->widths[j];
+        int rc = dev_alloc(ctx, &t->rows[j], h * w ? h * w : 1);
+        if (rc) return rc;
+        if (h * w)
+            CUDA_TRY(ctx, cudaMemcpyAsync(t->rows[j], matrices[j], h * w * 8,
+                                          space == QP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                          ctx->stream));
+        TreeBuf& st = t->stages[j];
+        st.shape.lg_leaves = ilog2(h);
+        st.shape.cap_height = j + 1 < n_matrices ? ilog2(t->heights[j + 1]) : t->cap_height;
+        if (j == 0) {
+            merkle::AffineLayout lay{t->rows[0], 1, w};
+            rc = build_tree(ctx, lay, (unsigned)w, &st);
+            if (rc) return rc;
+            continue;
+        }
+        // new_leaves[i] = cap_hash[i] || cur[i], batch_merkle_tree.rs:91-100
+        rc = dev_alloc(ctx, &t->scratch, h * (w + 4));
+        if (rc) return rc;
+        LAUNCH(ctx, merkle::concat_cap_rows_kernel, cdiv(h * (w + 4), 256), 256, 0, t->stages[j - 1].cap, t->rows[j], h, w,
+               t->scratch);
+        merkle::AffineLayout lay{t->scratch, 1, w + 4};
+        rc = build_tree(ctx, lay, (unsigned)(w + 4), &st);
+        if (rc) return rc;
+        dev_free(ctx, t->scratch);  // stream-ordered: released after the kernels above
+        t->scratch = nullptr;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return QP_OK;
+}
+
+extern "C" int qp_batch_merkle_tree_new(qp_ctx* ctx, const uint64_t* const* matrices, int space, const size_t* heights,
+                                        const size_t* widths, size_t n_matrices, unsigned cap_height,
+                                        qp_batch_tree** out) {
+    if (!ctx) return QP_ERR_BAD_ARG;
+    if (!out) return fail(ctx, QP_ERR_BAD_ARG, "null out");
+    *out = nullptr;
+    if (!n_matrices || !matrices || !heights || !widths) return fail(ctx, QP_ERR_BAD_ARG, "no leaves");
+    for (size_t j = 0; j < n_matrices; j++) {
+        if (!is_pow2(heights[j])) return fail(ctx, QP_ERR_NOT_POW2, "Not a power of two");
+        if (j && heights[j - 1] <= heights[j])
+            return fail(ctx, QP_ERR_BAD_ARG, "leaves must be sorted by height, tallest first, no duplicates");
+        if (!matrices[j] && widths[j]) return fail(ctx, QP_ERR_BAD_ARG, "null matrix");
+    }
+    if (cap_height > ilog2(heights[n_matrices - 1]))
+        return fail(ctx, QP_ERR_CAP_HEIGHT, "cap_height should be at most last_leaves_cap_height");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    qp_batch_tree* t = new qp_batch_tree();
+    t->ctx = ctx;
+    t->cap_height = cap_height;
+    t->heights.assign(heights, heights + n_matrices);
+    t->widths.assign(widths, widths + n_matrices);
+    t->rows.assign(n_matrices, nullptr);
+    t->stages.assign(n_matrices, TreeBuf{});
+    const int rc = batch_tree_build(ctx, t, matrices, space);
+    if (rc) {
+        qp_batch_tree_free(t);
+        return rc;
+    }
+    *out = t;
+    return QP_OK;
+}
+
+extern "C" int qp_batch_tree_cap(const qp_batch_tree* t, uint64_t* out, int space) {
+    if (!t) return QP_ERR_BAD_ARG;
+    return copy_out(t->ctx, out, space, t->stages.back().cap, t->stages.back().n_cap() * 4);
+}
+extern "C" size_t qp_batch_tree_digests_len(const qp_batch_tree* t) {
+    size_t n = 0;
+    if (t)
+        for (const TreeBuf& s : t->stages) n += s.n_digests();
+    return n;
+}
+extern "C" int qp_batch_tree_digests(const qp_batch_tree* t, uint64_t* out, int space) {
+    if (!t) return QP_ERR_BAD_ARG;
+    size_t pos = 0;
+    for (const TreeBuf& s : t->stages) {
+        int rc = copy_out(t->ctx, out + pos, space, s.digests, s.n_digests() * 4);
+        if (rc) return rc;
+        pos += s.n_digests() * 4;
+    }
+    return QP_OK;
+}
+extern "C" int qp_batch_tree_open(const qp_batch_tree* t, size_t leaf_index, uint64_t* siblings_out) {
+    if (!t) return QP_ERR_BAD_ARG;
+    if (leaf_index >= t->heights[0]) return fail(t->ctx, QP_ERR_BAD_ARG, "leaf index out of range");
+    const unsigned lg0 = ilog2(t->heights[0]);
+    size_t pos = 0;
+    for (const TreeBuf& s : t->stages) {  // batch_merkle_tree.rs:139-150
+        int rc = tree_prove(t->ctx, s, leaf_index >> (lg0 - s.shape.lg_leaves), siblings_out + pos);
+        if (rc) return rc;
+        pos += 4 * (size_t)s.shape.num_layers();
+    }
+    return QP_OK;
+}
+extern "C" int qp_batch_tree_values(const qp_batch_tree* t, size_t leaf_index, uint64_t* out) {
+    if (!t) return QP_ERR_BAD_ARG;
+    if (leaf_index >= t->heights[0]) return fail(t->ctx, QP_ERR_BAD_ARG, "leaf index out of range");
+    const unsigned lg0 = ilog2(t->heights[0]);
+    size_t pos = 0;
+    for (size_t j = 0; j < t->rows.size(); j++) {
+        const size_t row = leaf_index >> (lg0 - ilog2(t->heights[j])), w = t->widths[j];
+        if (w) {
+            int rc = copy_out(t->ctx, out + pos, QP_HOST, t->rows[j] + row * w, w);
+            if (rc) return rc;
+        }
+        pos += w;
+    }
+    return QP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Plonk permutation argument and quotient polynomials (quotient.cuh)
 // ---------------------------------------------------------------------------------------------
 struct qp_circuit {

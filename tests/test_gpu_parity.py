@@ -566,3 +566,48 @@ def test_batch_in_pieces_equals_from_coeffs(qp, ctx, cols, lg_n, blinding, first
     assert (b.merkle_tree.leaves() == want.merkle_tree.leaves()).all()
     with pytest.raises(qp.QpError):
         b.put_coeffs(co[:2], cols - 1)            # past the last column
+
+
+# ---- BatchMerkleTree (the oracle of batch FRI) ---------------------------------
+
+@pytest.mark.parametrize("shapes,cap_h", [([(4, 2)], 0), ([(4, 2), (2, 3)], 0), ([(64, 7), (16, 3), (8, 20)], 2),
+                                           ([(4096, 135), (512, 9), (32, 1)], 4), ([(256, 0), (16, 4)], 4),
+                                           ([(1 << 14, 20), (1 << 13, 16)], 4)])
+def test_batch_merkle_tree_parity(qp, ctx, shapes, cap_h):
+    """BatchMerkleTree::new / open_batch / values against the big-integer restatement
+    (plonky2/src/hash/batch_merkle_tree.rs:40-164), every digest; openings through the restated
+    verify_batch_merkle_proof_to_cap."""
+    rng = np.random.default_rng(len(shapes) * 100 + cap_h)
+    mats = [rng.integers(0, P, size=s, dtype=np.uint64) for s in shapes]
+    t = qp.BatchMerkleTree(ctx, mats, cap_h)
+    assert t.leaf_heights == [s[0].bit_length() - 1 for s in shapes]
+    lists = [m.tolist() for m in mats]
+    small = shapes[0][0] <= 4096
+    if small:
+        digests, cap, heights = pyref.batch_merkle_tree(lists, cap_h)
+        assert t.digests.tolist() == [list(d) for d in digests]
+        assert t.cap.tolist() == [list(c) for c in cap]
+    cap = t.cap.tolist()
+    n = shapes[0][0]
+    for i in sorted({0, 1, n // 2, n - 1, int(rng.integers(0, n))}):
+        rows = [[int(x) for x in r] for r in t.values(i)]
+        assert rows == [m[i >> (t.leaf_heights[0] - h)] for m, h in zip(lists, t.leaf_heights)]
+        proof = [list(map(int, s)) for s in t.open_batch(i)]
+        assert pyref.batch_merkle_verify(rows, t.leaf_heights, i, cap, proof)
+        if rows[-1]:
+            rows[-1][0] ^= 1
+            assert not pyref.batch_merkle_verify(rows, t.leaf_heights, i, cap, proof)
+    t.free()
+
+
+def test_batch_merkle_tree_errors(qp, ctx):
+    """the reference's asserts, batch_merkle_tree.rs:41-55"""
+    z = lambda h, w: np.zeros((h, w), dtype=np.uint64)
+    with pytest.raises(qp.QpError):
+        qp.BatchMerkleTree(ctx, [z(8, 2), z(8, 2)], 0)    # duplicate heights
+    with pytest.raises(qp.QpError):
+        qp.BatchMerkleTree(ctx, [z(4, 2), z(8, 2)], 0)    # not sorted tallest first
+    with pytest.raises(qp.QpError):
+        qp.BatchMerkleTree(ctx, [z(6, 2)], 0)             # not a power of two
+    with pytest.raises(qp.QpError):
+        qp.BatchMerkleTree(ctx, [z(16, 2), z(4, 2)], 3)   # cap_height > log2(last height)

@@ -322,3 +322,39 @@ def test_eval_poly_ext_vs_pyref():
     c = oracle.rand_felts(37, 5)
     pt = (123456789, 987654321)
     assert tuple(int(x) for x in oracle.eval_poly_ext(c, pt)) == pyref.eval_poly_ext([int(x) for x in c], pt)
+
+
+def test_batch_merkle_tree_restatement():
+    """BatchMerkleTree (plonky2/src/hash/batch_merkle_tree.rs): the reference's own structural tests
+    (commit_single / commit_mixed, :179-258) and its every-leaf open -> verify_batch_merkle_proof_to_cap
+    round trip (:286-336), on the big-integer restatement."""
+    from oracle import pyref
+
+    # commit_single: one matrix, cap height 0 -- an ordinary Merkle tree
+    mat_1 = [[0, 1], [2, 1], [2, 2], [0, 0]]
+    digests, cap, heights = pyref.batch_merkle_tree([mat_1], 0)
+    h = [pyref.hash_leaf(r) for r in mat_1]
+    assert digests[0:2] == h[0:2] and digests[4:6] == h[2:4] and heights == [2]
+    layer_1 = [pyref.two_to_one(h[0], h[1]), pyref.two_to_one(h[2], h[3])]
+    assert digests[2:4] == layer_1 and cap == [pyref.two_to_one(*layer_1)]
+    # commit_mixed: a second matrix of half the height joins one level up, hashed WITH the digests
+    mat_2 = [[1, 2, 1], [0, 2, 2]]
+    digests, cap, heights = pyref.batch_merkle_tree([mat_1, mat_2], 0)
+    assert digests[0:2] == h[0:2] and digests[2:4] == h[2:4] and heights == [2, 1]
+    layer_2 = [pyref.hash_leaf(list(layer_1[0]) + mat_2[0]), pyref.hash_leaf(list(layer_1[1]) + mat_2[1])]
+    assert digests[4:6] == layer_2 and cap == [pyref.two_to_one(*layer_2)]
+    assert pyref.batch_merkle_open(1, [mat_1, mat_2], 0, digests) == [h[0], layer_2[1]]   # :279-280
+    # random matrices, every leaf
+    rng = np.random.default_rng(3)
+    mats = [rng.integers(0, P, size=(32, 5), dtype=np.uint64).tolist(), rng.integers(0, P, size=(8, 3), dtype=np.uint64).tolist(),
+            rng.integers(0, P, size=(4, 9), dtype=np.uint64).tolist()]
+    for cap_h in (0, 1, 2):
+        digests, cap, heights = pyref.batch_merkle_tree(mats, cap_h)
+        assert len(digests) == 2 * (32 - (1 << cap_h)) and len(cap) == 1 << cap_h
+        for i in range(32):
+            proof = pyref.batch_merkle_open(i, mats, cap_h, digests)
+            rows = [m[i >> (5 - hh)] for m, hh in zip(mats, heights)]
+            assert pyref.batch_merkle_verify(rows, heights, i, cap, proof)
+            bad = [list(r) for r in rows]
+            bad[1][0] ^= 1
+            assert not pyref.batch_merkle_verify(bad, heights, i, cap, proof)
