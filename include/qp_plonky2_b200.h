@@ -106,6 +106,18 @@ size_t qp_batch_digests_len(const qp_batch* b);
 /* merkle_tree.leaves[first .. first+count): leaf-major rows [count][leaf_len], salt included. */
 int qp_batch_leaves(const qp_batch* b, size_t first, size_t count, uint64_t* out, int space);
 size_t qp_batch_leaf_len(const qp_batch* b);
+/* write_polynomial_batch / read_polynomial_batch (plonky2/src/util/serialization/mod.rs:1803-1822,
+ * 758-784): the byte form in which CircuitData stores its constants/sigmas commitment
+ * (circuit_data.rs:371-391) -- polynomials, Merkle tree (leaves, digests, cap), degree_log, rate_bits,
+ * blinding; u64 little-endian, canonical field elements.  Whole (unsharded) batches only.
+ * Deserialising rebuilds the device batch from the polynomials (and the salt found in the leaves)
+ * and fails with QP_ERR_BAD_ARG if the bytes are truncated, inconsistent, or their cap is not the
+ * cap of their polynomials. */
+/* out = {polynomials.len(), degree_log, rate_bits, cap height, blinding} */
+int qp_batch_describe(const qp_batch* b, uint64_t out[5]);
+size_t qp_batch_serialized_len(const qp_batch* b);
+int qp_batch_serialize(const qp_batch* b, uint8_t* out, size_t capacity);
+int qp_batch_deserialize(qp_ctx* ctx, const uint8_t* data, size_t len, qp_batch** out, size_t* consumed);
 /* get_lde_values(index, step) (oracle.rs:286-291): row at bit-reversed index*step, salt stripped;
  * out holds n_cols elements (host). */
 int qp_batch_get_lde_values(const qp_batch* b, size_t index, size_t step, uint64_t* out);

@@ -305,6 +305,26 @@ class PolynomialBatch:
         return row[: len(row) - (4 if self.blinding else 0)]
 
 
+def serialize_polynomial_batch(batch, rate_bits, blinding=False):
+    """write_polynomial_batch (plonky2/src/util/serialization/mod.rs:1803-1822; write_merkle_tree
+    :1476-1491): every integer a u64 LE, field elements canonical, the bool one byte."""
+    u64 = lambda x: np.uint64(x).tobytes()
+    co = np.ascontiguousarray(batch.polynomials, dtype="<u8")
+    out = [u64(co.shape[0])]
+    for col in co:
+        out += [u64(col.size), col.tobytes()]
+    leaves = np.ascontiguousarray(batch.leaves, dtype="<u8")
+    out.append(u64(leaves.shape[0]))
+    for row in leaves:
+        out += [u64(row.size), row.tobytes()]
+    dig = np.ascontiguousarray(batch.digests, dtype="<u8")
+    out += [u64(dig.shape[0]), dig.tobytes()]
+    cap = np.ascontiguousarray(batch.cap, dtype="<u8")
+    out += [u64(cap.shape[0].bit_length() - 1), cap.tobytes()]
+    out += [u64(co.shape[1].bit_length() - 1), u64(rate_bits), bytes([1 if blinding else 0])]
+    return b"".join(out)
+
+
 def fri_reduction_arity_bits(degree_bits, rate_bits, cap_height, arity_bits=4, final_poly_bits=5):
     out = (C.c_uint * 64)()
     k = lib().orc_fri_reduction_arity_bits(degree_bits, rate_bits, cap_height, arity_bits, final_poly_bits, out)

@@ -185,6 +185,10 @@ def lib():
         "qp_circuit_describe": (i32, [vp, vp]),
         "qp_circuit_has_sigmas": (i32, [vp]),
         "qp_dev_alloc": (i32, [vp, sz, pp]),
+        "qp_batch_describe": (i32, [vp, vp]),
+        "qp_batch_serialized_len": (sz, [vp]),
+        "qp_batch_serialize": (i32, [vp, vp, sz]),
+        "qp_batch_deserialize": (i32, [vp, vp, sz, pp, C.POINTER(sz)]),
         "qp_batch_merkle_tree_new": (i32, [vp, vp, i32, vp, vp, sz, u32, pp]),
         "qp_batch_tree_free": (None, [vp]),
         "qp_batch_tree_cap": (i32, [vp, vp, i32]),
@@ -422,6 +426,35 @@ class PolynomialBatch:
         lib().qp_batch_kernel_timing(self._h, ms)
         self.kernel_ms = dict(zip(("intt", "lde", "leaf_hash", "tree_levels"), list(ms)))
         return self
+
+    # ---- write_polynomial_batch / read_polynomial_batch (serialization/mod.rs:1803-1822, 758-784) ----
+    def to_bytes(self):
+        n = int(lib().qp_batch_serialized_len(self._h))
+        out = np.zeros(n, dtype=np.uint8)
+        self.ctx.check(lib().qp_batch_serialize(self._h, out.ctypes.data, n))
+        return out.tobytes()
+
+    @classmethod
+    def from_bytes(cls, ctx, data):
+        """-> (batch, bytes consumed).  The device batch is rebuilt from the stored polynomials; the
+        stored cap must be theirs."""
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        self = cls()
+        self.ctx = ctx
+        used = C.c_size_t()
+        ctx.check(lib().qp_batch_deserialize(ctx._h, buf.ctypes.data, buf.size, C.byref(self._h), C.byref(used)))
+        d = np.zeros(5, dtype=np.uint64)
+        lib().qp_batch_describe(self._h, d.ctypes.data)
+        self.n_cols, self.degree_log, self.rate_bits, self.cap_height = (int(x) for x in d[:4])
+        self.blinding = bool(d[4])
+        self.block_first, self.block_count = 0, 1 << self.rate_bits
+        self.leaf_len = int(lib().qp_batch_leaf_len(self._h))
+        self.n_local_leaves = self.block_count << self.degree_log
+        self.local_lg_leaves = self.n_local_leaves.bit_length() - 1
+        self.local_cap_height = self.cap_height
+        self.merkle_tree = BatchMerkleView(self)
+        self.timing, self.kernel_ms = {}, {}
+        return self, int(used.value)
 
     # ---- from_coeffs in pieces (columns arriving over time, e.g. from an all-gather) ----
     @classmethod

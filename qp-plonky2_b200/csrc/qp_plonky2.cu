@@ -1083,6 +1083,170 @@ extern "C" int qp_batch_kernel_timing(const qp_batch* b, double ms[4]) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// write_polynomial_batch / read_polynomial_batch (plonky2/src/util/serialization/mod.rs:1803-1822,
+// 758-784; write_merkle_tree :1476-1491): the byte form CircuitData keeps its constants/sigmas
+// commitment in.  All integers are u64 little-endian, field elements canonical, a bool one byte.
+// ---------------------------------------------------------------------------------------------
+extern "C" int qp_batch_describe(const qp_batch* b, uint64_t out[5]) {
+    if (!b || !out) return QP_ERR_BAD_ARG;
+    out[0] = b->n_cols;
+    out[1] = b->degree_log;
+    out[2] = b->rate_bits;
+    out[3] = b->cap_height;
+    out[4] = b->blinding ? 1 : 0;
+    return QP_OK;
+}
+
+extern "C" size_t qp_batch_serialized_len(const qp_batch* b) {
+    if (!b) return 0;
+    const size_t n = (size_t)1 << b->degree_log, N = n << b->rate_bits;
+    size_t words = 1 + b->n_cols * (1 + n);                      // polynomials
+    words += 1 + N * (1 + b->leaf_len);                          // leaves
+    words += 1 + b->tree.n_digests() * 4;                        // digests
+    words += 1 + b->tree.n_cap() * 4;                            // cap height, cap
+    words += 2;                                                  // degree_log, rate_bits
+    return words * 8 + 1;                                        // + blinding
+}
+
+extern "C" int qp_batch_serialize(const qp_batch* b, uint8_t* out, size_t capacity) {
+    if (!b) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = b->ctx;
+    if (b->block_first != 0 || b->block_count != (1u << b->rate_bits))
+        return fail(ctx, QP_ERR_BAD_ARG, "only a whole (unsharded) batch has the reference's byte form");
+    if (!out || capacity < qp_batch_serialized_len(b)) return fail(ctx, QP_ERR_BAD_ARG, "output buffer too small");
+    const size_t n = (size_t)1 << b->degree_log, N = n << b->rate_bits;
+    uint8_t* w = out;
+    auto put = [&](uint64_t x) {
+        std::memcpy(w, &x, 8);
+        w += 8;
+    };
+    std::vector<uint64_t> host(std::max(b->n_cols * n, std::max(b->tree.n_digests(), b->tree.n_cap()) * 4));
+    int rc = qp_batch_coeffs(b, host.data(), QP_HOST);
+    if (rc) return rc;
+    put(b->n_cols);
+    for (size_t c = 0; c < b->n_cols; c++) {
+        put(n);
+        std::memcpy(w, host.data() + c * n, n * 8);
+        w += n * 8;
+    }
+    put(N);
+    const size_t chunk = std::max<size_t>(1, ((size_t)1 << 22) / (b->leaf_len ? b->leaf_len : 1));  // ~32 MB of rows at a time
+    std::vector<uint64_t> rows(std::min(chunk, N) * b->leaf_len);
+    for (size_t first = 0; first < N; first += chunk) {
+        const size_t cnt = std::min(chunk, N - first);
+        if (b->leaf_len) {
+            rc = qp_batch_leaves(b, first, cnt, rows.data(), QP_HOST);
+            if (rc) return rc;
+        }
+        for (size_t i = 0; i < cnt; i++) {
+            put(b->leaf_len);
+            std::memcpy(w, rows.data() + i * b->leaf_len, b->leaf_len * 8);
+            w += b->leaf_len * 8;
+        }
+    }
+    put(b->tree.n_digests());
+    if (b->tree.n_digests()) {
+        rc = qp_batch_digests(b, host.data(), QP_HOST);
+        if (rc) return rc;
+        std::memcpy(w, host.data(), b->tree.n_digests() * 32);
+        w += b->tree.n_digests() * 32;
+    }
+    put(b->cap_height);
+    rc = qp_batch_cap(b, host.data(), QP_HOST);
+    if (rc) return rc;
+    std::memcpy(w, host.data(), b->tree.n_cap() * 32);
+    w += b->tree.n_cap() * 32;
+    put(b->degree_log);
+    put(b->rate_bits);
+    *w++ = b->blinding ? 1 : 0;
+    return (size_t)(w - out) == qp_batch_serialized_len(b) ? QP_OK : fail(ctx, QP_ERR_BAD_ARG, "internal: length");
+}
+
+// The device batch is rebuilt from the polynomials (and the salt columns found in the leaves); the
+// bytes' own cap must come out again -- the reference trusts the stored tree, this rejects a
+// tree that does not belong to its polynomials.
+extern "C" int qp_batch_deserialize(qp_ctx* ctx, const uint8_t* data, size_t len, qp_batch** out, size_t* consumed) {
+    if (!ctx) return QP_ERR_BAD_ARG;
+    if (!data || !out) return fail(ctx, QP_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    size_t pos = 0;
+    bool ok = true;
+    auto get = [&]() -> uint64_t {
+        uint64_t x = 0;
+        if (pos + 8 > len) ok = false;
+        else std::memcpy(&x, data + pos, 8);
+        pos += 8;
+        return x;
+    };
+    auto truncated = [&]() { return fail(ctx, QP_ERR_BAD_ARG, "serialized PolynomialBatch is truncated or malformed"); };
+    const uint64_t n_cols = get();
+    if (!ok || n_cols > ((uint64_t)1 << 24)) return truncated();
+    std::vector<uint64_t> coeffs;
+    uint64_t n = 0;
+    for (uint64_t c = 0; c < n_cols; c++) {
+        const uint64_t plen = get();
+        if (!ok || (c && plen != n) || plen > len / 8 || pos + plen * 8 > len) return truncated();
+        n = plen;
+        coeffs.resize((c + 1) * n);
+        std::memcpy(coeffs.data() + c * n, data + pos, n * 8);
+        pos += n * 8;
+    }
+    const uint64_t N = get();
+    if (!ok || N > len / 8) return truncated();
+    uint64_t leaf_len = 0;
+    std::vector<uint64_t> salt_rows;  // [N][4] when the leaves are salted
+    for (uint64_t i = 0; i < N; i++) {
+        const uint64_t l = get();
+        if (!ok || (i && l != leaf_len) || l > len / 8 || pos + l * 8 > len) return truncated();
+        leaf_len = l;
+        if (l == n_cols + QP_SALT_SIZE) {
+            if (salt_rows.empty()) salt_rows.resize(N * QP_SALT_SIZE);
+            std::memcpy(salt_rows.data() + i * QP_SALT_SIZE, data + pos + n_cols * 8, QP_SALT_SIZE * 8);
+        }
+        pos += l * 8;
+    }
+    const uint64_t n_digests = get();
+    if (!ok || n_digests > len / 32 || pos + n_digests * 32 > len) return truncated();
+    pos += n_digests * 32;
+    const uint64_t cap_height = get();
+    if (!ok || cap_height > 32 || pos + (((size_t)1 << cap_height) * 32) > len) return truncated();
+    const uint8_t* cap_bytes = data + pos;
+    pos += ((size_t)1 << cap_height) * 32;
+    const uint64_t degree_log = get(), rate_bits = get();
+    if (!ok || pos + 1 > len) return truncated();
+    const int blinding = data[pos++] ? 1 : 0;
+    if (degree_log > 32 || rate_bits > 8 || n_cols == 0 || n != (uint64_t)1 << degree_log || N != n << rate_bits ||
+        leaf_len != n_cols + (blinding ? QP_SALT_SIZE : 0) || cap_height > degree_log + rate_bits ||
+        n_digests != 2 * (N - ((uint64_t)1 << cap_height)))
+        return fail(ctx, QP_ERR_BAD_ARG, "serialized PolynomialBatch is inconsistent");
+    std::vector<uint64_t> salt;
+    if (blinding) {  // leaf i is the point bitrev(i): back to [QP_SALT_SIZE][N] in natural point order
+        salt.resize((size_t)QP_SALT_SIZE * N);
+        const unsigned bits = (unsigned)(degree_log + rate_bits);
+        for (uint64_t i = 0; i < N; i++) {
+            uint64_t nat = 0;
+            for (unsigned k = 0; k < bits; k++) nat |= ((i >> k) & 1) << (bits - 1 - k);
+            for (unsigned k = 0; k < QP_SALT_SIZE; k++) salt[(size_t)k * N + nat] = salt_rows[i * QP_SALT_SIZE + k];
+        }
+    }
+    qp_batch* b = nullptr;
+    int rc = qp_batch_from_coeffs(ctx, coeffs.data(), QP_HOST, n_cols, (unsigned)degree_log, (unsigned)rate_bits, blinding,
+                                  (unsigned)cap_height, blinding ? salt.data() : nullptr, 0, 1u << rate_bits, &b);
+    if (rc) return rc;
+    std::vector<uint64_t> cap(((size_t)1 << cap_height) * 4);
+    rc = qp_batch_cap(b, cap.data(), QP_HOST);
+    if (!rc && std::memcmp(cap.data(), cap_bytes, cap.size() * 8) != 0)
+        rc = fail(ctx, QP_ERR_BAD_ARG, "serialized Merkle cap does not belong to the serialized polynomials");
+    if (rc) {
+        qp_batch_free(b);
+        return rc;
+    }
+    *out = b;
+    if (consumed) *consumed = pos;
+    return QP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // MerkleTree::new on caller rows
 // ---------------------------------------------------------------------------------------------
 struct qp_tree {

@@ -611,3 +611,34 @@ def test_batch_merkle_tree_errors(qp, ctx):
         qp.BatchMerkleTree(ctx, [z(6, 2)], 0)             # not a power of two
     with pytest.raises(qp.QpError):
         qp.BatchMerkleTree(ctx, [z(16, 2), z(4, 2)], 3)   # cap_height > log2(last height)
+
+
+# ---- byte form of a PolynomialBatch (CircuitData (de)serialization) -----------------
+
+@pytest.mark.parametrize("lg_n,cols,rate,cap_h,salted", [(5, 3, 3, 4, False), (9, 7, 3, 4, False), (6, 4, 1, 0, True),
+                                                        (12, 84, 3, 4, False)])
+def test_polynomial_batch_bytes_round_trip(qp, ctx, lg_n, cols, rate, cap_h, salted):
+    """write_polynomial_batch / read_polynomial_batch (serialization/mod.rs:1803-1822, 758-784): the
+    device batch serialises to the oracle's bytes; the bytes deserialise to a batch with the same cap,
+    digests, leaves and polynomials; truncated or tampered bytes are refused."""
+    vals = oracle.rand_felts((cols, 1 << lg_n), 1200 + lg_n)
+    salt = oracle.rand_felts((4, 1 << (lg_n + rate)), 77) if salted else None
+    b = qp.PolynomialBatch.from_values(ctx, vals, rate, salted, cap_h, salt=salt)
+    want = oracle.PolynomialBatch.from_values(vals, rate, cap_h, salt=salt)
+    data = b.to_bytes()
+    assert data == oracle.serialize_polynomial_batch(want, rate, salted)
+    back, used = qp.PolynomialBatch.from_bytes(ctx, data + b"trailing")
+    assert used == len(data) and back.blinding == salted and back.n_cols == cols and back.degree_log == lg_n
+    assert (back.merkle_tree.cap == want.cap).all() and (back.merkle_tree.digests == want.digests).all()
+    assert (back.merkle_tree.leaves() == want.leaves).all() and (back.polynomials == want.polynomials).all()
+    assert back.to_bytes() == data
+    with pytest.raises(qp.QpError):
+        qp.PolynomialBatch.from_bytes(ctx, data[:-9])
+    bad = bytearray(data)
+    bad[8 + 8 + 3] ^= 1          # a coefficient of the first polynomial: the stored cap is no longer theirs
+    with pytest.raises(qp.QpError):
+        qp.PolynomialBatch.from_bytes(ctx, bytes(bad))
+    bad = bytearray(data)
+    bad[0] ^= 1                  # the polynomial count
+    with pytest.raises(qp.QpError):
+        qp.PolynomialBatch.from_bytes(ctx, bytes(bad))
