@@ -2254,7 +2254,7 @@ extern "C" int qp_circuit_compute_quotient_polys(qp_circuit* c, const qp_batch* 
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(d_apow, apow.data(), apow.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     p.alpha_pows = d_apow;
-    const size_t smem = quotient::smem_words(p.pool_len, nc, stride, p.n_regs) * 8;
+    const size_t smem = quotient::smem_words(p.pool_len, p.n_regs) * 8;
     if (smem > 200 * 1024) return fail(ctx, QP_ERR_TOO_LARGE, "constraint program needs too much shared memory");
     if (smem > 48 * 1024)
         CUDA_TRY(ctx, cudaFuncSetAttribute(quotient::quotient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -106,9 +106,11 @@ struct Params {
     uint64_t* out;
 };
 
-// shared memory: pool | alpha powers | register file [n_regs][BLOCK]
-__host__ __device__ inline size_t smem_words(unsigned pool_len, unsigned nc, unsigned apow_stride, unsigned n_regs) {
-    return (size_t)pool_len + (size_t)nc * apow_stride + (size_t)n_regs * BLOCK;
+// shared memory: pool | register file [n_regs][BLOCK].  The register file bounds the points resident
+// per SM, so the powers of alpha (2 KB, read by EMIT only) stay in global memory behind L1: with the
+// recursion gate set that is the difference between four and five resident blocks.
+__host__ __device__ inline size_t smem_words(unsigned pool_len, unsigned n_regs) {
+    return (size_t)pool_len + (size_t)n_regs * BLOCK;
 }
 
 // One thread per point of the quotient domain, enumerated in leaf order.  The work of a point is
@@ -117,10 +119,9 @@ __host__ __device__ inline size_t smem_words(unsigned pool_len, unsigned nc, uns
 __global__ void __launch_bounds__(BLOCK) quotient_kernel(Params p) {
     extern __shared__ uint64_t smem[];
     uint64_t* const sh_pool = smem;
-    uint64_t* const sh_apow = sh_pool + p.pool_len;
-    uint64_t* const regs = sh_apow + (size_t)p.nc * p.apow_stride;  // [n_regs][BLOCK]
+    uint64_t* const regs = sh_pool + p.pool_len;  // [n_regs][BLOCK]
+    const uint64_t* const __restrict__ sh_apow = p.alpha_pows;
     for (unsigned k = threadIdx.x; k < p.pool_len; k += BLOCK) sh_pool[k] = p.pool[k];
-    for (unsigned k = threadIdx.x; k < p.nc * p.apow_stride; k += BLOCK) sh_apow[k] = p.alpha_pows[k];
     __syncthreads();
     const size_t n_lde = (size_t)1 << p.lg_lde;
     const size_t pos_raw = (size_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(BLOCK) quotient_kernel(Params p) {
     auto add_term = [&](unsigned t, uint64_t term) {
 #pragma unroll
         for (int a = 0; a < MAX_CHALLENGES; a++)
-            if (a < (int)p.nc) res[a] = gl::add(res[a], gl::mul(term, sh_apow[a * p.apow_stride + t]));
+            if (a < (int)p.nc) res[a] = gl::add(res[a], gl::mul(term, __ldg(&sh_apow[a * p.apow_stride + t])));
     };
     constexpr unsigned REG_SHIFT = 10;  // one register = BLOCK * 8 bytes
     static_assert(BLOCK * 8 == 1 << REG_SHIFT, "register stride");
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(BLOCK) quotient_kernel(Params p) {
                 const uint64_t v = lds64(ra);
 #pragma unroll
                 for (int k = 0; k < MAX_CHALLENGES; k++)
-                    if (k < (int)p.nc) h[k] = gl::add(h[k], gl::mul(v, sh_apow[k * p.apow_stride + c]));
+                    if (k < (int)p.nc) h[k] = gl::add(h[k], gl::mul(v, __ldg(&sh_apow[k * p.apow_stride + c])));
             } else if (op == OP_ADDI) {
                 sts64(rd, gl::add(lds64(ra), lds64(pool_base + c * 8)));
             } else if (op == OP_LDI) {
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(BLOCK) quotient_kernel(Params p) {
 #pragma unroll
     for (int a = 0; a < MAX_CHALLENGES; a++)
         if (a < (int)p.nc) {
-            const uint64_t total = gl::add(res[a], gl::mul(G[a], sh_apow[a * p.apow_stride + base]));
+            const uint64_t total = gl::add(res[a], gl::mul(G[a], __ldg(&sh_apow[a * p.apow_stride + base])));
             if (gridDim.y == 1)
                 p.out[((size_t)a << p.lg_lde) + i] = gl::canon(gl::mul(total, zinv));  // prover.rs:848-853
             else
