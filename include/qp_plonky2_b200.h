@@ -257,6 +257,10 @@ int qp_fri_proof_of_work(qp_ctx* ctx, const uint64_t state12[12], unsigned witne
  *                issuing one, the device waits until at most 3 loads are in flight, so a program
  *                must not read a loaded register before 3 further loads or a WAIT have been issued
  *                (a program that puts a WAIT after every load is always valid).
+ *   14 NATIVE_POSEIDON  (a segment of its own: this one word) a PoseidonGate evaluated by the device's
+ *                native kernel instead of the interpreter: dst = end of the gate's selector group,
+ *                a = the gate's index in common_data.gates (= its selector value), b = start of the
+ *                group, c = selector polynomial | (num_selectors > 1) << 16.  At most one per program.
  *   0 END        end of a segment.  A program may consist of several self-contained segments
  *                (no register is live across an END); their contributions add up, and for small
  *                circuits different thread blocks evaluate different segments.

@@ -1960,8 +1960,9 @@ struct qp_circuit {
     uint64_t* k_is = nullptr;     // [num_routed_wires]
     uint64_t* sigmas = nullptr;   // [num_routed_wires][n], may be null (quotient-only circuits)
     uint64_t* program = nullptr;  // program_len + 1 words (OP_END appended)
-    uint32_t* seg_off = nullptr;  // first word of every OP_END-terminated segment of the program
+    uint32_t* seg_off = nullptr;  // first word of every OP_END-terminated segment the interpreter runs
     unsigned n_seg = 0;
+    quotient::NativePoseidon native{};  // a PoseidonGate handed to poseidon_gate_kernel (OP_NATIVE_POSEIDON)
     uint64_t* pool = nullptr;
     uint64_t* zh = nullptr;       // [2][2^qdb]: Z_H on the coset, and its inverses
     unsigned max_emit = 0;        // largest constraint index in the program
@@ -2008,7 +2009,20 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
     std::vector<uint32_t> seg_off;
     for (size_t k = 0, start = 0; k < prog.size(); k++)
         if ((prog[k] & 0xff) == quotient::OP_END) {
-            if (k > start) seg_off.push_back((uint32_t)start);
+            if (k == start + 1 && (prog[start] & 0xff) == quotient::OP_NATIVE_POSEIDON) {
+                const uint64_t w = prog[start];
+                if (c->native.present) return fail(ctx, QP_ERR_BAD_ARG, "more than one native PoseidonGate segment");
+                c->native = {1u, (unsigned)((w >> 16) & 0xff), (unsigned)((w >> 24) & 0xff), (unsigned)((w >> 8) & 0xff),
+                             (unsigned)((w >> 32) & 0xffff), (unsigned)((w >> 48) & 1)};
+                if (c->native.sel_column >= d->num_constants || c->native.group_start > c->native.index ||
+                    c->native.index >= c->native.group_end || d->num_wires < 135)
+                    return fail(ctx, QP_ERR_BAD_ARG, "malformed native PoseidonGate segment");
+            } else if (k > start) {
+                for (size_t q = start; q < k; q++)
+                    if ((prog[q] & 0xff) == quotient::OP_NATIVE_POSEIDON)
+                        return fail(ctx, QP_ERR_BAD_ARG, "a native PoseidonGate word must be a segment of its own");
+                seg_off.push_back((uint32_t)start);
+            }
             start = k + 1;
         }
     c->n_seg = (unsigned)seg_off.size();
@@ -2021,7 +2035,7 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
         const unsigned op = ins & 0xff, dst = (ins >> 8) & 0xff, a = (ins >> 16) & 0xff, b = (ins >> 24) & 0xff;
         const uint64_t cc = ins >> 32;
         const unsigned nr = d->program_regs;
-        bool ok = op <= quotient::OP_FMAI;
+        bool ok = op <= quotient::OP_NATIVE_POSEIDON;
         switch (op) {
             case quotient::OP_ADD: case quotient::OP_SUB: case quotient::OP_MUL: ok = dst < nr && a < nr && b < nr; break;
             case quotient::OP_FMAI: ok = dst < nr && a < nr && b < nr && cc < d->pool_len; break;
@@ -2037,6 +2051,7 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
         if (!ok) return fail(ctx, QP_ERR_BAD_ARG, "malformed constraint program");
         if (op == quotient::OP_EMIT && cc > c->max_emit) c->max_emit = (unsigned)cc;
     }
+    if (c->native.present && c->max_emit < 122) c->max_emit = 122;  // PoseidonGate has 123 constraints
     CUDA_TRY(ctx, cudaMemcpyAsync(c->program, prog.data(), prog.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (d->pool_len)
         CUDA_TRY(ctx, cudaMemcpyAsync(c->pool, d->pool, d->pool_len * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -2264,15 +2279,20 @@ extern "C" int qp_circuit_compute_quotient_polys(qp_circuit* c, const qp_batch* 
     unsigned ny = (unsigned)cdiv((size_t)ctx->sm_count * 8, (size_t)tiles);
     if (ny > units) ny = units;
     if (ny < 1) ny = 1;
+    // a native PoseidonGate is one more partial sum, from its own kernel
+    const unsigned n_parts = ny + (c->native.present ? 1 : 0);
     uint64_t* d_partial = nullptr;
-    if (ny > 1) {
-        rc = dev_alloc(ctx, &d_partial, (size_t)ny * out_words);
+    if (n_parts > 1) {
+        rc = dev_alloc(ctx, &d_partial, (size_t)n_parts * out_words);
         if (rc) return rc;
     }
-    p.out = ny > 1 ? d_partial : d_vals;
+    p.out = n_parts > 1 ? d_partial : d_vals;
+    p.partial_out = n_parts > 1;
     LAUNCH(ctx, quotient::quotient_kernel, dim3(tiles, ny), quotient::BLOCK, smem, p);
-    if (ny > 1)
-        LAUNCH(ctx, quotient::combine_kernel, cdiv(out_words, 256), 256, 0, d_partial, ny, nc, lg_lde,
+    if (c->native.present)
+        LAUNCH(ctx, quotient::poseidon_gate_kernel, cdiv(n_lde, 128), 128, 0, p, c->native, d_partial + (size_t)ny * out_words);
+    if (n_parts > 1)
+        LAUNCH(ctx, quotient::combine_kernel, cdiv(out_words, 256), 256, 0, d_partial, n_parts, nc, lg_lde,
                d.quotient_degree_bits, p.zh_inv, d_vals);
     dev_free(ctx, d_partial);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // apow dies at return

@@ -20,6 +20,7 @@
 // young (a Poseidon gate needs ~40 live values, not the ~330 a last-to-first Horner order forces).
 #pragma once
 #include "goldilocks.cuh"
+#include "poseidon.cuh"
 
 namespace quotient {
 
@@ -40,6 +41,10 @@ enum : unsigned {
     OP_ADDI = 11, // dst = r[a] + pool[c]
     OP_WAIT = 12, // every column load issued so far has arrived
     OP_FMAI = 13, // dst = r[a] * pool[c] + r[b]
+    // A segment that is this single word hands a whole PoseidonGate to poseidon_gate_kernel instead
+    // of the interpreter: dst = group end, a = the gate's index (= its selector value), b = group
+    // start, c = selector column | (num_selectors > 1) << 16.
+    OP_NATIVE_POSEIDON = 14,
 };
 
 // LDW / LDK are asynchronous copies global -> register file (cp.async, 8 bytes per thread): issuing
@@ -101,9 +106,10 @@ struct Params {
     const uint64_t* pool;
     unsigned pool_len;
     unsigned n_regs;
-    // gridDim.y == 1: out = the quotient values [nc][2^lg_lde], natural order.
-    // gridDim.y  > 1: out = partial sums [gridDim.y][nc][2^lg_lde] for combine_kernel.
+    // partial_out == 0: out = the quotient values [nc][2^lg_lde], natural order.
+    // partial_out != 0: out = partial sums [gridDim.y (+ 1)][nc][2^lg_lde] for combine_kernel.
     uint64_t* out;
+    unsigned partial_out;
 };
 
 // shared memory: pool | register file [n_regs][BLOCK].  The register file bounds the points resident
@@ -245,11 +251,103 @@ __global__ void __launch_bounds__(BLOCK) quotient_kernel(Params p) {
     for (int a = 0; a < MAX_CHALLENGES; a++)
         if (a < (int)p.nc) {
             const uint64_t total = gl::add(res[a], gl::mul(G[a], __ldg(&sh_apow[a * p.apow_stride + base])));
-            if (gridDim.y == 1)
+            if (!p.partial_out)
                 p.out[((size_t)a << p.lg_lde) + i] = gl::canon(gl::mul(total, zinv));  // prover.rs:848-853
             else
                 p.out[(((size_t)blockIdx.y * p.nc + a) << p.lg_lde) + i] = total;
         }
+}
+
+// ---- PoseidonGate, natively -----------------------------------------------------------------------
+// A recursive verifier spends its rows on PoseidonGate, and its 123 degree-7 constraints are half of
+// the interpreted program (3.6 k of 7.8 k operations at ~50 instructions each).  The gate is the
+// permutation with every S-box input replaced by a wire (plonky2/src/gates/poseidon.rs:204-283), so
+// it runs here on the permutation's own building blocks -- x^7 on the integer pipes, the MDS layer
+// with the next round's constants on the FP64 pipe (poseidon::mds_layer_split) -- with the state in
+// registers: one thread per point, no shared memory, ~27 k instructions instead of ~200 k.  The
+// partial rounds are evaluated in the naive form (S-box on lane 0, full MDS; core/src/poseidon.rs:
+// 613-633) where the reference's gate uses the sparse fast form: the two are the same function with
+// the same lane-0 values (the S-box inputs -- the only partial-round values the gate constrains).
+struct NativePoseidon {
+    unsigned present, index, group_start, group_end, sel_column, many_selectors;
+};
+
+__global__ void __launch_bounds__(128) poseidon_gate_kernel(Params p, NativePoseidon g, uint64_t* __restrict__ out) {
+    const size_t n_lde = (size_t)1 << p.lg_lde;
+    const size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n_lde) return;
+    const size_t i = brev(pos, p.lg_lde);
+    auto wire = [&](unsigned c) { return p.wires[c * p.wires_stride + pos]; };
+    uint64_t h[MAX_CHALLENGES];
+#pragma unroll
+    for (int a = 0; a < MAX_CHALLENGES; a++) h[a] = 0;
+    unsigned k = 0;  // constraint index, in the gate's order (poseidon.rs:204-283)
+    auto emit = [&](uint64_t v) {
+#pragma unroll
+        for (int a = 0; a < MAX_CHALLENGES; a++)
+            if (a < (int)p.nc) h[a] = gl::add(h[a], gl::mul(v, __ldg(&p.alpha_pows[a * p.apow_stride + k])));
+        k++;
+    };
+    constexpr unsigned SWAP = 24, DELTA = 25, FULL0 = 29, PARTIAL = 65, FULL1 = 87;
+    const uint64_t swap = wire(SWAP);
+    emit(gl::mul(swap, gl::sub(swap, 1)));
+    uint64_t s[12];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint64_t lhs = wire(j), rhs = wire(j + 4), delta = wire(DELTA + j);
+        emit(gl::sub(gl::mul(swap, gl::sub(rhs, lhs)), delta));
+        s[j] = gl::add(lhs, delta);
+        s[j + 4] = gl::sub(rhs, delta);
+    }
+#pragma unroll
+    for (int j = 8; j < 12; j++) s[j] = wire(j);
+#pragma unroll
+    for (int j = 0; j < 12; j++) s[j] = gl::add(s[j], poseidon::c_rc[j]);  // constant layer of round 0
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+        if (r != 0) {
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+                const uint64_t in = wire(FULL0 + 12 * (r - 1) + j);
+                emit(gl::sub(s[j], in));
+                s[j] = in;
+            }
+        }
+        poseidon::sbox_all(s);
+        poseidon::mds_layer_split(s, r + 1);  // + the constants of the next round
+    }
+#pragma unroll 1
+    for (int r = 0; r < 22; r++) {
+        const uint64_t in = wire(PARTIAL + r);
+        emit(gl::sub(s[0], in));
+        s[0] = gl::pow7(in);
+        poseidon::mds_layer_split(s, 4 + r + 1);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            const uint64_t in = wire(FULL1 + 12 * r + j);
+            emit(gl::sub(s[j], in));
+            s[j] = in;
+        }
+        poseidon::sbox_all(s);
+        poseidon::mds_layer_split(s, 26 + r + 1);  // row 30 of the constants is zero
+    }
+#pragma unroll
+    for (int j = 0; j < 12; j++) emit(gl::sub(s[j], wire(12 + j)));
+    // compute_filter, gates/gate.rs:326-333
+    const uint64_t sel = p.cs[g.sel_column * p.cs_stride + pos];
+    uint64_t f = 1;
+    for (unsigned j = g.group_start; j < g.group_end; j++)
+        if (j != g.index) f = gl::mul(f, gl::sub((uint64_t)j, sel));
+    if (g.many_selectors) f = gl::mul(f, gl::sub(0xFFFFFFFFull, sel));
+    const unsigned base = p.nc + p.nc * (p.np + 1);
+#pragma unroll
+    for (int a = 0; a < MAX_CHALLENGES; a++)
+        if (a < (int)p.nc)
+            out[((size_t)a << p.lg_lde) + i] =
+                gl::mul(gl::mul(f, h[a]), __ldg(&p.alpha_pows[a * p.apow_stride + base]));
 }
 
 // out[a][i] = Z_H(x_i)^-1 * sum_y partial[y][a][i]   (the units of quotient_kernel, summed)

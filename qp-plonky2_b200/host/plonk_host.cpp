@@ -17,6 +17,7 @@
 // Gate::eval_unfiltered_base_one; here the same recording evaluation is written in
 // C++ for the gates above.  Pure host logic: no field arithmetic on data happens here.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -31,7 +32,7 @@ namespace {
 constexpr uint64_t P = 0xFFFFFFFF00000001ULL;
 constexpr uint64_t UNUSED_SELECTOR = 0xFFFFFFFFULL;  // core/src/selectors.rs
 
-enum Op : unsigned { END = 0, LDW, LDK, LDP, LDI, ADD, SUB, MUL, EMIT, GATE, MULI, ADDI, WAIT, FMAI };
+enum Op : unsigned { END = 0, LDW, LDK, LDP, LDI, ADD, SUB, MUL, EMIT, GATE, MULI, ADDI, WAIT, FMAI, NATIVE_POSEIDON };
 
 struct Recorder;
 
@@ -780,9 +781,21 @@ extern "C" int qp_program_create(const qp_gate_desc* gates, size_t n_gates, unsi
     }
     const unsigned num_selectors = (unsigned)p->groups.size() / 2;
     // evaluate_gate_constraints_base_batch as a program, vanishing_poly.rs:700-726
+    // PoseidonGate -- half of a recursion circuit's constraint work -- is not compiled: the device has
+    // a native evaluator for it (quotient::poseidon_gate_kernel); the program carries one word with
+    // the gate's filter parameters in a segment of its own.  QP_NATIVE_POSEIDON=0 compiles it like
+    // any other gate (the two must agree: tests/test_gpu_plonk.py).
+    const char* env_native = getenv("QP_NATIVE_POSEIDON");
+    const bool native_poseidon = !(env_native && env_native[0] == '0');
+    std::vector<uint64_t> native_words;
     Recorder R;
     for (unsigned i = 0; i < num_gates; i++) {
         const unsigned sel = p->selector_indices[i];
+        if (native_poseidon && p->gates[i].kind == QP_GATE_POSEIDON && native_words.empty() && num_gates < 256) {
+            native_words.push_back(word(NATIVE_POSEIDON, p->groups[2 * sel + 1], i, p->groups[2 * sel],
+                                        sel | ((num_selectors > 1 ? 1u : 0u) << 16)));
+            continue;
+        }
         Val s = R.constant((int)sel);
         Val filt = R.imm(1);
         for (unsigned j = p->groups[2 * sel]; j < p->groups[2 * sel + 1]; j++)  // compute_filter, gate.rs:326-333
@@ -794,6 +807,11 @@ extern "C" int qp_program_create(const qp_gate_desc* gates, size_t n_gates, unsi
         else R.memo.clear();
     }
     compile(R, p);
+    for (uint64_t w : native_words) {  // a segment of its own (the library closes the last segment)
+        if (!p->code.empty()) p->code.push_back(END);
+        p->segments.push_back((uint32_t)p->code.size());
+        p->code.push_back(w);
+    }
     *out = p;
     return QP_OK;
 }

@@ -21,7 +21,8 @@ P = 0xFFFFFFFF00000001
 MULTIPLICATIVE_GROUP_GENERATOR = 14293326489335486720  # field/src/goldilocks_field.rs:84
 UNUSED_SELECTOR = 0xFFFFFFFF  # core/src/selectors.rs
 
-OP_END, OP_LDW, OP_LDK, OP_LDP, OP_LDI, OP_ADD, OP_SUB, OP_MUL, OP_EMIT, OP_GATE, OP_MULI, OP_ADDI, OP_WAIT, OP_FMAI = range(14)
+(OP_END, OP_LDW, OP_LDK, OP_LDP, OP_LDI, OP_ADD, OP_SUB, OP_MUL, OP_EMIT, OP_GATE, OP_MULI, OP_ADDI, OP_WAIT, OP_FMAI,
+ OP_NATIVE_POSEIDON) = range(15)
 
 
 def encode_word(op, dst=0, a=0, b=0, c=0):

@@ -35,6 +35,20 @@ def run_program(code, pool, n_regs, wires, consts, pih, alphas):
         if op == plonk.OP_END:     # segments are self-contained: no register survives an END
             assert not in_flight and h == [0] * nc
             r = [None] * n_regs
+        elif op == plonk.OP_NATIVE_POSEIDON:
+            # a PoseidonGate handed to the device's native evaluator: dst = group end, a = gate index,
+            # b = group start, c = selector column | many_selectors << 16 (quotient.cuh)
+            sel = int(consts[c & 0xFFFF])
+            f = 1
+            for j in range(b, dst):
+                if j != a:
+                    f = f * (j - sel) % P
+            if c >> 16:
+                f = f * (plonk.UNUSED_SELECTOR - sel) % P
+            cons = plonk.PoseidonGate().eval_unfiltered(None, lambda k: plonk.ModP(wires[k]), None)
+            for q in range(nc):
+                acc = sum(int(v) * pow(int(alphas[q]), k, P) for k, v in enumerate(cons)) % P
+                G[q] = (G[q] + f * acc) % P
         elif op == plonk.OP_WAIT:
             for d, x in in_flight:
                 assert r[d] is None
@@ -245,8 +259,11 @@ def test_native_program_sorts_gates_like_the_builder():
     # between constraints) and loads with distant uses are repeated instead of pinning registers:
     # BaseSumGate alone would need 65
     ends = [i for i, w in enumerate(prog["code"]) if int(w) & 0xFF == plonk.OP_END]
-    assert list(prog["segments"]) == [0] + [e + 1 for e in ends] and len(ends) >= 4
-    sizes = np.diff([0] + ends + [len(prog["code"])])
+    assert list(prog["segments"]) == [0] + [e + 1 for e in ends] and len(ends) >= 3
+    # PoseidonGate is not compiled: one word, a segment of its own, for the device's native evaluator
+    op, dst, a, b, c = plonk.decode_word(prog["code"][-1])
+    assert (op, dst, a, b, c) == (plonk.OP_NATIVE_POSEIDON, 14, 13, 13, 3 | 1 << 16)
+    sizes = np.diff([0] + ends)
     assert sizes.max() < 3 * sizes.min() and prog["n_regs"] <= 40
     g = plonk.RandomAccessGate.new_from_config(143, 80, 4)      # random_access.rs:58-76 under the standard config
     assert (g.num_copies, g.num_extra_constants, g.degree, g.num_constraints) == (4, 2, 5, 26)
