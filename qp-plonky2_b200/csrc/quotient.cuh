@@ -122,7 +122,7 @@ __host__ __device__ inline size_t smem_words(unsigned pool_len, unsigned n_regs)
 // One thread per point of the quotient domain, enumerated in leaf order.  The work of a point is
 // 1 + n_seg independent units -- the permutation terms and the segments of the gate program --
 // dealt round-robin over blockIdx.y, so that a 2^12-row circuit (256 tiles) still fills 148 SMs.
-__global__ void __launch_bounds__(BLOCK) quotient_kernel(Params p) {
+__global__ void __launch_bounds__(BLOCK, 6) quotient_kernel(Params p) {
     extern __shared__ uint64_t smem[];
     uint64_t* const sh_pool = smem;
     uint64_t* const regs = sh_pool + p.pool_len;  // [n_regs][BLOCK]

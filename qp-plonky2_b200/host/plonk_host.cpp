@@ -516,9 +516,18 @@ struct Scheduler {
     std::vector<int> val_of;      // node -> current value id (-1: not computed in this piece)
     std::vector<int> touched_at;  // node -> step index of its last use (leaves)
     std::vector<int> uses;        // node -> number of consumers inside this piece
+    std::vector<uint32_t> weight; // node -> size of its expression tree (saturating): which operand goes first
     int n_vals = 0;
     Scheduler(const Recorder& r, const std::vector<Recorder::Action>& acts)
-        : R(r), val_of(r.nodes.size(), -1), touched_at(r.nodes.size(), -1), uses(r.nodes.size(), 0) {
+        : R(r), val_of(r.nodes.size(), -1), touched_at(r.nodes.size(), -1), uses(r.nodes.size(), 0),
+          weight(r.nodes.size(), 1) {
+        // operands were recorded before their consumers, so one pass in index order sizes every tree
+        for (size_t i = 0; i < r.nodes.size(); i++) {
+            const auto& nd = r.nodes[i];
+            if (is_leaf(nd.op)) continue;
+            uint64_t w = 1 + (uint64_t)weight[nd.a] + (is_unary(nd.op) ? 0 : weight[nd.b]);
+            weight[i] = (uint32_t)std::min<uint64_t>(w, 1u << 30);
+        }
         std::vector<char> seen(r.nodes.size(), 0);
         std::vector<int> stack;
         for (const auto& a : acts) {
@@ -572,14 +581,18 @@ struct Scheduler {
                 if (!is_leaf(R.nodes[k].op) && val_of[k] < 0) stack.push_back({k, false});
             };
             if (!done) {
+                // the operand with the larger expression goes first (it is popped last-pushed-first):
+                // its intermediate values are gone by the time the smaller one is computed, and a long
+                // accumulation chain pulls in its small side terms just in time instead of all up front
                 stack.push_back({i, true});
+                int first = nd.a, second = is_unary(nd.op) ? -1 : nd.b;
                 if (prod >= 0) {
-                    want(prod == nd.a ? nd.b : nd.a);
-                    want(R.nodes[prod].a);
-                } else {
-                    if (!is_unary(nd.op)) want(nd.b);
-                    want(nd.a);
+                    first = R.nodes[prod].a;
+                    second = prod == nd.a ? nd.b : nd.a;
                 }
+                if (second >= 0 && weight[second] > weight[first]) std::swap(first, second);
+                if (second >= 0) want(second);
+                want(first);
                 continue;
             }
             if (prod >= 0) {
