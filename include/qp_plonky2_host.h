@@ -94,6 +94,17 @@ typedef struct {
 #define QP_PROGRAM_LOAD_LEAD 3
 typedef struct qp_program qp_program;
 int qp_program_create(const qp_gate_desc* gates, size_t n_gates, unsigned max_degree, qp_program** out);
+/* The same compiler on a recording made elsewhere (a Rust shim's recording field type run over
+ * Gate::eval_unfiltered_base_one, or qp-plonky2_b200/plonk.py): nodes in creation order (operands
+ * before their consumers), ops numbered like the program's (include/qp_plonky2_b200.h):
+ *   LDW / LDK: a = column; LDP: a = index into public_inputs_hash; LDI: a = pool slot;
+ *   ADD / SUB / MUL: a, b = nodes; MULI / ADDI: a = node, b = pool slot.
+ * actions: every gate's EMITs (node = the constraint's value, k = its index in the gate) followed
+ * by one GATE (node = the gate's filter).  The gate accessors below are empty for such a program. */
+typedef struct { uint32_t op, a, b; } qp_dag_node;
+typedef struct { uint32_t op, node, k; } qp_dag_action;
+int qp_program_from_dag(const qp_dag_node* nodes, size_t n_nodes, const uint64_t* pool, size_t pool_len,
+                        const qp_dag_action* actions, size_t n_actions, qp_program** out);
 void qp_program_free(qp_program* p);
 size_t qp_program_code(const qp_program* p, const uint64_t** code);
 size_t qp_program_pool(const qp_program* p, const uint64_t** pool);

@@ -200,6 +200,7 @@ def lib():
         "qp_memcpy": (i32, [vp, vp, i32, vp, i32, sz]),
         # host side of the quotient / prove (include/qp_plonky2_host.h)
         "qp_program_create": (i32, [vp, sz, u32, pp]),
+        "qp_program_from_dag": (i32, [vp, sz, vp, sz, vp, sz, pp]),
         "qp_program_free": (None, [vp]),
         "qp_program_code": (sz, [vp, pp]),
         "qp_program_pool": (sz, [vp, pp]),

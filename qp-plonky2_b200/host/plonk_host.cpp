@@ -829,6 +829,43 @@ extern "C" int qp_program_create(const qp_gate_desc* gates, size_t n_gates, unsi
     return QP_OK;
 }
 
+// The compiler on somebody else's recording: a shim (or the Python twin) that ran the gates'
+// eval_unfiltered over its own recording type hands over the node list and gets the same
+// scheduling, segments and register allocation as the built-in gates.
+extern "C" int qp_program_from_dag(const qp_dag_node* nodes, size_t n_nodes, const uint64_t* pool, size_t pool_len,
+                                   const qp_dag_action* actions, size_t n_actions, qp_program** out) {
+    if (!out || (n_nodes && !nodes) || (n_actions && !actions) || (pool_len && !pool)) return QP_ERR_BAD_ARG;
+    *out = nullptr;
+    Recorder R;
+    R.pool.assign(pool, pool + pool_len);
+    for (size_t i = 0; i < n_nodes; i++) {
+        const qp_dag_node& nd = nodes[i];
+        bool ok = false;
+        switch (nd.op) {
+            case LDW: case LDK: ok = true; break;
+            case LDP: ok = nd.a < 4; break;
+            case LDI: ok = nd.a < pool_len; break;
+            case ADD: case SUB: case MUL: ok = nd.a < i && nd.b < i; break;   // operands before consumers
+            case MULI: case ADDI: ok = nd.a < i && nd.b < pool_len; break;
+            default: break;
+        }
+        if (!ok) return QP_ERR_BAD_ARG;
+        R.nodes.push_back({nd.op, (int)nd.a, (int)nd.b});
+    }
+    bool open_gate = false;
+    for (size_t i = 0; i < n_actions; i++) {
+        const qp_dag_action& a = actions[i];
+        if ((a.op != EMIT && a.op != GATE) || a.node >= n_nodes || a.k >= 65536) return QP_ERR_BAD_ARG;
+        R.actions.push_back({a.op, (int)a.node, a.k});
+        open_gate = a.op == EMIT;
+    }
+    if (open_gate) return QP_ERR_BAD_ARG;  // constraints without a closing GATE (filter)
+    auto* p = new qp_program();
+    compile(R, p);
+    *out = p;
+    return QP_OK;
+}
+
 extern "C" void qp_program_free(qp_program* p) { delete p; }
 extern "C" size_t qp_program_code(const qp_program* p, const uint64_t** code) {
     if (code) *code = p->code.data();

@@ -123,6 +123,28 @@ class ConstraintProgram:
         # register until the last gate that reads it
         self.memo = {}
 
+    def compile_native(self):
+        """The recording handed to the native compiler (qp_program_from_dag, host/plonk_host.cpp): the
+        scheduling, segmentation and register allocation the device wants.  -> (code, pool, n_regs)"""
+        from . import lib
+        nodes = np.array([(op, a, b) for op, a, b in self.nodes], dtype=np.uint32).reshape(-1, 3)
+        acts = np.array([(op, node, k) for op, node, k in self.actions], dtype=np.uint32).reshape(-1, 3)
+        pool = np.array(self.pool or [0], dtype=np.uint64)
+        h = C.c_void_p()
+        rc = lib().qp_program_from_dag(nodes.ctypes.data, len(nodes), pool.ctypes.data, len(pool), acts.ctypes.data,
+                                       len(acts), C.byref(h))
+        if rc:
+            raise ValueError("qp_program_from_dag failed (%d)" % rc)
+        try:
+            ptr = C.c_void_p()
+            n = lib().qp_program_code(h, C.byref(ptr))
+            code = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+            n = lib().qp_program_pool(h, C.byref(ptr))
+            out_pool = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), shape=(n,)).copy()
+            return code, out_pool, int(lib().qp_program_regs(h))
+        finally:
+            lib().qp_program_free(h)
+
     def compile(self):
         """-> (code uint64[], pool uint64[], n_regs).  Nodes are scheduled lazily in action order
         and registers are reused after a node's last use."""
@@ -994,8 +1016,9 @@ class CommonCircuitData:
     def gate_index(self, gate_id):
         return next(i for i, g in enumerate(self.gates) if g.id() == gate_id)
 
-    def constraint_program(self):
-        """evaluate_gate_constraints_base_batch (vanishing_poly.rs:700-726) as a program."""
+    def constraint_program(self, native_compile=False):
+        """evaluate_gate_constraints_base_batch (vanishing_poly.rs:700-726) as a program.  With
+        `native_compile` the recording made here goes through the native compiler."""
         prog = ConstraintProgram()
         prefix = self.num_selectors + self.num_lookup_selectors  # gate.rs:179 remove_prefix
         for i, g in enumerate(self.gates):
@@ -1013,7 +1036,7 @@ class CommonCircuitData:
             assert len(cons) == g.num_constraints
             if cons:
                 prog.emit_gate(cons, filt)
-        return prog.compile()
+        return prog.compile_native() if native_compile else prog.compile()
 
 
 class _GateDesc(C.Structure):
@@ -1069,14 +1092,18 @@ class Circuit:
     """Device-resident circuit data: k_is, sigmas (prover_data.sigmas as columns), the compiled
     gate program.  One per circuit, like ProverOnlyCircuitData."""
 
-    def __init__(self, ctx, common, sigmas=None):
+    def __init__(self, ctx, common, sigmas=None, program_source="native"):
+        """program_source: "native" = the host library records and compiles the gates (qp_program_create);
+        "dag" = this module's recording, compiled by the host library (qp_program_from_dag -- the route
+        of a shim with gates the library does not know); "twin" = recorded and compiled here."""
         from . import _buf, lib  # late: this module is imported by the package
         self.ctx, self.common = ctx, common
-        # the native host compiler produces the program the device runs; the Python
-        # `constraint_program` is the readable mirror the CPU tests compare it with
-        native = native_constraint_program(common.gates, common.quotient_degree_factor + 1)
-        assert native["selector_indices"] == common.selector_indices and native["groups"] == common.groups
-        code, pool, n_regs = native["code"], native["pool"], native["n_regs"]
+        if program_source == "native":
+            native = native_constraint_program(common.gates, common.quotient_degree_factor + 1)
+            assert native["selector_indices"] == common.selector_indices and native["groups"] == common.groups
+            code, pool, n_regs = native["code"], native["pool"], native["n_regs"]
+        else:
+            code, pool, n_regs = common.constraint_program(native_compile=program_source == "dag")
         self.program = (code, pool, n_regs)
         k_is = np.ascontiguousarray(common.k_is, dtype=np.uint64)
         d = _Desc()

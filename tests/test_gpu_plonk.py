@@ -202,3 +202,23 @@ def test_device_proof_is_accepted_by_the_restated_verifier(qp, ctx, degree_bits,
     bad = bytearray(proof)
     bad[len(bad) // 2] ^= 4
     assert verifier.verify(bytes(bad), c, pd.fri, cap, pd.circuit_digest) is not None
+
+
+@pytest.mark.parametrize("source", ["dag", "twin"])
+def test_quotient_from_an_external_recording(qp, ctx, source):
+    """The device runs any valid program: the gates recorded by the Python mirror and compiled by the
+    host library (qp_program_from_dag -- what a shim with its own gates does), or recorded AND compiled
+    by the mirror (a WAIT after every load, no segments), give the oracle's quotient -- with
+    PoseidonGate interpreted, not native."""
+    sc = SynthCircuit(6, seed=21, poseidon=True, extra_gates=True, recursion_gates=True)
+    c = sc.common
+    circ = plonk.Circuit(ctx, c, sc.sigmas, program_source=source)
+    betas, gammas, alphas = [11, 12], [13, 14], [15, 16]
+    zs = circ.partial_products_and_zs(sc.wires, betas, gammas)
+    g_cs = qp.PolynomialBatch.from_values(ctx, sc.constants_sigmas(), c.rate_bits, False, c.cap_height)
+    g_w = qp.PolynomialBatch.from_values(ctx, sc.wires, c.rate_bits, False, c.cap_height)
+    g_z = qp.PolynomialBatch.from_values(ctx, zs, c.rate_bits, False, c.cap_height)
+    got = circ.compute_quotient_polys(g_cs, g_w, g_z, betas, gammas, alphas, sc.public_inputs_hash)
+    ref = plonk.Circuit(ctx, c, sc.sigmas)
+    want = ref.compute_quotient_polys(g_cs, g_w, g_z, betas, gammas, alphas, sc.public_inputs_hash)
+    assert (got == want).all()

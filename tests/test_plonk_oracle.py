@@ -95,7 +95,7 @@ def test_selectors_info_matches_reference_rule(qdf):
     assert c.num_partial_products == -(-80 // qdf) - 1
 
 
-@pytest.mark.parametrize("native", [False, True])
+@pytest.mark.parametrize("native", [False, True, "dag"])
 @pytest.mark.parametrize("qdf,poseidon,extra,rec", [(8, False, False, False), (4, False, False, False),
                                                     (8, True, False, False), (8, True, True, False),
                                                     (4, False, True, False), (8, True, True, True),
@@ -107,7 +107,10 @@ def test_constraint_program_matches_oracle_gate_evaluation(qdf, poseidon, native
     sc = SynthCircuit(5, seed=5, quotient_degree_factor=qdf, poseidon=poseidon, extra_gates=extra,
                       recursion_gates=rec)
     c = sc.common
-    if native:   # qp-plonky2_b200/host/plonk_host.cpp, the compiler whose output the device runs
+    if native == "dag":   # this module's recording of the gates through the native compiler (qp_program_from_dag)
+        code, pool, n_regs = c.constraint_program(native_compile=True)
+        assert any(int(w) & 0xFF == plonk.OP_FMAI for w in code) or not (poseidon or extra or rec)
+    elif native:   # qp-plonky2_b200/host/plonk_host.cpp, the compiler whose output the device runs
         prog = plonk.native_constraint_program(c.gates, qdf + 1)
         code, pool, n_regs = prog["code"], prog["pool"], prog["n_regs"]
         assert prog["selector_indices"] == c.selector_indices and prog["groups"] == c.groups
