@@ -148,6 +148,30 @@ size_t qp_tree_digests_len(const qp_tree* t);
 int qp_tree_prove(const qp_tree* t, size_t leaf_index, uint64_t* siblings_out);
 int qp_tree_get(const qp_tree* t, size_t leaf_index, uint64_t* out); /* MerkleTree::get */
 
+/* ---- BatchFriOracle::from_values / from_coeffs (plonky2/src/batch_fri/oracle.rs:78-160) ----------
+ * The commitment of batch FRI: polynomials of non-increasing power-of-two length; every run of equal
+ * length is one PolynomialBatch-style LDE (leaf order), and the runs are the matrices of one
+ * BatchMerkleTree (below), tallest first.  polys[i]: 2^degree_bits[i] values / coefficients.
+ * Errors: QP_ERR_BAD_ARG (empty, lengths increasing, blinding != 0: salt injection is not implemented
+ * for batch oracles), QP_ERR_CAP_HEIGHT, QP_ERR_TOO_LARGE. */
+typedef struct qp_batch_fri qp_batch_fri;
+int qp_batch_fri_from_values(qp_ctx* ctx, const uint64_t* const* polys, const unsigned* degree_bits, size_t n_polys,
+                             int space, unsigned rate_bits, int blinding, unsigned cap_height, qp_batch_fri** out);
+int qp_batch_fri_from_coeffs(qp_ctx* ctx, const uint64_t* const* polys, const unsigned* degree_bits, size_t n_polys,
+                             int space, unsigned rate_bits, int blinding, unsigned cap_height, qp_batch_fri** out);
+void qp_batch_fri_free(qp_batch_fri* o);
+size_t qp_batch_fri_num_groups(const qp_batch_fri* o);                 /* = degree_bits.len() after dedup */
+/* group g (tallest first): its degree_bits and number of polynomials (= leaf width of its matrix) */
+int qp_batch_fri_group(const qp_batch_fri* o, size_t g, unsigned* degree_bits, size_t* n_polys);
+int qp_batch_fri_coeffs(const qp_batch_fri* o, size_t g, uint64_t* out, int space);   /* [n_polys][2^degree_bits] */
+int qp_batch_fri_cap(const qp_batch_fri* o, uint64_t* out, int space);                /* [2^cap_height][4] */
+size_t qp_batch_fri_digests_len(const qp_batch_fri* o);
+int qp_batch_fri_digests(const qp_batch_fri* o, uint64_t* out, int space);
+/* batch_merkle_tree.open_batch(leaf_index): log2(N_0) - cap_height siblings */
+int qp_batch_fri_open(const qp_batch_fri* o, size_t leaf_index, uint64_t* siblings_out);
+/* batch_merkle_tree.values(leaf_index): every group's row, concatenated (host) */
+int qp_batch_fri_values(const qp_batch_fri* o, size_t leaf_index, uint64_t* out);
+
 /* ---- BatchMerkleTree::new (plonky2/src/hash/batch_merkle_tree.rs:40-130) ---------------------
  * One tree over several matrices of strictly decreasing power-of-two heights (the oracle of
  * batch FRI): the tree over the tallest matrix is capped at the height of the next one, whose rows

@@ -254,6 +254,24 @@ def batch_from_coeffs(coeffs, rate_bits, cap_height, salt=None):
     return leaves, digests, cap
 
 
+def batch_fri_from_coeffs(polys, rate_bits, cap_height):
+    """BatchFriOracle::from_coeffs (plonky2/src/batch_fri/oracle.rs:105-160) without blinding:
+    polynomials of non-increasing length; every run of equal length is extended onto the coset,
+    transposed and bit-reversed into one leaf matrix; the matrices go to BatchMerkleTree::new.
+    -> (leaf matrices, digests, cap, degree_bits tallest first)"""
+    lens = [len(p) for p in polys]
+    assert all(a >= b for a, b in zip(lens, lens[1:]))
+    mats, start = [], 0
+    for i in range(len(polys)):
+        if i == len(polys) - 1 or lens[i] > lens[i + 1]:
+            lde = [lde_onto_coset(c, rate_bits) for c in polys[start:i + 1]]
+            bits = len(lde[0]).bit_length() - 1
+            mats.append([[col[bitrev(r, bits)] for col in lde] for r in range(len(lde[0]))])
+            start = i + 1
+    digests, cap, _ = batch_merkle_tree(mats, cap_height)
+    return mats, digests, cap, sorted({n.bit_length() - 1 for n in lens}, reverse=True)
+
+
 # ----- Challenger (core/src/challenger.rs) -------------------------------------------------
 class Challenger:
     def __init__(self):

@@ -189,6 +189,17 @@ def lib():
         "qp_batch_serialized_len": (sz, [vp]),
         "qp_batch_serialize": (i32, [vp, vp, sz]),
         "qp_batch_deserialize": (i32, [vp, vp, sz, pp, C.POINTER(sz)]),
+        "qp_batch_fri_from_values": (i32, [vp, vp, vp, sz, i32, u32, i32, u32, pp]),
+        "qp_batch_fri_from_coeffs": (i32, [vp, vp, vp, sz, i32, u32, i32, u32, pp]),
+        "qp_batch_fri_free": (None, [vp]),
+        "qp_batch_fri_num_groups": (sz, [vp]),
+        "qp_batch_fri_group": (i32, [vp, sz, C.POINTER(u32), C.POINTER(sz)]),
+        "qp_batch_fri_coeffs": (i32, [vp, sz, vp, i32]),
+        "qp_batch_fri_cap": (i32, [vp, vp, i32]),
+        "qp_batch_fri_digests_len": (sz, [vp]),
+        "qp_batch_fri_digests": (i32, [vp, vp, i32]),
+        "qp_batch_fri_open": (i32, [vp, sz, vp]),
+        "qp_batch_fri_values": (i32, [vp, sz, vp]),
         "qp_batch_merkle_tree_new": (i32, [vp, vp, i32, vp, vp, sz, u32, pp]),
         "qp_batch_tree_free": (None, [vp]),
         "qp_batch_tree_cap": (i32, [vp, vp, i32]),
@@ -633,6 +644,89 @@ class BatchMerkleTree:
     def free(self):
         if self._h and self.ctx._h:
             lib().qp_batch_tree_free(self._h)
+        self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class BatchFriOracle:
+    """plonky2/src/batch_fri/oracle.rs:30-160 (the commitment; blinding = False): polynomials of
+    non-increasing power-of-two length -> `polynomials` (coefficients), `degree_bits` (deduplicated,
+    tallest first), and the BatchMerkleTree over the per-degree LDE matrices (`cap`, `digests`,
+    `open_batch`, `values`)."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+
+    @classmethod
+    def from_values(cls, ctx, values, rate_bits, blinding, cap_height):
+        return cls._make(ctx, values, rate_bits, blinding, cap_height, True)
+
+    @classmethod
+    def from_coeffs(cls, ctx, polynomials, rate_bits, blinding, cap_height):
+        return cls._make(ctx, polynomials, rate_bits, blinding, cap_height, False)
+
+    @classmethod
+    def _make(cls, ctx, polys, rate_bits, blinding, cap_height, is_values):
+        arrs = [np.ascontiguousarray(np.asarray(p, dtype=np.uint64).ravel()) for p in polys]
+        for a in arrs:
+            if a.size == 0 or a.size & (a.size - 1):
+                raise QpError(3, "Not a power of two: %d" % a.size)
+        self = cls()
+        self.ctx, self.rate_bits, self.cap_height, self.blinding = ctx, rate_bits, cap_height, bool(blinding)
+        n = len(arrs)
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+        bits = (C.c_uint32 * max(n, 1))(*[a.size.bit_length() - 1 for a in arrs])
+        fn = lib().qp_batch_fri_from_values if is_values else lib().qp_batch_fri_from_coeffs
+        ctx.check(fn(ctx._h, ptrs, bits, n, QP_HOST, rate_bits, int(bool(blinding)), cap_height, C.byref(self._h)))
+        self.degree_bits, self.group_sizes = [], []
+        for g in range(int(lib().qp_batch_fri_num_groups(self._h))):
+            d, k = C.c_uint32(), C.c_size_t()
+            lib().qp_batch_fri_group(self._h, g, C.byref(d), C.byref(k))
+            self.degree_bits.append(int(d.value))
+            self.group_sizes.append(int(k.value))
+        return self
+
+    @property
+    def polynomials(self):
+        out = []
+        for g, (d, k) in enumerate(zip(self.degree_bits, self.group_sizes)):
+            co = np.zeros((k, 1 << d), dtype=np.uint64)
+            self.ctx.check(lib().qp_batch_fri_coeffs(self._h, g, _np_ptr(co), QP_HOST))
+            out += list(co)
+        return out
+
+    @property
+    def cap(self):
+        out = np.zeros((1 << self.cap_height, 4), dtype=np.uint64)
+        self.ctx.check(lib().qp_batch_fri_cap(self._h, _np_ptr(out), QP_HOST))
+        return out
+
+    @property
+    def digests(self):
+        out = np.zeros((lib().qp_batch_fri_digests_len(self._h), 4), dtype=np.uint64)
+        if out.size:
+            self.ctx.check(lib().qp_batch_fri_digests(self._h, _np_ptr(out), QP_HOST))
+        return out
+
+    def open_batch(self, leaf_index):
+        k = self.degree_bits[0] + self.rate_bits - self.cap_height
+        out = np.zeros((k, 4), dtype=np.uint64)
+        self.ctx.check(lib().qp_batch_fri_open(self._h, leaf_index, _np_ptr(out) if k else None))
+        return out
+
+    def values(self, leaf_index):
+        out = np.zeros(sum(self.group_sizes), dtype=np.uint64)
+        self.ctx.check(lib().qp_batch_fri_values(self._h, leaf_index, _np_ptr(out)))
+        return np.split(out, np.cumsum(self.group_sizes)[:-1])
+
+    def free(self):
+        if self._h and self.ctx._h:
+            lib().qp_batch_fri_free(self._h)
         self._h = C.c_void_p()
 
     def __del__(self):

@@ -69,6 +69,18 @@ struct ExtPlanesLayout {
     }
 };
 
+// BatchMerkleTree stage leaves straight off a column-major LDE: leaf i = cap[i] (the digest the
+// previous stage left at this height, 4 words) || the columns at row i
+// (plonky2/src/hash/batch_merkle_tree.rs:91-100, batch_fri/oracle.rs:133-147).
+struct CapPrefixLayout {
+    const uint64_t* cap;
+    const uint64_t* data;
+    size_t col_stride;
+    __device__ __forceinline__ uint64_t get(size_t i, unsigned c) const {
+        return c < 4 ? cap[4 * i + c] : data[(size_t)(c - 4) * col_stride + i];
+    }
+};
+
 // One thread per leaf.
 #ifndef QP_LEAF_MIN_BLOCKS
 #define QP_LEAF_MIN_BLOCKS 1

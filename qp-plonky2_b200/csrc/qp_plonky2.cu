@@ -1952,6 +1952,170 @@ extern "C" int qp_batch_tree_values(const qp_batch_tree* t, size_t leaf_index, u
 }
 
 // ---------------------------------------------------------------------------------------------
+// BatchFriOracle::from_values / from_coeffs (plonky2/src/batch_fri/oracle.rs:78-160): one LDE per
+// run of equal-length polynomials, one BatchMerkleTree over the runs.  Group 0 is an ordinary
+// batch whose tree is capped at the next group's height; every later group hashes its LDE rows
+// together with the cap below it (merkle::CapPrefixLayout) -- no leaf-major copy is ever made.
+// ---------------------------------------------------------------------------------------------
+struct qp_batch_fri {
+    qp_ctx* ctx = nullptr;
+    std::vector<qp_batch*> groups;  // coefficients, LDE and the stage tree of every group
+    unsigned rate_bits = 0, cap_height = 0;
+};
+
+extern "C" void qp_batch_fri_free(qp_batch_fri* o) {
+    if (!o) return;
+    for (qp_batch* b : o->groups) qp_batch_free(b);
+    delete o;
+}
+
+static int batch_fri_build(qp_ctx* ctx, qp_batch_fri* o, const uint64_t* const* polys, const unsigned* degree_bits,
+                           size_t n_polys, int space, bool is_values) {
+    size_t start = 0;
+    for (size_t i = 0; i < n_polys; i++) {
+        if (i + 1 < n_polys && degree_bits[i] == degree_bits[i + 1]) continue;
+        const size_t cols = i + 1 - start;
+        const unsigned d = degree_bits[start];
+        const size_t n = (size_t)1 << d;
+        // next group's height decides where this stage's tree stops (batch_merkle_tree.rs:63-70)
+        const unsigned stage_cap = i + 1 < n_polys ? degree_bits[i + 1] + o->rate_bits : o->cap_height;
+        uint64_t* d_coeffs = nullptr;
+        int rc = dev_alloc(ctx, &d_coeffs, cols * n);
+        if (rc) return rc;
+        for (size_t c = 0; c < cols; c++)
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_coeffs + c * n, polys[start + c], n * 8,
+                                          space == QP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                          ctx->stream));
+        if (is_values) {  // "IFFT", oracle.rs:86-90 (out of place: the inverse transform permutes across CTAs)
+            uint64_t* d_vals = d_coeffs;
+            rc = dev_alloc(ctx, &d_coeffs, cols * n);
+            if (!rc) rc = qp_ifft_columns(ctx, d_vals, QP_DEVICE, cols, d, d_coeffs, QP_DEVICE);
+            dev_free(ctx, d_vals);
+            if (rc) {
+                dev_free(ctx, d_coeffs);
+                return rc;
+            }
+        }
+        qp_batch* b = nullptr;
+        if (o->groups.empty()) {
+            rc = batch_from_device_coeffs(ctx, d_coeffs, cols, d, o->rate_bits, 0, stage_cap, nullptr, 0, 1u << o->rate_bits, &b);
+            if (b) o->groups.push_back(b);
+            if (rc) return rc;
+        } else {
+            rc = batch_create(ctx, d_coeffs, cols, d, o->rate_bits, 0, stage_cap, 0, 1u << o->rate_bits, &b);
+            if (b) o->groups.push_back(b);
+            if (!rc) rc = batch_lde_columns(b, 0, cols);
+            if (rc) return rc;
+            const qp_batch* below = o->groups[o->groups.size() - 2];
+            merkle::CapPrefixLayout lay{below->tree.cap, b->lde, b->n_local};
+            rc = hash_leaves(ctx, lay, (unsigned)(cols + 4), &b->tree);
+            if (!rc) rc = build_tree_levels(ctx, &b->tree);
+            if (rc) return rc;
+        }
+        start = i + 1;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return QP_OK;
+}
+
+static int batch_fri_new(qp_ctx* ctx, const uint64_t* const* polys, const unsigned* degree_bits, size_t n_polys, int space,
+                         unsigned rate_bits, int blinding, unsigned cap_height, qp_batch_fri** out, bool is_values) {
+    if (!ctx) return QP_ERR_BAD_ARG;
+    if (!out) return fail(ctx, QP_ERR_BAD_ARG, "null out");
+    *out = nullptr;
+    if (!n_polys || !polys || !degree_bits) return fail(ctx, QP_ERR_BAD_ARG, "no polynomials");
+    if (blinding) return fail(ctx, QP_ERR_BAD_ARG, "salt injection is not implemented for batch oracles");
+    for (size_t i = 0; i < n_polys; i++) {
+        if (!polys[i]) return fail(ctx, QP_ERR_BAD_ARG, "null polynomial");
+        if (i && degree_bits[i - 1] < degree_bits[i])  // oracle.rs:118
+            return fail(ctx, QP_ERR_BAD_ARG, "polynomials must be sorted by degree, largest first");
+        if (degree_bits[i] + rate_bits > ctx->tw_lg) return fail(ctx, QP_ERR_TOO_LARGE, "LDE larger than the context's max_lde_log");
+    }
+    if (cap_height > degree_bits[n_polys - 1] + rate_bits)
+        return fail(ctx, QP_ERR_CAP_HEIGHT, "cap_height should be at most last_leaves_cap_height");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    qp_batch_fri* o = new qp_batch_fri();
+    o->ctx = ctx;
+    o->rate_bits = rate_bits;
+    o->cap_height = cap_height;
+    const int rc = batch_fri_build(ctx, o, polys, degree_bits, n_polys, space, is_values);
+    if (rc) {
+        qp_batch_fri_free(o);
+        return rc;
+    }
+    *out = o;
+    return QP_OK;
+}
+
+extern "C" int qp_batch_fri_from_values(qp_ctx* ctx, const uint64_t* const* polys, const unsigned* degree_bits,
+                                        size_t n_polys, int space, unsigned rate_bits, int blinding, unsigned cap_height,
+                                        qp_batch_fri** out) {
+    return batch_fri_new(ctx, polys, degree_bits, n_polys, space, rate_bits, blinding, cap_height, out, true);
+}
+extern "C" int qp_batch_fri_from_coeffs(qp_ctx* ctx, const uint64_t* const* polys, const unsigned* degree_bits,
+                                        size_t n_polys, int space, unsigned rate_bits, int blinding, unsigned cap_height,
+                                        qp_batch_fri** out) {
+    return batch_fri_new(ctx, polys, degree_bits, n_polys, space, rate_bits, blinding, cap_height, out, false);
+}
+extern "C" size_t qp_batch_fri_num_groups(const qp_batch_fri* o) { return o ? o->groups.size() : 0; }
+extern "C" int qp_batch_fri_group(const qp_batch_fri* o, size_t g, unsigned* degree_bits, size_t* n_polys) {
+    if (!o || g >= o->groups.size()) return QP_ERR_BAD_ARG;
+    if (degree_bits) *degree_bits = o->groups[g]->degree_log;
+    if (n_polys) *n_polys = o->groups[g]->n_cols;
+    return QP_OK;
+}
+extern "C" int qp_batch_fri_coeffs(const qp_batch_fri* o, size_t g, uint64_t* out, int space) {
+    if (!o || g >= o->groups.size()) return QP_ERR_BAD_ARG;
+    return qp_batch_coeffs(o->groups[g], out, space);
+}
+extern "C" int qp_batch_fri_cap(const qp_batch_fri* o, uint64_t* out, int space) {
+    if (!o) return QP_ERR_BAD_ARG;
+    const TreeBuf& t = o->groups.back()->tree;
+    return copy_out(o->ctx, out, space, t.cap, t.n_cap() * 4);
+}
+extern "C" size_t qp_batch_fri_digests_len(const qp_batch_fri* o) {
+    size_t n = 0;
+    if (o)
+        for (const qp_batch* b : o->groups) n += b->tree.n_digests();
+    return n;
+}
+extern "C" int qp_batch_fri_digests(const qp_batch_fri* o, uint64_t* out, int space) {
+    if (!o) return QP_ERR_BAD_ARG;
+    size_t pos = 0;
+    for (const qp_batch* b : o->groups) {
+        int rc = copy_out(o->ctx, out + pos, space, b->tree.digests, b->tree.n_digests() * 4);
+        if (rc) return rc;
+        pos += b->tree.n_digests() * 4;
+    }
+    return QP_OK;
+}
+extern "C" int qp_batch_fri_open(const qp_batch_fri* o, size_t leaf_index, uint64_t* siblings_out) {
+    if (!o) return QP_ERR_BAD_ARG;
+    const unsigned lg0 = o->groups[0]->tree.shape.lg_leaves;
+    if (leaf_index >> lg0) return fail(o->ctx, QP_ERR_BAD_ARG, "leaf index out of range");
+    size_t pos = 0;
+    for (const qp_batch* b : o->groups) {  // batch_merkle_tree.rs:139-150
+        int rc = tree_prove(o->ctx, b->tree, leaf_index >> (lg0 - b->tree.shape.lg_leaves), siblings_out + pos);
+        if (rc) return rc;
+        pos += 4 * (size_t)b->tree.shape.num_layers();
+    }
+    return QP_OK;
+}
+extern "C" int qp_batch_fri_values(const qp_batch_fri* o, size_t leaf_index, uint64_t* out) {
+    if (!o) return QP_ERR_BAD_ARG;
+    const unsigned lg0 = o->groups[0]->tree.shape.lg_leaves;
+    if (leaf_index >> lg0) return fail(o->ctx, QP_ERR_BAD_ARG, "leaf index out of range");
+    size_t pos = 0;
+    for (const qp_batch* b : o->groups) {
+        int rc = batch_gather(b, nullptr, leaf_index >> (lg0 - b->tree.shape.lg_leaves), 1, (unsigned)b->n_cols, out + pos,
+                              QP_HOST);
+        if (rc) return rc;
+        pos += b->n_cols;
+    }
+    return QP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Plonk permutation argument and quotient polynomials (quotient.cuh)
 // ---------------------------------------------------------------------------------------------
 struct qp_circuit {

@@ -642,3 +642,55 @@ def test_polynomial_batch_bytes_round_trip(qp, ctx, lg_n, cols, rate, cap_h, sal
     bad[0] ^= 1                  # the polynomial count
     with pytest.raises(qp.QpError):
         qp.PolynomialBatch.from_bytes(ctx, bytes(bad))
+
+
+# ---- BatchFriOracle -----------------------------------------------------------
+
+@pytest.mark.parametrize("lens,rate,cap_h,from_values", [([64, 64, 64, 16, 16, 8], 3, 2, False), ([32, 32, 4], 1, 0, True),
+                                                        ([128], 3, 4, True), ([256, 256, 64, 64, 64, 64, 64], 2, 4, True),
+                                                        ([1 << 12] * 20 + [1 << 10] * 9 + [1 << 7] * 3, 3, 4, False)])
+def test_batch_fri_oracle_parity(qp, ctx, lens, rate, cap_h, from_values):
+    """BatchFriOracle::from_values / from_coeffs (plonky2/src/batch_fri/oracle.rs:78-160): per-degree
+    LDEs in leaf order under one BatchMerkleTree -- cap, every digest, coefficients, rows and
+    openings against the big-integer restatement (small cases) / its verifier (all cases)."""
+    rng = np.random.default_rng(sum(lens) + rate)
+    polys = [rng.integers(0, P, size=n, dtype=np.uint64) for n in lens]
+    o = (qp.BatchFriOracle.from_values if from_values else qp.BatchFriOracle.from_coeffs)(ctx, polys, rate, False, cap_h)
+    assert o.degree_bits == sorted({n.bit_length() - 1 for n in lens}, reverse=True)
+    coeffs = [pyref.ifft(p.tolist()) for p in polys] if from_values and max(lens) <= 256 else None
+    if not from_values:
+        coeffs = [p.tolist() for p in polys]
+    got_polys = o.polynomials
+    if coeffs is not None:
+        assert [c.tolist() for c in got_polys] == coeffs
+    heights = [d + rate for d in o.degree_bits]
+    cap = o.cap.tolist()
+    if max(lens) <= 256:
+        mats, digests, want_cap, want_bits = pyref.batch_fri_from_coeffs(coeffs, rate, cap_h)
+        assert o.digests.tolist() == [list(d) for d in digests] and cap == [list(c) for c in want_cap]
+        assert want_bits == o.degree_bits
+    N = lens[0] << rate
+    g, w = pyref.GENERATOR, pyref.primitive_root_of_unity(heights[0])
+    for i in sorted({0, N - 1, int(rng.integers(0, N))}):
+        rows = [[int(x) for x in r] for r in o.values(i)]
+        proof = [list(map(int, s)) for s in o.open_batch(i)]
+        assert pyref.batch_merkle_verify(rows, heights, i, cap, proof)
+        # a row of the tallest group is that group's polynomials at g w^bitrev(i) (get_lde_values)
+        x = g * pow(w, pyref.bitrev(i, heights[0]), P) % P
+        acc = 0
+        for ci in reversed(got_polys[0].tolist()):
+            acc = (acc * x + ci) % P
+        assert rows[0][0] == acc
+    o.free()
+
+
+def test_batch_fri_oracle_errors(qp, ctx):
+    z = lambda n: np.zeros(n, dtype=np.uint64)
+    with pytest.raises(qp.QpError):
+        qp.BatchFriOracle.from_coeffs(ctx, [z(8), z(16)], 1, False, 0)     # degrees must not increase (oracle.rs:118)
+    with pytest.raises(qp.QpError):
+        qp.BatchFriOracle.from_coeffs(ctx, [z(16), z(4)], 1, False, 4)     # cap above the shortest matrix
+    with pytest.raises(qp.QpError):
+        qp.BatchFriOracle.from_coeffs(ctx, [z(16)], 1, True, 0)            # blinding: not implemented
+    with pytest.raises(qp.QpError):
+        qp.BatchFriOracle.from_coeffs(ctx, [z(12)], 1, False, 0)           # not a power of two

@@ -358,3 +358,22 @@ def test_batch_merkle_tree_restatement():
             bad = [list(r) for r in rows]
             bad[1][0] ^= 1
             assert not pyref.batch_merkle_verify(bad, heights, i, cap, proof)
+
+
+def test_batch_fri_oracle_restatement():
+    """BatchFriOracle::from_coeffs (plonky2/src/batch_fri/oracle.rs:105-160): with a single degree it is
+    PolynomialBatch::from_coeffs (same leaves, digests, cap); with several, every row opens against
+    the cap through verify_batch_merkle_proof_to_cap."""
+    from oracle import pyref
+
+    rng = np.random.default_rng(9)
+    polys = [rng.integers(0, P, size=8, dtype=np.uint64).tolist() for _ in range(3)]
+    mats, digests, cap, bits = pyref.batch_fri_from_coeffs(polys, 2, 1)
+    leaves, d1, c1 = pyref.batch_from_coeffs(polys, 2, 1)
+    assert mats == [leaves] and digests == d1 and cap == c1 and bits == [3]
+    polys += [rng.integers(0, P, size=2, dtype=np.uint64).tolist()]
+    mats, digests, cap, bits = pyref.batch_fri_from_coeffs(polys, 2, 1)
+    assert bits == [3, 1] and [len(m) for m in mats] == [32, 8] and [len(m[0]) for m in mats] == [3, 1]
+    for i in range(32):
+        rows = [mats[0][i], mats[1][i >> 2]]
+        assert pyref.batch_merkle_verify(rows, [5, 3], i, cap, pyref.batch_merkle_open(i, mats, 1, digests))
