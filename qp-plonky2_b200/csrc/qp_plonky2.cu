@@ -1788,9 +1788,11 @@ extern "C" int qp_fri_proof_of_work(qp_ctx* ctx, const uint64_t state12[12], uns
     CUDA_TRY(ctx, cudaMemcpyAsync(d_state, state12, 96, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(d_found, 0xff, 8, ctx->stream));
     // Batches in increasing candidate order; the first batch with a hit contains the global
-    // minimum.  A batch is 64 times the expected work 2^min_leading_zeros (at least 2^20): the
-    // kernel's blocks stop once a smaller witness exists, so a large batch costs nothing extra.
-    uint64_t batch = (uint64_t)1 << (min_leading_zeros + 6 < 20 ? 20 : (min_leading_zeros + 6 > 26 ? 26 : min_leading_zeros + 6));
+    // minimum.  A batch is 8 times the expected work 2^min_leading_zeros (a miss has probability
+    // e^-8; at least 2^17 = one wave): the kernel's blocks stop once a smaller witness exists, but
+    // every launched block still costs a few nanoseconds to retire (2^22 candidates: 0.14 ms).
+    const unsigned lg_batch = min_leading_zeros + 3 < 17 ? 17 : (min_leading_zeros + 3 > 26 ? 26 : min_leading_zeros + 3);
+    uint64_t batch = (uint64_t)1 << lg_batch;
     uint64_t base = 0;
     uint64_t found = UINT64_MAX;
     while (true) {
