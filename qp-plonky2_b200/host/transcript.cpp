@@ -15,29 +15,93 @@ namespace {
 typedef unsigned __int128 u128;
 constexpr uint64_t P = 0xFFFFFFFF00000001ULL;
 
-inline uint64_t fmul(uint64_t a, uint64_t b) { return (uint64_t)(((u128)a * b) % P); }
-inline uint64_t fadd(uint64_t a, uint64_t b) { return (uint64_t)(((u128)a + b) % P); }
+constexpr uint64_t EPS = 0xFFFFFFFFULL;  // 2^64 mod p = 2^32 - 1
 
-// Width-12 Poseidon in its defining form (core/src/poseidon.rs:613-633): add constants,
-// x^7 (all lanes in the 4+4 full rounds, lane 0 in the 22 partial ones), MDS.
-void host_permute(uint64_t s[12]) {
-    for (int r = 0; r < 30; r++) {
-        for (int i = 0; i < 12; i++) s[i] = fadd(s[i] % P, POSEIDON_ALL_ROUND_CONSTANTS[12 * r + i]);
-        const int lanes = (r < 4 || r >= 26) ? 12 : 1;
-        for (int i = 0; i < lanes; i++) {
-            uint64_t x = s[i], x2 = fmul(x, x), x4 = fmul(x2, x2);
-            s[i] = fmul(fmul(x, x2), x4);
-        }
-        uint64_t t[12];
-        for (int row = 0; row < 12; row++) {
-            u128 acc = (u128)s[row] * POSEIDON_MDS_DIAG[row];
-            for (int i = 0; i < 12; i++) acc += (u128)s[(i + row) % 12] * POSEIDON_MDS_CIRC[i];
-            t[row] = (uint64_t)(acc % P);
-        }
-        std::memcpy(s, t, sizeof t);
+// The transcript is ~120 serial permutations per proof -- a quarter of a 2^12-row proof's latency
+// with a textbook `% p` permutation -- so the host permutation is written like a CPU prover's:
+// Goldilocks reduction without division or data-dependent branches (field/src/goldilocks_field.rs:
+// 390-403), the MDS layer on 32-bit halves (small entries never carry), the partial rounds in
+// the reference's fast form (core/src/poseidon.rs:584-596).  tools/microbench/host_poseidon_*.cpp.
+inline uint64_t reduce128(u128 x) {   // branch-free: the conditions are data-dependent coin flips
+    const uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
+    const uint64_t hi_hi = hi >> 32, hi_lo = hi & EPS;
+    uint64_t t0 = lo - hi_hi;
+    t0 -= EPS & (0 - (uint64_t)(lo < hi_hi));
+    const uint64_t t1 = hi_lo * EPS;
+    uint64_t r = t0 + t1;
+    r += EPS & (0 - (uint64_t)(r < t1));
+    return r;                          // some representative < 2^64; canonicalised where it matters
+}
+inline uint64_t canon(uint64_t r) { return r - (P & (0 - (uint64_t)(r >= P))); }
+inline uint64_t fmul(uint64_t a, uint64_t b) { return reduce128((u128)a * b); }
+inline uint64_t fadd(uint64_t a, uint64_t b) {   // a any u64, b < p  ->  some representative
+    uint64_t s = a + b;
+    s += EPS & (0 - (uint64_t)(s < a));   // wrapped: + 2^64 = + EPS (cannot wrap again: b < p)
+    return s;
+}
+// lo + hi 2^32 with lo, hi < 2^42 -> mod p  (2^64 = EPS)
+inline uint64_t fold(uint64_t lo, uint64_t hi) {
+    // value = lo + (hi & EPS) 2^32 + (hi >> 32) 2^64
+    const u128 v = (u128)lo + ((u128)(hi & EPS) << 32) + (u128)(hi >> 32) * EPS;
+    const uint64_t l = (uint64_t)v, h = (uint64_t)(v >> 64);  // h <= 1
+    uint64_t r = l + h * EPS;
+    r += EPS & (0 - (uint64_t)(r < l));
+    return r;
+}
+// MDS layer (core/src/poseidon.rs:178-198): circulant with entries < 2^6 plus one diagonal entry.
+// 32-bit halves times small constants never carry: twelve independent 64-bit accumulators per half,
+// no 128-bit carry chains, one fold per row.
+static inline void mds(uint64_t s[12]) {
+    uint64_t lo[24], hi[24];
+    for (int i = 0; i < 12; i++) { lo[i] = lo[i + 12] = s[i] & EPS; hi[i] = hi[i + 12] = s[i] >> 32; }
+#pragma GCC unroll 12
+    for (int r = 0; r < 12; r++) {
+        uint64_t al = 0, ah = 0;
+#pragma GCC unroll 12
+        for (int i = 0; i < 12; i++) { al += lo[r + i] * POSEIDON_MDS_CIRC[i]; ah += hi[r + i] * POSEIDON_MDS_CIRC[i]; }
+        if (r == 0) { al += lo[0] * POSEIDON_MDS_DIAG[0]; ah += hi[0] * POSEIDON_MDS_DIAG[0]; }
+        s[r] = fold(al, ah);
     }
 }
-
+void host_permute(uint64_t s[12]) {
+    // poseidon(), core/src/poseidon.rs:599-609: 4 full rounds, 22 partial rounds in the fast form
+    // (:584-596 -- one S-box, a dot product and a rank-one update per round), 4 full rounds
+    int round = 0;
+    for (int half = 0; half < 2; half++) {
+        for (int r = 0; r < 4; r++, round++) {
+            for (int i = 0; i < 12; i++) s[i] = fadd(s[i], POSEIDON_ALL_ROUND_CONSTANTS[12 * round + i]);
+            for (int i = 0; i < 12; i++) {
+                const uint64_t x = s[i], x2 = fmul(x, x), x4 = fmul(x2, x2);
+                s[i] = fmul(fmul(x, x2), x4);
+            }
+            mds(s);
+        }
+        if (half) break;
+        for (int i = 0; i < 12; i++) s[i] = fadd(s[i], POSEIDON_FAST_PARTIAL_FIRST_ROUND_CONSTANT[i]);  // :304-312
+        {   // mds_partial_layer_init, :339-365
+            u128 acc[12] = {0};
+            for (int r = 1; r < 12; r++) {
+                const uint64_t x = canon(s[r]);
+                for (int c = 1; c < 12; c++)
+                    acc[c] += (u128)reduce128((u128)x * POSEIDON_FAST_PARTIAL_ROUND_INITIAL_MATRIX[(r - 1) * 11 + (c - 1)]);
+            }
+            for (int c = 1; c < 12; c++) s[c] = reduce128(acc[c]);
+        }
+        for (int r = 0; r < 22; r++) {
+            const uint64_t x = s[0], x2 = fmul(x, x), x4 = fmul(x2, x2);
+            const uint64_t s0 = fadd(fmul(fmul(x, x2), x4), POSEIDON_FAST_PARTIAL_ROUND_CONSTANTS[r]);
+            // mds_partial_layer_fast, :378-408
+            u128 d = (u128)reduce128((u128)s0 * (POSEIDON_MDS_CIRC[0] + POSEIDON_MDS_DIAG[0]));
+            for (int j = 1; j < 12; j++) {
+                d += (u128)reduce128((u128)s[j] * POSEIDON_FAST_PARTIAL_ROUND_W_HATS[11 * r + j - 1]);
+                s[j] = reduce128((u128)s0 * POSEIDON_FAST_PARTIAL_ROUND_VS[11 * r + j - 1] + s[j]);
+            }
+            s[0] = reduce128(d);
+        }
+        round += 22;
+    }
+    for (int i = 0; i < 12; i++) s[i] = canon(s[i]);
+}
 void duplexing(qp_challenger* c) {  // challenger.rs:125-140
     for (uint32_t i = 0; i < c->n_in; i++) c->sponge_state[i] = c->input_buffer[i];
     c->n_in = 0;
