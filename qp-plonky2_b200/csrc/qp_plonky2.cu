@@ -39,6 +39,11 @@ struct qp_ctx {
     uint64_t* tw = nullptr;  // tw[(1<<lg)+e] = w_{2^lg}^e, e < 2^lg
     unsigned tw_lg = 0;
     int sm_count = 148;
+    // small device -> host results (caps, openings, Merkle paths) go through pinned memory: a copy
+    // into a pageable buffer is staged by the driver and costs several microseconds more, and a
+    // proof makes dozens of them.  Guarded by `mu`: finished handles may be read from any thread.
+    static constexpr size_t STAGE_WORDS = 32768;
+    uint64_t* stage = nullptr;
     uint64_t launches = 0;
     std::string err;
     std::mutex mu;
@@ -100,6 +105,13 @@ static void dev_free(qp_ctx* ctx, uint64_t* p) {
 static int copy_out(qp_ctx* ctx, uint64_t* dst, int space, const uint64_t* src_dev, size_t n_words) {
     if (!dst) return fail(ctx, QP_ERR_BAD_ARG, "null output buffer");
     if (n_words == 0) return QP_OK;
+    if (space != QP_DEVICE && ctx->stage && n_words <= qp_ctx::STAGE_WORDS) {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage, src_dev, n_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        std::memcpy(dst, ctx->stage, n_words * 8);
+        return QP_OK;
+    }
     CUDA_TRY(ctx, cudaMemcpyAsync(dst, src_dev, n_words * 8,
                                   space == QP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                                   ctx->stream));
@@ -209,6 +221,10 @@ extern "C" int qp_ctx_create(int device, void* stream, unsigned max_lde_log, qp_
         }
         ctx->own_stream = true;
     }
+    if (cudaMallocHost((void**)&ctx->stage, qp_ctx::STAGE_WORDS * 8) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->stage = nullptr;  // not fatal: results are then copied straight into the caller's buffer
+    }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (ctx->sm_count < 1) ctx->sm_count = 148;
     for (auto& e : ctx->ev) cudaEventCreate(&e);
@@ -271,6 +287,7 @@ extern "C" void qp_ctx_destroy(qp_ctx* ctx) {
     for (auto& e : ctx->grp_ev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
     delete ctx;
 }
 
