@@ -127,6 +127,9 @@ int qp_batch_get_leaves(const qp_batch* b, const uint64_t* leaf_indices, unsigne
 int qp_batch_prove(const qp_batch* b, size_t leaf_index, uint64_t* siblings_out);
 /* The same for n leaves in one call: siblings_out[n][lg N - cap_height][4]. */
 int qp_batch_prove_many(const qp_batch* b, const uint64_t* leaf_indices, unsigned n, uint64_t* siblings_out);
+/* qp_batch_get_leaves + qp_batch_prove_many in one round trip (fri_prover_query_rounds, fri/prover.rs:246-253). */
+int qp_batch_open_many(const qp_batch* b, const uint64_t* leaf_indices, unsigned n, uint64_t* rows_out,
+                       uint64_t* siblings_out);
 /* TimingTree scopes (oracle.rs:176-214), milliseconds of device time:
  * [0] "IFFT", [1] "FFT + blinding", [2] "transpose LDEs" (always 0: fused away), [3] "build Merkle tree". */
 int qp_batch_timing(const qp_batch* b, double ms[4]);

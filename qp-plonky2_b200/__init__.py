@@ -185,6 +185,7 @@ def lib():
         "qp_circuit_describe": (i32, [vp, vp]),
         "qp_circuit_has_sigmas": (i32, [vp]),
         "qp_dev_alloc": (i32, [vp, sz, pp]),
+        "qp_batch_open_many": (i32, [vp, vp, u32, vp, vp]),
         "qp_batch_describe": (i32, [vp, vp]),
         "qp_batch_serialized_len": (sz, [vp]),
         "qp_batch_serialize": (i32, [vp, vp, sz]),

@@ -1085,6 +1085,44 @@ extern "C" int qp_batch_prove_many(const qp_batch* b, const uint64_t* leaf_indic
     return tree_prove_many(b->ctx, b->tree, leaf_indices, n, siblings_out);
 }
 
+// Rows and Merkle paths of n leaves in one round trip (the query openings of fri_proof: one call per
+// oracle instead of two): one index upload, two kernels, one device buffer back.
+extern "C" int qp_batch_open_many(const qp_batch* b, const uint64_t* leaf_indices, unsigned n, uint64_t* rows_out,
+                                  uint64_t* siblings_out) {
+    if (!b) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = b->ctx;
+    if (n == 0) return QP_OK;
+    if (!leaf_indices || !rows_out || (!siblings_out && b->tree.shape.num_layers()))
+        return fail(ctx, QP_ERR_BAD_ARG, "null buffer");
+    for (unsigned i = 0; i < n; i++)
+        if (leaf_indices[i] >= b->n_local) return fail(ctx, QP_ERR_BAD_ARG, "leaf index out of range");
+    const unsigned nl = b->tree.shape.num_layers();
+    const size_t row_words = (size_t)n * b->leaf_len, path_words = (size_t)n * nl * 4;
+    uint64_t* d_idx = nullptr;
+    uint64_t* d_out = nullptr;
+    int rc = dev_alloc(ctx, &d_idx, n);
+    if (!rc) rc = dev_alloc(ctx, &d_out, row_words + path_words ? row_words + path_words : 1);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_idx, leaf_indices, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (row_words) {
+        merkle::AffineLayout lay{b->lde, b->n_local, 1};
+        LAUNCH(ctx, merkle::gather_rows_kernel<merkle::AffineLayout>, cdiv(row_words, 256), 256, 0, lay,
+               (unsigned)b->leaf_len, d_idx, (size_t)0, (size_t)n, d_out);
+    }
+    if (path_words)
+        LAUNCH(ctx, merkle::merkle_paths_kernel, cdiv((size_t)n * nl, 128), 128, 0, b->tree.shape, b->tree.digests, d_idx, n,
+               d_out + row_words);
+    std::vector<uint64_t> host(row_words + path_words);
+    rc = copy_out(ctx, host.data(), QP_HOST, d_out, row_words + path_words);
+    if (!rc) {
+        std::memcpy(rows_out, host.data(), row_words * 8);
+        if (path_words) std::memcpy(siblings_out, host.data() + row_words, path_words * 8);
+    }
+    dev_free(ctx, d_idx);
+    dev_free(ctx, d_out);
+    return rc;
+}
+
 extern "C" int qp_batch_timing(const qp_batch* b, double ms[4]) {
     if (!b || !ms) return QP_ERR_BAD_ARG;
     for (int i = 0; i < 4; i++) ms[i] = b->ms[i];

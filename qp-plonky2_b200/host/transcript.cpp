@@ -261,8 +261,7 @@ extern "C" int qp_fri_proof(qp_ctx* ctx, const qp_batch* const* oracles, size_t 
         o_len[t] = qp_batch_leaf_len(oracles[t]);
         o_rows[t].resize((size_t)num_queries * o_len[t] + 1);
         o_paths[t].resize((size_t)num_queries * o_layers * 4 + 1);
-        rc = qp_batch_get_leaves(oracles[t], x.data(), num_queries, o_rows[t].data());
-        if (!rc) rc = qp_batch_prove_many(oracles[t], x.data(), num_queries, o_paths[t].data());
+        rc = qp_batch_open_many(oracles[t], x.data(), num_queries, o_rows[t].data(), o_paths[t].data());
     }
     lap("oracle openings");
     std::vector<std::vector<uint64_t>> r_rows(n_rounds), r_paths(n_rounds);
