@@ -15,10 +15,18 @@ polynomials, sigma polynomials, and a witness.  This module fabricates those dir
 """
 import numpy as np
 
-import oracle
 from qp_plonky2_b200 import plonk
 
-P = oracle.P
+P = plonk.P
+
+
+def rand_felts(shape, seed):
+    """Uniform canonical Goldilocks elements from a seeded PCG64 (the same stream as the oracle's
+    helper of that name).  Building a circuit needs nothing from oracle/: the benchmarks construct their
+    inputs with this module, and only the tests' checkers (`oracle_circuit`, `eval_poly`) import it."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = rng.integers(0, 2**64, size=shape, dtype=np.uint64)
+    return np.where(a >= np.uint64(P), a - np.uint64(P), a).astype(np.uint64)
 
 
 def _mulmod(a, b):
@@ -52,22 +60,7 @@ class SynthCircuit:
                       plonk.CosetInterpolationGate.with_max_degree(4, quotient_degree_factor)]
         self.common = c = plonk.CommonCircuitData(degree_bits, gates, num_wires, nr, num_challenges,
                                                   quotient_degree_factor, rate_bits, cap_height)
-        kinds = {"NoopGate": oracle.GATE_NOOP, "ConstantGate": oracle.GATE_CONSTANT,
-                 "PublicInputGate": oracle.GATE_PUBLIC_INPUT, "ArithmeticGate": oracle.GATE_ARITHMETIC,
-                 "PoseidonGate": oracle.GATE_POSEIDON, "ArithmeticExtensionGate": oracle.GATE_ARITHMETIC_EXT,
-                 "MulExtensionGate": oracle.GATE_MUL_EXT, "BaseSumGate": oracle.GATE_BASE_SUM_2,
-                 "RandomAccessGate": oracle.GATE_RANDOM_ACCESS, "ReducingGate": oracle.GATE_REDUCING,
-                 "ReducingExtensionGate": oracle.GATE_REDUCING_EXT, "PoseidonMdsGate": oracle.GATE_POSEIDON_MDS,
-                 "ExponentiationGate": oracle.GATE_EXPONENTIATION,
-                 "CosetInterpolationGate": oracle.GATE_COSET_INTERPOLATION}
-        og = []
-        for i, g in enumerate(c.gates):
-            name = g.id().split(" ")[0].split("(")[0]
-            param = g.param
-            og.append((kinds[name], param, c.selector_indices[i], c.groups[c.selector_indices[i]]))
-        self.oracle_circuit = oracle.Circuit(degree_bits, c.quotient_degree_bits, num_challenges, nr, num_wires,
-                                             c.num_constants, c.num_partial_products, quotient_degree_factor,
-                                             c.num_selectors, og, c.k_is)
+        self._oracle_circuit = None
         idx = {g.id().split(" ")[0].split("(")[0]: i for i, g in enumerate(c.gates)}
         # gate per row: mostly arithmetic (and Poseidon), a few of the others; row 0 is the public-input gate
         kinds_p = {"NoopGate": 0.2, "ConstantGate": 0.1, "ArithmeticGate": 0.7}
@@ -89,7 +82,7 @@ class SynthCircuit:
         for s, (a, b) in enumerate(c.groups):
             in_group = (row_gate >= a) & (row_gate < b)
             consts[s] = np.where(in_group, row_gate, plonk.UNUSED_SELECTOR if c.num_selectors > 1 else row_gate)
-        gate_consts = oracle.rand_felts((c.num_gate_constants, n), seed + 1)
+        gate_consts = rand_felts((c.num_gate_constants, n), seed + 1)
         uses = (row_gate == idx["ConstantGate"]) | (row_gate == idx["ArithmeticGate"])
         if extra_gates:
             uses |= (row_gate == idx["ArithmeticExtensionGate"]) | (row_gate == idx["MulExtensionGate"])
@@ -98,10 +91,11 @@ class SynthCircuit:
         consts[c.num_selectors:] = np.where(uses[None, :], gate_consts, 0)
         self.constants = consts
         # witness
-        wires = oracle.rand_felts((num_wires, n), seed + 2)
+        wires = rand_felts((num_wires, n), seed + 2)
         # public inputs and their hash (prover.rs:185-186); the PublicInputGate row carries the hash
-        self.public_inputs = [int(x) for x in oracle.rand_felts((3,), seed + 3)]
-        self.public_inputs_hash = oracle.hash_no_pad(np.array(self.public_inputs, dtype=np.uint64))
+        self.public_inputs = [int(x) for x in rand_felts((3,), seed + 3)]
+        from qp_plonky2_b200 import prover as _prover   # host-side hash_no_pad (qp_hash_no_pad), checked against the oracle's in tests
+        self.public_inputs_hash = _prover.hash_no_pad(self.public_inputs)
         pi_rows = row_gate == idx["PublicInputGate"]
         for k in range(4):
             wires[k, pi_rows] = self.public_inputs_hash[k]
@@ -204,7 +198,7 @@ class SynthCircuit:
                     wires[w, r] = v
         self.wires = wires
         # sigma polynomials' values: k_is[col] * w^row  (circuit_builder.rs sigma_vecs)
-        w = oracle.lib().orc_gl_primitive_root(degree_bits)
+        w = plonk.primitive_root_of_unity(degree_bits)
         sub = np.ones(n, dtype=object)
         for i in range(1, n):
             sub[i] = sub[i - 1] * w % P
@@ -212,12 +206,39 @@ class SynthCircuit:
         self.sigmas = ((k_obj[sigma_col] * sub[sigma_row]) % P).astype(np.uint64)
         self.subgroup = sub.astype(np.uint64)
 
+    @property
+    def oracle_circuit(self):
+        """The same circuit as the ORACLE describes it (checker side, tests only)."""
+        if self._oracle_circuit is None:
+            import oracle
+            c, nr = self.common, self.common.num_routed_wires
+            degree_bits, num_challenges, num_wires = c.degree_bits, c.num_challenges, c.num_wires
+            quotient_degree_factor = c.quotient_degree_factor
+            kinds = {"NoopGate": oracle.GATE_NOOP, "ConstantGate": oracle.GATE_CONSTANT,
+                     "PublicInputGate": oracle.GATE_PUBLIC_INPUT, "ArithmeticGate": oracle.GATE_ARITHMETIC,
+                     "PoseidonGate": oracle.GATE_POSEIDON, "ArithmeticExtensionGate": oracle.GATE_ARITHMETIC_EXT,
+                     "MulExtensionGate": oracle.GATE_MUL_EXT, "BaseSumGate": oracle.GATE_BASE_SUM_2,
+                     "RandomAccessGate": oracle.GATE_RANDOM_ACCESS, "ReducingGate": oracle.GATE_REDUCING,
+                     "ReducingExtensionGate": oracle.GATE_REDUCING_EXT, "PoseidonMdsGate": oracle.GATE_POSEIDON_MDS,
+                     "ExponentiationGate": oracle.GATE_EXPONENTIATION,
+                     "CosetInterpolationGate": oracle.GATE_COSET_INTERPOLATION}
+            og = []
+            for i, g in enumerate(c.gates):
+                name = g.id().split(" ")[0].split("(")[0]
+                param = g.param
+                og.append((kinds[name], param, c.selector_indices[i], c.groups[c.selector_indices[i]]))
+            self._oracle_circuit = oracle.Circuit(degree_bits, c.quotient_degree_bits, num_challenges, nr, num_wires,
+                                                 c.num_constants, c.num_partial_products, quotient_degree_factor,
+                                                 c.num_selectors, og, c.k_is)
+        return self._oracle_circuit
+
     def constants_sigmas(self):
         return np.ascontiguousarray(np.concatenate([self.constants, self.sigmas], axis=0))
 
 
 def eval_poly(coeffs, x):
     """Horner over F_p (PolynomialCoeffs::eval)."""
+    import oracle
     out = oracle.lib().orc_eval_poly_ext  # F_p^2 evaluator with point (x, 0)
     res = np.zeros(2, dtype=np.uint64)
     pt = np.array([x, 0], dtype=np.uint64)
@@ -232,7 +253,7 @@ def verifier_identity_holds(sc, cs_polys, wires_polys, zs_polys, quotient_coeffs
     vectors.  Size-independent property: it holds iff the committed quotient is the right one."""
     c = sc.common
     n = 1 << c.degree_bits
-    g = oracle.lib().orc_gl_primitive_root(c.degree_bits)
+    g = plonk.primitive_root_of_unity(c.degree_bits)
     x0 = int(x0)
     cs = [eval_poly(p, x0) for p in cs_polys]
     wv = [eval_poly(p, x0) for p in wires_polys]

@@ -3,7 +3,8 @@
 configs[1]: degree 2^12..2^14, 143 wires / 80 routed, standard_recursion_config) and larger, with
 the reference's TimingTree scope names; optionally the oracle's CPU prove() next to it.
     python tools/bench_prove.py [--degrees 12 13 14] [--cpu 12] > gpurun_out/prove.json
-Test-infrastructure imports (oracle, tests/synth_circuit) only build the inputs and the CPU leg."""
+The inputs come from tests/synth_circuit.py, which needs nothing from oracle/; the oracle is imported only
+for the CPU leg (--cpu), the counterpart of bench.py's cpu_baseline."""
 import argparse
 import json
 import os
