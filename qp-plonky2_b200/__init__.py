@@ -359,6 +359,16 @@ class BatchMerkleView:
     def get(self, i):
         return self.leaves(i, 1)[0]
 
+    def open_many(self, indices):
+        """rows and Merkle paths of many leaves in one round trip -> (rows [n][leaf_len], paths [n][layers][4])"""
+        b = self._b
+        idx = np.ascontiguousarray(np.asarray(indices, dtype=np.uint64))
+        layers = b.local_lg_leaves - b.local_cap_height
+        rows = np.zeros((idx.size, b.leaf_len), dtype=np.uint64)
+        paths = np.zeros((idx.size, layers, 4), dtype=np.uint64)
+        b.ctx.check(lib().qp_batch_open_many(b._h, _np_ptr(idx), idx.size, _np_ptr(rows), _np_ptr(paths) if layers else None))
+        return rows, paths
+
     def get_many(self, indices):
         b = self._b
         idx = np.ascontiguousarray(np.asarray(indices, dtype=np.uint64))

@@ -694,3 +694,20 @@ def test_batch_fri_oracle_errors(qp, ctx):
         qp.BatchFriOracle.from_coeffs(ctx, [z(16)], 1, True, 0)            # blinding: not implemented
     with pytest.raises(qp.QpError):
         qp.BatchFriOracle.from_coeffs(ctx, [z(12)], 1, False, 0)           # not a power of two
+
+
+def test_batch_open_many(qp, ctx):
+    """qp_batch_open_many = get_leaves + prove_many in one round trip: same rows and paths, and each pair
+    verifies against the cap (fri_prover_query_rounds, plonky2/src/fri/prover.rs:246-253)."""
+    vals = oracle.rand_felts((7, 1 << 8), 31)
+    b = qp.PolynomialBatch.from_values(ctx, vals, 3, False, 2)
+    idx = [0, 5, 2047, 1024, 5, 77]
+    rows, paths = b.merkle_tree.open_many(idx)
+    assert (rows == b.merkle_tree.get_many(idx)).all()
+    cap = b.merkle_tree.cap
+    for k, i in enumerate(idx):
+        assert (paths[k] == b.merkle_tree.prove(i)).all()
+        assert oracle.merkle_verify(rows[k], i, cap, paths[k])
+    with pytest.raises(qp.QpError):
+        b.merkle_tree.open_many([1 << 11])
+    b.free()
