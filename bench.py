@@ -6,9 +6,19 @@ configs[2]) on N B200s, beside the CPU restatement of the reference path.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--rows-log L]
 
 One "step" = one whole commit of one synthetic witness matrix.  `value` = ms per commit with
-the witness already resident in HBM (CUDA events, max over ranks); `e2e` = ms per commit through
-the C ABI with HOST (pinned) buffers, the host->device copy of the witness and the device->host
-read of the cap inside the timed region.  N > 1: coset-sharded strong scaling (dist.py).
+the witness already resident in HBM (CUDA events on the library's stream, max over ranks; the wall
+clock around the same region is reported as `wall_ms_per_step`); `e2e` = ms per commit through the
+C ABI with HOST (pinned) buffers, the host->device copy of the witness and the device->host read of
+the cap inside the timed region; `e2e_pageable` = the same through `qp_batch_from_values_cols` from
+135 separate pageable column vectors (what the reference's `Vec<PolynomialValues>` is).
+N > 1: coset-sharded strong scaling (dist.py).
+
+Both arms commit to the SAME witness (`synth_columns_*`: SplitMix64 of (seed, column, row), reduced
+to canonical form): at N = 1 the CPU restatement runs once on the very matrix the GPU committed to, at
+full size, its wall time is `cpu_baseline.value` and its Merkle cap must equal the GPU's
+(`cap_equal_cpu`).  `--impl reference` times the same full-size commit per step (no extrapolation).
+
+    python bench.py --workload merkle [--leaves-log L] [--gpus N]     MerkleTree::new sweep (configs[3])
 """
 import argparse
 import json
@@ -79,50 +89,109 @@ def peaks():
 
 
 # ---------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the CPU restatement of the reference path (oracle, kind "port")
+# synthetic witness: column c, row i = SplitMix64((seed << 40) + (c << 32) + i) reduced to [0, p).
+# The numpy form (CPU arm) and the torch form (generated on the device) are the same function, so
+# every arm, every rank and every N commits to the same matrix.
 # ---------------------------------------------------------------------------------------------
-def cpu_commit_ms(rows_log, sample_rows_log, repeats=1):
-    """Time oracle PolynomialBatch::from_values on a bounded sample (2^sample_rows_log rows x 135
-    columns, all host threads) and scale by the row ratio to the full workload."""
+P_GL = 0xFFFFFFFF00000001
+SEED = 42
+
+
+def synth_columns_numpy(c_lo, c_hi, n, seed=SEED):
+    out = np.empty((c_hi - c_lo, n), dtype=np.uint64)
+    i = np.arange(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for c in range(c_lo, c_hi):
+            z = (i + np.uint64((seed << 40) + (c << 32))) * np.uint64(0x9E3779B97F4A7C15)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+            out[c - c_lo] = np.where(z >= np.uint64(P_GL), z - np.uint64(P_GL), z)
+    return out
+
+
+def synth_columns_torch(c_lo, c_hi, n, dev, seed=SEED):
+    import torch
+
+    def s64(x):
+        x &= (1 << 64) - 1
+        return x - (1 << 64) if x >> 63 else x
+
+    def lsr(z, k):  # logical shift right on int64 storage
+        return (z >> k) & ((1 << (64 - k)) - 1)
+
+    out = torch.empty((c_hi - c_lo, n), dtype=torch.int64, device=dev)
+    i = torch.arange(n, dtype=torch.int64, device=dev)
+    for c in range(c_lo, c_hi):
+        z = (i + ((seed << 40) + (c << 32))) * s64(0x9E3779B97F4A7C15)
+        z = (z ^ lsr(z, 30)) * s64(0xBF58476D1CE4E5B9)
+        z = (z ^ lsr(z, 27)) * s64(0x94D049BB133111EB)
+        z = z ^ lsr(z, 31)
+        ge = (z < 0) & (z >= -0xFFFFFFFF)  # unsigned z >= p
+        out[c - c_lo] = torch.where(ge, z + 0xFFFFFFFF, z)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the CPU restatement of the reference path (oracle, kind "port"),
+# at FULL size on the same witness -- nothing is extrapolated
+# ---------------------------------------------------------------------------------------------
+def oracle_threads():
     # torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU arm uses every host core
     os.environ["OMP_NUM_THREADS"] = os.environ.get("QP_ORACLE_THREADS", str(os.cpu_count()))
     import oracle
 
-    vals = oracle.rand_felts((COLS, 1 << sample_rows_log), 42)
-    best, scopes = None, None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        b = oracle.PolynomialBatch.from_values(vals, RATE_BITS, CAP_HEIGHT)
-        dt = (time.perf_counter() - t0) * 1e3
-        if best is None or dt < best:
-            best, scopes = dt, b.scope_ms
-        del b
-    scale = 1 << (rows_log - sample_rows_log)
-    return best * scale, best, scopes, oracle.lib().orc_num_threads()
+    return oracle, oracle.lib().orc_num_threads()
+
+
+def cpu_commit(vals):
+    """One oracle PolynomialBatch::from_values on `vals` (all host threads): (ms, scopes, batch)."""
+    oracle, _ = oracle_threads()
+    t0 = time.perf_counter()
+    b = oracle.PolynomialBatch.from_values(vals, RATE_BITS, CAP_HEIGHT)
+    return (time.perf_counter() - t0) * 1e3, b.scope_ms, b
 
 
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
-    sample = min(args.rows_log, 16)
-    times = []
+    if args.workload == "merkle":
+        return run_reference_merkle(args)
+    _, cores = oracle_threads()
+    vals = synth_columns_numpy(0, COLS, 1 << args.rows_log)
+    # every step is one FULL-size commit; QP_REF_BUDGET_S bounds the whole run (steps_run says how many ran)
+    budget = float(os.environ.get("QP_REF_BUDGET_S", 1500))
+    t_start = time.perf_counter()
+    times, scopes, cap0 = [], None, None
+    warm = 0
     for _ in range(args.warmup):
-        cpu_commit_ms(args.rows_log, sample)
+        if warm and time.perf_counter() - t_start > budget / 4:
+            break
+        _, _, b = cpu_commit(vals)
+        cap0 = [int(x) for x in b.cap[0]]
+        del b
+        warm += 1
     for _ in range(args.steps):
-        full_ms, _, scopes, cores = cpu_commit_ms(args.rows_log, sample)
-        times.append(full_ms)
+        if times and time.perf_counter() - t_start + times[-1] / 1e3 > budget:
+            break
+        ms, scopes, b = cpu_commit(vals)
+        cap0 = [int(x) for x in b.cap[0]]
+        del b
+        times.append(ms)
     ms = sum(times) / len(times)
-    desc = "oracle (C/OpenMP restatement of the reference's rayon path) on 2^%d rows x %d cols, x%d" % (
-        sample, COLS, 1 << (args.rows_log - sample))
+    desc = ("oracle (C/OpenMP restatement of the reference's rayon path) on the full 2^%d rows x %d cols, "
+            "%d timed runs, nothing scaled" % (args.rows_log, COLS, len(times)))
     line = {
         "impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False,
+        "steps": len(times), "steps_requested": args.steps, "warmup": warm, "ms_per_step": ms,
+        "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port", "sample": desc,
-                         "scopes_ms_sample": scopes},
+                         "scopes_ms": scopes, "min_ms": min(times), "max_ms": max(times)},
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cap0": cap0,
     }
     print(json.dumps(line))
 
@@ -167,15 +236,9 @@ def run_ours(args):
     n = 1 << args.rows_log
     c_lo, c_hi = (0, COLS) if world == 1 else qd.column_shard(COLS, world, rank)
 
-    # synthetic witness: uniform canonical Goldilocks elements, seed 42 (same on every run)
-    # (per column, so that a rank generates only its own column shard and every N sees the same matrix)
-    gen = torch.Generator(device=dev)
-    d_vals = torch.empty((c_hi - c_lo, n), dtype=torch.int64, device=dev)
-    for c in range(c_lo, c_hi):
-        gen.manual_seed(42 + c)
-        col = torch.randint(0, 2**63 - 1, (n,), dtype=torch.int64, device=dev, generator=gen)
-        d_vals[c - c_lo] = col * 2 + torch.randint(0, 2, (n,), dtype=torch.int64, device=dev, generator=gen)  # 64 random bits
-    del col
+    # synthetic witness: uniform canonical Goldilocks elements (synth_columns_*), the same matrix in every
+    # arm; a rank generates only its own column shard
+    d_vals = synth_columns_torch(c_lo, c_hi, n, dev)
     h_vals = torch.empty(d_vals.shape, dtype=torch.int64).pin_memory()
     h_vals.copy_(d_vals)
     torch.cuda.synchronize()
@@ -225,17 +288,20 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # CUDA events on the stream the library launches on (= torch's current stream, see above)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ctx.launch_count
     kernel_ms = {"intt": 0.0, "lde": 0.0, "leaf_hash": 0.0, "tree_levels": 0.0}
-    t_wall0 = time.perf_counter()
-    dev_ms = 0.0
+    dev_ms = wall_ms = 0.0
     for _ in range(args.steps):
         barrier()
         t0 = time.perf_counter()
+        ev0.record(stream)
         b, cap = step(d_vals)
+        ev1.record(stream)
         torch.cuda.synchronize()
-        dev_ms += (time.perf_counter() - t0) * 1e3
+        wall_ms += (time.perf_counter() - t0) * 1e3
+        dev_ms += ev0.elapsed_time(ev1)
         for k in kernel_ms:
             kernel_ms[k] += b.kernel_ms.get(k, 0.0)
         caps.append(cap)
@@ -250,24 +316,42 @@ def run_ours(args):
     e2e_ms = 0.0
     for _ in range(args.steps):
         barrier()
-        t0 = time.perf_counter()
+        t0 = time.perf_counter()   # host buffers in, host cap out: the wall clock IS the end-to-end time
         b, cap = step(h_vals)
         torch.cuda.synchronize()
         e2e_ms += (time.perf_counter() - t0) * 1e3
         assert (cap == caps[0]).all(), "e2e cap differs from device-resident cap"
         b.free()
     barrier()
+    # ---- end to end from what the reference passes: one pageable heap vector per column ----
+    e2e_pg_ms = None
+    if world == 1 and hasattr(qp.PolynomialBatch, "from_values_cols"):
+        cols_pg = [np.array(h_vals[c].numpy(), copy=True).view(np.uint64) for c in range(COLS)]
+        for _ in range(min(args.warmup, 2)):
+            qp.PolynomialBatch.from_values_cols(ctx, cols_pg, RATE_BITS, False, CAP_HEIGHT).free()
+        e2e_pg_ms = 0.0
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            b = qp.PolynomialBatch.from_values_cols(ctx, cols_pg, RATE_BITS, False, CAP_HEIGHT)
+            cap = b.merkle_tree.cap
+            torch.cuda.synchronize()
+            e2e_pg_ms += (time.perf_counter() - t0) * 1e3
+            assert (cap == caps[0]).all(), "pageable-columns cap differs from device-resident cap"
+            b.free()
+        e2e_pg_ms /= args.steps
+        del cols_pg
     clocks = sampler.stop() if rank == 0 else None
 
     dev_ms /= args.steps
+    wall_ms /= args.steps
     e2e_ms /= args.steps
     for k in kernel_ms:
         kernel_ms[k] /= args.steps
     t = torch.tensor([dev_ms, e2e_ms, kernel_ms["intt"], kernel_ms["lde"], kernel_ms["leaf_hash"],
-                      kernel_ms["tree_levels"]], dtype=torch.float64, device=dev)
+                      kernel_ms["tree_levels"], wall_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, k_intt, k_lde, k_leaf, k_tree = [float(x) for x in t.cpu()]
+    dev_ms, e2e_ms, k_intt, k_lde, k_leaf, k_tree, wall_ms = [float(x) for x in t.cpu()]
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -286,11 +370,11 @@ def run_ours(args):
         rec = json.load(open(tp)).get("leaf_hash_kernel", {})
         if rec.get("rows_log") == args.rows_log and rec.get("cols", 135) == COLS:
             traffic = rec.get("dram_bytes")
-    roof = {"kernel": "merkle::leaf_hash_kernel", "bound": "hbm", "achieved": leaf_bytes / (k_leaf * 1e-3) / 1e9,
-            "peak": peak, "unit": "GB/s", "frac": leaf_bytes / (k_leaf * 1e-3) / 1e9 / peak, "traffic": traffic,
-            "peak_source": peak_src, "ms": k_leaf,
-            "note": "integer-issue bound, not HBM bound: %.3g Poseidon permutations/s per GPU" % (perms / (k_leaf * 1e-3)),
-            "permutations_per_s": perms / (k_leaf * 1e-3)}
+    roof_hbm = {"kernel": "merkle::leaf_hash_kernel", "bound": "hbm", "achieved": leaf_bytes / (k_leaf * 1e-3) / 1e9,
+                "peak": peak, "unit": "GB/s", "frac": leaf_bytes / (k_leaf * 1e-3) / 1e9 / peak, "traffic": traffic,
+                "peak_source": peak_src, "ms": k_leaf,
+                "note": "reported because the contract asks for it; this kernel is bound by instruction issue, "
+                        "not by HBM (see `roofline`)"}
     lde_bytes = COLS * n * 8 + COLS * n_loc * 8          # 8 B per coeff in + 8 B per value out
     roof_lde = {"kernel": "ntt::strided_pass_kernel + ntt::final_pass_kernel (LDE)", "bound": "hbm",
                 "achieved": lde_bytes / (k_lde * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
@@ -301,26 +385,40 @@ def run_ours(args):
         roof_intt = {"kernel": "ntt (iNTT)", "bound": "hbm", "achieved": intt_bytes / k_intt / 1e6, "peak": peak,
                      "unit": "GB/s", "frac": intt_bytes / k_intt / 1e6 / peak, "ms": k_intt}
 
-    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
-    cpu = None
+    # ---- CPU baseline: the oracle, once, at FULL size on the very witness the GPU committed to ----
+    cpu, cap_equal_cpu = None, None
     if world == 1 and not args.no_cpu:
-        sample = min(args.rows_log, 16)
-        full_ms, sample_ms, scopes, cores = cpu_commit_ms(args.rows_log, sample)
-        cpu = {"value": full_ms, "unit": "ms", "cores": cores, "kind": "port",
-               "sample": "oracle from_values on 2^%d rows x %d cols (%.0f ms), scaled x%d by rows; faithful "
-                         "C/OpenMP restatement, not the rustc-compiled reference" % (sample, COLS, sample_ms,
-                                                                                     1 << (args.rows_log - sample)),
-               "scopes_ms_sample": scopes}
+        _, cores = oracle_threads()
+        host = h_vals.numpy().view(np.uint64)
+        cpu_ms, scopes, ob = cpu_commit(host)
+        cap_equal_cpu = bool((ob.cap == caps[0]).all())
+        # and the digests of the first and the last cap subtree, against the device's
+        b, _ = step(d_vals)
+        dg = b.merkle_tree.digests
+        per = dg.shape[0] >> CAP_HEIGHT
+        digests_equal = bool((dg[:per] == ob.digests[:per]).all() and (dg[-per:] == ob.digests[-per:]).all())
+        b.free()
+        del ob, dg
+        cpu = {"value": cpu_ms, "unit": "ms", "cores": cores, "kind": "port",
+               "sample": "full size, 1 run: oracle from_values on the same 2^%d rows x %d cols the GPU arm committed to; "
+                         "faithful C/OpenMP restatement, not the rustc-compiled reference" % (args.rows_log, COLS),
+               "scopes_ms": scopes, "cap_equal": cap_equal_cpu, "digest_blocks_equal": digests_equal}
+        assert cap_equal_cpu and digests_equal, "GPU commitment differs from the CPU oracle's at full size"
 
-    # issue-slot roofline of the same kernel: ncu (profiles/r01h_ncu_full.md) counts 16.08k warp
-    # instructions per warp-permutation; one warp instruction per cycle per SM sub-partition is the ceiling
+    # issue-slot roofline of the same kernel: ncu counts warp instructions per warp-permutation
+    # (profiles/traffic.json "instr_per_warp_permutation"); one warp instruction per cycle per SM
+    # sub-partition is the ceiling
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     instr_per_warp_perm = 16080.0
+    if os.path.exists(tp):
+        instr_per_warp_perm = float(json.load(open(tp)).get("leaf_hash_kernel", {}).get("instr_per_warp_permutation", 16080.0))
     issue_peak = 148 * 4 * sm_mhz * 1e6 * 32 / instr_per_warp_perm
-    roof_issue = {"kernel": "merkle::leaf_hash_kernel", "bound": "issue slots (fma-heavy + ALU + FP64 pipes share one "
-                  "issue port per SM sub-partition)", "achieved": perms / (k_leaf * 1e-3), "peak": issue_peak,
-                  "unit": "Poseidon permutations/s", "frac": perms / (k_leaf * 1e-3) / issue_peak,
-                  "instr_per_warp_permutation": instr_per_warp_perm}
+    roof = {"kernel": "merkle::leaf_hash_kernel", "bound": "issue", "achieved": perms / (k_leaf * 1e-3),
+            "peak": issue_peak, "unit": "Poseidon permutations/s", "frac": perms / (k_leaf * 1e-3) / issue_peak,
+            "traffic": traffic, "ms": k_leaf, "instr_per_warp_permutation": instr_per_warp_perm,
+            "note": "the bound that binds: one warp instruction per cycle per SM sub-partition at the ncu-measured "
+                    "instruction count; the HBM view of the same launch is `roofline_hbm` (SURVEY 8d: HBM is not "
+                    "the yardstick for the hash kernels)"}
 
     # ---- secondary metric of BASELINE.json: proof latency at bench_recursion's degrees (N=1 only) ----
     prove = None
@@ -340,12 +438,15 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": dev_ms, "unit": "ms", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": False, "scaling": "strong",
-        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "wall_ms_per_step": wall_ms,
         "config": workload_config(args, world),
         "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(h_vals.numel() * 8),
                 "d2h_bytes_per_step": int((1 << CAP_HEIGHT) * 32 // world)},
-        "gpu_launches": int(launches),
-        "roofline": roof, "roofline_issue": roof_issue, "roofline_lde": roof_lde, "roofline_intt": roof_intt,
+        "e2e_pageable": None if e2e_pg_ms is None else {
+            "value": e2e_pg_ms, "unit": "ms", "what": "qp_batch_from_values_cols: %d separate pageable column "
+            "vectors (the reference's Vec<PolynomialValues>), staged through the library's pinned ring" % COLS},
+        "gpu_launches": int(launches), "cap_equal_cpu": cap_equal_cpu,
+        "roofline": roof, "roofline_hbm": roof_hbm, "roofline_lde": roof_lde, "roofline_intt": roof_intt,
         "prove": prove,
         "kernel_ms": {"intt": k_intt, "lde": k_lde, "leaf_hash": k_leaf, "tree_levels": k_tree},
         "cpu_baseline": cpu, "clocks": clocks,
@@ -367,6 +468,10 @@ def main():
     ap.add_argument("--rows-log", type=int, default=ROWS_LOG)
     ap.add_argument("--cols", type=int, default=COLS,
                     help="columns of the witness matrix (BASELINE.json configs[4]: --rows-log 23 --cols 400 --gpus 8)")
+    ap.add_argument("--workload", default="commit", choices=["commit", "merkle"],
+                    help="commit: PolynomialBatch::from_values (headline); merkle: MerkleTree::new sweep (configs[3])")
+    ap.add_argument("--leaves-log", type=int, default=None,
+                    help="merkle workload: one size (default: the sweep 2^16..2^24 on the GPU, 2^16..2^20 on the CPU arm)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-prove", action="store_true")
     args = ap.parse_args()
@@ -374,6 +479,8 @@ def main():
     METRIC = "commit_ms_2^%dx%d_rate%d" % (args.rows_log, COLS, RATE_BITS)
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "merkle":
+        run_merkle(args)
     else:
         run_ours(args)
 

@@ -14,13 +14,20 @@
  *   - column-major inputs are [n_cols][n] (the reference's Vec<PolynomialValues>), rows/leaves
  *     are leaf-major [count][leaf_len] (its Vec<Vec<F>>).
  *   - handles own device memory (LDE values stay on the device, column-major in leaf order);
- *     they are immutable after creation and may be read from any thread.
+ *     they are immutable after creation.
  *   - there is NO CPU fallback: without a CUDA device every call fails with QP_ERR_CUDA.
- *   - threading: a context serialises its work on one stream and keeps per-call scratch (events,
- *     error text), so calls that CREATE handles on the same context must not overlap; use one
- *     context per calling thread (contexts are cheap: a stream and a twiddle table).  Finished
- *     handles are immutable and may be read from any thread (the reference shares the
- *     constants/sigmas batch across concurrent prove() calls, circuit_data.rs:337-349).
+ *   - threading: a context owns ONE stream plus per-call scratch (events, staging buffers, error
+ *     text) and is NOT internally locked: every call that takes the context, or a handle created
+ *     on it (readers such as qp_batch_prove / qp_batch_open_many included: they launch on that
+ *     stream), must be serialised by the caller.  One context per prover thread; a batch that
+ *     several provers share (the reference shares the constants/sigmas batch across concurrent
+ *     prove() calls, circuit_data.rs:337-349) is shared by giving those provers the same
+ *     context under a caller-side mutex, or one copy per context (qp_batch_deserialize).
+ *   - stream ordering: the library orders its own work on the context's stream and synchronises
+ *     that stream before a call returns host-visible results.  QP_DEVICE inputs must be complete
+ *     (or produced on that same stream) before the call; QP_DEVICE outputs are ready once the
+ *     call has returned only if the caller waits on that stream (qp_ctx_synchronize) or works on
+ *     it.  Pass the producer's / consumer's cudaStream_t to qp_ctx_create to get that for free.
  */
 #ifndef QP_PLONKY2_B200_H
 #define QP_PLONKY2_B200_H
@@ -53,7 +60,8 @@ typedef struct qp_fri qp_fri;
 
 /* ---- context ------------------------------------------------------------------------------ */
 /* One context per (process, GPU).  `stream` is a cudaStream_t (or NULL for a private stream);
- * max_lde_log bounds the twiddle table (log2 of the largest transform, <= 32). */
+ * max_lde_log bounds the twiddle table (log2 of the largest transform, <= 30: the transform
+ * kernels index with 32 bits). */
 int qp_ctx_create(int device, void* stream, unsigned max_lde_log, qp_ctx** out);
 void qp_ctx_destroy(qp_ctx* ctx);
 const char* qp_last_error(const qp_ctx* ctx);
@@ -73,6 +81,15 @@ int qp_batch_from_values(qp_ctx* ctx, const uint64_t* values, int space, size_t 
                          unsigned degree_log, unsigned rate_bits, int blinding, unsigned cap_height,
                          const uint64_t* salt, unsigned block_first, unsigned block_count,
                          qp_batch** out);
+/* The same call on what the reference passes (`values: Vec<PolynomialValues<F>>`, oracle.rs:168-175):
+ * cols[c] points at column c, 2^degree_log words of ordinary (pageable) host memory -- no flattening
+ * copy on the caller's side.  Large inputs are staged through the context's pinned ring in groups of
+ * 16 columns by a few host threads while the device transforms and hashes the previous group; `salt`
+ * is host memory. */
+int qp_batch_from_values_cols(qp_ctx* ctx, const uint64_t* const* cols, size_t n_cols,
+                              unsigned degree_log, unsigned rate_bits, int blinding, unsigned cap_height,
+                              const uint64_t* salt, unsigned block_first, unsigned block_count,
+                              qp_batch** out);
 /* PolynomialBatch::from_coeffs (oracle.rs:193-223). */
 int qp_batch_from_coeffs(qp_ctx* ctx, const uint64_t* coeffs, int space, size_t n_cols,
                          unsigned degree_log, unsigned rate_bits, int blinding, unsigned cap_height,

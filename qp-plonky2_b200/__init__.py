@@ -120,6 +120,7 @@ def lib():
         "qp_ctx_launch_count": (u64, [vp]),
         "qp_batch_from_values": (i32, [vp, vp, i32, sz, u32, u32, i32, u32, vp, u32, u32, pp]),
         "qp_batch_from_coeffs": (i32, [vp, vp, i32, sz, u32, u32, i32, u32, vp, u32, u32, pp]),
+        "qp_batch_from_values_cols": (i32, [vp, vp, sz, u32, u32, i32, u32, vp, u32, u32, pp]),
         "qp_batch_free": (None, [vp]),
         "qp_batch_begin": (i32, [vp, sz, u32, u32, i32, u32, u32, u32, pp]),
         "qp_batch_put_coeffs": (i32, [vp, vp, i32, sz, sz]),
@@ -257,8 +258,20 @@ def _np_ptr(a):
 class Context:
     """One per (process, GPU): stream, twiddle table, scratch pool."""
 
-    def __init__(self, device: int = 0, max_lde_log: int = 24, stream=None):
+    def __init__(self, device: int = 0, max_lde_log: int = 24, stream=None, private_stream: bool = False):
+        """stream: a cudaStream_t handle the library launches on.  Default (None): torch's current
+        stream for `device` when torch is loaded with CUDA -- device tensors handed to the library
+        and device outputs it produces are then ordered with the caller's torch work without any
+        extra synchronisation (the legacy default stream is passed as cudaStreamLegacy).
+        private_stream=True asks for the library's own non-blocking stream instead; the caller then
+        owns the ordering (see "stream ordering" in include/qp_plonky2_b200.h)."""
         self._h = C.c_void_p()
+        if stream is None and not private_stream:
+            import sys
+
+            torch = sys.modules.get("torch")
+            if torch is not None and torch.cuda.is_available():
+                stream = torch.cuda.current_stream(device).cuda_stream or 1   # 1 = cudaStreamLegacy
         rc = lib().qp_ctx_create(device, C.c_void_p(stream) if stream else None, max_lde_log, C.byref(self._h))
         if rc:
             raise QpError(rc, "qp_ctx_create failed (no usable CUDA device? there is no CPU fallback)")
@@ -404,6 +417,55 @@ class PolynomialBatch:
         return cls._make(ctx, polynomials, rate_bits, blinding, cap_height, salt, block_first, block_count, False)
 
     @classmethod
+    def from_values_cols(cls, ctx, columns, rate_bits, blinding, cap_height, salt=None, block_first=0,
+                         block_count=None):
+        """from_values on a list of separately allocated host columns (numpy uint64 vectors) -- the
+        reference's `Vec<PolynomialValues<F>>` (oracle.rs:168-175): no flattening copy, the library stages
+        the pageable columns itself (qp_batch_from_values_cols)."""
+        cols = [np.ascontiguousarray(np.asarray(c, dtype=np.uint64).ravel()) for c in columns]
+        if len(cols) == 0:
+            raise QpError(5, "polynomials[0]: index out of bounds (empty batch)")
+        if len({c.size for c in cols}) != 1:
+            raise QpError(4, "Polynomial degrees inconsistent")
+        n = cols[0].size
+        lg = int(n).bit_length() - 1
+        if n == 0 or (1 << lg) != n:
+            raise QpError(3, "Not a power of two: %d" % n)
+        if block_count is None:
+            block_count = 1 << rate_bits
+        sp = skeep = None
+        if blinding:
+            if salt is None:
+                raise QpError(7, "blinding=True needs salt[4][N] (the reference draws it from its RNG)")
+            skeep = np.ascontiguousarray(np.asarray(salt, dtype=np.uint64))
+            if skeep.shape != (SALT_SIZE, n << rate_bits):
+                raise QpError(5, "salt must be [4][N]")
+            sp = _np_ptr(skeep)
+        ptrs = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+        self = cls()
+        self.ctx = ctx
+        rc = lib().qp_batch_from_values_cols(ctx._h, ptrs, len(cols), lg, rate_bits, int(bool(blinding)), cap_height,
+                                             sp, block_first, block_count, C.byref(self._h))
+        ctx.check(rc)
+        self._describe(len(cols), lg, rate_bits, blinding, cap_height, block_first, block_count)
+        return self
+
+    def _describe(self, n_cols, lg, rate_bits, blinding, cap_height, block_first, block_count):
+        self.n_cols, self.degree_log, self.rate_bits = n_cols, lg, rate_bits
+        self.blinding, self.cap_height = bool(blinding), cap_height
+        self.block_first, self.block_count = block_first, block_count
+        self.leaf_len = int(lib().qp_batch_leaf_len(self._h))
+        self.n_local_leaves = block_count << lg
+        self.local_lg_leaves = self.n_local_leaves.bit_length() - 1
+        self.local_cap_height = int(lib().qp_batch_cap_len(self._h)).bit_length() - 1
+        self.merkle_tree = BatchMerkleView(self)
+        ms = (C.c_double * 4)()
+        lib().qp_batch_timing(self._h, ms)
+        self.timing = dict(zip(self.SCOPES, list(ms)))
+        lib().qp_batch_kernel_timing(self._h, ms)
+        self.kernel_ms = dict(zip(("intt", "lde", "leaf_hash", "tree_levels"), list(ms)))
+
+    @classmethod
     def _make(cls, ctx, data, rate_bits, blinding, cap_height, salt, block_first, block_count, is_values):
         if not _is_torch(data):
             # Vec<PolynomialValues>: every column must have the same length (oracle.rs:277)
@@ -435,19 +497,7 @@ class PolynomialBatch:
         rc = fn(ctx._h, p, space, n_cols, lg, rate_bits, int(bool(blinding)), cap_height, sp, block_first,
                 block_count, C.byref(self._h))
         ctx.check(rc)
-        self.n_cols, self.degree_log, self.rate_bits = n_cols, lg, rate_bits
-        self.blinding, self.cap_height = bool(blinding), cap_height
-        self.block_first, self.block_count = block_first, block_count
-        self.leaf_len = int(lib().qp_batch_leaf_len(self._h))
-        self.n_local_leaves = block_count << lg
-        self.local_lg_leaves = self.n_local_leaves.bit_length() - 1
-        self.local_cap_height = int(lib().qp_batch_cap_len(self._h)).bit_length() - 1
-        self.merkle_tree = BatchMerkleView(self)
-        ms = (C.c_double * 4)()
-        lib().qp_batch_timing(self._h, ms)
-        self.timing = dict(zip(cls.SCOPES, list(ms)))
-        lib().qp_batch_kernel_timing(self._h, ms)
-        self.kernel_ms = dict(zip(("intt", "lde", "leaf_hash", "tree_levels"), list(ms)))
+        self._describe(n_cols, lg, rate_bits, blinding, cap_height, block_first, block_count)
         return self
 
     # ---- write_polynomial_batch / read_polynomial_batch (serialization/mod.rs:1803-1822, 758-784) ----

@@ -88,6 +88,9 @@ struct CapPrefixLayout {
 #ifndef QP_LEAF_BLOCK       // threads per block of the leaf kernel
 #define QP_LEAF_BLOCK 128
 #endif
+#ifndef QP_LEAF_PREFETCH   // 1: the next 8-element chunk is fetched into registers during the current permutation
+#define QP_LEAF_PREFETCH 1
+#endif
 #ifndef QP_LEAF_SYNC        // 1: barrier per Poseidon round (all warps of the block in lockstep)
 #define QP_LEAF_SYNC 0
 #endif
@@ -121,6 +124,7 @@ leaf_hash_kernel(Layout lay, unsigned leaf_len, TreeShape sh, uint64_t* __restri
 #pragma unroll
         for (int k = 0; k < 12; k++) s[k] = state[(size_t)k * n_leaves + i];
     }
+#if QP_LEAF_PREFETCH
     uint64_t nxt[8];
 #pragma unroll
     for (int k = 0; k < 8; k++)
@@ -138,6 +142,17 @@ leaf_hash_kernel(Layout lay, unsigned leaf_len, TreeShape sh, uint64_t* __restri
         }
         poseidon::permute<QP_LEAF_SYNC != 0>(s);
     }
+#else
+    // no register prefetch: 16 registers fewer, the load latency is left to the other resident warps
+#pragma unroll 1
+    for (unsigned ch = chunk_first; ch < ch_end; ch++) {
+        const unsigned c = ch * 8;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (c + k < leaf_len) s[k] = lay.get(i, c + k);
+        poseidon::permute<QP_LEAF_SYNC != 0>(s);
+    }
+#endif
     if (!live) return;
     if (ch_end == n_chunks) {
         store_digest(leaf_digest_ptr(sh, digests, cap, i), s);

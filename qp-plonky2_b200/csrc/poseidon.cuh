@@ -186,6 +186,18 @@ __device__ __forceinline__ uint64_t fold_row_f64(double al, double ah) {
 // (15,14,40,17,18,24) and (2,1,1,-1,-16,4) are integers and everything stays exact: 103 FP64
 // operations per plane instead of 144.  P_r starts at the constant of row r; row r + 6 adds the
 // difference of the two constants (exact: both are 2^52 + a 33-bit integer).
+#ifndef QP_MDS_COLMAJOR   // 1: accumulate column by column (all twelve chains consume u[0], v[0] first, ...)
+#define QP_MDS_COLMAJOR 0
+#endif
+#ifndef QP_ROUND_FUSED    // 1: full rounds run S-box -> conversion -> accumulation per lane pair (j, j + 6)
+#define QP_ROUND_FUSED 0
+#endif
+
+// sign-adjusted negacyclic coefficient: row r, column j of the 6 x 6 negacyclic block
+__host__ __device__ constexpr double negacyc(const double (&cm)[6], int r, int j) {
+    return (j >= r) ? cm[j - r] : -cm[j - r + 6];
+}
+
 __device__ __forceinline__ void mds_layer_split(uint64_t (&s)[12], int round) {
     constexpr double CP[6] = {15, 14, 40, 17, 18, 24};
     constexpr double CM[6] = {2, 1, 1, -1, -16, 4};
@@ -203,6 +215,24 @@ __device__ __forceinline__ void mds_layer_split(uint64_t (&s)[12], int round) {
             u[j] = d[j] + d[j + 6];
             v[j] = d[j] - d[j + 6];
         }
+#if QP_MDS_COLMAJOR
+        double P[6], Q[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++) P[r] = c_rc_d[12 * round + r][pl];
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                P[r] = fma(u[j], CP[(j - r + 6) % 6], P[r]);
+                Q[r] = (j == 0) ? v[j] * negacyc(CM, r, j) : fma(v[j], negacyc(CM, r, j), Q[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            y[pl][r] = P[r] + Q[r];
+            y[pl][r + 6] = (P[r] - Q[r]) + c_rc_dd[6 * round + r][pl];
+        }
+#else
 #pragma unroll
         for (int r = 0; r < 6; r++) {
             double P = c_rc_d[12 * round + r][pl];
@@ -216,10 +246,124 @@ __device__ __forceinline__ void mds_layer_split(uint64_t (&s)[12], int round) {
             y[pl][r] = P + Q;
             y[pl][r + 6] = (P - Q) + c_rc_dd[6 * round + r][pl];
         }
+#endif
         y[pl][0] = fma(d[0], 8.0, y[pl][0]);  // the diagonal entry of row 0
     }
 #pragma unroll
     for (int r = 0; r < 12; r++) s[r] = fold_row_f64(y[0][r], y[1][r]);
+}
+
+// Scheduling fence experiments (ptxas groups all integer work before all FP64 work otherwise)
+#ifndef QP_SCHED_FENCE
+#define QP_SCHED_FENCE 0
+#endif
+__device__ __forceinline__ void sched_fence() {
+#if QP_SCHED_FENCE == 1
+    asm volatile("bar.warp.sync 0xffffffff;");
+#elif QP_SCHED_FENCE == 2
+    asm volatile("pmevent 1;");
+#elif QP_SCHED_FENCE == 3
+    { uint32_t t_; asm volatile("mov.u32 %0, %%clock;" : "=r"(t_)); }
+#elif QP_SCHED_FENCE == 4
+    { uint32_t t_; asm volatile("{ .reg .pred p; mov.u32 %0, %%laneid; setp.eq.u32 p, %0, 77; @p trap; }" : "=r"(t_)); }
+#elif QP_SCHED_FENCE == 5
+    asm volatile("nanosleep.u32 0;");
+#endif
+}
+
+// S-box layer + linear layer of a full round, lane pair by lane pair: the FP64 accumulation of pair j
+// depends only on the S-boxes of lanes j and j + 6, so the integer work of the next pair can overlap it.
+__device__ __forceinline__ void full_round_fused(uint64_t (&s)[12], int round) {
+    constexpr double CP[6] = {15, 14, 40, 17, 18, 24};
+    constexpr double CM[6] = {2, 1, 1, -1, -16, 4};
+    double P[2][6], Q[2][6], d0[2];
+#pragma unroll
+    for (int pl = 0; pl < 2; pl++)
+#pragma unroll
+        for (int r = 0; r < 6; r++) P[pl][r] = c_rc_d[12 * round + r][pl];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        const uint64_t a = gl::pow7(s[j]), b = gl::pow7(s[j + 6]);
+        uint32_t wa[2], wb[2];
+        gl::unpack(a, wa[0], wa[1]);
+        gl::unpack(b, wb[0], wb[1]);
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+            const double da = f64::from_u32(wa[pl]), db = f64::from_u32(wb[pl]);
+            if (j == 0) d0[pl] = da;
+            const double u = da + db, v = da - db;
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                P[pl][r] = fma(u, CP[(j - r + 6) % 6], P[pl][r]);
+                Q[pl][r] = (j == 0) ? v * negacyc(CM, r, j) : fma(v, negacyc(CM, r, j), Q[pl][r]);
+            }
+        }
+        sched_fence();
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        double y0[2], y1[2];
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+            y0[pl] = P[pl][r] + Q[pl][r];
+            y1[pl] = (P[pl][r] - Q[pl][r]) + c_rc_dd[6 * round + r][pl];
+            if (r == 0) y0[pl] = fma(d0[pl], 8.0, y0[pl]);
+        }
+        s[r] = fold_row_f64(y0[0], y0[1]);
+        s[r + 6] = fold_row_f64(y1[0], y1[1]);
+    }
+}
+
+// Software-pipelined form: segment j holds the S-boxes of lane pair j AND the FP64 accumulation of pair
+// j - 1 (independent work for two different pipes), segments separated by scheduling fences.
+__device__ __forceinline__ void full_round_pipelined(uint64_t (&s)[12], int round) {
+    constexpr double CP[6] = {15, 14, 40, 17, 18, 24};
+    constexpr double CM[6] = {2, 1, 1, -1, -16, 4};
+    double P[2][6], Q[2][6], d0[2], da[2], db[2];
+#pragma unroll
+    for (int pl = 0; pl < 2; pl++)
+#pragma unroll
+        for (int r = 0; r < 6; r++) P[pl][r] = c_rc_d[12 * round + r][pl];
+#pragma unroll
+    for (int j = 0; j <= 6; j++) {
+        if (j > 0) {
+            // accumulation of pair j - 1
+#pragma unroll
+            for (int pl = 0; pl < 2; pl++) {
+                const double u = da[pl] + db[pl], v = da[pl] - db[pl];
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+                    P[pl][r] = fma(u, CP[(j - 1 - r + 6) % 6], P[pl][r]);
+                    Q[pl][r] = (j == 1) ? v * negacyc(CM, r, j - 1) : fma(v, negacyc(CM, r, j - 1), Q[pl][r]);
+                }
+            }
+        }
+        if (j < 6) {
+            const uint64_t a = gl::pow7(s[j]), b = gl::pow7(s[j + 6]);
+            uint32_t wa[2], wb[2];
+            gl::unpack(a, wa[0], wa[1]);
+            gl::unpack(b, wb[0], wb[1]);
+#pragma unroll
+            for (int pl = 0; pl < 2; pl++) {
+                da[pl] = f64::from_u32(wa[pl]);
+                db[pl] = f64::from_u32(wb[pl]);
+                if (j == 0) d0[pl] = da[pl];
+            }
+            sched_fence();
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        double y0[2], y1[2];
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+            y0[pl] = P[pl][r] + Q[pl][r];
+            y1[pl] = (P[pl][r] - Q[pl][r]) + c_rc_dd[6 * round + r][pl];
+            if (r == 0) y0[pl] = fma(d0[pl], 8.0, y0[pl]);
+        }
+        s[r] = fold_row_f64(y0[0], y0[1]);
+        s[r + 6] = fold_row_f64(y1[0], y1[1]);
+    }
 }
 
 // The same CRT split for the pair layer.  M = C + 8 e0 e0^T (C circulant), so
@@ -356,8 +500,14 @@ __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
 #pragma unroll 1
         for (int r = base; r < base + 4; r++) {
             if (SYNC) __syncthreads();
+#if QP_ROUND_FUSED == 2
+            full_round_pipelined(s, r + 1);
+#elif QP_ROUND_FUSED
+            full_round_fused(s, r + 1);
+#else
             sbox_all(s);
             mds_layer_split(s, r + 1);  // row 30 is zero
+#endif
         }
         if (half == 0) {
             // 22 partial rounds (poseidon.rs:623-628) as 11 fused pairs

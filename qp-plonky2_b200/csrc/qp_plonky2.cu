@@ -9,10 +9,13 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "fri.cuh"
@@ -44,7 +47,7 @@ struct qp_ctx {
     // proof makes dozens of them.  Guarded by `mu`: finished handles may be read from any thread.
     static constexpr size_t STAGE_WORDS = 32768;
     uint64_t* stage = nullptr;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};
     std::string err;
     std::mutex mu;
     // coset scale tables keyed by (L, rate_bits, block_first, block_count) for the LDE
@@ -57,6 +60,11 @@ struct qp_ctx {
     cudaEvent_t copy_ev[MAX_GROUPS] = {};
     cudaEvent_t ready_ev = nullptr;
     cudaEvent_t grp_ev[3 * MAX_GROUPS] = {};  // per column group: start, after LDE, after partial leaf hash
+    // pinned staging ring for pageable host columns (qp_batch_from_values_cols): allocated on first
+    // use, kept for the life of the context
+    static constexpr int RING_SLOTS = 2;
+    uint64_t* ring[RING_SLOTS] = {};
+    size_t ring_words = 0;
 };
 
 #define CUDA_TRY(ctx, expr)                                                                  \
@@ -101,6 +109,32 @@ static int dev_alloc(qp_ctx* ctx, uint64_t** p, size_t n_words) {
 static void dev_free(qp_ctx* ctx, uint64_t* p) {
     if (p) cudaFreeAsync(p, ctx->stream);
 }
+
+// Stream-ordered temporaries of one call: everything allocated through the scope is freed when the
+// scope ends, on every path (the early returns of CUDA_TRY / LAUNCH included); keep() hands a buffer
+// over to a longer-lived owner.
+struct TempScope {
+    qp_ctx* ctx;
+    std::vector<uint64_t*> bufs;
+    explicit TempScope(qp_ctx* c) : ctx(c) {}
+    TempScope(const TempScope&) = delete;
+    TempScope& operator=(const TempScope&) = delete;
+    ~TempScope() {
+        for (uint64_t* p : bufs) dev_free(ctx, p);
+    }
+    int alloc(uint64_t** p, size_t n_words) {
+        int rc = dev_alloc(ctx, p, n_words);
+        if (!rc && *p) bufs.push_back(*p);
+        return rc;
+    }
+    void adopt(uint64_t* p) {
+        if (p) bufs.push_back(p);
+    }
+    uint64_t* keep(uint64_t* p) {
+        bufs.erase(std::remove(bufs.begin(), bufs.end(), p), bufs.end());
+        return p;
+    }
+};
 
 static int copy_out(qp_ctx* ctx, uint64_t* dst, int space, const uint64_t* src_dev, size_t n_words) {
     if (!dst) return fail(ctx, QP_ERR_BAD_ARG, "null output buffer");
@@ -202,7 +236,8 @@ __global__ void __launch_bounds__(128) permute_states_kernel(uint64_t* states, s
 extern "C" int qp_ctx_create(int device, void* stream, unsigned max_lde_log, qp_ctx** out) {
     if (!out) return QP_ERR_BAD_ARG;
     *out = nullptr;
-    if (max_lde_log > 32) return QP_ERR_TOO_LARGE;
+    // 32-bit indices inside the transform kernels (1u << L, grid sizes): 2^30 points is the ceiling
+    if (max_lde_log > 30) return QP_ERR_TOO_LARGE;
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) {
         cudaGetLastError();
@@ -276,8 +311,8 @@ extern "C" void qp_ctx_destroy(qp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->scale_cache) {
-        cudaFree(kv.second.lo);
-        cudaFree(kv.second.hi);
+        cudaFreeAsync(kv.second.lo, ctx->stream);
+        cudaFreeAsync(kv.second.hi, ctx->stream);
     }
     cudaFreeAsync(ctx->tw, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
@@ -288,6 +323,8 @@ extern "C" void qp_ctx_destroy(qp_ctx* ctx) {
     cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stage) cudaFreeHost(ctx->stage);
+    for (auto& r : ctx->ring)
+        if (r) cudaFreeHost(r);
     delete ctx;
 }
 
@@ -296,7 +333,7 @@ extern "C" int qp_ctx_synchronize(qp_ctx* ctx) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return QP_OK;
 }
-extern "C" uint64_t qp_ctx_launch_count(const qp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t qp_ctx_launch_count(const qp_ctx* ctx) { return ctx ? ctx->launches.load() : (uint64_t)0; }
 
 // ---------------------------------------------------------------------------------------------
 // NTT driver
@@ -318,13 +355,17 @@ struct NttJob {
 
 template <int K>
 static int launch_strided(qp_ctx* ctx, const ntt::PassParams& p) {
-    const unsigned grid = p.n_vec << (p.L - ntt::TILE_LOG);
+    const size_t grid64 = (size_t)p.n_vec << (p.L - ntt::TILE_LOG);
+    if (grid64 > 0x7fffffffULL) return fail(ctx, QP_ERR_TOO_LARGE, "transform batch exceeds the launch grid limit");
+    const unsigned grid = (unsigned)grid64;
     LAUNCH(ctx, ntt::strided_pass_kernel<K>, grid, ntt::THREADS, ntt::SMEM_ELEMS * 8, p);
     return QP_OK;
 }
 template <int K>
 static int launch_final(qp_ctx* ctx, const ntt::PassParams& p) {
     const size_t chunks = (size_t)p.n_vec << (p.L - K);
+    if (((chunks - 1) >> (ntt::TILE_LOG - K)) + 1 > 0x7fffffffULL)
+        return fail(ctx, QP_ERR_TOO_LARGE, "transform batch exceeds the launch grid limit");
     const unsigned grid = cdiv(chunks, (size_t)1 << (ntt::TILE_LOG - K));
     LAUNCH(ctx, ntt::final_pass_kernel<K>, grid, ntt::THREADS, ntt::SMEM_ELEMS * 8, p);
     return QP_OK;
@@ -443,24 +484,19 @@ static int build_scale(qp_ctx* ctx, int L, const std::vector<uint64_t>& shifts, 
     const unsigned n_inner = (unsigned)shifts.size();
     out->split = L / 2;
     const size_t n_lo = (size_t)1 << out->split, n_hi = (size_t)1 << (L - out->split);
-    CUDA_TRY(ctx, cudaMalloc((void**)&out->lo, n_inner * n_lo * 8));
-    CUDA_TRY(ctx, cudaMalloc((void**)&out->hi, n_inner * n_hi * 8));
-    uint64_t* d_shifts = nullptr;
-    int rc = dev_alloc(ctx, &d_shifts, n_inner);
+    TempScope tmp(ctx);
+    uint64_t *lo = nullptr, *hi = nullptr, *d_shifts = nullptr;
+    int rc = tmp.alloc(&lo, n_inner * n_lo);
+    if (!rc) rc = tmp.alloc(&hi, n_inner * n_hi);
+    if (!rc) rc = tmp.alloc(&d_shifts, n_inner);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(d_shifts, shifts.data(), n_inner * 8, cudaMemcpyHostToDevice, ctx->stream));
     // `shifts` may die before the copy runs
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    LAUNCH(ctx, build_scale_kernel, cdiv(n_inner * (n_lo + n_hi), 256), 256, 0, out->lo, out->hi, d_shifts,
-           n_inner, L, out->split);
-    dev_free(ctx, d_shifts);
+    LAUNCH(ctx, build_scale_kernel, cdiv(n_inner * (n_lo + n_hi), 256), 256, 0, lo, hi, d_shifts, n_inner, L, out->split);
+    out->lo = tmp.keep(lo);
+    out->hi = tmp.keep(hi);
     return QP_OK;
-}
-
-static void free_scale(ScaleTables* s) {
-    cudaFree(s->lo);
-    cudaFree(s->hi);
-    s->lo = s->hi = nullptr;
 }
 
 static unsigned host_bitrev(unsigned x, unsigned bits) {
@@ -561,17 +597,16 @@ static int tree_prove_many(qp_ctx* ctx, const TreeBuf& t, const uint64_t* leaf_i
     if (!leaf_indices || !siblings_out) return fail(ctx, QP_ERR_BAD_ARG, "null buffer");
     for (unsigned i = 0; i < n_q; i++)
         if (leaf_indices[i] >> t.shape.lg_leaves) return fail(ctx, QP_ERR_BAD_ARG, "leaf index out of range");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TempScope tmp(ctx);
     uint64_t* d_idx = nullptr;
     uint64_t* d_out = nullptr;
-    int rc = dev_alloc(ctx, &d_idx, n_q);
-    if (!rc) rc = dev_alloc(ctx, &d_out, (size_t)n_q * nl * 4);
+    int rc = tmp.alloc(&d_idx, n_q);
+    if (!rc) rc = tmp.alloc(&d_out, (size_t)n_q * nl * 4);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(d_idx, leaf_indices, (size_t)n_q * 8, cudaMemcpyHostToDevice, ctx->stream));
     LAUNCH(ctx, merkle::merkle_paths_kernel, cdiv((size_t)n_q * nl, 128), 128, 0, t.shape, t.digests, d_idx, n_q, d_out);
-    rc = copy_out(ctx, siblings_out, QP_HOST, d_out, (size_t)n_q * nl * 4);
-    dev_free(ctx, d_idx);
-    dev_free(ctx, d_out);
-    return rc;
+    return copy_out(ctx, siblings_out, QP_HOST, d_out, (size_t)n_q * nl * 4);
 }
 
 static int tree_prove(qp_ctx* ctx, const TreeBuf& t, size_t leaf_index, uint64_t* siblings_out) {
@@ -579,19 +614,17 @@ static int tree_prove(qp_ctx* ctx, const TreeBuf& t, size_t leaf_index, uint64_t
     if (leaf_index >> t.shape.lg_leaves) return fail(ctx, QP_ERR_BAD_ARG, "leaf index out of range");
     const unsigned nl = t.shape.num_layers();
     if (nl == 0) return QP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TempScope tmp(ctx);
     uint64_t* d_idx = nullptr;
     uint64_t* d_out = nullptr;
-    int rc = dev_alloc(ctx, &d_idx, 1);
-    if (rc) return rc;
-    rc = dev_alloc(ctx, &d_out, (size_t)nl * 4);
+    int rc = tmp.alloc(&d_idx, 1);
+    if (!rc) rc = tmp.alloc(&d_out, (size_t)nl * 4);
     if (rc) return rc;
     uint64_t idx = leaf_index;
     CUDA_TRY(ctx, cudaMemcpyAsync(d_idx, &idx, 8, cudaMemcpyHostToDevice, ctx->stream));
     LAUNCH(ctx, merkle::merkle_paths_kernel, cdiv(nl, 64), 64, 0, t.shape, t.digests, d_idx, 1u, d_out);
-    rc = copy_out(ctx, siblings_out, QP_HOST, d_out, (size_t)nl * 4);
-    dev_free(ctx, d_idx);
-    dev_free(ctx, d_out);
-    return rc;
+    return copy_out(ctx, siblings_out, QP_HOST, d_out, (size_t)nl * 4);  // synchronises: `idx` outlives the copy
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -734,21 +767,23 @@ extern "C" int qp_batch_from_coeffs(qp_ctx* ctx, const uint64_t* coeffs, int spa
     if (rc) return rc;
     if (!coeffs) return fail(ctx, QP_ERR_BAD_ARG, "null coeffs");
     const size_t n = (size_t)1 << degree_log;
+    TempScope tmp(ctx);
     uint64_t* d_coeffs = nullptr;
-    rc = dev_alloc(ctx, &d_coeffs, n_cols * n);
+    rc = tmp.alloc(&d_coeffs, n_cols * n);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(d_coeffs, coeffs, n_cols * n * 8,
                                   space == QP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                   ctx->stream));
     const uint64_t* d_salt = nullptr;
-    uint64_t* salt_owned = nullptr;
     if (blinding) {
+        uint64_t* salt_owned = nullptr;
         rc = to_device(ctx, salt, space, (size_t)QP_SALT_SIZE << (degree_log + rate_bits), &d_salt, &salt_owned);
+        tmp.adopt(salt_owned);
         if (rc) return rc;
     }
-    rc = batch_from_device_coeffs(ctx, d_coeffs, n_cols, degree_log, rate_bits, blinding, cap_height, d_salt,
+    // the batch owns the coefficients from here on
+    rc = batch_from_device_coeffs(ctx, tmp.keep(d_coeffs), n_cols, degree_log, rate_bits, blinding, cap_height, d_salt,
                                   block_first, block_count, out);
-    dev_free(ctx, salt_owned);
     if (rc) {
         qp_batch_free(*out);
         *out = nullptr;
@@ -771,128 +806,129 @@ static int ifft_device(qp_ctx* ctx, const uint64_t* d_values, size_t n_cols, uns
     return run_ntt(ctx, job);
 }
 
-extern "C" int qp_batch_from_values(qp_ctx* ctx, const uint64_t* values, int space, size_t n_cols,
-                                    unsigned degree_log, unsigned rate_bits, int blinding,
-                                    unsigned cap_height, const uint64_t* salt, unsigned block_first,
-                                    unsigned block_count, qp_batch** out) {
-    int rc = check_batch_args(ctx, n_cols, degree_log, rate_bits, blinding, cap_height, salt, block_first,
-                              block_count, out);
-    if (rc) return rc;
-    if (!values) return fail(ctx, QP_ERR_BAD_ARG, "null values");
+// Host -> pinned staging of pageable columns, a few threads wide (one memcpy thread tops out well
+// below what PCIe 5 moves).
+static void stage_columns(uint64_t* dst, const uint64_t* const* cols, size_t c0, size_t c1, size_t n) {
+    const size_t total = (c1 - c0) * n;
+    unsigned n_thr = total * 8 >= ((size_t)8 << 20) ? 4 : 1;
+    const char* e = getenv("QP_STAGE_THREADS");
+    if (e) n_thr = (unsigned)std::max(1, atoi(e));
+    auto work = [&](unsigned t) {
+        // thread t copies the t-th slice of every column (keeps all threads on distinct pages)
+        const size_t lo = n * t / n_thr, hi = n * (t + 1) / n_thr;
+        for (size_t c = c0; c < c1; c++) std::memcpy(dst + (c - c0) * n + lo, cols[c] + lo, (hi - lo) * 8);
+    };
+    if (n_thr == 1) {
+        work(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < n_thr; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+}
+
+// The commit from HOST columns: `cols[c]` points at column c (2^degree_log words).  Columns travel in
+// groups of 16 (= two 8-element sponge chunks): the upload of group g + 1 overlaps the iNTT + LDE +
+// partial leaf hash of group g.  pinned_src: the columns can be handed to the copy engine as they
+// are; otherwise (pageable memory -- what a Rust Vec is) they are staged through the context's pinned
+// ring first.
+static int batch_from_host_columns(qp_ctx* ctx, const uint64_t* const* cols, bool pinned_src, size_t n_cols,
+                                   unsigned degree_log, unsigned rate_bits, int blinding, unsigned cap_height,
+                                   const uint64_t* salt, unsigned block_first, unsigned block_count, qp_batch** out) {
     const size_t n = (size_t)1 << degree_log;
-    uint64_t* d_coeffs = nullptr;
-    rc = dev_alloc(ctx, &d_coeffs, n_cols * n);
+    TempScope tmp(ctx);
+    uint64_t *d_coeffs = nullptr, *d_values = nullptr, *d_state = nullptr;
+    int rc = tmp.alloc(&d_coeffs, n_cols * n);
+    if (!rc) rc = tmp.alloc(&d_values, n_cols * n);
     if (rc) return rc;
-    const uint64_t* d_salt = nullptr;
-    uint64_t* salt_owned = nullptr;
-
-    // Host input of at least 64 MiB: upload in column groups on the copy stream and run the
-    // iNTT + LDE of group g while group g+1 is still in flight.
-    // (QP_PIPELINE_MIN_BYTES lowers the threshold so that the tests can drive this path with small inputs)
-    const char* thr_env = getenv("QP_PIPELINE_MIN_BYTES");
-    const size_t thr = thr_env ? (size_t)strtoull(thr_env, nullptr, 10) : ((size_t)64 << 20);
-    const bool pipelined = space != QP_DEVICE && n_cols * n * 8 >= thr && n_cols >= 2;
-    if (!pipelined) {
-        const uint64_t* d_values = nullptr;
-        uint64_t* values_owned = nullptr;
-        rc = to_device(ctx, values, space, n_cols * n, &d_values, &values_owned);
-        if (rc) return rc;
-        // "IFFT" (oracle.rs:176-180)
-        cudaEventRecord(ctx->ev[0], ctx->stream);
-        rc = ifft_device(ctx, d_values, n_cols, degree_log, d_coeffs, values_owned);
-        cudaEventRecord(ctx->ev[4], ctx->stream);
-        dev_free(ctx, values_owned);
-        if (rc) {
-            dev_free(ctx, d_coeffs);
-            return rc;
-        }
-        if (blinding) {
-            rc = to_device(ctx, salt, space, (size_t)QP_SALT_SIZE << (degree_log + rate_bits), &d_salt, &salt_owned);
-            if (rc) return rc;
-        }
-        rc = batch_from_device_coeffs(ctx, d_coeffs, n_cols, degree_log, rate_bits, blinding, cap_height, d_salt,
-                                      block_first, block_count, out);
-        dev_free(ctx, salt_owned);
-        if (rc) {
-            qp_batch_free(*out);
-            *out = nullptr;
-            return rc;
-        }
-        cudaEventElapsedTime(&(*out)->ms[0], ctx->ev[0], ctx->ev[4]);
-        return QP_OK;
-    }
-
-    uint64_t* d_values = nullptr;
-    rc = dev_alloc(ctx, &d_values, n_cols * n);
-    if (!rc) rc = batch_create(ctx, d_coeffs, n_cols, degree_log, rate_bits, blinding, cap_height, block_first,
-                               block_count, out);
-    if (rc) {
-        dev_free(ctx, d_values);
-        if (*out) {
-            qp_batch_free(*out);
-            *out = nullptr;
-        } else {
-            dev_free(ctx, d_coeffs);
-        }
-        return rc;
-    }
-    // groups of 16 columns = two 8-element sponge chunks, so that the leaf hash of a group can
-    // run as soon as its LDE is done (merkle::leaf_hash_kernel in pieces): the upload of the
-    // later groups hides behind the hashing of the earlier ones, not only behind the transforms
+    rc = batch_create(ctx, tmp.keep(d_coeffs), n_cols, degree_log, rate_bits, blinding, cap_height, block_first,
+                      block_count, out);
+    qp_batch* b = *out;
+    auto bail = [&](int code) {
+        // later copies may still be in flight into d_values / out of the caller's memory
+        cudaStreamSynchronize(ctx->copy_stream);
+        qp_batch_free(b);
+        *out = nullptr;
+        return code;
+    };
+    if (rc) return bail(rc);
     size_t per = 16;
     while ((n_cols + per - 1) / per > (size_t)qp_ctx::MAX_GROUPS) per += 16;
     const int n_groups = (int)((n_cols + per - 1) / per);
-    uint64_t* d_state = nullptr;
-    rc = dev_alloc(ctx, &d_state, 12 * (*out)->n_local);
-    if (rc) {
-        dev_free(ctx, d_values);
-        qp_batch_free(*out);
-        *out = nullptr;
-        return rc;
+    rc = tmp.alloc(&d_state, 12 * b->n_local);
+    if (rc) return bail(rc);
+    if (!pinned_src) {
+        const size_t need = std::min(per, n_cols) * n;
+        if (ctx->ring_words < need) {
+            for (auto& r : ctx->ring) {
+                if (r) cudaFreeHost(r);
+                r = nullptr;
+            }
+            ctx->ring_words = 0;
+            for (auto& r : ctx->ring)
+                if (cudaMallocHost((void**)&r, need * 8) != cudaSuccess) {
+                    cudaGetLastError();
+                    return bail(fail(ctx, QP_ERR_TOO_LARGE, "cannot allocate the pinned staging ring"));
+                }
+            ctx->ring_words = need;
+        }
     }
     // the copy stream may only touch d_values once the (stream-ordered) allocation has happened
     cudaEventRecord(ctx->ready_ev, ctx->stream);
     cudaStreamWaitEvent(ctx->copy_stream, ctx->ready_ev, 0);
-    for (int g = 0; g < n_groups; g++) {
-        const size_t c0 = g * per, c1 = (c0 + per < n_cols) ? c0 + per : n_cols;
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_values + c0 * n, values + c0 * n, (c1 - c0) * n * 8, cudaMemcpyHostToDevice,
-                                      ctx->copy_stream));
-        cudaEventRecord(ctx->copy_ev[g], ctx->copy_stream);
-    }
     cudaEventRecord(ctx->ev[1], ctx->stream);
-    merkle::AffineLayout lay{(*out)->lde, (*out)->n_local, 1};
+    merkle::AffineLayout lay{b->lde, b->n_local, 1};
     unsigned chunks_done = 0;
     int hashed_groups = 0;
+    // pinned source: queue every upload up front; pageable source: stage group g (host work) right
+    // before queueing its compute, so the host copies group g + 1 while the device works on group g
+    auto upload = [&](int g) -> int {
+        const size_t c0 = g * per, c1 = std::min(c0 + per, n_cols);
+        if (pinned_src) {
+            for (size_t c = c0; c < c1; c++)
+                CUDA_TRY(ctx, cudaMemcpyAsync(d_values + c * n, cols[c], n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+        } else {
+            uint64_t* slot = ctx->ring[g % qp_ctx::RING_SLOTS];
+            if (g >= qp_ctx::RING_SLOTS) CUDA_TRY(ctx, cudaEventSynchronize(ctx->copy_ev[g - qp_ctx::RING_SLOTS]));
+            stage_columns(slot, cols, c0, c1, n);
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_values + c0 * n, slot, (c1 - c0) * n * 8, cudaMemcpyHostToDevice,
+                                          ctx->copy_stream));
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[g], ctx->copy_stream));
+        return QP_OK;
+    };
+    if (pinned_src)
+        for (int g = 0; g < n_groups && !rc; g++) rc = upload(g);
     for (int g = 0; g < n_groups && !rc; g++) {
-        const size_t c0 = g * per, c1 = (c0 + per < n_cols) ? c0 + per : n_cols;
+        const size_t c0 = g * per, c1 = std::min(c0 + per, n_cols);
+        if (!pinned_src) rc = upload(g);
+        if (rc) break;
         cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[g], 0);
         cudaEventRecord(ctx->grp_ev[3 * g], ctx->stream);
-        rc = ifft_device(ctx, d_values + c0 * n, c1 - c0, degree_log, d_coeffs + c0 * n, d_values + c0 * n);
-        if (!rc) rc = batch_lde_columns(*out, c0, c1);
+        rc = ifft_device(ctx, d_values + c0 * n, c1 - c0, degree_log, b->coeffs + c0 * n, d_values + c0 * n);
+        if (!rc) rc = batch_lde_columns(b, c0, c1);
         cudaEventRecord(ctx->grp_ev[3 * g + 1], ctx->stream);
         // absorb the complete chunks of this group, leaving at least the last chunk of the leaf
         // (and the salt, if any) to batch_finish
         const unsigned chunk_end = (unsigned)(c1 / 8);
-        const unsigned n_chunks = (unsigned)(((*out)->leaf_len + 7) / 8);
+        const unsigned n_chunks = (unsigned)((b->leaf_len + 7) / 8);
         if (!rc && chunk_end > chunks_done && chunk_end < n_chunks) {
-            rc = hash_leaves(ctx, lay, (unsigned)(*out)->leaf_len, &(*out)->tree, chunks_done, chunk_end - chunks_done,
-                             d_state);
+            rc = hash_leaves(ctx, lay, (unsigned)b->leaf_len, &b->tree, chunks_done, chunk_end - chunks_done, d_state);
             chunks_done = chunk_end;
             hashed_groups = g + 1;
         }
         cudaEventRecord(ctx->grp_ev[3 * g + 2], ctx->stream);
     }
-    dev_free(ctx, d_values);
-    if (!rc && blinding)
-        rc = to_device(ctx, salt, space, (size_t)QP_SALT_SIZE << (degree_log + rate_bits), &d_salt, &salt_owned);
-    if (!rc) rc = batch_finish(*out, d_salt, chunks_done, d_state);  // synchronises the stream
-    dev_free(ctx, salt_owned);
-    dev_free(ctx, d_state);
-    if (rc) {
-        qp_batch_free(*out);
-        *out = nullptr;
-        return rc;
+    if (rc) return bail(rc);
+    const uint64_t* d_salt = nullptr;
+    if (blinding) {
+        uint64_t* salt_owned = nullptr;
+        rc = to_device(ctx, salt, QP_HOST, (size_t)QP_SALT_SIZE << (degree_log + rate_bits), &d_salt, &salt_owned);
+        tmp.adopt(salt_owned);
     }
+    if (!rc) rc = batch_finish(b, d_salt, chunks_done, d_state);  // synchronises the stream
+    if (rc) return bail(rc);
     // scopes: the transforms and the partial leaf hashes interleave, so sum them per group
     float t_ntt = 0, t_hash = 0, ms = 0;
     for (int g = 0; g < n_groups; g++) {
@@ -903,10 +939,98 @@ extern "C" int qp_batch_from_values(qp_ctx* ctx, const uint64_t* values, int spa
             t_hash += ms;
         }
     }
-    (*out)->ms[1] = t_ntt;             // "IFFT" + "FFT + blinding" (the upload wait is not in it)
-    (*out)->ms[3] += t_hash;           // "build Merkle tree"
-    (*out)->ms_leaf_hash += t_hash;
+    b->ms[1] = t_ntt;             // "IFFT" + "FFT + blinding" (the upload wait is not in it)
+    b->ms[3] += t_hash;           // "build Merkle tree"
+    b->ms_leaf_hash += t_hash;
     return QP_OK;
+}
+
+static bool host_pointer_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static size_t pipeline_threshold() {
+    // (QP_PIPELINE_MIN_BYTES lowers the threshold so that the tests can drive the pipelined path with small inputs)
+    const char* thr_env = getenv("QP_PIPELINE_MIN_BYTES");
+    return thr_env ? (size_t)strtoull(thr_env, nullptr, 10) : ((size_t)64 << 20);
+}
+
+extern "C" int qp_batch_from_values(qp_ctx* ctx, const uint64_t* values, int space, size_t n_cols,
+                                    unsigned degree_log, unsigned rate_bits, int blinding,
+                                    unsigned cap_height, const uint64_t* salt, unsigned block_first,
+                                    unsigned block_count, qp_batch** out) {
+    int rc = check_batch_args(ctx, n_cols, degree_log, rate_bits, blinding, cap_height, salt, block_first,
+                              block_count, out);
+    if (rc) return rc;
+    if (!values) return fail(ctx, QP_ERR_BAD_ARG, "null values");
+    const size_t n = (size_t)1 << degree_log;
+    // Host input of at least 64 MiB: upload in column groups on the copy stream and run the
+    // iNTT + LDE (+ partial leaf hash) of group g while group g+1 is still in flight.
+    if (space != QP_DEVICE && n_cols * n * 8 >= pipeline_threshold() && n_cols >= 2) {
+        std::vector<const uint64_t*> cols(n_cols);
+        for (size_t c = 0; c < n_cols; c++) cols[c] = values + c * n;
+        return batch_from_host_columns(ctx, cols.data(), host_pointer_is_pinned(values), n_cols, degree_log, rate_bits,
+                                       blinding, cap_height, salt, block_first, block_count, out);
+    }
+    TempScope tmp(ctx);
+    uint64_t* d_coeffs = nullptr;
+    rc = tmp.alloc(&d_coeffs, n_cols * n);
+    if (rc) return rc;
+    const uint64_t* d_values = nullptr;
+    uint64_t* values_owned = nullptr;
+    rc = to_device(ctx, values, space, n_cols * n, &d_values, &values_owned);
+    tmp.adopt(values_owned);
+    if (rc) return rc;
+    // "IFFT" (oracle.rs:176-180)
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    rc = ifft_device(ctx, d_values, n_cols, degree_log, d_coeffs, values_owned);
+    cudaEventRecord(ctx->ev[4], ctx->stream);
+    if (rc) return rc;
+    const uint64_t* d_salt = nullptr;
+    if (blinding) {
+        uint64_t* salt_owned = nullptr;
+        rc = to_device(ctx, salt, space, (size_t)QP_SALT_SIZE << (degree_log + rate_bits), &d_salt, &salt_owned);
+        tmp.adopt(salt_owned);
+        if (rc) return rc;
+    }
+    rc = batch_from_device_coeffs(ctx, tmp.keep(d_coeffs), n_cols, degree_log, rate_bits, blinding, cap_height, d_salt,
+                                  block_first, block_count, out);
+    if (rc) {
+        qp_batch_free(*out);
+        *out = nullptr;
+        return rc;
+    }
+    cudaEventElapsedTime(&(*out)->ms[0], ctx->ev[0], ctx->ev[4]);
+    return QP_OK;
+}
+
+// PolynomialBatch::from_values on what the reference actually passes (oracle.rs:168-175): one heap
+// vector per column, pageable.  Small inputs are gathered into one upload; large ones go through
+// the staged pipeline above.
+extern "C" int qp_batch_from_values_cols(qp_ctx* ctx, const uint64_t* const* cols, size_t n_cols,
+                                         unsigned degree_log, unsigned rate_bits, int blinding, unsigned cap_height,
+                                         const uint64_t* salt, unsigned block_first, unsigned block_count,
+                                         qp_batch** out) {
+    int rc = check_batch_args(ctx, n_cols, degree_log, rate_bits, blinding, cap_height, salt, block_first,
+                              block_count, out);
+    if (rc) return rc;
+    if (!cols) return fail(ctx, QP_ERR_BAD_ARG, "null column table");
+    for (size_t c = 0; c < n_cols; c++)
+        if (!cols[c]) return fail(ctx, QP_ERR_BAD_ARG, "null column");
+    const size_t n = (size_t)1 << degree_log;
+    if (n_cols * n * 8 >= pipeline_threshold() && n_cols >= 2)
+        return batch_from_host_columns(ctx, cols, false, n_cols, degree_log, rate_bits, blinding, cap_height, salt,
+                                       block_first, block_count, out);
+    std::vector<uint64_t> flat(n_cols * n);
+    for (size_t c = 0; c < n_cols; c++) std::memcpy(flat.data() + c * n, cols[c], n * 8);
+    // (the small-input path synchronises before it returns, so `flat` outlives its upload)
+    return qp_batch_from_values(ctx, flat.data(), QP_HOST, n_cols, degree_log, rate_bits, blinding, cap_height, salt,
+                                block_first, block_count, out);
 }
 
 // from_coeffs in pieces (multi-GPU: the LDE of the columns that have arrived overlaps the
@@ -1022,32 +1146,31 @@ static int batch_gather(const qp_batch* b, const uint64_t* idx_host, size_t firs
     qp_ctx* ctx = b->ctx;
     if (!out) return fail(ctx, QP_ERR_BAD_ARG, "null output buffer");
     if (count == 0) return QP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TempScope tmp(ctx);
     uint64_t* d_idx = nullptr;
     int rc;
     if (idx_host) {
         for (size_t i = 0; i < count; i++)
             if (idx_host[i] >= b->n_local) return fail(ctx, QP_ERR_BAD_ARG, "leaf index out of range");
-        rc = dev_alloc(ctx, &d_idx, count);
+        rc = tmp.alloc(&d_idx, count);
         if (rc) return rc;
         CUDA_TRY(ctx, cudaMemcpyAsync(d_idx, idx_host, count * 8, cudaMemcpyHostToDevice, ctx->stream));
     } else if (first + count > b->n_local) {
         return fail(ctx, QP_ERR_BAD_ARG, "leaf range out of bounds");
     }
     uint64_t* d_out = out;
-    uint64_t* owned = nullptr;
     if (space != QP_DEVICE) {
-        rc = dev_alloc(ctx, &owned, count * row_len);
+        rc = tmp.alloc(&d_out, count * row_len);
         if (rc) return rc;
-        d_out = owned;
     }
     merkle::AffineLayout lay{b->lde, b->n_local, 1};
     LAUNCH(ctx, merkle::gather_rows_kernel<merkle::AffineLayout>, cdiv(count * row_len, 256), 256, 0, lay,
            row_len, d_idx, first, count, d_out);
-    rc = QP_OK;
-    if (space != QP_DEVICE) rc = copy_out(ctx, out, QP_HOST, d_out, count * row_len);
-    dev_free(ctx, d_idx);
-    dev_free(ctx, owned);
-    return rc;
+    if (space != QP_DEVICE) return copy_out(ctx, out, QP_HOST, d_out, count * row_len);
+    // device output: the index upload must not outlive the caller's buffer
+    if (idx_host) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return QP_OK;
 }
 
 extern "C" int qp_batch_leaves(const qp_batch* b, size_t first, size_t count, uint64_t* out, int space) {
@@ -1098,10 +1221,12 @@ extern "C" int qp_batch_open_many(const qp_batch* b, const uint64_t* leaf_indice
         if (leaf_indices[i] >= b->n_local) return fail(ctx, QP_ERR_BAD_ARG, "leaf index out of range");
     const unsigned nl = b->tree.shape.num_layers();
     const size_t row_words = (size_t)n * b->leaf_len, path_words = (size_t)n * nl * 4;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TempScope tmp(ctx);
     uint64_t* d_idx = nullptr;
     uint64_t* d_out = nullptr;
-    int rc = dev_alloc(ctx, &d_idx, n);
-    if (!rc) rc = dev_alloc(ctx, &d_out, row_words + path_words ? row_words + path_words : 1);
+    int rc = tmp.alloc(&d_idx, n);
+    if (!rc) rc = tmp.alloc(&d_out, row_words + path_words ? row_words + path_words : 1);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(d_idx, leaf_indices, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (row_words) {
@@ -1118,8 +1243,6 @@ extern "C" int qp_batch_open_many(const qp_batch* b, const uint64_t* leaf_indice
         std::memcpy(rows_out, host.data(), row_words * 8);
         if (path_words) std::memcpy(siblings_out, host.data() + row_words, path_words * 8);
     }
-    dev_free(ctx, d_idx);
-    dev_free(ctx, d_out);
     return rc;
 }
 
@@ -1395,11 +1518,20 @@ extern "C" int qp_poseidon_permute(qp_ctx* ctx, uint64_t* states, int space, siz
 // coset FFT of device-resident vectors; output bit-reversed in `dst` (device).
 static int coset_fft_device(qp_ctx* ctx, const uint64_t* d_src, uint64_t* d_dst, size_t n_vec, unsigned lg_n,
                             uint64_t shift) {
-    ScaleTables st;
-    bool scaled = gl::canon(shift) != 1;
-    if (scaled) {
-        int rc = build_scale(ctx, (int)lg_n, std::vector<uint64_t>{shift}, &st);
-        if (rc) return rc;
+    // shift tables are cached per (size, shift): a FRI fold round then costs no allocation and no
+    // host round trip (the shifts of a proof are g^(arity^round): a handful of values per size)
+    const ScaleTables* st = nullptr;
+    if (gl::canon(shift) != 1) {
+        std::vector<uint64_t> key = {(uint64_t)lg_n, gl::canon(shift), ~0ULL, ~0ULL};
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        auto it = ctx->scale_cache.find(key);
+        if (it == ctx->scale_cache.end()) {
+            ScaleTables t;
+            int rc = build_scale(ctx, (int)lg_n, std::vector<uint64_t>{shift}, &t);
+            if (rc) return rc;
+            it = ctx->scale_cache.emplace(key, t).first;
+        }
+        st = &it->second;
     }
     NttJob job;
     job.src = d_src;
@@ -1407,13 +1539,8 @@ static int coset_fft_device(qp_ctx* ctx, const uint64_t* d_src, uint64_t* d_dst,
     job.L = (int)lg_n;
     job.n_vec = (unsigned)n_vec;
     job.src_outer = job.dst_outer = (size_t)1 << lg_n;
-    job.scale = scaled ? &st : nullptr;
-    int rc = run_ntt(ctx, job);
-    if (scaled) {
-        cudaStreamSynchronize(ctx->stream);
-        free_scale(&st);
-    }
-    return rc;
+    job.scale = st;
+    return run_ntt(ctx, job);
 }
 
 extern "C" int qp_coset_fft(qp_ctx* ctx, const uint64_t* coeffs, int space, size_t n_vec, unsigned lg_n,
@@ -2345,7 +2472,8 @@ extern "C" void qp_circuit_free(qp_circuit* c) {
     dev_free(c->ctx, c->pool);
     dev_free(c->ctx, c->zh);
     cudaStreamSynchronize(c->ctx->stream);
-    free_scale(&c->g_inv);
+    dev_free(c->ctx, c->g_inv.lo);
+    dev_free(c->ctx, c->g_inv.hi);
     delete c;
 }
 

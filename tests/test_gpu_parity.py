@@ -348,11 +348,10 @@ def test_challenger_matches_oracle(qp):
 # ---- BASELINE.json full-size configurations: size-independent properties -------------------------
 
 def test_full_size_commit_properties(qp, ctx):
-    """2^20 rows x 135 columns, rate 3, cap 4 (BASELINE.json configs[2]).  The oracle would need
-    ~20 GB and minutes; check instead: (1) random leaves verify against the cap with the
-    ORACLE's verifier, (2) rows are the Horner evaluation of the returned coefficients,
-    (3) the commitment of the first 2 columns alone, restricted to one cap subtree, matches the
-    oracle run on that sub-problem's leaf hashes."""
+    """2^20 rows x 135 columns, rate 3, cap 4 (BASELINE.json configs[2]): size-independent
+    properties -- (1) random leaves verify against the cap with the ORACLE's verifier, (2) rows are
+    the Horner evaluation of the returned coefficients, (3) the forward transform of the coefficients
+    returns the input.  The bit-for-bit comparison with the oracle at this size is the next test."""
     import torch
 
     lg_n, cols, rate, cap_h = 20, 135, 3, 4
@@ -382,6 +381,33 @@ def test_full_size_commit_properties(qp, ctx):
     back = ctx.coset_fft(coeffs[:2], shift=1)
     assert (back == d[:2].cpu().numpy().view(np.uint64)).all()
     print("full-size timing (ms):", b.timing)
+
+
+def test_full_size_commit_equals_oracle(qp, ctx):
+    """2^20 rows x 135 columns, rate 3, cap 4 (BASELINE.json configs[2]) against the oracle AT FULL SIZE
+    (about 21 GB of host memory and half a minute of host time on the GPU box): coefficients, the whole
+    digest array, the cap and sampled LDE rows, bit for bit, on bench.py's own witness."""
+    import torch
+
+    import bench
+
+    lg_n, cols, rate, cap_h = 20, 135, 3, 4
+    d = bench.synth_columns_torch(0, cols, 1 << lg_n, "cuda")
+    host = d.cpu().numpy().view(np.uint64)
+    assert (host == bench.synth_columns_numpy(0, cols, 1 << lg_n)).all()      # both arms of bench.py see one matrix
+    assert int(host.max()) < P
+    b = qp.PolynomialBatch.from_values(ctx, d, rate, False, cap_h)
+    want = oracle.PolynomialBatch.from_values(host, rate, cap_h)
+    assert (b.merkle_tree.cap == want.cap).all(), "cap differs at full size"
+    assert (b.polynomials == want.polynomials).all(), "coefficients differ at full size"
+    assert (b.merkle_tree.digests == want.digests).all(), "digests differ at full size"
+    N = 1 << (lg_n + rate)
+    rng = np.random.default_rng(7)
+    idxs = [0, 1, N // 2, N - 1] + [int(x) for x in rng.integers(0, N, 60)]
+    rows = b.merkle_tree.get_many(idxs)
+    for i, row in zip(idxs, rows):
+        assert (row == want.leaves[i]).all(), "LDE row %d differs at full size" % i
+    b.free()
 
 
 def test_config_c_row_count_commit_properties(qp):
@@ -544,6 +570,29 @@ def test_from_values_pipelined_upload_with_partial_leaf_hashing(qp, ctx, cols, l
     assert (got.polynomials == want.polynomials).all()
     assert (got.merkle_tree.leaves() == want.leaves).all()
     assert got.kernel_ms["leaf_hash"] > 0
+
+
+@pytest.mark.parametrize("cols,lg_n,blinding,pipelined", [(1, 6, False, False), (9, 8, True, False), (5, 8, False, True),
+                                                          (33, 9, True, True), (135, 10, False, True), (50, 11, False, True)])
+def test_from_values_cols_pageable_columns(qp, ctx, cols, lg_n, blinding, pipelined, monkeypatch):
+    """qp_batch_from_values_cols: one separately allocated pageable vector per column (the reference's
+    Vec<PolynomialValues>, oracle.rs:168-175), small (gathered) and large (staged through the pinned ring
+    in 16-column groups, more groups than ring slots) -- the oracle's commitment either way."""
+    if pipelined:
+        monkeypatch.setenv("QP_PIPELINE_MIN_BYTES", "1")
+    n = 1 << lg_n
+    vals = oracle.rand_felts((cols, n), 950 + cols)
+    columns = [np.array(vals[c], copy=True) for c in range(cols)]      # separate heap allocations
+    salt = oracle.rand_felts((4, n << 3), 951 + cols) if blinding else None
+    got = qp.PolynomialBatch.from_values_cols(ctx, columns, 3, blinding, 4, salt=salt)
+    want = oracle.PolynomialBatch.from_values(vals, 3, 4, salt=salt)
+    assert (got.merkle_tree.cap == want.cap).all()
+    assert (got.merkle_tree.digests == want.digests).all()
+    assert (got.polynomials == want.polynomials).all()
+    assert (got.merkle_tree.leaves() == want.leaves).all()
+    with pytest.raises(qp.QpError) as e:
+        qp.PolynomialBatch.from_values_cols(ctx, columns[:1] + [columns[0][: n // 2]], 3, False, 4)
+    assert e.value.code == 4   # "Polynomial degrees inconsistent" (oracle.rs:277)
 
 
 @pytest.mark.parametrize("cols,lg_n,blinding,first,count", [(7, 8, False, 0, 8), (19, 10, True, 0, 8), (35, 9, False, 4, 4),
