@@ -313,6 +313,83 @@ __device__ __forceinline__ uint64_t pow(uint64_t a, uint64_t e) {
 }
 
 
+// ---- lazy (redundant) form for butterfly networks -----------------------------------------------
+// Inside a radix-2^R butterfly a value is carried as three 32-bit words  w0 + w1 B + w2 B^2  (B = 2^32)
+// whose top word is a SMALL SIGNED integer: addition and subtraction are then plain 3-word carry chains
+// (3 IADD3 each, no modular fix-up -- the two-fix gl::add / gl::sub cost 8), and a multiplication by 2^s,
+// the only twiddle a radix-16 butterfly needs in this field (w_64 = 8), is a funnel shift followed by
+// the fold  B^2 = B - 1, B^3 = -1, B^4 = -B, B^5 = 1 - B  back to two words plus a small carry.
+// Bounds: lz_from gives |x| < 2^64 and lz_mul_pow2 gives |x| < 2^66; each lz_add / lz_sub at most doubles
+// the bound, so after the <= 4 levels of a radix-16 butterfly |x| < 2^70: w2 stays in [-64, 63], and a
+// shift by r <= 31 bits fits the fourth word that lz_mul_pow2 computes.
+struct lz {
+    uint32_t w0, w1, w2;
+};
+__device__ __forceinline__ lz lz_from(uint64_t x) {
+    lz r;
+    unpack(x, r.w0, r.w1);
+    r.w2 = 0;
+    return r;
+}
+__device__ __forceinline__ lz lz_add(const lz& a, const lz& b) {
+    lz r;
+    asm("add.cc.u32 %0, %3, %6;\n\taddc.cc.u32 %1, %4, %7;\n\taddc.u32 %2, %5, %8;"
+        : "=&r"(r.w0), "=&r"(r.w1), "=&r"(r.w2)
+        : "r"(a.w0), "r"(a.w1), "r"(a.w2), "r"(b.w0), "r"(b.w1), "r"(b.w2));
+    return r;
+}
+__device__ __forceinline__ lz lz_sub(const lz& a, const lz& b) {
+    lz r;
+    asm("sub.cc.u32 %0, %3, %6;\n\tsubc.cc.u32 %1, %4, %7;\n\tsubc.u32 %2, %5, %8;"
+        : "=&r"(r.w0), "=&r"(r.w1), "=&r"(r.w2)
+        : "r"(a.w0), "r"(a.w1), "r"(a.w2), "r"(b.w0), "r"(b.w1), "r"(b.w2));
+    return r;
+}
+// a * 2^s mod p for a compile-time-foldable 0 < s < 96.  With s = 32 q + r:  Y = a 2^r as four words
+// (y3 signed), then  Y B^q = u + v B  with
+//   q = 0: u =  y0 - y2 - y3,  v = y1 + y2          q = 1: u = -y1 - y2,  v = y0 + y1 - y3
+//   q = 2: u = -y0 - y1 + y3,  v = y0 - y2 - y3
+__device__ __forceinline__ lz lz_mul_pow2(const lz& a, int s) {
+    const int q = s >> 5, r = s & 31;
+    uint32_t y0, y1, y2;
+    int32_t y3;
+    if (r == 0) {
+        y0 = a.w0;
+        y1 = a.w1;
+        y2 = a.w2;
+        y3 = (int32_t)a.w2 >> 31;
+    } else {
+        y0 = a.w0 << r;
+        y1 = __funnelshift_l(a.w0, a.w1, r);
+        y2 = __funnelshift_l(a.w1, a.w2, r);
+        y3 = (int32_t)a.w2 >> (32 - r);
+    }
+    int64_t u, v;
+    if (q == 0) {
+        u = (int64_t)(uint64_t)y0 - (int64_t)(uint64_t)y2 - (int64_t)y3;
+        v = (int64_t)((uint64_t)y1 + y2);
+    } else if (q == 1) {
+        u = -(int64_t)((uint64_t)y1 + y2);
+        v = (int64_t)((uint64_t)y0 + y1) - (int64_t)y3;
+    } else {
+        u = (int64_t)y3 - (int64_t)((uint64_t)y0 + y1);
+        v = (int64_t)(uint64_t)y0 - (int64_t)(uint64_t)y2 - (int64_t)y3;
+    }
+    const int64_t t = v + (u >> 32);
+    lz o;
+    o.w0 = (uint32_t)u;
+    o.w1 = (uint32_t)t;
+    o.w2 = (uint32_t)(t >> 32);
+    return o;
+}
+// -> some u64 representative:  w0 + w1 B + w2 (B - 1)  =  (w0 - w2) + (w1 + w2) B, overflow word in {-1, 0, 1}
+__device__ __forceinline__ uint64_t lz_reduce(const lz& a) {
+    const int64_t w2 = (int64_t)(int32_t)a.w2;
+    const int64_t u = (int64_t)(uint64_t)a.w0 - w2;
+    const int64_t v = (int64_t)(uint64_t)a.w1 + w2 + (u >> 32);
+    return add_w_eps(pack((uint32_t)u, (uint32_t)v), (int32_t)(v >> 32));
+}
+
 // ---- host-side helpers (table setup only; never on a data path) ----
 static inline uint64_t host_mul(uint64_t a, uint64_t b) {
     unsigned __int128 x = (unsigned __int128)a * b;

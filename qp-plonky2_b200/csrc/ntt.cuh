@@ -74,9 +74,34 @@ __device__ __forceinline__ int padi(int idx) { return idx + (idx >> 4); }
 
 // In-register 2^R-point DFT, DIF, constant twiddles w_{2^R}^e = 2^(e*192/2^R); register b ends
 // up holding y_{bitrev_R(b)}.
+#ifndef QP_NTT_LAZY   // 1: butterflies in the lazy three-word form (goldilocks.cuh); 0: two-fix modular add / sub
+#define QP_NTT_LAZY 1
+#endif
 template <int R>
 __device__ __forceinline__ void dft_regs(uint64_t (&x)[1 << R]) {
     constexpr int N = 1 << R;
+#if QP_NTT_LAZY
+    gl::lz y[N];
+#pragma unroll
+    for (int q = 0; q < N; q++) y[q] = gl::lz_from(x[q]);
+#pragma unroll
+    for (int u = 0; u < R; u++) {
+        const int half = N >> (u + 1);
+#pragma unroll
+        for (int q = 0; q < N; q++) {
+            if ((q & half) == 0) {
+                const gl::lz a = y[q], b = y[q + half];
+                y[q] = gl::lz_add(a, b);
+                const int e = (q & (half - 1)) << u;  // exponent of w_{2^R}
+                const int sh = e * (192 / N);         // < 96
+                const gl::lz d = gl::lz_sub(a, b);
+                y[q + half] = (e == 0) ? d : gl::lz_mul_pow2(d, sh);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < N; q++) x[q] = gl::lz_reduce(y[q]);
+#else
 #pragma unroll
     for (int u = 0; u < R; u++) {
         const int half = N >> (u + 1);
@@ -92,6 +117,7 @@ __device__ __forceinline__ void dft_regs(uint64_t (&x)[1 << R]) {
             }
         }
     }
+#endif
 }
 
 template <int R>

@@ -806,11 +806,21 @@ static int ifft_device(qp_ctx* ctx, const uint64_t* d_values, size_t n_cols, uns
     return run_ntt(ctx, job);
 }
 
+// QP_STAGE_MODE (measurements): 0 = stage pageable columns through the pinned ring (default), 1 = hand them
+// to cudaMemcpyAsync directly
+static int stage_mode() {
+    static const int v = [] {
+        const char* e = getenv("QP_STAGE_MODE");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
+
 // Host -> pinned staging of pageable columns, a few threads wide (one memcpy thread tops out well
 // below what PCIe 5 moves).
 static void stage_columns(uint64_t* dst, const uint64_t* const* cols, size_t c0, size_t c1, size_t n) {
     const size_t total = (c1 - c0) * n;
-    unsigned n_thr = total * 8 >= ((size_t)8 << 20) ? 4 : 1;
+    unsigned n_thr = total * 8 >= ((size_t)8 << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1;
     const char* e = getenv("QP_STAGE_THREADS");
     if (e) n_thr = (unsigned)std::max(1, atoi(e));
     auto work = [&](unsigned t) {
@@ -886,6 +896,11 @@ static int batch_from_host_columns(qp_ctx* ctx, const uint64_t* const* cols, boo
     auto upload = [&](int g) -> int {
         const size_t c0 = g * per, c1 = std::min(c0 + per, n_cols);
         if (pinned_src) {
+            for (size_t c = c0; c < c1; c++)
+                CUDA_TRY(ctx, cudaMemcpyAsync(d_values + c * n, cols[c], n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+        } else if (stage_mode() == 1) {
+            // pageable source handed to the driver as it is (the driver stages it; the call returns
+            // once the source has been read)
             for (size_t c = c0; c < c1; c++)
                 CUDA_TRY(ctx, cudaMemcpyAsync(d_values + c * n, cols[c], n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
         } else {
