@@ -199,8 +199,9 @@ def run_reference(args):
 def workload_config(args, world):
     return {"workload": "PolynomialBatch::from_values 2^%d rows x %d cols, rate_bits=%d, cap_height=%d, "
                         "blinding=false (LDE + Poseidon Merkle commit)" % (args.rows_log, COLS, RATE_BITS, CAP_HEIGHT),
-            "parallelism": "single GPU" if world == 1 else "coset-sharded x%d (column-sharded iNTT, "
-                           "NCCL all-gather of coefficients and cap)" % world,
+            "parallelism": "single GPU" if world == 1 else "coset-sharded x%d (column-sharded upload + iNTT, per-owner "
+                           "NCCL broadcasts of 8-column pieces in column order overlapped with LDE + leaf hashing, "
+                           "all-gather of the cap)" % world,
             "l2": "inputs (%.2f GB) and LDE (%.2f GB) exceed the 126 MB L2" % (
                 COLS * 8 * 2 ** args.rows_log / 1e9, COLS * 8 * 2 ** (args.rows_log + RATE_BITS) / 1e9)}
 
@@ -254,29 +255,61 @@ def run_ours(args):
             cap = b.merkle_tree.cap
             return b, cap
     else:
-        pc = qd.padded_cols(COLS, world)
-
-        def ifft_fn(v, rows):
-            out = torch.zeros((rows, n), dtype=torch.int64, device=dev)
-            ctx.ifft_columns(v, out_device=out[: v.shape[0]])
-            return out
+        # coset-sharded commit, pipelined (dist.sharded_commit_pipelined): pieces of 8 columns travel in
+        # global column order, each uploaded + inverse-transformed by its owner on a producer stream (its own
+        # context) and broadcast (NCCL) straight into every rank's coefficient matrix; the main stream extends
+        # and hashes a piece as soon as it is there
+        s2 = torch.cuda.Stream(device=dev)
+        copy_stream = torch.cuda.Stream(device=dev)
+        ctx2 = qp.Context(local, max_lde_log=args.rows_log, stream=s2.cuda_stream)
+        d_in = torch.empty((c_hi - c_lo, n), dtype=torch.int64, device=dev)   # staging of this rank's host columns
+        cur = {}
 
         def begin_fn(first, count):
-            return qp.PolynomialBatch.begin(ctx, COLS, args.rows_log, RATE_BITS, False, CAP_HEIGHT,
-                                            block_first=first, block_count=count)
+            b = qp.PolynomialBatch.begin(ctx, COLS, args.rows_log, RATE_BITS, False, CAP_HEIGHT,
+                                         block_first=first, block_count=count)
+            ev = torch.cuda.Event()
+            ev.record(stream)          # the coefficient matrix is a stream-ordered allocation of the main stream
+            s2.wait_event(ev)
+            return b
 
-        def put_fn(batch, rows, c0):
-            batch.put_coeffs(rows, c0)
+        def produce_fn(b, c0, c1):
+            slot = b.coeffs_slot(c0, c1 - c0)
+            src = cur["src"]
+            with torch.cuda.stream(s2):
+                if src.is_cuda:
+                    v = src[c0 - c_lo: c1 - c_lo]
+                else:
+                    v = d_in[c0 - c_lo: c1 - c_lo]
+                    with torch.cuda.stream(copy_stream):
+                        v.copy_(src[c0 - c_lo: c1 - c_lo], non_blocking=True)
+                        e = torch.cuda.Event()
+                        e.record(copy_stream)
+                    s2.wait_event(e)
+                ctx2.ifft_columns(v, out_device=slot, sync=False)
+            return slot
+
+        def slot_fn(b, c0, c1):
+            return b.coeffs_slot(c0, c1 - c0)
+
+        def broadcast_fn(buf, src_rank):
+            with torch.cuda.stream(s2):    # ordered after the producer's transform (and the allocation)
+                w = dist.broadcast(buf, src_rank, async_op=True)
+            return w.wait                  # called on the main stream: extend / hash wait for the piece
+
+        def extend_fn(b, c0, c1):
+            b.extend_columns(c0, c1 - c0, absorb=True)
 
         def end_fn(batch):
             batch.end()
             return batch, torch.from_numpy(batch.merkle_tree.cap.view(np.int64)).to(dev)
 
         def step(src):
-            b, cap = qd.sharded_commit(src, COLS, args.rows_log, RATE_BITS, CAP_HEIGHT, rank=rank, world=world,
-                                       ifft_fn=ifft_fn, begin_fn=begin_fn, put_fn=put_fn, end_fn=end_fn,
-                                       all_gather_fn=qd.torch_all_gather,
-                                       all_gather_async_fn=qd.torch_all_gather_async)
+            cur["src"] = src
+            b, cap = qd.sharded_commit_pipelined(COLS, args.rows_log, RATE_BITS, CAP_HEIGHT, rank=rank, world=world,
+                                                 begin_fn=begin_fn, produce_fn=produce_fn, slot_fn=slot_fn,
+                                                 broadcast_fn=broadcast_fn, extend_fn=extend_fn, end_fn=end_fn,
+                                                 all_gather_fn=qd.torch_all_gather, piece_cols=args.piece_cols)
             return b, cap.cpu().numpy().view(np.uint64)
 
     # ---- device-resident arm ----
@@ -472,6 +505,7 @@ def main():
                     help="commit: PolynomialBatch::from_values (headline); merkle: MerkleTree::new sweep (configs[3])")
     ap.add_argument("--leaves-log", type=int, default=None,
                     help="merkle workload: one size (default: the sweep 2^16..2^24 on the GPU, 2^16..2^20 on the CPU arm)")
+    ap.add_argument("--piece-cols", type=int, default=8, help="N > 1: columns per broadcast piece")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-prove", action="store_true")
     args = ap.parse_args()

@@ -105,6 +105,16 @@ int qp_batch_begin(qp_ctx* ctx, size_t n_cols, unsigned degree_log, unsigned rat
                    unsigned cap_height, unsigned block_first, unsigned block_count, qp_batch** out);
 int qp_batch_put_coeffs(qp_batch* b, const uint64_t* coeffs, int space, size_t c0, size_t count);
 int qp_batch_end(qp_batch* b, const uint64_t* salt, int space);
+/* The same without the copy: qp_batch_coeffs_slot is the device address of column c0's coefficients
+ * inside the batch under construction (2^degree_log words per column, columns contiguous), for a
+ * producer that writes them in place -- an inverse transform (qp_ifft_columns with a QP_DEVICE output), a
+ * collective's receive buffer; qp_batch_extend_columns says "columns [c0, c0 + count) are in place": it
+ * runs their LDE and, if `absorb`, advances the leaf sponges over every complete 8-column chunk of the
+ * column prefix extended so far, so that leaf hashing overlaps the arrival of later columns (the sponge
+ * of hash_leaf, core/src/hashing.rs:150-168, absorbs the columns strictly in order).  The writes into the
+ * slot must be ordered before the call on the context's stream. */
+uint64_t* qp_batch_coeffs_slot(qp_batch* b, size_t c0);
+int qp_batch_extend_columns(qp_batch* b, size_t c0, size_t count, int absorb);
 
 /* iNTT of columns only (the "IFFT" scope, oracle.rs:176-180): values[n_cols][n] -> coeffs.
  * Used by the multi-GPU path, which shards columns for the iNTT and cosets for the rest. */

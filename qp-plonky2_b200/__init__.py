@@ -124,6 +124,8 @@ def lib():
         "qp_batch_free": (None, [vp]),
         "qp_batch_begin": (i32, [vp, sz, u32, u32, i32, u32, u32, u32, pp]),
         "qp_batch_put_coeffs": (i32, [vp, vp, i32, sz, sz]),
+        "qp_batch_coeffs_slot": (vp, [vp, sz]),
+        "qp_batch_extend_columns": (i32, [vp, sz, sz, i32]),
         "qp_batch_end": (i32, [vp, vp, i32]),
         "qp_ifft_columns": (i32, [vp, vp, i32, sz, u32, vp, i32]),
         "qp_batch_cap": (i32, [vp, vp, i32]),
@@ -317,8 +319,9 @@ class Context:
         self.check(lib().qp_coset_fft(self._h, p, space, n_vec, lg, shift, int(bit_reversed), _np_ptr(out), QP_HOST))
         return out.reshape(shape)
 
-    def ifft_columns(self, values, out_device=None):
-        """The "IFFT" scope alone (oracle.rs:176-180); out_device: optional torch CUDA tensor."""
+    def ifft_columns(self, values, out_device=None, sync=True):
+        """The "IFFT" scope alone (oracle.rs:176-180); out_device: optional torch CUDA tensor (sync=False
+        leaves the result stream-ordered on the context's stream, no host synchronisation)."""
         p, space, keep, shape = _buf(values)
         n_cols, n = shape
         lg = int(n).bit_length() - 1
@@ -326,7 +329,8 @@ class Context:
             raise QpError(3, "Not a power of two: %d" % n)
         if out_device is not None:
             self.check(lib().qp_ifft_columns(self._h, p, space, n_cols, lg, C.c_void_p(out_device.data_ptr()), QP_DEVICE))
-            self.synchronize()
+            if sync:
+                self.synchronize()
             return out_device
         out = np.zeros((n_cols, n), dtype=np.uint64)
         self.check(lib().qp_ifft_columns(self._h, p, space, n_cols, lg, _np_ptr(out), QP_HOST))
@@ -549,6 +553,27 @@ class PolynomialBatch:
         if len(shape) != 2 or shape[1] != 1 << self.degree_log:
             raise QpError(4, "Polynomial degrees inconsistent")
         self.ctx.check(lib().qp_batch_put_coeffs(self._h, p, space, c0, shape[0]))
+
+    def coeffs_slot(self, c0, count):
+        """Device view (torch int64 tensor [count][n], zero-copy) of coefficient columns [c0, c0 + count) of
+        a batch under construction: a producer (inverse transform, collective) writes them in place, then
+        extend_columns(c0, count) runs their LDE."""
+        import torch
+
+        n = 1 << self.degree_log
+        ptr = lib().qp_batch_coeffs_slot(self._h, c0)
+        if not ptr or c0 + count > self.n_cols:
+            raise QpError(5, "column range out of bounds")
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (count, n), "typestr": "<i8", "data": (int(ptr), False), "version": 3}
+
+        return torch.as_tensor(_Raw(), device=torch.device("cuda", self.ctx.device))
+
+    def extend_columns(self, c0, count, absorb=True):
+        """Columns [c0, c0 + count) are in place (coeffs_slot): LDE now; with `absorb` the leaf sponges also
+        advance over every complete 8-column chunk of the extended column prefix."""
+        self.ctx.check(lib().qp_batch_extend_columns(self._h, c0, count, int(bool(absorb))))
 
     def end(self, salt=None):
         sp, sspace, skeep = None, QP_HOST, None

@@ -643,6 +643,12 @@ struct qp_batch {
     TreeBuf tree;                // local tree: lg_leaves = log2(n_local), local cap height
     float ms[4] = {0, 0, 0, 0};
     float ms_leaf_hash = 0, ms_tree_levels = 0;
+    // a batch under construction (qp_batch_begin .. qp_batch_end): which columns have their LDE, how
+    // far the leaf sponges have absorbed the column prefix, and their state ([12][n_local])
+    std::vector<uint8_t> col_ready;
+    size_t cols_prefix = 0;
+    unsigned chunks_done = 0;
+    uint64_t* sponge_state = nullptr;
 };
 
 static bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
@@ -1074,6 +1080,34 @@ extern "C" int qp_batch_begin(qp_ctx* ctx, size_t n_cols, unsigned degree_log, u
     return QP_OK;
 }
 
+// The LDE of columns [c0, c0 + count) of a batch under construction (their coefficients are in place),
+// and -- when `absorb` -- the leaf sponges advanced over every complete 8-column chunk of the column
+// PREFIX that is now extended (merkle::leaf_hash_kernel in pieces): with columns arriving in order, the
+// hashing of the early columns overlaps the arrival of the late ones, and qp_batch_end only has the last
+// chunk left.
+static int batch_extend(qp_batch* b, size_t c0, size_t count, bool absorb) {
+    qp_ctx* ctx = b->ctx;
+    int rc = batch_lde_columns(b, c0, c0 + count);
+    if (rc) return rc;
+    if (b->col_ready.size() != b->n_cols) b->col_ready.assign(b->n_cols, 0);
+    for (size_t c = c0; c < c0 + count; c++) b->col_ready[c] = 1;
+    while (b->cols_prefix < b->n_cols && b->col_ready[b->cols_prefix]) b->cols_prefix++;
+    if (!absorb) return QP_OK;
+    const unsigned chunk_end = (unsigned)(b->cols_prefix / 8);
+    const unsigned n_chunks = (unsigned)((b->leaf_len + 7) / 8);
+    if (chunk_end > b->chunks_done && chunk_end < n_chunks) {
+        if (!b->sponge_state) {
+            rc = dev_alloc(ctx, &b->sponge_state, 12 * b->n_local);
+            if (rc) return rc;
+        }
+        merkle::AffineLayout lay{b->lde, b->n_local, 1};
+        rc = hash_leaves(ctx, lay, (unsigned)b->leaf_len, &b->tree, b->chunks_done, chunk_end - b->chunks_done,
+                         b->sponge_state);
+        b->chunks_done = chunk_end;
+    }
+    return rc;
+}
+
 extern "C" int qp_batch_put_coeffs(qp_batch* b, const uint64_t* coeffs, int space, size_t c0, size_t count) {
     if (!b) return QP_ERR_BAD_ARG;
     qp_ctx* ctx = b->ctx;
@@ -1084,21 +1118,41 @@ extern "C" int qp_batch_put_coeffs(qp_batch* b, const uint64_t* coeffs, int spac
     CUDA_TRY(ctx, cudaMemcpyAsync(b->coeffs + c0 * n, coeffs, count * n * 8,
                                   space == QP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     if (space != QP_DEVICE) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the host buffer may go away
-    return batch_lde_columns(b, c0, c0 + count);
+    return batch_extend(b, c0, count, false);
+}
+
+extern "C" uint64_t* qp_batch_coeffs_slot(qp_batch* b, size_t c0) {
+    if (!b || c0 >= b->n_cols) return nullptr;
+    return b->coeffs + (c0 << b->degree_log);
+}
+
+extern "C" int qp_batch_extend_columns(qp_batch* b, size_t c0, size_t count, int absorb) {
+    if (!b) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = b->ctx;
+    if (c0 + count > b->n_cols) return fail(ctx, QP_ERR_BAD_ARG, "column range out of bounds");
+    if (count == 0) return QP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return batch_extend(b, c0, count, absorb != 0);
 }
 
 extern "C" int qp_batch_end(qp_batch* b, const uint64_t* salt, int space) {
     if (!b) return QP_ERR_BAD_ARG;
     qp_ctx* ctx = b->ctx;
     if (b->blinding && !salt) return fail(ctx, QP_ERR_BLINDING_NO_SALT, "Cannot set blinding without salt");
+    if (b->cols_prefix != b->n_cols && !b->col_ready.empty())
+        return fail(ctx, QP_ERR_BAD_ARG, "qp_batch_end before every column was put");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TempScope tmp(ctx);
     const uint64_t* d_salt = nullptr;
-    uint64_t* salt_owned = nullptr;
     int rc = QP_OK;
-    if (b->blinding)
+    if (b->blinding) {
+        uint64_t* salt_owned = nullptr;
         rc = to_device(ctx, salt, space, (size_t)QP_SALT_SIZE << (b->degree_log + b->rate_bits), &d_salt, &salt_owned);
-    if (!rc) rc = batch_finish(b, d_salt);
-    dev_free(ctx, salt_owned);
+        tmp.adopt(salt_owned);
+    }
+    if (!rc) rc = batch_finish(b, d_salt, b->chunks_done, b->sponge_state);
+    dev_free(ctx, b->sponge_state);
+    b->sponge_state = nullptr;
     return rc;
 }
 
@@ -1131,6 +1185,7 @@ extern "C" void qp_batch_free(qp_batch* b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
     dev_free(b->ctx, b->coeffs);
+    dev_free(b->ctx, b->sponge_state);
     dev_free(b->ctx, b->lde);
     dev_free(b->ctx, b->tree.digests);
     dev_free(b->ctx, b->tree.cap);

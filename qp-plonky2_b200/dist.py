@@ -82,6 +82,48 @@ def sharded_commit(values_local, n_cols, degree_log, rate_bits, cap_height, *, r
     return batch, cap_full
 
 
+# ---- the pipelined form: per-owner broadcasts in global column order ------------------------------
+# hash_leaf's sponge absorbs the columns strictly in order (core/src/hashing.rs:150-168), so what hides
+# communication behind hashing is the arrival ORDER: the columns travel as small pieces in global column
+# order, each broadcast from the rank that owns (uploads + inverse-transforms) it straight into every
+# rank's coefficient matrix; a rank extends a piece to its cosets and advances its leaf sponges as soon
+# as the piece is there, while the later pieces -- the other ranks' uploads, transforms and broadcasts --
+# are still in flight.  Only the very first piece has nothing to hide behind.
+
+def pipeline_pieces(n_cols: int, world: int, piece_cols: int = 8):
+    """The global column order cut into pieces of at most piece_cols columns that never straddle an
+    owner: [(owner, c0, c1)]."""
+    out = []
+    for r in range(world):
+        lo, hi = column_shard(n_cols, world, r)
+        for c0 in range(lo, hi, piece_cols):
+            out.append((r, c0, min(c0 + piece_cols, hi)))
+    return out
+
+
+def sharded_commit_pipelined(n_cols, degree_log, rate_bits, cap_height, *, rank, world, begin_fn, produce_fn,
+                             slot_fn, broadcast_fn, extend_fn, end_fn, all_gather_fn, piece_cols=8):
+    """begin_fn(block_first, block_count) -> batch under construction
+    produce_fn(batch, c0, c1) -> buffer: this rank owns columns [c0, c1): put their coefficients in place
+                                (upload + inverse transform into the batch's coefficient matrix)
+    slot_fn(batch, c0, c1)    -> buffer: where columns [c0, c1) of another owner are to be received
+    broadcast_fn(buffer, src) -> wait: start the broadcast from rank src; wait() orders the consumer after it
+    extend_fn(batch, c0, c1)  -> LDE of the columns to this rank's cosets + leaf sponges over the prefix
+    end_fn(batch) -> (batch, cap_local [k][4]);  all_gather_fn(cap_local) -> cap [2^cap_height][4]
+    Every rank issues the same broadcasts in the same order (a collective); nothing else is exchanged."""
+    first, count = block_shard(rate_bits, cap_height, world, rank)
+    batch = begin_fn(first, count)
+    pending = []
+    for owner, c0, c1 in pipeline_pieces(n_cols, world, piece_cols):
+        buf = produce_fn(batch, c0, c1) if owner == rank else slot_fn(batch, c0, c1)
+        pending.append((c0, c1, broadcast_fn(buf, owner)))
+    for c0, c1, wait in pending:
+        wait()
+        extend_fn(batch, c0, c1)
+    batch, cap_local = end_fn(batch)
+    return batch, all_gather_fn(cap_local)
+
+
 # ---- torch.distributed glue (NCCL on GPUs, gloo on CPU) --------------------------------------
 
 def torch_all_gather(x, group=None):
@@ -95,6 +137,21 @@ def torch_all_gather(x, group=None):
     out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     dist.all_gather_into_tensor(out, t, group=group)
     return out.numpy().view(np.uint64) if is_np else out
+
+
+def torch_broadcast_async(x, src, group=None):
+    """Broadcast x (torch tensor, or numpy uint64 array updated in place) from rank src, started
+    asynchronously: -> wait.  NCCL: the collective is ordered after the work already queued on the CURRENT
+    stream, and wait() makes the stream that is current THEN wait for it; gloo: wait() blocks the host."""
+    import torch
+    import torch.distributed as dist
+
+    if isinstance(x, np.ndarray):
+        t = torch.from_numpy(x.view(np.int64))      # shares memory: the broadcast lands in x
+        work = dist.broadcast(t, src, group=group, async_op=True)
+        return work.wait
+    work = dist.broadcast(x, src, group=group, async_op=True)
+    return work.wait
 
 
 def torch_all_gather_async(x, group=None):

@@ -64,6 +64,82 @@ def _worker(rank, world, port, n_cols, lg_n, rate, cap_h, ret):
         dist.destroy_process_group()
 
 
+def _worker_pipelined(rank, world, port, n_cols, lg_n, rate, cap_h, piece_cols, ret):
+    import torch.distributed as dist
+
+    import oracle
+    import qp_plonky2_b200.dist as qd
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 1 << lg_n
+        vals = oracle.rand_felts((n_cols, n), 43)
+        want = oracle.PolynomialBatch.from_values(vals, rate, cap_h)
+        lo, hi = qd.column_shard(n_cols, world, rank)
+        state = {"order": []}
+
+        def begin_fn(first, count):
+            state["first"], state["count"] = first, count
+            return np.zeros((n_cols, n), dtype=np.uint64)           # the coefficient matrix under construction
+
+        def produce_fn(coeffs, c0, c1):
+            assert lo <= c0 < c1 <= hi, "asked to produce a column this rank does not own"
+            for c in range(c0, c1):
+                coeffs[c] = oracle.ifft(vals[c])
+            return coeffs[c0:c1]
+
+        def slot_fn(coeffs, c0, c1):
+            assert c1 <= lo or c0 >= hi, "a foreign slot inside this rank's own shard"
+            return coeffs[c0:c1]
+
+        def extend_fn(coeffs, c0, c1):
+            assert (coeffs[c0:c1] == want.polynomials[c0:c1]).all(), "piece arrived wrong or late"
+            state["order"].append((c0, c1))
+
+        def end_fn(coeffs):
+            assert state["order"] == [(a, b) for _, a, b in qd.pipeline_pieces(n_cols, world, piece_cols)]
+            assert state["order"][0][0] == 0 and state["order"][-1][1] == n_cols   # global column order, complete
+            b = oracle.PolynomialBatch.from_coeffs(coeffs, rate, cap_h)
+            per_block = (1 << cap_h) >> rate
+            first, count = state["first"], state["count"]
+            return b, b.cap[first * per_block: (first + count) * per_block].copy()
+
+        _, cap = qd.sharded_commit_pipelined(n_cols, lg_n, rate, cap_h, rank=rank, world=world, begin_fn=begin_fn,
+                                             produce_fn=produce_fn, slot_fn=slot_fn,
+                                             broadcast_fn=qd.torch_broadcast_async, extend_fn=extend_fn, end_fn=end_fn,
+                                             all_gather_fn=qd.torch_all_gather, piece_cols=piece_cols)
+        ret[rank] = bool((cap == want.cap).all())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_cols,piece_cols", [(2, 5, 8), (2, 19, 4), (4, 35, 8), (4, 7, 1)])
+def test_sharded_commit_pipelined_plumbing(world, n_cols, piece_cols):
+    """The per-owner broadcast pipeline (dist.sharded_commit_pipelined): every rank sees every column exactly
+    once, in global column order, with the owner's coefficients, and the gathered cap is the oracle's."""
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_pipelined, args=(world, port, n_cols, 6, 3, 4, piece_cols, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def test_pipeline_pieces():
+    import qp_plonky2_b200.dist as qd
+
+    for n_cols, world, pc in [(135, 8, 8), (135, 2, 8), (143, 4, 16), (5, 8, 8), (400, 8, 8)]:
+        pieces = qd.pipeline_pieces(n_cols, world, pc)
+        assert pieces[0][1] == 0 and pieces[-1][2] == n_cols
+        assert all(a[2] == b[1] for a, b in zip(pieces, pieces[1:]))             # contiguous, in order
+        for owner, c0, c1 in pieces:
+            lo, hi = qd.column_shard(n_cols, world, owner)
+            assert lo <= c0 < c1 <= hi and c1 - c0 <= pc                        # never straddles an owner
+
+
 @pytest.mark.parametrize("world,n_cols", [(2, 5), (2, 8), (4, 7), (2, 19), (4, 35)])
 def test_sharded_commit_plumbing(world, n_cols):
     import torch.multiprocessing as mp

@@ -619,6 +619,45 @@ def test_batch_in_pieces_equals_from_coeffs(qp, ctx, cols, lg_n, blinding, first
 
 # ---- BatchMerkleTree (the oracle of batch FRI) ---------------------------------
 
+@pytest.mark.parametrize("cols,lg_n,blinding,first,count,piece,in_order", [
+    (7, 8, False, 0, 8, 8, True), (19, 10, True, 0, 8, 8, True), (35, 9, False, 4, 4, 5, True),
+    (135, 8, False, 0, 8, 8, True), (33, 7, False, 6, 2, 8, False), (16, 6, True, 0, 8, 3, False)])
+def test_batch_extend_columns_in_place_with_sponge_absorption(qp, ctx, cols, lg_n, blinding, first, count, piece, in_order):
+    """qp_batch_coeffs_slot / qp_batch_extend_columns: coefficients written in place (as a collective's
+    receive buffer would be), extended piece by piece with the leaf sponges advancing over the completed
+    column prefix -- the batch from_coeffs gives, for in-order and out-of-order arrival, salted or not,
+    whole or a coset shard."""
+    import torch
+
+    n = 1 << lg_n
+    co = oracle.rand_felts((cols, n), 820 + cols)
+    salt = oracle.rand_felts((4, n << 3), 821 + cols) if blinding else None
+    want = qp.PolynomialBatch.from_coeffs(ctx, co, 3, blinding, 4, salt=salt, block_first=first, block_count=count)
+    b = qp.PolynomialBatch.begin(ctx, cols, lg_n, 3, blinding, 4, block_first=first, block_count=count)
+    starts = list(range(0, cols, piece))
+    if not in_order:
+        starts = starts[1::2] + starts[0::2]
+    d_co = torch.from_numpy(co.view(np.int64)).cuda()
+    for c0 in starts:
+        k = min(piece, cols - c0)
+        b.coeffs_slot(c0, k).copy_(d_co[c0:c0 + k])
+        torch.cuda.synchronize()
+        b.extend_columns(c0, k, absorb=True)
+    b.end(salt=salt)
+    assert (b.merkle_tree.cap == want.merkle_tree.cap).all()
+    assert (b.merkle_tree.digests == want.merkle_tree.digests).all()
+    assert (b.polynomials == want.polynomials).all()
+    assert (b.merkle_tree.leaves() == want.merkle_tree.leaves()).all()
+    with pytest.raises(qp.QpError):
+        b.extend_columns(cols, 1)
+    b2 = qp.PolynomialBatch.begin(ctx, cols, lg_n, 3, False, 4)
+    b2.extend_columns(0, 1)
+    if cols > 1:
+        with pytest.raises(qp.QpError):
+            b2.end()          # columns missing
+    b2.free()
+
+
 @pytest.mark.parametrize("shapes,cap_h", [([(4, 2)], 0), ([(4, 2), (2, 3)], 0), ([(64, 7), (16, 3), (8, 20)], 2),
                                            ([(4096, 135), (512, 9), (32, 1)], 4), ([(256, 0), (16, 4)], 4),
                                            ([(1 << 14, 20), (1 << 13, 16)], 4)])
