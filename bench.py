@@ -227,7 +227,10 @@ def run_ours(args):
         import torch.distributed as dist
 
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # high-priority NCCL stream: a broadcast kernel launched while a leaf-hash kernel (thousands of blocks)
+        # is running must not queue behind all of that kernel's blocks, or every piece of the pipeline pays it
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=not os.environ.get("QP_BENCH_LOW_PRIO"))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     # one stream for torch (NCCL, tensor ops) and the library, so their work is ordered
@@ -259,7 +262,7 @@ def run_ours(args):
         # global column order, each uploaded + inverse-transformed by its owner on a producer stream (its own
         # context) and broadcast (NCCL) straight into every rank's coefficient matrix; the main stream extends
         # and hashes a piece as soon as it is there
-        s2 = torch.cuda.Stream(device=dev)
+        s2 = torch.cuda.Stream(device=dev, priority=0 if os.environ.get("QP_BENCH_LOW_PRIO") else -1)  # producer: ahead of the hashing
         copy_stream = torch.cuda.Stream(device=dev)
         ctx2 = qp.Context(local, max_lde_log=args.rows_log, stream=s2.cuda_stream)
         d_in = torch.empty((c_hi - c_lo, n), dtype=torch.int64, device=dev)   # staging of this rank's host columns
@@ -271,10 +274,11 @@ def run_ours(args):
             ev = torch.cuda.Event()
             ev.record(stream)          # the coefficient matrix is a stream-ordered allocation of the main stream
             s2.wait_event(ev)
+            cur["coeffs"] = b.coeffs_slot(0, COLS)      # one zero-copy view of the whole matrix, sliced per piece
             return b
 
         def produce_fn(b, c0, c1):
-            slot = b.coeffs_slot(c0, c1 - c0)
+            slot = cur["coeffs"][c0:c1]
             src = cur["src"]
             with torch.cuda.stream(s2):
                 if src.is_cuda:
@@ -290,7 +294,7 @@ def run_ours(args):
             return slot
 
         def slot_fn(b, c0, c1):
-            return b.coeffs_slot(c0, c1 - c0)
+            return cur["coeffs"][c0:c1]
 
         def broadcast_fn(buf, src_rank):
             with torch.cuda.stream(s2):    # ordered after the producer's transform (and the allocation)
@@ -309,7 +313,8 @@ def run_ours(args):
             b, cap = qd.sharded_commit_pipelined(COLS, args.rows_log, RATE_BITS, CAP_HEIGHT, rank=rank, world=world,
                                                  begin_fn=begin_fn, produce_fn=produce_fn, slot_fn=slot_fn,
                                                  broadcast_fn=broadcast_fn, extend_fn=extend_fn, end_fn=end_fn,
-                                                 all_gather_fn=qd.torch_all_gather, piece_cols=args.piece_cols)
+                                                 all_gather_fn=qd.torch_all_gather, piece_cols=args.piece_cols,
+                                                 lookahead=args.lookahead)
             return b, cap.cpu().numpy().view(np.uint64)
 
     # ---- device-resident arm ----
@@ -506,6 +511,7 @@ def main():
     ap.add_argument("--leaves-log", type=int, default=None,
                     help="merkle workload: one size (default: the sweep 2^16..2^24 on the GPU, 2^16..2^20 on the CPU arm)")
     ap.add_argument("--piece-cols", type=int, default=8, help="N > 1: columns per broadcast piece")
+    ap.add_argument("--lookahead", type=int, default=3, help="N > 1: pieces the host issues ahead of the consumer")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-prove", action="store_true")
     args = ap.parse_args()

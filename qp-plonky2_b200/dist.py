@@ -102,7 +102,7 @@ def pipeline_pieces(n_cols: int, world: int, piece_cols: int = 8):
 
 
 def sharded_commit_pipelined(n_cols, degree_log, rate_bits, cap_height, *, rank, world, begin_fn, produce_fn,
-                             slot_fn, broadcast_fn, extend_fn, end_fn, all_gather_fn, piece_cols=8):
+                             slot_fn, broadcast_fn, extend_fn, end_fn, all_gather_fn, piece_cols=8, lookahead=3):
     """begin_fn(block_first, block_count) -> batch under construction
     produce_fn(batch, c0, c1) -> buffer: this rank owns columns [c0, c1): put their coefficients in place
                                 (upload + inverse transform into the batch's coefficient matrix)
@@ -113,12 +113,20 @@ def sharded_commit_pipelined(n_cols, degree_log, rate_bits, cap_height, *, rank,
     Every rank issues the same broadcasts in the same order (a collective); nothing else is exchanged."""
     first, count = block_shard(rate_bits, cap_height, world, rank)
     batch = begin_fn(first, count)
-    pending = []
-    for owner, c0, c1 in pipeline_pieces(n_cols, world, piece_cols):
+    pieces = pipeline_pieces(n_cols, world, piece_cols)
+    waits = []
+
+    def issue():
+        owner, c0, c1 = pieces[len(waits)]
         buf = produce_fn(batch, c0, c1) if owner == rank else slot_fn(batch, c0, c1)
-        pending.append((c0, c1, broadcast_fn(buf, owner)))
-    for c0, c1, wait in pending:
-        wait()
+        waits.append(broadcast_fn(buf, owner))
+
+    # the host stays `lookahead` pieces ahead of the consumer: far enough that transfers overlap compute,
+    # near enough that the first extend is queued before the host has walked the whole list
+    for k, (_, c0, c1) in enumerate(pieces):
+        while len(waits) < min(len(pieces), k + 1 + lookahead):
+            issue()
+        waits[k]()
         extend_fn(batch, c0, c1)
     batch, cap_local = end_fn(batch)
     return batch, all_gather_fn(cap_local)
