@@ -90,6 +90,31 @@ int qp_batch_from_values_cols(qp_ctx* ctx, const uint64_t* const* cols, size_t n
                               unsigned degree_log, unsigned rate_bits, int blinding, unsigned cap_height,
                               const uint64_t* salt, unsigned block_first, unsigned block_count,
                               qp_batch** out);
+/* ---- multi-device context: one process, a list of GPUs ----------------------------------------- */
+/* The reference's from_values is one call in one process (oracle.rs:168-175); this is that call over
+ * every GPU of the box.  The devices (a power of two of them, <= 2^rate_bits and <= 2^cap_height at commit
+ * time) shard the commitment by coset = by cap subtree: columns are sharded for the
+ * upload + inverse transform, coefficient pieces move device to device as peer copies over NVLink in
+ * column order, device i extends all columns to coset blocks [i 2^r / D, (i + 1) 2^r / D) and hashes exactly
+ * those leaves.  Shard i is an ordinary qp_batch living on devices[i] (its leaf indices are local: global
+ * leaf = i * (N / D) + local), to be read with the qp_batch_* getters through qp_mctx_ctx(m, i)'s stream. */
+typedef struct qp_mctx qp_mctx;
+typedef struct qp_mbatch qp_mbatch;
+int qp_mctx_create(const int* devices, unsigned n_devices, unsigned max_lde_log, qp_mctx** out);
+void qp_mctx_destroy(qp_mctx* m);
+unsigned qp_mctx_num_devices(const qp_mctx* m);
+qp_ctx* qp_mctx_ctx(qp_mctx* m, unsigned i);
+const char* qp_mctx_last_error(const qp_mctx* m);
+/* cols[c]: column c, 2^degree_log words of ordinary host memory; salt: host, [QP_SALT_SIZE][N], iff blinding */
+int qp_mbatch_from_values_cols(qp_mctx* m, const uint64_t* const* cols, size_t n_cols, unsigned degree_log,
+                               unsigned rate_bits, int blinding, unsigned cap_height, const uint64_t* salt,
+                               qp_mbatch** out);
+/* the whole cap, [2^cap_height][4], host */
+int qp_mbatch_cap(const qp_mbatch* b, uint64_t* out);
+unsigned qp_mbatch_num_shards(const qp_mbatch* b);
+qp_batch* qp_mbatch_shard(qp_mbatch* b, unsigned i);   /* owned by the mbatch */
+void qp_mbatch_free(qp_mbatch* b);
+
 /* PolynomialBatch::from_coeffs (oracle.rs:193-223). */
 int qp_batch_from_coeffs(qp_ctx* ctx, const uint64_t* coeffs, int space, size_t n_cols,
                          unsigned degree_log, unsigned rate_bits, int blinding, unsigned cap_height,

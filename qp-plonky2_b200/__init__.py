@@ -121,6 +121,16 @@ def lib():
         "qp_batch_from_values": (i32, [vp, vp, i32, sz, u32, u32, i32, u32, vp, u32, u32, pp]),
         "qp_batch_from_coeffs": (i32, [vp, vp, i32, sz, u32, u32, i32, u32, vp, u32, u32, pp]),
         "qp_batch_from_values_cols": (i32, [vp, vp, sz, u32, u32, i32, u32, vp, u32, u32, pp]),
+        "qp_mctx_create": (i32, [vp, u32, u32, pp]),
+        "qp_mctx_destroy": (None, [vp]),
+        "qp_mctx_num_devices": (u32, [vp]),
+        "qp_mctx_ctx": (vp, [vp, u32]),
+        "qp_mctx_last_error": (C.c_char_p, [vp]),
+        "qp_mbatch_from_values_cols": (i32, [vp, vp, sz, u32, u32, i32, u32, vp, pp]),
+        "qp_mbatch_cap": (i32, [vp, vp]),
+        "qp_mbatch_num_shards": (u32, [vp]),
+        "qp_mbatch_shard": (vp, [vp, u32]),
+        "qp_mbatch_free": (None, [vp]),
         "qp_batch_free": (None, [vp]),
         "qp_batch_begin": (i32, [vp, sz, u32, u32, i32, u32, u32, u32, pp]),
         "qp_batch_put_coeffs": (i32, [vp, vp, i32, sz, sz]),
@@ -335,6 +345,107 @@ class Context:
         out = np.zeros((n_cols, n), dtype=np.uint64)
         self.check(lib().qp_ifft_columns(self._h, p, space, n_cols, lg, _np_ptr(out), QP_HOST))
         return out
+
+
+class _BorrowedContext(Context):
+    """A context owned by someone else (a MultiContext's per-device context): same methods, never destroyed here."""
+
+    def __init__(self, handle, device):
+        self._h = C.c_void_p(handle)
+        self.device = device
+
+    def close(self):
+        self._h = C.c_void_p()
+
+
+class MultiContext:
+    """One process, a list of GPUs (qp_mctx): the coset-sharded commit driven from inside the library, peer
+    copies over NVLink between the devices, no torch.distributed."""
+
+    def __init__(self, devices, max_lde_log: int = 24):
+        self.devices = list(devices)
+        self._h = C.c_void_p()
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        rc = lib().qp_mctx_create(arr, len(self.devices), max_lde_log, C.byref(self._h))
+        if rc:
+            raise QpError(rc, "qp_mctx_create failed (devices must be distinct, a power of two of them)")
+        self.contexts = [_BorrowedContext(lib().qp_mctx_ctx(self._h, i), d) for i, d in enumerate(self.devices)]
+
+    def check(self, rc):
+        if rc:
+            raise QpError(rc, lib().qp_mctx_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            lib().qp_mctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiBatch:
+    """PolynomialBatch::from_values over every device of a MultiContext; `shards[i]` is the PolynomialBatch of
+    device i (coset blocks [i 2^r / D, (i + 1) 2^r / D), leaf indices local to the shard)."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+
+    @classmethod
+    def from_values_cols(cls, mctx, columns, rate_bits, blinding, cap_height, salt=None):
+        cols = [np.ascontiguousarray(np.asarray(c, dtype=np.uint64).ravel()) for c in columns]
+        if len(cols) == 0:
+            raise QpError(5, "polynomials[0]: index out of bounds (empty batch)")
+        if len({c.size for c in cols}) != 1:
+            raise QpError(4, "Polynomial degrees inconsistent")
+        n = cols[0].size
+        lg = int(n).bit_length() - 1
+        if n == 0 or (1 << lg) != n:
+            raise QpError(3, "Not a power of two: %d" % n)
+        sp = skeep = None
+        if blinding:
+            if salt is None:
+                raise QpError(7, "blinding=True needs salt[4][N] (the reference draws it from its RNG)")
+            skeep = np.ascontiguousarray(np.asarray(salt, dtype=np.uint64))
+            sp = _np_ptr(skeep)
+        ptrs = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+        self = cls()
+        self.mctx, self.cap_height = mctx, cap_height
+        mctx.check(lib().qp_mbatch_from_values_cols(mctx._h, ptrs, len(cols), lg, rate_bits, int(bool(blinding)),
+                                                    cap_height, sp, C.byref(self._h)))
+        D = int(lib().qp_mbatch_num_shards(self._h))
+        blocks = (1 << rate_bits) // D
+        self.shards = []
+        for i in range(D):
+            b = PolynomialBatch()
+            b._h = C.c_void_p(lib().qp_mbatch_shard(self._h, i))
+            b.ctx = mctx.contexts[i]
+            b._borrowed = True
+            b._describe(len(cols), lg, rate_bits, blinding, cap_height, i * blocks, blocks)
+            self.shards.append(b)
+        return self
+
+    @property
+    def cap(self):
+        out = np.zeros((1 << self.cap_height, 4), dtype=np.uint64)
+        self.mctx.check(lib().qp_mbatch_cap(self._h, _np_ptr(out)))
+        return out
+
+    def free(self):
+        if self._h:
+            for b in self.shards:
+                b._h = C.c_void_p()
+            lib().qp_mbatch_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class _Cap:
@@ -620,7 +731,7 @@ class PolynomialBatch:
         return lib().qp_batch_device_coeffs(self._h)
 
     def free(self):
-        if self._h and self.ctx._h:
+        if self._h and self.ctx._h and not getattr(self, "_borrowed", False):
             lib().qp_batch_free(self._h)
         self._h = C.c_void_p()
 

@@ -844,6 +844,43 @@ static void stage_columns(uint64_t* dst, const uint64_t* const* cols, size_t c0,
     for (auto& x : th) x.join();
 }
 
+// Make sure the context's pinned ring holds `need` words per slot.
+static int ensure_ring(qp_ctx* ctx, size_t need) {
+    if (ctx->ring_words >= need) return QP_OK;
+    for (auto& r : ctx->ring) {
+        if (r) cudaFreeHost(r);
+        r = nullptr;
+    }
+    ctx->ring_words = 0;
+    for (auto& r : ctx->ring)
+        if (cudaMallocHost((void**)&r, need * 8) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, QP_ERR_TOO_LARGE, "cannot allocate the pinned staging ring");
+        }
+    ctx->ring_words = need;
+    return QP_OK;
+}
+
+// Upload host columns [c0, c1) to d_dst ([c1 - c0][n]) on the context's copy stream and record
+// copy_ev[g % MAX_GROUPS]: as they are when the source is pinned, through the pinned ring (slot g % RING_SLOTS,
+// reused once the copy that last read it has completed) when it is pageable.
+static int upload_columns(qp_ctx* ctx, const uint64_t* const* cols, bool pinned_src, size_t c0, size_t c1, size_t n,
+                          uint64_t* d_dst, int g) {
+    if (pinned_src || stage_mode() == 1) {
+        // (mode 1: pageable source handed to the driver as it is; the call returns once the source has been read)
+        for (size_t c = c0; c < c1; c++)
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_dst + (c - c0) * n, cols[c], n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    } else {
+        uint64_t* slot = ctx->ring[g % qp_ctx::RING_SLOTS];
+        if (g >= qp_ctx::RING_SLOTS)
+            CUDA_TRY(ctx, cudaEventSynchronize(ctx->copy_ev[(g - qp_ctx::RING_SLOTS) % qp_ctx::MAX_GROUPS]));
+        stage_columns(slot, cols, c0, c1, n);
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_dst, slot, (c1 - c0) * n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[g % qp_ctx::MAX_GROUPS], ctx->copy_stream));
+    return QP_OK;
+}
+
 // The commit from HOST columns: `cols[c]` points at column c (2^degree_log words).  Columns travel in
 // groups of 16 (= two 8-element sponge chunks): the upload of group g + 1 overlaps the iNTT + LDE +
 // partial leaf hash of group g.  pinned_src: the columns can be handed to the copy engine as they
@@ -875,20 +912,8 @@ static int batch_from_host_columns(qp_ctx* ctx, const uint64_t* const* cols, boo
     rc = tmp.alloc(&d_state, 12 * b->n_local);
     if (rc) return bail(rc);
     if (!pinned_src) {
-        const size_t need = std::min(per, n_cols) * n;
-        if (ctx->ring_words < need) {
-            for (auto& r : ctx->ring) {
-                if (r) cudaFreeHost(r);
-                r = nullptr;
-            }
-            ctx->ring_words = 0;
-            for (auto& r : ctx->ring)
-                if (cudaMallocHost((void**)&r, need * 8) != cudaSuccess) {
-                    cudaGetLastError();
-                    return bail(fail(ctx, QP_ERR_TOO_LARGE, "cannot allocate the pinned staging ring"));
-                }
-            ctx->ring_words = need;
-        }
+        rc = ensure_ring(ctx, std::min(per, n_cols) * n);
+        if (rc) return bail(rc);
     }
     // the copy stream may only touch d_values once the (stream-ordered) allocation has happened
     cudaEventRecord(ctx->ready_ev, ctx->stream);
@@ -901,23 +926,7 @@ static int batch_from_host_columns(qp_ctx* ctx, const uint64_t* const* cols, boo
     // before queueing its compute, so the host copies group g + 1 while the device works on group g
     auto upload = [&](int g) -> int {
         const size_t c0 = g * per, c1 = std::min(c0 + per, n_cols);
-        if (pinned_src) {
-            for (size_t c = c0; c < c1; c++)
-                CUDA_TRY(ctx, cudaMemcpyAsync(d_values + c * n, cols[c], n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
-        } else if (stage_mode() == 1) {
-            // pageable source handed to the driver as it is (the driver stages it; the call returns
-            // once the source has been read)
-            for (size_t c = c0; c < c1; c++)
-                CUDA_TRY(ctx, cudaMemcpyAsync(d_values + c * n, cols[c], n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
-        } else {
-            uint64_t* slot = ctx->ring[g % qp_ctx::RING_SLOTS];
-            if (g >= qp_ctx::RING_SLOTS) CUDA_TRY(ctx, cudaEventSynchronize(ctx->copy_ev[g - qp_ctx::RING_SLOTS]));
-            stage_columns(slot, cols, c0, c1, n);
-            CUDA_TRY(ctx, cudaMemcpyAsync(d_values + c0 * n, slot, (c1 - c0) * n * 8, cudaMemcpyHostToDevice,
-                                          ctx->copy_stream));
-        }
-        CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[g], ctx->copy_stream));
-        return QP_OK;
+        return upload_columns(ctx, cols, pinned_src, c0, c1, n, d_values + c0 * n, g);
     };
     if (pinned_src)
         for (int g = 0; g < n_groups && !rc; g++) rc = upload(g);
@@ -2738,3 +2747,5 @@ extern "C" int qp_circuit_compute_quotient_polys(qp_circuit* c, const qp_batch* 
     if (!rc) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return rc;
 }
+
+#include "multi_device.inl"

@@ -799,3 +799,51 @@ def test_batch_open_many(qp, ctx):
     with pytest.raises(qp.QpError):
         b.merkle_tree.open_many([1 << 11])
     b.free()
+
+
+# ---- multi-device context (one process, a list of GPUs) ------------------------------------------
+
+def _check_multi(qp, devices, cols, lg_n, blinding, monkeypatch=None):
+    n = 1 << lg_n
+    vals = oracle.rand_felts((cols, n), 970 + cols)
+    columns = [np.array(vals[c], copy=True) for c in range(cols)]
+    salt = oracle.rand_felts((4, n << 3), 971 + cols) if blinding else None
+    want = oracle.PolynomialBatch.from_values(vals, 3, 4, salt=salt)
+    m = qp.MultiContext(devices, max_lde_log=lg_n + 3)
+    try:
+        mb = qp.MultiBatch.from_values_cols(m, columns, 3, blinding, 4, salt=salt)
+        assert (mb.cap == want.cap).all(), "multi-device cap differs from the oracle's"
+        D = len(devices)
+        per_dig = want.digests.shape[0] // D
+        per_leaf = want.leaves.shape[0] // D
+        for i, sh in enumerate(mb.shards):
+            assert (sh.merkle_tree.digests == want.digests[i * per_dig:(i + 1) * per_dig]).all()
+            assert (sh.merkle_tree.leaves() == want.leaves[i * per_leaf:(i + 1) * per_leaf]).all()
+            assert (sh.polynomials == want.polynomials).all()
+            # a local opening verifies against the GLOBAL cap at the global index
+            li = 5 % per_leaf
+            row = sh.merkle_tree.get_many([li])[0]
+            assert oracle.merkle_verify(row, i * per_leaf + li, mb.cap, sh.merkle_tree.prove(li))
+        mb.free()
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("cols,lg_n,blinding", [(5, 6, False), (19, 9, True), (135, 8, False)])
+def test_multi_context_single_device(qp, cols, lg_n, blinding):
+    """qp_mctx_* with one device: the producer / consumer threads, piece events and in-place slots of the
+    multi-device commit on a single GPU -- the oracle's commitment."""
+    _check_multi(qp, [0], cols, lg_n, blinding)
+
+
+@pytest.mark.parametrize("cols,lg_n,blinding", [(5, 6, False), (19, 9, True), (135, 10, False), (40, 12, False)])
+def test_multi_context_all_devices(qp, cols, lg_n, blinding):
+    """One process driving every GPU of the box (2, 4 or 8): coset = cap-subtree shards, coefficient pieces as
+    peer copies in column order, the cap and every shard's digests / rows / openings against the oracle."""
+    import torch
+
+    D = torch.cuda.device_count()
+    D = 8 if D >= 8 else 4 if D >= 4 else 2 if D >= 2 else 1
+    if D < 2:
+        pytest.skip("needs at least two GPUs (run with gpurun --gpus 2)")
+    _check_multi(qp, list(range(D)), cols, lg_n, blinding)
