@@ -196,7 +196,9 @@ extern "C" int qp_mbatch_from_values_cols(qp_mctx* m, const uint64_t* const* col
             if (abort_flag.load()) return QP_OK;
             const size_t c0 = pieces[k].c0, c1 = pieces[k].c1;
             uint64_t* dv = d_values + (c0 - lo) * n;
-            r = upload_columns(ctx, cols, false, c0, c1, n, dv, g);
+            // (columns the caller has pinned -- cudaHostRegister / cudaMallocHost -- skip the staging ring)
+            r = upload_columns(ctx, cols, host_pointer_is_pinned(cols[c0]) && host_pointer_is_pinned(cols[c1 - 1]), c0, c1,
+                               n, dv, g);
             if (r) return r;
             cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[g % qp_ctx::MAX_GROUPS], 0);
             g++;

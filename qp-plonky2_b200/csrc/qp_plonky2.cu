@@ -98,6 +98,7 @@ static int fail(qp_ctx* ctx, int code, const char* msg) {
 static int dev_alloc(qp_ctx* ctx, uint64_t** p, size_t n_words) {
     *p = nullptr;
     if (n_words == 0) return QP_OK;
+    cudaSetDevice(ctx->device);  // a handle may be read while another device is current (multi-device callers)
     cudaError_t e = cudaMallocAsync((void**)p, n_words * 8, ctx->stream);
     if (e != cudaSuccess) {
         ctx->err = std::string("cudaMallocAsync: ") + cudaGetErrorString(e);
@@ -139,6 +140,7 @@ struct TempScope {
 static int copy_out(qp_ctx* ctx, uint64_t* dst, int space, const uint64_t* src_dev, size_t n_words) {
     if (!dst) return fail(ctx, QP_ERR_BAD_ARG, "null output buffer");
     if (n_words == 0) return QP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (space != QP_DEVICE && ctx->stage && n_words <= qp_ctx::STAGE_WORDS) {
         std::lock_guard<std::mutex> lock(ctx->mu);
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage, src_dev, n_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -844,6 +846,15 @@ static void stage_columns(uint64_t* dst, const uint64_t* const* cols, size_t c0,
     for (auto& x : th) x.join();
 }
 
+static bool host_pointer_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
 // Make sure the context's pinned ring holds `need` words per slot.
 static int ensure_ring(qp_ctx* ctx, size_t need) {
     if (ctx->ring_words >= need) return QP_OK;
@@ -975,15 +986,6 @@ static int batch_from_host_columns(qp_ctx* ctx, const uint64_t* const* cols, boo
     return QP_OK;
 }
 
-static bool host_pointer_is_pinned(const void* p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
-}
-
 static size_t pipeline_threshold() {
     // (QP_PIPELINE_MIN_BYTES lowers the threshold so that the tests can drive the pipelined path with small inputs)
     const char* thr_env = getenv("QP_PIPELINE_MIN_BYTES");
@@ -1054,8 +1056,9 @@ extern "C" int qp_batch_from_values_cols(qp_ctx* ctx, const uint64_t* const* col
         if (!cols[c]) return fail(ctx, QP_ERR_BAD_ARG, "null column");
     const size_t n = (size_t)1 << degree_log;
     if (n_cols * n * 8 >= pipeline_threshold() && n_cols >= 2)
-        return batch_from_host_columns(ctx, cols, false, n_cols, degree_log, rate_bits, blinding, cap_height, salt,
-                                       block_first, block_count, out);
+        return batch_from_host_columns(ctx, cols, host_pointer_is_pinned(cols[0]) && host_pointer_is_pinned(cols[n_cols - 1]),
+                                       n_cols, degree_log, rate_bits, blinding, cap_height, salt, block_first,
+                                       block_count, out);
     std::vector<uint64_t> flat(n_cols * n);
     for (size_t c = 0; c < n_cols; c++) std::memcpy(flat.data() + c * n, cols[c], n * 8);
     // (the small-input path synchronises before it returns, so `flat` outlives its upload)
