@@ -196,6 +196,229 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------------------------
+# configs[3]: MerkleTree::new Poseidon sweep, 2^16 .. 2^24 leaves x 135 elements, cap height 4,
+# subtree-sharded at N > 1 (one shard of whole cap subtrees per GPU, qp_merkle_tree_new_shard)
+# ---------------------------------------------------------------------------------------------
+MERKLE_LEAF_LEN = 135
+
+
+def synth_leaves_numpy(first, count, leaf_len=MERKLE_LEAF_LEN, seed=SEED + 1):
+    """Leaf-major rows [count][leaf_len]: element (i, c) = SplitMix64((seed << 40) + i * leaf_len + c), canonical."""
+    out = np.empty((count, leaf_len), dtype=np.uint64)
+    step = 1 << 16
+    with np.errstate(over="ignore"):
+        for r0 in range(0, count, step):
+            r1 = min(r0 + step, count)
+            idx = (np.arange(first + r0, first + r1, dtype=np.uint64)[:, None] * np.uint64(leaf_len)
+                   + np.arange(leaf_len, dtype=np.uint64)[None, :])
+            z = (idx + np.uint64(seed << 40)) * np.uint64(0x9E3779B97F4A7C15)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+            out[r0:r1] = np.where(z >= np.uint64(P_GL), z - np.uint64(P_GL), z)
+    return out
+
+
+def synth_leaves_torch(first, count, dev, leaf_len=MERKLE_LEAF_LEN, seed=SEED + 1):
+    import torch
+
+    def s64(x):
+        x &= (1 << 64) - 1
+        return x - (1 << 64) if x >> 63 else x
+
+    def lsr(z, k):
+        return (z >> k) & ((1 << (64 - k)) - 1)
+
+    out = torch.empty((count, leaf_len), dtype=torch.int64, device=dev)
+    step = 1 << 20
+    col = torch.arange(leaf_len, dtype=torch.int64, device=dev)[None, :]
+    for r0 in range(0, count, step):
+        r1 = min(r0 + step, count)
+        z = torch.arange(first + r0, first + r1, dtype=torch.int64, device=dev)[:, None] * leaf_len + col
+        z = (z + (seed << 40)) * s64(0x9E3779B97F4A7C15)
+        z = (z ^ lsr(z, 30)) * s64(0xBF58476D1CE4E5B9)
+        z = (z ^ lsr(z, 27)) * s64(0x94D049BB133111EB)
+        z = z ^ lsr(z, 31)
+        ge = (z < 0) & (z >= -0xFFFFFFFF)
+        out[r0:r1] = torch.where(ge, z + 0xFFFFFFFF, z)
+    return out
+
+
+def merkle_config(sizes, world):
+    return {"workload": "MerkleTree::new (Poseidon, hash_leaf + two_to_one) sweep: 2^%s leaves x %d Goldilocks elements, "
+                        "cap_height=%d" % ("/".join(str(x) for x in sizes), MERKLE_LEAF_LEN, CAP_HEIGHT),
+            "parallelism": "single GPU" if world == 1 else "subtree-sharded x%d (whole cap subtrees per GPU, no data-path "
+                           "collective; all-gather of the cap)" % world,
+            "l2": "leaves of every size from 2^18 up (%.0f MB at 2^18) exceed the 126 MB L2; the smaller sizes are "
+                  "flushed by the larger ones between timed iterations" % (MERKLE_LEAF_LEN * 8 * 2 ** 18 / 1e6)}
+
+
+def run_reference_merkle(args):
+    oracle, cores = oracle_threads()
+    sizes = [args.leaves_log] if args.leaves_log else [16, 18, 20]
+    sweep = []
+    for L in sizes:
+        leaves = synth_leaves_numpy(0, 1 << L)
+        times = []
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            t = oracle.MerkleTree(leaves, CAP_HEIGHT)
+            dt = (time.perf_counter() - t0) * 1e3
+            if it >= args.warmup:
+                times.append(dt)
+        sweep.append({"leaves_log": L, "ms": sum(times) / len(times), "cap0": [int(x) for x in t.cap[0]]})
+        del t, leaves
+    ms = sweep[-1]["ms"]
+    metric = "merkle_tree_new_ms_2^%dx%d" % (sizes[-1], MERKLE_LEAF_LEN)
+    print(json.dumps({
+        "impl": "reference", "metric": metric, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic", "config": merkle_config(sizes, 1), "sweep": sweep,
+        "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port",
+                         "sample": "oracle MerkleTree::new at full size, every step"},
+        "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_merkle(args):
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    import torch
+
+    import qp_plonky2_b200 as qp
+    import qp_plonky2_b200.dist as qd
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    dist = None
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = qp.Context(local, max_lde_log=4, stream=stream.cuda_stream)
+    sizes = [args.leaves_log] if args.leaves_log else [16, 18, 20, 22, 24]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    sweep = []
+    for L in sizes:
+        n_loc = (1 << L) // world
+        d_leaves = synth_leaves_torch(rank * n_loc, n_loc, dev)
+        torch.cuda.synchronize()
+
+        def step(src):
+            t = qp.MerkleTree(ctx, src, CAP_HEIGHT, shard=rank, n_shards=world)
+            cap = t.cap
+            if dist is not None:
+                cap = qd.torch_all_gather(torch.from_numpy(cap.view(np.int64)).to(dev)).cpu().numpy().view(np.uint64)
+            return t, cap
+
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(args.warmup):
+            step(d_leaves)[0].free()
+        dev_ms, cap = 0.0, None
+        for _ in range(args.steps):
+            barrier()
+            ev0.record(stream)
+            t, cap = step(d_leaves)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            dev_ms += ev0.elapsed_time(ev1)
+            t.free()
+        dev_ms /= args.steps
+        # end to end from pinned host rows (H2D inside), sizes whose leaves fit comfortably in host memory
+        e2e_ms = None
+        if L <= 22:
+            h_leaves = torch.empty(d_leaves.shape, dtype=torch.int64).pin_memory()
+            h_leaves.copy_(d_leaves)
+            torch.cuda.synchronize()
+            for _ in range(min(args.warmup, 2)):
+                step(h_leaves)[0].free()
+            e2e_ms = 0.0
+            for _ in range(args.steps):
+                barrier()
+                t0 = time.perf_counter()
+                t, cap2 = step(h_leaves)
+                torch.cuda.synchronize()
+                e2e_ms += (time.perf_counter() - t0) * 1e3
+                assert (cap2 == cap).all()
+                t.free()
+            e2e_ms /= args.steps
+        tt = torch.tensor([dev_ms, e2e_ms if e2e_ms is not None else 0.0], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_max = [float(x) for x in tt.cpu()]
+        perms = (1 << L) * ((MERKLE_LEAF_LEN + 7) // 8) + (1 << L) - (1 << CAP_HEIGHT)
+        rec = {"leaves_log": L, "ms": dev_ms, "e2e_ms": e2e_max if e2e_ms is not None else None,
+               "permutations_per_s": perms / (dev_ms * 1e-3), "cap0": [int(x) for x in cap[0]]}
+        # the CPU restatement beside it, same rows (rank 0, N = 1, sizes it finishes in seconds)
+        if world == 1 and not args.no_cpu and L <= 20:
+            oracle, cores = oracle_threads()
+            host = d_leaves.cpu().numpy().view(np.uint64)
+            t0 = time.perf_counter()
+            ot = oracle.MerkleTree(host, CAP_HEIGHT)
+            rec["cpu_ms"] = (time.perf_counter() - t0) * 1e3
+            rec["cpu_cores"] = cores
+            rec["cap_equal_cpu"] = bool((ot.cap == cap).all())
+            assert rec["cap_equal_cpu"], "GPU MerkleTree::new cap differs from the CPU oracle's"
+            del ot, host
+        sweep.append(rec)
+        del d_leaves
+        torch.cuda.empty_cache()
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        last = sweep[-1]
+        with_cpu = [r for r in sweep if "cpu_ms" in r]
+        cpu = None
+        if with_cpu:
+            r = with_cpu[-1]
+            cpu = {"value": r["cpu_ms"], "unit": "ms", "cores": r["cpu_cores"], "kind": "port",
+                   "sample": "oracle MerkleTree::new on the same 2^%d x %d rows, full size, 1 run (the largest size the "
+                             "CPU arm runs; GPU value there: %.3f ms)" % (r["leaves_log"], MERKLE_LEAF_LEN, r["ms"])}
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        ipp = 16080.0
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            ipp = float(json.load(open(tp)).get("leaf_hash_kernel", {}).get("instr_per_warp_permutation", ipp))
+        peak_perm = 148 * 4 * sm_mhz * 1e6 * 32 / ipp * world
+        line = {
+            "metric": "merkle_tree_new_ms_2^%dx%d" % (last["leaves_log"], MERKLE_LEAF_LEN), "value": last["ms"], "unit": "ms",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": last["ms"],
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": merkle_config(sizes, world), "sweep": sweep,
+            "e2e": {"value": next((r["e2e_ms"] for r in reversed(sweep) if r["e2e_ms"] is not None), None), "unit": "ms",
+                    "what": "largest size with a host-resident arm (2^%d)" % max([r["leaves_log"] for r in sweep if r["e2e_ms"] is not None], default=0),
+                    "h2d_bytes_per_step": int(max([(1 << r["leaves_log"]) for r in sweep if r["e2e_ms"] is not None], default=0)
+                                              * MERKLE_LEAF_LEN * 8 // world),
+                    "d2h_bytes_per_step": int((1 << CAP_HEIGHT) * 32 // world)},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "merkle::leaf_hash_kernel + tree levels", "bound": "issue",
+                         "achieved": last["permutations_per_s"], "peak": peak_perm, "unit": "Poseidon permutations/s",
+                         "frac": last["permutations_per_s"] / peak_perm, "traffic": None,
+                         "instr_per_warp_permutation": ipp},
+            "cpu_baseline": cpu, "clocks": clocks,
+        }
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def workload_config(args, world):
     return {"workload": "PolynomialBatch::from_values 2^%d rows x %d cols, rate_bits=%d, cap_height=%d, "
                         "blinding=false (LDE + Poseidon Merkle commit)" % (args.rows_log, COLS, RATE_BITS, CAP_HEIGHT),

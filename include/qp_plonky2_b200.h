@@ -196,6 +196,13 @@ const uint64_t* qp_batch_device_coeffs(const qp_batch* b); /* [n_cols][n] */
 /* MerkleTree::new(leaves, cap_height) on caller-provided leaf-major rows. */
 int qp_merkle_tree_new(qp_ctx* ctx, const uint64_t* leaves, int space, size_t n_leaves,
                        size_t leaf_len, unsigned cap_height, qp_tree** out);
+/* One shard of MerkleTree::new for the multi-GPU form (the reference parallelises over cap subtrees,
+ * merkle_tree.rs:85-119): shard `shard` of `n_shards` (a power of two <= 2^cap_height) passes the leaves of
+ * ITS subtrees -- rows [shard * n_leaves_total / n_shards, ...) -- and gets their block of `digests` and
+ * their 2^cap_height / n_shards cap entries (leaf indices of the getters are local to the shard). */
+int qp_merkle_tree_new_shard(qp_ctx* ctx, const uint64_t* shard_leaves, int space, size_t n_leaves_total,
+                             size_t leaf_len, unsigned cap_height, unsigned shard, unsigned n_shards,
+                             qp_tree** out);
 void qp_tree_free(qp_tree* t);
 int qp_tree_cap(const qp_tree* t, uint64_t* out, int space);
 int qp_tree_digests(const qp_tree* t, uint64_t* out, int space);

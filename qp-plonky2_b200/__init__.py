@@ -121,6 +121,7 @@ def lib():
         "qp_batch_from_values": (i32, [vp, vp, i32, sz, u32, u32, i32, u32, vp, u32, u32, pp]),
         "qp_batch_from_coeffs": (i32, [vp, vp, i32, sz, u32, u32, i32, u32, vp, u32, u32, pp]),
         "qp_batch_from_values_cols": (i32, [vp, vp, sz, u32, u32, i32, u32, vp, u32, u32, pp]),
+        "qp_merkle_tree_new_shard": (i32, [vp, vp, i32, sz, sz, u32, u32, u32, pp]),
         "qp_mctx_create": (i32, [vp, u32, u32, pp]),
         "qp_mctx_destroy": (None, [vp]),
         "qp_mctx_num_devices": (u32, [vp]),
@@ -745,7 +746,10 @@ class PolynomialBatch:
 class MerkleTree:
     """plonky2/src/hash/merkle_tree.rs:163-207 on caller-provided leaf-major rows."""
 
-    def __init__(self, ctx, leaves, cap_height):
+    def __init__(self, ctx, leaves, cap_height, shard=0, n_shards=1):
+        """shard / n_shards: the multi-GPU form -- `leaves` are the rows of cap subtrees
+        [shard * 2^h / n_shards, ...) only (qp_merkle_tree_new_shard); `cap` / `digests` are then this
+        shard's slices of the reference's arrays and leaf indices are local."""
         self._h = C.c_void_p()
         self.ctx = ctx
         if not _is_torch(leaves) and not isinstance(leaves, np.ndarray):
@@ -755,8 +759,13 @@ class MerkleTree:
             leaves = np.asarray(leaves, dtype=np.uint64).reshape(len(leaves), -1)
         p, space, keep, shape = _buf(leaves)
         n, L = shape
+        if n_shards != 1:
+            ctx.check(lib().qp_merkle_tree_new_shard(ctx._h, p, space, n * n_shards, L, cap_height, shard, n_shards,
+                                                     C.byref(self._h)))
+            cap_height -= n_shards.bit_length() - 1
+        else:
+            ctx.check(lib().qp_merkle_tree_new(ctx._h, p, space, n, L, cap_height, C.byref(self._h)))
         self.n_leaves, self.leaf_len, self.cap_height = n, L, cap_height
-        ctx.check(lib().qp_merkle_tree_new(ctx._h, p, space, n, L, cap_height, C.byref(self._h)))
 
     @property
     def cap(self):

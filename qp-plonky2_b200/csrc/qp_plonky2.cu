@@ -1550,6 +1550,25 @@ extern "C" int qp_merkle_tree_new(qp_ctx* ctx, const uint64_t* leaves, int space
     return rc;
 }
 
+// MerkleTree::new, one shard of it: the reference parallelises over the 2^cap_height cap subtrees
+// (fill_digests_buf, plonky2/src/hash/merkle_tree.rs:85-119) and so does the multi-GPU form -- shard s of S
+// (a power of two <= 2^cap_height) is given the leaves of subtrees [s 2^h / S, (s + 1) 2^h / S) and returns
+// exactly their block of `digests` and their cap entries; concatenated over the shards these are the
+// reference's arrays.  (Whole subtrees form a Merkle tree of cap height h - log2 S: same kernels.)
+extern "C" int qp_merkle_tree_new_shard(qp_ctx* ctx, const uint64_t* shard_leaves, int space, size_t n_leaves_total,
+                                        size_t leaf_len, unsigned cap_height, unsigned shard, unsigned n_shards,
+                                        qp_tree** out) {
+    if (!ctx) return QP_ERR_BAD_ARG;
+    if (!out) return fail(ctx, QP_ERR_BAD_ARG, "null out");
+    *out = nullptr;
+    if (!is_pow2(n_leaves_total)) return fail(ctx, QP_ERR_NOT_POW2, "Not a power of two");
+    if (cap_height > ilog2(n_leaves_total))
+        return fail(ctx, QP_ERR_CAP_HEIGHT, "cap_height should be at most log2(leaves.len())");
+    if (!is_pow2(n_shards) || shard >= n_shards || n_shards > ((size_t)1 << cap_height))
+        return fail(ctx, QP_ERR_BAD_ARG, "shards must be a power of two of whole cap subtrees");
+    return qp_merkle_tree_new(ctx, shard_leaves, space, n_leaves_total / n_shards, leaf_len, cap_height - ilog2(n_shards), out);
+}
+
 extern "C" void qp_tree_free(qp_tree* t) {
     if (!t) return;
     cudaSetDevice(t->ctx->device);

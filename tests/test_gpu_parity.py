@@ -123,6 +123,27 @@ def test_merkle_tree_new_parity(qp, ctx, lg, leaf_len, cap_h):
         assert oracle.merkle_verify(leaves[i], i, t.cap, pr)
 
 
+@pytest.mark.parametrize("lg,leaf_len,cap_h,shards", [(10, 135, 4, 2), (12, 7, 4, 8), (9, 20, 3, 8), (8, 135, 0, 1), (11, 9, 4, 16)])
+def test_merkle_tree_new_shards_concatenate_to_the_tree(qp, ctx, lg, leaf_len, cap_h, shards):
+    """qp_merkle_tree_new_shard: the shards' digests blocks and cap entries, concatenated, are the reference's
+    arrays (merkle_tree.rs:85-119 parallelises over the same cap subtrees), and a shard-local opening verifies
+    against the whole cap at the global leaf index."""
+    leaves = oracle.rand_felts((1 << lg, leaf_len), 300 + lg)
+    want = oracle.MerkleTree(leaves, cap_h)
+    per = (1 << lg) // shards
+    caps, digs = [], []
+    for s in range(shards):
+        t = qp.MerkleTree(ctx, leaves[s * per:(s + 1) * per], cap_h, shard=s, n_shards=shards)
+        caps.append(t.cap)
+        digs.append(t.digests)
+        assert oracle.merkle_verify(leaves[s * per + 3 % per], s * per + 3 % per, want.cap, t.prove(3 % per))
+        t.free()
+    assert (np.concatenate(caps) == want.cap).all()
+    assert (np.concatenate(digs) == want.digests).all()
+    with pytest.raises(qp.QpError):
+        qp.MerkleTree(ctx, leaves[:per], cap_h, shard=0, n_shards=2 << cap_h)     # a shard smaller than a cap subtree
+
+
 def test_merkle_every_leaf_verifies(qp, ctx):
     """plonky2/src/hash/merkle_tree.rs:224-282: n = 2^8 x 7 elements, cap heights 0/1/8"""
     leaves = oracle.rand_felts((1 << 8, 7), 42)
