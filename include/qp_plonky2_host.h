@@ -136,13 +136,25 @@ typedef struct {
 /* prove_with_partition_witness from the full witness on, serialised like
  * write_proof_with_public_inputs (plonky2/src/util/serialization/mod.rs:2040-2079).  `wires`:
  * witness matrix [num_wires][n] (host or device); the circuit must have been created with sigmas.
- * No lookups, no blinding; PoW witness = smallest valid one.  Two-call protocol: with out == NULL only
+ * No lookups; PoW witness = smallest valid one (zero-knowledge blinding: qp_prove_zk below).  Two-call protocol: with out == NULL only
  * *len_out (an upper bound of the proof size) is written.  timing_ms (optional, 7 entries) receives the
  * reference's TimingTree scopes: wires commitment, partial products, their commitment, quotient polys,
  * quotient commitment, opening set, opening proofs. */
 int qp_prove(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* constants_sigmas, const uint64_t circuit_digest[4],
              const qp_prover_config* cfg, const uint64_t* wires, int space, const uint64_t* public_inputs,
              size_t n_public_inputs, uint8_t* out, size_t capacity, size_t* len_out, double* timing_ms);
+
+/* The same with config.zero_knowledge (prover.rs:210,280,328; standard_recursion_zk_config,
+ * core/src/circuit_config.rs:80-90): the wires, Z / partial-products and quotient oracles carry QP_SALT_SIZE
+ * salt columns per leaf, FriParams.leaf_hiding is observed as 1 and the query openings include the salted
+ * leaves.  The reference draws the salt from its RNG (fri/oracle.rs:259-263); here it is injected --
+ * [QP_SALT_SIZE][N] per oracle, N = n << rate_bits, natural point order, in the same memory space as `wires`
+ * -- so that the proof is reproducible.  (The blinding GATES of a zk circuit, circuit_builder.rs:990-1075,
+ * are the circuit builder's business: they are rows of the witness the caller brings.) */
+int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* constants_sigmas, const uint64_t circuit_digest[4],
+                const qp_prover_config* cfg, const uint64_t* wires, int space, const uint64_t* public_inputs,
+                size_t n_public_inputs, const uint64_t* wires_salt, const uint64_t* zs_salt,
+                const uint64_t* quotient_salt, uint8_t* out, size_t capacity, size_t* len_out, double* timing_ms);
 
 #ifdef __cplusplus
 }

@@ -3,7 +3,7 @@
 CPU restatement of prove_with_partition_witness from the full witness on
 (plonky2/src/plonk/prover.rs:176-398) out of the oracle's pieces, and of
 write_proof_with_public_inputs (plonky2/src/util/serialization/mod.rs:2040-2079).  Same scope as
-the device prover: no lookups, no blinding, smallest PoW witness.  Parity status: "unpinned" by
+the device prover: no lookups, smallest PoW witness, zero-knowledge salt injected.  Parity status: "unpinned" by
 golden data (the reference cannot be built here); pinned structurally by the verifier identity
 (tests/test_plonk_oracle.py) and, for the FRI part, by tests/test_oracle.py.
 """
@@ -27,17 +27,22 @@ def circuit_digest(cap, degree_bits):
 
 def prove(oc, cs_batch, num_constants, wires, sigmas, public_inputs, pih_wires_check=None, *, degree_bits,
           num_wires, num_routed_wires, num_challenges, quotient_degree_factor, num_partial_products,
-          rate_bits=3, cap_height=4, proof_of_work_bits=16, arity_bits=4, final_poly_bits=5, num_query_rounds=28):
-    """oc: oracle.Circuit; cs_batch: oracle.PolynomialBatch of constants + sigmas."""
+          rate_bits=3, cap_height=4, proof_of_work_bits=16, arity_bits=4, final_poly_bits=5, num_query_rounds=28,
+          salts=None):
+    """oc: oracle.Circuit; cs_batch: oracle.PolynomialBatch of constants + sigmas.  salts: None, or the injected
+    salt columns (wires, zs, quotient), each [4][N]: config.zero_knowledge (prover.rs:210,280,328) -- the three
+    oracles are salted (fri/oracle.rs:259-263) and leaf_hiding is observed as 1 (core/src/fri.rs:311)."""
     n = 1 << degree_bits
     nc = num_challenges
     public_inputs = [int(x) % P for x in public_inputs]
     pih = oracle.hash_no_pad(np.array(public_inputs, dtype=np.uint64))
-    wb = oracle.PolynomialBatch.from_values(wires, rate_bits, cap_height)
+    zk = salts is not None
+    sw, sz, sq = salts if zk else (None, None, None)
+    wb = oracle.PolynomialBatch.from_values(wires, rate_bits, cap_height, salt=sw)
     ch = oracle.Challenger()
     arities = oracle.fri_reduction_arity_bits(degree_bits, rate_bits, cap_height, arity_bits, final_poly_bits)
     # FriParams::observe, core/src/fri.rs:289-321
-    ch.observe([rate_bits, cap_height, proof_of_work_bits, 1, arity_bits, final_poly_bits, num_query_rounds, 0,
+    ch.observe([rate_bits, cap_height, proof_of_work_bits, 1, arity_bits, final_poly_bits, num_query_rounds, int(zk),
                 degree_bits] + list(arities))
     ch.observe(circuit_digest(cs_batch.cap, degree_bits))
     ch.observe(pih)
@@ -45,14 +50,17 @@ def prove(oc, cs_batch, num_constants, wires, sigmas, public_inputs, pih_wires_c
     betas = [ch.get_challenge() for _ in range(nc)]
     gammas = [ch.get_challenge() for _ in range(nc)]
     zs = oc.partial_products_and_zs(wires, sigmas, betas, gammas)
-    zb = oracle.PolynomialBatch.from_values(zs, rate_bits, cap_height)
+    zb = oracle.PolynomialBatch.from_values(zs, rate_bits, cap_height, salt=sz)
     ch.observe(zb.cap.reshape(-1))
     alphas = [ch.get_challenge() for _ in range(nc)]
-    q = oc.compute_quotient_polys(rate_bits, cs_batch.leaves, wb.leaves, zb.leaves, betas, gammas, alphas, pih)
+    def unsalted(b):   # get_lde_values strips the salt (fri/oracle.rs:290)
+        return np.ascontiguousarray(b.leaves[:, : b.leaves.shape[1] - 4]) if b.blinding else b.leaves
+
+    q = oc.compute_quotient_polys(rate_bits, cs_batch.leaves, unsalted(wb), unsalted(zb), betas, gammas, alphas, pih)
     qd = quotient_degree_factor * n
     assert not q[:, qd:].any(), "Quotient has failed, the vanishing polynomial is not divisible by Z_H"
     chunks = np.ascontiguousarray(q[:, :qd]).reshape(nc * quotient_degree_factor, n)
-    qb = oracle.PolynomialBatch.from_coeffs(chunks, rate_bits, cap_height)
+    qb = oracle.PolynomialBatch.from_coeffs(chunks, rate_bits, cap_height, salt=sq)
     ch.observe(qb.cap.reshape(-1))
     zeta = ch.get_extension_challenge()
     g = oracle.lib().orc_gl_primitive_root(degree_bits)

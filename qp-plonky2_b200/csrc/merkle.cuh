@@ -104,13 +104,15 @@ template <class Layout>
 __global__ void __launch_bounds__(QP_LEAF_BLOCK, QP_LEAF_MIN_BLOCKS)
 leaf_hash_kernel(Layout lay, unsigned leaf_len, TreeShape sh, uint64_t* __restrict__ digests,
                  uint64_t* __restrict__ cap, unsigned chunk_first, unsigned chunk_count,
-                 uint64_t* __restrict__ state) {
+                 uint64_t* __restrict__ state, size_t leaf_first = 0, size_t leaf_count = ~(size_t)0) {
     const size_t n_leaves = (size_t)1 << sh.lg_leaves;
-    const size_t i_raw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // this launch covers leaves [leaf_first, leaf_first + leaf_count) (rows that arrive over time)
+    const size_t leaf_end = leaf_count > n_leaves - leaf_first ? n_leaves : leaf_first + leaf_count;
+    const size_t i_raw = leaf_first + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     // threads past the end hash the last leaf again and drop the result, so that every thread
     // of the block reaches the same barriers
-    const bool live = i_raw < n_leaves;
-    const size_t i = live ? i_raw : n_leaves - 1;
+    const bool live = i_raw < leaf_end;
+    const size_t i = live ? i_raw : leaf_end - 1;
     // hashing.rs:160-163: one permutation per 8-chunk, the last chunk may be short (its missing
     // lanes keep the previous state).  Software pipeline: fetch chunk ch+1 while permuting ch.
     const unsigned n_chunks = (leaf_len + 7) / 8;

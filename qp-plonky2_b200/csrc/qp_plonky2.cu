@@ -541,7 +541,8 @@ struct TreeBuf {
 // Leaf hashing, possibly in pieces (merkle::leaf_hash_kernel), and the levels above it.
 template <class Layout>
 static int hash_leaves(qp_ctx* ctx, Layout lay, unsigned leaf_len, TreeBuf* t, unsigned chunk_first = 0,
-                       unsigned chunk_count = ~0u, uint64_t* state = nullptr) {
+                       unsigned chunk_count = ~0u, uint64_t* state = nullptr, size_t leaf_first = 0,
+                       size_t leaf_count = ~(size_t)0) {
     if (!t->digests) {
         int rc = dev_alloc(ctx, &t->digests, t->n_digests() * 4);
         if (rc) return rc;
@@ -549,8 +550,10 @@ static int hash_leaves(qp_ctx* ctx, Layout lay, unsigned leaf_len, TreeBuf* t, u
         if (rc) return rc;
     }
     const size_t n_leaves = (size_t)1 << t->shape.lg_leaves;
-    LAUNCH(ctx, merkle::leaf_hash_kernel<Layout>, cdiv(n_leaves, QP_LEAF_BLOCK), QP_LEAF_BLOCK, 0, lay, leaf_len,
-           t->shape, t->digests, t->cap, chunk_first, chunk_count, state);
+    if (leaf_first >= n_leaves) return QP_OK;
+    const size_t n_here = std::min(leaf_count, n_leaves - leaf_first);
+    LAUNCH(ctx, merkle::leaf_hash_kernel<Layout>, cdiv(n_here, QP_LEAF_BLOCK), QP_LEAF_BLOCK, 0, lay, leaf_len,
+           t->shape, t->digests, t->cap, chunk_first, chunk_count, state, leaf_first, n_here);
     return QP_OK;
 }
 
@@ -1534,13 +1537,33 @@ extern "C" int qp_merkle_tree_new(qp_ctx* ctx, const uint64_t* leaves, int space
     t->tree.shape.cap_height = cap_height;
     *out = t;
     int rc = dev_alloc(ctx, &t->leaves, n_leaves * leaf_len);
-    if (!rc && leaf_len)
-        CUDA_TRY(ctx, cudaMemcpyAsync(t->leaves, leaves, n_leaves * leaf_len * 8,
-                                      space == QP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                                      ctx->stream));
-    if (!rc) {
-        merkle::AffineLayout lay{t->leaves, 1, leaf_len};
-        rc = build_tree(ctx, lay, (unsigned)leaf_len, &t->tree);
+    merkle::AffineLayout lay{t->leaves, 1, leaf_len};
+    const size_t bytes = n_leaves * leaf_len * 8;
+    if (!rc && space != QP_DEVICE && bytes >= pipeline_threshold() && n_leaves >= 16) {
+        // host rows of at least 64 MiB: upload in row slices on the copy stream and hash the leaves of a
+        // slice while the next one is crossing PCIe (leaf rows are independent: hash_leaf per row)
+        const int n_slices = 16;
+        const size_t per = n_leaves / n_slices;
+        cudaEventRecord(ctx->ready_ev, ctx->stream);
+        cudaStreamWaitEvent(ctx->copy_stream, ctx->ready_ev, 0);
+        for (int g = 0; g < n_slices && !rc; g++) {
+            cudaError_t e = cudaMemcpyAsync(t->leaves + g * per * leaf_len, leaves + g * per * leaf_len, per * leaf_len * 8,
+                                            cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->copy_ev[g], ctx->copy_stream);
+            if (e != cudaSuccess) rc = fail(ctx, QP_ERR_CUDA, cudaGetErrorString(e));
+        }
+        for (int g = 0; g < n_slices && !rc; g++) {
+            cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[g], 0);
+            rc = hash_leaves(ctx, lay, (unsigned)leaf_len, &t->tree, 0, ~0u, nullptr, g * per, per);
+        }
+        if (rc) cudaStreamSynchronize(ctx->copy_stream);   // nothing may still be writing into t->leaves when it is freed
+        if (!rc) rc = build_tree_levels(ctx, &t->tree);
+    } else {
+        if (!rc && leaf_len)
+            CUDA_TRY(ctx, cudaMemcpyAsync(t->leaves, leaves, bytes,
+                                          space == QP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                          ctx->stream));
+        if (!rc) rc = build_tree(ctx, lay, (unsigned)leaf_len, &t->tree);
     }
     if (!rc) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (rc) {

@@ -87,6 +87,20 @@ extern "C" int qp_prove(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* consta
                         const uint64_t circuit_digest[4], const qp_prover_config* cfg, const uint64_t* wires,
                         int space, const uint64_t* public_inputs, size_t n_public_inputs, uint8_t* out,
                         size_t capacity, size_t* len_out, double* timing_ms) {
+    return qp_prove_zk(ctx, circuit, constants_sigmas, circuit_digest, cfg, wires, space, public_inputs, n_public_inputs,
+                       nullptr, nullptr, nullptr, out, capacity, len_out, timing_ms);
+}
+
+// config.zero_knowledge (plonky2/src/plonk/prover.rs:210,280,328): the wires, Z / partial-products and
+// quotient oracles are committed with four salt columns per leaf (fri/oracle.rs:259-263; the reference
+// draws them from its RNG, here they are injected so that the proof is reproducible), FriParams.leaf_hiding
+// is observed as 1 (core/src/fri.rs:311) and the query openings carry the salted leaves
+// (fri_verifier.rs:222 strips them again).  All three salts or none.
+extern "C" int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* constants_sigmas,
+                           const uint64_t circuit_digest[4], const qp_prover_config* cfg, const uint64_t* wires,
+                           int space, const uint64_t* public_inputs, size_t n_public_inputs,
+                           const uint64_t* wires_salt, const uint64_t* zs_salt, const uint64_t* quotient_salt,
+                           uint8_t* out, size_t capacity, size_t* len_out, double* timing_ms) {
     if (!ctx || !circuit || !constants_sigmas || !circuit_digest || !cfg || !len_out) return QP_ERR_BAD_ARG;
     qp_circuit_desc d;
     int rc = qp_circuit_describe(circuit, &d);
@@ -99,7 +113,10 @@ extern "C" int qp_prove(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* consta
     unsigned arities[64];
     const unsigned n_rounds = qp_fri_reduction_arity_bits(d.degree_bits, cfg->rate_bits, cfg->cap_height,
                                                           cfg->arity_bits, cfg->final_poly_bits, arities);
-    const size_t leaf_lens[4] = {n_pre, d.num_wires, n_zs, n_q};
+    const bool zk = wires_salt || zs_salt || quotient_salt;
+    if (zk && !(wires_salt && zs_salt && quotient_salt)) return QP_ERR_BLINDING_NO_SALT;
+    const size_t hide = zk ? QP_SALT_SIZE : 0;
+    const size_t leaf_lens[4] = {n_pre, d.num_wires + hide, n_zs + hide, n_q + hide};
     const size_t fri_len = qp_fri_proof_len(leaf_lens, 4, d.degree_bits + cfg->rate_bits, cfg->rate_bits,
                                             cfg->cap_height, arities, n_rounds, cfg->num_query_rounds);
     const size_t n_open = n_pre + d.num_wires + n_zs + nc + n_q;
@@ -117,7 +134,7 @@ extern "C" int qp_prove(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* consta
     qp_hash_no_pad(public_inputs, n_public_inputs, pih);  // prover.rs:185-186
     qp_batch *wb = nullptr, *zb = nullptr, *qb = nullptr;
     qp_fri* fri = nullptr;
-    uint64_t *d_zs = nullptr, *d_q = nullptr;
+    uint64_t *d_zs = nullptr, *d_q = nullptr, *d_salt_z = nullptr, *d_salt_q = nullptr;
     std::vector<uint8_t> bytes;
     bytes.reserve(total);
     auto cleanup = [&]() {
@@ -127,6 +144,8 @@ extern "C" int qp_prove(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* consta
         qp_batch_free(qb);
         qp_dev_free(ctx, d_zs);
         qp_dev_free(ctx, d_q);
+        qp_dev_free(ctx, d_salt_z);
+        qp_dev_free(ctx, d_salt_q);
     };
 #define QP_STEP(expr)            \
     do {                         \
@@ -137,9 +156,20 @@ extern "C" int qp_prove(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* consta
         }                        \
     } while (0)
 
+    // the Z and quotient oracles are committed from device data: their salt has to be there too
+    const uint64_t *salt_z = zs_salt, *salt_q = quotient_salt;
+    if (zk && space != QP_DEVICE) {
+        const size_t words = (size_t)QP_SALT_SIZE << (d.degree_bits + cfg->rate_bits);
+        QP_STEP(qp_dev_alloc(ctx, words, &d_salt_z));
+        QP_STEP(qp_dev_alloc(ctx, words, &d_salt_q));
+        QP_STEP(qp_memcpy(ctx, d_salt_z, QP_DEVICE, zs_salt, QP_HOST, words));
+        QP_STEP(qp_memcpy(ctx, d_salt_q, QP_DEVICE, quotient_salt, QP_HOST, words));
+        salt_z = d_salt_z;
+        salt_q = d_salt_q;
+    }
     // wires commitment, prover.rs:201-214
-    QP_STEP(qp_batch_from_values(ctx, wires, space, d.num_wires, d.degree_bits, cfg->rate_bits, 0, cfg->cap_height,
-                                 nullptr, 0, 1u << cfg->rate_bits, &wb));
+    QP_STEP(qp_batch_from_values(ctx, wires, space, d.num_wires, d.degree_bits, cfg->rate_bits, zk ? 1 : 0,
+                                 cfg->cap_height, wires_salt, 0, 1u << cfg->rate_bits, &wb));
     scopes[0] = tm.lap(ctx);
     // transcript, prover.rs:216-234; FriParams::observe core/src/fri.rs:289-321
     qp_challenger ch;
@@ -147,7 +177,7 @@ extern "C" int qp_prove(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* consta
     {
         std::vector<uint64_t> v = {cfg->rate_bits, cfg->cap_height, cfg->proof_of_work_bits,
                                    1, cfg->arity_bits, cfg->final_poly_bits,  // ConstantArityBits::serialize
-                                   cfg->num_query_rounds, 0 /* leaf_hiding */, d.degree_bits};
+                                   cfg->num_query_rounds, zk ? 1u : 0u /* leaf_hiding */, d.degree_bits};
         for (unsigned i = 0; i < n_rounds; i++) v.push_back(arities[i]);
         qp_challenger_observe(&ch, v.data(), v.size());
     }
@@ -164,8 +194,8 @@ extern "C" int qp_prove(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* consta
     QP_STEP(qp_dev_alloc(ctx, n_zs * n, &d_zs));
     QP_STEP(qp_circuit_partial_products_and_zs(circuit, wires, space, betas.data(), gammas.data(), d_zs, QP_DEVICE));
     scopes[1] = tm.lap(ctx);
-    QP_STEP(qp_batch_from_values(ctx, d_zs, QP_DEVICE, n_zs, d.degree_bits, cfg->rate_bits, 0, cfg->cap_height, nullptr,
-                                 0, 1u << cfg->rate_bits, &zb));
+    QP_STEP(qp_batch_from_values(ctx, d_zs, QP_DEVICE, n_zs, d.degree_bits, cfg->rate_bits, zk ? 1 : 0, cfg->cap_height,
+                                 salt_z, 0, 1u << cfg->rate_bits, &zb));
     scopes[2] = tm.lap(ctx);
     QP_STEP(qp_batch_cap(zb, cap.data(), QP_HOST));
     qp_challenger_observe(&ch, cap.data(), cap_words);
@@ -201,8 +231,8 @@ extern "C" int qp_prove(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* consta
         }
         d_chunks = d_trim;
     }
-    rc = qp_batch_from_coeffs(ctx, d_chunks, QP_DEVICE, n_q, d.degree_bits, cfg->rate_bits, 0, cfg->cap_height, nullptr,
-                              0, 1u << cfg->rate_bits, &qb);
+    rc = qp_batch_from_coeffs(ctx, d_chunks, QP_DEVICE, n_q, d.degree_bits, cfg->rate_bits, zk ? 1 : 0, cfg->cap_height,
+                              salt_q, 0, 1u << cfg->rate_bits, &qb);
     qp_dev_free(ctx, d_trim);
     QP_STEP(rc);
     scopes[4] = tm.lap(ctx);

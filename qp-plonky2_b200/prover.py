@@ -14,7 +14,8 @@ is its ctypes face.  Every polynomial-sized step runs on the device:
 
 Out of scope: circuit building and witness generation -- the caller brings
 the constants/sigmas commitment and the witness matrix, like `prove_with_partition_witness` gets
-them from ProverOnlyCircuitData and the generators.  No lookups, no zero-knowledge blinding.
+them from ProverOnlyCircuitData and the generators.  No lookups.  Zero-knowledge mode (`salts=`): the
+three prover oracles are committed with injected salt columns and leaf_hiding is on.
 Deterministic where the reference is not: the PoW witness is the smallest one (serial `find`).
 """
 import ctypes as C
@@ -87,8 +88,9 @@ SCOPES = ("compute wires commitment", "compute partial products", "commit to par
           "compute quotient polys", "commit to quotient polys", "construct the opening set", "compute opening proofs")
 
 
-def prove(prover_data, wires, public_inputs, timing=None):
-    """-> bytes of ProofWithPublicInputs.  wires: witness matrix [num_wires][n] (numpy, or a torch
+def prove(prover_data, wires, public_inputs, timing=None, salts=None):
+    """-> bytes of ProofWithPublicInputs.  salts: None, or (wires_salt, zs_salt, quotient_salt), each [4][N]
+    (N = n << rate_bits) in the same memory space as `wires`: config.zero_knowledge (prover.rs:210,280,328).  wires: witness matrix [num_wires][n] (numpy, or a torch
     CUDA tensor: then nothing but caps, openings and the FRI proof leaves the device);
     public_inputs: field elements (already part of the witness).  `timing` (dict) receives the
     reference's TimingTree scopes in milliseconds."""
@@ -103,12 +105,20 @@ def prove(prover_data, wires, public_inputs, timing=None):
     pis = np.ascontiguousarray(np.asarray([int(x) % P for x in public_inputs], dtype=np.uint64))
     digest = np.ascontiguousarray(pd.circuit_digest, dtype=np.uint64)
     need = C.c_size_t()
+    sp, skeep = [None, None, None], []
+    if salts is not None:
+        for k, sarr in enumerate(salts):
+            q, sspace, keep_s, sshape = _buf(sarr)
+            if sspace != space or tuple(sshape) != (4, (1 << c.degree_bits) << f.rate_bits):
+                raise ValueError("salts must be [4][N] in the same memory space as the wires")
+            sp[k] = q
+            skeep.append(keep_s)
     args = (ctx._h, pd.circuit._h, pd.constants_sigmas_commitment._h, digest.ctypes.data, C.byref(cfg), ptr, space,
-            pis.ctypes.data if pis.size else None, pis.size)
-    ctx.check(lib().qp_prove(*args, None, 0, C.byref(need), None))
+            pis.ctypes.data if pis.size else None, pis.size, sp[0], sp[1], sp[2])
+    ctx.check(lib().qp_prove_zk(*args, None, 0, C.byref(need), None))
     buf = (C.c_uint8 * need.value)()
     ms = (C.c_double * 7)()
-    rc = lib().qp_prove(*args, buf, need.value, C.byref(need), ms)
+    rc = lib().qp_prove_zk(*args, buf, need.value, C.byref(need), ms)
     if rc:
         from . import QpError
         raise QpError(rc, lib().qp_last_error(ctx._h).decode() or "qp_prove failed")

@@ -144,6 +144,19 @@ def test_merkle_tree_new_shards_concatenate_to_the_tree(qp, ctx, lg, leaf_len, c
         qp.MerkleTree(ctx, leaves[:per], cap_h, shard=0, n_shards=2 << cap_h)     # a shard smaller than a cap subtree
 
 
+@pytest.mark.parametrize("lg,leaf_len,cap_h", [(4, 3, 0), (6, 135, 4), (10, 20, 2), (12, 9, 4)])
+def test_merkle_tree_new_pipelined_host_rows(qp, ctx, lg, leaf_len, cap_h, monkeypatch):
+    """MerkleTree::new on large host rows: the upload runs in 16 row slices and the leaves of a slice are hashed
+    while the next slice crosses PCIe -- same digests, cap and openings as the oracle."""
+    monkeypatch.setenv("QP_PIPELINE_MIN_BYTES", "1")
+    leaves = oracle.rand_felts((1 << lg, leaf_len), 330 + lg)
+    want = oracle.MerkleTree(leaves, cap_h)
+    t = qp.MerkleTree(ctx, leaves, cap_h)
+    assert (t.cap == want.cap).all() and (t.digests == want.digests).all()
+    assert (t.get((1 << lg) - 1) == leaves[-1]).all()
+    assert oracle.merkle_verify(leaves[7], 7, want.cap, t.prove(7))
+
+
 def test_merkle_every_leaf_verifies(qp, ctx):
     """plonky2/src/hash/merkle_tree.rs:224-282: n = 2^8 x 7 elements, cap heights 0/1/8"""
     leaves = oracle.rand_felts((1 << 8, 7), 42)

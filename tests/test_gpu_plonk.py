@@ -141,6 +141,46 @@ def test_full_proof_bytes_match_oracle(qp, ctx, degree_bits, qdf, pow_bits, quer
     assert set(timing) >= {"compute wires commitment", "compute quotient polys", "compute opening proofs"}
 
 
+@pytest.mark.parametrize("degree_bits,poseidon,rec,device_witness", [(6, False, False, False), (9, True, False, False),
+                                                                      (8, True, True, True)])
+def test_zero_knowledge_proof_bytes_match_oracle(qp, ctx, degree_bits, poseidon, rec, device_witness):
+    """qp_prove_zk: config.zero_knowledge (plonky2/src/plonk/prover.rs:210,280,328) -- salted wires / Z /
+    quotient commitments, leaf_hiding observed as 1, salted leaves in the query openings.  With the salt
+    injected the proof is the oracle's byte for byte (host and device-resident witness), the restated verifier
+    accepts it in hiding mode only, and without salt the call is the plain prove()."""
+    import torch
+    import verifier
+    from oracle import prover as oprover
+    from qp_plonky2_b200 import prover
+
+    sc = SynthCircuit(degree_bits, seed=70 + degree_bits, poseidon=poseidon, extra_gates=rec, recursion_gates=rec)
+    c = sc.common
+    N = (1 << degree_bits) << c.rate_bits
+    salts = [oracle.rand_felts((4, N), 710 + k) for k in range(3)]
+    circ = plonk.Circuit(ctx, c, sc.sigmas)
+    cfg = prover.FriConfig(c.rate_bits, c.cap_height, 8, 4, 5, 6)
+    pd = prover.ProverData(ctx, circ, sc.constants_sigmas(), cfg)
+    if device_witness:
+        w = torch.from_numpy(np.ascontiguousarray(sc.wires).view(np.int64)).cuda()
+        sl = [torch.from_numpy(x.view(np.int64)).cuda() for x in salts]
+        got = prover.prove(pd, w, sc.public_inputs, salts=sl)
+    else:
+        got = prover.prove(pd, sc.wires, sc.public_inputs, salts=salts)
+    o_cs = oracle.PolynomialBatch.from_values(sc.constants_sigmas(), c.rate_bits, c.cap_height)
+    want, _ = oprover.prove(sc.oracle_circuit, o_cs, c.num_constants, sc.wires, sc.sigmas, sc.public_inputs,
+                            degree_bits=degree_bits, num_wires=c.num_wires, num_routed_wires=c.num_routed_wires,
+                            num_challenges=c.num_challenges, quotient_degree_factor=c.quotient_degree_factor,
+                            num_partial_products=c.num_partial_products, rate_bits=c.rate_bits,
+                            cap_height=c.cap_height, proof_of_work_bits=8, num_query_rounds=6, salts=salts)
+    assert len(got) == len(want)
+    assert got == want
+    cap = pd.constants_sigmas_commitment.merkle_tree.cap
+    assert verifier.verify(got, c, pd.fri, cap, pd.circuit_digest, hiding=True) is None
+    assert verifier.verify(got, c, pd.fri, cap, pd.circuit_digest, hiding=False) is not None
+    plain = prover.prove(pd, sc.wires, sc.public_inputs)
+    assert len(plain) == len(got) - 6 * 3 * 4 * 8 and verifier.verify(plain, c, pd.fri, cap, pd.circuit_digest) is None
+
+
 def test_large_proof_openings_pass_the_verifier(qp, ctx):
     """2^15-row proof on the device (the oracle's quotient would take a minute): parse the opening
     set back out of the proof bytes, re-derive the challenges with the host transcript and run the

@@ -332,3 +332,34 @@ def test_restated_verifier_accepts_oracle_proofs_and_rejects_tampering(degree_bi
         assert verifier.verify(bytes(bad), c, fri, cs.cap, digest) is not None, what
     # and a wrong circuit digest changes every challenge
     assert verifier.verify(proof, c, fri, cs.cap, digest ^ np.uint64(1)) is not None
+
+
+@pytest.mark.parametrize("degree_bits,qdf,poseidon", [(6, 8, False), (7, 8, True)])
+def test_restated_verifier_accepts_zero_knowledge_oracle_proofs(degree_bits, qdf, poseidon):
+    """config.zero_knowledge (plonky2/src/plonk/prover.rs:210,280,328): salted wires / Z / quotient oracles and
+    leaf_hiding = 1.  The restated verifier accepts the oracle's zk proof in hiding mode (stripping the salt,
+    core/src/fri_verifier.rs:222-228), refuses it in non-hiding mode, refuses a plain proof in hiding mode, and
+    a different salt gives different commitments but the same openings-independent acceptance."""
+    from oracle import prover as oprover
+    import verifier
+
+    sc = SynthCircuit(degree_bits, seed=92, quotient_degree_factor=qdf, poseidon=poseidon)
+    c = sc.common
+    N = (1 << degree_bits) << c.rate_bits
+    salts = [oracle.rand_felts((4, N), 700 + k) for k in range(3)]
+    cs = oracle.PolynomialBatch.from_values(sc.constants_sigmas(), c.rate_bits, c.cap_height)
+    zk_proof, _ = _oracle_prove(sc, proof_of_work_bits=6, num_query_rounds=5, salts=salts)
+    plain, _ = _oracle_prove(sc, proof_of_work_bits=6, num_query_rounds=5)
+    fri = _Fri(c.rate_bits, c.cap_height, 6, 4, 5, 5)
+    digest = oprover.circuit_digest(cs.cap, degree_bits)
+    assert len(zk_proof) == len(plain) + 5 * 3 * 4 * 8          # 3 salted leaves per query round
+    assert verifier.verify(zk_proof, c, fri, cs.cap, digest, hiding=True) is None
+    assert verifier.verify(zk_proof, c, fri, cs.cap, digest, hiding=False) is not None
+    assert verifier.verify(plain, c, fri, cs.cap, digest, hiding=True) is not None
+    other, _ = _oracle_prove(sc, proof_of_work_bits=6, num_query_rounds=5,
+                             salts=[oracle.rand_felts((4, N), 800 + k) for k in range(3)])
+    assert other[:64] != zk_proof[:64]                            # the wires cap depends on the salt
+    assert verifier.verify(other, c, fri, cs.cap, digest, hiding=True) is None
+    bad = bytearray(zk_proof)
+    bad[len(bad) // 2] ^= 2
+    assert verifier.verify(bytes(bad), c, fri, cs.cap, digest, hiding=True) is not None

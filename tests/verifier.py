@@ -54,8 +54,9 @@ class Reader:
         return self.u64s(4 * k).reshape(k, 4)
 
 
-def parse_proof(proof, common, fri, arities):
-    """-> dict with caps, openings, FRI proof parts, public inputs."""
+def parse_proof(proof, common, fri, arities, hiding=False):
+    """-> dict with caps, openings, FRI proof parts, public inputs.  hiding: the prover oracles' leaves carry
+    four salt elements each (validate_fri_proof_shape, core/src/fri_verifier... / fri/validate_shape.rs)."""
     c = common
     nc = c.num_challenges
     cap_words = 4 << fri.cap_height
@@ -65,8 +66,9 @@ def parse_proof(proof, common, fri, arities):
              ("plonk_zs", nc), ("plonk_zs_next", nc), ("partial_products", nc * c.num_partial_products),
              ("quotient_polys", nc * c.quotient_degree_factor)]
     out["openings"] = {name: r.ext(k) for name, k in sizes}
-    leaf_lens = [c.num_constants + c.num_routed_wires, c.num_wires, nc * (1 + c.num_partial_products),
-                 nc * c.quotient_degree_factor]
+    salt = 4 if hiding else 0
+    leaf_lens = [c.num_constants + c.num_routed_wires, c.num_wires + salt, nc * (1 + c.num_partial_products) + salt,
+                 nc * c.quotient_degree_factor + salt]
     out["commit_caps"] = [r.u64s(cap_words).reshape(-1, 4) for _ in arities]
     rounds = []
     for _ in range(fri.num_query_rounds):
@@ -109,22 +111,24 @@ def _interpolate(points, values, x):
     return total
 
 
-def verify(proof, common, fri, constants_sigmas_cap, circuit_digest):
-    """-> None if the proof is accepted, else a string naming the failed check."""
+def verify(proof, common, fri, constants_sigmas_cap, circuit_digest, hiding=False):
+    """-> None if the proof is accepted, else a string naming the failed check.  hiding = config.zero_knowledge:
+    leaf_hiding is observed as 1 and the salt is stripped from the blinded oracles' leaves
+    (unsalted_eval, core/src/fri_verifier.rs:222-228)."""
     c = common
     nc = c.num_challenges
     n = 1 << c.degree_bits
     arities = oracle.fri_reduction_arity_bits(c.degree_bits, fri.rate_bits, fri.cap_height, fri.arity_bits,
                                               fri.final_poly_bits)
     try:
-        pr = parse_proof(proof, c, fri, arities)
+        pr = parse_proof(proof, c, fri, arities, hiding)
     except Exception as e:  # validate_fri_proof_shape
         return "malformed proof: %r" % (e,)
     op = pr["openings"]
     # ---- challenges (get_challenges.rs:39-96) ----
     ch = oracle.Challenger()
     ch.observe([fri.rate_bits, fri.cap_height, fri.proof_of_work_bits, 1, fri.arity_bits, fri.final_poly_bits,
-                fri.num_query_rounds, 0, c.degree_bits] + list(arities))
+                fri.num_query_rounds, int(hiding), c.degree_bits] + list(arities))
     ch.observe(np.asarray(circuit_digest, dtype=np.uint64))
     pih = oracle.hash_no_pad(np.array(pr["public_inputs"], dtype=np.uint64))
     ch.observe(pih)
@@ -170,7 +174,9 @@ def verify(proof, common, fri, constants_sigmas_cap, circuit_digest):
                 return "initial tree Merkle proof"
         subgroup_x = GEN * pow(w_lde, reverse_bits(x_index, lde_bits), P) % P
         # fri_combine_initial: evaluations at x of every opened polynomial, from the leaves
-        leaf = [[Ext(int(v)) for v in evals] for evals, _ in initial]
+        # the blinded oracles (wires, zs, quotient: core/src/plonk_common.rs:20-35) lose their salt here
+        leaf = [[Ext(int(v)) for v in (evals[: len(evals) - 4] if hiding and k else evals)]
+                for k, (evals, _) in enumerate(initial)]
         batch_evals = [leaf[0] + leaf[1] + leaf[2] + leaf[3], leaf[2][:nc]]
         total = Ext(0)
         for evals, ro, pt in zip(batch_evals, reduced_openings, points):
