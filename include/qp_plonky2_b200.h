@@ -46,7 +46,8 @@ enum {
     QP_ERR_DEGREE_MISMATCH = 4,/* "Polynomial degrees inconsistent", plonky2/src/fri/oracle.rs:277 */
     QP_ERR_BAD_ARG = 5,        /* null pointer / out-of-range index (slice index panic) */
     QP_ERR_TOO_LARGE = 6,      /* exceeds the field's two-adicity (types.rs:281 assert) or device memory */
-    QP_ERR_BLINDING_NO_SALT = 7/* blinding requested without injected salt ("Cannot set blinding without rand feature", oracle.rs:238) */
+    QP_ERR_BLINDING_NO_SALT = 7,/* blinding requested without injected salt ("Cannot set blinding without rand feature", oracle.rs:238) */
+    QP_ERR_UNSUPPORTED = 8     /* a feature of the reference outside this library's contract (lookup arguments): refused, never approximated */
 };
 
 enum { QP_HOST = 0, QP_DEVICE = 1 };
@@ -369,6 +370,12 @@ typedef struct {
     const uint64_t* pool;            /* field constants of the program (host) */
     size_t pool_len;
     uint32_t program_regs;           /* registers the program uses */
+    /* What this library does NOT implement must be declared, so that it is refused instead of proved wrong:
+     * common_data.num_lookup_polys / num_lookup_selectors (lookup argument: compute_lookup_polys,
+     * plonky2/src/plonk/prover.rs:489-636, the lookup terms of vanishing_poly.rs:63-160).  A circuit with
+     * lookup tables has both nonzero; qp_circuit_create answers QP_ERR_UNSUPPORTED. */
+    uint32_t num_lookup_polys;
+    uint32_t num_lookup_selectors;
 } qp_circuit_desc;
 typedef struct qp_circuit qp_circuit;
 int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* desc, qp_circuit** out);

@@ -51,6 +51,7 @@ ERRORS = {
     5: "bad argument",
     6: "too large",
     7: "Cannot set blinding without salt",
+    8: "not supported by this library (refused, not approximated)",
 }
 
 

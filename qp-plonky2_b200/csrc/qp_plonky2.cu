@@ -2446,6 +2446,10 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
     *out = nullptr;
     if (d->num_challenges == 0 || d->num_challenges > (unsigned)quotient::MAX_CHALLENGES)
         return fail(ctx, QP_ERR_BAD_ARG, "num_challenges must be 1..4");
+    if (d->num_lookup_polys || d->num_lookup_selectors)
+        return fail(ctx, QP_ERR_UNSUPPORTED,
+                    "the circuit declares a lookup argument (num_lookup_polys / num_lookup_selectors): not implemented, "
+                    "prove it with the reference's CPU path");
     if (d->max_degree < 2) return fail(ctx, QP_ERR_BAD_ARG, "max_degree > 1 (util/partial_products.rs:17)");
     if (d->num_routed_wires == 0 || d->num_routed_wires > d->num_wires || !d->k_is)
         return fail(ctx, QP_ERR_BAD_ARG, "bad wire counts");

@@ -1084,7 +1084,7 @@ class _Desc(C.Structure):
         ("num_partial_products", C.c_uint32), ("max_degree", C.c_uint32),
         ("k_is", C.c_void_p), ("sigmas", C.c_void_p), ("sigmas_space", C.c_int),
         ("program", C.c_void_p), ("program_len", C.c_size_t), ("pool", C.c_void_p), ("pool_len", C.c_size_t),
-        ("program_regs", C.c_uint32),
+        ("program_regs", C.c_uint32), ("num_lookup_polys", C.c_uint32), ("num_lookup_selectors", C.c_uint32),
     ]
 
 
@@ -1121,6 +1121,9 @@ class Circuit:
         d.program, d.program_len = code.ctypes.data, code.size
         d.pool, d.pool_len = pool.ctypes.data, pool.size
         d.program_regs = n_regs
+        # lookup arguments are outside the library's contract: declared so that qp_circuit_create refuses them
+        d.num_lookup_polys = getattr(common, "num_lookup_polys", 0)
+        d.num_lookup_selectors = getattr(common, "num_lookup_selectors", 0)
         self._h = C.c_void_p()
         ctx.check(lib().qp_circuit_create(ctx._h, C.byref(d), C.byref(self._h)))
         del keep

@@ -92,6 +92,21 @@ def test_quotient_errors(qp, ctx):
         circ.compute_quotient_polys(g_w, g_w, few, [1, 2], [3, 4], [5, 6], [0, 0, 0, 0])
 
 
+def test_circuit_with_lookups_is_refused(qp, ctx):
+    """A circuit that declares a lookup argument (common_data.num_lookup_polys != 0, prover.rs:489-636) is
+    refused at qp_circuit_create with QP_ERR_UNSUPPORTED -- never proved as if the lookups were not there."""
+    sc = SynthCircuit(5, seed=3)
+    c = sc.common
+    c.num_lookup_polys, c.num_lookup_selectors = 2, 3
+    try:
+        with pytest.raises(qp.QpError) as e:
+            plonk.Circuit(ctx, c, sc.sigmas)
+        assert e.value.code == 8
+    finally:
+        c.num_lookup_polys = c.num_lookup_selectors = 0
+    plonk.Circuit(ctx, c, sc.sigmas)
+
+
 def test_large_circuit_verifier_identity(qp, ctx):
     """2^16 rows x 143 wires (the oracle would take minutes): the whole device pipeline -- Z and
     partial products, three commitments, quotient, quotient commitment -- checked through the
