@@ -585,7 +585,7 @@ def run_ours(args):
         b.free()
     barrier()
     # ---- end to end from what the reference passes: one pageable heap vector per column ----
-    e2e_pg_ms = None
+    e2e_pg_ms, e2e_pg_min = None, 1e30
     if world == 1 and hasattr(qp.PolynomialBatch, "from_values_cols"):
         cols_pg = [np.array(h_vals[c].numpy(), copy=True).view(np.uint64) for c in range(COLS)]
         for _ in range(min(args.warmup, 2)):
@@ -596,7 +596,9 @@ def run_ours(args):
             b = qp.PolynomialBatch.from_values_cols(ctx, cols_pg, RATE_BITS, False, CAP_HEIGHT)
             cap = b.merkle_tree.cap
             torch.cuda.synchronize()
-            e2e_pg_ms += (time.perf_counter() - t0) * 1e3
+            dt = (time.perf_counter() - t0) * 1e3
+            e2e_pg_ms += dt
+            e2e_pg_min = min(e2e_pg_min, dt)
             assert (cap == caps[0]).all(), "pageable-columns cap differs from device-resident cap"
             b.free()
         e2e_pg_ms /= args.steps
@@ -637,14 +639,19 @@ def run_ours(args):
                 "note": "reported because the contract asks for it; this kernel is bound by instruction issue, "
                         "not by HBM (see `roofline`)"}
     lde_bytes = COLS * n * 8 + COLS * n_loc * 8          # 8 B per coeff in + 8 B per value out
+    tj = json.load(open(tp)) if os.path.exists(tp) else {}
     roof_lde = {"kernel": "ntt::strided_pass_kernel + ntt::final_pass_kernel (LDE)", "bound": "hbm",
                 "achieved": lde_bytes / (k_lde * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": lde_bytes / (k_lde * 1e-3) / 1e9 / peak, "ms": k_lde}
+                "frac": lde_bytes / (k_lde * 1e-3) / 1e9 / peak, "ms": k_lde,
+                "traffic": tj.get("lde_passes", {}).get("dram_bytes") if world == 1 and args.rows_log == 20 and COLS == 135 else None,
+                "note": "ALU-pipe bound (74-83 % busy in ncu, profiles/): 64-bit modular butterflies cost ~15 integer "
+                        "instructions per element per stage; the HBM fraction is reported because the contract asks"}
     intt_bytes = (c_hi - c_lo) * n * 16
     roof_intt = None  # the sharded path runs the iNTT outside the batch handle (qp_ifft_columns)
     if k_intt > 0:
         roof_intt = {"kernel": "ntt (iNTT)", "bound": "hbm", "achieved": intt_bytes / k_intt / 1e6, "peak": peak,
-                     "unit": "GB/s", "frac": intt_bytes / k_intt / 1e6 / peak, "ms": k_intt}
+                     "unit": "GB/s", "frac": intt_bytes / k_intt / 1e6 / peak, "ms": k_intt,
+                     "traffic": tj.get("intt_passes", {}).get("dram_bytes") if args.rows_log == 20 and COLS == 135 else None}
 
     # ---- CPU baseline: the oracle, once, at FULL size on the very witness the GPU committed to ----
     cpu, cap_equal_cpu = None, None
@@ -704,7 +711,7 @@ def run_ours(args):
         "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(h_vals.numel() * 8),
                 "d2h_bytes_per_step": int((1 << CAP_HEIGHT) * 32 // world)},
         "e2e_pageable": None if e2e_pg_ms is None else {
-            "value": e2e_pg_ms, "unit": "ms", "what": "qp_batch_from_values_cols: %d separate pageable column "
+            "value": e2e_pg_ms, "min": e2e_pg_min, "unit": "ms", "what": "qp_batch_from_values_cols: %d separate pageable column "
             "vectors (the reference's Vec<PolynomialValues>), staged through the library's pinned ring" % COLS},
         "gpu_launches": int(launches), "cap_equal_cpu": cap_equal_cpu,
         "roofline": roof, "roofline_hbm": roof_hbm, "roofline_lde": roof_lde, "roofline_intt": roof_intt,

@@ -62,7 +62,7 @@ struct qp_ctx {
     cudaEvent_t grp_ev[3 * MAX_GROUPS] = {};  // per column group: start, after LDE, after partial leaf hash
     // pinned staging ring for pageable host columns (qp_batch_from_values_cols): allocated on first
     // use, kept for the life of the context
-    static constexpr int RING_SLOTS = 2;
+    static constexpr int RING_SLOTS = 3;
     uint64_t* ring[RING_SLOTS] = {};
     size_t ring_words = 0;
 };
@@ -687,25 +687,41 @@ static int batch_create(qp_ctx* ctx, uint64_t* d_coeffs, size_t n_cols, unsigned
 }
 
 // Phase 2: "FFT + blinding" (oracle.rs:202-206, 267-283) for columns [c0, c1).
+// Columns per transform launch pair (QP_LDE_GROUP; 0 = all columns of the call in one pair).  A strided pass
+// writes the whole intermediate before the final pass reads it back: with few columns per pair the
+// intermediate (group x 2^rate_bits x n x 8 bytes) can stay in the 126 MB L2 between the two.
+static size_t lde_group() {
+    static const size_t v = [] {
+        const char* e = getenv("QP_LDE_GROUP");
+        return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)0;
+    }();
+    return v;
+}
+
 static int batch_lde_columns(qp_batch* b, size_t c0, size_t c1) {
     qp_ctx* ctx = b->ctx;
     const size_t n = (size_t)1 << b->degree_log;
     const ScaleTables* st = nullptr;
     int rc = lde_scale(ctx, (int)b->degree_log, b->rate_bits, b->block_first, b->block_count, &st);
     if (rc) return rc;
-    NttJob job;
-    job.src = b->coeffs + c0 * n;
-    job.dst = b->lde + c0 * b->n_local;
-    job.L = (int)b->degree_log;
-    job.n_vec = (unsigned)((c1 - c0) * b->block_count);
-    job.inner_bits = (int)ilog2(b->block_count);
-    job.src_outer = n;
-    job.src_inner = 0;
-    job.dst_outer = b->n_local;
-    job.dst_inner = n;
-    job.scale = st;
-    job.out_mode = ntt::OUT_NATURAL;
-    return run_ntt(ctx, job);
+    const size_t grp = lde_group() ? lde_group() : (c1 - c0);
+    for (size_t a = c0; a < c1 && !rc; a += grp) {
+        const size_t e = std::min(a + grp, c1);
+        NttJob job;
+        job.src = b->coeffs + a * n;
+        job.dst = b->lde + a * b->n_local;
+        job.L = (int)b->degree_log;
+        job.n_vec = (unsigned)((e - a) * b->block_count);
+        job.inner_bits = (int)ilog2(b->block_count);
+        job.src_outer = n;
+        job.src_inner = 0;
+        job.dst_outer = b->n_local;
+        job.dst_inner = n;
+        job.scale = st;
+        job.out_mode = ntt::OUT_NATURAL;
+        rc = run_ntt(ctx, job);
+    }
+    return rc;
 }
 
 // Phase 3: salt columns, "build Merkle tree" (oracle.rs:210-214), timings.  ev[1] must have been
@@ -942,12 +958,37 @@ static int batch_from_host_columns(qp_ctx* ctx, const uint64_t* const* cols, boo
         const size_t c0 = g * per, c1 = std::min(c0 + per, n_cols);
         return upload_columns(ctx, cols, pinned_src, c0, c1, n, d_values + c0 * n, g);
     };
-    if (pinned_src)
+    // pinned source: every upload is queued up front.  Pageable source: a stager thread walks the groups
+    // (stage into the ring -- host-blocking -- then queue the copy) and publishes issued[g]; this thread
+    // queues the compute of a group once its copy has been queued, so staging never waits for launches.
+    std::vector<std::atomic<int>> issued(n_groups);
+    for (auto& f : issued) f.store(0);
+    std::atomic<int> stage_rc{QP_OK};
+    std::thread stager;
+    if (pinned_src) {
         for (int g = 0; g < n_groups && !rc; g++) rc = upload(g);
+        for (auto& f : issued) f.store(1);
+    } else {
+        stager = std::thread([&] {
+            cudaSetDevice(ctx->device);
+            for (int g = 0; g < n_groups; g++) {
+                int r = upload(g);
+                if (r) stage_rc.store(r);
+                issued[g].store(1, std::memory_order_release);
+                if (r) {
+                    for (int k = g + 1; k < n_groups; k++) issued[k].store(1, std::memory_order_release);
+                    return;
+                }
+            }
+        });
+    }
     for (int g = 0; g < n_groups && !rc; g++) {
         const size_t c0 = g * per, c1 = std::min(c0 + per, n_cols);
-        if (!pinned_src) rc = upload(g);
-        if (rc) break;
+        while (!issued[g].load(std::memory_order_acquire)) std::this_thread::yield();
+        if (stage_rc.load()) {
+            rc = stage_rc.load();
+            break;
+        }
         cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[g], 0);
         cudaEventRecord(ctx->grp_ev[3 * g], ctx->stream);
         rc = ifft_device(ctx, d_values + c0 * n, c1 - c0, degree_log, b->coeffs + c0 * n, d_values + c0 * n);
@@ -964,6 +1005,8 @@ static int batch_from_host_columns(qp_ctx* ctx, const uint64_t* const* cols, boo
         }
         cudaEventRecord(ctx->grp_ev[3 * g + 2], ctx->stream);
     }
+    if (stager.joinable()) stager.join();
+    if (!rc) rc = stage_rc.load();
     if (rc) return bail(rc);
     const uint64_t* d_salt = nullptr;
     if (blinding) {
