@@ -110,6 +110,12 @@ const char* qp_mctx_last_error(const qp_mctx* m);
 int qp_mbatch_from_values_cols(qp_mctx* m, const uint64_t* const* cols, size_t n_cols, unsigned degree_log,
                                unsigned rate_bits, int blinding, unsigned cap_height, const uint64_t* salt,
                                qp_mbatch** out);
+/* from_values (is_coeffs = 0) / from_coeffs (1) on a matrix [n_cols][2^degree_log] resident on devices[0] and
+ * complete before the call (the Z / partial-product columns and the quotient chunks of a proof are computed
+ * there): device 0 owns every piece, the other devices receive them as peer copies.  `salt`: host. */
+int qp_mbatch_from_device(qp_mctx* m, const uint64_t* dev0_data, int is_coeffs, size_t n_cols, unsigned degree_log,
+                          unsigned rate_bits, int blinding, unsigned cap_height, const uint64_t* salt,
+                          qp_mbatch** out);
 /* the whole cap, [2^cap_height][4], host */
 int qp_mbatch_cap(const qp_mbatch* b, uint64_t* out);
 unsigned qp_mbatch_num_shards(const qp_mbatch* b);
@@ -389,6 +395,8 @@ int qp_dev_alloc(qp_ctx* ctx, size_t n_words, uint64_t** out);
 void qp_dev_free(qp_ctx* ctx, uint64_t* p);
 /* Copy n_words u64 between host and device buffers on the context's stream (synchronous). */
 int qp_memcpy(qp_ctx* ctx, uint64_t* dst, int dst_space, const uint64_t* src, int src_space, size_t n_words);
+/* device memory of src_ctx's GPU -> device memory of dst_ctx's GPU (peer copy), complete at return */
+int qp_memcpy_peer(qp_ctx* dst_ctx, uint64_t* dst, qp_ctx* src_ctx, const uint64_t* src, size_t n_words);
 /* all_wires_permutation_partial_products (plonky2/src/plonk/prover.rs:402-480) followed by the
  * Z-first ordering of prover.rs:255-261.  wires: witness columns [>= num_routed_wires][n] (values on
  * H); betas, gammas: [num_challenges] (host).  out: [(nc + nc * num_partial_products)][n] value
@@ -405,6 +413,18 @@ int qp_circuit_compute_quotient_polys(qp_circuit* c, const qp_batch* constants_s
                                       const qp_batch* zs_partial_products, const uint64_t* betas,
                                       const uint64_t* gammas, const uint64_t* alphas,
                                       const uint64_t public_inputs_hash[4], uint64_t* out, int out_space);
+/* The same in two steps for a coset-sharded (multi-GPU) commitment: every term of the vanishing polynomial at a
+ * point needs that point and the next row of the same coset (prover.rs:679,750), so device i evaluates the
+ * positions of ITS shard from ITS shards of the three oracles (step 1: out_dev = [nc][*pos_count] on that device,
+ * leaf order, local; *pos_first = where the block belongs), the blocks are gathered side by side on one device and
+ * step 2 turns the whole domain's values (leaf order, [nc][n << quotient_degree_bits], consumed) into the
+ * quotient coefficients there. */
+int qp_circuit_quotient_values_shard(qp_circuit* c, const qp_batch* constants_sigmas, const qp_batch* wires,
+                                     const qp_batch* zs_partial_products, const uint64_t* betas,
+                                     const uint64_t* gammas, const uint64_t* alphas,
+                                     const uint64_t public_inputs_hash[4], uint64_t* out_dev, size_t* pos_first,
+                                     size_t* pos_count);
+int qp_circuit_quotient_finish(qp_circuit* c, uint64_t* vals_leaf_order, uint64_t* out, int out_space);
 
 #ifdef __cplusplus
 }

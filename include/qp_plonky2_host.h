@@ -68,6 +68,14 @@ int qp_fri_proof(qp_ctx* ctx, const qp_batch* const* initial_oracles, size_t n_o
                  unsigned n_rounds, unsigned proof_of_work_bits, unsigned num_query_rounds, uint8_t* out,
                  size_t capacity, size_t* len_out);
 
+/* The same with coset-sharded initial oracles (multi-GPU commitments): oracle_shards[t * n_shards + s] is shard s
+ * of oracle t; each query index is opened on the shard that owns it.  The bytes are those of qp_fri_proof on the
+ * whole batches. */
+int qp_fri_proof_sharded(qp_ctx* ctx, const qp_batch* const* oracle_shards, size_t n_oracles, unsigned n_shards,
+                         qp_fri* f, qp_challenger* challenger, unsigned rate_bits, unsigned cap_height,
+                         const unsigned* arity_bits, unsigned n_rounds, unsigned proof_of_work_bits,
+                         unsigned num_query_rounds, uint8_t* out, size_t capacity, size_t* len_out);
+
 /* ---- circuit data for the quotient (plonky2/src/plonk/circuit_data.rs:412-470) ---------------- */
 /* The gates of a circuit, compiled on the host into the constraint program of qp_circuit_desc
  * (qp_plonky2_b200.h): gates are sorted by (degree, id) like CircuitBuilder::build does
@@ -155,6 +163,16 @@ int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* constants_sigm
                 const qp_prover_config* cfg, const uint64_t* wires, int space, const uint64_t* public_inputs,
                 size_t n_public_inputs, const uint64_t* wires_salt, const uint64_t* zs_salt,
                 const uint64_t* quotient_salt, uint8_t* out, size_t capacity, size_t* len_out, double* timing_ms);
+
+/* prove() over every GPU of a multi-device context (qp_mctx, include/qp_plonky2_b200.h): the four commitments and
+ * the evaluation of the vanishing polynomial are sharded by coset = by cap subtree, the rest (Z / partial products,
+ * the inverse transform of the gathered quotient values, openings, FRI commit phase) runs on devices[0]; query
+ * openings come from the shard that owns the leaf.  circuits[i] must have been created on qp_mctx_ctx(m, i)
+ * (circuits[0] with sigmas); constants_sigmas is the multi-device commitment of the constants + sigmas columns;
+ * `wires` is HOST memory [num_wires][n].  Same two-call protocol, same bytes as qp_prove. */
+int qp_mprove(qp_mctx* m, qp_circuit* const* circuits, qp_mbatch* constants_sigmas, const uint64_t circuit_digest[4],
+              const qp_prover_config* cfg, const uint64_t* wires, const uint64_t* public_inputs,
+              size_t n_public_inputs, uint8_t* out, size_t capacity, size_t* len_out, double* timing_ms);
 
 #ifdef __cplusplus
 }

@@ -240,6 +240,7 @@ def lib():
         "qp_hash_no_pad": (None, [vp, sz, vp]),
         "qp_circuit_digest": (None, [vp, sz, u32, vp]),
         "qp_prove": (i32, [vp, vp, vp, vp, vp, vp, i32, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(C.c_double)]),
+        "qp_mprove": (i32, [vp, vp, vp, vp, vp, vp, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(C.c_double)]),
         "qp_prove_zk": (i32, [vp, vp, vp, vp, vp, vp, i32, vp, sz, vp, vp, vp, vp, sz, C.POINTER(sz), C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():

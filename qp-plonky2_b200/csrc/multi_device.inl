@@ -115,9 +115,45 @@ static void column_shard(size_t n_cols, unsigned world, unsigned rank, size_t* l
 }
 }  // namespace multi
 
+// Source of the columns: host column vectors (sharded across the devices for upload + inverse transform), or a
+// matrix [n_cols][n] already resident on devices[0] (values or coefficients: the Z / partial-product columns and
+// the quotient chunks of a proof are computed there) -- then device 0 owns every piece.
+static int mbatch_build(qp_mctx* m, const uint64_t* const* cols, const uint64_t* dev0_data, int dev0_is_coeffs,
+                        size_t n_cols, unsigned degree_log, unsigned rate_bits, int blinding, unsigned cap_height,
+                        const uint64_t* salt, qp_mbatch** out);
+
 extern "C" int qp_mbatch_from_values_cols(qp_mctx* m, const uint64_t* const* cols, size_t n_cols, unsigned degree_log,
                                           unsigned rate_bits, int blinding, unsigned cap_height, const uint64_t* salt,
                                           qp_mbatch** out) {
+    if (!m) return QP_ERR_BAD_ARG;
+    if (!cols) {
+        m->err = "null column table";
+        return QP_ERR_BAD_ARG;
+    }
+    for (size_t c = 0; c < n_cols; c++)
+        if (!cols[c]) {
+            m->err = "null column";
+            return QP_ERR_BAD_ARG;
+        }
+    return mbatch_build(m, cols, nullptr, 0, n_cols, degree_log, rate_bits, blinding, cap_height, salt, out);
+}
+
+// from_values / from_coeffs on a matrix [n_cols][2^degree_log] resident on devices[0] (complete before the call);
+// `salt` is host memory.
+extern "C" int qp_mbatch_from_device(qp_mctx* m, const uint64_t* dev0_data, int is_coeffs, size_t n_cols,
+                                     unsigned degree_log, unsigned rate_bits, int blinding, unsigned cap_height,
+                                     const uint64_t* salt, qp_mbatch** out) {
+    if (!m) return QP_ERR_BAD_ARG;
+    if (!dev0_data) {
+        m->err = "null device matrix";
+        return QP_ERR_BAD_ARG;
+    }
+    return mbatch_build(m, nullptr, dev0_data, is_coeffs, n_cols, degree_log, rate_bits, blinding, cap_height, salt, out);
+}
+
+static int mbatch_build(qp_mctx* m, const uint64_t* const* cols, const uint64_t* dev0_data, int dev0_is_coeffs,
+                        size_t n_cols, unsigned degree_log, unsigned rate_bits, int blinding, unsigned cap_height,
+                        const uint64_t* salt, qp_mbatch** out) {
     if (!m) return QP_ERR_BAD_ARG;
     auto mfail = [&](int code, const char* msg) {
         m->err = msg;
@@ -125,9 +161,6 @@ extern "C" int qp_mbatch_from_values_cols(qp_mctx* m, const uint64_t* const* col
     };
     if (!out) return mfail(QP_ERR_BAD_ARG, "null out");
     *out = nullptr;
-    if (!cols) return mfail(QP_ERR_BAD_ARG, "null column table");
-    for (size_t c = 0; c < n_cols; c++)
-        if (!cols[c]) return mfail(QP_ERR_BAD_ARG, "null column");
     const unsigned D = (unsigned)m->devices.size();
     if (D > (1u << rate_bits) || D > (1u << cap_height))
         return mfail(QP_ERR_BAD_ARG, "coset sharding needs #devices <= 2^rate_bits and <= 2^cap_height");
@@ -135,9 +168,17 @@ extern "C" int qp_mbatch_from_values_cols(qp_mctx* m, const uint64_t* const* col
     const size_t n = (size_t)1 << degree_log;
     const size_t PIECE = 8;
     std::vector<multi::Piece> pieces;
+    auto shard_of = [&](unsigned d, size_t* lo, size_t* hi) {
+        if (dev0_data) {  // everything lives on device 0
+            *lo = 0;
+            *hi = d == 0 ? n_cols : 0;
+        } else {
+            multi::column_shard(n_cols, D, d, lo, hi);
+        }
+    };
     for (unsigned d = 0; d < D; d++) {
         size_t lo, hi;
-        multi::column_shard(n_cols, D, d, &lo, &hi);
+        shard_of(d, &lo, &hi);
         for (size_t c0 = lo; c0 < hi; c0 += PIECE) pieces.push_back({d, c0, std::min(c0 + PIECE, hi)});
     }
     const size_t K = pieces.size();
@@ -181,29 +222,39 @@ extern "C" int qp_mbatch_from_values_cols(qp_mctx* m, const uint64_t* const* col
         qp_ctx* ctx = m->prod_ctx[d];
         if (cudaSetDevice(m->devices[d]) != cudaSuccess) return QP_ERR_CUDA;
         size_t lo, hi;
-        multi::column_shard(n_cols, D, d, &lo, &hi);
+        shard_of(d, &lo, &hi);
         if (lo == hi) return QP_OK;
         TempScope tmp(ctx);
         uint64_t* d_values = nullptr;
-        int r = tmp.alloc(&d_values, (hi - lo) * n);
-        if (!r) r = ensure_ring(ctx, std::min(PIECE, hi - lo) * n);
-        if (r) return r;
-        cudaEventRecord(ctx->ready_ev, ctx->stream);
-        cudaStreamWaitEvent(ctx->copy_stream, ctx->ready_ev, 0);
+        int r = QP_OK;
+        if (!dev0_data) {
+            r = tmp.alloc(&d_values, (hi - lo) * n);
+            if (!r) r = ensure_ring(ctx, std::min(PIECE, hi - lo) * n);
+            if (r) return r;
+            cudaEventRecord(ctx->ready_ev, ctx->stream);
+            cudaStreamWaitEvent(ctx->copy_stream, ctx->ready_ev, 0);
+        }
         int g = 0;
         for (size_t k = 0; k < K; k++) {
             if (pieces[k].owner != d) continue;
             if (abort_flag.load()) return QP_OK;
             const size_t c0 = pieces[k].c0, c1 = pieces[k].c1;
-            uint64_t* dv = d_values + (c0 - lo) * n;
-            // (columns the caller has pinned -- cudaHostRegister / cudaMallocHost -- skip the staging ring)
-            r = upload_columns(ctx, cols, host_pointer_is_pinned(cols[c0]) && host_pointer_is_pinned(cols[c1 - 1]), c0, c1,
-                               n, dv, g);
-            if (r) return r;
-            cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[g % qp_ctx::MAX_GROUPS], 0);
-            g++;
             uint64_t* own = mb->shards[d]->coeffs + c0 * n;
-            r = ifft_device(ctx, dv, c1 - c0, degree_log, own, dv);
+            if (dev0_data) {
+                if (dev0_is_coeffs)
+                    CUDA_TRY(ctx, cudaMemcpyAsync(own, dev0_data + c0 * n, (c1 - c0) * n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+                else
+                    r = ifft_device(ctx, dev0_data + c0 * n, c1 - c0, degree_log, own, nullptr);
+            } else {
+                uint64_t* dv = d_values + (c0 - lo) * n;
+                // (columns the caller has pinned -- cudaHostRegister / cudaMallocHost -- skip the staging ring)
+                r = upload_columns(ctx, cols, host_pointer_is_pinned(cols[c0]) && host_pointer_is_pinned(cols[c1 - 1]), c0,
+                                   c1, n, dv, g);
+                if (r) return r;
+                cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[g % qp_ctx::MAX_GROUPS], 0);
+                g++;
+                r = ifft_device(ctx, dv, c1 - c0, degree_log, own, dv);
+            }
             if (r) return r;
             CUDA_TRY(ctx, cudaEventRecord(ev_ready[k], ctx->stream));
             for (unsigned p = 0; p < D; p++) {

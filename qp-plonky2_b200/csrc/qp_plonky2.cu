@@ -2614,6 +2614,18 @@ extern "C" int qp_circuit_describe(const qp_circuit* c, qp_circuit_desc* out) {
 }
 extern "C" int qp_circuit_has_sigmas(const qp_circuit* c) { return c && c->sigmas ? 1 : 0; }
 
+// Device-to-device copy between two contexts' devices (peer copy over NVLink where the topology has it),
+// ordered after the work queued on src_ctx's stream and complete when the call returns.
+extern "C" int qp_memcpy_peer(qp_ctx* dst_ctx, uint64_t* dst, qp_ctx* src_ctx, const uint64_t* src, size_t n_words) {
+    if (!dst_ctx || !src_ctx) return QP_ERR_BAD_ARG;
+    if ((!dst || !src) && n_words) return fail(src_ctx, QP_ERR_BAD_ARG, "null buffer");
+    if (n_words == 0) return QP_OK;
+    CUDA_TRY(src_ctx, cudaSetDevice(src_ctx->device));
+    CUDA_TRY(src_ctx, cudaMemcpyPeerAsync(dst, dst_ctx->device, src, src_ctx->device, n_words * 8, src_ctx->stream));
+    CUDA_TRY(src_ctx, cudaStreamSynchronize(src_ctx->stream));
+    return QP_OK;
+}
+
 // Stream-ordered device scratch for host-side drivers that keep intermediates on the device.
 extern "C" int qp_dev_alloc(qp_ctx* ctx, size_t n_words, uint64_t** out) {
     if (!ctx || !out) return QP_ERR_BAD_ARG;
@@ -2710,33 +2722,18 @@ extern "C" int qp_circuit_partial_products_and_zs(qp_circuit* c, const uint64_t*
 }
 
 // compute_quotient_polys (prover.rs:640-866): out[num_challenges][n << qdb] coefficients.
-extern "C" int qp_circuit_compute_quotient_polys(qp_circuit* c, const qp_batch* constants_sigmas,
-                                                 const qp_batch* wires, const qp_batch* zs_partial_products,
-                                                 const uint64_t* betas, const uint64_t* gammas,
-                                                 const uint64_t* alphas, const uint64_t public_inputs_hash[4],
-                                                 uint64_t* out, int out_space) {
-    if (!c) return QP_ERR_BAD_ARG;
+// The quotient VALUES over the part of the quotient domain the three batches cover (all of it for whole
+// batches; a coset shard's positions for the shards of a multi-GPU commitment -- every term of the vanishing
+// polynomial at a point needs only that point and the next row of the same coset, prover.rs:679,750).
+// whole domain: d_vals = [nc][n_lde] in natural order.  shard: d_vals = [nc][pos_count] in leaf order, local.
+static int quotient_values(qp_circuit* c, const qp_batch* constants_sigmas, const qp_batch* wires,
+                           const qp_batch* zs_partial_products, const uint64_t* betas, const uint64_t* gammas,
+                           const uint64_t* alphas, const uint64_t public_inputs_hash[4], bool shard_layout,
+                           uint64_t* d_vals, size_t pos_first, size_t pos_count) {
     qp_ctx* ctx = c->ctx;
-    if (!constants_sigmas || !wires || !zs_partial_products || !betas || !gammas || !alphas ||
-        !public_inputs_hash || !out)
-        return fail(ctx, QP_ERR_BAD_ARG, "null argument");
     const qp_circuit_desc& d = c->d;
     const unsigned nc = d.num_challenges, np = d.num_partial_products;
-    const qp_batch* bs[3] = {constants_sigmas, wires, zs_partial_products};
-    for (const qp_batch* b : bs) {
-        if (b->ctx != ctx) return fail(ctx, QP_ERR_BAD_ARG, "batch belongs to another context");
-        if (b->degree_log != d.degree_bits) return fail(ctx, QP_ERR_DEGREE_MISMATCH, "Polynomial degrees inconsistent");
-        // "Having constraints of degree higher than the rate is not supported yet", prover.rs:662-666
-        if (d.quotient_degree_bits > b->rate_bits) return fail(ctx, QP_ERR_BAD_ARG, "quotient degree exceeds the rate");
-        if (b->block_first != 0 || b->block_count != (1u << b->rate_bits))
-            return fail(ctx, QP_ERR_BAD_ARG, "quotient evaluation needs unsharded batches");
-    }
-    if (constants_sigmas->n_cols < (size_t)d.num_constants + d.num_routed_wires || wires->n_cols < d.num_wires ||
-        zs_partial_products->n_cols < (size_t)nc + (size_t)nc * np)
-        return fail(ctx, QP_ERR_BAD_ARG, "batch has too few polynomials for this circuit");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const unsigned lg_lde = d.degree_bits + d.quotient_degree_bits;
-    const size_t n_lde = (size_t)1 << lg_lde;
     quotient::Params p{};
     p.degree_bits = d.degree_bits;
     p.qdb = d.quotient_degree_bits;
@@ -2762,6 +2759,10 @@ extern "C" int qp_circuit_compute_quotient_polys(qp_circuit* c, const qp_batch* 
     p.pool = c->pool;
     p.pool_len = (unsigned)d.pool_len;
     p.n_regs = d.program_regs ? d.program_regs : 1;
+    p.pos_first = pos_first;
+    p.pos_count = pos_count;
+    p.out_leaf_order = shard_layout ? 1 : 0;
+    p.out_lg = shard_layout ? ilog2(pos_count) : lg_lde;
     const unsigned base = nc + nc * (np + 1);
     const unsigned stride = (base > c->max_emit ? base : c->max_emit) + 1;
     p.apow_stride = stride;
@@ -2777,16 +2778,11 @@ extern "C" int qp_circuit_compute_quotient_polys(qp_circuit* c, const qp_batch* 
         }
     }
     for (int i = 0; i < 4; i++) p.pih[i] = public_inputs_hash[i];
-    uint64_t *d_apow = nullptr, *d_out = nullptr;
-    int rc = dev_alloc(ctx, &d_apow, apow.size());
-    const size_t out_words = (size_t)nc * n_lde;
-    if (!rc) {
-        if (out_space == QP_DEVICE) d_out = out;
-        else rc = dev_alloc(ctx, &d_out, out_words);
-    }
-    uint64_t* d_vals = nullptr;
-    if (!rc) rc = dev_alloc(ctx, &d_vals, out_words);
+    TempScope tmp(ctx);
+    uint64_t* d_apow = nullptr;
+    int rc = tmp.alloc(&d_apow, apow.size());
     if (rc) return rc;
+    const size_t out_words = (size_t)nc << p.out_lg;
     CUDA_TRY(ctx, cudaMemcpyAsync(d_apow, apow.data(), apow.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     p.alpha_pows = d_apow;
     const size_t smem = quotient::smem_words(p.pool_len, p.n_regs) * 8;
@@ -2795,7 +2791,7 @@ extern "C" int qp_circuit_compute_quotient_polys(qp_circuit* c, const qp_batch* 
         CUDA_TRY(ctx, cudaFuncSetAttribute(quotient::quotient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // The units of a point (permutation terms + program segments) are spread over blockIdx.y while
     // the tiles alone leave SMs idle: aim at ~8 resident blocks per SM.
-    const unsigned tiles = (unsigned)cdiv(n_lde, quotient::BLOCK), units = 1 + c->n_seg;
+    const unsigned tiles = (unsigned)cdiv(pos_count, quotient::BLOCK), units = 1 + c->n_seg;
     unsigned ny = (unsigned)cdiv((size_t)ctx->sm_count * 8, (size_t)tiles);
     if (ny > units) ny = units;
     if (ny < 1) ny = 1;
@@ -2803,39 +2799,142 @@ extern "C" int qp_circuit_compute_quotient_polys(qp_circuit* c, const qp_batch* 
     const unsigned n_parts = ny + (c->native.present ? 1 : 0);
     uint64_t* d_partial = nullptr;
     if (n_parts > 1) {
-        rc = dev_alloc(ctx, &d_partial, (size_t)n_parts * out_words);
+        rc = tmp.alloc(&d_partial, (size_t)n_parts * out_words);
         if (rc) return rc;
     }
     p.out = n_parts > 1 ? d_partial : d_vals;
     p.partial_out = n_parts > 1;
     LAUNCH(ctx, quotient::quotient_kernel, dim3(tiles, ny), quotient::BLOCK, smem, p);
     if (c->native.present)
-        LAUNCH(ctx, quotient::poseidon_gate_kernel, cdiv(n_lde, 128), 128, 0, p, c->native, d_partial + (size_t)ny * out_words);
+        LAUNCH(ctx, quotient::poseidon_gate_kernel, cdiv(pos_count, 128), 128, 0, p, c->native, d_partial + (size_t)ny * out_words);
     if (n_parts > 1)
-        LAUNCH(ctx, quotient::combine_kernel, cdiv(out_words, 256), 256, 0, d_partial, n_parts, nc, lg_lde,
-               d.quotient_degree_bits, p.zh_inv, d_vals);
-    dev_free(ctx, d_partial);
+        LAUNCH(ctx, quotient::combine_kernel, cdiv(out_words, 256), 256, 0, d_partial, n_parts, nc, p.out_lg,
+               d.quotient_degree_bits, p.zh_inv, d_vals, lg_lde, pos_first, p.out_leaf_order);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // apow dies at return
-    // values.coset_ifft(F::coset_shift()), polynomial/mod.rs:58-88
+    return QP_OK;
+}
+
+// values (natural order, [nc][n_lde], consumed as scratch) -> quotient coefficients:
+// values.coset_ifft(F::coset_shift()), polynomial/mod.rs:58-88
+static int quotient_finish(qp_circuit* c, uint64_t* d_vals, uint64_t* d_out) {
+    qp_ctx* ctx = c->ctx;
+    const qp_circuit_desc& d = c->d;
+    const unsigned lg_lde = d.degree_bits + d.quotient_degree_bits;
+    const size_t n_lde = (size_t)1 << lg_lde;
     NttJob job;
     job.src = d_vals;
     job.dst = d_out;
     job.L = (int)lg_lde;
-    job.n_vec = nc;
+    job.n_vec = d.num_challenges;
     job.inner_bits = 0;
     job.src_outer = n_lde;
     job.dst_outer = n_lde;
     job.out_mode = ntt::OUT_INVERSE;
     job.scratch = d_vals;
-    rc = run_ntt(ctx, job);
-    if (!rc) {
-        LAUNCH(ctx, quotient::scale_powers_kernel, cdiv(out_words, 256), 256, 0, d_out, (size_t)nc, lg_lde,
-               c->g_inv.lo, c->g_inv.hi, c->g_inv.split);
-        if (out_space != QP_DEVICE) rc = copy_out(ctx, out, QP_HOST, d_out, out_words);
+    int rc = run_ntt(ctx, job);
+    if (rc) return rc;
+    LAUNCH(ctx, quotient::scale_powers_kernel, cdiv((size_t)d.num_challenges * n_lde, 256), 256, 0, d_out,
+           (size_t)d.num_challenges, lg_lde, c->g_inv.lo, c->g_inv.hi, c->g_inv.split);
+    return QP_OK;
+}
+
+static int quotient_check_batches(qp_circuit* c, const qp_batch* const bs[3], bool whole) {
+    qp_ctx* ctx = c->ctx;
+    const qp_circuit_desc& d = c->d;
+    const unsigned nc = d.num_challenges, np = d.num_partial_products;
+    for (int k = 0; k < 3; k++) {
+        const qp_batch* b = bs[k];
+        if (b->ctx != ctx) return fail(ctx, QP_ERR_BAD_ARG, "batch belongs to another context");
+        if (b->degree_log != d.degree_bits) return fail(ctx, QP_ERR_DEGREE_MISMATCH, "Polynomial degrees inconsistent");
+        // "Having constraints of degree higher than the rate is not supported yet", prover.rs:662-666
+        if (d.quotient_degree_bits > b->rate_bits) return fail(ctx, QP_ERR_BAD_ARG, "quotient degree exceeds the rate");
+        if (whole && (b->block_first != 0 || b->block_count != (1u << b->rate_bits)))
+            return fail(ctx, QP_ERR_BAD_ARG, "quotient evaluation needs unsharded batches (shards: qp_circuit_quotient_values_shard)");
+        if (b->block_first != bs[0]->block_first || b->block_count != bs[0]->block_count || b->rate_bits != bs[0]->rate_bits)
+            return fail(ctx, QP_ERR_BAD_ARG, "the three batches must be the same coset shard");
     }
-    if (out_space != QP_DEVICE) dev_free(ctx, d_out);
-    dev_free(ctx, d_vals);
-    dev_free(ctx, d_apow);
+    if (bs[0]->n_cols < (size_t)d.num_constants + d.num_routed_wires || bs[1]->n_cols < d.num_wires ||
+        bs[2]->n_cols < (size_t)nc + (size_t)nc * np)
+        return fail(ctx, QP_ERR_BAD_ARG, "batch has too few polynomials for this circuit");
+    return QP_OK;
+}
+
+extern "C" int qp_circuit_compute_quotient_polys(qp_circuit* c, const qp_batch* constants_sigmas,
+                                                 const qp_batch* wires, const qp_batch* zs_partial_products,
+                                                 const uint64_t* betas, const uint64_t* gammas,
+                                                 const uint64_t* alphas, const uint64_t public_inputs_hash[4],
+                                                 uint64_t* out, int out_space) {
+    if (!c) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = c->ctx;
+    if (!constants_sigmas || !wires || !zs_partial_products || !betas || !gammas || !alphas ||
+        !public_inputs_hash || !out)
+        return fail(ctx, QP_ERR_BAD_ARG, "null argument");
+    const qp_circuit_desc& d = c->d;
+    const qp_batch* bs[3] = {constants_sigmas, wires, zs_partial_products};
+    int rc = quotient_check_batches(c, bs, true);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n_lde = (size_t)1 << (d.degree_bits + d.quotient_degree_bits);
+    const size_t out_words = (size_t)d.num_challenges * n_lde;
+    TempScope tmp(ctx);
+    uint64_t *d_out = out, *d_vals = nullptr;
+    if (out_space != QP_DEVICE) rc = tmp.alloc(&d_out, out_words);
+    if (!rc) rc = tmp.alloc(&d_vals, out_words);
+    if (!rc) rc = quotient_values(c, constants_sigmas, wires, zs_partial_products, betas, gammas, alphas,
+                                  public_inputs_hash, false, d_vals, 0, n_lde);
+    if (!rc) rc = quotient_finish(c, d_vals, d_out);
+    if (!rc && out_space != QP_DEVICE) rc = copy_out(ctx, out, QP_HOST, d_out, out_words);
+    if (!rc) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+// Multi-GPU form, step 1: the quotient values of ONE coset shard (the three batches are the shards of the
+// same device).  out_dev: [nc][*pos_count] on the shard's device, leaf order, local; *pos_first = the shard's
+// first position in the quotient domain (leaf order).  *pos_count = 0 (nothing written) if the shard lies
+// outside the quotient domain (quotient_degree_bits < rate_bits and a late coset).
+extern "C" int qp_circuit_quotient_values_shard(qp_circuit* c, const qp_batch* constants_sigmas, const qp_batch* wires,
+                                                const qp_batch* zs_partial_products, const uint64_t* betas,
+                                                const uint64_t* gammas, const uint64_t* alphas,
+                                                const uint64_t public_inputs_hash[4], uint64_t* out_dev,
+                                                size_t* pos_first, size_t* pos_count) {
+    if (!c) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = c->ctx;
+    if (!constants_sigmas || !wires || !zs_partial_products || !betas || !gammas || !alphas || !public_inputs_hash ||
+        !out_dev || !pos_first || !pos_count)
+        return fail(ctx, QP_ERR_BAD_ARG, "null argument");
+    const qp_circuit_desc& d = c->d;
+    const qp_batch* bs[3] = {constants_sigmas, wires, zs_partial_products};
+    int rc = quotient_check_batches(c, bs, false);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n_lde = (size_t)1 << (d.degree_bits + d.quotient_degree_bits);
+    const size_t first = (size_t)wires->block_first << d.degree_bits;
+    *pos_first = first;
+    *pos_count = first >= n_lde ? 0 : std::min(wires->n_local, n_lde - first);
+    if (*pos_count == 0) return QP_OK;
+    return quotient_values(c, constants_sigmas, wires, zs_partial_products, betas, gammas, alphas, public_inputs_hash,
+                           true, out_dev, *pos_first, *pos_count);
+}
+
+// Multi-GPU form, step 2 (on the device that gathered the shards' values): vals_leaf_order = [nc][n_lde] on
+// the circuit's device, the quotient values of the whole domain in LEAF order (the shards' blocks side by
+// side; consumed) -> quotient coefficients [nc][n_lde] (out: device or host).
+extern "C" int qp_circuit_quotient_finish(qp_circuit* c, uint64_t* vals_leaf_order, uint64_t* out, int out_space) {
+    if (!c) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = c->ctx;
+    if (!vals_leaf_order || !out) return fail(ctx, QP_ERR_BAD_ARG, "null argument");
+    const qp_circuit_desc& d = c->d;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const unsigned lg_lde = d.degree_bits + d.quotient_degree_bits;
+    const size_t out_words = (size_t)d.num_challenges << lg_lde;
+    TempScope tmp(ctx);
+    uint64_t *d_nat = nullptr, *d_out = out;
+    int rc = tmp.alloc(&d_nat, out_words);
+    if (!rc && out_space != QP_DEVICE) rc = tmp.alloc(&d_out, out_words);
+    if (rc) return rc;
+    LAUNCH(ctx, bitrev_permute_kernel, cdiv(out_words, 256), 256, 0, vals_leaf_order, d_nat, lg_lde, (size_t)d.num_challenges);
+    rc = quotient_finish(c, d_nat, d_out);
+    if (!rc && out_space != QP_DEVICE) rc = copy_out(ctx, out, QP_HOST, d_out, out_words);
     if (!rc) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return rc;
 }

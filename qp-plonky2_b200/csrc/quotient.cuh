@@ -110,6 +110,12 @@ struct Params {
     // partial_out != 0: out = partial sums [gridDim.y (+ 1)][nc][2^lg_lde] for combine_kernel.
     uint64_t* out;
     unsigned partial_out;
+    // A coset shard (multi-GPU): the kernel covers positions [pos_first, pos_first + pos_count) of the quotient
+    // domain in leaf order; the columns it reads are the shard's (position p lives at p - pos_first), and with
+    // out_leaf_order the outputs stay in leaf order, local: out[..][a][p - pos_first], rows of 2^out_lg words.
+    // Whole domain: pos_first = 0, pos_count = 2^lg_lde, out_lg = lg_lde, out_leaf_order = 0 (natural order).
+    size_t pos_first, pos_count;
+    unsigned out_lg, out_leaf_order;
 };
 
 // shared memory: pool | register file [n_regs][BLOCK].  The register file bounds the points resident
@@ -131,9 +137,9 @@ __global__ void __launch_bounds__(BLOCK, 6) quotient_kernel(Params p) {
     __syncthreads();
     const size_t n_lde = (size_t)1 << p.lg_lde;
     const size_t pos_raw = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-    const bool live = pos_raw < n_lde;
-    const size_t pos = live ? pos_raw : n_lde - 1;
-    const size_t i = brev(pos, p.lg_lde);  // natural index: the point is g w^i
+    const bool live = pos_raw < p.pos_count;
+    const size_t pos = live ? pos_raw : p.pos_count - 1;   // position inside the shard (what the columns are indexed by)
+    const size_t i = brev(p.pos_first + pos, p.lg_lde);    // natural index: the point is g w^i
     const unsigned zi = (unsigned)(i & (((size_t)1 << p.qdb) - 1));
     const unsigned base = p.nc + p.nc * (p.np + 1);
     uint64_t res[MAX_CHALLENGES], G[MAX_CHALLENGES], h[MAX_CHALLENGES];
@@ -150,7 +156,8 @@ __global__ void __launch_bounds__(BLOCK, 6) quotient_kernel(Params p) {
     const unsigned pool_base = (unsigned)__cvta_generic_to_shared(sh_pool);
     for (unsigned unit = blockIdx.y; unit < 1 + p.n_seg; unit += gridDim.y) {
         if (unit == 0) {
-            const size_t pos_next = brev((i + ((size_t)1 << p.qdb)) & (n_lde - 1), p.lg_lde);
+            // (the next row of the same coset: same high bits of the leaf index, so inside the shard)
+            const size_t pos_next = brev((i + ((size_t)1 << p.qdb)) & (n_lde - 1), p.lg_lde) - p.pos_first;
             const uint64_t x = gl::mul(gl::GENERATOR, p.tw_row[i]);
             // L_0(x) = Z_H(x) / (n (x - 1)), zero_poly_coset.rs:93-96
             const uint64_t l_0 = gl::mul(p.zh_eval[zi], inverse(gl::mul((uint64_t)1 << p.degree_bits, gl::sub(x, 1))));
@@ -251,10 +258,11 @@ __global__ void __launch_bounds__(BLOCK, 6) quotient_kernel(Params p) {
     for (int a = 0; a < MAX_CHALLENGES; a++)
         if (a < (int)p.nc) {
             const uint64_t total = gl::add(res[a], gl::mul(G[a], __ldg(&sh_apow[a * p.apow_stride + base])));
+            const size_t oi = p.out_leaf_order ? pos : i;
             if (!p.partial_out)
-                p.out[((size_t)a << p.lg_lde) + i] = gl::canon(gl::mul(total, zinv));  // prover.rs:848-853
+                p.out[((size_t)a << p.out_lg) + oi] = gl::canon(gl::mul(total, zinv));  // prover.rs:848-853
             else
-                p.out[(((size_t)blockIdx.y * p.nc + a) << p.lg_lde) + i] = total;
+                p.out[(((size_t)blockIdx.y * p.nc + a) << p.out_lg) + oi] = total;
         }
 }
 
@@ -273,10 +281,9 @@ struct NativePoseidon {
 };
 
 __global__ void __launch_bounds__(128) poseidon_gate_kernel(Params p, NativePoseidon g, uint64_t* __restrict__ out) {
-    const size_t n_lde = (size_t)1 << p.lg_lde;
     const size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= n_lde) return;
-    const size_t i = brev(pos, p.lg_lde);
+    if (pos >= p.pos_count) return;
+    const size_t i = brev(p.pos_first + pos, p.lg_lde);
     auto wire = [&](unsigned c) { return p.wires[c * p.wires_stride + pos]; };
     uint64_t h[MAX_CHALLENGES];
 #pragma unroll
@@ -346,19 +353,23 @@ __global__ void __launch_bounds__(128) poseidon_gate_kernel(Params p, NativePose
 #pragma unroll
     for (int a = 0; a < MAX_CHALLENGES; a++)
         if (a < (int)p.nc)
-            out[((size_t)a << p.lg_lde) + i] =
+            out[((size_t)a << p.out_lg) + (p.out_leaf_order ? pos : i)] =
                 gl::mul(gl::mul(f, h[a]), __ldg(&p.alpha_pows[a * p.apow_stride + base]));
 }
 
 // out[a][i] = Z_H(x_i)^-1 * sum_y partial[y][a][i]   (the units of quotient_kernel, summed)
-__global__ void combine_kernel(const uint64_t* __restrict__ partial, unsigned n_parts, unsigned nc, unsigned lg_lde,
-                               unsigned qdb, const uint64_t* __restrict__ zh_inv, uint64_t* __restrict__ out) {
+// (rows of 2^out_lg words; leaf_order: the word at row offset o is position pos_first + o of the domain,
+//  whose natural index is its bit reversal over lg_lde bits)
+__global__ void combine_kernel(const uint64_t* __restrict__ partial, unsigned n_parts, unsigned nc, unsigned out_lg,
+                               unsigned qdb, const uint64_t* __restrict__ zh_inv, uint64_t* __restrict__ out,
+                               unsigned lg_lde, size_t pos_first, unsigned leaf_order) {
     const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t words = (size_t)nc << lg_lde;
+    const size_t words = (size_t)nc << out_lg;
     if (id >= words) return;
     uint64_t acc = partial[id];
     for (unsigned y = 1; y < n_parts; y++) acc = gl::add(acc, partial[(size_t)y * words + id]);
-    const size_t i = id & (((size_t)1 << lg_lde) - 1);
+    const size_t o = id & (((size_t)1 << out_lg) - 1);
+    const size_t i = leaf_order ? brev(pos_first + o, lg_lde) : o;
     out[id] = gl::canon(gl::mul(acc, zh_inv[i & (((size_t)1 << qdb) - 1)]));
 }
 

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../include/qp_plonky2_host.h"
@@ -312,6 +313,259 @@ extern "C" int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* con
     QP_STEP(rc);
     scopes[6] = tm.lap(ctx);
     // public inputs: u64 length, then the elements (serialization/mod.rs:2077-2078)
+    const uint64_t npi = n_public_inputs;
+    for (int k = 0; k < 8; k++) bytes.push_back((uint8_t)(npi >> (8 * k)));
+    put_u64s(bytes, public_inputs, n_public_inputs);
+    cleanup();
+    if (bytes.size() != total) return QP_ERR_BAD_ARG;
+    std::memcpy(out, bytes.data(), total);
+    if (timing_ms) std::memcpy(timing_ms, scopes, sizeof scopes);
+    return QP_OK;
+#undef QP_STEP
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// prove() over every GPU of a multi-device context (BASELINE.json configs[4]: a large circuit whose LDEs do not
+// fit one GPU).  What is sharded by coset = by cap subtree: the four commitments -- LDE +
+// Merkle hashing, >= 90 % of the work of a large proof -- and the evaluation of the vanishing polynomial (a point
+// needs only its own coset, prover.rs:679,750).  What runs on device 0: the Z / partial-product columns (a
+// prefix product over the rows), the inverse transform of the quotient values (gathered there as peer copies:
+// num_challenges * 8 n words), the openings and the FRI commit phase of the final polynomial (every shard keeps
+// the full coefficient matrices, so device 0 has all it needs; the FRI oracle is 1/16 of one LDE column pair
+// per round).  Query openings are served by the shard that owns the leaf.  The proof is byte-identical to
+// qp_prove's.
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int qp_mprove(qp_mctx* m, qp_circuit* const* circuits, qp_mbatch* constants_sigmas,
+                         const uint64_t circuit_digest[4], const qp_prover_config* cfg, const uint64_t* wires,
+                         const uint64_t* public_inputs, size_t n_public_inputs, uint8_t* out, size_t capacity,
+                         size_t* len_out, double* timing_ms) {
+    if (!m || !circuits || !constants_sigmas || !circuit_digest || !cfg || !len_out) return QP_ERR_BAD_ARG;
+    const unsigned D = qp_mctx_num_devices(m);
+    if (D == 0 || qp_mbatch_num_shards(constants_sigmas) != D) return QP_ERR_BAD_ARG;
+    for (unsigned e = 0; e < D; e++)
+        if (!circuits[e]) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = qp_mctx_ctx(m, 0);
+    qp_circuit_desc d;
+    int rc = qp_circuit_describe(circuits[0], &d);
+    if (rc) return rc;
+    const unsigned nc = d.num_challenges, np = d.num_partial_products, qdf = cfg->quotient_degree_factor;
+    const size_t n = (size_t)1 << d.degree_bits;
+    const size_t n_pre = (size_t)d.num_constants + d.num_routed_wires;
+    const size_t n_zs = (size_t)nc * (1 + np), n_q = (size_t)nc * qdf;
+    const size_t cap_words = ((size_t)4) << cfg->cap_height;
+    unsigned arities[64];
+    const unsigned n_rounds = qp_fri_reduction_arity_bits(d.degree_bits, cfg->rate_bits, cfg->cap_height,
+                                                          cfg->arity_bits, cfg->final_poly_bits, arities);
+    const size_t leaf_lens[4] = {n_pre, d.num_wires, n_zs, n_q};
+    const size_t fri_len = qp_fri_proof_len(leaf_lens, 4, d.degree_bits + cfg->rate_bits, cfg->rate_bits,
+                                            cfg->cap_height, arities, n_rounds, cfg->num_query_rounds);
+    const size_t n_open = n_pre + d.num_wires + n_zs + nc + n_q;
+    const size_t total = 8 * (3 * cap_words + 2 * n_open) + fri_len + 8 * (1 + n_public_inputs);
+    *len_out = total;
+    if (!out) return QP_OK;
+    if (capacity < total || !wires || (n_public_inputs && !public_inputs)) return QP_ERR_BAD_ARG;
+    if (!qp_circuit_has_sigmas(circuits[0])) return QP_ERR_BAD_ARG;
+    if (qdf == 0 || qdf > (1u << d.quotient_degree_bits)) return QP_ERR_BAD_ARG;
+    if (qp_batch_leaf_len(qp_mbatch_shard(constants_sigmas, 0)) < n_pre) return QP_ERR_BAD_ARG;
+
+    Timer tm;
+    double scopes[7] = {0};
+    uint64_t pih[4];
+    qp_hash_no_pad(public_inputs, n_public_inputs, pih);
+    qp_mbatch *wb = nullptr, *zb = nullptr, *qb = nullptr;
+    qp_fri* fri = nullptr;
+    uint64_t *d_zs = nullptr, *d_q = nullptr, *d_vals = nullptr;
+    std::vector<uint8_t> bytes;
+    bytes.reserve(total);
+    auto cleanup = [&]() {
+        if (fri) qp_fri_free(fri);
+        qp_mbatch_free(wb);
+        qp_mbatch_free(zb);
+        qp_mbatch_free(qb);
+        qp_dev_free(ctx, d_zs);
+        qp_dev_free(ctx, d_q);
+        qp_dev_free(ctx, d_vals);
+    };
+#define QP_STEP(expr)            \
+    do {                         \
+        rc = (expr);             \
+        if (rc) {                \
+            cleanup();           \
+            return rc;           \
+        }                        \
+    } while (0)
+
+    // wires commitment over all devices, prover.rs:201-214
+    {
+        std::vector<const uint64_t*> cols(d.num_wires);
+        for (unsigned c = 0; c < d.num_wires; c++) cols[c] = wires + (size_t)c * n;
+        QP_STEP(qp_mbatch_from_values_cols(m, cols.data(), d.num_wires, d.degree_bits, cfg->rate_bits, 0, cfg->cap_height,
+                                           nullptr, &wb));
+    }
+    scopes[0] = tm.lap(ctx);
+    qp_challenger ch;
+    qp_challenger_init(&ch);
+    {
+        std::vector<uint64_t> v = {cfg->rate_bits, cfg->cap_height, cfg->proof_of_work_bits,
+                                   1, cfg->arity_bits, cfg->final_poly_bits,
+                                   cfg->num_query_rounds, 0 /* leaf_hiding */, d.degree_bits};
+        for (unsigned i = 0; i < n_rounds; i++) v.push_back(arities[i]);
+        qp_challenger_observe(&ch, v.data(), v.size());
+    }
+    qp_challenger_observe(&ch, circuit_digest, 4);
+    qp_challenger_observe(&ch, pih, 4);
+    std::vector<uint64_t> cap(cap_words);
+    QP_STEP(qp_mbatch_cap(wb, cap.data()));
+    qp_challenger_observe(&ch, cap.data(), cap_words);
+    put_u64s(bytes, cap.data(), cap_words);
+    std::vector<uint64_t> betas(nc), gammas(nc), alphas(nc);
+    for (auto& b : betas) b = qp_challenger_get(&ch);
+    for (auto& g : gammas) g = qp_challenger_get(&ch);
+    // Z and partial products on device 0 (prover.rs:250-261)
+    QP_STEP(qp_dev_alloc(ctx, n_zs * n, &d_zs));
+    QP_STEP(qp_circuit_partial_products_and_zs(circuits[0], wires, QP_HOST, betas.data(), gammas.data(), d_zs, QP_DEVICE));
+    QP_STEP(qp_ctx_synchronize(ctx));
+    scopes[1] = tm.lap(ctx);
+    QP_STEP(qp_mbatch_from_device(m, d_zs, 0, n_zs, d.degree_bits, cfg->rate_bits, 0, cfg->cap_height, nullptr, &zb));
+    scopes[2] = tm.lap(ctx);
+    QP_STEP(qp_mbatch_cap(zb, cap.data()));
+    qp_challenger_observe(&ch, cap.data(), cap_words);
+    put_u64s(bytes, cap.data(), cap_words);
+    for (auto& a : alphas) a = qp_challenger_get(&ch);
+    // quotient values, coset shard by coset shard, gathered on device 0 in leaf order (prover.rs:293-320)
+    const size_t n_lde = n << d.quotient_degree_bits;
+    QP_STEP(qp_dev_alloc(ctx, (size_t)nc * n_lde, &d_vals));
+    QP_STEP(qp_dev_alloc(ctx, (size_t)nc * n_lde, &d_q));
+    QP_STEP(qp_ctx_synchronize(ctx));   // the peers write into d_vals
+    {
+        std::vector<int> rcs(D, QP_OK);
+        std::vector<std::thread> th;
+        for (unsigned e = 0; e < D; e++)
+            th.emplace_back([&, e] {
+                qp_ctx* ce = qp_mctx_ctx(m, e);
+                const qp_batch* wsh = qp_mbatch_shard(wb, e);
+                const size_t n_loc = (size_t)qp_batch_cap_len(wsh) ? ((n << cfg->rate_bits) / D) : 0;
+                uint64_t* d_part = nullptr;
+                int r = qp_dev_alloc(ce, (size_t)nc * n_loc, &d_part);
+                size_t first = 0, count = 0;
+                if (!r)
+                    r = qp_circuit_quotient_values_shard(circuits[e], qp_mbatch_shard(constants_sigmas, e), wsh,
+                                                         qp_mbatch_shard(zb, e), betas.data(), gammas.data(), alphas.data(),
+                                                         pih, d_part, &first, &count);
+                for (unsigned a = 0; a < nc && !r && count; a++)
+                    r = qp_memcpy_peer(ctx, d_vals + (size_t)a * n_lde + first, ce, d_part + (size_t)a * count, count);
+                qp_dev_free(ce, d_part);
+                rcs[e] = r;
+            });
+        for (auto& t : th) t.join();
+        for (unsigned e = 0; e < D; e++)
+            if (rcs[e]) {
+                cleanup();
+                return rcs[e];
+            }
+    }
+    QP_STEP(qp_circuit_quotient_finish(circuits[0], d_vals, d_q, QP_DEVICE));
+    scopes[3] = tm.lap(ctx);
+    const uint64_t* d_chunks = d_q;
+    uint64_t* d_trim = nullptr;
+    if (qdf != (1u << d.quotient_degree_bits)) {
+        std::vector<uint64_t> host((size_t)nc * n_lde);
+        QP_STEP(qp_memcpy(ctx, host.data(), QP_HOST, d_q, QP_DEVICE, host.size()));
+        std::vector<uint64_t> trimmed((size_t)nc * qdf * n);
+        for (unsigned a = 0; a < nc; a++) {
+            for (size_t i = (size_t)qdf * n; i < n_lde; i++)
+                if (host[a * n_lde + i] % P) {
+                    cleanup();
+                    return QP_ERR_BAD_ARG;
+                }
+            std::memcpy(&trimmed[(size_t)a * qdf * n], &host[a * n_lde], (size_t)qdf * n * 8);
+        }
+        QP_STEP(qp_dev_alloc(ctx, trimmed.size(), &d_trim));
+        rc = qp_memcpy(ctx, d_trim, QP_DEVICE, trimmed.data(), QP_HOST, trimmed.size());
+        if (rc) {
+            qp_dev_free(ctx, d_trim);
+            cleanup();
+            return rc;
+        }
+        d_chunks = d_trim;
+    }
+    QP_STEP(qp_ctx_synchronize(ctx));
+    rc = qp_mbatch_from_device(m, d_chunks, 1, n_q, d.degree_bits, cfg->rate_bits, 0, cfg->cap_height, nullptr, &qb);
+    qp_dev_free(ctx, d_trim);
+    QP_STEP(rc);
+    scopes[4] = tm.lap(ctx);
+    QP_STEP(qp_mbatch_cap(qb, cap.data()));
+    qp_challenger_observe(&ch, cap.data(), cap_words);
+    put_u64s(bytes, cap.data(), cap_words);
+    const Ext zeta{qp_challenger_get(&ch), qp_challenger_get(&ch)};
+    {
+        Ext z = zeta;
+        for (unsigned i = 0; i < d.degree_bits; i++) z = emul(z, z);
+        if (z.a == 1 && z.b == 0) {
+            cleanup();
+            return QP_ERR_BAD_ARG;
+        }
+    }
+    const uint64_t g = fpow(7277203076849721926ULL, (uint64_t)1 << (32 - d.degree_bits));
+    const Ext zeta_next{fmul(g, zeta.a), fmul(g, zeta.b)};
+    // every shard holds the full coefficient matrices: device 0 evaluates (proof.rs:289-327)
+    const qp_batch *cs0 = qp_mbatch_shard(constants_sigmas, 0), *w0 = qp_mbatch_shard(wb, 0), *z0 = qp_mbatch_shard(zb, 0),
+                   *q0 = qp_mbatch_shard(qb, 0);
+    std::vector<uint64_t> cs_eval(2 * qp_batch_leaf_len(cs0)), w_eval(2 * (size_t)d.num_wires), z_eval(2 * n_zs),
+        zn_eval(2 * n_zs), q_eval(2 * n_q);
+    const uint64_t pz[2] = {zeta.a, zeta.b}, pzn[2] = {zeta_next.a, zeta_next.b};
+    QP_STEP(qp_batch_eval_polys(cs0, pz, cs_eval.data()));
+    QP_STEP(qp_batch_eval_polys(w0, pz, w_eval.data()));
+    QP_STEP(qp_batch_eval_polys(z0, pz, z_eval.data()));
+    QP_STEP(qp_batch_eval_polys(z0, pzn, zn_eval.data()));
+    QP_STEP(qp_batch_eval_polys(q0, pz, q_eval.data()));
+    scopes[5] = tm.lap(ctx);
+    qp_challenger_observe(&ch, cs_eval.data(), 2 * n_pre);
+    qp_challenger_observe(&ch, w_eval.data(), 2 * (size_t)d.num_wires);
+    qp_challenger_observe(&ch, z_eval.data(), 2 * (size_t)nc);
+    qp_challenger_observe(&ch, z_eval.data() + 2 * nc, 2 * (size_t)nc * np);
+    qp_challenger_observe(&ch, q_eval.data(), 2 * n_q);
+    qp_challenger_observe(&ch, zn_eval.data(), 2 * (size_t)nc);
+    put_u64s(bytes, cs_eval.data(), 2 * n_pre);
+    put_u64s(bytes, w_eval.data(), 2 * (size_t)d.num_wires);
+    put_u64s(bytes, z_eval.data(), 2 * (size_t)nc);
+    put_u64s(bytes, zn_eval.data(), 2 * (size_t)nc);
+    put_u64s(bytes, z_eval.data() + 2 * nc, 2 * (size_t)nc * np);
+    put_u64s(bytes, q_eval.data(), 2 * n_q);
+    const Ext alpha{qp_challenger_get(&ch), qp_challenger_get(&ch)};
+    const qp_batch* oracles0[4] = {cs0, w0, z0, q0};
+    std::vector<qp_opening_term> t0, t1;
+    Ext w{1, 0};
+    auto add_terms = [&](std::vector<qp_opening_term>& t, const qp_batch* b, size_t count) {
+        for (size_t i = 0; i < count; i++) {
+            t.push_back(qp_opening_term{b, i, {w.a, w.b}});
+            w = emul(w, alpha);
+        }
+    };
+    add_terms(t0, oracles0[0], n_pre);
+    add_terms(t0, oracles0[1], d.num_wires);
+    add_terms(t0, oracles0[2], n_zs);
+    add_terms(t0, oracles0[3], n_q);
+    const Ext shift0 = w;
+    w = Ext{1, 0};
+    add_terms(t1, oracles0[2], nc);
+    const Ext shift1 = w;
+    qp_opening_batch ob[2] = {{{zeta.a, zeta.b}, t0.data(), t0.size(), {shift0.a, shift0.b}},
+                              {{zeta_next.a, zeta_next.b}, t1.data(), t1.size(), {shift1.a, shift1.b}}};
+    QP_STEP(qp_fri_begin_from_openings(ctx, ob, 2, d.degree_bits, cfg->rate_bits, cfg->cap_height, &fri));
+    std::vector<const qp_batch*> shards(4 * (size_t)D);
+    qp_mbatch* mbs[4] = {constants_sigmas, wb, zb, qb};
+    for (unsigned t = 0; t < 4; t++)
+        for (unsigned e = 0; e < D; e++) shards[(size_t)t * D + e] = qp_mbatch_shard(mbs[t], e);
+    const size_t at = bytes.size();
+    bytes.resize(at + fri_len);
+    size_t got = 0;
+    rc = qp_fri_proof_sharded(ctx, shards.data(), 4, D, fri, &ch, cfg->rate_bits, cfg->cap_height, arities, n_rounds,
+                              cfg->proof_of_work_bits, cfg->num_query_rounds, bytes.data() + at, fri_len, &got);
+    if (!rc && got != fri_len) rc = QP_ERR_BAD_ARG;
+    QP_STEP(rc);
+    scopes[6] = tm.lap(ctx);
     const uint64_t npi = n_public_inputs;
     for (int k = 0; k < 8; k++) bytes.push_back((uint8_t)(npi >> (8 * k)));
     put_u64s(bytes, public_inputs, n_public_inputs);

@@ -213,7 +213,19 @@ extern "C" int qp_fri_proof(qp_ctx* ctx, const qp_batch* const* oracles, size_t 
                             qp_challenger* ch, unsigned rate_bits, unsigned cap_height, const unsigned* arity_bits,
                             unsigned n_rounds, unsigned pow_bits, unsigned num_queries, uint8_t* out,
                             size_t capacity, size_t* len_out) {
+    return qp_fri_proof_sharded(ctx, oracles, n_oracles, 1, f, ch, rate_bits, cap_height, arity_bits, n_rounds, pow_bits,
+                                num_queries, out, capacity, len_out);
+}
+
+// The same with the initial oracles held as coset shards (multi-GPU commitments): oracles[t * n_shards + s] is
+// shard s of oracle t, i.e. leaves [s N / S, (s + 1) N / S) with their part of the tree; a query index is
+// opened on the shard that owns it (the shard's cap entries ARE the global ones, so the path is the reference's).
+extern "C" int qp_fri_proof_sharded(qp_ctx* ctx, const qp_batch* const* oracles, size_t n_oracles, unsigned n_shards,
+                                    qp_fri* f, qp_challenger* ch, unsigned rate_bits, unsigned cap_height,
+                                    const unsigned* arity_bits, unsigned n_rounds, unsigned pow_bits,
+                                    unsigned num_queries, uint8_t* out, size_t capacity, size_t* len_out) {
     if (!ctx || !f || !ch || !len_out || (n_oracles && !oracles) || (n_rounds && !arity_bits)) return QP_ERR_BAD_ARG;
+    if (n_shards == 0 || (n_shards & (n_shards - 1)) || n_shards > (1u << cap_height)) return QP_ERR_BAD_ARG;
     const size_t cap_words = ((size_t)1 << cap_height) * 4;
     // QP_TRACE=1: wall-clock of the stages on stderr (every stage ends synchronised)
     static const bool trace = getenv("QP_TRACE") != nullptr;
@@ -256,12 +268,34 @@ extern "C" int qp_fri_proof(qp_ctx* ctx, const qp_batch* const* oracles, size_t 
     std::vector<std::vector<uint64_t>> o_rows(n_oracles), o_paths(n_oracles);
     std::vector<size_t> o_len(n_oracles);
     const unsigned o_layers = lde_bits - cap_height;
+    const size_t per_shard = lde / n_shards;
     for (size_t t = 0; t < n_oracles && !rc; t++) {
-        if (qp_batch_cap_len(oracles[t]) != ((size_t)1 << cap_height)) return QP_ERR_BAD_ARG;  // sharded batch
-        o_len[t] = qp_batch_leaf_len(oracles[t]);
+        const qp_batch* const* sh = oracles + t * n_shards;
+        if (qp_batch_cap_len(sh[0]) * n_shards != ((size_t)1 << cap_height)) return QP_ERR_BAD_ARG;  // not S shards of the tree
+        o_len[t] = qp_batch_leaf_len(sh[0]);
         o_rows[t].resize((size_t)num_queries * o_len[t] + 1);
         o_paths[t].resize((size_t)num_queries * o_layers * 4 + 1);
-        rc = qp_batch_open_many(oracles[t], x.data(), num_queries, o_rows[t].data(), o_paths[t].data());
+        if (n_shards == 1) {
+            rc = qp_batch_open_many(sh[0], x.data(), num_queries, o_rows[t].data(), o_paths[t].data());
+            continue;
+        }
+        for (unsigned s = 0; s < n_shards && !rc; s++) {
+            std::vector<uint64_t> local;
+            std::vector<unsigned> who;
+            for (unsigned q = 0; q < num_queries; q++)
+                if (x[q] / per_shard == s) {
+                    local.push_back(x[q] % per_shard);
+                    who.push_back(q);
+                }
+            if (local.empty()) continue;
+            std::vector<uint64_t> rows(local.size() * o_len[t] + 1), paths(local.size() * o_layers * 4 + 1);
+            rc = qp_batch_open_many(sh[s], local.data(), (unsigned)local.size(), rows.data(), paths.data());
+            for (size_t k = 0; k < who.size() && !rc; k++) {
+                std::memcpy(o_rows[t].data() + (size_t)who[k] * o_len[t], rows.data() + k * o_len[t], o_len[t] * 8);
+                std::memcpy(o_paths[t].data() + (size_t)who[k] * o_layers * 4, paths.data() + k * o_layers * 4,
+                            (size_t)o_layers * 32);
+            }
+        }
     }
     lap("oracle openings");
     std::vector<std::vector<uint64_t>> r_rows(n_rounds), r_paths(n_rounds);

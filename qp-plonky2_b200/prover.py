@@ -125,3 +125,51 @@ def prove(prover_data, wires, public_inputs, timing=None, salts=None):
     if timing is not None:
         timing.update(dict(zip(SCOPES, list(ms))))
     return bytes(buf)
+
+
+class MultiProverData:
+    """ProverData over a MultiContext: one Circuit per device (the gate program, k_is and -- on device 0 -- the
+    sigmas), the constants / sigmas commitment as a MultiBatch."""
+
+    def __init__(self, mctx, common, sigmas, constants_sigmas_values, fri_config=None):
+        from . import MultiBatch, fri_reduction_arity_bits
+        from .plonk import Circuit
+        self.mctx, self.common = mctx, common
+        self.fri = fri_config or FriConfig(common.rate_bits, common.cap_height)
+        self.circuits = [Circuit(ctx, common, sigmas if i == 0 else None) for i, ctx in enumerate(mctx.contexts)]
+        self.constants_sigmas_commitment = MultiBatch.from_values_cols(
+            mctx, list(constants_sigmas_values), self.fri.rate_bits, False, self.fri.cap_height)
+        self.reduction_arity_bits = fri_reduction_arity_bits(
+            common.degree_bits, self.fri.rate_bits, self.fri.cap_height, self.fri.arity_bits, self.fri.final_poly_bits)
+        self.circuit_digest = circuit_digest(self.constants_sigmas_commitment.cap, common.degree_bits)
+
+
+def mprove(prover_data, wires, public_inputs, timing=None):
+    """prove() over every GPU of the MultiContext (qp_mprove): the four commitments and the quotient evaluation are
+    sharded by coset, the rest runs on device 0; the bytes are prove()'s.  wires: host matrix [num_wires][n]."""
+    from . import QpError, lib
+    pd = prover_data
+    c, f = pd.common, pd.fri
+    cfg = _Config(f.rate_bits, f.cap_height, f.proof_of_work_bits, f.num_query_rounds, f.arity_bits,
+                  f.final_poly_bits, c.quotient_degree_factor)
+    w = np.ascontiguousarray(np.asarray(wires, dtype=np.uint64))
+    if w.shape != (c.num_wires, 1 << c.degree_bits):
+        raise ValueError("wires must be [num_wires][n]")
+    pis = np.ascontiguousarray(np.asarray([int(x) % P for x in public_inputs], dtype=np.uint64))
+    digest = np.ascontiguousarray(pd.circuit_digest, dtype=np.uint64)
+    circs = (C.c_void_p * len(pd.circuits))(*[x._h.value for x in pd.circuits])
+    need = C.c_size_t()
+    args = (pd.mctx._h, circs, pd.constants_sigmas_commitment._h, digest.ctypes.data, C.byref(cfg), w.ctypes.data,
+            pis.ctypes.data if pis.size else None, pis.size)
+    rc = lib().qp_mprove(*args, None, 0, C.byref(need), None)
+    if rc:
+        raise QpError(rc, "qp_mprove (sizing) failed")
+    buf = (C.c_uint8 * need.value)()
+    ms = (C.c_double * 7)()
+    rc = lib().qp_mprove(*args, buf, need.value, C.byref(need), ms)
+    if rc:
+        msgs = [lib().qp_last_error(x._h).decode() for x in pd.mctx.contexts] + [lib().qp_mctx_last_error(pd.mctx._h).decode()]
+        raise QpError(rc, "qp_mprove failed: " + " | ".join(x for x in msgs if x))
+    if timing is not None:
+        timing.update(dict(zip(SCOPES, list(ms))))
+    return bytes(buf)

@@ -277,3 +277,39 @@ def test_quotient_from_an_external_recording(qp, ctx, source):
     ref = plonk.Circuit(ctx, c, sc.sigmas)
     want = ref.compute_quotient_polys(g_cs, g_w, g_z, betas, gammas, alphas, sc.public_inputs_hash)
     assert (got == want).all()
+
+
+@pytest.mark.parametrize("degree_bits,poseidon,rec", [(7, False, False), (10, True, False), (12, True, True)])
+def test_multi_device_prove_equals_single_device_prove(qp, ctx, degree_bits, poseidon, rec):
+    """qp_mprove (BASELINE.json configs[4]: prove() with coset-sharded commitments and quotient evaluation over
+    every GPU of the box, one process): the proof is byte for byte the single-device proof, and the restated
+    verifier accepts it.  On a one-GPU box the multi-device driver runs with a single device (same code path:
+    shard gathering, peer copies onto itself, sharded query openings)."""
+    import torch
+    import verifier
+    from qp_plonky2_b200 import prover
+
+    D = torch.cuda.device_count()
+    D = 8 if D >= 8 else 4 if D >= 4 else 2 if D >= 2 else 1
+    sc = SynthCircuit(degree_bits, seed=500 + degree_bits, poseidon=poseidon, extra_gates=rec, recursion_gates=rec)
+    c = sc.common
+    cfg = prover.FriConfig(c.rate_bits, c.cap_height, 10, 4, 5, 12)
+    circ = plonk.Circuit(ctx, c, sc.sigmas)
+    pd = prover.ProverData(ctx, circ, sc.constants_sigmas(), cfg)
+    want = prover.prove(pd, sc.wires, sc.public_inputs)
+    m = qp.MultiContext(list(range(D)), max_lde_log=degree_bits + c.rate_bits)
+    try:
+        mpd = prover.MultiProverData(m, c, sc.sigmas, sc.constants_sigmas(), cfg)
+        assert (mpd.circuit_digest == pd.circuit_digest).all()
+        timing = {}
+        got = prover.mprove(mpd, sc.wires, sc.public_inputs, timing)
+        assert len(got) == len(want)
+        assert got == want
+        cap = pd.constants_sigmas_commitment.merkle_tree.cap
+        assert verifier.verify(got, c, pd.fri, cap, pd.circuit_digest) is None
+        assert set(timing) >= {"compute wires commitment", "compute quotient polys"}
+        mpd.constants_sigmas_commitment.free()
+        for x in mpd.circuits:
+            x.free()
+    finally:
+        m.close()
