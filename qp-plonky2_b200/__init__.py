@@ -30,7 +30,7 @@ LIB_PATH = os.environ.get("QP_PLONKY2_LIB") or os.path.join(_HERE, "libqp_plonky
 _SOURCES = [
     os.path.join(_HERE, "csrc", f)
     for f in ("qp_plonky2.cu", "goldilocks.cuh", "poseidon.cuh", "poseidon_constants.h", "ntt.cuh",
-              "merkle.cuh", "fri.cuh", "openings.cuh", "quotient.cuh")
+              "merkle.cuh", "fri.cuh", "openings.cuh", "quotient.cuh", "multi_device.inl")
 ] + [
     os.path.join(_HERE, "host", "transcript.cpp"),
     os.path.join(_HERE, "host", "plonk_host.cpp"),

@@ -5,9 +5,10 @@
 //
 // Decomposition (same as qp-plonky2_b200/dist.py, which is the one-process-per-GPU form):
 //   * columns are sharded across the devices for the upload and the inverse transform;
-//   * a piece of <= 8 coefficient columns goes from its owner to every other device as a PEER COPY
-//     (cudaMemcpyPeerAsync over NVLink / NVSwitch, copy engines: no SM is taken from the hashing, no
-//     NCCL) as soon as its inverse transform is done, pieces in global column order;
+//   * a piece of <= 8 coefficient columns is PULLED from its owner by every other device as a peer copy
+//     (cudaMemcpyPeerAsync over NVLink / NVSwitch on the pulling device's transfer stream, copy engines:
+//     no SM is taken from the hashing, no NCCL) once its inverse transform is done, pieces in global
+//     column order, a few ahead of the compute stream;
 //   * device e extends every piece to ITS cosets (leaf blocks [e 2^r / D, (e + 1) 2^r / D) = whole cap
 //     subtrees) and advances its leaf sponges over the column prefix while later pieces are in flight;
 //   * the cap is the concatenation of the shards' caps (no data-path collective besides the peer copies).
@@ -17,11 +18,25 @@
 // which then publishes `issued[k]`; consumers wait for the flag before they make their stream wait on the
 // event (an event that has not been recorded yet would not block anything).
 
+// A piece travels as a COPY KERNEL on the pulling device: 16-byte loads straight out of the owner's memory over
+// NVLink (peer access), grid-stride, a few dozen blocks -- measured here, cudaMemcpyPeerAsync blocked the issuing
+// host thread for milliseconds per call when several devices pulled at once, which serialised the whole pipeline;
+// a kernel launch does not.  (Without peer access the driver-staged cudaMemcpyPeerAsync remains the fallback.)
+__global__ void __launch_bounds__(256) peer_copy_kernel(const ulonglong2* __restrict__ src, ulonglong2* __restrict__ dst,
+                                                        size_t n16) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
 struct qp_mctx {
     std::vector<int> devices;
     std::vector<qp_ctx*> main_ctx;   // extend + hash
     std::vector<qp_ctx*> prod_ctx;   // upload + inverse transform
     std::vector<cudaStream_t> xfer;  // peer copies out of device d
+    // the producer's stream: HIGH priority -- an inverse transform launched while a leaf-hash kernel (thousands of
+    // blocks) is running must get SM slots as blocks retire, not after all of that kernel's blocks
+    std::vector<cudaStream_t> prod_stream;
+    std::vector<uint8_t> peer_ok;    // [D * D]: device a can load from device b's memory
     std::string err;
 };
 
@@ -38,6 +53,7 @@ extern "C" void qp_mctx_destroy(qp_mctx* m) {
         if (d < m->xfer.size() && m->xfer[d]) cudaStreamDestroy(m->xfer[d]);
         if (d < m->main_ctx.size()) qp_ctx_destroy(m->main_ctx[d]);
         if (d < m->prod_ctx.size()) qp_ctx_destroy(m->prod_ctx[d]);
+        if (d < m->prod_stream.size() && m->prod_stream[d]) cudaStreamDestroy(m->prod_stream[d]);
     }
     delete m;
 }
@@ -54,10 +70,17 @@ extern "C" int qp_mctx_create(const int* devices, unsigned n_devices, unsigned m
     m->main_ctx.assign(n_devices, nullptr);
     m->prod_ctx.assign(n_devices, nullptr);
     m->xfer.assign(n_devices, nullptr);
+    m->prod_stream.assign(n_devices, nullptr);
+    m->peer_ok.assign((size_t)n_devices * n_devices, 0);
     for (unsigned d = 0; d < n_devices; d++) {
         int rc = qp_ctx_create(devices[d], nullptr, max_lde_log, &m->main_ctx[d]);
-        if (!rc) rc = qp_ctx_create(devices[d], nullptr, max_lde_log, &m->prod_ctx[d]);
-        if (!rc && cudaStreamCreateWithFlags(&m->xfer[d], cudaStreamNonBlocking) != cudaSuccess) rc = QP_ERR_CUDA;
+        int lo_prio = 0, hi_prio = 0;
+        if (!rc && (cudaSetDevice(devices[d]) != cudaSuccess ||
+                    cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio) != cudaSuccess ||
+                    cudaStreamCreateWithPriority(&m->prod_stream[d], cudaStreamNonBlocking, hi_prio) != cudaSuccess ||
+                    cudaStreamCreateWithPriority(&m->xfer[d], cudaStreamNonBlocking, hi_prio) != cudaSuccess))
+            rc = QP_ERR_CUDA;
+        if (!rc) rc = qp_ctx_create(devices[d], m->prod_stream[d], max_lde_log, &m->prod_ctx[d]);
         if (rc) {
             qp_mctx_destroy(m);
             return rc;
@@ -67,9 +90,29 @@ extern "C" int qp_mctx_create(const int* devices, unsigned n_devices, unsigned m
         for (unsigned p = 0; p < n_devices; p++) {
             if (p == d) continue;
             int can = 0;
+            cudaSetDevice(devices[d]);
             if (cudaDeviceCanAccessPeer(&can, devices[d], devices[p]) == cudaSuccess && can) {
                 cudaError_t e = cudaDeviceEnablePeerAccess(devices[p], 0);
                 if (e != cudaSuccess) cudaGetLastError();  // already enabled is fine
+                bool ok = (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled);
+                // the coefficient matrices are stream-ordered allocations: the OWNER's pool must grant the access too
+                cudaMemPool_t pool;
+                if (ok && cudaDeviceGetDefaultMemPool(&pool, devices[p]) == cudaSuccess) {
+                    cudaMemAccessDesc desc = {};
+                    desc.location.type = cudaMemLocationTypeDevice;
+                    desc.location.id = devices[d];
+                    desc.flags = cudaMemAccessFlagsProtReadWrite;
+                    if (cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) {
+                        cudaGetLastError();
+                        ok = false;
+                    }
+                } else {
+                    ok = false;
+                }
+                m->peer_ok[(size_t)d * n_devices + p] = ok ? 1 : 0;
+                if (getenv("QP_TRACE")) fprintf(stderr, "[qp_mctx] peer access %d -> %d: %s\n", devices[d], devices[p], cudaGetErrorString(e));
+            } else if (getenv("QP_TRACE")) {
+                fprintf(stderr, "[qp_mctx] peer access %d -> %d: not available (copies are staged by the driver)\n", devices[d], devices[p]);
             }
         }
     }
@@ -204,15 +247,24 @@ static int mbatch_build(qp_mctx* m, const uint64_t* const* cols, const uint64_t*
     }
     // events: ev_ready[k] on the owner's producer stream (inverse transform done), ev_arrived[k * D + p] on
     // the owner's transfer stream (copy to device p done)
+    const auto t_setup = std::chrono::steady_clock::now();
     std::vector<cudaEvent_t> ev_ready(K, nullptr), ev_arrived(K * D, nullptr);
     for (size_t k = 0; k < K && !rc; k++) {
         cudaSetDevice(m->devices[pieces[k].owner]);
         if (cudaEventCreateWithFlags(&ev_ready[k], cudaEventDisableTiming) != cudaSuccess) rc = QP_ERR_CUDA;
-        for (unsigned p = 0; p < D && !rc; p++)
-            if (p != pieces[k].owner &&
-                cudaEventCreateWithFlags(&ev_arrived[k * D + p], cudaEventDisableTiming) != cudaSuccess)
-                rc = QP_ERR_CUDA;
+        for (unsigned p = 0; p < D && !rc; p++) {
+            if (p == pieces[k].owner) continue;
+            cudaSetDevice(m->devices[p]);   // recorded on the PULLING device's transfer stream
+            if (cudaEventCreateWithFlags(&ev_arrived[k * D + p], cudaEventDisableTiming) != cudaSuccess) rc = QP_ERR_CUDA;
+        }
     }
+    const bool trace = getenv("QP_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    if (trace)
+        fprintf(stderr, "[qp_mbatch] event creation took %.2f ms\n",
+                std::chrono::duration<double, std::milli>(t_begin - t_setup).count());
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    std::vector<double> t_prod_done(D, 0), t_cons_issued(D, 0), t_cons_done(D, 0), t_first_piece(D, 0);
     std::vector<std::atomic<int>> issued(K);
     for (auto& f : issued) f.store(0);
     std::atomic<int> abort_flag{0};
@@ -256,35 +308,62 @@ static int mbatch_build(qp_mctx* m, const uint64_t* const* cols, const uint64_t*
                 r = ifft_device(ctx, dv, c1 - c0, degree_log, own, dv);
             }
             if (r) return r;
+            const double t_a = since();
             CUDA_TRY(ctx, cudaEventRecord(ev_ready[k], ctx->stream));
-            for (unsigned p = 0; p < D; p++) {
-                if (p == d) continue;
-                CUDA_TRY(ctx, cudaStreamWaitEvent(m->xfer[d], ev_ready[k], 0));
-                CUDA_TRY(ctx, cudaMemcpyPeerAsync(mb->shards[p]->coeffs + c0 * n, m->devices[p], own, m->devices[d],
-                                                  (c1 - c0) * n * 8, m->xfer[d]));
-                CUDA_TRY(ctx, cudaEventRecord(ev_arrived[k * D + p], m->xfer[d]));
-            }
-            issued[k].store(1, std::memory_order_release);
+            issued[k].store(1, std::memory_order_release);   // the consumers PULL the piece (below)
+            if (trace && d == D - 1)
+                fprintf(stderr, "[qp_mbatch]     producer %u piece %zu: upload + inverse transform queued at %.2f ms\n", d, k, t_a);
         }
         // the staging buffer and the ring must outlive the copies that read them
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(m->xfer[d]));
+        t_prod_done[d] = since();
         return QP_OK;
     };
     auto consumer = [&](unsigned d) -> int {
         qp_ctx* ctx = m->main_ctx[d];
         qp_batch* b = mb->shards[d];
         if (cudaSetDevice(m->devices[d]) != cudaSuccess) return QP_ERR_CUDA;
-        for (size_t k = 0; k < K; k++) {
-            while (!issued[k].load(std::memory_order_acquire)) {
-                if (abort_flag.load()) return QP_OK;
-                std::this_thread::yield();
+        // pieces of other owners are PULLED by this device on its own transfer stream (peer copy out of the
+        // owner's matrix once its inverse transform is done), a few pieces ahead of the compute stream
+        const size_t LOOKAHEAD = 4;
+        size_t pulled = 0;
+        auto pull_up_to = [&](size_t upto) -> int {
+            for (; pulled < upto && pulled < K; pulled++) {
+                const size_t k = pulled;
+                while (!issued[k].load(std::memory_order_acquire)) {
+                    if (abort_flag.load()) return QP_OK;
+                    std::this_thread::yield();
+                }
+                const unsigned o = pieces[k].owner;
+                if (o == d) continue;
+                const size_t c0 = pieces[k].c0, c1 = pieces[k].c1;
+                CUDA_TRY(ctx, cudaStreamWaitEvent(m->xfer[d], ev_ready[k], 0));
+                if (m->peer_ok[(size_t)d * D + o]) {
+                    const size_t n16 = (c1 - c0) * n / 2;
+                    peer_copy_kernel<<<64, 256, 0, m->xfer[d]>>>(
+                        reinterpret_cast<const ulonglong2*>(mb->shards[o]->coeffs + c0 * n),
+                        reinterpret_cast<ulonglong2*>(b->coeffs + c0 * n), n16);
+                    ctx->launches++;
+                    CUDA_TRY(ctx, cudaGetLastError());
+                } else {
+                    CUDA_TRY(ctx, cudaMemcpyPeerAsync(b->coeffs + c0 * n, m->devices[d], mb->shards[o]->coeffs + c0 * n,
+                                                      m->devices[o], (c1 - c0) * n * 8, m->xfer[d]));
+                }
+                CUDA_TRY(ctx, cudaEventRecord(ev_arrived[k * D + d], m->xfer[d]));
             }
+            return QP_OK;
+        };
+        for (size_t k = 0; k < K; k++) {
+            int r = pull_up_to(k + 1 + LOOKAHEAD);
+            if (r) return r;
+            if (abort_flag.load()) return QP_OK;
             cudaEvent_t e = pieces[k].owner == d ? ev_ready[k] : ev_arrived[k * D + d];
+            if (k == 0) t_first_piece[d] = since();
             CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, e, 0));
-            int r = batch_extend(b, pieces[k].c0, pieces[k].c1 - pieces[k].c0, true);
+            r = batch_extend(b, pieces[k].c0, pieces[k].c1 - pieces[k].c0, true);
             if (r) return r;
         }
+        t_cons_issued[d] = since();
         TempScope tmp(ctx);
         const uint64_t* d_salt = nullptr;
         if (blinding) {
@@ -294,6 +373,7 @@ static int mbatch_build(qp_mctx* m, const uint64_t* const* cols, const uint64_t*
             if (r) return r;
         }
         int r = batch_finish(b, d_salt, b->chunks_done, b->sponge_state);
+        t_cons_done[d] = since();
         dev_free(ctx, b->sponge_state);
         b->sponge_state = nullptr;
         return r;
@@ -327,6 +407,14 @@ static int mbatch_build(qp_mctx* m, const uint64_t* const* cols, const uint64_t*
         cudaStreamSynchronize(m->xfer[d]);
         cudaStreamSynchronize(m->prod_ctx[d]->stream);
         cudaStreamSynchronize(m->main_ctx[d]->stream);
+    }
+    if (trace) {
+        fprintf(stderr, "[qp_mbatch] %zu cols, %u devices, %zu pieces: setup done at t=0, all done at %.2f ms\n", n_cols, D, K, since());
+        for (unsigned d = 0; d < D; d++)
+            fprintf(stderr, "[qp_mbatch]   device %u: producer drained %.2f ms | consumer: first piece seen %.2f, all issued %.2f, "
+                            "finished %.2f ms (LDE+sponge phase %.2f ms, final hash + tree %.2f ms on the device)\n",
+                    d, t_prod_done[d], t_first_piece[d], t_cons_issued[d], t_cons_done[d], mb->shards[d] ? mb->shards[d]->ms[1] : 0.f,
+                    mb->shards[d] ? mb->shards[d]->ms[3] : 0.f);
     }
     for (cudaEvent_t e : ev_ready)
         if (e) cudaEventDestroy(e);
