@@ -236,6 +236,9 @@ int qp_batch_fri_coeffs(const qp_batch_fri* o, size_t g, uint64_t* out, int spac
 int qp_batch_fri_cap(const qp_batch_fri* o, uint64_t* out, int space);                /* [2^cap_height][4] */
 size_t qp_batch_fri_digests_len(const qp_batch_fri* o);
 int qp_batch_fri_digests(const qp_batch_fri* o, uint64_t* out, int space);
+/* group g as a PolynomialBatch view (its coefficients for qp_opening_term / qp_batch_eval_polys, its LDE rows);
+ * owned by the oracle, valid until qp_batch_fri_free */
+const qp_batch* qp_batch_fri_group_batch(const qp_batch_fri* o, size_t g);
 /* batch_merkle_tree.open_batch(leaf_index): log2(N_0) - cap_height siblings */
 int qp_batch_fri_open(const qp_batch_fri* o, size_t leaf_index, uint64_t* siblings_out);
 /* batch_merkle_tree.values(leaf_index): every group's row, concatenated (host) */
@@ -281,6 +284,14 @@ int qp_fri_begin(qp_ctx* ctx, const uint64_t* coeffs_ext, const uint64_t* values
                  unsigned lg_n, unsigned rate_bits, unsigned cap_height, qp_fri** out);
 int qp_fri_commit_round(qp_fri* f, unsigned arity_bits, uint64_t* cap_out /* [2^cap_height][4] host */);
 int qp_fri_fold_round(qp_fri* f, const uint64_t beta[2], int is_last);
+/* Batch FRI (plonky2/src/batch_fri/prover.rs:122-141): after a fold round that is not the last, when the next
+ * polynomial of the batch has exactly the current length:
+ *     final_values = final_values * beta + values[polynomial_index];  final_coeffs = final_values.coset_ifft(shift)
+ * `lower` = the FRI state of that polynomial (qp_fri_begin / qp_fri_begin_from_openings), no round committed.
+ * Errors: QP_ERR_DEGREE_MISMATCH (lengths differ), QP_ERR_BAD_ARG (called out of order). */
+int qp_fri_mix_values(qp_fri* f, const qp_fri* lower, const uint64_t beta[2]);
+/* log2 of the current codeword length (lde_bits minus the arities folded so far) */
+unsigned qp_fri_domain_bits(const qp_fri* f);
 /* Final polynomial: coeffs truncated to len >> rate_bits (prover.rs:138-141); returns its
  * length in *len_out (ext elements) and writes [len][2] to out (host). */
 int qp_fri_final_poly(qp_fri* f, uint64_t* out, size_t* len_out);

@@ -76,6 +76,24 @@ int qp_fri_proof_sharded(qp_ctx* ctx, const qp_batch* const* oracle_shards, size
                          const unsigned* arity_bits, unsigned n_rounds, unsigned proof_of_work_bits,
                          unsigned num_query_rounds, uint8_t* out, size_t capacity, size_t* len_out);
 
+/* ---- batch FRI (plonky2/src/batch_fri/prover.rs:25-230): one FRI proof over polynomials of several degrees ----
+ * `f` is the FRI state of the largest final polynomial, lower[k] those of the smaller ones in strictly decreasing
+ * length (each built by qp_fri_begin on (lde_final_poly, lde_final_values), or by qp_fri_begin_from_openings on the
+ * opening batches of that degree with the groups of the BatchFriOracles as polynomial sources,
+ * qp_batch_fri_group_batch -- that is BatchFriOracle::prove_openings, batch_fri/oracle.rs:163-229).
+ * qp_batch_fri_run_commit_phase = batch_fri_committed_trees; qp_batch_fri_proof = batch_fri_proof followed by
+ * write_fri_proof (the byte layout of qp_fri_proof; an oracle's initial opening is values(x) of all its matrices
+ * and open_batch(x)).  Errors: QP_ERR_DEGREE_MISMATCH where the reference asserts (lengths not strictly
+ * decreasing, reduction_arity_bits not covering every polynomial, oracle height != the FRI domain). */
+int qp_batch_fri_run_commit_phase(qp_fri* f, qp_fri* const* lower, size_t n_lower, unsigned cap_height,
+                                  const unsigned* arity_bits, unsigned n_rounds, qp_challenger* challenger,
+                                  uint64_t* caps_out, uint64_t* final_poly_out, size_t* final_len_out);
+int qp_batch_fri_proof(qp_ctx* ctx, const qp_batch_fri* const* initial_oracles, size_t n_oracles, qp_fri* f,
+                       qp_fri* const* lower, size_t n_lower, qp_challenger* challenger, unsigned rate_bits,
+                       unsigned cap_height, const unsigned* arity_bits, unsigned n_rounds,
+                       unsigned proof_of_work_bits, unsigned num_query_rounds, uint8_t* out, size_t capacity,
+                       size_t* len_out);
+
 /* ---- circuit data for the quotient (plonky2/src/plonk/circuit_data.rs:412-470) ---------------- */
 /* The gates of a circuit, compiled on the host into the constraint program of qp_circuit_desc
  * (qp_plonky2_b200.h): gates are sorted by (degree, id) like CircuitBuilder::build does

@@ -368,3 +368,155 @@ def reduce_openings(batches, n):
             q[i - 1] = acc
         final = [ext_add(ext_mul(final[k], b["shift"]), q[k]) for k in range(n)]
     return final
+
+
+# ----- batch FRI (plonky2/src/batch_fri/prover.rs, batch_fri/oracle.rs:163-229) ---------------
+def coset_ifft(values, shift):
+    """field/src/polynomial/mod.rs:58-88: ifft, then coefficient i times shift^-i."""
+    co = ifft(values)
+    s_inv = inv(shift)
+    return [c * pow(s_inv, i, P) % P for i, c in enumerate(co)]
+
+
+def fri_proof_of_work(challenger, pow_bits):
+    """plonky2/src/fri/prover.rs:159-208 with the serial smallest-witness rule."""
+    st = list(challenger.state)
+    st[: len(challenger.inp)] = challenger.inp
+    pos = len(challenger.inp)
+    w = 0
+    while True:
+        t = list(st)
+        t[pos] = w
+        resp = poseidon(t)[7]                       # squeeze().last()
+        if resp < (1 << (64 - pow_bits)):           # leading_zeros >= pow_bits
+            break
+        w += 1
+    challenger.observe([w])
+    challenger.get_challenge()
+    return w
+
+
+def batch_fri_committed_trees(coeffs, values_list, rate_bits, cap_height, arity_bits, challenger):
+    """batch_fri_committed_trees (batch_fri/prover.rs:83-150).  coeffs: the LDE coefficients of the largest
+    final polynomial; values_list[k]: the LDE values (natural order) of final polynomial k, lengths strictly
+    decreasing.  -> (caps, betas, final_poly, trees)"""
+    final_coeffs = [tuple(c) for c in coeffs]
+    final_values = [tuple(v) for v in values_list[0]]
+    assert all(len(a) > len(b) for a, b in zip(values_list, values_list[1:]))
+    shift = GENERATOR
+    polynomial_index = 1
+    caps, betas, trees = [], [], []
+    for step, ab in enumerate(arity_bits):
+        arity = 1 << ab
+        final_values = reverse_index_bits(final_values)
+        leaves = [[x for e in final_values[i : i + arity] for x in e] for i in range(0, len(final_values), arity)]
+        digests, cap = merkle_tree(leaves, cap_height)
+        trees.append((leaves, digests))
+        caps.append(cap)
+        challenger.observe([x for d in cap for x in d])
+        beta = challenger.get_extension_challenge()
+        betas.append(beta)
+        folded = []
+        for i in range(0, len(final_coeffs), arity):
+            acc = (0, 0)
+            for c in reversed(final_coeffs[i : i + arity]):
+                acc = ext_add(ext_mul(acc, beta), c)
+            folded.append(acc)
+        final_coeffs = folded
+        if step + 1 == len(arity_bits):
+            continue
+        shift = pow(shift, arity, P)
+        final_values = list(zip(coset_fft([c[0] for c in final_coeffs], shift),
+                                coset_fft([c[1] for c in final_coeffs], shift)))
+        if polynomial_index != len(values_list) and len(final_values) == len(values_list[polynomial_index]):
+            final_values = [ext_add(ext_mul(f, beta), tuple(v))
+                            for f, v in zip(final_values, values_list[polynomial_index])]
+            polynomial_index += 1
+        final_coeffs = list(zip(coset_ifft([v[0] for v in final_values], shift),
+                                coset_ifft([v[1] for v in final_values], shift)))
+    assert polynomial_index == len(values_list)
+    final = final_coeffs[: len(final_coeffs) >> rate_bits]
+    challenger.observe([x for c in final for x in c])
+    return caps, betas, final, trees
+
+
+def _u64s(xs):
+    return b"".join(int(x).to_bytes(8, "little") for x in xs)
+
+
+def batch_fri_proof_bytes(oracles, coeffs, values_list, challenger, rate_bits, cap_height, arity_bits, pow_bits,
+                          num_query_rounds):
+    """batch_fri_proof (batch_fri/prover.rs:25-80) + write_fri_proof (serialization/mod.rs:1654-1667).
+    oracles: list of (leaf matrices, digests) as batch_fri_from_coeffs returns them."""
+    n = len(coeffs)
+    caps, betas, final, trees = batch_fri_committed_trees(coeffs, values_list, rate_bits, cap_height, arity_bits,
+                                                          challenger)
+    w = fri_proof_of_work(challenger, pow_bits)
+    xs = [challenger.get_challenge() % n for _ in range(num_query_rounds)]
+    out = bytearray()
+    for cap in caps:
+        out += _u64s(x for d in cap for x in d)
+    lg0 = n.bit_length() - 1
+    for x in xs:
+        for mats, digests in oracles:
+            # BatchMerkleTree::values(x) flattened, then open_batch(x) (prover.rs:189-203)
+            row = []
+            for m in mats:
+                row += list(m[x >> (lg0 - (len(m).bit_length() - 1))])
+            sib = batch_merkle_open(x, mats, cap_height, digests)
+            out += _u64s(row) + bytes([len(sib)]) + _u64s(v for d in sib for v in d)
+        idx, m = x, n
+        for k, a in enumerate(arity_bits):
+            idx >>= a
+            m >>= a
+            leaves, digests = trees[k]
+            sib = merkle_prove(idx, m, cap_height, digests)
+            out += _u64s(leaves[idx]) + bytes([len(sib)]) + _u64s(v for d in sib for v in d)
+    out += _u64s(x for c in final for x in c)
+    out += int(w).to_bytes(8, "little")
+    return bytes(out)
+
+
+def ext_pow(a, e):
+    r = (1, 0)
+    while e:
+        if e & 1:
+            r = ext_mul(r, a)
+        a = ext_mul(a, a)
+        e >>= 1
+    return r
+
+
+def fri_coefficient(coeff, point):
+    """FriCoefficient (core/src/fri_structure.rs:100-108) at the batch point."""
+    if coeff == "one" or coeff == ("one",):
+        return (1, 0)
+    if coeff[0] == "point_power":
+        return ext_pow(tuple(point), coeff[1])
+    return (coeff[1][0] % P, coeff[1][1] % P)
+
+
+def batch_prove_openings_bytes(degree_bits, instances, oracle_polys, oracles, challenger, rate_bits, cap_height,
+                               arity_bits, pow_bits, num_query_rounds):
+    """BatchFriOracle::prove_openings (batch_fri/oracle.rs:163-229).  oracle_polys[o]: the coefficient vectors
+    of oracle o (tallest first); oracles[o] = (leaf matrices, digests); instances as in the reference:
+    instances[i]["batches"][b] = dict(point, openings=[[(oracle_index, polynomial_index, coefficient), ...], ...])."""
+    alpha = challenger.get_extension_challenge()
+    final_coeffs, final_values = [], []
+    for d, inst in zip(degree_bits, instances):
+        n = 1 << d
+        batches = []
+        for b in inst["batches"]:
+            terms, apow = [], (1, 0)
+            for expr in b["openings"]:
+                for oi, pi, coeff in expr:
+                    assert len(oracle_polys[oi][pi]) == n
+                    terms.append((oracle_polys[oi][pi], ext_mul(apow, fri_coefficient(coeff, b["point"]))))
+                apow = ext_mul(apow, alpha)
+            batches.append(dict(point=tuple(b["point"]), shift=apow, terms=terms))
+        fin = reduce_openings(batches, n)
+        lde = fin + [(0, 0)] * (n * ((1 << rate_bits) - 1))
+        final_coeffs.append(lde)
+        final_values.append(list(zip(coset_fft([c[0] for c in lde], GENERATOR), coset_fft([c[1] for c in lde], GENERATOR))))
+    return batch_fri_proof_bytes(oracles, final_coeffs[0], final_values, challenger, rate_bits, cap_height, arity_bits,
+                                 pow_bits, num_query_rounds)

@@ -216,6 +216,13 @@ def lib():
         "qp_batch_fri_digests": (i32, [vp, vp, i32]),
         "qp_batch_fri_open": (i32, [vp, sz, vp]),
         "qp_batch_fri_values": (i32, [vp, sz, vp]),
+        "qp_batch_fri_group_batch": (vp, [vp, sz]),
+        "qp_fri_mix_values": (i32, [vp, vp, vp]),
+        "qp_fri_domain_bits": (u32, [vp]),
+        "qp_batch_fri_run_commit_phase": (i32, [vp, pp, sz, u32, C.POINTER(u32), u32, C.POINTER(_ChallengerState), vp, vp,
+                                                C.POINTER(sz)]),
+        "qp_batch_fri_proof": (i32, [vp, pp, sz, vp, pp, sz, C.POINTER(_ChallengerState), u32, u32, C.POINTER(u32), u32,
+                                     u32, u32, vp, sz, C.POINTER(sz)]),
         "qp_batch_merkle_tree_new": (i32, [vp, vp, i32, vp, vp, sz, u32, pp]),
         "qp_batch_tree_free": (None, [vp]),
         "qp_batch_tree_cap": (i32, [vp, vp, i32]),
@@ -225,6 +232,12 @@ def lib():
         "qp_batch_tree_values": (i32, [vp, sz, vp]),
         "qp_dev_free": (None, [vp, vp]),
         "qp_memcpy": (i32, [vp, vp, i32, vp, i32, sz]),
+        "qp_memcpy_peer": (i32, [vp, vp, vp, vp, sz]),
+        "qp_mbatch_from_device": (i32, [vp, vp, i32, sz, u32, u32, i32, u32, vp, pp]),
+        "qp_circuit_quotient_values_shard": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(sz), C.POINTER(sz)]),
+        "qp_circuit_quotient_finish": (i32, [vp, vp, vp, i32]),
+        "qp_fri_proof_sharded": (i32, [vp, pp, sz, u32, vp, C.POINTER(_ChallengerState), u32, u32, C.POINTER(u32), u32,
+                                       u32, u32, vp, sz, C.POINTER(sz)]),
         # host side of the quotient / prove (include/qp_plonky2_host.h)
         "qp_program_create": (i32, [vp, sz, u32, pp]),
         "qp_program_from_dag": (i32, [vp, sz, vp, sz, vp, sz, pp]),
@@ -933,6 +946,54 @@ class BatchFriOracle:
         self.ctx.check(lib().qp_batch_fri_values(self._h, leaf_index, _np_ptr(out)))
         return np.split(out, np.cumsum(self.group_sizes)[:-1])
 
+    @property
+    def leaf_len(self):
+        return sum(self.group_sizes)
+
+    def locate(self, polynomial_index):
+        """(group, column) of `polynomials[polynomial_index]` (the polynomials are sorted tallest first)."""
+        for g, k in enumerate(self.group_sizes):
+            if polynomial_index < k:
+                return g, polynomial_index
+            polynomial_index -= k
+        raise IndexError("polynomial index out of range")
+
+    def group_batch(self, g):
+        """Group g as a PolynomialBatch handle (what an opening term refers to); owned by this oracle."""
+        return _BorrowedBatch(lib().qp_batch_fri_group_batch(self._h, g))
+
+    @staticmethod
+    def prove_openings(ctx, degree_bits, instances, oracles, challenger, rate_bits, cap_height, arity_bits,
+                       proof_of_work_bits, num_query_rounds) -> bytes:
+        """BatchFriOracle::prove_openings (plonky2/src/batch_fri/oracle.rs:163-229) -> the FriProof bytes.
+        instances[i] (one per entry of degree_bits, tallest first): dict(batches=[dict(point=(a, b),
+        openings=[expression, ...])]); an expression is a list of terms (oracle_index, polynomial_index,
+        coefficient) with coefficient "one" | ("point_power", k) | ("constant", (c0, c1))
+        (core/src/fri_structure.rs:59-108)."""
+        if len(degree_bits) != len(instances):
+            raise QpError(5, "degree_bits and instances differ in length")
+        alpha = challenger.get_extension_challenge()
+        fris = []
+        try:
+            for d, inst in zip(degree_bits, instances):
+                flat = []
+                for b in inst["batches"]:
+                    terms, apow = [], (1, 0)
+                    for expr in b["openings"]:                     # reduce_polys: sum_i alpha^i expr_i
+                        for oi, pi, coeff in expr:
+                            g, col = oracles[oi].locate(pi)
+                            if oracles[oi].degree_bits[g] != d:
+                                raise QpError(6, "opening term of another degree")
+                            terms.append((oracles[oi].group_batch(g), col, _ext_mul(apow, _coefficient(coeff, b["point"]))))
+                        apow = _ext_mul(apow, alpha)
+                    flat.append(dict(point=b["point"], shift=apow, terms=terms))   # shift_poly: alpha^len(openings)
+                fris.append(fri_from_openings(ctx, flat, d, rate_bits, cap_height))
+            return batch_fri_proof(ctx, oracles, fris, challenger, rate_bits, cap_height, arity_bits, proof_of_work_bits,
+                                   num_query_rounds)
+        finally:
+            for f in fris:
+                f.free()
+
     def free(self):
         if self._h and self.ctx._h:
             lib().qp_batch_fri_free(self._h)
@@ -943,6 +1004,37 @@ class BatchFriOracle:
             self.free()
         except Exception:
             pass
+
+
+class _BorrowedBatch:
+    """A qp_batch handle owned by something else (a group of a BatchFriOracle)."""
+
+    def __init__(self, h):
+        self._h = C.c_void_p(h)
+
+
+_GL_P = 0xFFFFFFFF00000001
+
+
+def _ext_mul(a, b):      # F_p^2 = F_p[X] / (X^2 - 7)
+    return ((a[0] * b[0] + 7 * a[1] * b[1]) % _GL_P, (a[0] * b[1] + a[1] * b[0]) % _GL_P)
+
+
+def _coefficient(coeff, point):
+    """FriCoefficient (core/src/fri_structure.rs:100-108) evaluated at the batch point."""
+    if coeff == "one" or coeff == ("one",):
+        return (1, 0)
+    if coeff[0] == "point_power":
+        r, base, e = (1, 0), (int(point[0]) % _GL_P, int(point[1]) % _GL_P), int(coeff[1])
+        while e:
+            if e & 1:
+                r = _ext_mul(r, base)
+            base = _ext_mul(base, base)
+            e >>= 1
+        return r
+    if coeff[0] == "constant":
+        return (int(coeff[1][0]) % _GL_P, int(coeff[1][1]) % _GL_P)
+    raise ValueError("unknown coefficient %r" % (coeff,))
 
 
 class Challenger:
@@ -1102,6 +1194,40 @@ def fri_proof(ctx, oracles, fri, challenger, rate_bits, arity_bits, proof_of_wor
                                  ab, R, proof_of_work_bits, num_query_rounds, buf, need, C.byref(got)))
     assert got.value == need, (got.value, need)
     return bytes(buf)
+
+
+def batch_fri_proof(ctx, oracles, fris, challenger, rate_bits, cap_height, arity_bits, proof_of_work_bits,
+                    num_query_rounds) -> bytes:
+    """batch_fri_proof (plonky2/src/batch_fri/prover.rs:25-80) serialised like write_fri_proof.  oracles:
+    BatchFriOracle objects (the initial BatchMerkleTrees); fris[0]: the FRI state of the largest final polynomial,
+    fris[1:]: those of the smaller ones, strictly decreasing (fri_from_openings / fri_begin)."""
+    R = len(arity_bits)
+    ab = (C.c_uint * max(R, 1))(*arity_bits)
+    lens = (C.c_size_t * max(len(oracles), 1))(*[o.leaf_len for o in oracles])
+    need = lib().qp_fri_proof_len(lens, len(oracles), fris[0].lg_n, rate_bits, cap_height, ab, R, num_query_rounds)
+    buf = (C.c_uint8 * need)()
+    hs = (C.c_void_p * max(len(oracles), 1))(*[o._h for o in oracles])
+    lower = (C.c_void_p * max(len(fris) - 1, 1))(*[f._h for f in fris[1:]])
+    got = C.c_size_t()
+    ctx.check(lib().qp_batch_fri_proof(ctx._h, hs, len(oracles), fris[0]._h, lower, len(fris) - 1, C.byref(challenger._s),
+                                       rate_bits, cap_height, ab, R, proof_of_work_bits, num_query_rounds, buf, need,
+                                       C.byref(got)))
+    assert got.value == need, (got.value, need)
+    return bytes(buf)
+
+
+def fri_begin(ctx, coeffs, values, rate_bits, cap_height):
+    """A device FRI state from (lde_polynomial_coeffs, lde_polynomial_values), F_p^2 arrays [n][2] in natural
+    order -- fri_proof's / batch_fri_proof's two polynomial arguments."""
+    co = np.ascontiguousarray(np.asarray(coeffs, dtype=np.uint64))
+    va = np.ascontiguousarray(np.asarray(values, dtype=np.uint64))
+    n = co.shape[0]
+    lg = int(n).bit_length() - 1
+    if n == 0 or (1 << lg) != n or co.shape != va.shape:
+        raise QpError(3, "Not a power of two / shapes differ")
+    h = C.c_void_p()
+    ctx.check(lib().qp_fri_begin(ctx._h, _np_ptr(co), _np_ptr(va), QP_HOST, lg, rate_bits, cap_height, C.byref(h)))
+    return FriCommitment(ctx, h, None, None, [], lg, cap_height)
 
 
 def fri_initial_coeffs(fri, degree_log):

@@ -73,6 +73,18 @@ __global__ void fold_kernel(const uint64_t* __restrict__ in, size_t n_in, unsign
     out[n_out + i] = gl::canon(acc.c1);
 }
 
+// Batch FRI: when the folded codeword has reached the length of the next (smaller) polynomial, it absorbs
+// that polynomial's values, v <- v * beta + w (plonky2/src/batch_fri/prover.rs:126-137).  Both operands are
+// planes in bit-reversed order over domains of the same size, so the update is elementwise.
+__global__ void mix_kernel(uint64_t* __restrict__ v, const uint64_t* __restrict__ w, size_t n, uint64_t beta0,
+                           uint64_t beta1) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Ext r = ext_mul(Ext{v[i], v[n + i]}, Ext{beta0, beta1});
+    v[i] = gl::canon(gl::add(r.c0, w[i]));
+    v[n + i] = gl::canon(gl::add(r.c1, w[n + i]));
+}
+
 // Proof-of-work search (plonky2/src/fri/prover.rs:185-200).  Candidate w = base + global thread
 // id; `found` holds the smallest successful candidate so far (init UINT64_MAX).  A launch covers
 // far more candidates than the expected 2^min_lz, and a block whose candidates are all larger than

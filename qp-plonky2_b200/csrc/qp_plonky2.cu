@@ -1684,23 +1684,29 @@ extern "C" int qp_poseidon_permute(qp_ctx* ctx, uint64_t* states, int space, siz
 }
 
 // coset FFT of device-resident vectors; output bit-reversed in `dst` (device).
+// Tables of shift^i, i < 2^lg_n, cached per (size, shift): a FRI fold round then costs no allocation and no
+// host round trip (the shifts of a proof are g^(arity^round): a handful of values per size).  shift = 1: none.
+static int shift_tables(qp_ctx* ctx, unsigned lg_n, uint64_t shift, const ScaleTables** out) {
+    *out = nullptr;
+    if (gl::canon(shift) == 1) return QP_OK;
+    std::vector<uint64_t> key = {(uint64_t)lg_n, gl::canon(shift), ~0ULL, ~0ULL};
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    auto it = ctx->scale_cache.find(key);
+    if (it == ctx->scale_cache.end()) {
+        ScaleTables t;
+        int rc = build_scale(ctx, (int)lg_n, std::vector<uint64_t>{shift}, &t);
+        if (rc) return rc;
+        it = ctx->scale_cache.emplace(key, t).first;
+    }
+    *out = &it->second;
+    return QP_OK;
+}
+
 static int coset_fft_device(qp_ctx* ctx, const uint64_t* d_src, uint64_t* d_dst, size_t n_vec, unsigned lg_n,
                             uint64_t shift) {
-    // shift tables are cached per (size, shift): a FRI fold round then costs no allocation and no
-    // host round trip (the shifts of a proof are g^(arity^round): a handful of values per size)
     const ScaleTables* st = nullptr;
-    if (gl::canon(shift) != 1) {
-        std::vector<uint64_t> key = {(uint64_t)lg_n, gl::canon(shift), ~0ULL, ~0ULL};
-        std::lock_guard<std::mutex> lock(ctx->mu);
-        auto it = ctx->scale_cache.find(key);
-        if (it == ctx->scale_cache.end()) {
-            ScaleTables t;
-            int rc = build_scale(ctx, (int)lg_n, std::vector<uint64_t>{shift}, &t);
-            if (rc) return rc;
-            it = ctx->scale_cache.emplace(key, t).first;
-        }
-        st = &it->second;
-    }
+    int rc_st = shift_tables(ctx, lg_n, shift, &st);
+    if (rc_st) return rc_st;
     NttJob job;
     job.src = d_src;
     job.dst = d_dst;
@@ -2033,6 +2039,53 @@ extern "C" int qp_fri_fold_round(qp_fri* f, const uint64_t beta[2], int is_last)
     return coset_fft_device(ctx, f->coeffs, f->values, 2, f->cur_lg, f->shift);
 }
 
+// Batch FRI (plonky2/src/batch_fri/prover.rs:122-141): after a fold round that is not the last, if the next
+// polynomial of the batch has exactly the current length,
+//     final_values = final_values * beta + values[polynomial_index];  final_coeffs = final_values.coset_ifft(shift)
+// `lower` is the FRI state of that polynomial (qp_fri_begin / qp_fri_begin_from_openings), untouched so far: its
+// `values` are the LDE values on a domain of the same size, in the same bit-reversed order as ours.
+extern "C" int qp_fri_mix_values(qp_fri* f, const qp_fri* lower, const uint64_t beta[2]) {
+    if (!f) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = f->ctx;
+    if (!lower || !beta) return fail(ctx, QP_ERR_BAD_ARG, "null argument");
+    if (lower->ctx != ctx) return fail(ctx, QP_ERR_BAD_ARG, "FRI state belongs to another context");
+    if (f->committed || !f->values) return fail(ctx, QP_ERR_BAD_ARG, "mix_values called out of order");
+    if (!lower->values || !lower->rounds.empty() || lower->cur_lg != f->cur_lg)
+        return fail(ctx, QP_ERR_DEGREE_MISMATCH, "the polynomial to absorb must have the current length and no rounds");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const unsigned lg = f->cur_lg;
+    const size_t n = (size_t)1 << lg;
+    LAUNCH(ctx, fri::mix_kernel, cdiv(n, 256), 256, 0, f->values, lower->values, n, beta[0] % gl::P, beta[1] % gl::P);
+    // coset_ifft (polynomial/mod.rs:58-88): natural-order values -> inverse transform -> coefficient i times shift^-i
+    TempScope tmp(ctx);
+    uint64_t* nat = nullptr;
+    int rc = tmp.alloc(&nat, 2 * n);
+    if (rc) return rc;
+    LAUNCH(ctx, bitrev_permute_kernel, cdiv(2 * n, 256), 256, 0, f->values, nat, lg, (size_t)2);
+    NttJob job;
+    job.src = nat;
+    job.dst = f->coeffs;
+    job.L = (int)lg;
+    job.n_vec = 2;
+    job.inner_bits = 0;
+    job.src_outer = n;
+    job.dst_outer = n;
+    job.out_mode = ntt::OUT_INVERSE;
+    job.scratch = nat;
+    rc = run_ntt(ctx, job);
+    if (rc) return rc;
+    const ScaleTables* st = nullptr;
+    rc = shift_tables(ctx, lg, gl::host_pow(f->shift, gl::P - 2), &st);
+    if (rc) return rc;
+    if (st)
+        LAUNCH(ctx, quotient::scale_powers_kernel, cdiv(2 * n, 256), 256, 0, f->coeffs, (size_t)2, lg, st->lo, st->hi,
+               st->split);
+    return QP_OK;
+}
+
+/* log2 of the current codeword length (after the folds done so far) */
+extern "C" unsigned qp_fri_domain_bits(const qp_fri* f) { return f ? f->cur_lg : 0; }
+
 extern "C" int qp_fri_final_poly(qp_fri* f, uint64_t* out, size_t* len_out) {
     if (!f) return QP_ERR_BAD_ARG;
     qp_ctx* ctx = f->ctx;
@@ -2314,6 +2367,11 @@ struct qp_batch_fri {
     std::vector<qp_batch*> groups;  // coefficients, LDE and the stage tree of every group
     unsigned rate_bits = 0, cap_height = 0;
 };
+
+/* group g as a PolynomialBatch view (coefficients, LDE rows); owned by the oracle */
+extern "C" const qp_batch* qp_batch_fri_group_batch(const qp_batch_fri* o, size_t g) {
+    return (o && g < o->groups.size()) ? o->groups[g] : nullptr;
+}
 
 extern "C" void qp_batch_fri_free(qp_batch_fri* o) {
     if (!o) return;

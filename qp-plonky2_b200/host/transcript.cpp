@@ -334,6 +334,135 @@ extern "C" int qp_fri_proof_sharded(qp_ctx* ctx, const qp_batch* const* oracles,
     return (out && w.len > capacity) ? QP_ERR_BAD_ARG : QP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// batch FRI (plonky2/src/batch_fri/prover.rs): one FRI proof over polynomials of several degrees
+// ---------------------------------------------------------------------------------------------
+// batch_fri_committed_trees (prover.rs:83-150): the commit phase of `f` (the largest polynomial); whenever the
+// folded codeword reaches the length of the next polynomial of the batch it absorbs that polynomial's values.
+extern "C" int qp_batch_fri_run_commit_phase(qp_fri* f, qp_fri* const* lower, size_t n_lower, unsigned cap_height,
+                                             const unsigned* arity_bits, unsigned n_rounds, qp_challenger* ch,
+                                             uint64_t* caps_out, uint64_t* final_poly_out, size_t* final_len_out) {
+    if (!f || !ch || (n_rounds && (!arity_bits || !caps_out)) || (n_lower && !lower)) return QP_ERR_BAD_ARG;
+    // "The polynomial vectors should be sorted by degree, from largest to smallest, with no duplicate degrees"
+    // and "reduction_arity_bits covers all polynomials" (prover.rs:36-52)
+    {
+        unsigned cur = qp_fri_domain_bits(f);
+        size_t idx = 0;
+        for (size_t k = 0; k < n_lower; k++) {
+            if (!lower[k]) return QP_ERR_BAD_ARG;
+            const unsigned prev = k ? qp_fri_domain_bits(lower[k - 1]) : cur;
+            if (qp_fri_domain_bits(lower[k]) >= prev) return QP_ERR_DEGREE_MISMATCH;
+        }
+        for (unsigned i = 0; i < n_rounds; i++) {
+            if (arity_bits[i] > cur) return QP_ERR_BAD_ARG;
+            cur -= arity_bits[i];
+            if (idx < n_lower && cur == qp_fri_domain_bits(lower[idx])) idx++;
+        }
+        if (idx != n_lower) return QP_ERR_DEGREE_MISMATCH;
+    }
+    const size_t cap_words = ((size_t)1 << cap_height) * 4;
+    size_t polynomial_index = 0;
+    int rc = QP_OK;
+    for (unsigned step = 0; step < n_rounds && !rc; step++) {
+        uint64_t* cap = caps_out + step * cap_words;
+        rc = qp_fri_commit_round(f, arity_bits[step], cap);
+        if (rc) break;
+        qp_challenger_observe(ch, cap, cap_words);
+        uint64_t beta[2] = {qp_challenger_get(ch), qp_challenger_get(ch)};
+        const bool last = step + 1 == n_rounds;
+        rc = qp_fri_fold_round(f, beta, last);
+        if (rc || last) continue;
+        if (polynomial_index < n_lower && qp_fri_domain_bits(f) == qp_fri_domain_bits(lower[polynomial_index]))
+            rc = qp_fri_mix_values(f, lower[polynomial_index++], beta);
+    }
+    // (prover.rs:142: every polynomial must have been absorbed; one whose length is only reached by the LAST
+    // fold never is -- the reference asserts, so do we)
+    if (!rc && polynomial_index != n_lower) rc = QP_ERR_DEGREE_MISMATCH;
+    if (!rc) rc = qp_fri_final_poly(f, final_poly_out, final_len_out);
+    return rc;
+}
+
+// batch_fri_proof (prover.rs:25-80) + write_fri_proof: commit phase, final polynomial, PoW, query rounds with
+// the initial openings taken from BatchMerkleTrees (values(x) of every matrix + open_batch(x), prover.rs:189-203).
+extern "C" int qp_batch_fri_proof(qp_ctx* ctx, const qp_batch_fri* const* oracles, size_t n_oracles, qp_fri* f,
+                                  qp_fri* const* lower, size_t n_lower, qp_challenger* ch, unsigned rate_bits,
+                                  unsigned cap_height, const unsigned* arity_bits, unsigned n_rounds,
+                                  unsigned pow_bits, unsigned num_queries, uint8_t* out, size_t capacity,
+                                  size_t* len_out) {
+    if (!ctx || !f || !ch || !len_out || (n_oracles && !oracles) || (n_rounds && !arity_bits)) return QP_ERR_BAD_ARG;
+    const size_t cap_words = ((size_t)1 << cap_height) * 4;
+    const unsigned lde_bits = qp_fri_domain_bits(f);
+    const size_t lde = (size_t)1 << lde_bits;
+    std::vector<uint64_t> caps(cap_words * (n_rounds ? n_rounds : 1));
+    size_t final_len = 0;
+    int rc = qp_batch_fri_run_commit_phase(f, lower, n_lower, cap_height, arity_bits, n_rounds, ch, caps.data(), nullptr,
+                                           &final_len);
+    if (rc) return rc;
+    std::vector<uint64_t> final_poly(2 * (final_len ? final_len : 1));
+    rc = qp_fri_final_poly(f, final_poly.data(), &final_len);
+    if (rc) return rc;
+    qp_challenger_observe(ch, final_poly.data(), 2 * final_len);
+    uint64_t pow_witness = 0;
+    rc = qp_fri_grind(ctx, ch, pow_bits, &pow_witness);
+    if (rc) return rc;
+    std::vector<uint64_t> x(num_queries);
+    for (unsigned q = 0; q < num_queries; q++) x[q] = qp_challenger_get(ch) % lde;
+    // initial openings
+    const unsigned o_layers = lde_bits - cap_height;
+    std::vector<size_t> o_len(n_oracles, 0);
+    std::vector<std::vector<uint64_t>> o_rows(n_oracles), o_paths(n_oracles);
+    for (size_t t = 0; t < n_oracles && !rc; t++) {
+        if (!oracles[t]) return QP_ERR_BAD_ARG;
+        for (size_t g = 0; g < qp_batch_fri_num_groups(oracles[t]); g++) {
+            unsigned db = 0;
+            size_t np = 0;
+            rc = qp_batch_fri_group(oracles[t], g, &db, &np);
+            if (rc) return rc;
+            if (g == 0 && db + rate_bits != lde_bits) return QP_ERR_DEGREE_MISMATCH;
+            o_len[t] += np;
+        }
+        o_rows[t].resize((size_t)num_queries * o_len[t] + 1);
+        o_paths[t].resize((size_t)num_queries * o_layers * 4 + 1);
+        for (unsigned q = 0; q < num_queries && !rc; q++) {
+            rc = qp_batch_fri_values(oracles[t], x[q], o_rows[t].data() + (size_t)q * o_len[t]);
+            if (!rc) rc = qp_batch_fri_open(oracles[t], x[q], o_paths[t].data() + (size_t)q * o_layers * 4);
+        }
+    }
+    if (rc) return rc;
+    std::vector<std::vector<uint64_t>> r_rows(n_rounds), r_paths(n_rounds);
+    std::vector<unsigned> r_layers(n_rounds);
+    {
+        std::vector<uint64_t> idx(x);
+        unsigned bits = lde_bits;
+        for (unsigned i = 0; i < n_rounds && !rc; i++) {
+            for (auto& v : idx) v >>= arity_bits[i];
+            bits -= arity_bits[i];
+            r_layers[i] = bits - cap_height;
+            r_rows[i].resize((size_t)num_queries * (2u << arity_bits[i]) + 1);
+            r_paths[i].resize((size_t)num_queries * r_layers[i] * 4 + 1);
+            rc = qp_fri_tree_open_many(f, i, idx.data(), num_queries, r_rows[i].data(), r_paths[i].data());
+        }
+    }
+    if (rc) return rc;
+    ByteSink w{out, capacity};
+    for (unsigned i = 0; i < n_rounds; i++) w.u64s(caps.data() + i * cap_words, cap_words);
+    for (unsigned q = 0; q < num_queries; q++) {
+        for (size_t t = 0; t < n_oracles; t++) {
+            w.u64s(o_rows[t].data() + (size_t)q * o_len[t], o_len[t]);
+            w.path(o_paths[t].data() + (size_t)q * o_layers * 4, o_layers);
+        }
+        for (unsigned i = 0; i < n_rounds; i++) {
+            const size_t row = 2u << arity_bits[i];
+            w.u64s(r_rows[i].data() + (size_t)q * row, row);
+            w.path(r_paths[i].data() + (size_t)q * r_layers[i] * 4, r_layers[i]);
+        }
+    }
+    w.u64s(final_poly.data(), 2 * final_len);
+    w.u64s(&pow_witness, 1);
+    *len_out = w.len;
+    return (out && w.len > capacity) ? QP_ERR_BAD_ARG : QP_OK;
+}
+
 extern "C" size_t qp_fri_proof_len(const size_t* oracle_leaf_lens, size_t n_oracles, unsigned lde_bits,
                                    unsigned rate_bits, unsigned cap_height, const unsigned* arity_bits,
                                    unsigned n_rounds, unsigned num_queries) {

@@ -209,3 +209,127 @@ def verify(proof, common, fri, constants_sigmas_cap, circuit_digest, hiding=Fals
         if not (fp == old_eval):
             return "Final polynomial evaluation is invalid."
     return None
+
+
+# ---------------------------------------------------------------------------------------------
+# batch FRI: verify_batch_fri_proof (plonky2/src/batch_fri/verifier.rs:23-247)
+# ---------------------------------------------------------------------------------------------
+def parse_fri_proof(data, oracle_leaf_lens, lde_bits, rate_bits, cap_height, arities, num_query_rounds):
+    """write_fri_proof's layout (serialization/mod.rs:1654-1667) -> dict."""
+    r = Reader(data)
+    cap_words = 4 << cap_height
+    out = {"commit_caps": [r.u64s(cap_words).reshape(-1, 4) for _ in arities]}
+    rounds = []
+    for _ in range(num_query_rounds):
+        initial = [(r.u64s(n), r.merkle_proof()) for n in oracle_leaf_lens]
+        steps = [(r.ext(1 << a), r.merkle_proof()) for a in arities]
+        rounds.append((initial, steps))
+    out["query_rounds"] = rounds
+    out["final_poly"] = r.ext((1 << (lde_bits - sum(arities))) >> rate_bits)
+    out["pow_witness"] = int(r.u64s(1)[0])
+    assert r.p == len(data), "trailing bytes"
+    return out
+
+
+def _coefficient(coeff, point):
+    if coeff == "one" or coeff == ("one",):
+        return Ext(1)
+    if coeff[0] == "point_power":
+        return point.pow(coeff[1])
+    return Ext(int(coeff[1][0]), int(coeff[1][1]))
+
+
+def verify_batch_fri_proof(degree_bits, instances, openings, challenger, initial_caps, proof, rate_bits, cap_height,
+                           arities, pow_bits, num_query_rounds):
+    """-> None if accepted, else the failed check.  degree_bits: polynomial degrees, tallest first;
+    instances[i] = dict(oracles=[num_polys per oracle], batches=[dict(point=(a, b), openings=[expression, ...])]);
+    openings[i][b] = list of claimed (c0, c1) values of instance i's batch b; challenger: an oracle.pyref
+    Challenger in the state the prover's had right before prove_openings; initial_caps[o]: cap of oracle o."""
+    from oracle import pyref
+
+    lde = [d + rate_bits for d in degree_bits]
+    leaf_lens = [sum(inst["oracles"][o] for inst in instances) for o in range(len(initial_caps))]
+    try:
+        pr = parse_fri_proof(proof, leaf_lens, lde[0], rate_bits, cap_height, arities, num_query_rounds)
+    except Exception as e:
+        return "malformed proof: %r" % (e,)
+    # fri_challenges (core/src/fri.rs:358-420)
+    ch = challenger
+    fri_alpha = _e(ch.get_extension_challenge())
+    fri_betas = []
+    for cap in pr["commit_caps"]:
+        ch.observe([int(v) for v in cap.reshape(-1)])
+        fri_betas.append(_e(ch.get_extension_challenge()))
+    ch.observe([int(v) for v in pr["final_poly"].reshape(-1)])
+    ch.observe([pr["pow_witness"]])
+    pow_response = ch.get_challenge()
+    N = 1 << lde[0]
+    x_indices = [ch.get_challenge() % N for _ in range(num_query_rounds)]
+    if pow_bits and pow_response >> (64 - pow_bits):
+        return "Invalid proof of work witness."
+    # PrecomputedReducedOpenings::from_os_and_alpha
+    reduced = [[_reduce([_e(v) for v in vals], fri_alpha) for vals in inst_open] for inst_open in openings]
+
+    def combine_initial(index, initial, subgroup_x):        # batch_fri_combine_initial, verifier.rs:112-152
+        total = Ext(0)
+        for b, ro in zip(instances[index]["batches"], reduced[index]):
+            pt = _e(b["point"])
+            evals = []
+            for expr in b["openings"]:
+                acc = Ext(0)
+                for oi, pi, coeff in expr:
+                    acc = acc + _coefficient(coeff, pt) * Ext(int(initial[oi][0][pi]))
+                evals.append(acc)
+            num = _reduce(evals, fri_alpha) - ro
+            total = total * fri_alpha.pow(len(evals)) + num * (Ext(subgroup_x) - pt).inv()
+        return total
+
+    for x_index, (initial, steps) in zip(x_indices, pr["query_rounds"]):
+        # batch_fri_verify_initial_proof: per oracle, the rows of every degree under one batch Merkle proof
+        for o, ((evals, path), cap) in enumerate(zip(initial, initial_caps)):
+            rows, pos = [], 0
+            for inst in instances:
+                k = inst["oracles"][o]
+                rows.append([int(v) for v in evals[pos:pos + k]])
+                pos += k
+            if not pyref.batch_merkle_verify(rows, lde, x_index, [[int(v) for v in d] for d in cap],
+                                             [[int(v) for v in d] for d in path]):
+                return "initial batch Merkle proof"
+        n = lde[0]
+        subgroup_x = GEN * pow(root_of_unity(n), reverse_bits(x_index, n), P) % P
+        batch_index = 0
+        old_eval = combine_initial(batch_index, initial, subgroup_x)
+        batch_index += 1
+        xi = x_index
+        for k, a in enumerate(arities):
+            evals, path = steps[k]
+            arity = 1 << a
+            coset_index, within = xi >> a, xi & (arity - 1)
+            if not (_e(evals[within]) == old_eval):
+                return "FRI consistency at reduction %d" % k
+            ga = root_of_unity(a)
+            ev = [None] * arity
+            for i in range(arity):
+                ev[reverse_bits(i, a)] = _e(evals[i])
+            start = subgroup_x * pow(ga, arity - reverse_bits(within, a), P) % P
+            pts = [start * pow(ga, i, P) % P for i in range(arity)]
+            old_eval = _interpolate(pts, ev, fri_betas[k])
+            if not pyref.merkle_verify([int(v) for v in evals.reshape(-1)], coset_index,
+                                       [[int(v) for v in d] for d in pr["commit_caps"][k]],
+                                       [[int(v) for v in d] for d in path]):
+                return "commit-phase Merkle proof %d" % k
+            subgroup_x = pow(subgroup_x, arity, P)
+            xi = coset_index
+            n -= a
+            if batch_index < len(lde) and n == lde[batch_index]:
+                x_init = GEN * pow(root_of_unity(n), reverse_bits(xi, n), P) % P
+                old_eval = old_eval * fri_betas[k] + combine_initial(batch_index, initial, x_init)
+                batch_index += 1
+        if batch_index != len(instances):
+            return "Wrong number of folded instances."
+        fp = Ext(0)
+        for coef in reversed(pr["final_poly"]):
+            fp = fp * subgroup_x + _e(coef)
+        if not (fp == old_eval):
+            return "Final polynomial evaluation is invalid."
+    return None
