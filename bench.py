@@ -161,7 +161,7 @@ def run_reference(args):
     _, cores = oracle_threads()
     vals = synth_columns_numpy(0, COLS, 1 << args.rows_log)
     # every step is one FULL-size commit; QP_REF_BUDGET_S bounds the whole run (steps_run says how many ran)
-    budget = float(os.environ.get("QP_REF_BUDGET_S", 1500))
+    budget = float(os.environ.get("QP_REF_BUDGET_S", 420))   # "ends within a few minutes"
     t_start = time.perf_counter()
     times, scopes, cap0 = [], None, None
     warm = 0

@@ -284,7 +284,20 @@ __device__ __forceinline__ uint64_t sqr_hv(uint64_t a) {
 
 // x^7 (core/src/poseidon.rs:546-552)
 __device__ __forceinline__ uint64_t pow7(uint64_t x) {
-#if QP_POSEIDON_SQR_HV
+#if defined(QP_POW7_VARIANT)
+    // measurement variants (tools/microbench): bit 0 / bit 1 = first / second squaring explicit (sqr_hv) or the
+    // compiler's; bit 2 = multiplications explicit (mul_hv); bit 3 = the chain x^2, x^3, x^6, x^7
+    constexpr int V = QP_POW7_VARIANT;
+    auto S1 = [](uint64_t a) { return (V & 1) ? sqr_hv(a) : sqr(a); };
+    auto S2 = [](uint64_t a) { return (V & 2) ? sqr_hv(a) : sqr(a); };
+    auto M = [](uint64_t a, uint64_t b) { return (V & 4) ? mul_hv(a, b) : mul(a, b); };
+    if (V & 8) {
+        const uint64_t x2 = S1(x), x3 = M(x2, x), x6 = S2(x3);
+        return M(x6, x);
+    }
+    const uint64_t x2 = S1(x), x4 = S2(x2), x3 = M(x, x2);
+    return M(x3, x4);
+#elif QP_POSEIDON_SQR_HV
     uint64_t x2 = sqr_hv(x);
     uint64_t x4 = sqr_hv(x2);
     uint64_t x3 = mul(x, x2);

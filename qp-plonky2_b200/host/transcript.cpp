@@ -130,7 +130,9 @@ extern "C" uint64_t qp_challenger_get(qp_challenger* c) {  // challenger.rs:78-8
 extern "C" unsigned qp_fri_reduction_arity_bits(unsigned degree_bits, unsigned rate_bits, unsigned cap_height,
                                                 unsigned arity_bits, unsigned final_poly_bits, unsigned out[64]) {
     unsigned k = 0;
-    while (degree_bits > final_poly_bits && degree_bits + rate_bits - arity_bits >= cap_height && k < 64) {
+    if (arity_bits == 0) return 0;  // the reference asserts arity_bits > 0 (core/src/fri.rs:50-61)
+    while (degree_bits > final_poly_bits && degree_bits + rate_bits >= cap_height + arity_bits && k < 64) {
+        if (arity_bits > degree_bits) break;  // would fold below one coefficient
         out[k++] = arity_bits;
         degree_bits -= arity_bits;
     }
