@@ -319,6 +319,12 @@ extern "C" void qp_ctx_destroy(qp_ctx* ctx) {
     }
     cudaFreeAsync(ctx->tw, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
+    {
+        // the release threshold is raised for the life of a context (a 9 GB LDE is recycled between commits);
+        // when a context goes away, what the pool holds and nobody uses goes back to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     for (auto& e : ctx->copy_ev) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ready_ev);

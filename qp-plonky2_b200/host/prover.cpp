@@ -148,13 +148,14 @@ extern "C" int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* con
         qp_dev_free(ctx, d_salt_z);
         qp_dev_free(ctx, d_salt_q);
     };
-#define QP_STEP(expr)            \
-    do {                         \
-        rc = (expr);             \
-        if (rc) {                \
-            cleanup();           \
-            return rc;           \
-        }                        \
+#define QP_STEP(expr)                                                                                   \
+    do {                                                                                                \
+        rc = (expr);                                                                                    \
+        if (rc) {                                                                                       \
+            if (getenv("QP_TRACE")) fprintf(stderr, "[prover.cpp:%d] rc=%d: %s\n", __LINE__, rc, #expr); \
+            cleanup();                                                                                  \
+            return rc;                                                                                  \
+        }                                                                                               \
     } while (0)
 
     // the Z and quotient oracles are committed from device data: their salt has to be there too
@@ -387,13 +388,14 @@ extern "C" int qp_mprove(qp_mctx* m, qp_circuit* const* circuits, qp_mbatch* con
         qp_dev_free(ctx, d_q);
         qp_dev_free(ctx, d_vals);
     };
-#define QP_STEP(expr)            \
-    do {                         \
-        rc = (expr);             \
-        if (rc) {                \
-            cleanup();           \
-            return rc;           \
-        }                        \
+#define QP_STEP(expr)                                                                                   \
+    do {                                                                                                \
+        rc = (expr);                                                                                    \
+        if (rc) {                                                                                       \
+            if (getenv("QP_TRACE")) fprintf(stderr, "[prover.cpp:%d] rc=%d: %s\n", __LINE__, rc, #expr); \
+            cleanup();                                                                                  \
+            return rc;                                                                                  \
+        }                                                                                               \
     } while (0)
 
     // wires commitment over all devices, prover.rs:201-214

@@ -50,7 +50,8 @@ if __name__ == "__main__":
         circ.free()
         ctx.close()
         same = True
-        for D in [x for x in (1, 2, 4, 8) if x <= n_dev]:
+        only = [int(x) for x in os.environ.get("QP_MPROVE_DEVICES", "").split(",") if x]
+        for D in [x for x in (1, 2, 4, 8) if x <= n_dev and (not only or x in only)]:
             m = qp.MultiContext(list(range(D)), max_lde_log=db + c.rate_bits)
             mpd = prover.MultiProverData(m, c, sc.sigmas, sc.constants_sigmas())
             best, timing = 1e30, {}
