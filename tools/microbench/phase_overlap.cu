@@ -30,6 +30,21 @@ __global__ void __launch_bounds__(256, 1) k(uint64_t* out, uint64_t seed) {
     } else if (MODE == 2 || (MODE == 5 && odd)) {
 #pragma unroll 1
         for (int it = 0; it < ITER; it++) poseidon::partial_pair_split(s, it % 11);
+    } else if (MODE == 6) {
+        // two independent states per thread: the S-box layer of one and the linear layer of the other sit in the
+        // same basic block, so ptxas is free to interleave MUL.WIDE / IADD3 with DFMA inside one warp
+        uint64_t t[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) t[i] = s[i] ^ 0x5555555555555555ULL;
+#pragma unroll 1
+        for (int it = 0; it < ITER / 2; it++) {
+            poseidon::sbox_all(s);
+            poseidon::mds_layer_split(t, 1 + (it & 3));
+            poseidon::sbox_all(t);
+            poseidon::mds_layer_split(s, 1 + (it & 3));
+        }
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] ^= t[i];
     } else {
 #pragma unroll 1
         for (int it = 0; it < ITER / 16; it++) poseidon::permute<false>(s);
@@ -84,6 +99,9 @@ int main(int argc, char** argv) {
         const double SM = run("S|M", k<3>, w, ITER) * 2;
         const double SP = run("S|P", k<5>, w, ITER) * 2;
         const double perm = run("perm", k<4>, w, ITER / 16);
+        // per (S + M) of ONE state: the kernel does ITER S-layers and ITER linear layers per thread
+        const double SM2 = run("S+M x2", k<6>, w, ITER);
+        printf("  two states per thread, S-box layer of one next to the linear layer of the other: %.0f per (S + M) (sum %.0f)\n", SM2, S + M);
         printf("  %d warps/SMSP: S %.0f  M %.0f  P %.0f | one S-warp + one M-warp side by side: %.0f per (S+M) "
                "(sum %.0f, max %.0f) | S+P side by side %.0f (sum %.0f)\n",
                w, S, M, P, SM, S + M, S > M ? S : M, SP, S + P);
