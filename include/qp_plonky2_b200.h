@@ -47,7 +47,7 @@ enum {
     QP_ERR_BAD_ARG = 5,        /* null pointer / out-of-range index (slice index panic) */
     QP_ERR_TOO_LARGE = 6,      /* exceeds the field's two-adicity (types.rs:281 assert) or device memory */
     QP_ERR_BLINDING_NO_SALT = 7,/* blinding requested without injected salt ("Cannot set blinding without rand feature", oracle.rs:238) */
-    QP_ERR_UNSUPPORTED = 8     /* a feature of the reference outside this library's contract (lookup arguments): refused, never approximated */
+    QP_ERR_UNSUPPORTED = 8     /* a feature of the reference outside this library's contract: refused, never approximated */
 };
 
 enum { QP_HOST = 0, QP_DEVICE = 1 };
@@ -371,6 +371,14 @@ int qp_fri_proof_of_work(qp_ctx* ctx, const uint64_t state12[12], unsigned witne
  * The program evaluates evaluate_gate_constraints_base_batch (vanishing_poly.rs:700-726); a Rust
  * shim produces it by running Gate::eval_unfiltered_base_one over a recording field type, the
  * Python mirror (qp-plonky2_b200/plonk.py) from its own gate classes. */
+/* One lookup table and where its gates sit (LookupTable = Vec<(u16, u16)>, gates/lookup_table.rs:33;
+ * LookupWire, plonk/circuit_builder.rs:78-90: rows are "upside down" -- LookupGate rows
+ * [last_lu_row, last_lut_row), LookupTableGate rows [last_lut_row, first_lut_row], gadgets/lookup.rs:80-160). */
+typedef struct {
+    const uint16_t* table;           /* [len][2]: (input, output) pairs (host) */
+    size_t len;
+    uint32_t last_lu_row, last_lut_row, first_lut_row;
+} qp_lookup_table;
 typedef struct {
     uint32_t degree_bits;            /* common_data.degree_bits() */
     uint32_t quotient_degree_bits;   /* log2_ceil(quotient_degree_factor) */
@@ -387,12 +395,18 @@ typedef struct {
     const uint64_t* pool;            /* field constants of the program (host) */
     size_t pool_len;
     uint32_t program_regs;           /* registers the program uses */
-    /* What this library does NOT implement must be declared, so that it is refused instead of proved wrong:
-     * common_data.num_lookup_polys / num_lookup_selectors (lookup argument: compute_lookup_polys,
-     * plonky2/src/plonk/prover.rs:489-636, the lookup terms of vanishing_poly.rs:63-160).  A circuit with
-     * lookup tables has both nonzero; qp_circuit_create answers QP_ERR_UNSUPPORTED. */
+    /* Lookup argument (compute_lookup_polys, plonky2/src/plonk/prover.rs:489-636; the lookup terms of
+     * vanishing_poly.rs:273-292,521-680).  A circuit without lookup tables has all of these zero / NULL.
+     * num_lookup_polys = common_data.num_lookup_polys (RE + the partial SLDC polynomials, per challenge:
+     * 1 + ceil((num_routed_wires / 2) / (max_degree - 1)), circuit_builder.rs:1284-1290);
+     * num_lookup_selectors = 4 + n_luts (gates/selectors.rs:27-75), stored right after the num_selectors
+     * selector polynomials of the constants (circuit_builder.rs:1183-1194); luts = common_data.luts with
+     * prover_data.lookup_rows (one LookupWire per table).  Inconsistent declarations are QP_ERR_BAD_ARG. */
     uint32_t num_lookup_polys;
     uint32_t num_lookup_selectors;
+    uint32_t num_selectors;          /* selectors_info.num_selectors(); read only when there are lookups */
+    const qp_lookup_table* luts;     /* (host) */
+    size_t n_luts;
 } qp_circuit_desc;
 typedef struct qp_circuit qp_circuit;
 int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* desc, qp_circuit** out);
@@ -415,7 +429,19 @@ int qp_memcpy_peer(qp_ctx* dst_ctx, uint64_t* dst, qp_ctx* src_ctx, const uint64
  * second PolynomialBatch::from_values of prove(). */
 int qp_circuit_partial_products_and_zs(qp_circuit* c, const uint64_t* wires, int space, const uint64_t* betas,
                                        const uint64_t* gammas, uint64_t* out, int out_space);
-/* compute_quotient_polys (plonky2/src/plonk/prover.rs:640-866, without lookups): evaluates the
+/* compute_all_lookup_polys (plonky2/src/plonk/prover.rs:489-636) for a circuit with lookup tables.  wires: the
+ * witness columns [>= num_routed_wires][n]; deltas: [num_challenges][4] = (ChallengeA, ChallengeB, ChallengeAlpha,
+ * ChallengeDelta) per challenge -- the reference's flat `deltas` (prover.rs:236-248: betas, gammas, then the
+ * additional challenges).  out: [num_challenges * num_lookup_polys][n] value columns, per challenge RE first,
+ * then the partial SLDC polynomials: the columns prove() appends to the Z / partial-product batch (prover.rs:265-271). */
+int qp_circuit_lookup_polys(qp_circuit* c, const uint64_t* wires, int space, const uint64_t* deltas, uint64_t* out,
+                            int out_space);
+/* The lookup challenges of the proof in progress: the quotient entry points below evaluate the lookup terms with
+ * them (and with get_lut_poly(..).eval(delta) of every table, prover.rs:687-716, computed here).  Must be called
+ * before them when the circuit has lookup tables. */
+int qp_circuit_set_lookup_challenges(qp_circuit* c, const uint64_t* deltas);
+/* compute_quotient_polys (plonky2/src/plonk/prover.rs:640-866; with lookup tables zs_partial_products also holds
+ * the lookup polynomials, lookup_range circuit_data.rs:582): evaluates the
  * vanishing polynomial on the coset of size n << quotient_degree_bits from the three oracles' LDEs
  * (which stay on the device), divides by Z_H and interpolates (coset_ifft).  out:
  * [num_challenges][n << quotient_degree_bits] coefficients; read as [num_challenges *

@@ -106,20 +106,31 @@ int qp_batch_fri_proof(qp_ctx* ctx, const qp_batch_fri* const* initial_oracles, 
 enum { QP_GATE_NOOP = 0, QP_GATE_CONSTANT = 1, QP_GATE_PUBLIC_INPUT = 2, QP_GATE_ARITHMETIC = 3, QP_GATE_POSEIDON = 4,
        QP_GATE_ARITHMETIC_EXT = 5, QP_GATE_MUL_EXT = 6, QP_GATE_BASE_SUM_2 = 7, QP_GATE_RANDOM_ACCESS = 8,
        QP_GATE_REDUCING = 9, QP_GATE_REDUCING_EXT = 10, QP_GATE_POSEIDON_MDS = 11, QP_GATE_EXPONENTIATION = 12,
-       QP_GATE_COSET_INTERPOLATION = 13 };
+       QP_GATE_COSET_INTERPOLATION = 13,
+       QP_GATE_LOOKUP = 14, QP_GATE_LOOKUP_TABLE = 15 /* gates/lookup.rs, gates/lookup_table.rs; qp_program_create_lookups */ };
 typedef struct {
     uint32_t kind;   /* QP_GATE_* */
     uint32_t param;  /* ConstantGate: num_consts; Arithmetic / ArithmeticExtension / MulExtension: num_ops;
                         BaseSumGate<2>: num_limbs; Reducing / ReducingExtension: num_coeffs;
                         Exponentiation: num_power_bits;
                         RandomAccess: bits | num_copies << 8 | num_extra_constants << 16;
-                        CosetInterpolation: subgroup_bits | degree << 8; otherwise 0 */
+                        CosetInterpolation: subgroup_bits | degree << 8;
+                        Lookup / LookupTable: index of the gate's table in `luts`; otherwise 0 */
 } qp_gate_desc;
 /* Column loads of a compiled program are issued this many loads ahead of their first use (the
  * device keeps that many asynchronous loads in flight; include/qp_plonky2_b200.h, op 12 WAIT). */
 #define QP_PROGRAM_LOAD_LEAD 3
 typedef struct qp_program qp_program;
 int qp_program_create(const qp_gate_desc* gates, size_t n_gates, unsigned max_degree, qp_program** out);
+/* The same for a circuit with lookup tables: LookupGate / LookupTableGate have no constraints of their own, but their
+ * ids -- "LookupGate {num_slots: .., lut_hash: [..]}", "LookupTableGate {num_slots: .., lut_hash: [..], last_lut_row:
+ * ..}" with the Keccak-256 of the table (lookup.rs:44-55,72-77; lookup_table.rs:50-62,86-92) -- take part in the
+ * gate ordering, and the gates' constants start after num_selectors + num_lookup_selectors (= 4 + n_luts) columns
+ * (gate.rs:179, circuit_builder.rs:1183-1197). */
+int qp_program_create_lookups(const qp_gate_desc* gates, size_t n_gates, unsigned max_degree, unsigned num_routed_wires,
+                              const qp_lookup_table* luts, size_t n_luts, qp_program** out);
+/* keccak_hash::keccak (Keccak-256, the pre-NIST padding) -- the lut_hash of the two lookup gates. */
+void qp_keccak256(const uint8_t* data, size_t len, uint8_t out[32]);
 /* The same compiler on a recording made elsewhere (a Rust shim's recording field type run over
  * Gate::eval_unfiltered_base_one, or qp-plonky2_b200/plonk.py): nodes in creation order (operands
  * before their consumers), ops numbered like the program's (include/qp_plonky2_b200.h):
@@ -162,7 +173,8 @@ typedef struct {
 /* prove_with_partition_witness from the full witness on, serialised like
  * write_proof_with_public_inputs (plonky2/src/util/serialization/mod.rs:2040-2079).  `wires`:
  * witness matrix [num_wires][n] (host or device); the circuit must have been created with sigmas.
- * No lookups; PoW witness = smallest valid one (zero-knowledge blinding: qp_prove_zk below).  Two-call protocol: with out == NULL only
+ * Lookup tables: the circuit's (qp_circuit_desc.luts; the deltas are drawn and the lookup polynomials committed
+ * with the Z's, prover.rs:236-271).  PoW witness = smallest valid one (zero-knowledge blinding: qp_prove_zk below).  Two-call protocol: with out == NULL only
  * *len_out (an upper bound of the proof size) is written.  timing_ms (optional, 7 entries) receives the
  * reference's TimingTree scopes: wires commitment, partial products, their commitment, quotient polys,
  * quotient commitment, opening set, opening proofs. */

@@ -125,6 +125,11 @@ def lib():
         "orc_compute_quotient_polys": (C.c_int, [C.c_void_p, u32, u64p, sz, u64p, sz, u64p, sz, u64p, u64p, u64p,
                                                  u64p, u64p]),
         "orc_partial_products_and_zs": (None, [C.c_void_p, u64p, u64p, u64p, u64p, u64p]),
+        "orc_lookup_polys": (None, [C.c_void_p, u64p, u64p, u64p]),
+        "orc_lut_poly_eval": (u64, [C.c_void_p, u32, u64p]),
+        "orc_eval_vanishing_poly_base_lookup": (None, [C.c_void_p, u64, u64] + [u64p] * 14),
+        "orc_compute_quotient_polys_lookup": (C.c_int, [C.c_void_p, u32, u64p, sz, u64p, sz, u64p, sz, u64p, u64p, u64p,
+                                                        u64p, u64p, u64p]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -433,6 +438,7 @@ GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON = 0,
 GATE_ARITHMETIC_EXT, GATE_MUL_EXT, GATE_BASE_SUM_2 = 5, 6, 7
 (GATE_RANDOM_ACCESS, GATE_REDUCING, GATE_REDUCING_EXT, GATE_POSEIDON_MDS, GATE_EXPONENTIATION,
  GATE_COSET_INTERPOLATION) = range(8, 14)
+GATE_LOOKUP, GATE_LOOKUP_TABLE = 14, 15
 
 
 class _OrcGate(C.Structure):
@@ -440,12 +446,18 @@ class _OrcGate(C.Structure):
                 ("selector_index", C.c_uint32), ("group_start", C.c_uint32), ("group_end", C.c_uint32)]
 
 
+class _OrcLookups(C.Structure):
+    _fields_ = [("num_luts", C.c_uint32), ("lut_lens", C.POINTER(C.c_uint32)),
+                ("luts", C.POINTER(C.POINTER(C.c_uint16))), ("lookup_rows", C.POINTER(C.c_uint32)),
+                ("num_lookup_polys", C.c_uint32), ("lookup_degree", C.c_uint32)]
+
+
 class _OrcCircuit(C.Structure):
     _fields_ = [("degree_bits", C.c_uint32), ("quotient_degree_bits", C.c_uint32),
                 ("num_challenges", C.c_uint32), ("num_routed_wires", C.c_uint32), ("num_wires", C.c_uint32),
                 ("num_constants", C.c_uint32), ("num_partial_products", C.c_uint32), ("max_degree", C.c_uint32),
                 ("num_selectors", C.c_uint32), ("num_lookup_selectors", C.c_uint32), ("num_gates", C.c_uint32),
-                ("gates", C.POINTER(_OrcGate)), ("k_is", u64p)]
+                ("gates", C.POINTER(_OrcGate)), ("k_is", u64p), ("lookups", C.POINTER(_OrcLookups))]
 
 
 class Circuit:
@@ -453,14 +465,30 @@ class Circuit:
     (kind, param, selector_index, (group_start, group_end)) in SORTED gate order."""
 
     def __init__(self, degree_bits, quotient_degree_bits, num_challenges, num_routed_wires, num_wires,
-                 num_constants, num_partial_products, max_degree, num_selectors, gates, k_is):
+                 num_constants, num_partial_products, max_degree, num_selectors, gates, k_is, luts=None,
+                 lookup_rows=None):
+        """luts: list of [(input, output), ...] tables (common_data.luts); lookup_rows: one
+        (last_lu_row, last_lut_row, first_lut_row) per table (prover_data.lookup_rows)."""
         self._gates = (_OrcGate * len(gates))()
         for i, (kind, param, sel, (gs, ge)) in enumerate(gates):
             self._gates[i] = _OrcGate(kind, param, i, sel, gs, ge)
         self._k_is = np.ascontiguousarray(k_is, dtype=np.uint64)
+        self.luts = [np.ascontiguousarray(t, dtype=np.uint16).reshape(-1, 2) for t in (luts or [])]
+        self.num_lookup_polys = 0
+        lk_ptr = C.POINTER(_OrcLookups)()
+        if self.luts:
+            lookup_degree = max_degree - 1                      # lookup_accumulator_degree, circuit_data.rs:557-559
+            self.num_lookup_polys = -(-(num_routed_wires // 2) // lookup_degree) + 1   # circuit_builder.rs:1284-1290
+            self._lut_lens = np.array([len(t) for t in self.luts], dtype=np.uint32)
+            self._lut_ptrs = (C.POINTER(C.c_uint16) * len(self.luts))(
+                *[t.ctypes.data_as(C.POINTER(C.c_uint16)) for t in self.luts])
+            self._rows = np.ascontiguousarray(lookup_rows, dtype=np.uint32).reshape(len(self.luts), 3)
+            self._lk = _OrcLookups(len(self.luts), self._lut_lens.ctypes.data_as(C.POINTER(C.c_uint32)), self._lut_ptrs,
+                                   self._rows.ctypes.data_as(C.POINTER(C.c_uint32)), self.num_lookup_polys, lookup_degree)
+            lk_ptr = C.pointer(self._lk)
         self.c = _OrcCircuit(degree_bits, quotient_degree_bits, num_challenges, num_routed_wires, num_wires,
-                             num_constants, num_partial_products, max_degree, num_selectors, 0, len(gates),
-                             self._gates, _ptr(self._k_is))
+                             num_constants, num_partial_products, max_degree, num_selectors,
+                             4 + len(self.luts) if self.luts else 0, len(gates), self._gates, _ptr(self._k_is), lk_ptr)
         self.num_challenges = num_challenges
         self.degree_bits, self.quotient_degree_bits = degree_bits, quotient_degree_bits
         self.num_partial_products = num_partial_products
@@ -475,16 +503,44 @@ class Circuit:
         lib().orc_eval_vanishing_poly_base(C.byref(self.c), int(x), z_h, *[_ptr(a) for a in arrs], _ptr(res))
         return res
 
-    def compute_quotient_polys(self, rate_bits, cs_leaves, wires_leaves, zs_leaves, betas, gammas, alphas, pih):
-        """compute_quotient_polys (prover.rs:640-866) from the three oracles' leaf-major LDE rows."""
+    def compute_quotient_polys(self, rate_bits, cs_leaves, wires_leaves, zs_leaves, betas, gammas, alphas, pih,
+                               deltas=None):
+        """compute_quotient_polys (prover.rs:640-866) from the three oracles' leaf-major LDE rows.  deltas: the
+        lookup challenges [nc][4] of a circuit with lookup tables (the lookup polynomials are then the last
+        columns of the third oracle)."""
         arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in (betas, gammas, alphas, pih)]
         L = [np.ascontiguousarray(a, dtype=np.uint64) for a in (cs_leaves, wires_leaves, zs_leaves)]
         out = np.zeros((self.num_challenges, 1 << (self.degree_bits + self.quotient_degree_bits)), dtype=np.uint64)
-        rc = lib().orc_compute_quotient_polys(C.byref(self.c), rate_bits, _ptr(L[0]), L[0].shape[1], _ptr(L[1]),
-                                              L[1].shape[1], _ptr(L[2]), L[2].shape[1],
-                                              *[_ptr(a) for a in arrs], _ptr(out))
+        if deltas is None:
+            rc = lib().orc_compute_quotient_polys(C.byref(self.c), rate_bits, _ptr(L[0]), L[0].shape[1], _ptr(L[1]),
+                                                  L[1].shape[1], _ptr(L[2]), L[2].shape[1],
+                                                  *[_ptr(a) for a in arrs], _ptr(out))
+        else:
+            d = np.ascontiguousarray(deltas, dtype=np.uint64)
+            rc = lib().orc_compute_quotient_polys_lookup(
+                C.byref(self.c), rate_bits, _ptr(L[0]), L[0].shape[1], _ptr(L[1]), L[1].shape[1], _ptr(L[2]),
+                L[2].shape[1], _ptr(arrs[0]), _ptr(arrs[1]), _ptr(d), _ptr(arrs[2]), _ptr(arrs[3]), _ptr(out))
         assert rc == 0, "Having constraints of degree higher than the rate is not supported yet."
         return out
+
+    def lookup_polys(self, wires, deltas):
+        """compute_all_lookup_polys (prover.rs:489-636): -> [nc * num_lookup_polys][n] value columns."""
+        w = np.ascontiguousarray(wires, dtype=np.uint64)
+        d = np.ascontiguousarray(deltas, dtype=np.uint64)
+        out = np.zeros((self.num_challenges * self.num_lookup_polys, 1 << self.degree_bits), dtype=np.uint64)
+        lib().orc_lookup_polys(C.byref(self.c), _ptr(w), _ptr(d), _ptr(out))
+        return out
+
+    def eval_vanishing_poly_base_lookup(self, x, constants, wires, local_zs, next_zs, partial_products, s_sigmas,
+                                        local_lookup_zs, next_lookup_zs, betas, gammas, deltas, alphas, pih):
+        """eval_vanishing_poly_base_batch for one point x, lookup terms included."""
+        arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in
+                (constants, wires, local_zs, next_zs, partial_products, s_sigmas, local_lookup_zs, next_lookup_zs,
+                 betas, gammas, deltas, alphas, pih)]
+        res = np.zeros(self.num_challenges, dtype=np.uint64)
+        z_h = (pow(int(x), 1 << self.degree_bits, P) - 1) % P
+        lib().orc_eval_vanishing_poly_base_lookup(C.byref(self.c), int(x), z_h, *[_ptr(a) for a in arrs], _ptr(res))
+        return res
 
     def partial_products_and_zs(self, wires, sigmas, betas, gammas):
         """all_wires_permutation_partial_products, Z columns first (prover.rs:255-261,402-480)."""

@@ -850,6 +850,8 @@ static void gate_eval_add(const orc_gate *g, const uint64_t *consts, const uint6
                           const uint64_t pih[4], uint64_t filter, uint64_t *acc) {
     switch (g->kind) {
     case ORC_GATE_NOOP: /* gates/noop.rs: no constraints */
+    case ORC_GATE_LOOKUP: /* gates/lookup.rs:190-195, gates/lookup_table.rs:177-181: no gate constraints */
+    case ORC_GATE_LOOKUP_TABLE:
         break;
     case ORC_GATE_CONSTANT: /* gates/constant.rs:121-129 */
         for (unsigned i = 0; i < g->param; i++)
@@ -1101,9 +1103,142 @@ void orc_eval_vanishing_poly_base(const orc_circuit *c, uint64_t x, uint64_t z_h
                                   const uint64_t *partial_products, const uint64_t *s_sigmas,
                                   const uint64_t *betas, const uint64_t *gammas, const uint64_t *alphas,
                                   const uint64_t pih[4], uint64_t *res) {
+    orc_eval_vanishing_poly_base_lookup(c, x, z_h_x, constants, wires, local_zs, next_zs, partial_products, s_sigmas,
+                                        NULL, NULL, betas, gammas, NULL, alphas, pih, res);
+}
+
+/* get_lut_poly(...).eval(delta), vanishing_poly.rs:29-52: the table's combos input + b * output, padded with
+ * the first entry to whole LookupTableGate rows, as the coefficients of a polynomial in reverse order -- i.e.
+ * a Horner accumulation over the entries in table order. */
+uint64_t orc_lut_poly_eval(const orc_circuit *c, unsigned lut_index, const uint64_t deltas4[4]) {
+    const orc_lookups *lk = c->lookups;
+    const unsigned n = lk->lut_lens[lut_index], slots = c->num_routed_wires / 3;
+    const unsigned padded = (slots - n % slots) % slots;
+    const uint16_t *t = lk->luts[lut_index];
+    const uint64_t b = deltas4[1], delta = deltas4[3];
+    uint64_t acc = 0;
+    for (unsigned k = 0; k < n + padded; k++) {
+        const unsigned e = k < n ? k : 0;
+        acc = gl_add(gl_mul(acc, delta), gl_add(t[2 * e], gl_mul(b, t[2 * e + 1])));
+    }
+    return orc_gl_canon(acc);
+}
+
+/* check_lookup_constraints_batch, vanishing_poly.rs:521-680, for one challenge: 4 + num_luts + 2 num_sldc
+ * constraints into out[].  lookup_selectors = constants[num_selectors ..]; d = this challenge's four deltas. */
+static unsigned lookup_constraints(const orc_circuit *c, const uint64_t *wires, const uint64_t *local_zs,
+                                   const uint64_t *next_zs, const uint64_t *sel, const uint64_t d[4], uint64_t *out) {
+    const orc_lookups *lk = c->lookups;
+    const unsigned num_lu_slots = c->num_routed_wires / 2, num_lut_slots = c->num_routed_wires / 3;
+    const unsigned lu_degree = lk->lookup_degree, num_sldc = lk->num_lookup_polys - 1;
+    const unsigned lut_degree = (num_lut_slots + num_sldc - 1) / num_sldc;
+    enum { TRANS_SRE = 0, TRANS_LDC = 1, INIT_SRE = 2, LAST_LDC = 3, START_END = 4 };
+    const uint64_t z_re = local_zs[0], next_z_re = next_zs[0];
+    const uint64_t *z_x = local_zs + 1, *z_gx = next_zs + 1;
+    uint64_t looked[num_lut_slots], looking[num_lu_slots], lookup[num_lut_slots];
+    for (unsigned s = 0; s < num_lut_slots; s++) {
+        looked[s] = gl_add(wires[3 * s], gl_mul(d[0], wires[3 * s + 1]));
+        lookup[s] = gl_add(wires[3 * s], gl_mul(d[1], wires[3 * s + 1]));
+    }
+    for (unsigned s = 0; s < num_lu_slots; s++) looking[s] = gl_add(wires[2 * s], gl_mul(d[0], wires[2 * s + 1]));
+    unsigned k = 0;
+    out[k++] = gl_mul(sel[LAST_LDC], z_x[num_sldc - 1]);
+    out[k++] = gl_mul(sel[INIT_SRE], z_x[0]);
+    out[k++] = gl_mul(sel[INIT_SRE], z_re);
+    for (unsigned r = 0; r < lk->num_luts; r++)
+        out[k++] = gl_mul(sel[START_END + r], gl_sub(z_re, orc_lut_poly_eval(c, r, d)));
+    uint64_t cur = next_z_re;
+    for (unsigned s = 0; s < num_lut_slots; s++) cur = gl_add(gl_mul(cur, d[3]), lookup[s]);
+    out[k++] = gl_mul(sel[TRANS_SRE], gl_sub(z_re, cur));
+    for (unsigned poly = 0; poly < num_sldc; poly++) {
+        const unsigned t0 = poly * lut_degree, t1 = (poly + 1) * lut_degree < num_lut_slots ? (poly + 1) * lut_degree : num_lut_slots;
+        const unsigned u0 = poly * lu_degree, u1 = (poly + 1) * lu_degree < num_lu_slots ? (poly + 1) * lu_degree : num_lu_slots;
+        uint64_t lut_prod = 1, lu_prod = 1, lu_sum_prods = 0, lut_sum_prods_mul = 0;
+        for (unsigned i = t0; i < t1; i++) lut_prod = gl_mul(lut_prod, gl_sub(d[2], looked[i]));
+        for (unsigned i = u0; i < u1; i++) lu_prod = gl_mul(lu_prod, gl_sub(d[2], looking[i]));
+        for (unsigned i = u0; i < u1; i++) {
+            uint64_t pr = 1;
+            for (unsigned j = u0; j < u1; j++)
+                if (j != i) pr = gl_mul(pr, gl_sub(d[2], looking[j]));
+            lu_sum_prods = gl_add(lu_sum_prods, pr);
+        }
+        for (unsigned i = t0; i < t1; i++) {
+            uint64_t pr = 1;
+            for (unsigned j = t0; j < t1; j++)
+                if (j != i) pr = gl_mul(pr, gl_sub(d[2], looked[j]));
+            lut_sum_prods_mul = gl_add(lut_sum_prods_mul, gl_mul(wires[3 * i + 2], pr));
+        }
+        const uint64_t prev = poly == 0 ? z_gx[num_sldc - 1] : z_x[poly - 1];
+        const uint64_t diff = gl_sub(z_x[poly], prev);
+        out[k++] = gl_mul(sel[TRANS_SRE], gl_sub(gl_mul(lut_prod, diff), lut_sum_prods_mul));
+        out[k++] = gl_mul(sel[TRANS_LDC], gl_add(gl_mul(lu_prod, diff), lu_sum_prods));
+    }
+    return k;
+}
+
+/* compute_lookup_polys for every challenge (prover.rs:489-636): out[nc * num_lookup_polys][n] value columns,
+ * per challenge RE first, then the partial SLDC polynomials.  wires[num_wires][n]. */
+void orc_lookup_polys(const orc_circuit *c, const uint64_t *wires, const uint64_t *deltas, uint64_t *out) {
+    const orc_lookups *lk = c->lookups;
+    const size_t n = (size_t)1 << c->degree_bits;
+    const unsigned num_lu_slots = c->num_routed_wires / 2, num_lut_slots = c->num_routed_wires / 3;
+    const unsigned max_lu_deg = lk->lookup_degree, npl = (num_lu_slots + max_lu_deg - 1) / max_lu_deg;
+    const unsigned max_lut_deg = (num_lut_slots + npl - 1) / npl;
+    const unsigned np1 = npl + 1;
+    memset(out, 0, (size_t)c->num_challenges * np1 * n * 8);
+#define WIRE(col, row) wires[(size_t)(col) * n + (row)]
+    for (unsigned ch = 0; ch < c->num_challenges; ch++) {
+        const uint64_t *d = deltas + 4 * ch;
+        uint64_t *polys = out + (size_t)ch * np1 * n; /* polys[p * n + row] */
+        for (unsigned t = 0; t < lk->num_luts; t++) {
+            const size_t last_lu = lk->lookup_rows[3 * t], last_lut = lk->lookup_rows[3 * t + 1],
+                         first_lut = lk->lookup_rows[3 * t + 2];
+            for (size_t row = first_lut + 1; row-- > last_lut;) {
+                uint64_t inv[num_lut_slots];
+                uint64_t new_re = polys[row + 1];
+                for (unsigned s = 0; s < num_lut_slots; s++) {
+                    const uint64_t inp = WIRE(3 * s, row), outp = WIRE(3 * s + 1, row);
+                    inv[s] = orc_gl_inv(gl_sub(d[2], gl_add(inp, gl_mul(d[0], outp))));
+                    new_re = gl_add(gl_mul(new_re, d[3]), gl_add(inp, gl_mul(d[1], outp)));
+                }
+                polys[row] = orc_gl_canon(new_re);
+                for (unsigned slot = 0; slot < npl; slot++) {
+                    uint64_t sum = slot != 0 ? polys[(size_t)slot * n + row] : polys[(size_t)npl * n + row + 1];
+                    const unsigned hi = (slot + 1) * max_lut_deg < num_lut_slots ? (slot + 1) * max_lut_deg : num_lut_slots;
+                    for (unsigned s = slot * max_lut_deg; s < hi; s++)
+                        sum = gl_add(sum, gl_mul(WIRE(3 * s + 2, row), inv[s]));
+                    polys[(size_t)(slot + 1) * n + row] = orc_gl_canon(sum);
+                }
+            }
+            for (size_t row = last_lut; row-- > last_lu;) {
+                uint64_t inv[num_lu_slots];
+                for (unsigned s = 0; s < num_lu_slots; s++)
+                    inv[s] = orc_gl_inv(gl_sub(d[2], gl_add(WIRE(2 * s, row), gl_mul(d[0], WIRE(2 * s + 1, row)))));
+                for (unsigned slot = 0; slot < npl; slot++) {
+                    const uint64_t prev = slot == 0 ? polys[(size_t)npl * n + row + 1] : polys[(size_t)slot * n + row];
+                    uint64_t sum = 0;
+                    const unsigned hi = (slot + 1) * max_lu_deg < num_lu_slots ? (slot + 1) * max_lu_deg : num_lu_slots;
+                    for (unsigned s = slot * max_lu_deg; s < hi; s++) sum = gl_add(sum, inv[s]);
+                    polys[(size_t)(slot + 1) * n + row] = orc_gl_canon(gl_sub(prev, sum));
+                }
+            }
+        }
+    }
+#undef WIRE
+}
+
+void orc_eval_vanishing_poly_base_lookup(const orc_circuit *c, uint64_t x, uint64_t z_h_x, const uint64_t *constants,
+                                         const uint64_t *wires, const uint64_t *local_zs, const uint64_t *next_zs,
+                                         const uint64_t *partial_products, const uint64_t *s_sigmas,
+                                         const uint64_t *local_lookup_zs, const uint64_t *next_lookup_zs,
+                                         const uint64_t *betas, const uint64_t *gammas, const uint64_t *deltas,
+                                         const uint64_t *alphas, const uint64_t pih[4], uint64_t *res) {
     const unsigned nc = c->num_challenges, nr = c->num_routed_wires, np = c->num_partial_products;
     const unsigned ngc = circuit_num_gate_constraints(c);
-    const unsigned n_terms = nc + nc * (np + 1) + ngc;
+    const int has_lookup = c->lookups != NULL && local_lookup_zs != NULL;
+    const unsigned nlp = has_lookup ? c->lookups->num_lookup_polys : 0;
+    const unsigned n_lookup_terms = has_lookup ? nc * (4 + c->lookups->num_luts + 2 * (nlp - 1)) : 0;
+    const unsigned n_terms = nc + nc * (np + 1) + n_lookup_terms + ngc;
     uint64_t *terms = calloc(n_terms, 8);
     uint64_t *num = malloc(nr * 8), *den = malloc(nr * 8);
     /* L_0(x) = Z_H(x) / (n (x - 1)), zero_poly_coset.rs:93-96 */
@@ -1131,8 +1266,15 @@ void orc_eval_vanishing_poly_base(const orc_circuit *c, uint64_t x, uint64_t z_h
             pp_terms[(size_t)i * (np + 1) + w] = gl_sub(gl_mul(prev, pn), gl_mul(next, pd));
         }
     }
+    /* lookup constraints, vanishing_poly.rs:273-292: after the partial-product terms, challenge by challenge */
+    if (has_lookup) {
+        uint64_t *lt = terms + nc + nc * (np + 1);
+        for (unsigned i = 0; i < nc; i++)
+            lt += lookup_constraints(c, wires, local_lookup_zs + (size_t)i * nlp, next_lookup_zs + (size_t)i * nlp,
+                                     constants + c->num_selectors, deltas + 4 * i, lt);
+    }
     /* gate constraints, vanishing_poly.rs:700-726 */
-    uint64_t *gate_terms = terms + nc + nc * (np + 1);
+    uint64_t *gate_terms = terms + nc + nc * (np + 1) + n_lookup_terms;
     const unsigned prefix = c->num_selectors + c->num_lookup_selectors;
     for (unsigned g = 0; g < c->num_gates; g++) {
         const orc_gate *gt = &c->gates[g];
@@ -1158,6 +1300,17 @@ int orc_compute_quotient_polys(const orc_circuit *c, unsigned rate_bits, const u
                                const uint64_t *zs_leaves, size_t zs_len, const uint64_t *betas,
                                const uint64_t *gammas, const uint64_t *alphas, const uint64_t pih[4],
                                uint64_t *out) {
+    return orc_compute_quotient_polys_lookup(c, rate_bits, cs_leaves, cs_len, wires_leaves, wires_len, zs_leaves, zs_len,
+                                             betas, gammas, NULL, alphas, pih, out);
+}
+
+/* With lookups the third oracle's rows are Z's, partial products, then the lookup polynomials
+ * (lookup_range, circuit_data.rs:582-584). */
+int orc_compute_quotient_polys_lookup(const orc_circuit *c, unsigned rate_bits, const uint64_t *cs_leaves,
+                                      size_t cs_len, const uint64_t *wires_leaves, size_t wires_len,
+                                      const uint64_t *zs_leaves, size_t zs_len, const uint64_t *betas,
+                                      const uint64_t *gammas, const uint64_t *deltas, const uint64_t *alphas,
+                                      const uint64_t pih[4], uint64_t *out) {
     const unsigned qdb = c->quotient_degree_bits, nc = c->num_challenges;
     if (qdb > rate_bits) return 1; /* prover.rs:662-666 */
     const unsigned lg_lde = c->degree_bits + qdb, lg_N = c->degree_bits + rate_bits;
@@ -1183,8 +1336,11 @@ int orc_compute_quotient_polys(const orc_circuit *c, unsigned rate_bits, const u
         const uint64_t *cs = cs_leaves + row * cs_len;
         const uint64_t *zl = zs_leaves + row * zs_len, *zn = zs_leaves + row_next * zs_len;
         uint64_t res[16];
-        orc_eval_vanishing_poly_base(c, x, zh_eval[i % rate], cs, wires_leaves + row * wires_len, zl, zn,
-                                     zl + nc, cs + c->num_constants, betas, gammas, alphas, pih, res);
+        const size_t lk_off = (size_t)nc * (1 + np);
+        const int lk = c->lookups != NULL && deltas != NULL;
+        orc_eval_vanishing_poly_base_lookup(c, x, zh_eval[i % rate], cs, wires_leaves + row * wires_len, zl, zn,
+                                            zl + nc, cs + c->num_constants, lk ? zl + lk_off : NULL,
+                                            lk ? zn + lk_off : NULL, betas, gammas, deltas, alphas, pih, res);
         for (unsigned a = 0; a < nc; a++) out[(size_t)a * lde_size + i] = gl_mul(res[a], zh_inv[i % rate]);
     }
     (void)np;

@@ -127,7 +127,8 @@ void orc_reduce_openings(size_t n_batches, const size_t *n_terms, const uint64_t
 enum { ORC_GATE_NOOP = 0, ORC_GATE_CONSTANT = 1, ORC_GATE_PUBLIC_INPUT = 2, ORC_GATE_ARITHMETIC = 3,
        ORC_GATE_POSEIDON = 4, ORC_GATE_ARITHMETIC_EXT = 5, ORC_GATE_MUL_EXT = 6, ORC_GATE_BASE_SUM_2 = 7,
        ORC_GATE_RANDOM_ACCESS = 8, ORC_GATE_REDUCING = 9, ORC_GATE_REDUCING_EXT = 10, ORC_GATE_POSEIDON_MDS = 11,
-       ORC_GATE_EXPONENTIATION = 12, ORC_GATE_COSET_INTERPOLATION = 13 };
+       ORC_GATE_EXPONENTIATION = 12, ORC_GATE_COSET_INTERPOLATION = 13,
+       ORC_GATE_LOOKUP = 14, ORC_GATE_LOOKUP_TABLE = 15 /* param: index of the table */ };
 typedef struct {
     uint32_t kind;           /* ORC_GATE_* */
     uint32_t param;          /* num_consts (ConstantGate) / num_ops (Arithmetic*) / num_limbs / num_coeffs /
@@ -137,6 +138,17 @@ typedef struct {
     uint32_t selector_index; /* SelectorsInfo.selector_indices[index] */
     uint32_t group_start, group_end; /* SelectorsInfo.groups[selector_index] */
 } orc_gate;
+/* The lookup argument's share of CommonCircuitData / ProverOnlyCircuitData (circuit_data.rs: luts,
+ * num_lookup_polys; circuit_builder.rs:78-90 LookupWire): one LookupGate run + one LookupTableGate run per
+ * table, rows "upside down" (gadgets/lookup.rs:80-160). */
+typedef struct orc_lookups {
+    uint32_t num_luts;
+    const uint32_t *lut_lens;      /* [num_luts] */
+    const uint16_t *const *luts;   /* luts[k] = [lut_lens[k]][2] (input, output) pairs */
+    const uint32_t *lookup_rows;   /* [num_luts][3]: last_lu_row, last_lut_row, first_lut_row */
+    uint32_t num_lookup_polys;     /* per challenge: RE + the partial SLDC polynomials */
+    uint32_t lookup_degree;        /* lookup_accumulator_degree() = quotient_degree_factor - 1 */
+} orc_lookups;
 typedef struct {
     uint32_t degree_bits, quotient_degree_bits;
     uint32_t num_challenges, num_routed_wires, num_wires;
@@ -146,6 +158,7 @@ typedef struct {
     uint32_t num_gates;
     const orc_gate *gates;
     const uint64_t *k_is;    /* [num_routed_wires] */
+    const struct orc_lookups *lookups; /* NULL: the circuit has no lookup tables */
 } orc_circuit;
 unsigned orc_gate_num_constraints(const orc_gate *g);
 void orc_eval_vanishing_poly_base(const orc_circuit *c, uint64_t x, uint64_t z_h_x, const uint64_t *constants,
@@ -160,6 +173,23 @@ int orc_compute_quotient_polys(const orc_circuit *c, unsigned rate_bits, const u
                                uint64_t *out);
 void orc_partial_products_and_zs(const orc_circuit *c, const uint64_t *wires, const uint64_t *sigmas,
                                  const uint64_t *betas, const uint64_t *gammas, uint64_t *out);
+/* ---- lookup argument (plonky2/src/plonk/prover.rs:489-636, vanishing_poly.rs:29-52,330-520) ----
+ * deltas: [num_challenges][4] = (ChallengeA, ChallengeB, ChallengeAlpha, ChallengeDelta) per challenge, i.e. the
+ * reference's flat `deltas` vector (prover.rs:236-248).  The *_lookup forms take the circuit's lookups into
+ * account (c->lookups != NULL); the plain forms above are the same functions with no lookup terms. */
+void orc_lookup_polys(const orc_circuit *c, const uint64_t *wires, const uint64_t *deltas, uint64_t *out);
+uint64_t orc_lut_poly_eval(const orc_circuit *c, unsigned lut_index, const uint64_t deltas4[4]);
+void orc_eval_vanishing_poly_base_lookup(const orc_circuit *c, uint64_t x, uint64_t z_h_x, const uint64_t *constants,
+                                         const uint64_t *wires, const uint64_t *local_zs, const uint64_t *next_zs,
+                                         const uint64_t *partial_products, const uint64_t *s_sigmas,
+                                         const uint64_t *local_lookup_zs, const uint64_t *next_lookup_zs,
+                                         const uint64_t *betas, const uint64_t *gammas, const uint64_t *deltas,
+                                         const uint64_t *alphas, const uint64_t pih[4], uint64_t *res);
+int orc_compute_quotient_polys_lookup(const orc_circuit *c, unsigned rate_bits, const uint64_t *cs_leaves,
+                                      size_t cs_len, const uint64_t *wires_leaves, size_t wires_len,
+                                      const uint64_t *zs_leaves, size_t zs_len, const uint64_t *betas,
+                                      const uint64_t *gammas, const uint64_t *deltas, const uint64_t *alphas,
+                                      const uint64_t pih[4], uint64_t *out);
 
 int orc_num_threads(void);
 

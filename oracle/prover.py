@@ -3,7 +3,7 @@
 CPU restatement of prove_with_partition_witness from the full witness on
 (plonky2/src/plonk/prover.rs:176-398) out of the oracle's pieces, and of
 write_proof_with_public_inputs (plonky2/src/util/serialization/mod.rs:2040-2079).  Same scope as
-the device prover: no lookups, smallest PoW witness, zero-knowledge salt injected.  Parity status: "unpinned" by
+the device prover: lookup argument included, smallest PoW witness, zero-knowledge salt injected.  Parity status: "unpinned" by
 golden data (the reference cannot be built here); pinned structurally by the verifier identity
 (tests/test_plonk_oracle.py) and, for the FRI part, by tests/test_oracle.py.
 """
@@ -49,14 +49,21 @@ def prove(oc, cs_batch, num_constants, wires, sigmas, public_inputs, pih_wires_c
     ch.observe(wb.cap.reshape(-1))
     betas = [ch.get_challenge() for _ in range(nc)]
     gammas = [ch.get_challenge() for _ in range(nc)]
+    # prover.rs:227-243: with lookup tables, 2 nc more challenges; deltas = betas ++ gammas ++ those
+    has_lookup = oc.num_lookup_polys != 0
+    deltas = betas + gammas + [ch.get_challenge() for _ in range(2 * nc)] if has_lookup else None
     zs = oc.partial_products_and_zs(wires, sigmas, betas, gammas)
+    n_zs = zs.shape[0]
+    if has_lookup:   # compute_all_lookup_polys, committed after the Z's and partial products (prover.rs:262-271)
+        zs = np.concatenate([zs, oc.lookup_polys(wires, deltas)])
     zb = oracle.PolynomialBatch.from_values(zs, rate_bits, cap_height, salt=sz)
     ch.observe(zb.cap.reshape(-1))
     alphas = [ch.get_challenge() for _ in range(nc)]
     def unsalted(b):   # get_lde_values strips the salt (fri/oracle.rs:290)
         return np.ascontiguousarray(b.leaves[:, : b.leaves.shape[1] - 4]) if b.blinding else b.leaves
 
-    q = oc.compute_quotient_polys(rate_bits, cs_batch.leaves, unsalted(wb), unsalted(zb), betas, gammas, alphas, pih)
+    q = oc.compute_quotient_polys(rate_bits, cs_batch.leaves, unsalted(wb), unsalted(zb), betas, gammas, alphas, pih,
+                                  deltas=deltas)
     qd = quotient_degree_factor * n
     assert not q[:, qd:].any(), "Quotient has failed, the vanishing polynomial is not divisible by Z_H"
     chunks = np.ascontiguousarray(q[:, :qd]).reshape(nc * quotient_degree_factor, n)
@@ -73,13 +80,17 @@ def prove(oc, cs_batch, num_constants, wires, sigmas, public_inputs, pih_wires_c
     zs_next_eval, quotient_eval = ev(zb, zeta_next), ev(qb, zeta)
     n_pre = num_constants + num_routed_wires
     constants, sig = cs_eval[:num_constants], cs_eval[num_constants:n_pre]
-    plonk_zs, plonk_zs_next, pps = zs_eval[:nc], zs_next_eval[:nc], zs_eval[nc:]
-    for v in (constants, sig, wires_eval, plonk_zs, pps, quotient_eval, plonk_zs_next):
+    plonk_zs, plonk_zs_next, pps = zs_eval[:nc], zs_next_eval[:nc], zs_eval[nc:n_zs]
+    lookup_zs, lookup_zs_next = zs_eval[n_zs:], zs_next_eval[n_zs:]      # lookup_range, circuit_data.rs:582
+    # observe_openings(to_fri_openings()), proof.rs:328-368
+    for v in (constants, sig, wires_eval, plonk_zs, pps, quotient_eval, lookup_zs, plonk_zs_next, lookup_zs_next):
         ch.observe(np.asarray(v).reshape(-1))
     alpha = ch.get_extension_challenge()
     batches = []
-    zeta_polys = list(cs_batch.polynomials[:n_pre]) + list(wb.polynomials) + list(zb.polynomials) + list(qb.polynomials)
-    for point, polys in ((zeta, zeta_polys), (zeta_next, list(zb.polynomials[:nc]))):
+    # fri_all_openings / fri_next_batch_openings, circuit_data.rs:711-747
+    zeta_polys = (list(cs_batch.polynomials[:n_pre]) + list(wb.polynomials) + list(zb.polynomials[:n_zs]) +
+                  list(qb.polynomials) + list(zb.polynomials[n_zs:]))
+    for point, polys in ((zeta, zeta_polys), (zeta_next, list(zb.polynomials[:nc]) + list(zb.polynomials[n_zs:]))):
         terms, w = [], (1, 0)
         for p in polys:
             terms.append((p, w))
@@ -96,10 +107,11 @@ def prove(oc, cs_batch, num_constants, wires, sigmas, public_inputs, pih_wires_c
     out = bytearray()
     for cap in (wb.cap, zb.cap, qb.cap):
         out += np.ascontiguousarray(cap).astype("<u8").tobytes()
-    for v in (constants, sig, wires_eval, plonk_zs, plonk_zs_next, pps, quotient_eval):
+    # write_opening_set, serialization/mod.rs:1495-1508
+    for v in (constants, sig, wires_eval, plonk_zs, plonk_zs_next, lookup_zs, lookup_zs_next, pps, quotient_eval):
         out += np.ascontiguousarray(v).astype("<u8").tobytes()
     out += fri_bytes
     out += np.array([len(public_inputs)] + public_inputs, dtype="<u8").tobytes()
-    return bytes(out), dict(zeta=zeta, alphas=alphas, betas=betas, gammas=gammas, pih=pih, openings=dict(
+    return bytes(out), dict(zeta=zeta, alphas=alphas, betas=betas, gammas=gammas, deltas=deltas, pih=pih, openings=dict(
         constants=constants, plonk_sigmas=sig, wires=wires_eval, plonk_zs=plonk_zs, plonk_zs_next=plonk_zs_next,
-        partial_products=pps, quotient_polys=quotient_eval))
+        partial_products=pps, quotient_polys=quotient_eval, lookup_zs=lookup_zs, lookup_zs_next=lookup_zs_next))

@@ -240,6 +240,10 @@ def lib():
                                        u32, u32, vp, sz, C.POINTER(sz)]),
         # host side of the quotient / prove (include/qp_plonky2_host.h)
         "qp_program_create": (i32, [vp, sz, u32, pp]),
+        "qp_program_create_lookups": (i32, [vp, sz, u32, u32, vp, sz, pp]),
+        "qp_keccak256": (None, [vp, sz, vp]),
+        "qp_circuit_lookup_polys": (i32, [vp, vp, i32, vp, vp, i32]),
+        "qp_circuit_set_lookup_challenges": (i32, [vp, vp]),
         "qp_program_from_dag": (i32, [vp, sz, vp, sz, vp, sz, pp]),
         "qp_program_free": (None, [vp]),
         "qp_program_code": (sz, [vp, pp]),

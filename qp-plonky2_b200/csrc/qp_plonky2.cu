@@ -2547,6 +2547,15 @@ struct qp_circuit {
     uint64_t* zh = nullptr;       // [2][2^qdb]: Z_H on the coset, and its inverses
     unsigned max_emit = 0;        // largest constraint index in the program
     ScaleTables g_inv;            // powers of 1/g up to 2^(degree_bits + qdb)
+    // lookup argument (common_data.luts, prover_data.lookup_rows); none: luts empty
+    std::vector<std::vector<uint16_t>> luts;  // [t][2 len]: (input, output) pairs
+    std::vector<uint32_t> lookup_tables;      // [n_luts][3]: last_lu_row, last_lut_row, first_lut_row
+    uint64_t* d_lookup_tables = nullptr;      // the same on the device (uint32)
+    uint64_t* d_lookup_rows = nullptr;        // uint32 [n_lookup_rows]: row | LookupTableGate row << 31
+    unsigned n_lookup_rows = 0;
+    uint64_t* lookup_consts = nullptr;        // [nc][4 + n_luts]: the challenges' deltas and table evaluations
+    bool lookup_challenges_set = false;
+    unsigned lookup_terms() const { return d.n_luts ? 4 + (unsigned)d.n_luts + 2 * (d.num_lookup_polys - 1) : 0; }
 };
 
 extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circuit** out) {
@@ -2554,11 +2563,31 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
     *out = nullptr;
     if (d->num_challenges == 0 || d->num_challenges > (unsigned)quotient::MAX_CHALLENGES)
         return fail(ctx, QP_ERR_BAD_ARG, "num_challenges must be 1..4");
-    if (d->num_lookup_polys || d->num_lookup_selectors)
-        return fail(ctx, QP_ERR_UNSUPPORTED,
-                    "the circuit declares a lookup argument (num_lookup_polys / num_lookup_selectors): not implemented, "
-                    "prove it with the reference's CPU path");
     if (d->max_degree < 2) return fail(ctx, QP_ERR_BAD_ARG, "max_degree > 1 (util/partial_products.rs:17)");
+    if (d->n_luts || d->num_lookup_polys || d->num_lookup_selectors) {
+        // circuit_builder.rs:1183-1194,1284-1290: 4 + n_luts lookup selectors after the gate selectors; per challenge
+        // RE + ceil(num_lu_slots / lookup_accumulator_degree) partial polynomials, lookup_accumulator_degree =
+        // quotient_degree_factor - 1 (circuit_data.rs:557-559) = max_degree - 1 here
+        const unsigned lu_slots = d->num_routed_wires / 2, lut_slots = d->num_routed_wires / 3;
+        if (!d->n_luts || !d->luts || d->max_degree < 3 || lut_slots == 0 ||
+            d->num_lookup_selectors != 4 + d->n_luts ||
+            d->num_lookup_polys != 1 + (lu_slots + d->max_degree - 2) / (d->max_degree - 1) ||
+            (size_t)d->num_selectors + d->num_lookup_selectors > d->num_constants)
+            return fail(ctx, QP_ERR_BAD_ARG, "inconsistent lookup declaration (num_lookup_polys / num_lookup_selectors / luts)");
+        const size_t n_rows = (size_t)1 << d->degree_bits;
+        for (size_t t = 0; t < d->n_luts; t++) {
+            const qp_lookup_table& lt = d->luts[t];
+            if (!lt.table || !lt.len) return fail(ctx, QP_ERR_BAD_ARG, "Empty LUTs are not supported.");
+            // the rows are upside down: LookupGate rows [last_lu_row, last_lut_row), LookupTableGate rows
+            // [last_lut_row, first_lut_row] holding the table, and the row after them is read (prover.rs:553,580)
+            if (!(lt.last_lu_row <= lt.last_lut_row && lt.last_lut_row <= lt.first_lut_row && (size_t)lt.first_lut_row + 1 < n_rows) ||
+                lt.first_lut_row - lt.last_lut_row + 1 != (lt.len + lut_slots - 1) / lut_slots)
+                return fail(ctx, QP_ERR_BAD_ARG, "lookup rows inconsistent with the table");
+            for (size_t u = 0; u < d->n_luts; u++)   // the row after a table belongs to no table (the builder's NoopGate)
+                if (d->luts[u].last_lu_row <= lt.first_lut_row + 1 && lt.first_lut_row + 1 <= d->luts[u].first_lut_row && u != t)
+                    return fail(ctx, QP_ERR_BAD_ARG, "lookup tables' rows overlap");
+        }
+    }
     if (d->num_routed_wires == 0 || d->num_routed_wires > d->num_wires || !d->k_is)
         return fail(ctx, QP_ERR_BAD_ARG, "bad wire counts");
     // num_partial_products(n, max_degree) = ceil(n / max_degree) - 1, util/partial_products.rs:41-48
@@ -2575,6 +2604,7 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
     c->ctx = ctx;
     c->d = *d;
     c->d.k_is = c->d.sigmas = c->d.program = c->d.pool = nullptr;  // the caller's host pointers die with the call
+    c->d.luts = nullptr;
     struct Guard {  // every early return below releases what has been allocated so far
         qp_circuit* c;
         ~Guard() {
@@ -2650,6 +2680,25 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
         zh[rate + k] = gl::host_pow(zh[k], gl::P - 2);
     }
     CUDA_TRY(ctx, cudaMemcpyAsync(c->zh, zh.data(), zh.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<uint32_t> lookup_rows;
+    if (d->n_luts) {
+        for (size_t t = 0; t < d->n_luts; t++) {
+            const qp_lookup_table& lt = d->luts[t];
+            c->luts.emplace_back(lt.table, lt.table + 2 * lt.len);
+            c->lookup_tables.insert(c->lookup_tables.end(), {lt.last_lu_row, lt.last_lut_row, lt.first_lut_row});
+            for (uint32_t r = lt.last_lu_row; r <= lt.first_lut_row; r++)
+                lookup_rows.push_back(r | (r >= lt.last_lut_row ? 1u << 31 : 0u));
+        }
+        c->n_lookup_rows = (unsigned)lookup_rows.size();
+        rc = dev_alloc(ctx, &c->d_lookup_tables, (c->lookup_tables.size() + 1) / 2);
+        if (!rc) rc = dev_alloc(ctx, &c->d_lookup_rows, (lookup_rows.size() + 1) / 2);
+        if (!rc) rc = dev_alloc(ctx, &c->lookup_consts, (size_t)d->num_challenges * (4 + d->n_luts));
+        if (rc) return rc;
+        CUDA_TRY(ctx, cudaMemcpyAsync(c->d_lookup_tables, c->lookup_tables.data(), c->lookup_tables.size() * 4,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(c->d_lookup_rows, lookup_rows.data(), lookup_rows.size() * 4, cudaMemcpyHostToDevice,
+                                      ctx->stream));
+    }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors die here
     if (d->sigmas) {
         const uint64_t* dev = nullptr;
@@ -2667,6 +2716,7 @@ extern "C" int qp_circuit_create(qp_ctx* ctx, const qp_circuit_desc* d, qp_circu
     if (rc) return rc;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     c->d.k_is = c->d.sigmas = c->d.program = c->d.pool = nullptr;
+    c->d.luts = nullptr;
     guard.c = nullptr;
     *out = c;
     return QP_OK;
@@ -2719,6 +2769,9 @@ extern "C" void qp_circuit_free(qp_circuit* c) {
     dev_free(c->ctx, (uint64_t*)c->seg_off);
     dev_free(c->ctx, c->pool);
     dev_free(c->ctx, c->zh);
+    dev_free(c->ctx, c->d_lookup_tables);
+    dev_free(c->ctx, c->d_lookup_rows);
+    dev_free(c->ctx, c->lookup_consts);
     cudaStreamSynchronize(c->ctx->stream);
     dev_free(c->ctx, c->g_inv.lo);
     dev_free(c->ctx, c->g_inv.hi);
@@ -2786,6 +2839,87 @@ extern "C" int qp_circuit_partial_products_and_zs(qp_circuit* c, const uint64_t*
     return rc;
 }
 
+// The lookup challenges of the proof in progress and get_lut_poly(t).eval(delta) of every table
+// (vanishing_poly.rs:29-52, prover.rs:687-716): the table's combos input + b output, padded with its first entry
+// to whole LookupTableGate rows, are the coefficients in reverse order -- a Horner pass in table order.
+static int lookup_set_challenges(qp_circuit* c, const uint64_t* deltas) {
+    qp_ctx* ctx = c->ctx;
+    const qp_circuit_desc& d = c->d;
+    if (!d.n_luts) return fail(ctx, QP_ERR_BAD_ARG, "the circuit has no lookup tables");
+    if (!deltas) return fail(ctx, QP_ERR_BAD_ARG, "null argument");
+    const unsigned slots = d.num_routed_wires / 3, w = 4 + (unsigned)d.n_luts;
+    std::vector<uint64_t> consts((size_t)d.num_challenges * w);
+    for (unsigned ch = 0; ch < d.num_challenges; ch++) {
+        uint64_t* k = &consts[(size_t)ch * w];
+        for (int j = 0; j < 4; j++) k[j] = deltas[4 * ch + j] % gl::P;
+        for (size_t t = 0; t < d.n_luts; t++) {
+            const std::vector<uint16_t>& tab = c->luts[t];
+            const size_t len = tab.size() / 2, padded = (slots - len % slots) % slots;
+            uint64_t acc = 0;
+            for (size_t e = 0; e < len + padded; e++) {
+                const size_t q = e < len ? e : 0;
+                const uint64_t combo = (uint64_t)(((unsigned __int128)gl::host_mul(k[1], tab[2 * q + 1]) + tab[2 * q]) % gl::P);
+                acc = (uint64_t)(((unsigned __int128)gl::host_mul(acc, k[3]) + combo) % gl::P);
+            }
+            k[4 + t] = acc;
+        }
+    }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemcpyAsync(c->lookup_consts, consts.data(), consts.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // consts dies here
+    c->lookup_challenges_set = true;
+    return QP_OK;
+}
+
+extern "C" int qp_circuit_set_lookup_challenges(qp_circuit* c, const uint64_t* deltas) {
+    if (!c) return QP_ERR_BAD_ARG;
+    return lookup_set_challenges(c, deltas);
+}
+
+// compute_all_lookup_polys (prover.rs:489-636): out[nc * num_lookup_polys][n] value columns.
+extern "C" int qp_circuit_lookup_polys(qp_circuit* c, const uint64_t* wires, int space, const uint64_t* deltas,
+                                       uint64_t* out, int out_space) {
+    if (!c) return QP_ERR_BAD_ARG;
+    qp_ctx* ctx = c->ctx;
+    if (!wires || !deltas || !out) return fail(ctx, QP_ERR_BAD_ARG, "null argument");
+    int rc = lookup_set_challenges(c, deltas);
+    if (rc) return rc;
+    const qp_circuit_desc& d = c->d;
+    const size_t n = (size_t)1 << d.degree_bits;
+    const size_t out_words = (size_t)d.num_challenges * d.num_lookup_polys * n;
+    TempScope tmp(ctx);
+    const uint64_t* d_wires = nullptr;
+    uint64_t *owned = nullptr, *d_out = out;
+    rc = to_device(ctx, wires, space, (size_t)d.num_routed_wires * n, &d_wires, &owned);  // only routed wires are read
+    if (rc) return rc;
+    tmp.adopt(owned);
+    if (out_space != QP_DEVICE) {
+        rc = tmp.alloc(&d_out, out_words);
+        if (rc) return rc;
+    }
+    quotient::LookupPolyParams p{};
+    p.degree_bits = d.degree_bits;
+    p.nc = d.num_challenges;
+    p.np1 = d.num_lookup_polys;
+    p.num_lu_slots = d.num_routed_wires / 2;
+    p.num_lut_slots = d.num_routed_wires / 3;
+    p.lu_degree = d.max_degree - 1;
+    p.lut_degree = (p.num_lut_slots + p.np1 - 2) / (p.np1 - 1);
+    p.wires = d_wires;
+    p.rows = (const uint32_t*)c->d_lookup_rows;
+    p.n_rows = c->n_lookup_rows;
+    p.tables = (const uint32_t*)c->d_lookup_tables;
+    p.n_luts = (unsigned)d.n_luts;
+    p.consts = c->lookup_consts;
+    p.out = d_out;
+    CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, out_words * 8, ctx->stream));
+    LAUNCH(ctx, quotient::lookup_rows_kernel, cdiv((size_t)p.n_rows * p.nc, 128), 128, 0, p);
+    LAUNCH(ctx, quotient::lookup_chain_kernel, 1, 32, 0, p);
+    if (out_space != QP_DEVICE) rc = copy_out(ctx, out, QP_HOST, d_out, out_words);
+    if (!rc) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
 // compute_quotient_polys (prover.rs:640-866): out[num_challenges][n << qdb] coefficients.
 // The quotient VALUES over the part of the quotient domain the three batches cover (all of it for whole
 // batches; a coset shard's positions for the shards of a multi-GPU commitment -- every term of the vanishing
@@ -2829,7 +2963,21 @@ static int quotient_values(qp_circuit* c, const qp_batch* constants_sigmas, cons
     p.out_leaf_order = shard_layout ? 1 : 0;
     p.out_lg = shard_layout ? ilog2(pos_count) : lg_lde;
     const unsigned base = nc + nc * (np + 1);
-    const unsigned stride = (base > c->max_emit ? base : c->max_emit) + 1;
+    if (d.n_luts) {
+        if (!c->lookup_challenges_set)
+            return fail(ctx, QP_ERR_BAD_ARG, "lookup challenges not set (qp_circuit_set_lookup_challenges / qp_circuit_lookup_polys)");
+        p.n_luts = (unsigned)d.n_luts;
+        p.nlp = d.num_lookup_polys;
+        p.num_selectors = d.num_selectors;
+        p.num_lu_slots = d.num_routed_wires / 2;
+        p.num_lut_slots = d.num_routed_wires / 3;
+        p.lu_degree = d.max_degree - 1;
+        p.lut_degree = (p.num_lut_slots + p.nlp - 2) / (p.nlp - 1);
+        p.lookup_terms = c->lookup_terms();
+        p.lookup_consts = c->lookup_consts;
+    }
+    p.gate_base = base + nc * c->lookup_terms();
+    const unsigned stride = (p.gate_base > c->max_emit ? p.gate_base : c->max_emit) + 1;
     p.apow_stride = stride;
     std::vector<uint64_t> apow((size_t)nc * stride);
     for (unsigned a = 0; a < nc; a++) {
@@ -2860,8 +3008,8 @@ static int quotient_values(qp_circuit* c, const qp_batch* constants_sigmas, cons
     unsigned ny = (unsigned)cdiv((size_t)ctx->sm_count * 8, (size_t)tiles);
     if (ny > units) ny = units;
     if (ny < 1) ny = 1;
-    // a native PoseidonGate is one more partial sum, from its own kernel
-    const unsigned n_parts = ny + (c->native.present ? 1 : 0);
+    // a native PoseidonGate is one more partial sum, from its own kernel; so are the lookup terms
+    const unsigned n_parts = ny + (c->native.present ? 1 : 0) + (d.n_luts ? 1 : 0);
     uint64_t* d_partial = nullptr;
     if (n_parts > 1) {
         rc = tmp.alloc(&d_partial, (size_t)n_parts * out_words);
@@ -2872,6 +3020,8 @@ static int quotient_values(qp_circuit* c, const qp_batch* constants_sigmas, cons
     LAUNCH(ctx, quotient::quotient_kernel, dim3(tiles, ny), quotient::BLOCK, smem, p);
     if (c->native.present)
         LAUNCH(ctx, quotient::poseidon_gate_kernel, cdiv(pos_count, 128), 128, 0, p, c->native, d_partial + (size_t)ny * out_words);
+    if (d.n_luts)
+        LAUNCH(ctx, quotient::lookup_terms_kernel, cdiv(pos_count, 128), 128, 0, p, d_partial + (size_t)(n_parts - 1) * out_words);
     if (n_parts > 1)
         LAUNCH(ctx, quotient::combine_kernel, cdiv(out_words, 256), 256, 0, d_partial, n_parts, nc, p.out_lg,
                d.quotient_degree_bits, p.zh_inv, d_vals, lg_lde, pos_first, p.out_leaf_order);
@@ -2919,7 +3069,7 @@ static int quotient_check_batches(qp_circuit* c, const qp_batch* const bs[3], bo
             return fail(ctx, QP_ERR_BAD_ARG, "the three batches must be the same coset shard");
     }
     if (bs[0]->n_cols < (size_t)d.num_constants + d.num_routed_wires || bs[1]->n_cols < d.num_wires ||
-        bs[2]->n_cols < (size_t)nc + (size_t)nc * np)
+        bs[2]->n_cols < (size_t)nc + (size_t)nc * np + (size_t)nc * d.num_lookup_polys)
         return fail(ctx, QP_ERR_BAD_ARG, "batch has too few polynomials for this circuit");
     return QP_OK;
 }

@@ -6,6 +6,8 @@
 //   eval_vanishing_poly_base_batch              plonky2/src/plonk/vanishing_poly.rs:166-330
 //   check_partial_products                      plonky2/src/util/partial_products.rs:52-95
 //   ZeroPolyOnCoset                             field/src/zero_poly_coset.rs
+//   check_lookup_constraints_batch              plonky2/src/plonk/vanishing_poly.rs:521-680
+//   compute_lookup_polys                        plonky2/src/plonk/prover.rs:489-636
 //   reduce_with_powers_multi                    core/src/plonk_common.rs:68-85
 //
 // B200 formulation.  The three oracles keep their LDE column-major in leaf order (ntt.cuh), so
@@ -116,6 +118,16 @@ struct Params {
     // Whole domain: pos_first = 0, pos_count = 2^lg_lde, out_lg = lg_lde, out_leaf_order = 0 (natural order).
     size_t pos_first, pos_count;
     unsigned out_lg, out_leaf_order;
+    // Lookup argument (n_luts == 0: the circuit has none).  The terms of challenge ch are vanishing terms
+    // base + ch * lookup_terms .. (base = nc + nc (np + 1)); the gate constraints follow them, so gate
+    // constraint k carries alpha^(gate_base + k), gate_base = base + nc * lookup_terms (vanishing_poly.rs:313-318).
+    unsigned n_luts, nlp;              // tables; num_lookup_polys = 1 (RE) + the partial SLDC polynomials
+    unsigned num_selectors;            // the lookup selectors are constants columns num_selectors .. + 4 + n_luts
+    unsigned num_lu_slots, num_lut_slots, lu_degree, lut_degree;
+    unsigned lookup_terms;             // 4 + n_luts + 2 (nlp - 1) per challenge
+    unsigned gate_base;
+    const uint64_t* lookup_consts;     // [nc][4 + n_luts]: ChallengeA, ChallengeB, ChallengeAlpha, ChallengeDelta, then
+                                       // get_lut_poly(t).eval(delta) of every table (prover.rs:687-716)
 };
 
 // shared memory: pool | register file [n_regs][BLOCK].  The register file bounds the points resident
@@ -141,7 +153,6 @@ __global__ void __launch_bounds__(BLOCK, 6) quotient_kernel(Params p) {
     const size_t pos = live ? pos_raw : p.pos_count - 1;   // position inside the shard (what the columns are indexed by)
     const size_t i = brev(p.pos_first + pos, p.lg_lde);    // natural index: the point is g w^i
     const unsigned zi = (unsigned)(i & (((size_t)1 << p.qdb) - 1));
-    const unsigned base = p.nc + p.nc * (p.np + 1);
     uint64_t res[MAX_CHALLENGES], G[MAX_CHALLENGES], h[MAX_CHALLENGES];
 #pragma unroll
     for (int a = 0; a < MAX_CHALLENGES; a++) res[a] = G[a] = h[a] = 0;
@@ -257,7 +268,7 @@ __global__ void __launch_bounds__(BLOCK, 6) quotient_kernel(Params p) {
 #pragma unroll
     for (int a = 0; a < MAX_CHALLENGES; a++)
         if (a < (int)p.nc) {
-            const uint64_t total = gl::add(res[a], gl::mul(G[a], __ldg(&sh_apow[a * p.apow_stride + base])));
+            const uint64_t total = gl::add(res[a], gl::mul(G[a], __ldg(&sh_apow[a * p.apow_stride + p.gate_base])));
             const size_t oi = p.out_leaf_order ? pos : i;
             if (!p.partial_out)
                 p.out[((size_t)a << p.out_lg) + oi] = gl::canon(gl::mul(total, zinv));  // prover.rs:848-853
@@ -349,12 +360,81 @@ __global__ void __launch_bounds__(128) poseidon_gate_kernel(Params p, NativePose
     for (unsigned j = g.group_start; j < g.group_end; j++)
         if (j != g.index) f = gl::mul(f, gl::sub((uint64_t)j, sel));
     if (g.many_selectors) f = gl::mul(f, gl::sub(0xFFFFFFFFull, sel));
-    const unsigned base = p.nc + p.nc * (p.np + 1);
 #pragma unroll
     for (int a = 0; a < MAX_CHALLENGES; a++)
         if (a < (int)p.nc)
             out[((size_t)a << p.out_lg) + (p.out_leaf_order ? pos : i)] =
-                gl::mul(gl::mul(f, h[a]), __ldg(&p.alpha_pows[a * p.apow_stride + base]));
+                gl::mul(gl::mul(f, h[a]), __ldg(&p.alpha_pows[a * p.apow_stride + p.gate_base]));
+}
+
+// ---- lookup argument ---------------------------------------------------------------------------------
+// The lookup terms of the vanishing polynomial (check_lookup_constraints_batch, vanishing_poly.rs:521-680),
+// one thread per point like poseidon_gate_kernel: a partial sum of its own for combine_kernel, so the
+// interpreter kernel's registers stay what the gate program needs.
+__global__ void __launch_bounds__(128) lookup_terms_kernel(Params p, uint64_t* __restrict__ out) {
+    const size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= p.pos_count) return;
+    const size_t n_lde = (size_t)1 << p.lg_lde;
+    const size_t i = brev(p.pos_first + pos, p.lg_lde);
+    const unsigned base = p.nc + p.nc * (p.np + 1);
+    uint64_t res[MAX_CHALLENGES];
+#pragma unroll
+    for (int a = 0; a < MAX_CHALLENGES; a++) res[a] = 0;
+    auto add_term = [&](unsigned t, uint64_t term) {
+#pragma unroll
+        for (int a = 0; a < MAX_CHALLENGES; a++)
+            if (a < (int)p.nc) res[a] = gl::add(res[a], gl::mul(term, __ldg(&p.alpha_pows[a * p.apow_stride + t])));
+    };
+    // challenge by challenge (vanishing_poly.rs:263-283)
+    const size_t pos_next = brev((i + ((size_t)1 << p.qdb)) & (n_lde - 1), p.lg_lde) - p.pos_first;
+    const unsigned num_sldc = p.nlp - 1;
+    const uint64_t* const sel = p.cs + (size_t)p.num_selectors * p.cs_stride + pos;  // column k: sel[k * cs_stride]
+    const uint64_t s_trans_sre = sel[0], s_trans_ldc = sel[p.cs_stride], s_init_sre = sel[2 * p.cs_stride],
+                   s_last_ldc = sel[3 * p.cs_stride];
+    for (unsigned ch = 0; ch < p.nc; ch++) {
+        const uint64_t* const d = p.lookup_consts + (size_t)ch * (4 + p.n_luts);
+        const uint64_t da = d[0], db = d[1], dalpha = d[2], ddelta = d[3];
+        const uint64_t* const z = p.zs + ((size_t)p.nc * (1 + p.np) + (size_t)ch * p.nlp) * p.zs_stride;
+        const uint64_t z_re = z[pos], next_z_re = z[pos_next];
+        unsigned t = base + ch * p.lookup_terms;
+        add_term(t++, gl::mul(s_last_ldc, z[(size_t)num_sldc * p.zs_stride + pos]));   // last LDC
+        add_term(t++, gl::mul(s_init_sre, z[p.zs_stride + pos]));                       // initial Sum
+        add_term(t++, gl::mul(s_init_sre, z_re));                                       // initial RE
+        for (unsigned r = 0; r < p.n_luts; r++)                                         // final RE of every table
+            add_term(t++, gl::mul(sel[(size_t)(4 + r) * p.cs_stride], gl::sub(z_re, d[4 + r])));
+        uint64_t cur = next_z_re;                                                       // RE row transition
+        for (unsigned s = 0; s < p.num_lut_slots; s++)
+            cur = gl::add(gl::mul(cur, ddelta), gl::add(p.wires[(size_t)(3 * s) * p.wires_stride + pos],
+                                                        gl::mul(db, p.wires[(size_t)(3 * s + 1) * p.wires_stride + pos])));
+        add_term(t++, gl::mul(s_trans_sre, gl::sub(z_re, cur)));
+        for (unsigned poly = 0; poly < num_sldc; poly++) {
+            // prod = prod_i f_i and sum = sum_i m_i prod_{j != i} f_j, f_i = alpha - combo_i, built slot by
+            // slot: (prod, sum) <- (prod f, sum f + m prod)
+            uint64_t lut_prod = 1, lut_sum = 0, lu_prod = 1, lu_sum = 0;
+            const unsigned t1 = min((poly + 1) * p.lut_degree, p.num_lut_slots);
+            for (unsigned s = poly * p.lut_degree; s < t1; s++) {
+                const uint64_t* const w = p.wires + (size_t)(3 * s) * p.wires_stride + pos;
+                const uint64_t f = gl::sub(dalpha, gl::add(w[0], gl::mul(da, w[p.wires_stride])));
+                lut_sum = gl::add(gl::mul(lut_sum, f), gl::mul(w[2 * p.wires_stride], lut_prod));
+                lut_prod = gl::mul(lut_prod, f);
+            }
+            const unsigned u1 = min((poly + 1) * p.lu_degree, p.num_lu_slots);
+            for (unsigned s = poly * p.lu_degree; s < u1; s++) {
+                const uint64_t* const w = p.wires + (size_t)(2 * s) * p.wires_stride + pos;
+                const uint64_t f = gl::sub(dalpha, gl::add(w[0], gl::mul(da, w[p.wires_stride])));
+                lu_sum = gl::add(gl::mul(lu_sum, f), lu_prod);
+                lu_prod = gl::mul(lu_prod, f);
+            }
+            // the previous accumulator: the previous polynomial of this row, or the last one of the next row
+            const uint64_t prev = poly == 0 ? z[(size_t)num_sldc * p.zs_stride + pos_next] : z[(size_t)poly * p.zs_stride + pos];
+            const uint64_t diff = gl::sub(z[(size_t)(poly + 1) * p.zs_stride + pos], prev);
+            add_term(t++, gl::mul(s_trans_sre, gl::sub(gl::mul(lut_prod, diff), lut_sum)));
+            add_term(t++, gl::mul(s_trans_ldc, gl::add(gl::mul(lu_prod, diff), lu_sum)));
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < MAX_CHALLENGES; a++)
+        if (a < (int)p.nc) out[((size_t)a << p.out_lg) + (p.out_leaf_order ? pos : i)] = res[a];
 }
 
 // out[a][i] = Z_H(x_i)^-1 * sum_y partial[y][a][i]   (the units of quotient_kernel, summed)
@@ -541,6 +621,83 @@ __global__ void __launch_bounds__(SCAN_BLOCK) perm_finish_kernel(PermParams p, s
                 out[((size_t)p.nc + (size_t)ch * p.np + k) * n + i] = gl::canon(a);
             }
             z = gl::mul(z, v[e]);
+        }
+    }
+}
+
+// ---- lookup polynomials (compute_lookup_polys, plonky2/src/plonk/prover.rs:489-636) ---------------------
+// RE and the partial Sum / LDC polynomials are recurrences down the rows of a table's gates (LookupTableGate
+// rows first_lut_row .. last_lut_row, then LookupGate rows last_lut_row - 1 .. last_lu_row): every row adds
+// its own contribution to the value handed over by the row below it.  The contributions need the field
+// inversions (one per slot) and are independent: phase 1 computes them with one thread per (challenge, row);
+// phase 2 walks the chain, which is then additions and one multiplication per row.
+struct LookupPolyParams {
+    unsigned degree_bits, nc, np1;     // np1 = num_lookup_polys = 1 + num_partial_lookups
+    unsigned num_lu_slots, num_lut_slots, lu_degree, lut_degree;
+    const uint64_t* wires;             // [>= num_routed_wires][n] witness columns
+    const uint32_t* rows;              // [n_rows]: row | (LookupTableGate row ? 1u << 31 : 0), all tables
+    unsigned n_rows;
+    const uint32_t* tables;            // [n_luts][3]: last_lu_row, last_lut_row, first_lut_row
+    unsigned n_luts;
+    const uint64_t* consts;            // [nc][4 + n_luts] (Params::lookup_consts)
+    uint64_t* out;                     // [nc][np1][n], zero outside the tables' rows
+};
+
+// phase 1: out[ch][0][row] = sum_s combo_b(s) delta^(slots - 1 - s) (LookupTableGate rows: what the row adds to
+// delta^slots RE(row + 1)); out[ch][k + 1][row] = the row's share of partial polynomial k: + sum m_s / (alpha -
+// combo_a(s)) over the LookupTableGate slots of k, - sum 1 / (alpha - combo_a(s)) over the LookupGate slots of k.
+__global__ void __launch_bounds__(128) lookup_rows_kernel(LookupPolyParams p) {
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= p.n_rows * p.nc) return;
+    const unsigned ch = id / p.n_rows, code = p.rows[id % p.n_rows];
+    const size_t n = (size_t)1 << p.degree_bits, row = code & 0x7fffffffu;
+    const uint64_t* const d = p.consts + (size_t)ch * (4 + p.n_luts);
+    const uint64_t da = d[0], db = d[1], dalpha = d[2], ddelta = d[3];
+    uint64_t* const out = p.out + (size_t)ch * p.np1 * n + row;
+    auto wire = [&](unsigned c) { return p.wires[(size_t)c * n + row]; };
+    const unsigned npl = p.np1 - 1;
+    if (code >> 31) {
+        uint64_t re = 0;
+        for (unsigned s = 0; s < p.num_lut_slots; s++)
+            re = gl::add(gl::mul(re, ddelta), gl::add(wire(3 * s), gl::mul(db, wire(3 * s + 1))));
+        out[0] = re;
+        for (unsigned k = 0; k < npl; k++) {
+            uint64_t sum = 0;
+            const unsigned hi = min((k + 1) * p.lut_degree, p.num_lut_slots);
+            for (unsigned s = k * p.lut_degree; s < hi; s++)
+                sum = gl::add(sum, gl::mul(wire(3 * s + 2), inverse(gl::sub(dalpha, gl::add(wire(3 * s), gl::mul(da, wire(3 * s + 1)))))));
+            out[(size_t)(k + 1) * n] = sum;
+        }
+    } else {
+        for (unsigned k = 0; k < npl; k++) {
+            uint64_t sum = 0;
+            const unsigned hi = min((k + 1) * p.lu_degree, p.num_lu_slots);
+            for (unsigned s = k * p.lu_degree; s < hi; s++)
+                sum = gl::add(sum, inverse(gl::sub(dalpha, gl::add(wire(2 * s), gl::mul(da, wire(2 * s + 1))))));
+            out[(size_t)(k + 1) * n] = gl::sub(0, sum);
+        }
+    }
+}
+
+// phase 2: one thread per challenge walks the tables in the reference's order, rows downwards:
+// RE(row) = delta^slots RE(row + 1) + share; SLDC_0(row) = SLDC_last(row + 1) + share_0, SLDC_k(row) = SLDC_(k-1)(row)
+// + share_k.  (A circuit's lookup rows are few next to its degree; the chain is serial by definition.)
+__global__ void lookup_chain_kernel(LookupPolyParams p) {
+    const unsigned ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.nc) return;
+    const size_t n = (size_t)1 << p.degree_bits;
+    const unsigned npl = p.np1 - 1;
+    uint64_t* const out = p.out + (size_t)ch * p.np1 * n;
+    const uint64_t delta_pow = gl::pow(p.consts[(size_t)ch * (4 + p.n_luts) + 3], p.num_lut_slots);
+    for (unsigned t = 0; t < p.n_luts; t++) {
+        const size_t last_lu = p.tables[3 * t], last_lut = p.tables[3 * t + 1], first_lut = p.tables[3 * t + 2];
+        for (size_t row = first_lut + 1; row-- > last_lu;) {
+            if (row >= last_lut) out[row] = gl::canon(gl::add(gl::mul(out[row + 1], delta_pow), out[row]));
+            uint64_t acc = out[(size_t)npl * n + row + 1];
+            for (unsigned k = 0; k < npl; k++) {
+                acc = gl::add(acc, out[(size_t)(k + 1) * n + row]);
+                out[(size_t)(k + 1) * n + row] = gl::canon(acc);
+            }
         }
     }
 }

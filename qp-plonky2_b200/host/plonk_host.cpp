@@ -212,6 +212,53 @@ GateInfo gate_info(uint32_t kind, uint32_t param) {
     return {kind, param, 0, 0, 0, ""};
 }
 
+// Keccak-f[1600] / Keccak-256 with the original 0x01 padding (keccak_hash::keccak = tiny-keccak's Keccak::v256):
+// the lut_hash of LookupGate / LookupTableGate (gates/lookup.rs:44-55, gates/lookup_table.rs:50-62).
+void keccak_f(uint64_t st[25]) {
+    static const uint64_t RC[24] = {
+        0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
+        0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+        0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+        0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+        0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+        0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+    static const int ROT[24] = {1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 2, 14, 27, 41, 56, 8, 25, 43, 62, 18, 39, 61, 20, 44};
+    static const int PIL[24] = {10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+    for (int round = 0; round < 24; round++) {
+        uint64_t bc[5];
+        for (int i = 0; i < 5; i++) bc[i] = st[i] ^ st[i + 5] ^ st[i + 10] ^ st[i + 15] ^ st[i + 20];
+        for (int i = 0; i < 5; i++) {
+            const uint64_t t = bc[(i + 4) % 5] ^ ((bc[(i + 1) % 5] << 1) | (bc[(i + 1) % 5] >> 63));
+            for (int j = 0; j < 25; j += 5) st[j + i] ^= t;
+        }
+        uint64_t t = st[1];
+        for (int i = 0; i < 24; i++) {
+            const int j = PIL[i];
+            const uint64_t b = st[j];
+            st[j] = (t << ROT[i]) | (t >> (64 - ROT[i]));
+            t = b;
+        }
+        for (int j = 0; j < 25; j += 5) {
+            for (int i = 0; i < 5; i++) bc[i] = st[j + i];
+            for (int i = 0; i < 5; i++) st[j + i] ^= (~bc[(i + 1) % 5]) & bc[(i + 2) % 5];
+        }
+        st[0] ^= RC[round];
+    }
+}
+
+std::string lut_hash_debug(const qp_lookup_table& t) {  // "{:?}" of [u8; 32]
+    std::vector<uint8_t> bytes;  // input.to_le_bytes() ++ output.to_le_bytes() per entry
+    for (size_t i = 0; i < 2 * t.len; i++) {
+        bytes.push_back((uint8_t)(t.table[i] & 0xff));
+        bytes.push_back((uint8_t)(t.table[i] >> 8));
+    }
+    uint8_t h[32];
+    qp_keccak256(bytes.data(), bytes.size(), h);
+    std::string out = "[";
+    for (int i = 0; i < 32; i++) out += (i ? ", " : "") + std::to_string((unsigned)h[i]);
+    return out + "]";
+}
+
 // F_p^2 = F_p[X]/(X^2 - 7) over recording values (field/src/extension/quadratic.rs:186-199)
 struct ExtVal {
     Val a, b;
@@ -749,13 +796,51 @@ static void compile(Recorder& R, qp_program* out) {
     out->n_regs = n_regs ? n_regs : 1;
 }
 
+extern "C" void qp_keccak256(const uint8_t* data, size_t len, uint8_t out[32]) {
+    uint64_t st[25] = {0};
+    const size_t rate = 136;
+    std::vector<uint8_t> msg(data, data + len);
+    msg.push_back(0x01);
+    while (msg.size() % rate) msg.push_back(0);
+    msg.back() |= 0x80;
+    for (size_t off = 0; off < msg.size(); off += rate) {
+        for (size_t i = 0; i < rate / 8; i++) {
+            uint64_t w = 0;
+            for (int k = 0; k < 8; k++) w |= (uint64_t)msg[off + 8 * i + k] << (8 * k);
+            st[i] ^= w;
+        }
+        keccak_f(st);
+    }
+    for (int i = 0; i < 32; i++) out[i] = (uint8_t)(st[i / 8] >> (8 * (i % 8)));
+}
+
 extern "C" int qp_program_create(const qp_gate_desc* gates, size_t n_gates, unsigned max_degree, qp_program** out) {
-    if (!gates || !n_gates || !out) return QP_ERR_BAD_ARG;
+    return qp_program_create_lookups(gates, n_gates, max_degree, 0, nullptr, 0, out);
+}
+
+extern "C" int qp_program_create_lookups(const qp_gate_desc* gates, size_t n_gates, unsigned max_degree,
+                                         unsigned num_routed_wires, const qp_lookup_table* luts, size_t n_luts,
+                                         qp_program** out) {
+    if (!gates || !n_gates || !out || (n_luts && (!luts || !num_routed_wires))) return QP_ERR_BAD_ARG;
     *out = nullptr;
+    for (size_t t = 0; t < n_luts; t++)
+        if (!luts[t].table || !luts[t].len) return QP_ERR_BAD_ARG;  // "Empty LUTs are not supported."
+    // gates/selectors.rs:27-75: TransSre, TransLdc, InitSre, LastLdc, then one "ends" selector per table
+    const unsigned num_lookup_selectors = n_luts ? 4 + (unsigned)n_luts : 0;
     auto* p = new qp_program();
     std::vector<std::pair<GateInfo, uint32_t>> gs;
     for (size_t i = 0; i < n_gates; i++) {
         GateInfo g = gate_info(gates[i].kind, gates[i].param);
+        if ((gates[i].kind == QP_GATE_LOOKUP || gates[i].kind == QP_GATE_LOOKUP_TABLE) && gates[i].param < n_luts) {
+            const qp_lookup_table& t = luts[gates[i].param];
+            if (gates[i].kind == QP_GATE_LOOKUP)   // lookup.rs:72-77; degree 0, no constants, no constraints
+                g = {gates[i].kind, gates[i].param, 0, 0, 0,
+                     "LookupGate {num_slots: " + std::to_string(num_routed_wires / 2) + ", lut_hash: " + lut_hash_debug(t) + "}"};
+            else                                    // lookup_table.rs:86-92
+                g = {gates[i].kind, gates[i].param, 0, 0, 0,
+                     "LookupTableGate {num_slots: " + std::to_string(num_routed_wires / 3) + ", lut_hash: " + lut_hash_debug(t) +
+                         ", last_lut_row: " + std::to_string(t.last_lut_row) + "}"};
+        }
         if (g.id.empty()) {
             delete p;
             return QP_ERR_BAD_ARG;
@@ -815,7 +900,7 @@ extern "C" int qp_program_create(const qp_gate_desc* gates, size_t n_gates, unsi
             if (j != i) filt = filt * (R.imm(j) - s);
         if (num_selectors > 1) filt = filt * (R.imm(UNUSED_SELECTOR) - s);
         std::vector<Val> cons;
-        eval_gate(R, p->gates[i], num_selectors /* + num_lookup_selectors = 0 */, cons);
+        eval_gate(R, p->gates[i], num_selectors + num_lookup_selectors /* gate.rs:179 */, cons);
         if (!cons.empty()) R.emit_gate(cons, filt);
         else R.memo.clear();
     }

@@ -110,6 +110,10 @@ extern "C" int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* con
     const size_t n = (size_t)1 << d.degree_bits;
     const size_t n_pre = (size_t)d.num_constants + d.num_routed_wires;
     const size_t n_zs = (size_t)nc * (1 + np), n_q = (size_t)nc * qdf;
+    // lookup argument: the RE / partial SLDC polynomials are committed after the Z's and partial products
+    // (prover.rs:265-271; lookup_range, circuit_data.rs:582) and opened at zeta and g zeta
+    const bool has_lookup = d.num_lookup_polys != 0;
+    const size_t n_lk = (size_t)nc * d.num_lookup_polys, n_zs_all = n_zs + n_lk;
     const size_t cap_words = ((size_t)4) << cfg->cap_height;
     unsigned arities[64];
     const unsigned n_rounds = qp_fri_reduction_arity_bits(d.degree_bits, cfg->rate_bits, cfg->cap_height,
@@ -117,10 +121,10 @@ extern "C" int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* con
     const bool zk = wires_salt || zs_salt || quotient_salt;
     if (zk && !(wires_salt && zs_salt && quotient_salt)) return QP_ERR_BLINDING_NO_SALT;
     const size_t hide = zk ? QP_SALT_SIZE : 0;
-    const size_t leaf_lens[4] = {n_pre, d.num_wires + hide, n_zs + hide, n_q + hide};
+    const size_t leaf_lens[4] = {n_pre, d.num_wires + hide, n_zs_all + hide, n_q + hide};
     const size_t fri_len = qp_fri_proof_len(leaf_lens, 4, d.degree_bits + cfg->rate_bits, cfg->rate_bits,
                                             cfg->cap_height, arities, n_rounds, cfg->num_query_rounds);
-    const size_t n_open = n_pre + d.num_wires + n_zs + nc + n_q;
+    const size_t n_open = n_pre + d.num_wires + n_zs_all + nc + n_lk + n_q;
     const size_t total = 8 * (3 * cap_words + 2 * n_open) + fri_len + 8 * (1 + n_public_inputs);
     *len_out = total;
     if (!out) return QP_OK;
@@ -192,11 +196,20 @@ extern "C" int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* con
     std::vector<uint64_t> betas(nc), gammas(nc), alphas(nc);
     for (auto& b : betas) b = qp_challenger_get(&ch);
     for (auto& g : gammas) g = qp_challenger_get(&ch);
+    // prover.rs:227-243: four lookup challenges per challenge; betas and gammas are reused for the first 2 nc
+    std::vector<uint64_t> deltas;
+    if (has_lookup) {
+        deltas = betas;
+        deltas.insert(deltas.end(), gammas.begin(), gammas.end());
+        for (unsigned i = 0; i < 2 * nc; i++) deltas.push_back(qp_challenger_get(&ch));
+    }
     // Z and partial products (prover.rs:250-261), kept on the device
-    QP_STEP(qp_dev_alloc(ctx, n_zs * n, &d_zs));
+    QP_STEP(qp_dev_alloc(ctx, n_zs_all * n, &d_zs));
     QP_STEP(qp_circuit_partial_products_and_zs(circuit, wires, space, betas.data(), gammas.data(), d_zs, QP_DEVICE));
+    if (has_lookup)  // compute_all_lookup_polys, prover.rs:262-263 (also hands the deltas to the quotient evaluation)
+        QP_STEP(qp_circuit_lookup_polys(circuit, wires, space, deltas.data(), d_zs + n_zs * n, QP_DEVICE));
     scopes[1] = tm.lap(ctx);
-    QP_STEP(qp_batch_from_values(ctx, d_zs, QP_DEVICE, n_zs, d.degree_bits, cfg->rate_bits, zk ? 1 : 0, cfg->cap_height,
+    QP_STEP(qp_batch_from_values(ctx, d_zs, QP_DEVICE, n_zs_all, d.degree_bits, cfg->rate_bits, zk ? 1 : 0, cfg->cap_height,
                                  salt_z, 0, 1u << cfg->rate_bits, &zb));
     scopes[2] = tm.lap(ctx);
     QP_STEP(qp_batch_cap(zb, cap.data(), QP_HOST));
@@ -255,7 +268,7 @@ extern "C" int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* con
     const Ext zeta_next{fmul(g, zeta.a), fmul(g, zeta.b)};
     // OpeningSet::new, proof.rs:289-327
     std::vector<uint64_t> cs_eval(2 * qp_batch_leaf_len(constants_sigmas)), w_eval(2 * (size_t)d.num_wires),
-        z_eval(2 * n_zs), zn_eval(2 * n_zs), q_eval(2 * n_q);
+        z_eval(2 * n_zs_all), zn_eval(2 * n_zs_all), q_eval(2 * n_q);
     const uint64_t pz[2] = {zeta.a, zeta.b}, pzn[2] = {zeta_next.a, zeta_next.b};
     QP_STEP(qp_batch_eval_polys(constants_sigmas, pz, cs_eval.data()));
     QP_STEP(qp_batch_eval_polys(wb, pz, w_eval.data()));
@@ -264,19 +277,23 @@ extern "C" int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* con
     QP_STEP(qp_batch_eval_polys(qb, pz, q_eval.data()));
     scopes[5] = tm.lap(ctx);
     // observe_openings(to_fri_openings()), proof.rs:328-368: zeta batch = constants, sigmas, wires,
-    // zs, partial products, quotient polys; zeta_next batch = zs
+    // zs, partial products, quotient polys, lookup_zs; zeta_next batch = zs, lookup_zs
     qp_challenger_observe(&ch, cs_eval.data(), 2 * n_pre);
     qp_challenger_observe(&ch, w_eval.data(), 2 * (size_t)d.num_wires);
     qp_challenger_observe(&ch, z_eval.data(), 2 * (size_t)nc);
     qp_challenger_observe(&ch, z_eval.data() + 2 * nc, 2 * (size_t)nc * np);
     qp_challenger_observe(&ch, q_eval.data(), 2 * n_q);
+    qp_challenger_observe(&ch, z_eval.data() + 2 * n_zs, 2 * n_lk);   // lookup_zs close the zeta batch (proof.rs:330-343)
     qp_challenger_observe(&ch, zn_eval.data(), 2 * (size_t)nc);
+    qp_challenger_observe(&ch, zn_eval.data() + 2 * n_zs, 2 * n_lk);  // zeta_next batch: zs_next, lookup_zs_next
     // write_opening_set, serialization/mod.rs:1495-1508: constants, sigmas, wires, zs, zs_next,
-    // (lookups: none), partial products, quotient polys
+    // lookup_zs, lookup_zs_next, partial products, quotient polys
     put_u64s(bytes, cs_eval.data(), 2 * n_pre);
     put_u64s(bytes, w_eval.data(), 2 * (size_t)d.num_wires);
     put_u64s(bytes, z_eval.data(), 2 * (size_t)nc);
     put_u64s(bytes, zn_eval.data(), 2 * (size_t)nc);
+    put_u64s(bytes, z_eval.data() + 2 * n_zs, 2 * n_lk);   // lookup_zs, lookup_zs_next
+    put_u64s(bytes, zn_eval.data() + 2 * n_zs, 2 * n_lk);
     put_u64s(bytes, z_eval.data() + 2 * nc, 2 * (size_t)nc * np);
     put_u64s(bytes, q_eval.data(), 2 * n_q);
     // prove_openings (fri/oracle.rs:320-358) on get_fri_instance(zeta) (circuit_data.rs:592-612)
@@ -284,19 +301,22 @@ extern "C" int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* con
     const qp_batch* oracles[4] = {constants_sigmas, wb, zb, qb};
     std::vector<qp_opening_term> t0, t1;
     Ext w{1, 0};
-    auto add_terms = [&](std::vector<qp_opening_term>& t, const qp_batch* b, size_t count) {
-        for (size_t i = 0; i < count; i++) {  // reduce_polys: sum_i alpha^i p_i, core/src/reducing.rs:63-72
+    auto add_terms = [&](std::vector<qp_opening_term>& t, const qp_batch* b, size_t first, size_t count) {
+        for (size_t i = first; i < first + count; i++) {  // reduce_polys: sum_i alpha^i p_i, core/src/reducing.rs:63-72
             t.push_back(qp_opening_term{b, i, {w.a, w.b}});
             w = emul(w, alpha);
         }
     };
-    add_terms(t0, oracles[0], n_pre);
-    add_terms(t0, oracles[1], d.num_wires);
-    add_terms(t0, oracles[2], n_zs);
-    add_terms(t0, oracles[3], n_q);
+    // fri_all_openings / fri_next_batch_openings, circuit_data.rs:711-747
+    add_terms(t0, oracles[0], 0, n_pre);
+    add_terms(t0, oracles[1], 0, d.num_wires);
+    add_terms(t0, oracles[2], 0, n_zs);
+    add_terms(t0, oracles[3], 0, n_q);
+    add_terms(t0, oracles[2], n_zs, n_lk);
     const Ext shift0 = w;  // shift_poly: alpha^count, reducing.rs:94-97
     w = Ext{1, 0};
-    add_terms(t1, oracles[2], nc);
+    add_terms(t1, oracles[2], 0, nc);
+    add_terms(t1, oracles[2], n_zs, n_lk);
     const Ext shift1 = w;
     qp_opening_batch ob[2] = {{{zeta.a, zeta.b}, t0.data(), t0.size(), {shift0.a, shift0.b}},
                               {{zeta_next.a, zeta_next.b}, t1.data(), t1.size(), {shift1.a, shift1.b}}};
@@ -354,14 +374,18 @@ extern "C" int qp_mprove(qp_mctx* m, qp_circuit* const* circuits, qp_mbatch* con
     const size_t n = (size_t)1 << d.degree_bits;
     const size_t n_pre = (size_t)d.num_constants + d.num_routed_wires;
     const size_t n_zs = (size_t)nc * (1 + np), n_q = (size_t)nc * qdf;
+    // lookup argument: the RE / partial SLDC polynomials are committed after the Z's and partial products
+    // (prover.rs:265-271; lookup_range, circuit_data.rs:582) and opened at zeta and g zeta
+    const bool has_lookup = d.num_lookup_polys != 0;
+    const size_t n_lk = (size_t)nc * d.num_lookup_polys, n_zs_all = n_zs + n_lk;
     const size_t cap_words = ((size_t)4) << cfg->cap_height;
     unsigned arities[64];
     const unsigned n_rounds = qp_fri_reduction_arity_bits(d.degree_bits, cfg->rate_bits, cfg->cap_height,
                                                           cfg->arity_bits, cfg->final_poly_bits, arities);
-    const size_t leaf_lens[4] = {n_pre, d.num_wires, n_zs, n_q};
+    const size_t leaf_lens[4] = {n_pre, d.num_wires, n_zs_all, n_q};
     const size_t fri_len = qp_fri_proof_len(leaf_lens, 4, d.degree_bits + cfg->rate_bits, cfg->rate_bits,
                                             cfg->cap_height, arities, n_rounds, cfg->num_query_rounds);
-    const size_t n_open = n_pre + d.num_wires + n_zs + nc + n_q;
+    const size_t n_open = n_pre + d.num_wires + n_zs_all + nc + n_lk + n_q;
     const size_t total = 8 * (3 * cap_words + 2 * n_open) + fri_len + 8 * (1 + n_public_inputs);
     *len_out = total;
     if (!out) return QP_OK;
@@ -424,12 +448,23 @@ extern "C" int qp_mprove(qp_mctx* m, qp_circuit* const* circuits, qp_mbatch* con
     std::vector<uint64_t> betas(nc), gammas(nc), alphas(nc);
     for (auto& b : betas) b = qp_challenger_get(&ch);
     for (auto& g : gammas) g = qp_challenger_get(&ch);
+    // prover.rs:227-243: four lookup challenges per challenge; betas and gammas are reused for the first 2 nc
+    std::vector<uint64_t> deltas;
+    if (has_lookup) {
+        deltas = betas;
+        deltas.insert(deltas.end(), gammas.begin(), gammas.end());
+        for (unsigned i = 0; i < 2 * nc; i++) deltas.push_back(qp_challenger_get(&ch));
+    }
     // Z and partial products on device 0 (prover.rs:250-261)
-    QP_STEP(qp_dev_alloc(ctx, n_zs * n, &d_zs));
+    QP_STEP(qp_dev_alloc(ctx, n_zs_all * n, &d_zs));
     QP_STEP(qp_circuit_partial_products_and_zs(circuits[0], wires, QP_HOST, betas.data(), gammas.data(), d_zs, QP_DEVICE));
+    if (has_lookup) {  // on device 0 like the Z's; every shard's quotient evaluation needs the challenges
+        QP_STEP(qp_circuit_lookup_polys(circuits[0], wires, QP_HOST, deltas.data(), d_zs + n_zs * n, QP_DEVICE));
+        for (unsigned e = 1; e < D; e++) QP_STEP(qp_circuit_set_lookup_challenges(circuits[e], deltas.data()));
+    }
     QP_STEP(qp_ctx_synchronize(ctx));
     scopes[1] = tm.lap(ctx);
-    QP_STEP(qp_mbatch_from_device(m, d_zs, 0, n_zs, d.degree_bits, cfg->rate_bits, 0, cfg->cap_height, nullptr, &zb));
+    QP_STEP(qp_mbatch_from_device(m, d_zs, 0, n_zs_all, d.degree_bits, cfg->rate_bits, 0, cfg->cap_height, nullptr, &zb));
     scopes[2] = tm.lap(ctx);
     QP_STEP(qp_mbatch_cap(zb, cap.data()));
     qp_challenger_observe(&ch, cap.data(), cap_words);
@@ -514,8 +549,8 @@ extern "C" int qp_mprove(qp_mctx* m, qp_circuit* const* circuits, qp_mbatch* con
     // every shard holds the full coefficient matrices: device 0 evaluates (proof.rs:289-327)
     const qp_batch *cs0 = qp_mbatch_shard(constants_sigmas, 0), *w0 = qp_mbatch_shard(wb, 0), *z0 = qp_mbatch_shard(zb, 0),
                    *q0 = qp_mbatch_shard(qb, 0);
-    std::vector<uint64_t> cs_eval(2 * qp_batch_leaf_len(cs0)), w_eval(2 * (size_t)d.num_wires), z_eval(2 * n_zs),
-        zn_eval(2 * n_zs), q_eval(2 * n_q);
+    std::vector<uint64_t> cs_eval(2 * qp_batch_leaf_len(cs0)), w_eval(2 * (size_t)d.num_wires), z_eval(2 * n_zs_all),
+        zn_eval(2 * n_zs_all), q_eval(2 * n_q);
     const uint64_t pz[2] = {zeta.a, zeta.b}, pzn[2] = {zeta_next.a, zeta_next.b};
     QP_STEP(qp_batch_eval_polys(cs0, pz, cs_eval.data()));
     QP_STEP(qp_batch_eval_polys(w0, pz, w_eval.data()));
@@ -528,30 +563,36 @@ extern "C" int qp_mprove(qp_mctx* m, qp_circuit* const* circuits, qp_mbatch* con
     qp_challenger_observe(&ch, z_eval.data(), 2 * (size_t)nc);
     qp_challenger_observe(&ch, z_eval.data() + 2 * nc, 2 * (size_t)nc * np);
     qp_challenger_observe(&ch, q_eval.data(), 2 * n_q);
+    qp_challenger_observe(&ch, z_eval.data() + 2 * n_zs, 2 * n_lk);   // lookup_zs close the zeta batch (proof.rs:330-343)
     qp_challenger_observe(&ch, zn_eval.data(), 2 * (size_t)nc);
+    qp_challenger_observe(&ch, zn_eval.data() + 2 * n_zs, 2 * n_lk);  // zeta_next batch: zs_next, lookup_zs_next
     put_u64s(bytes, cs_eval.data(), 2 * n_pre);
     put_u64s(bytes, w_eval.data(), 2 * (size_t)d.num_wires);
     put_u64s(bytes, z_eval.data(), 2 * (size_t)nc);
     put_u64s(bytes, zn_eval.data(), 2 * (size_t)nc);
+    put_u64s(bytes, z_eval.data() + 2 * n_zs, 2 * n_lk);   // lookup_zs, lookup_zs_next
+    put_u64s(bytes, zn_eval.data() + 2 * n_zs, 2 * n_lk);
     put_u64s(bytes, z_eval.data() + 2 * nc, 2 * (size_t)nc * np);
     put_u64s(bytes, q_eval.data(), 2 * n_q);
     const Ext alpha{qp_challenger_get(&ch), qp_challenger_get(&ch)};
     const qp_batch* oracles0[4] = {cs0, w0, z0, q0};
     std::vector<qp_opening_term> t0, t1;
     Ext w{1, 0};
-    auto add_terms = [&](std::vector<qp_opening_term>& t, const qp_batch* b, size_t count) {
-        for (size_t i = 0; i < count; i++) {
+    auto add_terms = [&](std::vector<qp_opening_term>& t, const qp_batch* b, size_t first, size_t count) {
+        for (size_t i = first; i < first + count; i++) {
             t.push_back(qp_opening_term{b, i, {w.a, w.b}});
             w = emul(w, alpha);
         }
     };
-    add_terms(t0, oracles0[0], n_pre);
-    add_terms(t0, oracles0[1], d.num_wires);
-    add_terms(t0, oracles0[2], n_zs);
-    add_terms(t0, oracles0[3], n_q);
+    add_terms(t0, oracles0[0], 0, n_pre);
+    add_terms(t0, oracles0[1], 0, d.num_wires);
+    add_terms(t0, oracles0[2], 0, n_zs);
+    add_terms(t0, oracles0[3], 0, n_q);
+    add_terms(t0, oracles0[2], n_zs, n_lk);
     const Ext shift0 = w;
     w = Ext{1, 0};
-    add_terms(t1, oracles0[2], nc);
+    add_terms(t1, oracles0[2], 0, nc);
+    add_terms(t1, oracles0[2], n_zs, n_lk);
     const Ext shift1 = w;
     qp_opening_batch ob[2] = {{{zeta.a, zeta.b}, t0.data(), t0.size(), {shift0.a, shift0.b}},
                               {{zeta_next.a, zeta_next.b}, t1.data(), t1.size(), {shift1.a, shift1.b}}};

@@ -222,7 +222,7 @@ class ConstraintProgram:
 # ---- gates ------------------------------------------------------------------------------------------
 (GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON, GATE_ARITHMETIC_EXT, GATE_MUL_EXT,
  GATE_BASE_SUM_2, GATE_RANDOM_ACCESS, GATE_REDUCING, GATE_REDUCING_EXT, GATE_POSEIDON_MDS, GATE_EXPONENTIATION,
- GATE_COSET_INTERPOLATION) = range(14)  # qp_plonky2_host.h
+ GATE_COSET_INTERPOLATION, GATE_LOOKUP, GATE_LOOKUP_TABLE) = range(16)  # qp_plonky2_host.h
 
 # Debug rendering of PhantomData<F> inside gate ids: core::any::type_name of the field type.  The
 # field crate's package is `qp-plonky2-field` with no [lib] rename (field/Cargo.toml:2), so the path
@@ -949,6 +949,67 @@ class PoseidonGate(Gate):
         return {w: v.v for w, v in row.items()}
 
 
+def keccak256(data):
+    """keccak_hash::keccak (Keccak-256 with the original 0x01 padding; hashlib's sha3_256 pads with 0x06)."""
+    rc = [0x0000000000000001, 0x0000000000008082, 0x800000000000808a, 0x8000000080008000, 0x000000000000808b,
+          0x0000000080000001, 0x8000000080008081, 0x8000000000008009, 0x000000000000008a, 0x0000000000000088,
+          0x0000000080008009, 0x000000008000000a, 0x000000008000808b, 0x800000000000008b, 0x8000000000008089,
+          0x8000000000008003, 0x8000000000008002, 0x8000000000000080, 0x000000000000800a, 0x800000008000000a,
+          0x8000000080008081, 0x8000000000008080, 0x0000000080000001, 0x8000000080008008]
+    m64 = (1 << 64) - 1
+    rol = lambda x, k: ((x << k) | (x >> (64 - k))) & m64 if k else x
+    msg = bytearray(data) + b"\x01"
+    msg += b"\x00" * (-len(msg) % 136)
+    msg[-1] |= 0x80
+    a = [[0] * 5 for _ in range(5)]   # a[x][y]
+    for off in range(0, len(msg), 136):
+        for i in range(17):
+            a[i % 5][i // 5] ^= int.from_bytes(msg[off + 8 * i: off + 8 * i + 8], "little")
+        for rnd in range(24):
+            c = [a[x][0] ^ a[x][1] ^ a[x][2] ^ a[x][3] ^ a[x][4] for x in range(5)]
+            d = [c[(x - 1) % 5] ^ rol(c[(x + 1) % 5], 1) for x in range(5)]
+            a = [[a[x][y] ^ d[x] for y in range(5)] for x in range(5)]
+            b = [[0] * 5 for _ in range(5)]
+            x, y, cur = 1, 0, a[1][0]
+            b[0][0] = a[0][0]
+            for t in range(24):           # rho + pi along the (x, y) -> (y, 2x + 3y) orbit
+                x, y = y, (2 * x + 3 * y) % 5
+                nxt = a[x][y]
+                b[x][y] = rol(cur, ((t + 1) * (t + 2) // 2) % 64)
+                cur = nxt
+            a = [[b[x][y] ^ ((~b[(x + 1) % 5][y]) & m64 & b[(x + 2) % 5][y]) for y in range(5)] for x in range(5)]
+            a[0][0] ^= rc[rnd]
+    return b"".join(a[i % 5][i // 5].to_bytes(8, "little") for i in range(4))
+
+
+def _lut_hash(lut):
+    """keccak over input.to_le_bytes() ++ output.to_le_bytes() of every entry, rendered like `{:?}` of [u8; 32]
+    (gates/lookup.rs:44-55, gates/lookup_table.rs:50-62)."""
+    data = b"".join(int(i).to_bytes(2, "little") + int(o).to_bytes(2, "little") for i, o in lut)
+    return "[" + ", ".join(str(b) for b in keccak256(data)) + "]"
+
+
+class LookupGate(Gate):  # plonky2/src/gates/lookup.rs: no gate constraints (the lookup argument's terms are global)
+    kind = GATE_LOOKUP
+
+    def __init__(self, num_routed_wires, lut, lut_index):
+        self.num_slots, self.lut, self.param = num_routed_wires // 2, lut, lut_index
+
+    def id(self):
+        return "LookupGate {num_slots: %d, lut_hash: %s}" % (self.num_slots, _lut_hash(self.lut))
+
+
+class LookupTableGate(Gate):  # plonky2/src/gates/lookup_table.rs
+    kind = GATE_LOOKUP_TABLE
+
+    def __init__(self, num_routed_wires, lut, lut_index, last_lut_row):
+        self.num_slots, self.lut, self.param, self.last_lut_row = num_routed_wires // 3, lut, lut_index, last_lut_row
+
+    def id(self):
+        return "LookupTableGate {num_slots: %d, lut_hash: %s, last_lut_row: %d}" % (
+            self.num_slots, _lut_hash(self.lut), self.last_lut_row)
+
+
 def sort_gates(gates):
     """circuit_builder.rs:1177-1179: by (degree, id)."""
     return sorted(gates, key=lambda g: (g.degree, g.id()))
@@ -990,11 +1051,16 @@ def log2_ceil(x):
 
 
 class CommonCircuitData:
-    """The fields of CommonCircuitData (circuit_data.rs:412-470) that the permutation argument and
-    the quotient use; no lookups.  `gates` in any order (sorted here like the builder does)."""
+    """The fields of CommonCircuitData (circuit_data.rs:412-470) that the permutation argument, the lookup
+    argument and the quotient use.  `gates` in any order (sorted here like the builder does).  luts: the lookup
+    tables ([(input, output), ...] each); lookup_rows: prover_data.lookup_rows, one (last_lu_row, last_lut_row,
+    first_lut_row) per table (the LookupGate / LookupTableGate of every table must be in `gates`)."""
 
     def __init__(self, degree_bits, gates, num_wires=143, num_routed_wires=80, num_challenges=2,
-                 quotient_degree_factor=8, rate_bits=3, cap_height=4):
+                 quotient_degree_factor=8, rate_bits=3, cap_height=4, luts=None, lookup_rows=None):
+        self.luts = [[(int(i), int(o)) for i, o in t] for t in (luts or [])]
+        self.lookup_rows = [tuple(int(v) for v in r) for r in (lookup_rows or [])]
+        assert len(self.luts) == len(self.lookup_rows)
         self.degree_bits = degree_bits
         self.num_wires, self.num_routed_wires = num_wires, num_routed_wires
         self.num_challenges = num_challenges
@@ -1004,9 +1070,11 @@ class CommonCircuitData:
         # circuit_builder.rs:1180-1181: selector_polynomials(gates, instances, quotient_degree_factor + 1)
         self.selector_indices, self.groups = selectors_info(self.gates, quotient_degree_factor + 1)
         self.num_selectors = len(self.groups)
-        self.num_lookup_selectors = 0
+        # selectors_lookup + selector_ends_lookups, gates/selectors.rs:27-75; circuit_builder.rs:1183-1194,1284-1290
+        self.num_lookup_selectors = 4 + len(self.luts) if self.luts else 0
+        self.num_lookup_polys = -(-(num_routed_wires // 2) // (quotient_degree_factor - 1)) + 1 if self.luts else 0
         self.num_gate_constants = max(g.num_constants for g in self.gates)
-        self.num_constants = self.num_selectors + self.num_gate_constants  # circuit_builder.rs:1196-1197
+        self.num_constants = self.num_selectors + self.num_lookup_selectors + self.num_gate_constants  # circuit_builder.rs:1180-1197
         self.num_gate_constraints = max(g.num_constraints for g in self.gates)
         self.k_is = get_unique_coset_shifts(num_routed_wires)
         # util/partial_products.rs:41-48
@@ -1043,14 +1111,33 @@ class _GateDesc(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("param", C.c_uint32)]
 
 
-def native_constraint_program(gates, max_degree):
-    """The host library's compiler (qp-plonky2_b200/host/plonk_host.cpp, qp_program_create): the
+class _LookupTable(C.Structure):   # qp_lookup_table, include/qp_plonky2_b200.h
+    _fields_ = [("table", C.c_void_p), ("len", C.c_size_t), ("last_lu_row", C.c_uint32), ("last_lut_row", C.c_uint32),
+                ("first_lut_row", C.c_uint32)]
+
+
+def _lookup_tables(luts, lookup_rows):
+    """-> (ctypes array of qp_lookup_table, the numpy tables it points into)."""
+    keep = [np.ascontiguousarray(t, dtype=np.uint16).reshape(-1, 2) for t in luts]
+    arr = (_LookupTable * max(1, len(keep)))()
+    for k, (t, r) in enumerate(zip(keep, lookup_rows)):
+        arr[k] = _LookupTable(t.ctypes.data, len(t), r[0], r[1], r[2])
+    return arr, keep
+
+
+def native_constraint_program(gates, max_degree, num_routed_wires=0, luts=(), lookup_rows=()):
+    """The host library's compiler (qp-plonky2_b200/host/plonk_host.cpp, qp_program_create[_lookups]): the
     program the device runs.  -> dict(code, pool, n_regs, num_selectors, selector_indices, groups,
     order) with gates in the reference's sorted order; `order[i]` = index in `gates` of sorted gate i."""
     from . import lib
     arr = (_GateDesc * len(gates))(*[_GateDesc(g.kind, g.param) for g in gates])
     h = C.c_void_p()
-    rc = lib().qp_program_create(arr, len(gates), max_degree, C.byref(h))
+    if luts:
+        lt, keep = _lookup_tables(luts, lookup_rows)
+        rc = lib().qp_program_create_lookups(arr, len(gates), max_degree, num_routed_wires, lt, len(luts), C.byref(h))
+        del keep
+    else:
+        rc = lib().qp_program_create(arr, len(gates), max_degree, C.byref(h))
     if rc:
         raise ValueError("qp_program_create failed (%d): unsupported gate, or a gate of too high degree" % rc)
     try:
@@ -1085,6 +1172,7 @@ class _Desc(C.Structure):
         ("k_is", C.c_void_p), ("sigmas", C.c_void_p), ("sigmas_space", C.c_int),
         ("program", C.c_void_p), ("program_len", C.c_size_t), ("pool", C.c_void_p), ("pool_len", C.c_size_t),
         ("program_regs", C.c_uint32), ("num_lookup_polys", C.c_uint32), ("num_lookup_selectors", C.c_uint32),
+        ("num_selectors", C.c_uint32), ("luts", C.c_void_p), ("n_luts", C.c_size_t),
     ]
 
 
@@ -1099,7 +1187,8 @@ class Circuit:
         from . import _buf, lib  # late: this module is imported by the package
         self.ctx, self.common = ctx, common
         if program_source == "native":
-            native = native_constraint_program(common.gates, common.quotient_degree_factor + 1)
+            native = native_constraint_program(common.gates, common.quotient_degree_factor + 1, common.num_routed_wires,
+                                               getattr(common, "luts", ()), getattr(common, "lookup_rows", ()))
             assert native["selector_indices"] == common.selector_indices and native["groups"] == common.groups
             code, pool, n_regs = native["code"], native["pool"], native["n_regs"]
         else:
@@ -1121,12 +1210,17 @@ class Circuit:
         d.program, d.program_len = code.ctypes.data, code.size
         d.pool, d.pool_len = pool.ctypes.data, pool.size
         d.program_regs = n_regs
-        # lookup arguments are outside the library's contract: declared so that qp_circuit_create refuses them
+        # the lookup argument's share of the circuit data (common_data.luts, prover_data.lookup_rows)
         d.num_lookup_polys = getattr(common, "num_lookup_polys", 0)
         d.num_lookup_selectors = getattr(common, "num_lookup_selectors", 0)
+        d.num_selectors = common.num_selectors
+        luts = getattr(common, "luts", [])
+        lt, keep_luts = _lookup_tables(luts, getattr(common, "lookup_rows", []))
+        if luts:
+            d.luts, d.n_luts = C.addressof(lt), len(luts)
         self._h = C.c_void_p()
         ctx.check(lib().qp_circuit_create(ctx._h, C.byref(d), C.byref(self._h)))
-        del keep
+        del keep, keep_luts, lt
 
     def partial_products_and_zs(self, wires, betas, gammas, out_device=None):
         """all_wires_permutation_partial_products + Z-first ordering (prover.rs:255-261,402-480):
@@ -1147,11 +1241,34 @@ class Circuit:
             self._h, ptr, space, _np_ptr(b), _np_ptr(g), _np_ptr(out), QP_HOST))
         return out
 
+    def lookup_polys(self, wires, deltas):
+        """compute_all_lookup_polys (prover.rs:489-636) -> value columns [nc * num_lookup_polys][n].
+        deltas: [nc][4] (ChallengeA, ChallengeB, ChallengeAlpha, ChallengeDelta per challenge)."""
+        from . import QP_HOST, _buf, _np_ptr, lib
+        c = self.common
+        ptr, space, keep, shape = _buf(wires)
+        assert shape[0] >= c.num_routed_wires and shape[1] == 1 << c.degree_bits
+        d = np.ascontiguousarray(deltas, dtype=np.uint64)
+        assert d.size == 4 * c.num_challenges
+        out = np.zeros((c.num_challenges * c.num_lookup_polys, 1 << c.degree_bits), dtype=np.uint64)
+        self.ctx.check(lib().qp_circuit_lookup_polys(self._h, ptr, space, _np_ptr(d), _np_ptr(out), QP_HOST))
+        return out
+
+    def set_lookup_challenges(self, deltas):
+        """The lookup challenges the next quotient evaluation uses (qp_circuit_set_lookup_challenges)."""
+        from . import _np_ptr, lib
+        d = np.ascontiguousarray(deltas, dtype=np.uint64)
+        assert d.size == 4 * self.common.num_challenges
+        self.ctx.check(lib().qp_circuit_set_lookup_challenges(self._h, _np_ptr(d)))
+
     def compute_quotient_polys(self, constants_sigmas, wires, zs_partial_products, betas, gammas, alphas,
-                               public_inputs_hash, out_device=None):
-        """compute_quotient_polys (prover.rs:640-866) -> coefficients [nc][n << quotient_degree_bits]."""
+                               public_inputs_hash, out_device=None, deltas=None):
+        """compute_quotient_polys (prover.rs:640-866) -> coefficients [nc][n << quotient_degree_bits].
+        deltas: the lookup challenges of a circuit with lookup tables."""
         from . import QP_DEVICE, QP_HOST, _np_ptr, lib
         c = self.common
+        if deltas is not None:
+            self.set_lookup_challenges(deltas)
         arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in (betas, gammas, alphas, public_inputs_hash)]
         n_lde = 1 << (c.degree_bits + c.quotient_degree_bits)
         if out_device is not None:

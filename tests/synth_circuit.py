@@ -8,6 +8,11 @@ polynomials, sigma polynomials, and a witness.  This module fabricates those dir
     and, with `poseidon=True`, PoseidonGate (the gate recursion circuits spend their rows on;
     degree 7, 123 constraints, its own selector group) -- gate semantics: plonky2/src/gates/*.rs --
     with random gate constants;
+  * with `lookups=True`, two lookup tables with their LookupGate / LookupTableGate rows laid out the way
+    CircuitBuilder::add_all_lookups does (gadgets/lookup.rs:80-160: per table the LookupGate rows, then the
+    LookupTableGate rows holding the table upside down, then a NoopGate row), the wires set_lookup_wires fills
+    (prover.rs:39-141: multiplicities, padding with the table's first entry) and the lookup selectors
+    (gates/selectors.rs:27-75);
   * the witness satisfies every gate; inputs of arithmetic operations are, with probability 1/2,
     COPIES of unconstrained cells elsewhere in the trace, and every copy class is wired as one cycle
     of the permutation sigma (what CircuitBuilder::sigma_vecs derives from `connect` calls,
@@ -40,13 +45,30 @@ def _addmod(a, b):
 class SynthCircuit:
     def __init__(self, degree_bits, seed=1, num_wires=143, num_routed_wires=80, num_challenges=2,
                  quotient_degree_factor=8, rate_bits=3, cap_height=4, poseidon=False, extra_gates=False,
-                 recursion_gates=False):
+                 recursion_gates=False, lookups=False):
         rng = np.random.Generator(np.random.PCG64(seed))
         n = 1 << degree_bits
         nr = num_routed_wires
         self.n = n
         gates = [plonk.NoopGate(), plonk.ConstantGate(2), plonk.PublicInputGate(),
                  plonk.ArithmeticGate.new_from_config(nr)]
+        luts, lookup_rows, lookup_layout = [], [], []
+        if lookups:
+            # two tables; 2.4 and exactly 1 LookupGate rows of lookups (the last row of the first is padded)
+            lu_slots, lut_slots = nr // 2, nr // 3
+            luts = [[(i, (3 * i * i + 5) & 0xffff) for i in range(lut_slots + 11)],
+                    [(2 * i + 1, i ^ 0x5a5a) for i in range(2 * lut_slots + 8)]]
+            row = 1   # row 0 is the PublicInputGate
+            for t, (lut, n_lookups) in enumerate(zip(luts, (2 * lu_slots + lu_slots // 2 - 1, lu_slots))):
+                last_lu = row
+                last_lut = last_lu + -(-n_lookups // lu_slots)
+                first_lut = last_lut + -(-len(lut) // lut_slots) - 1
+                lookup_rows.append((last_lu, last_lut, first_lut))
+                lu_gate, lut_gate = plonk.LookupGate(nr, lut, t), plonk.LookupTableGate(nr, lut, t, last_lut)
+                gates += [lu_gate, lut_gate]
+                lookup_layout.append((lu_gate, lut_gate, n_lookups))
+                row = first_lut + 2   # the NoopGate row after the table
+            assert row <= n, "circuit too small for the lookup rows"
         if poseidon:
             gates.append(plonk.PoseidonGate())
         if extra_gates:   # the extension-field arithmetic and bit-decomposition gates of recursion circuits
@@ -59,9 +81,12 @@ class SynthCircuit:
                       plonk.PoseidonMdsGate(), plonk.ExponentiationGate.new_from_config(num_wires, nr),
                       plonk.CosetInterpolationGate.with_max_degree(4, quotient_degree_factor)]
         self.common = c = plonk.CommonCircuitData(degree_bits, gates, num_wires, nr, num_challenges,
-                                                  quotient_degree_factor, rate_bits, cap_height)
+                                                  quotient_degree_factor, rate_bits, cap_height, luts=luts,
+                                                  lookup_rows=lookup_rows)
         self._oracle_circuit = None
-        idx = {g.id().split(" ")[0].split("(")[0]: i for i, g in enumerate(c.gates)}
+        idx = {g.id().split(" ")[0].split("(")[0]: i for i, g in enumerate(c.gates)
+               if not isinstance(g, (plonk.LookupGate, plonk.LookupTableGate))}
+        gc0 = c.num_selectors + c.num_lookup_selectors   # first gate constant (gate.rs:179)
         # gate per row: mostly arithmetic (and Poseidon), a few of the others; row 0 is the public-input gate
         kinds_p = {"NoopGate": 0.2, "ConstantGate": 0.1, "ArithmeticGate": 0.7}
         if poseidon:
@@ -76,6 +101,10 @@ class SynthCircuit:
             kinds_p.update({k: 0.03 for k in rec_names})
         row_gate = rng.choice([idx[k] for k in kinds_p], size=n, p=list(kinds_p.values()))
         row_gate[0] = idx["PublicInputGate"]
+        for (lu_gate, lut_gate, _), (last_lu, last_lut, first_lut) in zip(lookup_layout, lookup_rows):
+            row_gate[last_lu:last_lut] = c.gates.index(lu_gate)
+            row_gate[last_lut:first_lut + 1] = c.gates.index(lut_gate)
+            row_gate[first_lut + 1] = idx["NoopGate"]
         self.row_gate = row_gate
         # constants: selector polynomials (selectors.rs:141-159), then the gate constants
         consts = np.zeros((c.num_constants, n), dtype=np.uint64)
@@ -88,10 +117,32 @@ class SynthCircuit:
             uses |= (row_gate == idx["ArithmeticExtensionGate"]) | (row_gate == idx["MulExtensionGate"])
         if recursion_gates:
             uses |= row_gate == idx["RandomAccessGate"]
-        consts[c.num_selectors:] = np.where(uses[None, :], gate_consts, 0)
+        consts[gc0:] = np.where(uses[None, :], gate_consts, 0)
+        # lookup selectors: TransSre, TransLdc, InitSre, LastLdc, then one "ends" selector per table
+        for t, (last_lu, last_lut, first_lut) in enumerate(lookup_rows):
+            ls = consts[c.num_selectors:]
+            ls[0, last_lut:first_lut + 1] = 1
+            ls[1, last_lu:last_lut] = 1
+            ls[2, first_lut + 1] = 1
+            ls[3, last_lu] = 1
+            ls[4 + t, last_lut] = 1
         self.constants = consts
         # witness
         wires = rand_felts((num_wires, n), seed + 2)
+        for (_, _, n_lookups), (last_lu, last_lut, first_lut), lut in zip(lookup_layout, lookup_rows, luts):
+            lu_slots, lut_slots = nr // 2, nr // 3
+            wires[:, first_lut + 1] = 0   # "Will ensure the next row's wires will be all zeros", gadgets/lookup.rs:150
+            looked_up = [int(k) for k in rng.integers(0, len(lut), size=n_lookups)]
+            looked_up += [0] * (-n_lookups % lu_slots)            # padding of the last LookupGate row: the first entry
+            mult = np.bincount(looked_up, minlength=len(lut))
+            for k, e in enumerate(looked_up):
+                r, s_ = last_lu + k // lu_slots, k % lu_slots
+                wires[2 * s_, r], wires[2 * s_ + 1, r] = lut[e]
+            for k in range(-(-len(lut) // lut_slots) * lut_slots):
+                r, s_ = first_lut - k // lut_slots, k % lut_slots
+                e = k if k < len(lut) else 0                     # unused slots: the first entry, multiplicity 0
+                wires[3 * s_, r], wires[3 * s_ + 1, r] = lut[e]
+                wires[3 * s_ + 2, r] = mult[k] if k < len(lut) else 0
         # public inputs and their hash (prover.rs:185-186); the PublicInputGate row carries the hash
         self.public_inputs = [int(x) for x in rand_felts((3,), seed + 3)]
         from qp_plonky2_b200 import prover as _prover   # host-side hash_no_pad (qp_hash_no_pad), checked against the oracle's in tests
@@ -101,9 +152,10 @@ class SynthCircuit:
             wires[k, pi_rows] = self.public_inputs_hash[k]
         const_rows = row_gate == idx["ConstantGate"]
         for k in range(2):
-            wires[k, const_rows] = consts[c.num_selectors + k, const_rows]
+            wires[k, const_rows] = consts[gc0 + k, const_rows]
         # copy constraints: free cells = routed wires of Noop rows (unconstrained)
         noop_rows = np.nonzero(row_gate == idx["NoopGate"])[0]
+        noop_rows = noop_rows[~np.isin(noop_rows, [r[2] + 1 for r in lookup_rows])]   # the tables' zero rows stay zero
         arith_rows = np.nonzero(row_gate == idx["ArithmeticGate"])[0]
         sigma_row = np.tile(np.arange(n, dtype=np.int64), (nr, 1))
         sigma_col = np.tile(np.arange(nr, dtype=np.int64)[:, None], (1, n))
@@ -134,14 +186,14 @@ class SynthCircuit:
             sigma_row[tc, tr] = nxt_r
         # arithmetic outputs (arithmetic_base.rs:181)
         if len(arith_rows):
-            c0 = consts[c.num_selectors][arith_rows]
-            c1 = consts[c.num_selectors + 1][arith_rows]
+            c0 = consts[gc0][arith_rows]
+            c1 = consts[gc0 + 1][arith_rows]
             for o in range(num_ops):
                 m0, m1, ad = wires[4 * o][arith_rows], wires[4 * o + 1][arith_rows], wires[4 * o + 2][arith_rows]
                 wires[4 * o + 3][arith_rows] = _addmod(_mulmod(_mulmod(m0, m1), c0), _mulmod(ad, c1))
         if extra_gates:
-            c0 = consts[c.num_selectors].astype(object)
-            c1 = consts[c.num_selectors + 1].astype(object)
+            c0 = consts[gc0].astype(object)
+            c1 = consts[gc0 + 1].astype(object)
             W = wires.astype(object)
             rows = np.nonzero(row_gate == idx["ArithmeticExtensionGate"])[0]
             for o in range(nr // 8):   # arithmetic_extension.rs:92-110
@@ -176,7 +228,7 @@ class SynthCircuit:
                 if name == "RandomAccessGate":
                     row = g.generate([(int(rng.integers(0, g.vec_size)), [felt() for _ in range(g.vec_size)])
                                       for _ in range(g.num_copies)],
-                                     [int(consts[c.num_selectors + i, r]) for i in range(g.num_extra_constants)])
+                                     [int(consts[gc0 + i, r]) for i in range(g.num_extra_constants)])
                 elif name == "ReducingGate":
                     row = g.generate(ext(), ext(), [felt() for _ in range(g.num_coeffs)])
                 elif name == "ReducingExtensionGate":
@@ -222,6 +274,7 @@ class SynthCircuit:
                      "ReducingExtensionGate": oracle.GATE_REDUCING_EXT, "PoseidonMdsGate": oracle.GATE_POSEIDON_MDS,
                      "ExponentiationGate": oracle.GATE_EXPONENTIATION,
                      "CosetInterpolationGate": oracle.GATE_COSET_INTERPOLATION}
+            kinds.update({"LookupGate": oracle.GATE_LOOKUP, "LookupTableGate": oracle.GATE_LOOKUP_TABLE})
             og = []
             for i, g in enumerate(c.gates):
                 name = g.id().split(" ")[0].split("(")[0]
@@ -229,7 +282,7 @@ class SynthCircuit:
                 og.append((kinds[name], param, c.selector_indices[i], c.groups[c.selector_indices[i]]))
             self._oracle_circuit = oracle.Circuit(degree_bits, c.quotient_degree_bits, num_challenges, nr, num_wires,
                                                  c.num_constants, c.num_partial_products, quotient_degree_factor,
-                                                 c.num_selectors, og, c.k_is)
+                                                 c.num_selectors, og, c.k_is, luts=c.luts, lookup_rows=c.lookup_rows)
         return self._oracle_circuit
 
     def constants_sigmas(self):
@@ -320,10 +373,66 @@ class Ext:
         return Ext(self.a * d, -self.b * d)
 
 
-def verifier_plonk_identity(common, openings, zeta, betas, gammas, alphas, pih):
+def check_lookup_constraints(common, wires, local_lookup_zs, next_lookup_zs, lookup_selectors, deltas):
+    """check_lookup_constraints (verifier/src/plonk/vanishing_poly.rs:212-381) for one challenge, over Ext values;
+    deltas = this challenge's (ChallengeA, ChallengeB, ChallengeAlpha, ChallengeDelta).  Written from the reference's
+    extension-field form (sum over i of prod over j != i), independently of the oracle's base-field one."""
+    c = common
+    num_lu_slots, num_lut_slots = c.num_routed_wires // 2, c.num_routed_wires // 3
+    lu_degree = c.quotient_degree_factor - 1            # lookup_accumulator_degree
+    num_sldc = len(local_lookup_zs) - 1
+    lut_degree = -(-num_lut_slots // num_sldc)
+    a, b, alpha, delta = (int(v) for v in deltas)
+    TRANS_SRE, TRANS_LDC, INIT_SRE, LAST_LDC, START_END = 0, 1, 2, 3, 4
+    z_re, next_z_re = local_lookup_zs[0], next_lookup_zs[0]
+    z_x, z_gx = local_lookup_zs[1:], next_lookup_zs[1:]
+    looked = [wires[3 * s] + wires[3 * s + 1] * a for s in range(num_lut_slots)]
+    looking = [wires[2 * s] + wires[2 * s + 1] * a for s in range(num_lu_slots)]
+    lookup = [wires[3 * s] + wires[3 * s + 1] * b for s in range(num_lut_slots)]
+    out = [lookup_selectors[LAST_LDC] * z_x[num_sldc - 1], lookup_selectors[INIT_SRE] * z_x[0],
+           lookup_selectors[INIT_SRE] * z_re]
+    for r in range(START_END, c.num_lookup_selectors):
+        lut = c.luts[r - START_END]
+        # get_lut_poly(..).eval(delta): coefficients = the combos in table order, padded, REVERSED
+        coeffs = [(i + b * o) % P for i, o in lut]
+        coeffs += [coeffs[0]] * ((num_lut_slots - len(lut) % num_lut_slots) % num_lut_slots)
+        coeffs.reverse()
+        ev = sum(cf * pow(delta, k, P) for k, cf in enumerate(coeffs)) % P
+        out.append(lookup_selectors[r] * (z_re - ev))
+    cur = next_z_re
+    for e in lookup:
+        cur = cur * delta + e
+    out.append(lookup_selectors[TRANS_SRE] * (z_re - cur))
+
+    def prod(vals):
+        r = Ext(1)
+        for v in vals:
+            r = r * v
+        return r
+
+    for poly in range(num_sldc):
+        t_rng = range(poly * lut_degree, min((poly + 1) * lut_degree, num_lut_slots))
+        u_rng = range(poly * lu_degree, min((poly + 1) * lu_degree, num_lu_slots))
+        lut_prod = prod(Ext(alpha) - looked[i] for i in t_rng)
+        lu_prod = prod(Ext(alpha) - looking[i] for i in u_rng)
+        lu_sum_prods = Ext(0)
+        for i in u_rng:
+            lu_sum_prods = lu_sum_prods + prod(Ext(alpha) - looking[j] for j in u_rng if j != i)
+        lut_sum_prods_with_mul = Ext(0)
+        for i in t_rng:
+            lut_sum_prods_with_mul = lut_sum_prods_with_mul + wires[3 * i + 2] * prod(
+                Ext(alpha) - looked[j] for j in t_rng if j != i)
+        prev = z_gx[num_sldc - 1] if poly == 0 else z_x[poly - 1]
+        out.append(lookup_selectors[TRANS_SRE] * (lut_prod * (z_x[poly] - prev) - lut_sum_prods_with_mul))
+        out.append(lookup_selectors[TRANS_LDC] * (lu_prod * (z_x[poly] - prev) + lu_sum_prods))
+    return out
+
+
+def verifier_plonk_identity(common, openings, zeta, betas, gammas, alphas, pih, deltas=None):
     """verify_with_challenges' algebraic check (verifier/src/plonk/verifier.rs:60-100): evaluate the
     vanishing polynomial at zeta from the OPENINGS (eval_vanishing_poly, vanishing_poly.rs:38-150)
-    and compare with Z_H(zeta) * sum_i zeta^(n i) quotient_chunk_i(zeta), per challenge."""
+    and compare with Z_H(zeta) * sum_i zeta^(n i) quotient_chunk_i(zeta), per challenge.  deltas: the flat
+    lookup challenges (4 per challenge) of a circuit with lookup tables."""
     c = common
     n = 1 << c.degree_bits
     z = Ext(*zeta)
@@ -346,8 +455,15 @@ def verifier_plonk_identity(common, openings, zeta, betas, gammas, alphas, pih):
             for j in range(w * md, min((w + 1) * md, nr)):
                 pn, pd = pn * num[j], pd * den[j]
             terms.append(accs[w] * pn - accs[w + 1] * pd)
+    nlp = getattr(c, "num_lookup_polys", 0)
+    if nlp:
+        lz, lzn = E(openings["lookup_zs"]), E(openings["lookup_zs_next"])
+        sel = consts[c.num_selectors:c.num_selectors + c.num_lookup_selectors]
+        for i in range(nc):
+            terms += check_lookup_constraints(c, wires, lz[i * nlp:(i + 1) * nlp], lzn[i * nlp:(i + 1) * nlp], sel,
+                                              deltas[4 * i:4 * i + 4])
     gate_terms = [Ext(0)] * c.num_gate_constraints
-    prefix = c.num_selectors
+    prefix = c.num_selectors + getattr(c, "num_lookup_selectors", 0)
     for gi, g in enumerate(c.gates):
         sel = c.selector_indices[gi]
         a, b = c.groups[sel]

@@ -92,19 +92,141 @@ def test_quotient_errors(qp, ctx):
         circ.compute_quotient_polys(g_w, g_w, few, [1, 2], [3, 4], [5, 6], [0, 0, 0, 0])
 
 
-def test_circuit_with_lookups_is_refused(qp, ctx):
-    """A circuit that declares a lookup argument (common_data.num_lookup_polys != 0, prover.rs:489-636) is
-    refused at qp_circuit_create with QP_ERR_UNSUPPORTED -- never proved as if the lookups were not there."""
+def test_inconsistent_lookup_declarations_are_refused(qp, ctx):
+    """qp_circuit_create checks the lookup share of the circuit data against the reference's own formulas
+    (circuit_builder.rs:1183-1194,1284-1290; gadgets/lookup.rs:80-160): lookup polynomials / selectors declared
+    without tables, a wrong polynomial count, table rows that do not hold the table, or quotient evaluation before
+    the lookup challenges are set -- all refused, never proved as if the lookups were not there."""
     sc = SynthCircuit(5, seed=3)
     c = sc.common
     c.num_lookup_polys, c.num_lookup_selectors = 2, 3
     try:
         with pytest.raises(qp.QpError) as e:
             plonk.Circuit(ctx, c, sc.sigmas)
-        assert e.value.code == 8
+        assert e.value.code == 5
     finally:
         c.num_lookup_polys = c.num_lookup_selectors = 0
     plonk.Circuit(ctx, c, sc.sigmas)
+    lk = SynthCircuit(6, seed=4, lookups=True)
+    c = lk.common
+    good_polys, good_rows = c.num_lookup_polys, list(c.lookup_rows)
+    try:
+        c.num_lookup_polys = good_polys + 1
+        with pytest.raises(qp.QpError):
+            plonk.Circuit(ctx, c, lk.sigmas)
+        c.num_lookup_polys = good_polys
+        c.lookup_rows = [(good_rows[0][0], good_rows[0][1], good_rows[0][2] + 1)] + good_rows[1:]   # one row too many
+        with pytest.raises(qp.QpError):
+            plonk.Circuit(ctx, c, lk.sigmas, program_source="twin")
+    finally:
+        c.num_lookup_polys, c.lookup_rows = good_polys, good_rows
+    circ = plonk.Circuit(ctx, c, lk.sigmas)
+    g_w = qp.PolynomialBatch.from_values(ctx, lk.wires, c.rate_bits, False, c.cap_height)
+    g_cs = qp.PolynomialBatch.from_values(ctx, lk.constants_sigmas(), c.rate_bits, False, c.cap_height)
+    with pytest.raises(qp.QpError):     # lookup challenges not set
+        circ.compute_quotient_polys(g_cs, g_w, g_w, [1, 2], [3, 4], [5, 6], [0, 0, 0, 0])
+
+
+@pytest.mark.parametrize("degree_bits,nc,poseidon,device_witness", [(5, 2, False, False), (8, 2, True, False),
+                                                                    (10, 1, False, True), (12, 2, True, True)])
+def test_lookup_polys_match_oracle(qp, ctx, degree_bits, nc, poseidon, device_witness):
+    """compute_all_lookup_polys (plonky2/src/plonk/prover.rs:489-636): RE and the partial Sum / LDC polynomials of
+    two tables, bit for bit against the oracle, from a host and from a device-resident witness."""
+    import torch
+
+    sc = SynthCircuit(degree_bits, seed=30 + degree_bits, num_challenges=nc, poseidon=poseidon, lookups=True)
+    c = sc.common
+    deltas = oracle.rand_felts((4 * nc,), 90 + degree_bits)
+    want = sc.oracle_circuit.lookup_polys(sc.wires, deltas)
+    circ = plonk.Circuit(ctx, c, sc.sigmas)
+    w = torch.from_numpy(np.ascontiguousarray(sc.wires).view(np.int64)).cuda() if device_witness else sc.wires
+    got = circ.lookup_polys(w, deltas)
+    assert got.shape == want.shape == (nc * c.num_lookup_polys, 1 << degree_bits)
+    assert (got == want).all()
+    circ.free()
+
+
+@pytest.mark.parametrize("degree_bits,nc,poseidon,rec", [(5, 2, False, False), (7, 2, True, True), (9, 1, False, False),
+                                                         (10, 2, True, False)])
+def test_quotient_polys_with_lookups_match_oracle(qp, ctx, degree_bits, nc, poseidon, rec):
+    """compute_quotient_polys with the lookup terms of the vanishing polynomial (check_lookup_constraints_batch,
+    vanishing_poly.rs:521-680; the gate constraints' powers of alpha start after them): bit-exact against the oracle."""
+    sc = SynthCircuit(degree_bits, seed=40 + degree_bits, num_challenges=nc, poseidon=poseidon, extra_gates=rec,
+                      recursion_gates=rec, lookups=True)
+    c = sc.common
+    betas, gammas, alphas = (a[:nc] for a in challenges(170 + degree_bits))
+    deltas = np.concatenate([betas, gammas, oracle.rand_felts((2 * nc,), 180 + degree_bits)])
+    oc = sc.oracle_circuit
+    zs = np.concatenate([oc.partial_products_and_zs(sc.wires, sc.sigmas, betas, gammas), oc.lookup_polys(sc.wires, deltas)])
+    o_cs = oracle.PolynomialBatch.from_values(sc.constants_sigmas(), c.rate_bits, c.cap_height)
+    o_w = oracle.PolynomialBatch.from_values(sc.wires, c.rate_bits, c.cap_height)
+    o_z = oracle.PolynomialBatch.from_values(zs, c.rate_bits, c.cap_height)
+    want = oc.compute_quotient_polys(c.rate_bits, o_cs.leaves, o_w.leaves, o_z.leaves, betas, gammas, alphas,
+                                     sc.public_inputs_hash, deltas=deltas)
+    g_cs = qp.PolynomialBatch.from_values(ctx, sc.constants_sigmas(), c.rate_bits, False, c.cap_height)
+    g_w = qp.PolynomialBatch.from_values(ctx, sc.wires, c.rate_bits, False, c.cap_height)
+    g_z = qp.PolynomialBatch.from_values(ctx, zs, c.rate_bits, False, c.cap_height)
+    circ = plonk.Circuit(ctx, c, sc.sigmas)
+    got = circ.compute_quotient_polys(g_cs, g_w, g_z, betas, gammas, alphas, sc.public_inputs_hash, deltas=deltas)
+    assert (got == want).all()
+    # other challenges give another quotient: the terms are really in
+    other = circ.compute_quotient_polys(g_cs, g_w, g_z, betas, gammas, alphas, sc.public_inputs_hash,
+                                        deltas=np.concatenate([betas, gammas, oracle.rand_felts((2 * nc,), 5)]))
+    assert not (other == want).all()
+    for b in (g_cs, g_w, g_z):
+        b.free()
+    circ.free()
+
+
+@pytest.mark.parametrize("degree_bits,pow_bits,queries,poseidon,rec,zk", [
+    (6, 6, 4, False, False, False), (9, 16, 28, True, False, False), (8, 10, 7, True, True, False),
+    (7, 8, 6, True, False, True)])
+def test_full_proof_with_lookups_bytes_match_oracle(qp, ctx, degree_bits, pow_bits, queries, poseidon, rec, zk):
+    """prove() of a circuit with two lookup tables (deltas drawn after the gammas, lookup polynomials committed with
+    the Z's, lookup_zs / lookup_zs_next in the opening set and in both FRI batches): byte for byte the oracle's proof,
+    accepted by the restated verifier; also in zero-knowledge mode."""
+    import verifier
+    from oracle import prover as oprover
+    from qp_plonky2_b200 import prover
+
+    sc = SynthCircuit(degree_bits, seed=80 + degree_bits, poseidon=poseidon, extra_gates=rec, recursion_gates=rec,
+                      lookups=True)
+    c = sc.common
+    circ = plonk.Circuit(ctx, c, sc.sigmas)
+    cfg = prover.FriConfig(c.rate_bits, c.cap_height, pow_bits, 4, 5, queries)
+    pd = prover.ProverData(ctx, circ, sc.constants_sigmas(), cfg)
+    N = (1 << degree_bits) << c.rate_bits
+    salts = [oracle.rand_felts((4, N), 720 + k) for k in range(3)] if zk else None
+    got = prover.prove(pd, sc.wires, sc.public_inputs, salts=salts)
+    o_cs = oracle.PolynomialBatch.from_values(sc.constants_sigmas(), c.rate_bits, c.cap_height)
+    want, _ = oprover.prove(sc.oracle_circuit, o_cs, c.num_constants, sc.wires, sc.sigmas, sc.public_inputs,
+                            degree_bits=degree_bits, num_wires=c.num_wires, num_routed_wires=c.num_routed_wires,
+                            num_challenges=c.num_challenges, quotient_degree_factor=c.quotient_degree_factor,
+                            num_partial_products=c.num_partial_products, rate_bits=c.rate_bits,
+                            cap_height=c.cap_height, proof_of_work_bits=pow_bits, num_query_rounds=queries, salts=salts)
+    assert len(got) == len(want)
+    assert got == want
+    cap = pd.constants_sigmas_commitment.merkle_tree.cap
+    assert verifier.verify(got, c, pd.fri, cap, pd.circuit_digest, hiding=zk) is None
+
+
+def test_large_lookup_proof_is_accepted_by_the_restated_verifier(qp, ctx):
+    """2^13 rows, standard_recursion_config, all gate types + two lookup tables: beyond the size the oracle prover
+    is run at, the restated verifier accepts the device's proof and rejects it after a bit flip in a lookup opening."""
+    import verifier
+    from qp_plonky2_b200 import prover
+
+    sc = SynthCircuit(13, seed=313, poseidon=True, extra_gates=True, recursion_gates=True, lookups=True)
+    c = sc.common
+    circ = plonk.Circuit(ctx, c, sc.sigmas)
+    pd = prover.ProverData(ctx, circ, sc.constants_sigmas())
+    proof = prover.prove(pd, sc.wires, sc.public_inputs)
+    cap = pd.constants_sigmas_commitment.merkle_tree.cap
+    assert verifier.verify(proof, c, pd.fri, cap, pd.circuit_digest) is None
+    at = 3 * (4 << c.cap_height) * 8 + 16 * (c.num_constants + c.num_routed_wires + c.num_wires + 2 * c.num_challenges) + 5
+    bad = bytearray(proof)
+    bad[at] ^= 1
+    assert verifier.verify(bytes(bad), c, pd.fri, cap, pd.circuit_digest) is not None
 
 
 def test_large_circuit_verifier_identity(qp, ctx):
@@ -279,8 +401,9 @@ def test_quotient_from_an_external_recording(qp, ctx, source):
     assert (got == want).all()
 
 
-@pytest.mark.parametrize("degree_bits,poseidon,rec", [(7, False, False), (10, True, False), (12, True, True)])
-def test_multi_device_prove_equals_single_device_prove(qp, ctx, degree_bits, poseidon, rec):
+@pytest.mark.parametrize("degree_bits,poseidon,rec,lookups", [(7, False, False, False), (10, True, False, False),
+                                                              (12, True, True, False), (9, True, False, True)])
+def test_multi_device_prove_equals_single_device_prove(qp, ctx, degree_bits, poseidon, rec, lookups):
     """qp_mprove (BASELINE.json configs[4]: prove() with coset-sharded commitments and quotient evaluation over
     every GPU of the box, one process): the proof is byte for byte the single-device proof, and the restated
     verifier accepts it.  On a one-GPU box the multi-device driver runs with a single device (same code path:
@@ -291,7 +414,8 @@ def test_multi_device_prove_equals_single_device_prove(qp, ctx, degree_bits, pos
 
     D = torch.cuda.device_count()
     D = 8 if D >= 8 else 4 if D >= 4 else 2 if D >= 2 else 1
-    sc = SynthCircuit(degree_bits, seed=500 + degree_bits, poseidon=poseidon, extra_gates=rec, recursion_gates=rec)
+    sc = SynthCircuit(degree_bits, seed=500 + degree_bits, poseidon=poseidon, extra_gates=rec, recursion_gates=rec,
+                      lookups=lookups)
     c = sc.common
     cfg = prover.FriConfig(c.rate_bits, c.cap_height, 10, 4, 5, 12)
     circ = plonk.Circuit(ctx, c, sc.sigmas)

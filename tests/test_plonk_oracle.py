@@ -363,3 +363,144 @@ def test_restated_verifier_accepts_zero_knowledge_oracle_proofs(degree_bits, qdf
     bad = bytearray(zk_proof)
     bad[len(bad) // 2] ^= 2
     assert verifier.verify(bytes(bad), c, fri, cs.cap, digest, hiding=True) is not None
+
+
+# ---------------------------------------------------------------------------------------------
+# lookup argument (gates/lookup.rs, gates/lookup_table.rs, prover.rs:489-636, vanishing_poly.rs:212-381)
+# ---------------------------------------------------------------------------------------------
+def test_keccak256_known_answers():
+    """keccak_hash::keccak = Keccak-256 with the original padding (the lut_hash inside the lookup gates' ids decides
+    the gate ORDER, hence selectors and constraint indices): the published vectors of Keccak-256, for the host
+    library's implementation and for the Python mirror's, plus a multi-block message."""
+    import ctypes as C
+    import qp_plonky2_b200 as qp
+    from qp_plonky2_b200 import plonk
+
+    def native(data):
+        out = (C.c_uint8 * 32)()
+        buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+        qp.lib().qp_keccak256(buf, len(data), out)
+        return bytes(out)
+
+    kats = {b"": "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470",
+            b"abc": "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"}
+    for msg, want in kats.items():
+        assert plonk.keccak256(msg).hex() == want
+        assert native(msg).hex() == want
+    long = bytes(range(256)) * 3   # 768 bytes: six rate blocks
+    assert native(long) == plonk.keccak256(long)
+    assert native(bytes(135)) == plonk.keccak256(bytes(135)) and native(bytes(136)) == plonk.keccak256(bytes(136))
+
+
+def _lookup_polys_bigint(c, wires, deltas):
+    """compute_lookup_polys (prover.rs:489-636) with Python integers, written from the reference loop by loop."""
+    n, nr = 1 << c.degree_bits, c.num_routed_wires
+    num_lu_slots, num_lut_slots = nr // 2, nr // 3
+    max_lu = c.quotient_degree_factor - 1
+    npl = -(-num_lu_slots // max_lu)
+    max_lut = -(-num_lut_slots // npl)
+    W = wires.astype(object)
+    out = []
+    for ch in range(c.num_challenges):
+        a, b, alpha, delta = (int(v) for v in deltas[4 * ch:4 * ch + 4])
+        polys = [[0] * (n + 1) for _ in range(npl + 1)]
+        for last_lu, last_lut, first_lut in c.lookup_rows:
+            for row in range(first_lut, last_lut - 1, -1):
+                looked = [(W[3 * s, row] + a * W[3 * s + 1, row]) % P for s in range(num_lut_slots)]
+                inv = [pow((alpha - v) % P, P - 2, P) for v in looked]
+                lookup = [(W[3 * s, row] + b * W[3 * s + 1, row]) % P for s in range(num_lut_slots)]
+                re = polys[0][row + 1]
+                for e in lookup:
+                    re = (re * delta + e) % P
+                polys[0][row] = re
+                for slot in range(npl):
+                    prev = polys[slot][row] if slot else polys[npl][row + 1]
+                    for s in range(slot * max_lut, min((slot + 1) * max_lut, num_lut_slots)):
+                        prev = (prev + W[3 * s + 2, row] * inv[s]) % P
+                    polys[slot + 1][row] = prev
+            for row in range(last_lut - 1, last_lu - 1, -1):
+                looking = [(W[2 * s, row] + a * W[2 * s + 1, row]) % P for s in range(num_lu_slots)]
+                inv = [pow((alpha - v) % P, P - 2, P) for v in looking]
+                for slot in range(npl):
+                    prev = polys[npl][row + 1] if slot == 0 else polys[slot][row]
+                    tot = sum(inv[slot * max_lu:min((slot + 1) * max_lu, num_lu_slots)]) % P
+                    polys[slot + 1][row] = (prev - tot) % P
+        out += [p[:n] for p in polys]
+    return np.array(out, dtype=object)
+
+
+@pytest.mark.parametrize("degree_bits,poseidon", [(5, False), (7, True)])
+def test_oracle_lookup_polys_match_bigint_restatement(degree_bits, poseidon):
+    """RE and the partial Sum / LDC polynomials of the C oracle == a big-integer restatement; the argument closes
+    (the last partial polynomial is 0 at last_lu_row: Sum(end) == LDC(end)), RE at last_lut_row is the table's
+    polynomial at delta, and a wrong multiplicity breaks the closing."""
+    sc = SynthCircuit(degree_bits, seed=61, poseidon=poseidon, lookups=True)
+    c, oc = sc.common, sc.oracle_circuit
+    assert c.num_lookup_selectors == 6 and c.num_lookup_polys == 1 + -(-(c.num_routed_wires // 2) // 7)
+    deltas = oracle.rand_felts((4 * c.num_challenges,), 62)
+    got = oc.lookup_polys(sc.wires, deltas)
+    want = _lookup_polys_bigint(c, sc.wires, deltas)
+    assert got.shape == want.shape and (got.astype(object) == want).all()
+    nlp = c.num_lookup_polys
+    for ch in range(c.num_challenges):
+        d4 = np.ascontiguousarray(deltas[4 * ch:4 * ch + 4])
+        for t, (last_lu, last_lut, first_lut) in enumerate(c.lookup_rows):
+            assert got[ch * nlp + nlp - 1][last_lu] == 0
+            assert int(got[ch * nlp][last_lut]) == int(oracle.lib().orc_lut_poly_eval(oracle.C.byref(oc.c), t, oracle._ptr(d4)))
+            assert got[ch * nlp][first_lut + 1] == 0 and got[ch * nlp + 1][first_lut + 1] == 0
+    bad = sc.wires.copy()
+    bad[2, c.lookup_rows[0][2]] += 1     # multiplicity of the first entry of table 0
+    assert oc.lookup_polys(bad, deltas)[nlp - 1][c.lookup_rows[0][0]] != 0
+
+
+def test_native_program_orders_lookup_gates_like_the_builder():
+    """The lookup gates have no constraints but their ids (with the Keccak of the table) take part in the sort, and
+    the gates' constants start after the 4 + n_luts lookup selectors (gate.rs:179): the host library's compiler
+    reproduces the Python mirror's selectors and the oracle's gate constraint values."""
+    from qp_plonky2_b200 import plonk
+
+    sc = SynthCircuit(6, seed=63, poseidon=True, lookups=True)
+    c = sc.common
+    nat = plonk.native_constraint_program(c.gates, c.quotient_degree_factor + 1, c.num_routed_wires, c.luts, c.lookup_rows)
+    assert nat["selector_indices"] == c.selector_indices and nat["groups"] == c.groups
+    assert nat["order"] == list(range(len(c.gates)))
+    shuffled = list(reversed(c.gates))
+    nat2 = plonk.native_constraint_program(shuffled, c.quotient_degree_factor + 1, c.num_routed_wires, c.luts, c.lookup_rows)
+    assert [shuffled[i].id() for i in nat2["order"]] == [g.id() for g in c.gates]
+
+
+@pytest.mark.parametrize("degree_bits,poseidon,rec", [(6, False, False), (7, True, True)])
+def test_restated_verifier_accepts_oracle_proofs_with_lookups(degree_bits, poseidon, rec):
+    """prove() with two lookup tables: the restated verifier -- whose lookup constraints are written from the
+    reference's extension-field check_lookup_constraints, independently of the oracle's -- accepts the oracle's
+    proof; it rejects a flipped lookup opening, and it rejects a proof whose witness looks up a pair that is not in
+    the table."""
+    from oracle import prover as oprover
+    import verifier
+
+    sc = SynthCircuit(degree_bits, seed=93, poseidon=poseidon, extra_gates=rec, recursion_gates=rec, lookups=True)
+    c = sc.common
+    cs = oracle.PolynomialBatch.from_values(sc.constants_sigmas(), c.rate_bits, c.cap_height)
+    proof, info = _oracle_prove(sc, proof_of_work_bits=6, num_query_rounds=5)
+    fri = _Fri(c.rate_bits, c.cap_height, 6, 4, 5, 5)
+    digest = oprover.circuit_digest(cs.cap, degree_bits)
+    assert verifier.verify(proof, c, fri, cs.cap, digest) is None
+    nc, nlp = c.num_challenges, c.num_lookup_polys
+    assert info["openings"]["lookup_zs"].shape == (nc * nlp, 2) and len(info["deltas"]) == 4 * nc
+    assert info["deltas"][:2 * nc] == info["betas"] + info["gammas"]
+    cap_bytes = 3 * (4 << c.cap_height) * 8
+    at_lookup = cap_bytes + 16 * (c.num_constants + c.num_routed_wires + c.num_wires + 2 * nc) + 16 * 3
+    for at in (at_lookup, at_lookup + 16 * nc * nlp):       # a lookup_zs opening, a lookup_zs_next opening
+        bad = bytearray(proof)
+        bad[at] ^= 1
+        assert verifier.verify(bytes(bad), c, fri, cs.cap, digest) is not None
+    # a looking pair that is not in the table: the oracle's prover still produces a proof (like the reference's
+    # would from such a witness), and the verifier refuses it
+    wires = sc.wires.copy()
+    wires[1, c.lookup_rows[0][0]] = (int(wires[1, c.lookup_rows[0][0]]) + 1) % P
+    good_wires, sc.wires = sc.wires, wires
+    try:
+        forged, _ = _oracle_prove(sc, proof_of_work_bits=6, num_query_rounds=5)
+    finally:
+        sc.wires = good_wires
+    assert verifier.verify(forged, c, fri, cs.cap, digest) == "vanishing(zeta) != Z_H(zeta) * quotient(zeta)"

@@ -62,13 +62,14 @@ def parse_proof(proof, common, fri, arities, hiding=False):
     cap_words = 4 << fri.cap_height
     r = Reader(proof)
     out = {"caps": [r.u64s(cap_words).reshape(-1, 4) for _ in range(3)]}
+    n_lk = nc * getattr(c, "num_lookup_polys", 0)
     sizes = [("constants", c.num_constants), ("plonk_sigmas", c.num_routed_wires), ("wires", c.num_wires),
-             ("plonk_zs", nc), ("plonk_zs_next", nc), ("partial_products", nc * c.num_partial_products),
-             ("quotient_polys", nc * c.quotient_degree_factor)]
+             ("plonk_zs", nc), ("plonk_zs_next", nc), ("lookup_zs", n_lk), ("lookup_zs_next", n_lk),
+             ("partial_products", nc * c.num_partial_products), ("quotient_polys", nc * c.quotient_degree_factor)]
     out["openings"] = {name: r.ext(k) for name, k in sizes}
     salt = 4 if hiding else 0
-    leaf_lens = [c.num_constants + c.num_routed_wires, c.num_wires + salt, nc * (1 + c.num_partial_products) + salt,
-                 nc * c.quotient_degree_factor + salt]
+    leaf_lens = [c.num_constants + c.num_routed_wires, c.num_wires + salt,
+                 nc * (1 + c.num_partial_products) + n_lk + salt, nc * c.quotient_degree_factor + salt]
     out["commit_caps"] = [r.u64s(cap_words).reshape(-1, 4) for _ in arities]
     rounds = []
     for _ in range(fri.num_query_rounds):
@@ -135,11 +136,16 @@ def verify(proof, common, fri, constants_sigmas_cap, circuit_digest, hiding=Fals
     ch.observe(pr["caps"][0].reshape(-1))
     betas = [ch.get_challenge() for _ in range(nc)]
     gammas = [ch.get_challenge() for _ in range(nc)]
+    has_lookup = getattr(c, "num_lookup_polys", 0) != 0
+    # get_challenges.rs:53-68: four lookup challenges per challenge, the first 2 nc of them are the betas and gammas
+    deltas = betas + gammas + [ch.get_challenge() for _ in range(2 * nc)] if has_lookup else None
     ch.observe(pr["caps"][1].reshape(-1))
     alphas = [ch.get_challenge() for _ in range(nc)]
     ch.observe(pr["caps"][2].reshape(-1))
     zeta = ch.get_extension_challenge()
-    for name in ("constants", "plonk_sigmas", "wires", "plonk_zs", "partial_products", "quotient_polys", "plonk_zs_next"):
+    # observe_openings(to_fri_openings()), plonky2/src/plonk/proof.rs:328-368
+    for name in ("constants", "plonk_sigmas", "wires", "plonk_zs", "partial_products", "quotient_polys", "lookup_zs",
+                 "plonk_zs_next", "lookup_zs_next"):
         ch.observe(op[name].reshape(-1))
     fri_alpha = _e(ch.get_extension_challenge())
     fri_betas = []
@@ -153,7 +159,7 @@ def verify(proof, common, fri, constants_sigmas_cap, circuit_digest, hiding=Fals
     N = 1 << lde_bits
     x_indices = [ch.get_challenge() % N for _ in range(fri.num_query_rounds)]
     # ---- plonk identity at zeta (verifier.rs:60-100) ----
-    if not verifier_plonk_identity(c, op, zeta, betas, gammas, alphas, pih):
+    if not verifier_plonk_identity(c, op, zeta, betas, gammas, alphas, pih, deltas):
         return "vanishing(zeta) != Z_H(zeta) * quotient(zeta)"
     # ---- FRI (fri_verifier.rs:69-118) ----
     if pow_response >> (64 - fri.proof_of_work_bits) if fri.proof_of_work_bits else 0:
@@ -163,8 +169,9 @@ def verify(proof, common, fri, constants_sigmas_cap, circuit_digest, hiding=Fals
     points = [z, z * g]
     # openings per batch, in the order of get_fri_instance (circuit_data.rs:592-612, 741-749)
     batch_open = [[_e(v) for name in ("constants", "plonk_sigmas", "wires", "plonk_zs", "partial_products",
-                                      "quotient_polys") for v in op[name]],
-                  [_e(v) for v in op["plonk_zs_next"]]]
+                                      "quotient_polys", "lookup_zs") for v in op[name]],
+                  [_e(v) for name in ("plonk_zs_next", "lookup_zs_next") for v in op[name]]]
+    n_zs = nc * (1 + c.num_partial_products)
     reduced_openings = [_reduce(vals, fri_alpha) for vals in batch_open]
     caps = [np.asarray(constants_sigmas_cap, dtype=np.uint64).reshape(-1, 4)] + pr["caps"]
     w_lde = root_of_unity(lde_bits)
@@ -177,7 +184,9 @@ def verify(proof, common, fri, constants_sigmas_cap, circuit_digest, hiding=Fals
         # the blinded oracles (wires, zs, quotient: core/src/plonk_common.rs:20-35) lose their salt here
         leaf = [[Ext(int(v)) for v in (evals[: len(evals) - 4] if hiding and k else evals)]
                 for k, (evals, _) in enumerate(initial)]
-        batch_evals = [leaf[0] + leaf[1] + leaf[2] + leaf[3], leaf[2][:nc]]
+        # fri_all_openings / fri_next_batch_openings (circuit_data.rs:711-747): the lookup polynomials of oracle 2
+        # come after the quotient polynomials in the zeta batch, and after the Z's in the zeta_next batch
+        batch_evals = [leaf[0] + leaf[1] + leaf[2][:n_zs] + leaf[3] + leaf[2][n_zs:], leaf[2][:nc] + leaf[2][n_zs:]]
         total = Ext(0)
         for evals, ro, pt in zip(batch_evals, reduced_openings, points):
             num = _reduce(evals, fri_alpha) - ro
