@@ -699,7 +699,10 @@ def run_ours(args):
                              "recursive verifier (22% PoseidonGate rows, four selector groups, copy constraints), "
                              "standard_recursion_config; witness device-resident; best of 4",
                      "runs": bench_prove.measure([12, 13, 14], [] if args.no_cpu else [12], reps=5, device=local,
-                                                 verbose=False, recursion=True)}
+                                                 verbose=False, recursion=True),
+                     # the same circuit with two lookup tables (lookup argument: prover.rs:489-636, vanishing_poly.rs:521-680)
+                     "runs_with_lookups": bench_prove.measure([12], [] if args.no_cpu else [12], reps=5, device=local,
+                                                              verbose=False, recursion=True, lookups=True)}
         except Exception as e:  # the headline metric does not depend on it
             prove = {"error": repr(e)}
 

@@ -5,6 +5,7 @@ is its ctypes face.  Every polynomial-sized step runs on the device:
     wires commitment            PolynomialBatch.from_values            prover.rs:201-214
     transcript                  Challenger (host, core/src/challenger.rs)   prover.rs:216-234
     Z / partial products        Circuit.partial_products_and_zs        prover.rs:250-261
+    lookup polynomials          Circuit.lookup_polys                   prover.rs:262-271,489-636
     their commitment            PolynomialBatch.from_values            prover.rs:275-287
     quotient polynomials        Circuit.compute_quotient_polys         prover.rs:293-307
     quotient commitment         PolynomialBatch.from_coeffs            prover.rs:322-334
@@ -14,8 +15,10 @@ is its ctypes face.  Every polynomial-sized step runs on the device:
 
 Out of scope: circuit building and witness generation -- the caller brings
 the constants/sigmas commitment and the witness matrix, like `prove_with_partition_witness` gets
-them from ProverOnlyCircuitData and the generators.  No lookups.  Zero-knowledge mode (`salts=`): the
-three prover oracles are committed with injected salt columns and leaf_hiding is on.
+them from ProverOnlyCircuitData and the generators.  Lookup tables: the circuit's (CommonCircuitData(luts=...,
+lookup_rows=...)): the deltas are drawn after the gammas and the lookup polynomials are committed with the Z's
+(prover.rs:227-271).  Zero-knowledge mode (`salts=`): the three prover oracles are committed with injected salt
+columns and leaf_hiding is on.
 Deterministic where the reference is not: the PoW witness is the smallest one (serial `find`).
 """
 import ctypes as C

@@ -34,12 +34,33 @@ def rand_felts(shape, seed):
     return np.where(a >= np.uint64(P), a - np.uint64(P), a).astype(np.uint64)
 
 
+_M32 = np.uint64(0xFFFFFFFF)
+_S32 = np.uint64(32)
+
+
 def _mulmod(a, b):
-    return ((a.astype(object) * b.astype(object)) % P).astype(np.uint64)
+    """a * b mod p on uint64 arrays without Python integers: 32-bit halves, then reduce128 (goldilocks_field.rs:
+    390-403) -- the witness of a 2^20-row circuit in seconds."""
+    a, b = np.asarray(a, dtype=np.uint64), np.asarray(b, dtype=np.uint64)
+    a0, a1, b0, b1 = a & _M32, a >> _S32, b & _M32, b >> _S32
+    ll, lh, hl, hh = a0 * b0, a0 * b1, a1 * b0, a1 * b1
+    mid = (ll >> _S32) + (lh & _M32) + (hl & _M32)
+    lo = (ll & _M32) | ((mid & _M32) << _S32)
+    hi = hh + (lh >> _S32) + (hl >> _S32) + (mid >> _S32)
+    hi_hi, hi_lo = hi >> _S32, hi & _M32
+    t = lo - hi_hi
+    t = np.where(lo < hi_hi, t - _M32, t)      # a borrow is -2^64 = -(2^32 - 1)
+    u = hi_lo * _M32
+    r = t + u
+    r = np.where(r < u, r + _M32, r)           # a carry is +2^64 = 2^32 - 1
+    return np.where(r >= np.uint64(P), r - np.uint64(P), r)
 
 
 def _addmod(a, b):
-    return ((a.astype(object) + b.astype(object)) % P).astype(np.uint64)
+    a, b = np.asarray(a, dtype=np.uint64), np.asarray(b, dtype=np.uint64)   # canonical inputs
+    r = a + b
+    r = np.where(r < a, r + _M32, r)
+    return np.where(r >= np.uint64(P), r - np.uint64(P), r)
 
 
 class SynthCircuit:
@@ -251,12 +272,14 @@ class SynthCircuit:
         self.wires = wires
         # sigma polynomials' values: k_is[col] * w^row  (circuit_builder.rs sigma_vecs)
         w = plonk.primitive_root_of_unity(degree_bits)
-        sub = np.ones(n, dtype=object)
-        for i in range(1, n):
-            sub[i] = sub[i - 1] * w % P
-        k_obj = np.array([int(k) for k in c.k_is], dtype=object)
-        self.sigmas = ((k_obj[sigma_col] * sub[sigma_row]) % P).astype(np.uint64)
-        self.subgroup = sub.astype(np.uint64)
+        sub = np.ones(n, dtype=np.uint64)           # w^i by doubling: sub[m .. 2m) = sub[0 .. m) * w^m
+        m, wm = 1, w
+        while m < n:
+            sub[m:2 * m] = _mulmod(sub[:m], np.uint64(wm))
+            m, wm = 2 * m, wm * wm % P
+        k_arr = np.array([int(k) for k in c.k_is], dtype=np.uint64)
+        self.sigmas = _mulmod(k_arr[sigma_col], sub[sigma_row])
+        self.subgroup = sub
 
     @property
     def oracle_circuit(self):

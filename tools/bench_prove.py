@@ -20,7 +20,7 @@ import qp_plonky2_b200 as qp  # noqa: E402
 from qp_plonky2_b200 import plonk, prover  # noqa: E402
 
 
-def measure(degrees, cpu_degrees=(), reps=5, device=0, verbose=True, poseidon=True, recursion=False):
+def measure(degrees, cpu_degrees=(), reps=5, device=0, verbose=True, poseidon=True, recursion=False, lookups=False):
     """-> list of per-degree records (ms = best of reps - 1 timed runs after one warm-up)."""
     import torch
     from synth_circuit import SynthCircuit
@@ -32,7 +32,7 @@ def measure(degrees, cpu_degrees=(), reps=5, device=0, verbose=True, poseidon=Tr
     ctx = qp.Context(device, max_lde_log=max(a.degrees) + 3)
     out = {"prove": []}
     for lg in a.degrees:
-        sc = SynthCircuit(lg, seed=lg, poseidon=poseidon, extra_gates=recursion, recursion_gates=recursion)
+        sc = SynthCircuit(lg, seed=lg, poseidon=poseidon, extra_gates=recursion, recursion_gates=recursion, lookups=lookups)
         c = sc.common
         circ = plonk.Circuit(ctx, c, sc.sigmas)
         pd = prover.ProverData(ctx, circ, sc.constants_sigmas())
@@ -50,6 +50,8 @@ def measure(degrees, cpu_degrees=(), reps=5, device=0, verbose=True, poseidon=Tr
         rec = {"degree_bits": lg, "num_wires": c.num_wires, "gates": [g.id().split(" ")[0].split("(")[0] for g in c.gates],
                "ms": best, "proof_bytes": nbytes, "scopes_ms": best_t,
                "witness": "device-resident"}
+        if lookups:
+            rec["lookup_tables"] = [len(t) for t in c.luts]
         if lg in a.cpu:
             import oracle
             from oracle import prover as oprover
@@ -78,8 +80,10 @@ def main():
     ap.add_argument("--no-poseidon", action="store_true")
     ap.add_argument("--recursion", action="store_true",
                     help="all 14 gate types of a recursive verifier circuit (four selector groups)")
+    ap.add_argument("--lookups", action="store_true", help="two lookup tables with their LookupGate / LookupTableGate rows")
     a = ap.parse_args()
-    print(json.dumps({"prove": measure(a.degrees, a.cpu, a.reps, poseidon=not a.no_poseidon, recursion=a.recursion)}))
+    print(json.dumps({"prove": measure(a.degrees, a.cpu, a.reps, poseidon=not a.no_poseidon, recursion=a.recursion,
+                                       lookups=a.lookups)}))
 
 
 if __name__ == "__main__":
