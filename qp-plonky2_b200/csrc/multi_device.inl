@@ -37,6 +37,10 @@ struct qp_mctx {
     // blocks) is running must get SM slots as blocks retire, not after all of that kernel's blocks
     std::vector<cudaStream_t> prod_stream;
     std::vector<uint8_t> peer_ok;    // [D * D]: device a can load from device b's memory
+    // one memory pool per device, made for this multi-device context and destroyed with it: the coefficient
+    // matrices the peers read are stream-ordered allocations, so their pool must grant the peers access -- and the
+    // device's DEFAULT pool is left alone (contexts created before or after keep a pool nobody else is mapped into)
+    std::vector<cudaMemPool_t> pool;
     std::string err;
 };
 
@@ -54,6 +58,7 @@ extern "C" void qp_mctx_destroy(qp_mctx* m) {
         if (d < m->main_ctx.size()) qp_ctx_destroy(m->main_ctx[d]);
         if (d < m->prod_ctx.size()) qp_ctx_destroy(m->prod_ctx[d]);
         if (d < m->prod_stream.size() && m->prod_stream[d]) cudaStreamDestroy(m->prod_stream[d]);
+        if (d < m->pool.size() && m->pool[d]) cudaMemPoolDestroy(m->pool[d]);
     }
     delete m;
 }
@@ -72,15 +77,30 @@ extern "C" int qp_mctx_create(const int* devices, unsigned n_devices, unsigned m
     m->xfer.assign(n_devices, nullptr);
     m->prod_stream.assign(n_devices, nullptr);
     m->peer_ok.assign((size_t)n_devices * n_devices, 0);
+    m->pool.assign(n_devices, nullptr);
+    const bool own_pools = !getenv("QP_MCTX_DEFAULT_POOL");   // (measurement knob: the devices' default pools instead)
+    for (unsigned d = 0; d < n_devices && own_pools; d++) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = devices[d];
+        if (cudaSetDevice(devices[d]) != cudaSuccess || cudaMemPoolCreate(&m->pool[d], &props) != cudaSuccess) {
+            cudaGetLastError();
+            m->pool[d] = nullptr;
+            qp_mctx_destroy(m);
+            return QP_ERR_CUDA;
+        }
+    }
     for (unsigned d = 0; d < n_devices; d++) {
-        int rc = qp_ctx_create(devices[d], nullptr, max_lde_log, &m->main_ctx[d]);
+        int rc = ctx_create_in_pool(devices[d], nullptr, max_lde_log, m->pool[d], &m->main_ctx[d]);
         int lo_prio = 0, hi_prio = 0;
         if (!rc && (cudaSetDevice(devices[d]) != cudaSuccess ||
                     cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio) != cudaSuccess ||
                     cudaStreamCreateWithPriority(&m->prod_stream[d], cudaStreamNonBlocking, hi_prio) != cudaSuccess ||
                     cudaStreamCreateWithPriority(&m->xfer[d], cudaStreamNonBlocking, hi_prio) != cudaSuccess))
             rc = QP_ERR_CUDA;
-        if (!rc) rc = qp_ctx_create(devices[d], m->prod_stream[d], max_lde_log, &m->prod_ctx[d]);
+        if (!rc) rc = ctx_create_in_pool(devices[d], m->prod_stream[d], max_lde_log, m->pool[d], &m->prod_ctx[d]);
         if (rc) {
             qp_mctx_destroy(m);
             return rc;
@@ -96,8 +116,8 @@ extern "C" int qp_mctx_create(const int* devices, unsigned n_devices, unsigned m
                 if (e != cudaSuccess) cudaGetLastError();  // already enabled is fine
                 bool ok = (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled);
                 // the coefficient matrices are stream-ordered allocations: the OWNER's pool must grant the access too
-                cudaMemPool_t pool;
-                if (ok && cudaDeviceGetDefaultMemPool(&pool, devices[p]) == cudaSuccess) {
+                cudaMemPool_t pool = m->pool[p];
+                if (ok && (pool || cudaDeviceGetDefaultMemPool(&pool, devices[p]) == cudaSuccess)) {
                     cudaMemAccessDesc desc = {};
                     desc.location.type = cudaMemLocationTypeDevice;
                     desc.location.id = devices[d];

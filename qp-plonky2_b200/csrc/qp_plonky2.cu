@@ -40,6 +40,9 @@ struct qp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // stream-ordered allocations come from the device's default pool, or from a pool the owner of the context
+    // made for it (multi-device contexts: a pool of their own that grants the peers access, multi_device.inl)
+    cudaMemPool_t pool = nullptr;
     uint64_t* tw = nullptr;  // tw[(1<<lg)+e] = w_{2^lg}^e, e < 2^lg
     unsigned tw_lg = 0;
     int sm_count = 148;
@@ -100,10 +103,26 @@ static int dev_alloc(qp_ctx* ctx, uint64_t** p, size_t n_words) {
     *p = nullptr;
     if (n_words == 0) return QP_OK;
     cudaSetDevice(ctx->device);  // a handle may be read while another device is current (multi-device callers)
-    cudaError_t e = cudaMallocAsync((void**)p, n_words * 8, ctx->stream);
+    cudaError_t e = ctx->pool ? cudaMallocFromPoolAsync((void**)p, n_words * 8, ctx->pool, ctx->stream)
+                              : cudaMallocAsync((void**)p, n_words * 8, ctx->stream);
     if (e != cudaSuccess) {
-        ctx->err = std::string("cudaMallocAsync: ") + cudaGetErrorString(e);
         cudaGetLastError();
+        // what the device and the pool held when the request failed (an out-of-memory with free memory left points
+        // at the pool's mappings, not at the request)
+        size_t free_b = 0, total_b = 0;
+        uint64_t reserved = 0, used = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        cudaMemPool_t pool = ctx->pool;
+        if (pool || cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        }
+        cudaGetLastError();
+        char buf[256];
+        snprintf(buf, sizeof buf, "cudaMallocAsync of %zu bytes on device %d: %s (device free %zu of %zu MiB; pool reserved %llu MiB, in use %llu MiB)",
+                 n_words * 8, ctx->device, cudaGetErrorString(e), free_b >> 20, total_b >> 20,
+                 (unsigned long long)(reserved >> 20), (unsigned long long)(used >> 20));
+        ctx->err = buf;
         return e == cudaErrorMemoryAllocation ? QP_ERR_TOO_LARGE : QP_ERR_CUDA;
     }
     return QP_OK;
@@ -236,7 +255,11 @@ __global__ void __launch_bounds__(128) permute_states_kernel(uint64_t* states, s
 }
 
 // ---------------------------------------------------------------------------------------------
+static int ctx_create_in_pool(int device, void* stream, unsigned max_lde_log, cudaMemPool_t pool, qp_ctx** out);
 extern "C" int qp_ctx_create(int device, void* stream, unsigned max_lde_log, qp_ctx** out) {
+    return ctx_create_in_pool(device, stream, max_lde_log, nullptr, out);
+}
+static int ctx_create_in_pool(int device, void* stream, unsigned max_lde_log, cudaMemPool_t own_pool, qp_ctx** out) {
     if (!out) return QP_ERR_BAD_ARG;
     *out = nullptr;
     // 32-bit indices inside the transform kernels (1u << L, grid sizes): 2^30 points is the ceiling
@@ -248,6 +271,7 @@ extern "C" int qp_ctx_create(int device, void* stream, unsigned max_lde_log, qp_
     }
     qp_ctx* ctx = new qp_ctx();
     ctx->device = device;
+    ctx->pool = own_pool;
     CUDA_TRY(ctx, cudaSetDevice(device));
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
@@ -271,8 +295,8 @@ extern "C" int qp_ctx_create(int device, void* stream, unsigned max_lde_log, qp_
     cudaEventCreateWithFlags(&ctx->ready_ev, cudaEventDisableTiming);
     for (auto& e : ctx->grp_ev) cudaEventCreate(&e);
     // keep freed blocks cached in the pool: commits allocate and free multi-GB buffers
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    cudaMemPool_t pool = own_pool;
+    if (pool || cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
@@ -322,8 +346,8 @@ extern "C" void qp_ctx_destroy(qp_ctx* ctx) {
     {
         // the release threshold is raised for the life of a context (a 9 GB LDE is recycled between commits);
         // when a context goes away, what the pool holds and nobody uses goes back to the driver
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        cudaMemPool_t pool = ctx->pool;   // (a pool of the context's owner goes away with the owner)
+        if (pool || cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     }
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     for (auto& e : ctx->copy_ev) cudaEventDestroy(e);

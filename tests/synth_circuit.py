@@ -22,6 +22,8 @@ import numpy as np
 
 from qp_plonky2_b200 import plonk
 
+import gate_witness
+
 P = plonk.P
 
 
@@ -247,26 +249,26 @@ class SynthCircuit:
                     continue
                 g = G[name]
                 if name == "RandomAccessGate":
-                    row = g.generate([(int(rng.integers(0, g.vec_size)), [felt() for _ in range(g.vec_size)])
+                    row = gate_witness.generate(g, [(int(rng.integers(0, g.vec_size)), [felt() for _ in range(g.vec_size)])
                                       for _ in range(g.num_copies)],
                                      [int(consts[gc0 + i, r]) for i in range(g.num_extra_constants)])
                 elif name == "ReducingGate":
-                    row = g.generate(ext(), ext(), [felt() for _ in range(g.num_coeffs)])
+                    row = gate_witness.generate(g, ext(), ext(), [felt() for _ in range(g.num_coeffs)])
                 elif name == "ReducingExtensionGate":
-                    row = g.generate(ext(), ext(), [ext() for _ in range(g.num_coeffs)])
+                    row = gate_witness.generate(g, ext(), ext(), [ext() for _ in range(g.num_coeffs)])
                 elif name == "PoseidonMdsGate":
-                    row = g.generate([ext() for _ in range(12)])
+                    row = gate_witness.generate(g, [ext() for _ in range(12)])
                 elif name == "ExponentiationGate":
-                    row = g.generate(felt(), [int(b) for b in rng.integers(0, 2, size=g.num_power_bits)])
+                    row = gate_witness.generate(g, felt(), [int(b) for b in rng.integers(0, 2, size=g.num_power_bits)])
                 else:
-                    row = g.generate(felt() or 1, [ext() for _ in range(g.num_points)], ext())
+                    row = gate_witness.generate(g, felt() or 1, [ext() for _ in range(g.num_points)], ext())
                 for w, v in row.items():
                     wires[w, r] = v
         # Poseidon rows: inputs and swap are free, everything else follows (PoseidonGenerator)
         if poseidon:
             pg = plonk.PoseidonGate()
             for r in np.nonzero(row_gate == idx["PoseidonGate"])[0]:
-                row = pg.generate([int(wires[i, r]) for i in range(12)], int(rng.integers(0, 2)))
+                row = gate_witness.generate(pg, [int(wires[i, r]) for i in range(12)], int(rng.integers(0, 2)))
                 for w, v in row.items():
                     wires[w, r] = v
         self.wires = wires

@@ -9,6 +9,7 @@ import pytest
 import oracle
 from qp_plonky2_b200 import plonk
 
+import gate_witness
 from synth_circuit import SynthCircuit, verifier_identity_holds
 
 P = oracle.P
@@ -45,7 +46,7 @@ def run_program(code, pool, n_regs, wires, consts, pih, alphas):
                     f = f * (j - sel) % P
             if c >> 16:
                 f = f * (plonk.UNUSED_SELECTOR - sel) % P
-            cons = plonk.PoseidonGate().eval_unfiltered(None, lambda k: plonk.ModP(wires[k]), None)
+            cons = plonk.PoseidonGate().eval_unfiltered(None, lambda k: gate_witness.ModP(wires[k]), None)
             for q in range(nc):
                 acc = sum(int(v) * pow(int(alphas[q]), k, P) for k, v in enumerate(cons)) % P
                 G[q] = (G[q] + f * acc) % P
