@@ -37,10 +37,6 @@ struct qp_mctx {
     // blocks) is running must get SM slots as blocks retire, not after all of that kernel's blocks
     std::vector<cudaStream_t> prod_stream;
     std::vector<uint8_t> peer_ok;    // [D * D]: device a can load from device b's memory
-    // one memory pool per device, made for this multi-device context and destroyed with it: the coefficient
-    // matrices the peers read are stream-ordered allocations, so their pool must grant the peers access -- and the
-    // device's DEFAULT pool is left alone (contexts created before or after keep a pool nobody else is mapped into)
-    std::vector<cudaMemPool_t> pool;
     std::string err;
 };
 
@@ -58,7 +54,7 @@ extern "C" void qp_mctx_destroy(qp_mctx* m) {
         if (d < m->main_ctx.size()) qp_ctx_destroy(m->main_ctx[d]);
         if (d < m->prod_ctx.size()) qp_ctx_destroy(m->prod_ctx[d]);
         if (d < m->prod_stream.size() && m->prod_stream[d]) cudaStreamDestroy(m->prod_stream[d]);
-        if (d < m->pool.size() && m->pool[d]) cudaMemPoolDestroy(m->pool[d]);
+        peer_buf_trim(m->devices[d]);   // cached peer-readable buffers nobody uses go back to the driver
     }
     delete m;
 }
@@ -77,30 +73,15 @@ extern "C" int qp_mctx_create(const int* devices, unsigned n_devices, unsigned m
     m->xfer.assign(n_devices, nullptr);
     m->prod_stream.assign(n_devices, nullptr);
     m->peer_ok.assign((size_t)n_devices * n_devices, 0);
-    m->pool.assign(n_devices, nullptr);
-    const bool own_pools = !getenv("QP_MCTX_DEFAULT_POOL");   // (measurement knob: the devices' default pools instead)
-    for (unsigned d = 0; d < n_devices && own_pools; d++) {
-        cudaMemPoolProps props = {};
-        props.allocType = cudaMemAllocationTypePinned;
-        props.handleTypes = cudaMemHandleTypeNone;
-        props.location.type = cudaMemLocationTypeDevice;
-        props.location.id = devices[d];
-        if (cudaSetDevice(devices[d]) != cudaSuccess || cudaMemPoolCreate(&m->pool[d], &props) != cudaSuccess) {
-            cudaGetLastError();
-            m->pool[d] = nullptr;
-            qp_mctx_destroy(m);
-            return QP_ERR_CUDA;
-        }
-    }
     for (unsigned d = 0; d < n_devices; d++) {
-        int rc = ctx_create_in_pool(devices[d], nullptr, max_lde_log, m->pool[d], &m->main_ctx[d]);
+        int rc = qp_ctx_create(devices[d], nullptr, max_lde_log, &m->main_ctx[d]);
         int lo_prio = 0, hi_prio = 0;
         if (!rc && (cudaSetDevice(devices[d]) != cudaSuccess ||
                     cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio) != cudaSuccess ||
                     cudaStreamCreateWithPriority(&m->prod_stream[d], cudaStreamNonBlocking, hi_prio) != cudaSuccess ||
                     cudaStreamCreateWithPriority(&m->xfer[d], cudaStreamNonBlocking, hi_prio) != cudaSuccess))
             rc = QP_ERR_CUDA;
-        if (!rc) rc = ctx_create_in_pool(devices[d], m->prod_stream[d], max_lde_log, m->pool[d], &m->prod_ctx[d]);
+        if (!rc) rc = qp_ctx_create(devices[d], m->prod_stream[d], max_lde_log, &m->prod_ctx[d]);
         if (rc) {
             qp_mctx_destroy(m);
             return rc;
@@ -114,21 +95,9 @@ extern "C" int qp_mctx_create(const int* devices, unsigned n_devices, unsigned m
             if (cudaDeviceCanAccessPeer(&can, devices[d], devices[p]) == cudaSuccess && can) {
                 cudaError_t e = cudaDeviceEnablePeerAccess(devices[p], 0);
                 if (e != cudaSuccess) cudaGetLastError();  // already enabled is fine
-                bool ok = (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled);
-                // the coefficient matrices are stream-ordered allocations: the OWNER's pool must grant the access too
-                cudaMemPool_t pool = m->pool[p];
-                if (ok && (pool || cudaDeviceGetDefaultMemPool(&pool, devices[p]) == cudaSuccess)) {
-                    cudaMemAccessDesc desc = {};
-                    desc.location.type = cudaMemLocationTypeDevice;
-                    desc.location.id = devices[d];
-                    desc.flags = cudaMemAccessFlagsProtReadWrite;
-                    if (cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) {
-                        cudaGetLastError();
-                        ok = false;
-                    }
-                } else {
-                    ok = false;
-                }
+                // (the matrices the peers read are plain cudaMalloc buffers, peer_buf_acquire: device-level peer access
+                //  covers them; the stream-ordered pools stay private to their device)
+                const bool ok = (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled);
                 m->peer_ok[(size_t)d * n_devices + p] = ok ? 1 : 0;
                 if (getenv("QP_TRACE")) fprintf(stderr, "[qp_mctx] peer access %d -> %d: %s\n", devices[d], devices[p], cudaGetErrorString(e));
             } else if (getenv("QP_TRACE")) {
@@ -256,9 +225,13 @@ static int mbatch_build(qp_mctx* m, const uint64_t* const* cols, const uint64_t*
         rc = check_batch_args(ctx, n_cols, degree_log, rate_bits, blinding, cap_height, salt, d * blocks, blocks,
                               &mb->shards[d]);
         uint64_t* d_coeffs = nullptr;
-        if (!rc) rc = dev_alloc(ctx, &d_coeffs, n_cols * n);
-        if (!rc) rc = batch_create(ctx, d_coeffs, n_cols, degree_log, rate_bits, blinding, cap_height, d * blocks, blocks,
-                                   &mb->shards[d]);
+        // with peers, the matrix is read by them: a peer-readable buffer instead of a pool allocation
+        if (!rc) rc = D > 1 ? peer_buf_acquire(ctx, n_cols * n, &d_coeffs) : dev_alloc(ctx, &d_coeffs, n_cols * n);
+        if (!rc) {
+            rc = batch_create(ctx, d_coeffs, n_cols, degree_log, rate_bits, blinding, cap_height, d * blocks, blocks,
+                              &mb->shards[d]);
+            if (mb->shards[d]) mb->shards[d]->coeffs_peer_buf = D > 1;   // (the batch owns the matrix from here on)
+        }
         if (!rc) {
             cudaEventRecord(ctx->ev[1], ctx->stream);
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = QP_ERR_CUDA;  // peers write into the matrix

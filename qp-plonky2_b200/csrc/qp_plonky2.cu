@@ -40,9 +40,6 @@ struct qp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    // stream-ordered allocations come from the device's default pool, or from a pool the owner of the context
-    // made for it (multi-device contexts: a pool of their own that grants the peers access, multi_device.inl)
-    cudaMemPool_t pool = nullptr;
     uint64_t* tw = nullptr;  // tw[(1<<lg)+e] = w_{2^lg}^e, e < 2^lg
     unsigned tw_lg = 0;
     int sm_count = 148;
@@ -103,17 +100,27 @@ static int dev_alloc(qp_ctx* ctx, uint64_t** p, size_t n_words) {
     *p = nullptr;
     if (n_words == 0) return QP_OK;
     cudaSetDevice(ctx->device);  // a handle may be read while another device is current (multi-device callers)
-    cudaError_t e = ctx->pool ? cudaMallocFromPoolAsync((void**)p, n_words * 8, ctx->pool, ctx->stream)
-                              : cudaMallocAsync((void**)p, n_words * 8, ctx->stream);
+    cudaError_t e = cudaMallocAsync((void**)p, n_words * 8, ctx->stream);
+    static const bool trace_alloc = getenv("QP_TRACE_ALLOC") != nullptr;
+    if (trace_alloc)
+        fprintf(stderr, "[alloc] dev %d ctx %p stream %p: %zu bytes -> %p %s\n", ctx->device, (void*)ctx, (void*)ctx->stream,
+                n_words * 8, (void*)*p, cudaGetErrorString(e));
     if (e != cudaSuccess) {
         cudaGetLastError();
+        if (trace_alloc) {   // can the device itself still give memory?
+            void* q = nullptr;
+            cudaError_t e2 = cudaMalloc(&q, n_words * 8);
+            fprintf(stderr, "[alloc]   plain cudaMalloc of the same size: %s\n", cudaGetErrorString(e2));
+            if (e2 == cudaSuccess) cudaFree(q);
+            cudaGetLastError();
+        }
         // what the device and the pool held when the request failed (an out-of-memory with free memory left points
         // at the pool's mappings, not at the request)
         size_t free_b = 0, total_b = 0;
         uint64_t reserved = 0, used = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        cudaMemPool_t pool = ctx->pool;
-        if (pool || cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
             cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
             cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
         }
@@ -128,7 +135,11 @@ static int dev_alloc(qp_ctx* ctx, uint64_t** p, size_t n_words) {
     return QP_OK;
 }
 static void dev_free(qp_ctx* ctx, uint64_t* p) {
-    if (p) cudaFreeAsync(p, ctx->stream);
+    static const bool trace_alloc = getenv("QP_TRACE_ALLOC") != nullptr;
+    if (p) {
+        cudaError_t e = cudaFreeAsync(p, ctx->stream);
+        if (trace_alloc) fprintf(stderr, "[free ] dev %d ctx %p stream %p: %p %s\n", ctx->device, (void*)ctx, (void*)ctx->stream, (void*)p, cudaGetErrorString(e));
+    }
 }
 
 // Stream-ordered temporaries of one call: everything allocated through the scope is freed when the
@@ -255,11 +266,7 @@ __global__ void __launch_bounds__(128) permute_states_kernel(uint64_t* states, s
 }
 
 // ---------------------------------------------------------------------------------------------
-static int ctx_create_in_pool(int device, void* stream, unsigned max_lde_log, cudaMemPool_t pool, qp_ctx** out);
 extern "C" int qp_ctx_create(int device, void* stream, unsigned max_lde_log, qp_ctx** out) {
-    return ctx_create_in_pool(device, stream, max_lde_log, nullptr, out);
-}
-static int ctx_create_in_pool(int device, void* stream, unsigned max_lde_log, cudaMemPool_t own_pool, qp_ctx** out) {
     if (!out) return QP_ERR_BAD_ARG;
     *out = nullptr;
     // 32-bit indices inside the transform kernels (1u << L, grid sizes): 2^30 points is the ceiling
@@ -271,7 +278,6 @@ static int ctx_create_in_pool(int device, void* stream, unsigned max_lde_log, cu
     }
     qp_ctx* ctx = new qp_ctx();
     ctx->device = device;
-    ctx->pool = own_pool;
     CUDA_TRY(ctx, cudaSetDevice(device));
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
@@ -295,8 +301,8 @@ static int ctx_create_in_pool(int device, void* stream, unsigned max_lde_log, cu
     cudaEventCreateWithFlags(&ctx->ready_ev, cudaEventDisableTiming);
     for (auto& e : ctx->grp_ev) cudaEventCreate(&e);
     // keep freed blocks cached in the pool: commits allocate and free multi-GB buffers
-    cudaMemPool_t pool = own_pool;
-    if (pool || cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
@@ -346,8 +352,8 @@ extern "C" void qp_ctx_destroy(qp_ctx* ctx) {
     {
         // the release threshold is raised for the life of a context (a 9 GB LDE is recycled between commits);
         // when a context goes away, what the pool holds and nobody uses goes back to the driver
-        cudaMemPool_t pool = ctx->pool;   // (a pool of the context's owner goes away with the owner)
-        if (pool || cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     }
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     for (auto& e : ctx->copy_ev) cudaEventDestroy(e);
@@ -675,6 +681,7 @@ struct qp_batch {
     size_t leaf_len = 0;     // n_cols (+4 when blinding)
     size_t n_local = 0;      // local leaves = block_count << degree_log
     uint64_t* coeffs = nullptr;  // [n_cols][n]
+    bool coeffs_peer_buf = false;  // coeffs is a peer-readable buffer (peer_buf_acquire), not a pool allocation
     uint64_t* lde = nullptr;     // [leaf_len][n_local], leaf order
     TreeBuf tree;                // local tree: lg_leaves = log2(n_local), local cap height
     float ms[4] = {0, 0, 0, 0};
@@ -686,6 +693,74 @@ struct qp_batch {
     unsigned chunks_done = 0;
     uint64_t* sponge_state = nullptr;
 };
+
+// Buffers that OTHER devices read (the coefficient matrices of a multi-device commit, multi_device.inl): plain
+// cudaMalloc memory, which cudaDeviceEnablePeerAccess makes visible to the peers.  (Granting the peers access to the
+// stream-ordered pool instead -- cudaMemPoolSetAccess -- was measured to stop the pool from growing: allocations of
+// a few hundred MB failed with "out of memory" at 1-2 GB of pool and 180 GB of device memory free, while cudaMalloc
+// of the same size succeeded; profiles/r02q_pool_peer_access.txt.)  cudaMalloc / cudaFree synchronise the device, so
+// released buffers are kept per device and handed out again: a prover that commits the same shapes proof after
+// proof allocates them once.
+struct PeerBufCache {
+    std::mutex mu;
+    std::vector<std::pair<size_t, uint64_t*>> free_list[64];   // per device: (words, pointer)
+    static constexpr size_t MAX_CACHED = 6;
+};
+static PeerBufCache g_peer_bufs;
+
+static int peer_buf_acquire(qp_ctx* ctx, size_t words, uint64_t** out) {
+    *out = nullptr;
+    if (words == 0) return QP_OK;
+    if (ctx->device < 0 || ctx->device >= 64) return fail(ctx, QP_ERR_BAD_ARG, "device index out of range");
+    {
+        std::lock_guard<std::mutex> lock(g_peer_bufs.mu);
+        auto& fl = g_peer_bufs.free_list[ctx->device];
+        size_t best = fl.size();
+        for (size_t i = 0; i < fl.size(); i++)   // smallest cached buffer that fits without wasting more than half
+            if (fl[i].first >= words && fl[i].first <= 2 * words && (best == fl.size() || fl[i].first < fl[best].first)) best = i;
+        if (best != fl.size()) {
+            *out = fl[best].second;
+            fl.erase(fl.begin() + best);
+            return QP_OK;
+        }
+    }
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaMalloc((void**)out, words * 8);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        ctx->err = std::string("cudaMalloc (peer-readable buffer): ") + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? QP_ERR_TOO_LARGE : QP_ERR_CUDA;
+    }
+    return QP_OK;
+}
+// every piece of work that reads the buffer must be complete (the callers synchronise their streams first)
+static void peer_buf_release(int device, uint64_t* p, size_t words) {
+    if (!p) return;
+    uint64_t* victim = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_peer_bufs.mu);
+        auto& fl = g_peer_bufs.free_list[device];
+        fl.emplace_back(words, p);
+        if (fl.size() > PeerBufCache::MAX_CACHED) {   // the oldest one goes back to the driver
+            victim = fl.front().second;
+            fl.erase(fl.begin());
+        }
+    }
+    if (victim) {
+        cudaSetDevice(device);
+        cudaFree(victim);
+    }
+}
+static void peer_buf_trim(int device) {
+    std::vector<std::pair<size_t, uint64_t*>> all;
+    {
+        std::lock_guard<std::mutex> lock(g_peer_bufs.mu);
+        all.swap(g_peer_bufs.free_list[device]);
+    }
+    cudaSetDevice(device);
+    for (auto& e : all) cudaFree(e.second);
+}
 
 static bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
 static unsigned ilog2(size_t x) {
@@ -1273,7 +1348,12 @@ extern "C" int qp_ifft_columns(qp_ctx* ctx, const uint64_t* values, int space, s
 extern "C" void qp_batch_free(qp_batch* b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
-    dev_free(b->ctx, b->coeffs);
+    if (b->coeffs_peer_buf) {
+        cudaStreamSynchronize(b->ctx->stream);   // readers of the matrix on this device; the peers' copies ended with the commit
+        peer_buf_release(b->ctx->device, b->coeffs, b->n_cols << b->degree_log);
+    } else {
+        dev_free(b->ctx, b->coeffs);
+    }
     dev_free(b->ctx, b->sponge_state);
     dev_free(b->ctx, b->lde);
     dev_free(b->ctx, b->tree.digests);
@@ -1885,14 +1965,22 @@ extern "C" int qp_batch_eval_polys(const qp_batch* b, const uint64_t point[2], u
     uint64_t* pw = nullptr;
     uint64_t* d_out = nullptr;
     int rc = build_power_table(ctx, hx::E{point[0] % gl::P, point[1] % gl::P}, b->degree_log, &pw);
+    // segments per polynomial: about eight resident blocks per SM in total, at least 1024 coefficients each
+    const size_t n = (size_t)1 << b->degree_log;
+    unsigned n_seg = (unsigned)cdiv((size_t)ctx->sm_count * 8, b->n_cols ? b->n_cols : 1);
+    if (n_seg > n / 1024) n_seg = (unsigned)(n / 1024);
+    if (n_seg < 1) n_seg = 1;
+    uint64_t* d_partial = nullptr;
     if (!rc) rc = dev_alloc(ctx, &d_out, 2 * b->n_cols);
+    if (!rc) rc = dev_alloc(ctx, &d_partial, 2 * b->n_cols * n_seg);
     if (!rc) {
-        LAUNCH(ctx, openings::eval_polys_kernel, (unsigned)b->n_cols, 256, 0, b->coeffs, (size_t)1 << b->degree_log, pw,
-               d_out);
+        LAUNCH(ctx, openings::eval_polys_kernel, dim3((unsigned)b->n_cols, n_seg), 256, 0, b->coeffs, n, pw, d_partial);
+        LAUNCH(ctx, openings::eval_polys_finish_kernel, cdiv(b->n_cols, 128), 128, 0, d_partial, (unsigned)b->n_cols, n_seg, d_out);
         rc = copy_out(ctx, out, QP_HOST, d_out, 2 * b->n_cols);
     }
     dev_free(ctx, pw);
     dev_free(ctx, d_out);
+    dev_free(ctx, d_partial);
     return rc;
 }
 

@@ -139,7 +139,7 @@ extern "C" int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* con
     qp_hash_no_pad(public_inputs, n_public_inputs, pih);  // prover.rs:185-186
     qp_batch *wb = nullptr, *zb = nullptr, *qb = nullptr;
     qp_fri* fri = nullptr;
-    uint64_t *d_zs = nullptr, *d_q = nullptr, *d_salt_z = nullptr, *d_salt_q = nullptr;
+    uint64_t *d_zs = nullptr, *d_q = nullptr, *d_salt_z = nullptr, *d_salt_q = nullptr, *d_routed = nullptr;
     std::vector<uint8_t> bytes;
     bytes.reserve(total);
     auto cleanup = [&]() {
@@ -151,6 +151,7 @@ extern "C" int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* con
         qp_dev_free(ctx, d_q);
         qp_dev_free(ctx, d_salt_z);
         qp_dev_free(ctx, d_salt_q);
+        qp_dev_free(ctx, d_routed);
     };
 #define QP_STEP(expr)                                                                                   \
     do {                                                                                                \
@@ -205,9 +206,21 @@ extern "C" int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* con
     }
     // Z and partial products (prover.rs:250-261), kept on the device
     QP_STEP(qp_dev_alloc(ctx, n_zs_all * n, &d_zs));
-    QP_STEP(qp_circuit_partial_products_and_zs(circuit, wires, space, betas.data(), gammas.data(), d_zs, QP_DEVICE));
+    // The permutation and lookup arguments read the routed wires' VALUES.  A host witness has just been uploaded and
+    // interpolated for the commitment: transforming the routed columns' coefficients back on the device (exact, a
+    // few ms at 2^20 rows) replaces a second trip of 80 columns over PCIe (14 ms at 2^20 rows).
+    const uint64_t* routed = wires;
+    int routed_space = space;
+    if (space != QP_DEVICE) {
+        QP_STEP(qp_dev_alloc(ctx, (size_t)d.num_routed_wires * n, &d_routed));
+        QP_STEP(qp_coset_fft(ctx, qp_batch_device_coeffs(wb), QP_DEVICE, d.num_routed_wires, d.degree_bits, 1, 0, d_routed,
+                             QP_DEVICE));
+        routed = d_routed;
+        routed_space = QP_DEVICE;
+    }
+    QP_STEP(qp_circuit_partial_products_and_zs(circuit, routed, routed_space, betas.data(), gammas.data(), d_zs, QP_DEVICE));
     if (has_lookup)  // compute_all_lookup_polys, prover.rs:262-263 (also hands the deltas to the quotient evaluation)
-        QP_STEP(qp_circuit_lookup_polys(circuit, wires, space, deltas.data(), d_zs + n_zs * n, QP_DEVICE));
+        QP_STEP(qp_circuit_lookup_polys(circuit, routed, routed_space, deltas.data(), d_zs + n_zs * n, QP_DEVICE));
     scopes[1] = tm.lap(ctx);
     QP_STEP(qp_batch_from_values(ctx, d_zs, QP_DEVICE, n_zs_all, d.degree_bits, cfg->rate_bits, zk ? 1 : 0, cfg->cap_height,
                                  salt_z, 0, 1u << cfg->rate_bits, &zb));
@@ -400,7 +413,7 @@ extern "C" int qp_mprove(qp_mctx* m, qp_circuit* const* circuits, qp_mbatch* con
     qp_hash_no_pad(public_inputs, n_public_inputs, pih);
     qp_mbatch *wb = nullptr, *zb = nullptr, *qb = nullptr;
     qp_fri* fri = nullptr;
-    uint64_t *d_zs = nullptr, *d_q = nullptr, *d_vals = nullptr;
+    uint64_t *d_zs = nullptr, *d_q = nullptr, *d_vals = nullptr, *d_routed = nullptr;
     std::vector<uint8_t> bytes;
     bytes.reserve(total);
     auto cleanup = [&]() {
@@ -411,6 +424,7 @@ extern "C" int qp_mprove(qp_mctx* m, qp_circuit* const* circuits, qp_mbatch* con
         qp_dev_free(ctx, d_zs);
         qp_dev_free(ctx, d_q);
         qp_dev_free(ctx, d_vals);
+        qp_dev_free(ctx, d_routed);
     };
 #define QP_STEP(expr)                                                                                   \
     do {                                                                                                \
@@ -457,9 +471,13 @@ extern "C" int qp_mprove(qp_mctx* m, qp_circuit* const* circuits, qp_mbatch* con
     }
     // Z and partial products on device 0 (prover.rs:250-261)
     QP_STEP(qp_dev_alloc(ctx, n_zs_all * n, &d_zs));
-    QP_STEP(qp_circuit_partial_products_and_zs(circuits[0], wires, QP_HOST, betas.data(), gammas.data(), d_zs, QP_DEVICE));
+    // the routed wires' values from device 0's copy of the coefficient matrix (see qp_prove_zk): no second upload
+    QP_STEP(qp_dev_alloc(ctx, (size_t)d.num_routed_wires * n, &d_routed));
+    QP_STEP(qp_coset_fft(ctx, qp_batch_device_coeffs(qp_mbatch_shard(wb, 0)), QP_DEVICE, d.num_routed_wires, d.degree_bits, 1, 0,
+                         d_routed, QP_DEVICE));
+    QP_STEP(qp_circuit_partial_products_and_zs(circuits[0], d_routed, QP_DEVICE, betas.data(), gammas.data(), d_zs, QP_DEVICE));
     if (has_lookup) {  // on device 0 like the Z's; every shard's quotient evaluation needs the challenges
-        QP_STEP(qp_circuit_lookup_polys(circuits[0], wires, QP_HOST, deltas.data(), d_zs + n_zs * n, QP_DEVICE));
+        QP_STEP(qp_circuit_lookup_polys(circuits[0], d_routed, QP_DEVICE, deltas.data(), d_zs + n_zs * n, QP_DEVICE));
         for (unsigned e = 1; e < D; e++) QP_STEP(qp_circuit_set_lookup_challenges(circuits[e], deltas.data()));
     }
     QP_STEP(qp_ctx_synchronize(ctx));
