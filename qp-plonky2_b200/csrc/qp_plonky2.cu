@@ -3025,7 +3025,11 @@ extern "C" int qp_circuit_lookup_polys(qp_circuit* c, const uint64_t* wires, int
     p.consts = c->lookup_consts;
     p.out = d_out;
     CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, out_words * 8, ctx->stream));
-    LAUNCH(ctx, quotient::lookup_rows_kernel, cdiv((size_t)p.n_rows * p.nc, 128), 128, 0, p);
+    // one block per (challenge, row); one thread per slot and a spare one for the RE contribution
+    const unsigned slots = std::max(std::max(p.num_lu_slots, p.num_lut_slots), p.np1);
+    const unsigned block = std::max(64u, (slots + 1 + 31) / 32 * 32);
+    if (block > 1024) return fail(ctx, QP_ERR_UNSUPPORTED, "more than 1023 lookup slots per row");
+    LAUNCH(ctx, quotient::lookup_rows_kernel, p.n_rows * p.nc, block, block * 8, p);
     LAUNCH(ctx, quotient::lookup_chain_kernel, 1, 32, 0, p);
     if (out_space != QP_DEVICE) rc = copy_out(ctx, out, QP_HOST, d_out, out_words);
     if (!rc) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

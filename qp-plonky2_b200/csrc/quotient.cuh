@@ -646,36 +646,40 @@ struct LookupPolyParams {
 // phase 1: out[ch][0][row] = sum_s combo_b(s) delta^(slots - 1 - s) (LookupTableGate rows: what the row adds to
 // delta^slots RE(row + 1)); out[ch][k + 1][row] = the row's share of partial polynomial k: + sum m_s / (alpha -
 // combo_a(s)) over the LookupTableGate slots of k, - sum 1 / (alpha - combo_a(s)) over the LookupGate slots of k.
-__global__ void __launch_bounds__(128) lookup_rows_kernel(LookupPolyParams p) {
-    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= p.n_rows * p.nc) return;
-    const unsigned ch = id / p.n_rows, code = p.rows[id % p.n_rows];
+// One block per (challenge, row), one thread per slot: the Fermat inversions -- ~100 dependent multiplications
+// each -- are the whole cost and run side by side (one thread per row took 0.3 ms for the 11 lookup rows of a
+// 2^14-row circuit, a tenth of a small proof; profiles/r02p_ncu_plonk_kernels.md); the block's last thread
+// evaluates the RE contribution meanwhile.  blockDim.x > max(slots per row, partial polynomials).
+__global__ void lookup_rows_kernel(LookupPolyParams p) {
+    extern __shared__ uint64_t term[];   // [blockDim.x]
+    const unsigned ch = blockIdx.x / p.n_rows, code = p.rows[blockIdx.x % p.n_rows];
     const size_t n = (size_t)1 << p.degree_bits, row = code & 0x7fffffffu;
     const uint64_t* const d = p.consts + (size_t)ch * (4 + p.n_luts);
     const uint64_t da = d[0], db = d[1], dalpha = d[2], ddelta = d[3];
     uint64_t* const out = p.out + (size_t)ch * p.np1 * n + row;
     auto wire = [&](unsigned c) { return p.wires[(size_t)c * n + row]; };
-    const unsigned npl = p.np1 - 1;
-    if (code >> 31) {
+    const bool lut = (code >> 31) != 0;
+    const unsigned n_slots = lut ? p.num_lut_slots : p.num_lu_slots, deg = lut ? p.lut_degree : p.lu_degree;
+    const unsigned s = threadIdx.x;
+    uint64_t t = 0;
+    if (s < n_slots) {
+        if (lut)
+            t = gl::mul(wire(3 * s + 2), inverse(gl::sub(dalpha, gl::add(wire(3 * s), gl::mul(da, wire(3 * s + 1))))));
+        else
+            t = inverse(gl::sub(dalpha, gl::add(wire(2 * s), gl::mul(da, wire(2 * s + 1)))));
+    } else if (lut && s == blockDim.x - 1) {
         uint64_t re = 0;
-        for (unsigned s = 0; s < p.num_lut_slots; s++)
-            re = gl::add(gl::mul(re, ddelta), gl::add(wire(3 * s), gl::mul(db, wire(3 * s + 1))));
+        for (unsigned q = 0; q < p.num_lut_slots; q++)
+            re = gl::add(gl::mul(re, ddelta), gl::add(wire(3 * q), gl::mul(db, wire(3 * q + 1))));
         out[0] = re;
-        for (unsigned k = 0; k < npl; k++) {
-            uint64_t sum = 0;
-            const unsigned hi = min((k + 1) * p.lut_degree, p.num_lut_slots);
-            for (unsigned s = k * p.lut_degree; s < hi; s++)
-                sum = gl::add(sum, gl::mul(wire(3 * s + 2), inverse(gl::sub(dalpha, gl::add(wire(3 * s), gl::mul(da, wire(3 * s + 1)))))));
-            out[(size_t)(k + 1) * n] = sum;
-        }
-    } else {
-        for (unsigned k = 0; k < npl; k++) {
-            uint64_t sum = 0;
-            const unsigned hi = min((k + 1) * p.lu_degree, p.num_lu_slots);
-            for (unsigned s = k * p.lu_degree; s < hi; s++)
-                sum = gl::add(sum, inverse(gl::sub(dalpha, gl::add(wire(2 * s), gl::mul(da, wire(2 * s + 1))))));
-            out[(size_t)(k + 1) * n] = gl::sub(0, sum);
-        }
+    }
+    term[s] = t;
+    __syncthreads();
+    if (s < p.np1 - 1) {
+        uint64_t sum = 0;
+        const unsigned hi = min((s + 1) * deg, n_slots);
+        for (unsigned q = s * deg; q < hi; q++) sum = gl::add(sum, term[q]);
+        out[(size_t)(s + 1) * n] = lut ? sum : gl::sub(0, sum);
     }
 }
 
