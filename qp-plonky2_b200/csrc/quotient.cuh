@@ -685,7 +685,8 @@ __global__ void lookup_rows_kernel(LookupPolyParams p) {
 
 // phase 2: one thread per challenge walks the tables in the reference's order, rows downwards:
 // RE(row) = delta^slots RE(row + 1) + share; SLDC_0(row) = SLDC_last(row + 1) + share_0, SLDC_k(row) = SLDC_(k-1)(row)
-// + share_k.  (A circuit's lookup rows are few next to its degree; the chain is serial by definition.)
+// + share_k.  The chain is serial by definition; the values handed from row to row stay in registers, so a row costs
+// one multiplication and a few additions on shares whose loads do not depend on the chain.
 __global__ void lookup_chain_kernel(LookupPolyParams p) {
     const unsigned ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= p.nc) return;
@@ -695,13 +696,19 @@ __global__ void lookup_chain_kernel(LookupPolyParams p) {
     const uint64_t delta_pow = gl::pow(p.consts[(size_t)ch * (4 + p.n_luts) + 3], p.num_lut_slots);
     for (unsigned t = 0; t < p.n_luts; t++) {
         const size_t last_lu = p.tables[3 * t], last_lut = p.tables[3 * t + 1], first_lut = p.tables[3 * t + 2];
+        // the row after the table (no table's row, qp_circuit_create): whatever the polynomials hold there
+        uint64_t re = out[first_lut + 1], last = out[(size_t)npl * n + first_lut + 1];
         for (size_t row = first_lut + 1; row-- > last_lu;) {
-            if (row >= last_lut) out[row] = gl::canon(gl::add(gl::mul(out[row + 1], delta_pow), out[row]));
-            uint64_t acc = out[(size_t)npl * n + row + 1];
-            for (unsigned k = 0; k < npl; k++) {
-                acc = gl::add(acc, out[(size_t)(k + 1) * n + row]);
-                out[(size_t)(k + 1) * n + row] = gl::canon(acc);
+            if (row >= last_lut) {
+                re = gl::canon(gl::add(gl::mul(re, delta_pow), out[row]));
+                out[row] = re;
             }
+            uint64_t acc = last;
+            for (unsigned k = 0; k < npl; k++) {
+                acc = gl::canon(gl::add(acc, out[(size_t)(k + 1) * n + row]));
+                out[(size_t)(k + 1) * n + row] = acc;
+            }
+            last = acc;
         }
     }
 }
