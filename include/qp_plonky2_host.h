@@ -194,6 +194,15 @@ int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* constants_sigm
                 size_t n_public_inputs, const uint64_t* wires_salt, const uint64_t* zs_salt,
                 const uint64_t* quotient_salt, uint8_t* out, size_t capacity, size_t* len_out, double* timing_ms);
 
+/* The same from the witness as the reference holds it -- MatrixWitness.wire_values, one heap vector per wire
+ * (plonky2/src/iop/witness.rs; prover.rs:201-206): wire_cols[w] points at the 2^degree_bits values of wire w in
+ * ordinary (pageable) host memory, no flattening copy on the caller's side.  The columns are read once, by the wires
+ * commitment (qp_batch_from_values_cols); the salts (all three or none) are host memory. */
+int qp_prove_cols(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* constants_sigmas, const uint64_t circuit_digest[4],
+                  const qp_prover_config* cfg, const uint64_t* const* wire_cols, const uint64_t* public_inputs,
+                  size_t n_public_inputs, const uint64_t* wires_salt, const uint64_t* zs_salt,
+                  const uint64_t* quotient_salt, uint8_t* out, size_t capacity, size_t* len_out, double* timing_ms);
+
 /* prove() over every GPU of a multi-device context (qp_mctx, include/qp_plonky2_b200.h): the four commitments and
  * the evaluation of the vanishing polynomial are sharded by coset = by cap subtree, the rest (Z / partial products,
  * the inverse transform of the gathered quotient values, openings, FRI commit phase) runs on devices[0]; query
@@ -203,6 +212,10 @@ int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* constants_sigm
 int qp_mprove(qp_mctx* m, qp_circuit* const* circuits, qp_mbatch* constants_sigmas, const uint64_t circuit_digest[4],
               const qp_prover_config* cfg, const uint64_t* wires, const uint64_t* public_inputs,
               size_t n_public_inputs, uint8_t* out, size_t capacity, size_t* len_out, double* timing_ms);
+/* ... from MatrixWitness.wire_values: wire_cols[w] = the host vector of wire w (pageable or pinned). */
+int qp_mprove_cols(qp_mctx* m, qp_circuit* const* circuits, qp_mbatch* constants_sigmas, const uint64_t circuit_digest[4],
+                   const qp_prover_config* cfg, const uint64_t* const* wire_cols, const uint64_t* public_inputs,
+                   size_t n_public_inputs, uint8_t* out, size_t capacity, size_t* len_out, double* timing_ms);
 
 #ifdef __cplusplus
 }

@@ -259,6 +259,8 @@ def lib():
         "qp_prove": (i32, [vp, vp, vp, vp, vp, vp, i32, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(C.c_double)]),
         "qp_mprove": (i32, [vp, vp, vp, vp, vp, vp, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(C.c_double)]),
         "qp_prove_zk": (i32, [vp, vp, vp, vp, vp, vp, i32, vp, sz, vp, vp, vp, vp, sz, C.POINTER(sz), C.POINTER(C.c_double)]),
+        "qp_prove_cols": (i32, [vp, vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp, sz, C.POINTER(sz), C.POINTER(C.c_double)]),
+        "qp_mprove_cols": (i32, [vp, vp, vp, vp, vp, vp, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

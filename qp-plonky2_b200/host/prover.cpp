@@ -97,11 +97,40 @@ extern "C" int qp_prove(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* consta
 // draws them from its RNG, here they are injected so that the proof is reproducible), FriParams.leaf_hiding
 // is observed as 1 (core/src/fri.rs:311) and the query openings carry the salted leaves
 // (fri_verifier.rs:222 strips them again).  All three salts or none.
+static int prove_impl(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* constants_sigmas,
+                      const uint64_t circuit_digest[4], const qp_prover_config* cfg, const uint64_t* wires, int space,
+                      const uint64_t* const* wire_cols, const uint64_t* public_inputs, size_t n_public_inputs,
+                      const uint64_t* wires_salt, const uint64_t* zs_salt, const uint64_t* quotient_salt, uint8_t* out,
+                      size_t capacity, size_t* len_out, double* timing_ms);
+
 extern "C" int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* constants_sigmas,
                            const uint64_t circuit_digest[4], const qp_prover_config* cfg, const uint64_t* wires,
                            int space, const uint64_t* public_inputs, size_t n_public_inputs,
                            const uint64_t* wires_salt, const uint64_t* zs_salt, const uint64_t* quotient_salt,
                            uint8_t* out, size_t capacity, size_t* len_out, double* timing_ms) {
+    return prove_impl(ctx, circuit, constants_sigmas, circuit_digest, cfg, wires, space, nullptr, public_inputs,
+                      n_public_inputs, wires_salt, zs_salt, quotient_salt, out, capacity, len_out, timing_ms);
+}
+
+// The witness as the reference holds it: MatrixWitness.wire_values, one heap vector per wire
+// (plonky2/src/iop/witness.rs; prover.rs:201-206 wraps each in a PolynomialValues).  The columns are only needed by
+// the wires commitment (staged through the pinned ring, qp_batch_from_values_cols); the permutation and lookup
+// arguments read the routed wires' values back out of the committed coefficients on the device.
+extern "C" int qp_prove_cols(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* constants_sigmas,
+                             const uint64_t circuit_digest[4], const qp_prover_config* cfg,
+                             const uint64_t* const* wire_cols, const uint64_t* public_inputs, size_t n_public_inputs,
+                             const uint64_t* wires_salt, const uint64_t* zs_salt, const uint64_t* quotient_salt,
+                             uint8_t* out, size_t capacity, size_t* len_out, double* timing_ms) {
+    if (out && !wire_cols) return QP_ERR_BAD_ARG;
+    return prove_impl(ctx, circuit, constants_sigmas, circuit_digest, cfg, nullptr, QP_HOST, wire_cols, public_inputs,
+                      n_public_inputs, wires_salt, zs_salt, quotient_salt, out, capacity, len_out, timing_ms);
+}
+
+static int prove_impl(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* constants_sigmas,
+                      const uint64_t circuit_digest[4], const qp_prover_config* cfg, const uint64_t* wires, int space,
+                      const uint64_t* const* wire_cols, const uint64_t* public_inputs, size_t n_public_inputs,
+                      const uint64_t* wires_salt, const uint64_t* zs_salt, const uint64_t* quotient_salt, uint8_t* out,
+                      size_t capacity, size_t* len_out, double* timing_ms) {
     if (!ctx || !circuit || !constants_sigmas || !circuit_digest || !cfg || !len_out) return QP_ERR_BAD_ARG;
     qp_circuit_desc d;
     int rc = qp_circuit_describe(circuit, &d);
@@ -128,7 +157,10 @@ extern "C" int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* con
     const size_t total = 8 * (3 * cap_words + 2 * n_open) + fri_len + 8 * (1 + n_public_inputs);
     *len_out = total;
     if (!out) return QP_OK;
-    if (capacity < total || !wires || (n_public_inputs && !public_inputs)) return QP_ERR_BAD_ARG;
+    if (capacity < total || (!wires && !wire_cols) || (n_public_inputs && !public_inputs)) return QP_ERR_BAD_ARG;
+    if (wire_cols)
+        for (unsigned c = 0; c < d.num_wires; c++)
+            if (!wire_cols[c]) return QP_ERR_BAD_ARG;
     if (!qp_circuit_has_sigmas(circuit)) return QP_ERR_BAD_ARG;
     if (qdf == 0 || qdf > (1u << d.quotient_degree_bits)) return QP_ERR_BAD_ARG;
     if (qp_batch_leaf_len(constants_sigmas) < n_pre) return QP_ERR_BAD_ARG;
@@ -175,8 +207,12 @@ extern "C" int qp_prove_zk(qp_ctx* ctx, qp_circuit* circuit, const qp_batch* con
         salt_q = d_salt_q;
     }
     // wires commitment, prover.rs:201-214
-    QP_STEP(qp_batch_from_values(ctx, wires, space, d.num_wires, d.degree_bits, cfg->rate_bits, zk ? 1 : 0,
-                                 cfg->cap_height, wires_salt, 0, 1u << cfg->rate_bits, &wb));
+    if (wire_cols)
+        QP_STEP(qp_batch_from_values_cols(ctx, wire_cols, d.num_wires, d.degree_bits, cfg->rate_bits, zk ? 1 : 0,
+                                          cfg->cap_height, wires_salt, 0, 1u << cfg->rate_bits, &wb));
+    else
+        QP_STEP(qp_batch_from_values(ctx, wires, space, d.num_wires, d.degree_bits, cfg->rate_bits, zk ? 1 : 0,
+                                     cfg->cap_height, wires_salt, 0, 1u << cfg->rate_bits, &wb));
     scopes[0] = tm.lap(ctx);
     // transcript, prover.rs:216-234; FriParams::observe core/src/fri.rs:289-321
     qp_challenger ch;
@@ -374,6 +410,21 @@ extern "C" int qp_mprove(qp_mctx* m, qp_circuit* const* circuits, qp_mbatch* con
                          const uint64_t circuit_digest[4], const qp_prover_config* cfg, const uint64_t* wires,
                          const uint64_t* public_inputs, size_t n_public_inputs, uint8_t* out, size_t capacity,
                          size_t* len_out, double* timing_ms) {
+    if (!m || !circuits || !circuits[0] || !cfg) return QP_ERR_BAD_ARG;
+    qp_circuit_desc d;
+    int rc = qp_circuit_describe(circuits[0], &d);
+    if (rc) return rc;
+    std::vector<const uint64_t*> cols(d.num_wires, nullptr);
+    for (unsigned c = 0; wires && c < d.num_wires; c++) cols[c] = wires + ((size_t)c << d.degree_bits);
+    return qp_mprove_cols(m, circuits, constants_sigmas, circuit_digest, cfg, wires ? cols.data() : nullptr, public_inputs,
+                          n_public_inputs, out, capacity, len_out, timing_ms);
+}
+
+// The same from the reference's MatrixWitness.wire_values (one host vector per wire, pageable or pinned).
+extern "C" int qp_mprove_cols(qp_mctx* m, qp_circuit* const* circuits, qp_mbatch* constants_sigmas,
+                              const uint64_t circuit_digest[4], const qp_prover_config* cfg,
+                              const uint64_t* const* wire_cols, const uint64_t* public_inputs, size_t n_public_inputs,
+                              uint8_t* out, size_t capacity, size_t* len_out, double* timing_ms) {
     if (!m || !circuits || !constants_sigmas || !circuit_digest || !cfg || !len_out) return QP_ERR_BAD_ARG;
     const unsigned D = qp_mctx_num_devices(m);
     if (D == 0 || qp_mbatch_num_shards(constants_sigmas) != D) return QP_ERR_BAD_ARG;
@@ -402,7 +453,9 @@ extern "C" int qp_mprove(qp_mctx* m, qp_circuit* const* circuits, qp_mbatch* con
     const size_t total = 8 * (3 * cap_words + 2 * n_open) + fri_len + 8 * (1 + n_public_inputs);
     *len_out = total;
     if (!out) return QP_OK;
-    if (capacity < total || !wires || (n_public_inputs && !public_inputs)) return QP_ERR_BAD_ARG;
+    if (capacity < total || !wire_cols || (n_public_inputs && !public_inputs)) return QP_ERR_BAD_ARG;
+    for (unsigned c = 0; c < d.num_wires; c++)
+        if (!wire_cols[c]) return QP_ERR_BAD_ARG;
     if (!qp_circuit_has_sigmas(circuits[0])) return QP_ERR_BAD_ARG;
     if (qdf == 0 || qdf > (1u << d.quotient_degree_bits)) return QP_ERR_BAD_ARG;
     if (qp_batch_leaf_len(qp_mbatch_shard(constants_sigmas, 0)) < n_pre) return QP_ERR_BAD_ARG;
@@ -437,12 +490,8 @@ extern "C" int qp_mprove(qp_mctx* m, qp_circuit* const* circuits, qp_mbatch* con
     } while (0)
 
     // wires commitment over all devices, prover.rs:201-214
-    {
-        std::vector<const uint64_t*> cols(d.num_wires);
-        for (unsigned c = 0; c < d.num_wires; c++) cols[c] = wires + (size_t)c * n;
-        QP_STEP(qp_mbatch_from_values_cols(m, cols.data(), d.num_wires, d.degree_bits, cfg->rate_bits, 0, cfg->cap_height,
-                                           nullptr, &wb));
-    }
+    QP_STEP(qp_mbatch_from_values_cols(m, wire_cols, d.num_wires, d.degree_bits, cfg->rate_bits, 0, cfg->cap_height, nullptr,
+                                       &wb));
     scopes[0] = tm.lap(ctx);
     qp_challenger ch;
     qp_challenger_init(&ch);

@@ -91,20 +91,36 @@ SCOPES = ("compute wires commitment", "compute partial products", "commit to par
           "compute quotient polys", "commit to quotient polys", "construct the opening set", "compute opening proofs")
 
 
+def _wire_columns(wires, c):
+    """A witness given as a list / tuple of per-wire host vectors (MatrixWitness.wire_values) -> (ctypes pointer array,
+    the arrays it points into), or None for a matrix."""
+    if not isinstance(wires, (list, tuple)):
+        return None
+    cols = [np.ascontiguousarray(np.asarray(w, dtype=np.uint64).ravel()) for w in wires]
+    if len(cols) != c.num_wires or any(w.size != 1 << c.degree_bits for w in cols):
+        raise ValueError("wires must be num_wires vectors of n values")
+    return (C.c_void_p * len(cols))(*[w.ctypes.data for w in cols]), cols
+
+
 def prove(prover_data, wires, public_inputs, timing=None, salts=None):
     """-> bytes of ProofWithPublicInputs.  salts: None, or (wires_salt, zs_salt, quotient_salt), each [4][N]
-    (N = n << rate_bits) in the same memory space as `wires`: config.zero_knowledge (prover.rs:210,280,328).  wires: witness matrix [num_wires][n] (numpy, or a torch
-    CUDA tensor: then nothing but caps, openings and the FRI proof leaves the device);
-    public_inputs: field elements (already part of the witness).  `timing` (dict) receives the
-    reference's TimingTree scopes in milliseconds."""
-    from . import _buf, lib
+    (N = n << rate_bits) in the same memory space as `wires`: config.zero_knowledge (prover.rs:210,280,328).
+    wires: the witness -- a matrix [num_wires][n] (numpy, or a torch CUDA tensor: then nothing but caps, openings and
+    the FRI proof leaves the device), or a LIST of num_wires separately allocated host vectors, the reference's
+    MatrixWitness.wire_values (qp_prove_cols: no flattening copy); public_inputs: field elements (already part of
+    the witness).  `timing` (dict) receives the reference's TimingTree scopes in milliseconds."""
+    from . import QP_HOST, _buf, lib
     pd = prover_data
     ctx, c, f = pd.ctx, pd.circuit.common, pd.fri
     cfg = _Config(f.rate_bits, f.cap_height, f.proof_of_work_bits, f.num_query_rounds, f.arity_bits,
                   f.final_poly_bits, c.quotient_degree_factor)
-    ptr, space, keep, shape = _buf(wires)
-    if tuple(shape) != (c.num_wires, 1 << c.degree_bits):
-        raise ValueError("wires must be [num_wires][n]")
+    as_cols = _wire_columns(wires, c)
+    if as_cols is None:
+        ptr, space, keep, shape = _buf(wires)
+        if tuple(shape) != (c.num_wires, 1 << c.degree_bits):
+            raise ValueError("wires must be [num_wires][n]")
+    else:
+        space = QP_HOST
     pis = np.ascontiguousarray(np.asarray([int(x) % P for x in public_inputs], dtype=np.uint64))
     digest = np.ascontiguousarray(pd.circuit_digest, dtype=np.uint64)
     need = C.c_size_t()
@@ -116,12 +132,16 @@ def prove(prover_data, wires, public_inputs, timing=None, salts=None):
                 raise ValueError("salts must be [4][N] in the same memory space as the wires")
             sp[k] = q
             skeep.append(keep_s)
-    args = (ctx._h, pd.circuit._h, pd.constants_sigmas_commitment._h, digest.ctypes.data, C.byref(cfg), ptr, space,
-            pis.ctypes.data if pis.size else None, pis.size, sp[0], sp[1], sp[2])
-    ctx.check(lib().qp_prove_zk(*args, None, 0, C.byref(need), None))
+    head = (ctx._h, pd.circuit._h, pd.constants_sigmas_commitment._h, digest.ctypes.data, C.byref(cfg))
+    tail = (pis.ctypes.data if pis.size else None, pis.size, sp[0], sp[1], sp[2])
+    if as_cols is None:
+        fn, args = lib().qp_prove_zk, head + (ptr, space) + tail
+    else:
+        fn, args = lib().qp_prove_cols, head + (as_cols[0],) + tail
+    ctx.check(fn(*args, None, 0, C.byref(need), None))
     buf = (C.c_uint8 * need.value)()
     ms = (C.c_double * 7)()
-    rc = lib().qp_prove_zk(*args, buf, need.value, C.byref(need), ms)
+    rc = fn(*args, buf, need.value, C.byref(need), ms)
     if rc:
         from . import QpError
         raise QpError(rc, lib().qp_last_error(ctx._h).decode() or "qp_prove failed")
@@ -149,27 +169,31 @@ class MultiProverData:
 
 def mprove(prover_data, wires, public_inputs, timing=None):
     """prove() over every GPU of the MultiContext (qp_mprove): the four commitments and the quotient evaluation are
-    sharded by coset, the rest runs on device 0; the bytes are prove()'s.  wires: host matrix [num_wires][n]."""
+    sharded by coset, the rest runs on device 0; the bytes are prove()'s.  wires: host matrix [num_wires][n], or a list
+    of num_wires separately allocated host vectors (MatrixWitness.wire_values, qp_mprove_cols)."""
     from . import QpError, lib
     pd = prover_data
     c, f = pd.common, pd.fri
     cfg = _Config(f.rate_bits, f.cap_height, f.proof_of_work_bits, f.num_query_rounds, f.arity_bits,
                   f.final_poly_bits, c.quotient_degree_factor)
-    w = np.ascontiguousarray(np.asarray(wires, dtype=np.uint64))
-    if w.shape != (c.num_wires, 1 << c.degree_bits):
-        raise ValueError("wires must be [num_wires][n]")
+    as_cols = _wire_columns(wires, c)
+    if as_cols is None:
+        w = np.ascontiguousarray(np.asarray(wires, dtype=np.uint64))
+        if w.shape != (c.num_wires, 1 << c.degree_bits):
+            raise ValueError("wires must be [num_wires][n]")
     pis = np.ascontiguousarray(np.asarray([int(x) % P for x in public_inputs], dtype=np.uint64))
     digest = np.ascontiguousarray(pd.circuit_digest, dtype=np.uint64)
     circs = (C.c_void_p * len(pd.circuits))(*[x._h.value for x in pd.circuits])
     need = C.c_size_t()
-    args = (pd.mctx._h, circs, pd.constants_sigmas_commitment._h, digest.ctypes.data, C.byref(cfg), w.ctypes.data,
-            pis.ctypes.data if pis.size else None, pis.size)
-    rc = lib().qp_mprove(*args, None, 0, C.byref(need), None)
+    fn = lib().qp_mprove if as_cols is None else lib().qp_mprove_cols
+    args = (pd.mctx._h, circs, pd.constants_sigmas_commitment._h, digest.ctypes.data, C.byref(cfg),
+            w.ctypes.data if as_cols is None else as_cols[0], pis.ctypes.data if pis.size else None, pis.size)
+    rc = fn(*args, None, 0, C.byref(need), None)
     if rc:
         raise QpError(rc, "qp_mprove (sizing) failed")
     buf = (C.c_uint8 * need.value)()
     ms = (C.c_double * 7)()
-    rc = lib().qp_mprove(*args, buf, need.value, C.byref(need), ms)
+    rc = fn(*args, buf, need.value, C.byref(need), ms)
     if rc:
         msgs = [lib().qp_last_error(x._h).decode() for x in pd.mctx.contexts] + [lib().qp_mctx_last_error(pd.mctx._h).decode()]
         raise QpError(rc, "qp_mprove failed: " + " | ".join(x for x in msgs if x))

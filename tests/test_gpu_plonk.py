@@ -318,6 +318,43 @@ def test_zero_knowledge_proof_bytes_match_oracle(qp, ctx, degree_bits, poseidon,
     assert len(plain) == len(got) - 6 * 3 * 4 * 8 and verifier.verify(plain, c, pd.fri, cap, pd.circuit_digest) is None
 
 
+@pytest.mark.parametrize("degree_bits,lookups,zk", [(7, False, False), (9, True, False), (8, False, True)])
+def test_proof_from_witness_column_vectors(qp, ctx, degree_bits, lookups, zk):
+    """qp_prove_cols / qp_mprove_cols: the witness as the reference holds it -- MatrixWitness.wire_values, one
+    separately allocated (pageable) host vector per wire -- gives byte for byte the proof of the matrix form (host and
+    device-resident), with lookup tables and in zero-knowledge mode, and over the multi-device driver."""
+    import torch
+    from qp_plonky2_b200 import prover
+
+    sc = SynthCircuit(degree_bits, seed=610 + degree_bits, poseidon=True, lookups=lookups)
+    c = sc.common
+    circ = plonk.Circuit(ctx, c, sc.sigmas)
+    cfg = prover.FriConfig(c.rate_bits, c.cap_height, 8, 4, 5, 6)
+    pd = prover.ProverData(ctx, circ, sc.constants_sigmas(), cfg)
+    N = (1 << degree_bits) << c.rate_bits
+    salts = [oracle.rand_felts((4, N), 730 + k) for k in range(3)] if zk else None
+    want = prover.prove(pd, sc.wires, sc.public_inputs, salts=salts)
+    cols = [np.array(sc.wires[w], copy=True) for w in range(c.num_wires)]     # one heap vector per wire
+    assert prover.prove(pd, cols, sc.public_inputs, salts=salts) == want
+    w_dev = torch.from_numpy(np.ascontiguousarray(sc.wires).view(np.int64)).cuda()
+    s_dev = [torch.from_numpy(x.view(np.int64)).cuda() for x in salts] if zk else None
+    assert prover.prove(pd, w_dev, sc.public_inputs, salts=s_dev) == want
+    with pytest.raises(ValueError):
+        prover.prove(pd, cols[:-1], sc.public_inputs)
+    if not zk:
+        m = qp.MultiContext([0], max_lde_log=degree_bits + c.rate_bits)
+        try:
+            mpd = prover.MultiProverData(m, c, sc.sigmas, sc.constants_sigmas(), cfg)
+            assert prover.mprove(mpd, cols, sc.public_inputs) == want
+            assert prover.mprove(mpd, sc.wires, sc.public_inputs) == want
+            mpd.constants_sigmas_commitment.free()
+            for x in mpd.circuits:
+                x.free()
+        finally:
+            m.close()
+    circ.free()
+
+
 def test_large_proof_openings_pass_the_verifier(qp, ctx):
     """2^15-row proof on the device (the oracle's quotient would take a minute): parse the opening
     set back out of the proof bytes, re-derive the challenges with the host transcript and run the
