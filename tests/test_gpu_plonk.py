@@ -355,6 +355,37 @@ def test_proof_from_witness_column_vectors(qp, ctx, degree_bits, lookups, zk):
     circ.free()
 
 
+def test_factorial_example_circuit_on_the_device(qp, ctx):
+    """BASELINE.json configs[0] (plonky2/examples/factorial.rs) as a real circuit (tests/factorial_circuit.py: chained
+    multiplications, constants, the in-circuit public-input hash) under standard_recursion_config: the device's proof
+    is the oracle's byte for byte, the restated verifier accepts it with public inputs (1, 100! mod p), and a proof for
+    a wrong claimed result is refused."""
+    import math
+    import verifier
+    from factorial_circuit import factorial_circuit
+    from oracle import prover as oprover
+    from qp_plonky2_b200 import prover
+
+    sc = factorial_circuit()
+    c = sc.common
+    circ = plonk.Circuit(ctx, c, sc.sigmas)
+    pd = prover.ProverData(ctx, circ, sc.constants_sigmas())          # standard_recursion_config
+    got = prover.prove(pd, sc.wires, sc.public_inputs)
+    o_cs = oracle.PolynomialBatch.from_values(sc.constants_sigmas(), c.rate_bits, c.cap_height)
+    want, _ = oprover.prove(sc.oracle_circuit, o_cs, c.num_constants, sc.wires, sc.sigmas, sc.public_inputs,
+                            degree_bits=c.degree_bits, num_wires=c.num_wires, num_routed_wires=c.num_routed_wires,
+                            num_challenges=c.num_challenges, quotient_degree_factor=c.quotient_degree_factor,
+                            num_partial_products=c.num_partial_products)
+    assert got == want
+    assert prover.prove(pd, [np.array(sc.wires[w], copy=True) for w in range(c.num_wires)], sc.public_inputs) == want
+    cap = pd.constants_sigmas_commitment.merkle_tree.cap
+    assert verifier.verify(got, c, pd.fri, cap, pd.circuit_digest) is None
+    assert [int(x) for x in np.frombuffer(got[-16:], dtype="<u8")] == [1, math.factorial(100) % P]
+    forged = prover.prove(pd, sc.wires, [1, (sc.public_inputs[1] + 1) % P])
+    assert verifier.verify(forged, c, pd.fri, cap, pd.circuit_digest) is not None
+    circ.free()
+
+
 def test_large_proof_openings_pass_the_verifier(qp, ctx):
     """2^15-row proof on the device (the oracle's quotient would take a minute): parse the opening
     set back out of the proof bytes, re-derive the challenges with the host transcript and run the

@@ -505,3 +505,46 @@ def test_restated_verifier_accepts_oracle_proofs_with_lookups(degree_bits, posei
     finally:
         sc.wires = good_wires
     assert verifier.verify(forged, c, fri, cs.cap, digest) == "vanishing(zeta) != Z_H(zeta) * quotient(zeta)"
+
+
+def test_factorial_example_circuit_proves_and_verifies():
+    """BASELINE.json configs[0], `cargo run --example factorial` (plonky2/examples/factorial.rs): a REAL circuit --
+    99 chained multiplications, constants, the in-circuit public-input hash tied to the PublicInputGate -- under
+    standard_recursion_config.  The oracle's proof of "1 * 2 * ... * 100 = 100! mod p" passes the restated verifier;
+    a wrong claimed result, a broken multiplication and a broken copy constraint do not."""
+    import math
+
+    from factorial_circuit import factorial_circuit
+    from oracle import prover as oprover
+    import verifier
+
+    sc = factorial_circuit()
+    c = sc.common
+    assert sc.public_inputs == [1, math.factorial(100) % P]
+    cs = oracle.PolynomialBatch.from_values(sc.constants_sigmas(), c.rate_bits, c.cap_height)
+    fri = _Fri(c.rate_bits, c.cap_height, 16, 4, 5, 28)
+    digest = oprover.circuit_digest(cs.cap, c.degree_bits)
+    proof, _ = _oracle_prove(sc)
+    assert verifier.verify(proof, c, fri, cs.cap, digest) is None
+    tail = np.frombuffer(proof[-24:], dtype="<u8")
+    assert [int(x) for x in tail] == [2, 1, math.factorial(100) % P]
+    good_pi, good_wires = list(sc.public_inputs), sc.wires
+    try:
+        sc.public_inputs = [1, (good_pi[1] + 1) % P]                 # claim another result: the PI hash no longer matches
+        bad, _ = _oracle_prove(sc)
+        assert verifier.verify(bad, c, fri, cs.cap, digest) is not None
+        sc.public_inputs = good_pi
+        w = good_wires.copy()
+        arith_row = int(np.nonzero(sc.row_gate == [g.id().startswith("ArithmeticGate") for g in c.gates].index(True))[0][0])
+        w[3, arith_row] = (int(w[3, arith_row]) + 1) % P             # first product wrong: gate constraint AND its copies fail
+        sc.wires = w
+        bad, _ = _oracle_prove(sc)
+        assert verifier.verify(bad, c, fri, cs.cap, digest) is not None
+        w = good_wires.copy()
+        w[4, arith_row] = (int(w[4, arith_row]) + 1) % P             # second multiplicand != first product: only the copy
+        w[7, arith_row] = int(w[4, arith_row]) * int(w[5, arith_row]) % P   # constraint breaks (the gate itself holds)
+        sc.wires = w
+        bad, _ = _oracle_prove(sc)
+        assert verifier.verify(bad, c, fri, cs.cap, digest) is not None
+    finally:
+        sc.public_inputs, sc.wires = good_pi, good_wires
