@@ -705,6 +705,10 @@ def run_ours(args):
                                                               verbose=False, recursion=True, lookups=True)}
         except Exception as e:  # the headline metric does not depend on it
             prove = {"error": repr(e)}
+        try:   # BASELINE.json configs[0]: the factorial example as a real circuit
+            prove["factorial_example"] = bench_prove.measure_factorial(cpu=not args.no_cpu, device=local)
+        except Exception as e:
+            prove["factorial_example"] = {"error": repr(e)}
 
     line = {
         "metric": METRIC, "value": dev_ms, "unit": "ms", "n_gpus": world, "steps": args.steps,

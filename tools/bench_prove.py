@@ -83,6 +83,44 @@ def measure(degrees, cpu_degrees=(), reps=5, device=0, verbose=True, poseidon=Tr
     return out["prove"]
 
 
+def measure_factorial(cpu=True, reps=5, device=0):
+    """BASELINE.json configs[0]: the `factorial` example (plonky2/examples/factorial.rs) as a real circuit
+    (tests/factorial_circuit.py), standard_recursion_config -- proof latency on the device from the host witness, the
+    oracle's CPU prove() beside it, equal bytes."""
+    from factorial_circuit import factorial_circuit
+
+    sc = factorial_circuit()
+    c = sc.common
+    ctx = qp.Context(device, max_lde_log=c.degree_bits + 3)
+    circ = plonk.Circuit(ctx, c, sc.sigmas)
+    pd = prover.ProverData(ctx, circ, sc.constants_sigmas())
+    best, proof = None, None
+    for rep in range(reps):
+        t0 = time.perf_counter()
+        proof = prover.prove(pd, sc.wires, sc.public_inputs)
+        ms = (time.perf_counter() - t0) * 1e3
+        if rep and (best is None or ms < best):
+            best = ms
+    rec = {"what": "factorial example: 99 chained multiplications, in-circuit public-input hash; host witness",
+           "degree_bits": c.degree_bits, "public_inputs": [int(x) for x in sc.public_inputs], "ms": best,
+           "proof_bytes": len(proof)}
+    if cpu:
+        import oracle
+        from oracle import prover as oprover
+        o_cs = oracle.PolynomialBatch.from_values(sc.constants_sigmas(), c.rate_bits, c.cap_height)
+        t0 = time.perf_counter()
+        want, _ = oprover.prove(sc.oracle_circuit, o_cs, c.num_constants, sc.wires, sc.sigmas, sc.public_inputs,
+                                degree_bits=c.degree_bits, num_wires=c.num_wires, num_routed_wires=c.num_routed_wires,
+                                num_challenges=c.num_challenges, quotient_degree_factor=c.quotient_degree_factor,
+                                num_partial_products=c.num_partial_products)
+        rec["cpu_oracle_ms"] = (time.perf_counter() - t0) * 1e3
+        rec["cpu_threads"] = oracle.lib().orc_num_threads()
+        rec["bytes_equal_cpu"] = want == proof
+    circ.free()
+    ctx.close()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--degrees", type=int, nargs="*", default=[12, 13, 14, 16])
